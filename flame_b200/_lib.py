@@ -1,0 +1,320 @@
+"""ctypes loader for libflame_b200.so (the C ABI declared in include/flame_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no sm_100 device is visible when a
+context is created, this module raises — it never routes to the oracle or to numpy.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libflame_b200.so")
+
+f32p = C.POINTER(C.c_float)
+i32p = C.POINTER(C.c_int32)
+u8p = C.POINTER(C.c_uint8)
+
+
+class FlameB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("flame_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class PDParams(C.Structure):
+    """nltgv2_l1_graph_regularizer::Params (nltgv2_l1_graph_regularizer.h:121-129)."""
+    _fields_ = [("data_factor", C.c_float), ("step_x", C.c_float), ("step_q", C.c_float),
+                ("theta", C.c_float), ("x_min", C.c_float), ("x_max", C.c_float)]
+
+
+class GraphIn(C.Structure):
+    _fields_ = [("V", C.c_int32), ("E", C.c_int32), ("pos", f32p), ("edges", i32p),
+                ("data_term", f32p), ("data_weight", f32p),
+                ("x", f32p), ("w1", f32p), ("w2", f32p),
+                ("x_bar", f32p), ("w1_bar", f32p), ("w2_bar", f32p),
+                ("x_prev", f32p), ("w1_prev", f32p), ("w2_prev", f32p),
+                ("alpha", f32p), ("beta", f32p), ("q1", f32p), ("q2", f32p), ("q3", f32p)]
+
+
+class GraphOut(C.Structure):
+    _fields_ = [(k, f32p) for k in ("x", "w1", "w2", "x_bar", "w1_bar", "w2_bar", "x_prev",
+                                    "w1_prev", "w2_prev", "alpha", "beta", "q1", "q2", "q3")]
+
+
+class LSParams(C.Structure):
+    _fields_ = [("max_cost", C.c_float), ("do_subpixel", C.c_int32), ("sample_dist", C.c_float),
+                ("second_best_factor", C.c_float)]
+
+
+class FilterParams(C.Structure):
+    _fields_ = [("win_size", C.c_int32), ("search_sigma", C.c_float), ("min_grad_mag", C.c_float),
+                ("idepth_min", C.c_float), ("idepth_max", C.c_float),
+                ("epilength_min", C.c_float), ("epilength_max", C.c_float),
+                ("process_var_factor", C.c_float), ("process_fail_var_factor", C.c_float),
+                ("sparams", LSParams)]
+
+
+class MeasParams(C.Structure):
+    _fields_ = [("win_size", C.c_int32), ("pixel_var", C.c_float), ("epipolar_line_var", C.c_float)]
+
+
+class TrackParams(C.Structure):
+    _fields_ = [("fparams", FilterParams), ("zparams", MeasParams), ("min_baseline", C.c_float),
+                ("rescale_factor_min", C.c_float), ("rescale_factor_max", C.c_float),
+                ("idepth_var_max", C.c_float), ("max_dropouts", C.c_int32),
+                ("outlier_sigma_thresh", C.c_float), ("do_meas_fusion", C.c_int32),
+                ("do_letterbox", C.c_int32)]
+
+
+FEATURE_DTYPE = np.dtype([("id", "<u4"), ("frame_id", "<u4"), ("x", "<f4"), ("y", "<f4"),
+                          ("idepth_mu", "<f4"), ("idepth_var", "<f4"), ("valid", "<i4"),
+                          ("num_updates", "<u4"), ("num_dropouts", "<u4"), ("search_status", "<i4")])
+DIAG_DTYPE = np.dtype([("flow_x", "<f4"), ("flow_y", "<f4"), ("mu_meas", "<f4"),
+                       ("var_meas", "<f4"), ("stage", "<i4")])
+
+PD_AUTO, PD_STREAM, PD_RESIDENT = 0, 1, 2
+
+_lib = None
+
+# every symbol include/flame_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "flame_b200_last_error", "flame_b200_version", "flame_b200_kernel_launches",
+    "flame_b200_ctx_create", "flame_b200_ctx_destroy", "flame_b200_ctx_sync", "flame_b200_ctx_stream",
+    "flame_b200_host_alloc", "flame_b200_host_free",
+    "flame_b200_pd_default_params", "flame_b200_graph_upload", "flame_b200_graph_init",
+    "flame_b200_graph_set_data", "flame_b200_graph_reset", "flame_b200_graph_download", "flame_b200_pd_run",
+    "flame_b200_pd_cost", "flame_b200_interpolate_mesh", "flame_b200_mesh_bind",
+    "flame_b200_mesh_project", "flame_b200_mesh_download", "flame_b200_track_default_params",
+    "flame_b200_set_camera", "flame_b200_frame_upload", "flame_b200_update_feature_idepths",
+]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FlameB200Error(-2, "%s not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                                 "flame_b200 has no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.flame_b200_last_error.restype = C.c_char_p
+    L.flame_b200_kernel_launches.restype = C.c_uint64
+    L.flame_b200_ctx_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+    L.flame_b200_ctx_destroy.argtypes = [vp]
+    L.flame_b200_ctx_destroy.restype = None
+    L.flame_b200_ctx_sync.argtypes = [vp]
+    L.flame_b200_ctx_stream.argtypes = [vp]
+    L.flame_b200_ctx_stream.restype = vp
+    L.flame_b200_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.flame_b200_host_free.argtypes = [vp]
+    L.flame_b200_pd_default_params.argtypes = [C.POINTER(PDParams)]
+    L.flame_b200_pd_default_params.restype = None
+    L.flame_b200_graph_upload.argtypes = [vp, C.c_int, C.POINTER(GraphIn)]
+    L.flame_b200_graph_init.argtypes = [vp, C.c_int, C.c_int32, f32p, f32p, f32p, C.c_int32, i32p]
+    L.flame_b200_graph_set_data.argtypes = [vp, C.c_int, f32p, f32p]
+    L.flame_b200_graph_reset.argtypes = [vp, C.c_int, C.c_int]
+    L.flame_b200_graph_download.argtypes = [vp, C.c_int, C.POINTER(GraphOut)]
+    L.flame_b200_pd_run.argtypes = [vp, C.c_int, C.c_int, C.POINTER(PDParams), C.c_int, C.c_int]
+    L.flame_b200_pd_cost.argtypes = [vp, C.c_int, C.POINTER(PDParams), C.c_int, f32p, f32p]
+    L.flame_b200_interpolate_mesh.argtypes = [vp, C.c_int, C.c_int32, i32p, C.c_int32, f32p, f32p,
+                                              C.c_float, u8p, u8p, C.c_int, C.c_int, C.c_int, f32p]
+    L.flame_b200_mesh_bind.argtypes = [vp, C.c_int, C.c_int32, i32p, u8p, u8p, C.c_int, C.c_int]
+    L.flame_b200_mesh_project.argtypes = [vp, C.c_int, C.c_int, C.c_float]
+    L.flame_b200_mesh_download.argtypes = [vp, C.c_int, vp]
+    L.flame_b200_track_default_params.argtypes = [C.POINTER(TrackParams)]
+    L.flame_b200_track_default_params.restype = None
+    L.flame_b200_set_camera.argtypes = [vp, C.c_int, C.c_int, f32p, f32p]
+    L.flame_b200_frame_upload.argtypes = [vp, C.c_int, u8p, f32p, f32p, C.c_int, f32p]
+    L.flame_b200_update_feature_idepths.argtypes = [vp, C.POINTER(TrackParams), C.c_int, C.c_int, vp,
+                                                    C.c_int32, vp, C.POINTER(C.c_int32)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise FlameB200Error(rc, lib().flame_b200_last_error().decode("utf-8", "replace"))
+
+
+def fptr(a):
+    if a is None:
+        return None
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"], "need contiguous float32"
+    return a.ctypes.data_as(f32p)
+
+
+def iptr(a):
+    if a is None:
+        return None
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"], "need contiguous int32"
+    return a.ctypes.data_as(i32p)
+
+
+def bptr(a):
+    if a is None:
+        return None
+    assert a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"], "need contiguous uint8"
+    return a.ctypes.data_as(u8p)
+
+
+def default_pd_params():
+    p = PDParams()
+    lib().flame_b200_pd_default_params(C.byref(p))
+    return p
+
+
+def default_track_params():
+    p = TrackParams()
+    lib().flame_b200_track_default_params(C.byref(p))
+    return p
+
+
+def kernel_launches():
+    return int(lib().flame_b200_kernel_launches())
+
+
+class PinnedArray:
+    """A numpy view over page-locked host memory from flame_b200_host_alloc."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._p = C.c_void_p()
+        check(lib().flame_b200_host_alloc(self.nbytes, C.byref(self._p)))
+        buf = (C.c_uint8 * self.nbytes).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib().flame_b200_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One CUDA stream + n_slots frame slots (flame_b200_ctx)."""
+
+    def __init__(self, device=0, n_slots=1):
+        self._h = C.c_void_p()
+        check(lib().flame_b200_ctx_create(device, n_slots, C.byref(self._h)))
+        self.device = device
+        self.n_slots = n_slots
+
+    def close(self):
+        if self._h:
+            lib().flame_b200_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def stream(self):
+        return lib().flame_b200_ctx_stream(self._h)
+
+    def sync(self):
+        check(lib().flame_b200_ctx_sync(self._h))
+
+    # ---- graph ----
+    def graph_upload(self, slot, g):
+        """g: dict of contiguous numpy arrays named as flame_b200_graph_in's fields."""
+        s = GraphIn()
+        s.V = g["pos"].shape[0]
+        s.E = g["edges"].shape[0]
+        s.pos = fptr(g["pos"])
+        s.edges = iptr(g["edges"])
+        for k in ("data_term", "data_weight", "x", "w1", "w2", "x_bar", "w1_bar", "w2_bar", "x_prev",
+                  "w1_prev", "w2_prev", "alpha", "beta", "q1", "q2", "q3"):
+            setattr(s, k, fptr(g.get(k)))
+        check(lib().flame_b200_graph_upload(self._h, slot, C.byref(s)))
+
+    def graph_init(self, slot, pos, idepth, edges, weight=None):
+        check(lib().flame_b200_graph_init(self._h, slot, pos.shape[0], fptr(pos), fptr(idepth),
+                                          fptr(weight), edges.shape[0], iptr(edges)))
+
+    def graph_set_data(self, slot, data_term=None, data_weight=None):
+        check(lib().flame_b200_graph_set_data(self._h, slot, fptr(data_term), fptr(data_weight)))
+
+    def graph_reset(self, slot0=0, n_slots=1):
+        check(lib().flame_b200_graph_reset(self._h, slot0, n_slots))
+
+    def graph_download(self, slot, V, E, fields=None):
+        names = ("x", "w1", "w2", "x_bar", "w1_bar", "w2_bar", "x_prev", "w1_prev", "w2_prev",
+                 "alpha", "beta", "q1", "q2", "q3")
+        fields = names if fields is None else fields
+        out = {}
+        o = GraphOut()
+        for k in fields:
+            n = E if k in ("alpha", "beta", "q1", "q2", "q3") else V
+            out[k] = np.empty(n, np.float32)
+            setattr(o, k, fptr(out[k]))
+        check(lib().flame_b200_graph_download(self._h, slot, C.byref(o)))
+        return out
+
+    def pd_run(self, params, n_iters, slot0=0, n_slots=1, mode=PD_AUTO):
+        check(lib().flame_b200_pd_run(self._h, slot0, n_slots, C.byref(params), n_iters, mode))
+
+    def pd_cost(self, slot, params, exact_order=False):
+        a, b = C.c_float(), C.c_float()
+        check(lib().flame_b200_pd_cost(self._h, slot, C.byref(params), int(exact_order), C.byref(a),
+                                       C.byref(b)))
+        return a.value, b.value
+
+    # ---- dense projection ----
+    def interpolate_mesh(self, slot, tris, pos, values, rows, cols, vtx_valid=None, tri_valid=None,
+                         img=None, scale=1.0):
+        fill = img is None
+        if img is None:
+            img = np.empty((rows, cols), np.float32)
+        check(lib().flame_b200_interpolate_mesh(self._h, slot, tris.shape[0], iptr(tris), pos.shape[0],
+                                                fptr(pos), fptr(values), scale, bptr(vtx_valid),
+                                                bptr(tri_valid), rows, cols, int(fill), fptr(img)))
+        return img
+
+    def mesh_bind(self, slot, tris, rows, cols, vtx_valid=None, tri_valid=None):
+        check(lib().flame_b200_mesh_bind(self._h, slot, tris.shape[0], iptr(tris), bptr(vtx_valid),
+                                         bptr(tri_valid), rows, cols))
+
+    def mesh_project(self, slot0=0, n_slots=1, scale=1.0):
+        check(lib().flame_b200_mesh_project(self._h, slot0, n_slots, scale))
+
+    def mesh_download(self, slot, out):
+        """Asynchronous; out: numpy array (ideally PinnedArray.array). Complete after sync()."""
+        check(lib().flame_b200_mesh_download(self._h, slot, out.ctypes.data_as(C.c_void_p)))
+
+    # ---- epipolar search ----
+    def set_camera(self, width, height, K, Kinv):
+        K = np.ascontiguousarray(K, np.float32).ravel()
+        Kinv = np.ascontiguousarray(Kinv, np.float32).ravel()
+        check(lib().flame_b200_set_camera(self._h, width, height, fptr(K), fptr(Kinv)))
+
+    def frame_upload(self, fslot, img_pad, gradx_pad, grady_pad, pad, pose):
+        pose = np.ascontiguousarray(pose, np.float32)
+        check(lib().flame_b200_frame_upload(self._h, fslot, bptr(np.ascontiguousarray(img_pad)),
+                                            fptr(np.ascontiguousarray(gradx_pad)),
+                                            fptr(np.ascontiguousarray(grady_pad)), pad, fptr(pose)))
+
+    def update_feature_idepths(self, params, fnew, curr_pf, feats, want_diag=True):
+        assert feats.dtype == FEATURE_DTYPE and feats.flags["C_CONTIGUOUS"]
+        diag = np.zeros(feats.shape[0], DIAG_DTYPE) if want_diag else None
+        n = C.c_int32()
+        check(lib().flame_b200_update_feature_idepths(
+            self._h, C.byref(params), fnew, curr_pf, feats.ctypes.data_as(C.c_void_p), feats.shape[0],
+            diag.ctypes.data_as(C.c_void_p) if want_diag else None, C.byref(n)))
+        return n.value, diag

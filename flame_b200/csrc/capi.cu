@@ -1,0 +1,782 @@
+// C ABI + host runtime of libflame_b200.so (context, slots, staging, host-side graph prep).
+// The compute is in pd.cu / raster.cu / stereo.cu; nothing here falls back to the CPU.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+
+#include "internal.h"
+
+namespace fb {
+
+static thread_local std::string t_last_error;
+void set_error(const std::string& msg) { t_last_error = msg; }
+std::atomic<uint64_t> g_kernel_launches{0};
+
+int stereo_set_camera(void** state, int width, int height, const float K[9], const float Kinv[9]);
+int stereo_frame_upload(void** state, cudaStream_t st, int fslot, const uint8_t* img_pad,
+                        const float* gradx_pad, const float* grady_pad, int pad, const float pose[7]);
+int stereo_update(void* state, cudaStream_t st, const flame_b200_track_params* params, int fnew,
+                  int curr_pf, flame_b200_feature* feats, int32_t n_feats,
+                  flame_b200_track_diag* diag, int32_t* n_updates);
+void stereo_destroy(void* state);
+
+// ------------------------------------------------------------------------------------------
+struct Slot {
+  GraphDev g{};
+  bool loaded = false;
+  // one device blob: [raw floats (13V + 5E) | ints: vperm V | eperm E | ends 2E | inc_off V+1 |
+  //                   inc 2E | esrc_off V+1], mirrored by one pinned host blob -> single H2D.
+  unsigned char* d_blob = nullptr;
+  size_t d_blob_cap = 0;
+  unsigned char* h_blob = nullptr;
+  size_t h_blob_cap = 0;
+  cudaEvent_t blob_free = nullptr;  // recorded after the last async op that reads/writes h_blob
+  int capV = 0, capE = 0;
+  float* d_pos = nullptr;           // 2V caller order (kept for the dense projection)
+  float* d_values = nullptr;        // V caller order
+  std::vector<int> h_esrc_off, h_inc_off;  // host copies for resident planning
+  // mesh
+  MeshDev m{};
+  int capT = 0;
+  size_t cap_pix = 0;
+  float* d_mpos = nullptr;          // interpolate_mesh(): caller-supplied pos / values
+  float* d_mvalues = nullptr;
+  int capMV = 0;
+  float* d_raw() const { return reinterpret_cast<float*>(d_blob); }
+};
+
+}  // namespace fb
+
+struct flame_b200_ctx {
+  int device = 0;
+  int n_slots = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<fb::Slot> slots;
+  fb::GraphDev* d_graphs = nullptr;  // n_slots entries, mirrors slots[i].g
+  fb::GraphDev* h_graphs = nullptr;  // pinned
+  double* d_cost = nullptr;
+  double* h_cost = nullptr;          // pinned, 2 doubles
+  void* stereo = nullptr;
+  // host scratch for graph prep
+  std::vector<uint32_t> keys, keys2;
+  std::vector<int> idx, idx2, vinv, einv, cursor;
+};
+
+namespace fb {
+
+template <typename T>
+static int grow(T** p, size_t* cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*p) FB_CUDA(cudaFree(*p));
+  *p = nullptr;
+  size_t n = std::max(need, *cap + *cap / 2);
+  FB_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  *cap = n;
+  return 0;
+}
+
+static inline uint32_t part1by1(uint32_t x) {
+  x &= 0x0000ffffu;
+  x = (x ^ (x << 8)) & 0x00ff00ffu;
+  x = (x ^ (x << 4)) & 0x0f0f0f0fu;
+  x = (x ^ (x << 2)) & 0x33333333u;
+  x = (x ^ (x << 1)) & 0x55555555u;
+  return x;
+}
+
+static size_t ints_total(int V, int E) { return (size_t)2 * V + 2 + (size_t)5 * E; }
+static size_t blob_bytes(int V, int E) {
+  return (raw_f_total(V, E) + ints_total(V, E)) * 4 + 64;
+}
+
+// Spatial (Morton) vertex order, edges grouped by internal source vertex, per-vertex incidence
+// lists in ascending ORIGINAL edge id. O(V + E), deterministic.
+static int host_prep(flame_b200_ctx* c, int V, int E, const float* pos, const int32_t* edges,
+                     int* vperm, int* eperm, int* ends, int* inc_off, int* inc, int* esrc_off) {
+  for (int e = 0; e < 2 * E; ++e)
+    if (edges[e] < 0 || edges[e] >= V) {
+      set_error("graph_upload: edge endpoint out of range");
+      return FLAME_B200_EINVAL;
+    }
+  // 1. Morton keys on the bounding box
+  float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+  for (int v = 0; v < V; ++v) {
+    xmin = std::min(xmin, pos[2 * v]);
+    xmax = std::max(xmax, pos[2 * v]);
+    ymin = std::min(ymin, pos[2 * v + 1]);
+    ymax = std::max(ymax, pos[2 * v + 1]);
+  }
+  const float span = std::max(std::max(xmax - xmin, ymax - ymin), 1e-6f);
+  const float sc = 65535.0f / span;
+  c->keys.resize(V);
+  c->keys2.resize(V);
+  c->idx.resize(V);
+  c->idx2.resize(V);
+  for (int v = 0; v < V; ++v) {
+    float fx = (pos[2 * v] - xmin) * sc, fy = (pos[2 * v + 1] - ymin) * sc;
+    uint32_t qx = (fx >= 0 && fx <= 65535.0f) ? (uint32_t)fx : 0u;  // NaN-safe
+    uint32_t qy = (fy >= 0 && fy <= 65535.0f) ? (uint32_t)fy : 0u;
+    c->keys[v] = part1by1(qx) | (part1by1(qy) << 1);
+    c->idx[v] = v;
+  }
+  // LSD radix sort, 4 x 8 bits, stable
+  uint32_t* ka = c->keys.data();
+  uint32_t* kb = c->keys2.data();
+  int* ia = c->idx.data();
+  int* ib = c->idx2.data();
+  for (int pass = 0; pass < 4; ++pass) {
+    size_t cnt[257] = {0};
+    const int sh = 8 * pass;
+    for (int v = 0; v < V; ++v) cnt[((ka[v] >> sh) & 255u) + 1]++;
+    for (int b = 0; b < 256; ++b) cnt[b + 1] += cnt[b];
+    for (int v = 0; v < V; ++v) {
+      const size_t d = cnt[(ka[v] >> sh) & 255u]++;
+      kb[d] = ka[v];
+      ib[d] = ia[v];
+    }
+    std::swap(ka, kb);
+    std::swap(ia, ib);
+  }
+  c->vinv.resize(V);
+  for (int i = 0; i < V; ++i) {
+    vperm[i] = ia[i];
+    c->vinv[ia[i]] = i;
+  }
+  // 2. edges grouped by internal source (stable in original id)
+  for (int v = 0; v <= V; ++v) esrc_off[v] = 0;
+  for (int o = 0; o < E; ++o) esrc_off[c->vinv[edges[2 * o]] + 1]++;
+  for (int v = 0; v < V; ++v) esrc_off[v + 1] += esrc_off[v];
+  c->cursor.assign(esrc_off, esrc_off + V);
+  c->einv.resize(E);
+  for (int o = 0; o < E; ++o) {
+    const int s = c->vinv[edges[2 * o]], d = c->vinv[edges[2 * o + 1]];
+    const int p = c->cursor[s]++;
+    eperm[p] = o;
+    ends[2 * p] = s;
+    ends[2 * p + 1] = d;
+    c->einv[o] = p;
+  }
+  // 3. incidence lists, ascending original edge id
+  for (int v = 0; v <= V; ++v) inc_off[v] = 0;
+  for (int o = 0; o < E; ++o) {
+    inc_off[c->vinv[edges[2 * o]] + 1]++;
+    inc_off[c->vinv[edges[2 * o + 1]] + 1]++;
+  }
+  for (int v = 0; v < V; ++v) inc_off[v + 1] += inc_off[v];
+  c->cursor.assign(inc_off, inc_off + V);
+  for (int o = 0; o < E; ++o) {
+    const int s = c->vinv[edges[2 * o]], d = c->vinv[edges[2 * o + 1]];
+    inc[c->cursor[s]++] = (c->einv[o] << 1);
+    inc[c->cursor[d]++] = (c->einv[o] << 1) | 1;
+  }
+  return 0;
+}
+
+static int check_slot(flame_b200_ctx* c, int slot, int n = 1) {
+  if (!c) {
+    set_error("null context");
+    return FLAME_B200_EINVAL;
+  }
+  if (slot < 0 || n < 1 || slot + n > c->n_slots) {
+    set_error("slot range out of bounds");
+    return FLAME_B200_EINVAL;
+  }
+  return 0;
+}
+
+static int use_device(flame_b200_ctx* c) {
+  FB_CUDA(cudaSetDevice(c->device));
+  return 0;
+}
+
+static int wait_blob(Slot& s) {
+  if (s.blob_free) FB_CUDA(cudaEventSynchronize(s.blob_free));
+  return 0;
+}
+
+static int ensure_blob(Slot& s, int V, int E) {
+  const size_t need = blob_bytes(V, E);
+  if (need > s.d_blob_cap) {
+    if (s.d_blob) FB_CUDA(cudaFree(s.d_blob));
+    s.d_blob = nullptr;
+    const size_t n = std::max(need, s.d_blob_cap + s.d_blob_cap / 2);
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_blob), n));
+    s.d_blob_cap = n;
+  }
+  if (need > s.h_blob_cap) {
+    if (s.h_blob) FB_CUDA(cudaFreeHost(s.h_blob));
+    s.h_blob = nullptr;
+    const size_t n = std::max(need, s.h_blob_cap + s.h_blob_cap / 2);
+    FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s.h_blob), n));
+    s.h_blob_cap = n;
+  }
+  if (!s.blob_free) FB_CUDA(cudaEventCreateWithFlags(&s.blob_free, cudaEventDisableTiming));
+  return 0;
+}
+
+static int ensure_graph(Slot& s, int V, int E) {
+  if (V > s.capV) {
+    const int n = std::max(V, s.capV + s.capV / 2);
+    for (void* p : {(void*)s.g.vprim, (void*)s.g.vbar, (void*)s.g.vprev, (void*)s.g.vwt,
+                    (void*)s.d_pos, (void*)s.d_values})
+      if (p) FB_CUDA(cudaFree(p));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.vprim), (size_t)n * sizeof(float4)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.vbar), (size_t)n * sizeof(float4)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.vprev), (size_t)n * sizeof(float4)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.vwt), (size_t)n * sizeof(float)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_pos), (size_t)n * 2 * sizeof(float)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_values), (size_t)n * sizeof(float)));
+    s.capV = n;
+  }
+  if (E > s.capE) {
+    const int n = std::max(E, s.capE + s.capE / 2);
+    if (s.g.erec) FB_CUDA(cudaFree(s.g.erec));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.erec), (size_t)n * sizeof(EdgeRec)));
+    s.capE = n;
+  }
+  return 0;
+}
+
+static void fill_or_copy(float* dst, const float* src, size_t n, float fill) {
+  if (src) std::memcpy(dst, src, n * sizeof(float));
+  else std::fill(dst, dst + n, fill);
+}
+
+static int publish_graph(flame_b200_ctx* c, int slot) {
+  c->h_graphs[slot] = c->slots[slot].g;
+  FB_CUDA(cudaMemcpyAsync(c->d_graphs + slot, c->h_graphs + slot, sizeof(GraphDev),
+                          cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+extern "C" {
+
+const char* flame_b200_last_error(void) { return t_last_error.c_str(); }
+int flame_b200_version(void) { return FLAME_B200_VERSION; }
+uint64_t flame_b200_kernel_launches(void) { return g_kernel_launches.load(); }
+
+void flame_b200_pd_default_params(flame_b200_pd_params* p) {
+  // nltgv2_l1_graph_regularizer.h:121-129
+  p->data_factor = 0.1f;
+  p->step_x = 0.001f;
+  p->step_q = 125.0f;
+  p->theta = 0.25f;
+  p->x_min = 0.0f;
+  p->x_max = 10.0f;
+}
+
+void flame_b200_track_default_params(flame_b200_track_params* p) {
+  // inverse_depth_filter.h:48-68, line_stereo.h:47-59, inverse_depth_meas_model.h:44-52, params.h:58-67
+  p->fparams.win_size = 5;
+  p->fparams.search_sigma = 2.0f;
+  p->fparams.min_grad_mag = 5.0f;
+  p->fparams.idepth_min = 1e-3f;
+  p->fparams.idepth_max = 2.0f;
+  p->fparams.epilength_min = 3.0f;
+  p->fparams.epilength_max = 32.0f;
+  p->fparams.process_var_factor = 1.01f;
+  p->fparams.process_fail_var_factor = 1.1f;
+  p->fparams.sparams.max_cost = 1300.0f;
+  p->fparams.sparams.do_subpixel = 1;
+  p->fparams.sparams.sample_dist = 1.0f;
+  p->fparams.sparams.second_best_factor = 1.5f;
+  p->zparams.win_size = 5;
+  p->zparams.pixel_var = 16.0f;
+  p->zparams.epipolar_line_var = 1.0f;
+  p->min_baseline = 0.01f;
+  p->rescale_factor_min = 0.7f;
+  p->rescale_factor_max = 1.4f;
+  p->idepth_var_max = 0.5f * 0.5f;
+  p->max_dropouts = 5;
+  p->outlier_sigma_thresh = 3.0f;
+  p->do_meas_fusion = 1;
+  p->do_letterbox = 0;
+}
+
+int flame_b200_ctx_create(int device, int n_slots, flame_b200_ctx** out) {
+  if (!out || n_slots < 1) {
+    set_error("ctx_create: bad arguments");
+    return FLAME_B200_EINVAL;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error(std::string("no CUDA device: ") + cudaGetErrorString(e) +
+              " (libflame_b200 has no CPU fallback)");
+    return FLAME_B200_ENODEV;
+  }
+  if (device < 0 || device >= ndev) {
+    set_error("ctx_create: device ordinal out of range");
+    return FLAME_B200_EINVAL;
+  }
+  cudaDeviceProp prop;
+  FB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error(std::string("device ") + prop.name + " is not sm_100: kernels are built for sm_100a only");
+    return FLAME_B200_ENODEV;
+  }
+  FB_CUDA(cudaSetDevice(device));
+  std::unique_ptr<flame_b200_ctx> c(new flame_b200_ctx());
+  c->device = device;
+  c->n_slots = n_slots;
+  c->slots.resize(n_slots);
+  FB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_graphs), sizeof(GraphDev) * n_slots));
+  FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_graphs), sizeof(GraphDev) * n_slots));
+  FB_CUDA(cudaMemset(c->d_graphs, 0, sizeof(GraphDev) * n_slots));
+  std::memset(c->h_graphs, 0, sizeof(GraphDev) * n_slots);
+  FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_cost), 2 * sizeof(double)));
+  FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_cost), 2 * sizeof(double)));
+  if (int rc = pd_resident_init()) return rc;
+  *out = c.release();
+  return 0;
+}
+
+void flame_b200_ctx_destroy(flame_b200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& s : c->slots) {
+    for (void* p : {(void*)s.g.vprim, (void*)s.g.vbar, (void*)s.g.vprev, (void*)s.g.vwt,
+                    (void*)s.g.erec, (void*)s.d_blob, (void*)s.d_pos, (void*)s.d_values,
+                    (void*)s.m.tris, (void*)s.m.tri_ok, (void*)s.m.img, (void*)s.m.win,
+                    (void*)s.d_mpos, (void*)s.d_mvalues})
+      if (p) cudaFree(p);
+    if (s.h_blob) cudaFreeHost(s.h_blob);
+    if (s.blob_free) cudaEventDestroy(s.blob_free);
+  }
+  stereo_destroy(c->stereo);
+  cudaFree(c->d_graphs);
+  cudaFreeHost(c->h_graphs);
+  cudaFree(c->d_cost);
+  cudaFreeHost(c->h_cost);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int flame_b200_ctx_sync(flame_b200_ctx* c) {
+  if (!c) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  FB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+void* flame_b200_ctx_stream(flame_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int flame_b200_host_alloc(size_t bytes, void** out) {
+  if (!out) return FLAME_B200_EINVAL;
+  FB_CUDA(cudaMallocHost(out, bytes));
+  return 0;
+}
+int flame_b200_host_free(void* p) {
+  if (p) FB_CUDA(cudaFreeHost(p));
+  return 0;
+}
+
+int flame_b200_graph_upload(flame_b200_ctx* c, int slot, const flame_b200_graph_in* g) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (!g || g->V < 0 || g->E < 0 || (g->V > 0 && (!g->pos || !g->data_term || !g->x)) ||
+      (g->E > 0 && !g->edges)) {
+    set_error("graph_upload: missing required array");
+    return FLAME_B200_EINVAL;
+  }
+  if (int rc = use_device(c)) return rc;
+  Slot& s = c->slots[slot];
+  const int V = g->V, E = g->E;
+  if (int rc = wait_blob(s)) return rc;
+  if (int rc = ensure_blob(s, V, E)) return rc;
+  if (int rc = ensure_graph(s, V, E)) return rc;
+
+  float* hf = reinterpret_cast<float*>(s.h_blob);
+  int* hi = reinterpret_cast<int*>(hf + raw_f_total(V, E));
+  int* h_vperm = hi;
+  int* h_eperm = h_vperm + V;
+  int* h_ends = h_eperm + E;
+  int* h_inc_off = h_ends + 2 * (size_t)E;
+  int* h_inc = h_inc_off + V + 1;
+  int* h_esrc_off = h_inc + 2 * (size_t)E;
+  if (int rc = host_prep(c, V, E, g->pos, g->edges, h_vperm, h_eperm, h_ends, h_inc_off, h_inc,
+                         h_esrc_off))
+    return rc;
+  s.h_esrc_off.assign(h_esrc_off, h_esrc_off + V + 1);
+  s.h_inc_off.assign(h_inc_off, h_inc_off + V + 1);
+
+  std::memcpy(hf + raw_f_offset(RF_POS, V, E), g->pos, (size_t)2 * V * sizeof(float));
+  fill_or_copy(hf + raw_f_offset(RF_X, V, E), g->x, V, 0.0f);
+  fill_or_copy(hf + raw_f_offset(RF_W1, V, E), g->w1, V, 0.0f);
+  fill_or_copy(hf + raw_f_offset(RF_W2, V, E), g->w2, V, 0.0f);
+  fill_or_copy(hf + raw_f_offset(RF_XB, V, E), g->x_bar ? g->x_bar : g->x, V, 0.0f);
+  fill_or_copy(hf + raw_f_offset(RF_W1B, V, E), g->w1_bar, V, 0.0f);
+  fill_or_copy(hf + raw_f_offset(RF_W2B, V, E), g->w2_bar, V, 0.0f);
+  fill_or_copy(hf + raw_f_offset(RF_XP, V, E), g->x_prev ? g->x_prev : g->x, V, 0.0f);
+  fill_or_copy(hf + raw_f_offset(RF_W1P, V, E), g->w1_prev, V, 0.0f);
+  fill_or_copy(hf + raw_f_offset(RF_W2P, V, E), g->w2_prev, V, 0.0f);
+  fill_or_copy(hf + raw_f_offset(RF_DATA, V, E), g->data_term, V, 0.0f);
+  fill_or_copy(hf + raw_f_offset(RF_WT, V, E), g->data_weight, V, 1.0f);
+  fill_or_copy(hf + raw_f_offset(RF_ALPHA, V, E), g->alpha, E, 0.0f);
+  fill_or_copy(hf + raw_f_offset(RF_BETA, V, E), g->beta, E, 1.0f);
+  fill_or_copy(hf + raw_f_offset(RF_Q1, V, E), g->q1, E, 0.0f);
+  fill_or_copy(hf + raw_f_offset(RF_Q2, V, E), g->q2, E, 0.0f);
+  fill_or_copy(hf + raw_f_offset(RF_Q3, V, E), g->q3, E, 0.0f);
+
+  const size_t bytes = (raw_f_total(V, E) + ints_total(V, E)) * 4;
+  FB_CUDA(cudaMemcpyAsync(s.d_blob, s.h_blob, bytes, cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
+  int* di = reinterpret_cast<int*>(s.d_raw() + raw_f_total(V, E));
+  s.g.V = V;
+  s.g.E = E;
+  s.g.vperm = di;
+  s.g.eperm = di + V;
+  s.g.ends = reinterpret_cast<int2*>(di + V + E);
+  s.g.inc_off = di + V + E + 2 * (size_t)E;
+  s.g.inc = s.g.inc_off + V + 1;
+  s.g.esrc_off = s.g.inc + 2 * (size_t)E;
+  // int offset of `ends` is 14V + 6E (even) and the blob is 256-byte aligned: int2 loads are aligned
+  if (V > 0)
+    FB_CUDA(cudaMemcpyAsync(s.d_pos, s.d_raw(), (size_t)2 * V * sizeof(float),
+                            cudaMemcpyDeviceToDevice, c->stream));
+  if (int rc = pd_pack(c->stream, s.g, s.d_raw(), g->alpha == nullptr, g->beta == nullptr)) return rc;
+  s.loaded = true;
+  return publish_graph(c, slot);
+}
+
+int flame_b200_graph_init(flame_b200_ctx* c, int slot, int32_t V, const float* pos,
+                          const float* idepth, const float* weight, int32_t E,
+                          const int32_t* edges) {
+  flame_b200_graph_in g;
+  std::memset(&g, 0, sizeof(g));
+  g.V = V;
+  g.E = E;
+  g.pos = pos;
+  g.edges = edges;
+  g.data_term = idepth;
+  g.data_weight = weight;
+  g.x = idepth;  // x = x_bar = x_prev = idepth (flame.cc:2045-2048)
+  return flame_b200_graph_upload(c, slot, &g);
+}
+
+int flame_b200_graph_set_data(flame_b200_ctx* c, int slot, const float* data_term,
+                              const float* data_weight) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (int rc = use_device(c)) return rc;
+  Slot& s = c->slots[slot];
+  if (!s.loaded) {
+    set_error("graph_set_data: slot has no graph");
+    return FLAME_B200_ESTATE;
+  }
+  const int V = s.g.V;
+  if (int rc = wait_blob(s)) return rc;
+  float* hf = reinterpret_cast<float*>(s.h_blob);
+  if (data_term) std::memcpy(hf, data_term, (size_t)V * 4);
+  if (data_weight) std::memcpy(hf + V, data_weight, (size_t)V * 4);
+  FB_CUDA(cudaMemcpyAsync(s.d_raw(), hf, (size_t)2 * V * 4, cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
+  return pd_set_data(c->stream, s.g, data_term ? s.d_raw() : nullptr,
+                     data_weight ? s.d_raw() + V : nullptr);
+}
+
+int flame_b200_graph_reset(flame_b200_ctx* c, int slot0, int n_slots) {
+  if (int rc = check_slot(c, slot0, n_slots)) return rc;
+  if (int rc = use_device(c)) return rc;
+  int maxV = 0, maxE = 0;
+  for (int i = slot0; i < slot0 + n_slots; ++i) {
+    if (!c->slots[i].loaded) {
+      set_error("graph_reset: slot has no graph");
+      return FLAME_B200_ESTATE;
+    }
+    maxV = std::max(maxV, c->slots[i].g.V);
+    maxE = std::max(maxE, c->slots[i].g.E);
+  }
+  return pd_reset(c->stream, c->d_graphs + slot0, n_slots, maxV, maxE);
+}
+
+int flame_b200_graph_download(flame_b200_ctx* c, int slot, const flame_b200_graph_out* out) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (!out) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  Slot& s = c->slots[slot];
+  if (!s.loaded) {
+    set_error("graph_download: slot has no graph");
+    return FLAME_B200_ESTATE;
+  }
+  const int V = s.g.V, E = s.g.E;
+  if (int rc = wait_blob(s)) return rc;
+  if (int rc = pd_unpack(c->stream, s.g, s.d_raw())) return rc;
+  float* vdst[9] = {out->x, out->w1, out->w2, out->x_bar, out->w1_bar, out->w2_bar,
+                    out->x_prev, out->w1_prev, out->w2_prev};
+  float* edst[5] = {out->alpha, out->beta, out->q1, out->q2, out->q3};
+  int vlo = 9, vhi = -1, elo = 5, ehi = -1;
+  for (int i = 0; i < 9; ++i)
+    if (vdst[i]) { vlo = std::min(vlo, i); vhi = std::max(vhi, i); }
+  for (int i = 0; i < 5; ++i)
+    if (edst[i]) { elo = std::min(elo, i); ehi = std::max(ehi, i); }
+  float* hf = reinterpret_cast<float*>(s.h_blob);
+  if (vhi >= 0 && V > 0) {
+    const size_t off = raw_f_offset(RF_X + vlo, V, E), n = (size_t)(vhi - vlo + 1) * V;
+    FB_CUDA(cudaMemcpyAsync(hf + off, s.d_raw() + off, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (ehi >= 0 && E > 0) {
+    const size_t off = raw_f_offset(RF_ALPHA + elo, V, E), n = (size_t)(ehi - elo + 1) * E;
+    FB_CUDA(cudaMemcpyAsync(hf + off, s.d_raw() + off, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  FB_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 9; ++i)
+    if (vdst[i] && V > 0) std::memcpy(vdst[i], hf + raw_f_offset(RF_X + i, V, E), (size_t)V * 4);
+  for (int i = 0; i < 5; ++i)
+    if (edst[i] && E > 0) std::memcpy(edst[i], hf + raw_f_offset(RF_ALPHA + i, V, E), (size_t)E * 4);
+  return 0;
+}
+
+int flame_b200_pd_run(flame_b200_ctx* c, int slot0, int n_slots, const flame_b200_pd_params* params,
+                      int n_iters, int mode) {
+  if (int rc = check_slot(c, slot0, n_slots)) return rc;
+  if (!params || n_iters < 0 || mode < FLAME_B200_PD_AUTO || mode > FLAME_B200_PD_RESIDENT) {
+    set_error("pd_run: bad arguments");
+    return FLAME_B200_EINVAL;
+  }
+  if (int rc = use_device(c)) return rc;
+  int maxV = 0, maxE = 0;
+  for (int i = slot0; i < slot0 + n_slots; ++i) {
+    if (!c->slots[i].loaded) {
+      set_error("pd_run: slot has no graph");
+      return FLAME_B200_ESTATE;
+    }
+    maxV = std::max(maxV, c->slots[i].g.V);
+    maxE = std::max(maxE, c->slots[i].g.E);
+  }
+  if (n_iters == 0 || maxV == 0) return 0;
+  ResidentPlan plan{};
+  if (mode != FLAME_B200_PD_STREAM) {
+    // common plan for the batch: largest preferred cluster, then maxima of the per-CTA extents
+    int C = 0;
+    bool fits = true;
+    for (int i = slot0; i < slot0 + n_slots && fits; ++i) {
+      const Slot& s = c->slots[i];
+      ResidentPlan p1 = pd_plan_resident(s.g.V, s.g.E, s.h_esrc_off.data(), s.h_inc_off.data());
+      if (p1.cluster == 0) fits = false;
+      C = std::max(C, p1.cluster);
+      plan.threads = p1.threads;
+    }
+    if (fits) {
+      plan.cluster = C;
+      plan.Vc = (maxV + C - 1) / C;
+      plan.maxE = 1;
+      plan.maxInc = 1;
+      for (int i = slot0; i < slot0 + n_slots; ++i) {
+        const Slot& s = c->slots[i];
+        for (int k = 0; k < C; ++k) {
+          const int a = std::min(k * plan.Vc, s.g.V), b = std::min(a + plan.Vc, s.g.V);
+          plan.maxE = std::max(plan.maxE, s.h_esrc_off[b] - s.h_esrc_off[a]);
+          plan.maxInc = std::max(plan.maxInc, s.h_inc_off[b] - s.h_inc_off[a]);
+        }
+      }
+      plan.smem_bytes = pd_resident_smem(C, plan.Vc, plan.maxE, plan.maxInc);
+      if (plan.smem_bytes > 227 * 1024) fits = false;
+    }
+    if (!fits) {
+      if (mode == FLAME_B200_PD_RESIDENT) {
+        set_error("pd_run: graph does not fit the resident (cluster shared memory) mode");
+        return FLAME_B200_EINVAL;
+      }
+      plan.cluster = 0;
+    }
+  }
+  if (plan.cluster > 0)
+    return pd_run_resident(c->stream, c->d_graphs + slot0, n_slots, plan, *params, n_iters);
+  return pd_run_stream(c->stream, c->d_graphs + slot0, n_slots, maxV, maxE, *params, n_iters);
+}
+
+int flame_b200_pd_cost(flame_b200_ctx* c, int slot, const flame_b200_pd_params* params,
+                       int exact_order, float* smoothness_cost, float* data_cost) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (!params) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  Slot& s = c->slots[slot];
+  if (!s.loaded) {
+    set_error("pd_cost: slot has no graph");
+    return FLAME_B200_ESTATE;
+  }
+  if (int rc = wait_blob(s)) return rc;
+  if (int rc = pd_cost(c->stream, s.g, *params, exact_order, s.d_raw(), c->d_cost)) return rc;
+  FB_CUDA(cudaMemcpyAsync(c->h_cost, c->d_cost, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(cudaStreamSynchronize(c->stream));
+  if (smoothness_cost)
+    *smoothness_cost = exact_order ? (float)c->h_cost[0] : params->data_factor * (float)c->h_cost[0];
+  if (data_cost) *data_cost = (float)c->h_cost[1];
+  return 0;
+}
+
+// ---- dense projection ---------------------------------------------------------------------
+static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* tris, int32_t V,
+                          const uint8_t* vtx_valid, const uint8_t* tri_valid, int rows, int cols) {
+  if (T < 0 || rows <= 0 || cols <= 0 || (T > 0 && !tris)) {
+    set_error("mesh: bad arguments");
+    return FLAME_B200_EINVAL;
+  }
+  for (int i = 0; i < 3 * T; ++i)
+    if (tris[i] < 0 || tris[i] >= V) {
+      set_error("mesh: triangle vertex index out of range");
+      return FLAME_B200_EINVAL;
+    }
+  if (T > s.capT) {
+    const int n = std::max(T, s.capT + s.capT / 2);
+    if (s.m.tris) FB_CUDA(cudaFree(s.m.tris));
+    if (s.m.tri_ok) FB_CUDA(cudaFree(s.m.tri_ok));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.tris), (size_t)n * 3 * sizeof(int)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.tri_ok), (size_t)n));
+    s.capT = n;
+  }
+  const size_t npix = (size_t)rows * cols;
+  if (npix > s.cap_pix) {
+    if (s.m.img) FB_CUDA(cudaFree(s.m.img));
+    if (s.m.win) FB_CUDA(cudaFree(s.m.win));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.img), npix * sizeof(float)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.win), npix * sizeof(unsigned long long)));
+    s.cap_pix = npix;
+  }
+  s.m.T = T;
+  s.m.rows = rows;
+  s.m.cols = cols;
+  if (T > 0) {
+    // staged through the slot's pinned blob (tris + combined validity)
+    const size_t need = (size_t)T * 13 + 64;
+    if (int rc = wait_blob(s)) return rc;
+    if (need > s.h_blob_cap) {
+      if (s.h_blob) FB_CUDA(cudaFreeHost(s.h_blob));
+      s.h_blob = nullptr;
+      FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s.h_blob), need));
+      s.h_blob_cap = need;
+    }
+    if (!s.blob_free) FB_CUDA(cudaEventCreateWithFlags(&s.blob_free, cudaEventDisableTiming));
+    int* ht = reinterpret_cast<int*>(s.h_blob);
+    unsigned char* hok = s.h_blob + (size_t)T * 12;
+    std::memcpy(ht, tris, (size_t)T * 12);
+    for (int t = 0; t < T; ++t) {
+      bool ok = !tri_valid || tri_valid[t];
+      if (ok && vtx_valid)
+        ok = vtx_valid[tris[3 * t]] && vtx_valid[tris[3 * t + 1]] && vtx_valid[tris[3 * t + 2]];
+      hok[t] = ok ? 1 : 0;
+    }
+    FB_CUDA(cudaMemcpyAsync(s.m.tris, ht, (size_t)T * 12, cudaMemcpyHostToDevice, c->stream));
+    FB_CUDA(cudaMemcpyAsync(s.m.tri_ok, hok, (size_t)T, cudaMemcpyHostToDevice, c->stream));
+    FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
+  }
+  return 0;
+}
+
+int flame_b200_mesh_bind(flame_b200_ctx* c, int slot, int32_t T, const int32_t* tris,
+                         const uint8_t* vtx_valid, const uint8_t* tri_valid, int rows, int cols) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (int rc = use_device(c)) return rc;
+  Slot& s = c->slots[slot];
+  if (!s.loaded) {
+    set_error("mesh_bind: slot has no graph");
+    return FLAME_B200_ESTATE;
+  }
+  return mesh_bind_impl(c, s, T, tris, s.g.V, vtx_valid, tri_valid, rows, cols);
+}
+
+int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float scale) {
+  if (int rc = check_slot(c, slot0, n_slots)) return rc;
+  if (int rc = use_device(c)) return rc;
+  for (int i = slot0; i < slot0 + n_slots; ++i) {
+    Slot& s = c->slots[i];
+    if (!s.loaded || !s.m.img) {
+      set_error("mesh_project: slot has no graph / bound mesh");
+      return FLAME_B200_ESTATE;
+    }
+    if (int rc = raster_values_from_graph(c->stream, s.g, scale, s.d_values)) return rc;
+    if (int rc = raster_project(c->stream, s.m, s.d_pos, s.d_values, 1)) return rc;
+  }
+  return 0;
+}
+
+int flame_b200_mesh_download(flame_b200_ctx* c, int slot, float* out_host) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (!out_host) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  Slot& s = c->slots[slot];
+  if (!s.m.img) {
+    set_error("mesh_download: no dense map in this slot");
+    return FLAME_B200_ESTATE;
+  }
+  FB_CUDA(cudaMemcpyAsync(out_host, s.m.img, (size_t)s.m.rows * s.m.cols * sizeof(float),
+                          cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+
+int flame_b200_interpolate_mesh(flame_b200_ctx* c, int slot, int32_t T, const int32_t* tris,
+                                int32_t V, const float* pos, const float* values, float scale,
+                                const uint8_t* vtx_valid, const uint8_t* tri_valid, int rows,
+                                int cols, int fill_nan, float* out_host) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (!out_host || V < 0 || (V > 0 && !pos)) {
+    set_error("interpolate_mesh: bad arguments");
+    return FLAME_B200_EINVAL;
+  }
+  if (int rc = use_device(c)) return rc;
+  Slot& s = c->slots[slot];
+  if (!values && (!s.loaded || s.g.V != V)) {
+    set_error("interpolate_mesh: values == NULL needs a graph with V vertices in the slot");
+    return FLAME_B200_ESTATE;
+  }
+  if (V > s.capMV) {
+    const int n = std::max(V, s.capMV + s.capMV / 2);
+    if (s.d_mpos) FB_CUDA(cudaFree(s.d_mpos));
+    if (s.d_mvalues) FB_CUDA(cudaFree(s.d_mvalues));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_mpos), (size_t)n * 2 * sizeof(float)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_mvalues), (size_t)n * sizeof(float)));
+    s.capMV = n;
+  }
+  if (int rc = mesh_bind_impl(c, s, T, tris, V, vtx_valid, tri_valid, rows, cols)) return rc;
+  if (V > 0)
+    FB_CUDA(cudaMemcpyAsync(s.d_mpos, pos, (size_t)2 * V * 4, cudaMemcpyHostToDevice, c->stream));
+  if (values) {
+    if (V > 0)
+      FB_CUDA(cudaMemcpyAsync(s.d_mvalues, values, (size_t)V * 4, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    if (int rc = raster_values_from_graph(c->stream, s.g, scale, s.d_mvalues)) return rc;
+  }
+  const size_t npix = (size_t)rows * cols;
+  if (!fill_nan)
+    FB_CUDA(cudaMemcpyAsync(s.m.img, out_host, npix * 4, cudaMemcpyHostToDevice, c->stream));
+  if (int rc = raster_project(c->stream, s.m, s.d_mpos, s.d_mvalues, fill_nan)) return rc;
+  FB_CUDA(cudaMemcpyAsync(out_host, s.m.img, npix * 4, cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- epipolar search ------------------------------------------------------------------------
+int flame_b200_set_camera(flame_b200_ctx* c, int width, int height, const float K[9],
+                          const float Kinv[9]) {
+  if (!c || !K || !Kinv || width <= 0 || height <= 0) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  return stereo_set_camera(&c->stereo, width, height, K, Kinv);
+}
+
+int flame_b200_frame_upload(flame_b200_ctx* c, int fslot, const uint8_t* img_pad,
+                            const float* gradx_pad, const float* grady_pad, int pad,
+                            const float pose[7]) {
+  if (!c || !img_pad || !gradx_pad || !grady_pad || !pose) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  return stereo_frame_upload(&c->stereo, c->stream, fslot, img_pad, gradx_pad, grady_pad, pad, pose);
+}
+
+int flame_b200_update_feature_idepths(flame_b200_ctx* c, const flame_b200_track_params* params,
+                                      int fnew, int curr_pf, flame_b200_feature* feats,
+                                      int32_t n_feats, flame_b200_track_diag* diag,
+                                      int32_t* n_updates) {
+  if (!c || !params || (n_feats > 0 && !feats) || n_feats < 0) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  return stereo_update(c->stereo, c->stream, params, fnew, curr_pf, feats, n_feats, diag, n_updates);
+}
+
+}  // extern "C"

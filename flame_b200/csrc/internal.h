@@ -1,0 +1,101 @@
+// Internal declarations shared by the translation units of libflame_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "flame_b200.h"
+
+namespace fb {
+
+void set_error(const std::string& msg);
+extern std::atomic<uint64_t> g_kernel_launches;
+inline void count_launch(int n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define FB_CUDA(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::fb::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                  \
+      return FLAME_B200_ECUDA;                                                              \
+    }                                                                                       \
+  } while (0)
+
+// ---- device-side record layouts (internal vertex/edge order, see DESIGN.md "HBM layout") ----
+struct __align__(32) EdgeRec {
+  float4 q;  // q1, q2, q3, 0          (EdgeData::q1..q3)
+  float4 s;  // alpha, beta, dx, dy    (EdgeData::alpha/beta; dx = pos_i.x - pos_j.x)
+};
+
+// Plain-pointer view of one slot's graph, passed to kernels by value / in an array.
+struct GraphDev {
+  int V, E;
+  float4* vprim;   // x, w1, w2, data_term
+  float4* vbar;    // x_bar, w1_bar, w2_bar, 0
+  float4* vprev;   // x_prev, w1_prev, w2_prev, 0
+  float* vwt;      // data_weight
+  EdgeRec* erec;
+  int2* ends;      // internal (source, target)
+  int* inc_off;    // V+1
+  int* inc;        // 2E entries: (internal edge << 1) | is_target, ascending ORIGINAL edge id
+  int* esrc_off;   // V+1: first internal edge whose source is >= v (edges sorted by source)
+  int* vperm;      // internal -> caller vertex index
+  int* eperm;      // internal -> caller edge index
+};
+
+struct MeshDev {
+  int T, rows, cols;
+  int* tris;                  // 3T caller vertex indices
+  unsigned char* tri_ok;      // T: tri_valid && all three vtx_valid
+  float* img;                 // rows*cols
+  unsigned long long* win;    // rows*cols: (tri+1) << 32 | value bits
+};
+
+// ---- PD (pd.cu) ----
+struct ResidentPlan {
+  int cluster;        // CTAs per graph (0 = does not fit)
+  int threads;
+  size_t smem_bytes;
+  int Vc, maxE, maxInc;
+};
+
+int pd_pack(cudaStream_t st, const GraphDev& g, const float* raw_f, int alpha_on_device,
+            int beta_default);
+int pd_unpack(cudaStream_t st, const GraphDev& g, float* raw_f);
+int pd_set_data(cudaStream_t st, const GraphDev& g, const float* data_term, const float* data_weight);
+int pd_run_stream(cudaStream_t st, const GraphDev* gs_dev, int n, int maxV, int maxE,
+                  const flame_b200_pd_params& p, int n_iters);
+ResidentPlan pd_plan_resident(int V, int E, const int* esrc_off, const int* inc_off);
+int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const ResidentPlan& plan,
+                    const flame_b200_pd_params& p, int n_iters);
+int pd_reset(cudaStream_t st, const GraphDev* gs_dev, int n, int maxV, int maxE);
+int pd_resident_init();  // one-time function attributes
+size_t pd_resident_smem(int C, int Vc, int maxE, int maxInc);
+int pd_cost(cudaStream_t st, const GraphDev& g, const flame_b200_pd_params& p, int exact_order,
+            float* terms_scratch, double* out_dev /*2 doubles*/);
+
+// raw staging layout (floats), caller order: see capi.cu
+enum RawF {
+  RF_POS = 0,  // 2V
+  RF_X, RF_W1, RF_W2, RF_XB, RF_W1B, RF_W2B, RF_XP, RF_W1P, RF_W2P, RF_DATA, RF_WT,  // V each
+  RF_ALPHA, RF_BETA, RF_Q1, RF_Q2, RF_Q3,                                           // E each
+  RF_COUNT
+};
+inline size_t raw_f_offset(int field, int V, int E) {
+  // pos first (2V), then 11 V-arrays, then 5 E-arrays
+  if (field == RF_POS) return 0;
+  if (field <= RF_WT) return (size_t)2 * V + (size_t)(field - RF_X) * V;
+  return (size_t)2 * V + (size_t)11 * V + (size_t)(field - RF_ALPHA) * E;
+}
+inline size_t raw_f_total(int V, int E) { return (size_t)13 * V + (size_t)5 * E; }
+
+// ---- dense projection (raster.cu) ----
+int raster_project(cudaStream_t st, const MeshDev& m, const float* pos /*2V caller order*/,
+                   const float* values /*V caller order*/, int fill_nan);
+// values[vperm[v]] = vprim[v].x * scale  (vtx_idepths_ = x * graph_scale_, flame.cc:376)
+int raster_values_from_graph(cudaStream_t st, const GraphDev& g, float scale, float* values);
+
+}  // namespace fb

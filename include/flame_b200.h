@@ -1,0 +1,257 @@
+/*
+ * flame_b200.h — C ABI of libflame_b200.so: the B200-native (sm_100a) replacement for FLaME's
+ * per-frame variational depth regularisation hot path.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * robustrobotics/flame checkout, src/flame/...). Plain pointers and sizes only; no C++ or torch
+ * types cross this boundary. Conventions follow the reference's:
+ *   - the caller owns every host buffer; the library copies what it needs before returning
+ *     (uploads are staged through pinned memory), so buffers may be reused immediately;
+ *   - functions return 0 on success, a negative FLAME_B200_E* code otherwise, never throw;
+ *     flame_b200_last_error() returns a thread-local description of the last failure;
+ *   - one context = one CUDA stream + `n_slots` independent frame slots. A context is
+ *     thread-compatible (serialise calls on it, as Flame serialises step() under graph_mtx_,
+ *     flame.cc:100-111); distinct contexts may be driven from distinct threads concurrently;
+ *   - work is enqueued asynchronously on the context's stream; calls that return data to
+ *     host memory synchronise that stream before returning unless documented otherwise.
+ *   - there is NO CPU fallback: with no usable sm_100 device every call fails with
+ *     FLAME_B200_ENODEV.
+ *
+ * Vertex order = caller's order. Edge order = caller's order; edges[2e] is the SOURCE and
+ * edges[2e+1] the TARGET of edge e (flame.cc:2085-2096 inserts Triangle's edgelist in order;
+ * orientation matters, nltgv2_l1_graph_regularizer.cc:99-101,129-133). Results are bit-identical
+ * to the reference's scalar fp32 arithmetic for the PD iteration, the edge weights and the dense
+ * projection (see DESIGN.md "Parity").
+ */
+#ifndef FLAME_B200_H_
+#define FLAME_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLAME_B200_VERSION 100
+
+enum {
+  FLAME_B200_OK = 0,
+  FLAME_B200_EINVAL = -1,   /* bad argument (the reference would FLAME_ASSERT) */
+  FLAME_B200_ENODEV = -2,   /* no sm_100 device / CUDA runtime unusable */
+  FLAME_B200_ECUDA = -3,    /* a CUDA call failed; see flame_b200_last_error() */
+  FLAME_B200_ENOMEM = -4,
+  FLAME_B200_ESTATE = -5    /* call sequence error (e.g. pd_run before graph_upload) */
+};
+
+typedef struct flame_b200_ctx flame_b200_ctx;
+
+const char* flame_b200_last_error(void);
+int flame_b200_version(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py "gpu_launches"). */
+uint64_t flame_b200_kernel_launches(void);
+
+/* ---- context ------------------------------------------------------------------------- */
+/* device: CUDA ordinal. n_slots >= 1 independent frames resident at once. */
+int flame_b200_ctx_create(int device, int n_slots, flame_b200_ctx** out);
+void flame_b200_ctx_destroy(flame_b200_ctx* ctx);
+int flame_b200_ctx_sync(flame_b200_ctx* ctx);
+/* cudaStream_t of the context, as an opaque pointer (for CUDA-event timing by the caller). */
+void* flame_b200_ctx_stream(flame_b200_ctx* ctx);
+
+/* Pinned (page-locked) host memory for buffers handed to the asynchronous download calls. */
+int flame_b200_host_alloc(size_t bytes, void** out);
+int flame_b200_host_free(void* p);
+
+/* ---- PD solver: optimizers/nltgv2_l1_graph_regularizer.{h,cc} ------------------------- */
+
+/* nltgv2_l1_graph_regularizer::Params (h:121-129), same fields, same defaults. */
+typedef struct {
+  float data_factor; /* 0.1   */
+  float step_x;      /* 0.001 */
+  float step_q;      /* 125   */
+  float theta;       /* 0.25  */
+  float x_min;       /* 0     */
+  float x_max;       /* 10    */
+} flame_b200_pd_params;
+void flame_b200_pd_default_params(flame_b200_pd_params* p);
+
+/* Flat SoA image of nltgv2_l1_graph_regularizer::Graph (VertexData h:74-90, EdgeData h:95-102).
+ * For upload every pointer except those marked nullable must be set; a NULL nullable array
+ * means "all zeros" (w*, q*) / "copy of x" (x_bar, x_prev) / "all ones" (data_weight, beta) /
+ * "1/edge length computed on the device" (alpha: the flame.cc:2084-2105 rule).
+ * For download any pointer may be NULL (skipped). */
+typedef struct {
+  int32_t V, E;
+  const float* pos;        /* 2V, x,y interleaved (VertexData::pos)           */
+  const int32_t* edges;    /* 2E, source,target                                */
+  const float* data_term;  /* V                                                */
+  const float* data_weight;/* V, nullable -> 1                                 */
+  const float* x;          /* V                                                */
+  const float* w1;         /* V, nullable -> 0 */
+  const float* w2;         /* V, nullable -> 0 */
+  const float* x_bar;      /* V, nullable -> x */
+  const float* w1_bar;     /* V, nullable -> 0 */
+  const float* w2_bar;     /* V, nullable -> 0 */
+  const float* x_prev;     /* V, nullable -> x */
+  const float* w1_prev;    /* V, nullable -> 0 */
+  const float* w2_prev;    /* V, nullable -> 0 */
+  const float* alpha;      /* E, nullable -> 1/||pos_i - pos_j|| on device     */
+  const float* beta;       /* E, nullable -> 1                                 */
+  const float* q1;         /* E, nullable -> 0 */
+  const float* q2;         /* E, nullable -> 0 */
+  const float* q3;         /* E, nullable -> 0 */
+} flame_b200_graph_in;
+
+typedef struct {
+  float *x, *w1, *w2, *x_bar, *w1_bar, *w2_bar, *x_prev, *w1_prev, *w2_prev; /* V each */
+  float *alpha, *beta, *q1, *q2, *q3;                                         /* E each */
+} flame_b200_graph_out;
+
+/* Replaces the property writes of Flame::syncGraph (flame.cc:1998-2014, 2035-2048, 2084-2105,
+ * 2160-2162): loads one graph into `slot`. Asynchronous; host buffers are consumed on return. */
+int flame_b200_graph_upload(flame_b200_ctx* ctx, int slot, const flame_b200_graph_in* g);
+
+/* Convenience for a fresh graph (flame.cc:2039-2048 + 2084-2105): x = x_bar = x_prev = idepth,
+ * data_term = idepth, w = q = 0, data_weight = weight (nullable -> 1), alpha = 1/len, beta = 1. */
+int flame_b200_graph_init(flame_b200_ctx* ctx, int slot, int32_t V, const float* pos,
+                          const float* idepth, const float* weight, int32_t E,
+                          const int32_t* edges);
+
+/* Only refresh the data term / weights of an already uploaded graph (flame.cc:1998-2014). */
+int flame_b200_graph_set_data(flame_b200_ctx* ctx, int slot, const float* data_term,
+                              const float* data_weight);
+
+/* Re-applies the fresh-vertex rule of Flame::syncGraph (flame.cc:2039-2048) on the device to slots
+ * [slot0, slot0 + n_slots): x = x_bar = x_prev = data_term, w* = 0, q* = 0. Asynchronous. */
+int flame_b200_graph_reset(flame_b200_ctx* ctx, int slot0, int n_slots);
+
+/* Replaces the property reads at flame.cc:372-380. Synchronises the stream. */
+int flame_b200_graph_download(flame_b200_ctx* ctx, int slot, const flame_b200_graph_out* out);
+
+enum {
+  FLAME_B200_PD_AUTO = 0,     /* resident if the graph fits one cluster's shared memory */
+  FLAME_B200_PD_STREAM = 1,   /* state in HBM/L2, two kernels per iteration, any size    */
+  FLAME_B200_PD_RESIDENT = 2  /* state in (distributed) shared memory for all iterations */
+};
+
+/* Replaces n_iters consecutive calls of nltgv2_l1_graph_regularizer::step(params, &graph)
+ * (h:134, cc:33-49) on slots [slot0, slot0 + n_slots). Asynchronous. */
+int flame_b200_pd_run(flame_b200_ctx* ctx, int slot0, int n_slots,
+                      const flame_b200_pd_params* params, int n_iters, int mode);
+
+/* Replaces smoothnessCost / dataCost (h:139,144; cc:51-85). exact_order != 0 reproduces the
+ * reference's sequential fp32 accumulation order bit-for-bit (slower); 0 uses a tree reduction
+ * in fp64. Synchronises the stream. */
+int flame_b200_pd_cost(flame_b200_ctx* ctx, int slot, const flame_b200_pd_params* params,
+                       int exact_order, float* smoothness_cost, float* data_cost);
+
+/* ---- dense projection: utils::interpolateMesh (utils/image_utils.h:646-651, .cc:373-396) over
+ *      utils::DrawShadedTriangleBarycentric (utils/rasterization.cc:164-245) -------------- */
+
+/* tris: 3T vertex indices in Triangle's (clockwise) order, as utils::Delaunay::triangles().
+ * values: V floats, NULL -> the slot's current x scaled by `scale` (vtx_idepths_ = x *
+ * graph_scale_, flame.cc:376). vtx_valid / tri_valid: nullable (all true).
+ * out_host: rows x cols floats. fill_nan != 0 pre-fills the image with quiet NaN (as
+ * Flame::update does, flame.cc:412); otherwise out_host is read as the pre-initialised image.
+ * Synchronises the stream. */
+int flame_b200_interpolate_mesh(flame_b200_ctx* ctx, int slot, int32_t T, const int32_t* tris,
+                                int32_t V, const float* pos, const float* values, float scale,
+                                const uint8_t* vtx_valid, const uint8_t* tri_valid, int rows,
+                                int cols, int fill_nan, float* out_host);
+
+/* Device-resident variant for pipelines and for timing without PCIe: the mesh (tris, validity)
+ * is bound to the slot once, the image stays in HBM; `values` come from the slot's x. */
+int flame_b200_mesh_bind(flame_b200_ctx* ctx, int slot, int32_t T, const int32_t* tris,
+                         const uint8_t* vtx_valid, const uint8_t* tri_valid, int rows, int cols);
+int flame_b200_mesh_project(flame_b200_ctx* ctx, int slot0, int n_slots, float scale); /* async */
+/* Asynchronous device->host copy of the slot's dense map into PINNED or pageable host memory;
+ * complete after flame_b200_ctx_sync(). */
+int flame_b200_mesh_download(flame_b200_ctx* ctx, int slot, float* out_host);
+
+/* ---- epipolar search + measurement + fusion: Flame::updateFeatureIDepths / trackFeature
+ *      (flame.cc:1280-1752) over stereo::inverse_depth_filter::{predict,getSearchRegion,search,
+ *      update} (stereo/inverse_depth_filter.h:73-107), stereo::line_stereo::match
+ *      (stereo/line_stereo.h:75-385), stereo::InverseDepthMeasModel::idepth
+ *      (stereo/inverse_depth_meas_model.cc:49-156), stereo::EpipolarGeometry<float>
+ *      (stereo/epipolar_geometry.h:44-428) --------------------------------------------------- */
+
+typedef struct { /* stereo::line_stereo::Params, line_stereo.h:47-59 */
+  float max_cost;
+  int32_t do_subpixel;
+  float sample_dist;
+  float second_best_factor;
+} flame_b200_ls_params;
+
+typedef struct { /* stereo::inverse_depth_filter::Params, inverse_depth_filter.h:48-68 */
+  int32_t win_size;
+  float search_sigma;
+  float min_grad_mag;
+  float idepth_min, idepth_max;
+  float epilength_min, epilength_max;
+  float process_var_factor;
+  float process_fail_var_factor;
+  flame_b200_ls_params sparams;
+} flame_b200_filter_params;
+
+typedef struct { /* stereo::InverseDepthMeasModel::Params, inverse_depth_meas_model.h:44-52 */
+  int32_t win_size;
+  float pixel_var;
+  float epipolar_line_var;
+} flame_b200_meas_params;
+
+typedef struct { /* the fields of flame::Params (params.h:36-143) the per-feature driver reads */
+  flame_b200_filter_params fparams;
+  flame_b200_meas_params zparams;
+  float min_baseline;
+  float rescale_factor_min, rescale_factor_max;
+  float idepth_var_max;
+  int32_t max_dropouts;
+  float outlier_sigma_thresh;
+  int32_t do_meas_fusion;
+  int32_t do_letterbox;
+} flame_b200_track_params;
+void flame_b200_track_default_params(flame_b200_track_params* p);
+
+typedef struct { /* flame::FeatureWithIDepth, flame.h:88-99 */
+  uint32_t id;
+  uint32_t frame_id;      /* frame slot of the parent pose-frame */
+  float x, y;
+  float idepth_mu, idepth_var;
+  int32_t valid;
+  uint32_t num_updates;
+  uint32_t num_dropouts;
+  int32_t search_status;  /* inverse_depth_filter::Status, inverse_depth_filter.h:38-43 */
+} flame_b200_feature;
+
+typedef struct { /* per-feature diagnostics (what the reference keeps in locals) */
+  float flow_x, flow_y;
+  float mu_meas, var_meas;
+  int32_t stage; /* 0 skipped(baseline) 1 predict-fail 2 re-parented 3 re-parent-fail 4 region-fail
+                    5 out-of-bounds 6 search-fail 7 sense-fail 8 fuse-fail 9 updated */
+} flame_b200_track_diag;
+
+/* Camera intrinsics for the search (Flame ctor, flame.h:123-125). Row-major 3x3. */
+int flame_b200_set_camera(flame_b200_ctx* ctx, int width, int height, const float K[9],
+                          const float Kinv[9]);
+
+/* Replaces utils::Frame's padded level-0 buffers (utils/frame.cc:54-63; img_pad REFLECT_101,
+ * gradients zero-padded, border `pad`) for frame slot `fslot` (0 <= fslot < 64).
+ * pose = camera-to-world (qw,qx,qy,qz,tx,ty,tz) as utils::Frame::pose. Asynchronous. */
+int flame_b200_frame_upload(flame_b200_ctx* ctx, int fslot, const uint8_t* img_pad,
+                            const float* gradx_pad, const float* grady_pad, int pad,
+                            const float pose[7]);
+
+/* Replaces the loop body of Flame::updateFeatureIDepths (flame.cc:1308-1496) for n features:
+ * feats is updated in place (host memory), diag (nullable) receives per-feature diagnostics.
+ * fnew = frame slot of the new frame, curr_pf = frame slot of the current pose-frame.
+ * Returns the number of successful updates in *n_updates. Synchronises the stream. */
+int flame_b200_update_feature_idepths(flame_b200_ctx* ctx, const flame_b200_track_params* params,
+                                      int fnew, int curr_pf, flame_b200_feature* feats,
+                                      int32_t n_feats, flame_b200_track_diag* diag,
+                                      int32_t* n_updates);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLAME_B200_H_ */

@@ -1,0 +1,136 @@
+"""GPU parity: libflame_b200's PD solver vs the CPU oracle (bit-exact), through the C ABI."""
+import numpy as np
+import pytest
+
+from flame_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+STATE = ("x", "w1", "w2", "x_bar", "w1_bar", "w2_bar", "x_prev", "w1_prev", "w2_prev", "q1", "q2", "q3")
+
+
+def _oracle_state(oracle, g, n_iters, params=None):
+    alpha, beta = oracle.edge_weights(g["edges"], g["pos"])
+    s = synth.init_state(g, alpha, beta)
+    p = oracle.pd_default_params() if params is None else params
+    oracle.pd_run(s, p, n_iters)
+    return s
+
+
+def _assert_bit_equal(got, want, names):
+    for k in names:
+        a, b = got[k].view(np.uint32), want[k].view(np.uint32)
+        bad = np.flatnonzero(a != b)
+        assert bad.size == 0, "%s differs at %d/%d entries (first %d: %r vs %r)" % (
+            k, bad.size, a.size, bad[0], got[k][bad[0]], want[k][bad[0]])
+
+
+@pytest.mark.parametrize("cfg", ["A", "B", "C", "D"])
+@pytest.mark.parametrize("mode", [_lib.PD_STREAM, _lib.PD_RESIDENT, _lib.PD_AUTO])
+def test_pd_bit_exact(gpu_ctx, oracle, cfg, mode):
+    g = synth.config_graph(cfg)
+    n = g["pd_iters"]
+    want = _oracle_state(oracle, g, n)
+    V, E = g["pos"].shape[0], g["edges"].shape[0]
+    gpu_ctx.graph_init(0, g["pos"], g["data_term"], g["edges"])
+    gpu_ctx.pd_run(_lib.default_pd_params(), n, mode=mode)
+    got = gpu_ctx.graph_download(0, V, E)
+    _assert_bit_equal(got, want, STATE + ("alpha", "beta"))
+
+
+def test_pd_full_state_upload_and_resume(gpu_ctx, oracle):
+    """Upload an arbitrary mid-run state (all 19 arrays), run more iterations, compare."""
+    g = synth.config_graph("B")
+    mid = _oracle_state(oracle, g, 7)
+    want = {k: v.copy() if isinstance(v, np.ndarray) else v for k, v in mid.items()}
+    oracle.pd_run(want, oracle.pd_default_params(), 13)
+    gpu_ctx.graph_upload(1, mid)
+    gpu_ctx.pd_run(_lib.default_pd_params(), 13, slot0=1)
+    got = gpu_ctx.graph_download(1, g["pos"].shape[0], g["edges"].shape[0])
+    _assert_bit_equal(got, want, STATE)
+
+
+def test_pd_zero_and_one_iteration(gpu_ctx, oracle):
+    g = synth.config_graph("A")
+    V, E = g["pos"].shape[0], g["edges"].shape[0]
+    for n in (0, 1):
+        want = _oracle_state(oracle, g, n)
+        gpu_ctx.graph_init(0, g["pos"], g["data_term"], g["edges"])
+        gpu_ctx.pd_run(_lib.default_pd_params(), n)
+        got = gpu_ctx.graph_download(0, V, E)
+        _assert_bit_equal(got, want, STATE)
+
+
+def test_pd_nondefault_params_weights_and_clamp(gpu_ctx, oracle):
+    g = synth.make_graph(640, 480, 800, seed=11, noise_seed=12, triangulator="scipy")
+    rng = np.random.default_rng(5)
+    g["data_weight"] = rng.uniform(0.2, 5.0, g["pos"].shape[0]).astype(np.float32)
+    g["data_term"][::7] = 9.99  # pushes x against x_max
+    g["data_term"][3::11] = 0.0
+    alpha, beta = oracle.edge_weights(g["edges"], g["pos"])
+    beta = rng.uniform(0.5, 2.0, beta.shape[0]).astype(np.float32)
+    s = synth.init_state(g, alpha, beta)
+    p = oracle.pd_default_params()
+    p.data_factor, p.step_x, p.step_q, p.theta, p.x_min, p.x_max = 0.35, 0.004, 60.0, 0.5, 0.05, 4.0
+    want = {k: v.copy() if isinstance(v, np.ndarray) else v for k, v in s.items()}
+    oracle.pd_run(want, p, 40)
+    gp = _lib.PDParams(0.35, 0.004, 60.0, 0.5, 0.05, 4.0)
+    for mode in (_lib.PD_STREAM, _lib.PD_RESIDENT):
+        gpu_ctx.graph_upload(2, s)
+        gpu_ctx.pd_run(gp, 40, slot0=2, mode=mode)
+        got = gpu_ctx.graph_download(2, g["pos"].shape[0], g["edges"].shape[0])
+        _assert_bit_equal(got, want, STATE)
+
+
+def test_pd_batch_of_different_graphs(gpu_ctx, oracle):
+    """Slots 0..5 hold different graphs (different V/E); one batched launch per mode."""
+    graphs = [synth.make_graph(640, 480, 300 + 170 * i, seed=20 + i, noise_seed=40 + i,
+                               triangulator="scipy") for i in range(6)]
+    wants = [_oracle_state(oracle, g, 25) for g in graphs]
+    for mode in (_lib.PD_STREAM, _lib.PD_RESIDENT):
+        for i, g in enumerate(graphs):
+            gpu_ctx.graph_init(i, g["pos"], g["data_term"], g["edges"])
+        gpu_ctx.pd_run(_lib.default_pd_params(), 25, slot0=0, n_slots=6, mode=mode)
+        for i, g in enumerate(graphs):
+            got = gpu_ctx.graph_download(i, g["pos"].shape[0], g["edges"].shape[0])
+            _assert_bit_equal(got, wants[i], STATE)
+
+
+def test_pd_cost(gpu_ctx, oracle):
+    g = synth.config_graph("C")
+    want = _oracle_state(oracle, g, 30)
+    ws, wd = oracle.pd_costs(want, oracle.pd_default_params())
+    gpu_ctx.graph_init(0, g["pos"], g["data_term"], g["edges"])
+    gpu_ctx.pd_run(_lib.default_pd_params(), 30)
+    s, d = gpu_ctx.pd_cost(0, _lib.default_pd_params(), exact_order=True)
+    assert np.float32(s) == np.float32(ws) and np.float32(d) == np.float32(wd)
+    s, d = gpu_ctx.pd_cost(0, _lib.default_pd_params(), exact_order=False)
+    assert abs(s - ws) <= 1e-4 * abs(ws) and abs(d - wd) <= 1e-4 * abs(wd)
+
+
+def test_pd_energy_decreases_and_fixed_point(gpu_ctx):
+    """Properties at full size (config D): energy after 200 iterations is far below the start's
+    smoothness cost; a constant data term is a fixed point (x stays, q stays 0)."""
+    g = synth.config_graph("D")
+    V, E = g["pos"].shape[0], g["edges"].shape[0]
+    p = _lib.default_pd_params()
+    gpu_ctx.graph_init(0, g["pos"], g["data_term"], g["edges"])
+    s0, d0 = gpu_ctx.pd_cost(0, p)
+    gpu_ctx.pd_run(p, 200)
+    s1, d1 = gpu_ctx.pd_cost(0, p)
+    assert d0 == 0.0 and s1 + d1 < s0 + d0 and s1 < 0.5 * s0
+    const = np.full(V, 0.7, np.float32)
+    gpu_ctx.graph_init(0, g["pos"], const, g["edges"])
+    gpu_ctx.pd_run(p, 50)
+    got = gpu_ctx.graph_download(0, V, E)
+    assert np.all(got["x"] == np.float32(0.7)) and not got["q1"].any() and not got["w1"].any()
+
+
+def test_pd_errors(gpu_ctx):
+    with pytest.raises(_lib.FlameB200Error):
+        gpu_ctx.pd_run(_lib.default_pd_params(), 1, slot0=7, n_slots=3)  # out of range
+    g = synth.config_graph("A")
+    bad = g["edges"].copy()
+    bad[0, 0] = 10 ** 6
+    with pytest.raises(_lib.FlameB200Error):
+        gpu_ctx.graph_init(0, g["pos"], g["data_term"], bad)
