@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the FLaME variational-depth hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+Workload (BASELINE.json configs[3], the one `metric` is quoted on): 1920x1080 frames, 10 000
+Delaunay vertices each, 200 primal-dual iterations + dense inverse-depth projection.
+A "step" is one pass of the hot path over one batch of B independent synthetic frames per GPU:
+    graph_reset (fresh-vertex rule)  ->  200 x step()  ->  interpolateMesh
+`value`  = frames/s with inputs resident in HBM (CUDA events on the library's stream, max over ranks).
+`e2e`    = the same metric through the public C ABI with HOST buffers: per frame, upload of the
+           graph + triangles (H2D), PD, projection, download of the dense map + vertex idepths (D2H).
+`roofline` is for the dominant kernel (the resident PD solver) — see DESIGN.md for the byte model.
+Multi-GPU: frames shard by rank (weak scaling), no data-path collective; torch.distributed (NCCL)
+is only used for the barrier and the max-over-ranks reduction.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = "D"
+METRIC = "frames/sec at 1080p (10k vertices, 200 PD iters + dense projection)"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _frames(n, first=0):
+    from flame_b200 import synth
+    W, H, V, iters = synth.CONFIGS[CFG]
+    out = []
+    for f in range(first, first + n):
+        g = synth.config_graph(CFG, frame=f)
+        out.append(g)
+    return out, (W, H, V, iters)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons during the timed region (pynvml)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.sm_max = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            }
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+
+
+def _cpu_frame(pyoracle, synth, g, iters):
+    """One frame of the hot path on one CPU thread (the reference runs step() on exactly one thread,
+    flame.cc:100-111): edge weights, 200 x step, interpolateMesh."""
+    alpha, beta = pyoracle.edge_weights(g["edges"], g["pos"])
+    s = synth.init_state(g, alpha, beta)
+    pyoracle.pd_run(s, pyoracle.pd_default_params(), iters)
+    pyoracle.interpolate_mesh(g["tris"], g["pos"], s["x"], g["H"], g["W"])
+    return s
+
+
+def cpu_baseline(budget_s=12.0):
+    from flame_b200 import synth
+    from oracle import pyoracle
+    pyoracle.build()
+    frames, (W, H, V, iters) = _frames(1)
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < budget_s:
+        _cpu_frame(pyoracle, synth, frames[0], iters)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": "%d frames of config %s (%dx%d, V=%d, %d PD iters + dense projection), "
+                      "oracle C port, 1 thread, %.1f s" % (n, CFG, W, H, V, iters, dt)}
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path on the host cores: independent frames in
+    parallel, one thread per frame (each Flame instance runs step() on one thread)."""
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    from flame_b200 import synth
+    from oracle import pyoracle
+    pyoracle.build()
+    cores = os.cpu_count() or 1
+    frames, (W, H, V, iters) = _frames(min(cores, 8))
+    per_step = cores  # one frame per core per step
+    pool = ThreadPoolExecutor(cores)
+
+    def step():
+        list(pool.map(lambda i: _cpu_frame(pyoracle, synth, frames[i % len(frames)], iters),
+                      range(per_step)))
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "config D: 1920x1080, 10k vertices, 200 PD iters + dense projection",
+                   "frames_per_step": per_step},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": "%d frames per step (one per core), oracle C port of the reference "
+                                   "CPU path" % per_step},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from flame_b200 import _lib
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    B = args.batch
+    frames, (W, H, V, iters) = _frames(B, first=rank * B)
+    p = _lib.default_pd_params()
+    ctx = _lib.Context(local_rank, B)
+    for i, g in enumerate(frames):
+        ctx.graph_init(i, g["pos"], g["data_term"], g["edges"])
+        ctx.mesh_bind(i, g["tris"], H, W)
+    ctx.sync()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step(ev=None):
+        ctx.graph_reset(0, B)
+        if ev is not None:
+            ev[0].record(stream)
+        ctx.pd_run(p, iters, 0, B, args.mode)
+        if ev is not None:
+            ev[1].record(stream)
+        ctx.mesh_project(0, B, 1.0)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: device-resident inputs ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.kernel_launches()
+    e0.record(stream)
+    for k in range(args.steps):
+        step(kev[k])
+    e1.record(stream)
+    barrier()
+    launches = _lib.kernel_launches() - launches0
+    ms_total = e0.elapsed_time(e1)
+    pd_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    clocks = sampler.stop()
+    if dist is not None:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- single-frame latency (one cluster per frame, B = 1) ----
+    lat = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.graph_reset(0, 1)
+        a.record(stream)
+        ctx.pd_run(p, iters, 0, 1, args.mode)
+        b.record(stream)
+        ctx.mesh_project(0, 1, 1.0)
+        ctx.sync()
+        lat.append(a.elapsed_time(b))
+    lat_ms = float(np.median(lat))
+
+    # ---- e2e: host buffers in, host buffers out, through the public C ABI ----
+    e2e = run_e2e(args, local_rank, frames, (W, H, V, iters), barrier)
+    if dist is not None:
+        t = torch.tensor([e2e["seconds"]], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e["seconds"] = float(t.item())
+    e2e_value = world * e2e["frames"] / e2e["seconds"]
+
+    if rank == 0:
+        E = int(np.mean([g["edges"].shape[0] for g in frames]))
+        peak, peak_src = _peaks()
+        alg_bytes = 76.0 * (V + E) * iters * B  # 76 B per vertex + 76 B per edge per iteration
+        achieved = alg_bytes / (pd_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config D: 1920x1080, V=%d, E~%d, %d PD iters + dense projection; "
+                                   "%d independent frames per GPU per step" % (V, E, iters, B),
+                       "frames_per_step_per_gpu": B, "pd_mode": ["auto", "stream", "resident"][args.mode],
+                       "l2": "per-step working set %.0f MB per GPU (> 126 MB L2): inputs larger than L2"
+                             % (B * (76.0 * (V + E) / 2 + 12.0 * W * H) / 1e6),
+                       "parallelism": "frames sharded by rank, no data-path collective"},
+            "ms_per_pd_iter": pd_ms / iters / B,
+            "single_frame_pd_latency_ms": lat_ms,
+            "single_frame_ms_per_pd_iter": lat_ms / iters,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_pd_resident" if args.mode != 1 else "k_dual/primal_stream",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": pd_ms,
+                         "note": "algorithmic bytes = 76*(V+E) per PD iteration per frame; the resident kernel "
+                                 "keeps the state in shared memory, so achieved is an EFFECTIVE bandwidth "
+                                 "(DRAM traffic is far below the algorithmic bytes; see DESIGN.md)"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": e2e["h2d"],
+                    "d2h_bytes_per_step": e2e["d2h"], "frames_per_step": e2e["per_step"],
+                    "pipelines": e2e["pipelines"]},
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, local_rank, frames, dims, barrier):
+    """Per frame: graph_init + mesh_bind (H2D) -> pd_run -> mesh_project -> dense map + x (D2H).
+    `pipelines` host threads each drive their own context/stream so copies overlap compute."""
+    from concurrent.futures import ThreadPoolExecutor
+    from flame_b200 import _lib
+    W, H, V, iters = dims
+    P = args.pipelines
+    p = _lib.default_pd_params()
+    ctxs = [_lib.Context(local_rank, 1) for _ in range(P)]
+    outs = [_lib.PinnedArray((H, W)) for _ in range(P)]
+    per_step = len(frames)
+
+    def one(job):
+        k, i = job
+        g = frames[i]
+        ctx, out = ctxs[k], outs[k]
+        ctx.graph_init(0, g["pos"], g["data_term"], g["edges"])
+        ctx.mesh_bind(0, g["tris"], H, W)
+        ctx.pd_run(p, iters, 0, 1, args.mode)
+        ctx.mesh_project(0, 1, 1.0)
+        ctx.mesh_download(0, out.array)
+        x = ctx.graph_download(0, V, g["edges"].shape[0], fields=("x", "w1", "w2"))  # syncs the stream
+        return float(x["x"][0]) + float(out.array[H // 2, W // 2])
+
+    pool = ThreadPoolExecutor(P)
+
+    def worker(k, n_steps):
+        acc = 0.0
+        for s in range(n_steps):
+            for i in range(k, per_step, P):
+                acc += one((k, i))
+        return acc
+
+    def run(n_steps):
+        return sum(pool.map(lambda k: worker(k, n_steps), range(P)))
+
+    run(1)  # warm-up (allocations)
+    barrier()
+    t0 = time.perf_counter()
+    run(args.steps)
+    barrier()
+    dt = time.perf_counter() - t0
+    g = frames[0]
+    E, T = g["edges"].shape[0], g["tris"].shape[0]
+    h2d = per_step * (4 * (13 * V + 5 * E) + 4 * (3 * V + 2 + 5 * E) + 13 * T)
+    d2h = per_step * (4 * W * H + 12 * V)
+    for c in ctxs:
+        c.close()
+    return {"seconds": dt, "frames": per_step * args.steps, "h2d": h2d, "d2h": d2h,
+            "per_step": per_step, "pipelines": P}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
+    ap.add_argument("--pipelines", type=int, default=4, help="host threads / streams for the e2e leg")
+    ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 stream, 2 resident")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -87,7 +87,7 @@ static inline uint32_t part1by1(uint32_t x) {
   return x;
 }
 
-static size_t ints_total(int V, int E) { return (size_t)2 * V + 2 + (size_t)5 * E; }
+static size_t ints_total(int V, int E) { return (size_t)3 * V + 2 + (size_t)5 * E; }
 static size_t blob_bytes(int V, int E) {
   return (raw_f_total(V, E) + ints_total(V, E)) * 4 + 64;
 }
