@@ -1,0 +1,246 @@
+"""Pins the CPU oracle against every known-answer test the reference holds for this path
+(SURVEY.md §8c): test/stereo/epipolar_geometry_test.cc (all 21 cases), test/utils/image_utils_test.cc
+(bilinearInterp x4, Liang-Barsky x5, interpolateMesh), test/utils/rasterization_test.cc
+(DrawShadedTriangleBarycentric1/2 vs the reference's golden PNGs, byte-exact) — and, when the
+reference checkout was available at build time, against the reference sources compiled verbatim
+(oracle/_ref). CPU only."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from flame_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+K525 = np.array([[525, 0, 320], [0, 525, 240], [0, 0, 1]], np.float32)
+I4 = (1.0, 0.0, 0.0, 0.0)
+
+
+def aa_quat(angle, axis):
+    """Eigen::Quaternionf(Eigen::AngleAxisf(angle, axis)) as (w, x, y, z)."""
+    h = np.float32(angle) * np.float32(0.5)
+    s = np.float32(math.sin(float(h)))
+    c = np.float32(math.cos(float(h)))
+    ax = np.asarray(axis, np.float32)
+    return np.array([c, s * ax[0], s * ax[1], s * ax[2]], np.float32)
+
+
+def qrot(q, v):
+    w, x, y, z = [float(a) for a in q]
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                  [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                  [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    return R @ np.asarray(v, np.float64)
+
+
+def qconj(q):
+    return np.array([q[0], -q[1], -q[2], -q[3]], np.float32)
+
+
+def epi(oracle, K=K525):
+    return oracle.Epi(K)
+
+
+# ---------------------------------------------------------------- epipolar_geometry_test.cc:47-131
+@pytest.mark.parametrize("u_ref,axis", [((320, 240), 0), ((320, 0), 0), ((320, 240), 1), ((0, 240), 1)])
+def test_min_depth_projection_translate(oracle, u_ref, axis):
+    e = epi(oracle)
+    t = [0.0, 0.0, 0.0]
+    t[axis] = 2.0
+    e.load(I4, t)
+    m = e.min_depth_projection(u_ref)
+    assert m[axis] > K525[axis, 2] * 2
+    assert abs(m[1 - axis] - u_ref[1 - axis]) < 1e-3
+    t[axis] = -2.0
+    e.load(I4, t)
+    m = e.min_depth_projection(u_ref)
+    assert m[axis] < 0
+    assert abs(m[1 - axis] - u_ref[1 - axis]) < 1e-3
+
+
+def test_min_depth_projection_60_yaw(oracle):  # :161-196
+    q21 = aa_quat(-math.pi / 3, (0, 1, 0))
+    t21 = np.array([2, 0, 0], np.float32)
+    q12 = qconj(q21)
+    t12 = (-qrot(q12, t21)).astype(np.float32)
+    e = epi(oracle)
+    e.load(q12, t12)
+    m = e.min_depth_projection((320, 240))
+    assert abs(m[0] - 16.8910904) < 1e-4 and abs(m[1] - 240) < 1e-4
+    e.load(q21, t21)
+    m = e.min_depth_projection((320, 240))
+    assert abs(m[0] - 1049999424) < 1e-4 and abs(m[1] - 240) < 1e-4
+
+
+KREAL = np.array([[535.43310546875, 0, 320.106652814575], [0, 539.212524414062, 247.632132204719],
+                  [0, 0, 1]], np.float32)
+
+
+def test_min_depth_projection_real_data(oracle):  # :201-243
+    e = oracle.Epi(KREAL)
+    e.load((0.999138, -0.000878, 0.041493, 0.000386), (-0.221092, -0.036134, 0.084099))
+    m = e.min_depth_projection((320, 240))
+    assert abs(m[0] - -1087.525391) < 1e-2 and abs(m[1] - 15.954912) < 1e-2
+    e.load((-0.999853, 0.014856, -0.005249, -0.006822), (-0.258187, 0.040849, -0.054990))
+    m = e.min_depth_projection((320, 240))
+    assert abs(m[0] - 187.65597534179688) < 1e-1 and abs(m[1] - 278.55392456054688) < 1e-1
+
+
+def test_max_depth_projection(oracle):  # :248-311
+    e = epi(oracle)
+    e.load(I4, (0, 0, 0))
+    m = e.max_depth_projection((320, 240))
+    assert abs(m[0] - 320) < 1e-3 and abs(m[1] - 240) < 1e-3
+    e.load(aa_quat(-math.pi / 6, (0, 1, 0)), (0, 0, 0))
+    m = e.max_depth_projection((320, 240))
+    assert abs(m[0] - 16.891090393066406) < 1e-4 and abs(m[1] - 240) < 1e-4
+    e.load(aa_quat(-math.pi / 6, (1, 0, 0)), (0, 0, 0))
+    m = e.max_depth_projection((320, 240))
+    assert abs(m[0] - 320) < 1e-4 and abs(m[1] - 543.10888671875) < 1e-4
+
+
+def test_epiline(oracle):  # :313-361
+    q = aa_quat(-math.pi / 3, (0, 1, 0))
+    e = epi(oracle)
+    e.load(qconj(q), (-qrot(q, (2, 0, 0))).astype(np.float32))
+    _, ep = e.epiline((320, 240))
+    assert abs(ep[0] - 1) < 1e-4 and abs(ep[1]) < 1e-4
+    q = aa_quat(math.pi / 3, (1, 0, 0))
+    e.load(qconj(q), (-qrot(q, (0, 2, 0))).astype(np.float32))
+    _, ep = e.epiline((320, 240))
+    assert abs(ep[0]) < 1e-4 and abs(ep[1] - 1) < 1e-4
+
+
+def _two_cameras(oracle, angle, p_world):
+    """T1 = yaw `angle` at the origin, T2 = identity rotation at (1,0,0); poses are camera-to-world."""
+    T1 = np.concatenate([aa_quat(angle, (0, 1, 0)), [0, 0, 0]]).astype(np.float32)
+    T2 = np.array([1, 0, 0, 0, 1, 0, 0], np.float32)
+    T12 = oracle.se3_inv_mul(T2, T1)  # T2^-1 * T1
+    T21 = oracle.se3_inv_mul(T1, T2)
+    u1 = oracle.project_world(K525, T1[:4], T1[4:], p_world)
+    u2 = oracle.project_world(K525, T2[:4], T2[4:], p_world)
+    z1 = qrot(qconj(T1[:4]), np.asarray(p_world, np.float64) - T1[4:])[2]
+    z2 = qrot(qconj(T2[:4]), np.asarray(p_world, np.float64) - T2[4:])[2]
+    return T12, T21, u1, u2, z1, z2
+
+
+CASES = [(-math.pi / 12, (1, 0, 10)), (-math.pi / 12, (-1, 0, 10)), (math.pi / 12, (0, 1, 10)),
+         (math.pi / 12, (0, -1, 10))]
+
+
+@pytest.mark.parametrize("angle,p_world", CASES)
+def test_disparity_to_depth(oracle, angle, p_world):  # :370-560
+    T12, T21, u1, u2, z1, z2 = _two_cameras(oracle, angle, p_world)
+    e1 = epi(oracle)
+    e1.load(T12[:4], T12[4:])
+    d, u_inf, ep = e1.disparity(u1, u2)
+    assert abs(e1.disparity_to_depth(u1, u_inf, ep, d) - z1) < 1e-4 * max(1.0, abs(z1)) + 1e-4
+    e2 = epi(oracle)
+    e2.load(T21[:4], T21[4:])
+    d, u_inf, ep = e2.disparity(u2, u1)
+    assert abs(e2.disparity_to_depth(u2, u_inf, ep, d) - z2) < 1e-4 * max(1.0, abs(z2)) + 1e-4
+
+
+@pytest.mark.parametrize("angle,p_world,tol1", [(c[0], c[1], t) for c, t in zip(CASES, (1e-4, 1e-4, 1e-2, 1e-2))])
+def test_disparity_to_inverse_depth(oracle, angle, p_world, tol1):  # :570-760
+    T12, T21, u1, u2, z1, z2 = _two_cameras(oracle, angle, p_world)
+    e1 = epi(oracle)
+    e1.load(T12[:4], T12[4:])
+    d, u_inf, ep = e1.disparity(u1, u2)
+    assert abs(e1.disparity_to_idepth(u1, u_inf, ep, d) - 1.0 / z1) < tol1
+    e2 = epi(oracle)
+    e2.load(T21[:4], T21[4:])
+    d, u_inf, ep = e2.disparity(u2, u1)
+    assert abs(e2.disparity_to_idepth(u2, u_inf, ep, d) - 1.0 / z2) < 1e-4
+
+
+def test_project_round_trip(oracle):  # :773-805
+    T12, T21, u1, u2, _, _ = _two_cameras(oracle, -math.pi / 12, (1, 0, 10))
+    e = epi(oracle)
+    e.load(T21[:4], T21[4:])
+    uc = e.project(u2, 1.0 / 10.0)
+    assert abs(uc[0] - u1[0]) < 1e-4 and abs(uc[1] - u1[1]) < 1e-4
+
+
+# ---------------------------------------------------------------- image_utils_test.cc
+def test_bilinear_interp_kats(oracle):  # :150-166
+    img = np.array([[91, 210], [162, 95]], np.uint8)
+    for (x, y), want in (((0.5, 0.2), 146.1), ((0.2, 0.5), 131.70001), ((0.5, 0.5), 139.5),
+                         ((0.2, 0.2), 121.5600052)):
+        assert abs(oracle.bilinear_u8(img, x, y) - want) < 1e-5 * 10  # EXPECT_NEAR(…, 1e-5) on fp32
+    f = img.astype(np.float32)
+    assert abs(oracle.bilinear_f32(f, 0.5, 0.5) - 139.5) < 1e-5
+
+
+def test_liang_barsky_cases(oracle):  # :644-749
+    ok, c = oracle.clip_line(0, 3, 0, 3, 1, 1, 2, 2)
+    assert ok and np.allclose(c, (1, 1, 2, 2), atol=1e-6)
+    ok, c = oracle.clip_line(1.1, 3, 1.2, 3, 1, 1, 2, 2)
+    assert ok and np.allclose(c, (1.2, 1.2, 2, 2), atol=1e-6)
+    ok, c = oracle.clip_line(1, 1.5, 1, 1.25, 1, 1, 2, 2)
+    assert ok and np.allclose(c, (1, 1, 1.25, 1.25), atol=1e-6)
+    ok, c = oracle.clip_line(1.1, 1.5, 1.15, 1.25, 1, 1, 2, 2)
+    assert ok and np.allclose(c, (1.15, 1.15, 1.25, 1.25), atol=1e-6)
+    lo = np.float32(2 + 1e-3 + 1)
+    ok, _ = oracle.clip_line(lo, np.float32(640 - 2 - 1e-3 - 2), lo, np.float32(480 - 2 - 1e-3 - 2),
+                             -3.40414, 1.95745, -3.26889, 2.17682)
+    assert not ok
+
+
+def test_interpolate_mesh_kat(oracle):  # :754-783
+    tris = np.array([[0, 1, 2]], np.int32)
+    pos = np.array([[10, 10], [20, 10], [10, 20]], np.float32)
+    vals = np.array([1, 2, 3], np.float32)
+    for use_ref in ([False, True] if oracle.have_ref() else [False]):
+        img = oracle.interpolate_mesh(tris, pos, vals, 40, 40, use_ref=use_ref)
+        assert abs(img[10, 10] - 1) < 1e-3 and abs(img[10, 20] - 2) < 1e-3 and abs(img[20, 10] - 3) < 1e-3
+        assert abs(img[15, 15] - 2.5) < 1e-3
+
+
+# ---------------------------------------------------------------- rasterization_test.cc:514-598
+def _normalize_u8(img):
+    mn, mx = float(img.min()), float(img.max())
+    return np.rint((img - mn) * (255.0 / (mx - mn))).astype(np.uint8)  # cv::normalize MINMAX + convertTo
+
+
+@pytest.mark.parametrize("k,pts,vals", [(1, ((150, 100), (100, 200), (200, 300)), (0.0, 1.0, 0.0)),
+                                         (2, ((150, 100), (100, 300), (200, 200)), (0.0, 0.0, 1.0))])
+def test_rasteriser_golden_png(oracle, k, pts, vals):
+    cv2 = pytest.importorskip("cv2")
+    truth = cv2.imread(os.path.join(GOLDEN, "RasterizationTest_DrawShadedTriangleBarycentric%d.png" % k),
+                       cv2.IMREAD_GRAYSCALE)
+    assert truth is not None and truth.shape == (480, 640)
+    for use_ref in ([False, True] if oracle.have_ref() else [False]):
+        img = np.zeros((480, 640), np.float32)
+        oracle.draw_triangle(img, pts[0], pts[1], pts[2], *vals, use_ref=use_ref)
+        assert np.array_equal(_normalize_u8(img), truth)  # byte-exact, as cvCompare
+
+
+# ---------------------------------------------------------------- oracle vs reference-compiled-verbatim
+def _need_ref(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference at build time)")
+
+
+@pytest.mark.parametrize("cfg", ["A", "B"])
+def test_oracle_raster_equals_reference_verbatim(oracle, cfg):
+    _need_ref(oracle)
+    g = synth.config_graph(cfg)
+    a = oracle.interpolate_mesh(g["tris"], g["pos"], g["data_term"], g["H"], g["W"])
+    b = oracle.interpolate_mesh(g["tris"], g["pos"], g["data_term"], g["H"], g["W"], use_ref=True)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    m = ~np.isnan(a)
+    assert np.array_equal(a[m].view(np.uint32), b[m].view(np.uint32))
+
+
+def test_golden_graph_fixtures_match_reference_triangle(oracle):
+    """The committed index arrays are what the reference's own Triangle returns today (bit-exact)."""
+    _need_ref(oracle)
+    for name, (W, H, V, _) in synth.CONFIGS.items():
+        z = np.load(os.path.join(GOLDEN, "graph_%dx%d_v%d_s1.npz" % (W, H, V)))
+        assert np.array_equal(z["pos"], synth.make_vertices(W, H, V, seed=1))
+        tris, edges, _ = oracle.ref_delaunay(z["pos"])
+        assert np.array_equal(tris, z["tris"]) and np.array_equal(edges, z["edges"])
+        if name == "B":
+            break  # A and B are enough for the CPU suite's time budget
