@@ -330,7 +330,8 @@ struct EpiGeo {
     float epx = zx - *ix, epy = zy - *iy;
     const float norm2 = epx * epx + epy * epy;
     if ((double)norm2 > 1e-10) {
-      const float inv_norm = 1.0f / sqrt_rn(norm2);
+      // `1.0f / sqrt(norm2)` in the reference: ::sqrt(double) -> the quotient is formed in double
+      const float inv_norm = (float)(1.0 / sqrt((double)norm2));
       epx *= inv_norm;
       epy *= inv_norm;
     } else {
@@ -345,7 +346,7 @@ struct EpiGeo {
     const float rx = -K[0] * t_cmp_to_ref[0] + t_cmp_to_ref[2] * (ux - K[2]);
     const float ry = -K[4] * t_cmp_to_ref[1] + t_cmp_to_ref[2] * (uy - K[5]);
     const float n2 = rx * rx + ry * ry;
-    const float inv = 1.0f / sqrt_rn(n2);
+    const float inv = (float)(1.0 / sqrt((double)n2));  // :325, double quotient as above
     *ex = rx * inv;
     *ey = ry * inv;
   }

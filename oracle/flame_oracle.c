@@ -549,7 +549,9 @@ void oracle_epigeo_epiline(const oracle_epigeo* g, float ux, float uy, float* ix
   float epx = zx - *ix, epy = zy - *iy;
   float norm2 = epx * epx + epy * epy;
   if ((double)norm2 > 1e-10) {
-    float inv_norm = 1.0f / (float)sqrt((double)norm2);
+    /* `1.0f / sqrt(norm2)`: unqualified sqrt on a float resolves to ::sqrt(double), so the quotient is
+     * formed in double and rounded once on assignment (verified against oracle/_ref) */
+    float inv_norm = (float)(1.0 / sqrt((double)norm2));
     epx *= inv_norm;
     epy *= inv_norm;
   } else {
@@ -566,7 +568,7 @@ void oracle_epigeo_reference_epiline(const oracle_epigeo* g, float ux, float uy,
   float rx = -g->K[0] * g->t_cmp_to_ref[0] + g->t_cmp_to_ref[2] * (ux - g->K[2]);
   float ry = -g->K[4] * g->t_cmp_to_ref[1] + g->t_cmp_to_ref[2] * (uy - g->K[5]);
   float n2 = rx * rx + ry * ry;
-  float inv = 1.0f / (float)sqrt((double)n2);
+  float inv = (float)(1.0 / sqrt((double)n2)); /* :325, double quotient as above */
   *ex = rx * inv;
   *ey = ry * inv;
 }

@@ -367,3 +367,81 @@ def update_feature_idepths(params, K, Kinv, width, height, pad, frames, fnew, cu
         C.byref(params), _f(K), _f(Kinv), width, height, pad, arr, len(frames), fnew, curr_pf,
         feats.ctypes.data_as(C.c_void_p), feats.shape[0], diag.ctypes.data_as(C.c_void_p))
     return int(n), diag
+
+
+# ---------------------------------------------------------------------------- reference (verbatim) arms
+class _RefGraph(C.Structure):
+    _fields_ = [("V", C.c_int32), ("E", C.c_int32), ("pos", f32p),
+                ("x", f32p), ("w1", f32p), ("w2", f32p),
+                ("x_bar", f32p), ("w1_bar", f32p), ("w2_bar", f32p),
+                ("x_prev", f32p), ("w1_prev", f32p), ("w2_prev", f32p),
+                ("data_term", f32p), ("data_weight", f32p), ("edges", i32p),
+                ("alpha", f32p), ("beta", f32p), ("q1", f32p), ("q2", f32p), ("q3", f32p)]
+
+
+def _ref_graph_struct(g):
+    s = _RefGraph()
+    s.V = g["pos"].shape[0]
+    s.E = g["edges"].shape[0]
+    s.pos = _f(g["pos"])
+    s.edges = _i(g["edges"])
+    for k in GRAPH_STATE + ("data_term", "data_weight", "alpha", "beta"):
+        setattr(s, k, _f(g[k]))
+    return s
+
+
+def _params6(p):
+    return np.array([p.data_factor, p.step_x, p.step_q, p.theta, p.x_min, p.x_max], np.float32)
+
+
+def ref_pd_run(g, params, n_iters):
+    """nltgv2_l1_graph_regularizer.cc compiled verbatim (Boost.Graph container shimmed): step() x n."""
+    s = _ref_graph_struct(g)
+    p6 = _params6(params)
+    ref().ref_pd_run(_f(p6), C.byref(s), C.c_int(n_iters))
+    return g
+
+
+def ref_pd_costs(g, params):
+    s = _ref_graph_struct(g)
+    p6 = _params6(params)
+    a, b = C.c_float(), C.c_float()
+    ref().ref_pd_costs(_f(p6), C.byref(s), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def ref_update_feature_idepths(params, K, Kinv, width, height, pad, frames, fnew, curr_pf, feats):
+    """The reference's stereo sources compiled verbatim (Eigen/Sophus/OpenCV types shimmed)."""
+    K = np.ascontiguousarray(K, np.float32).ravel()
+    Kinv = np.ascontiguousarray(Kinv, np.float32).ravel()
+    arr = (Frame * len(frames))()
+    keep = []
+    for i, fr in enumerate(frames):
+        pose = np.ascontiguousarray(fr["pose"], np.float32)
+        for k in range(7):
+            arr[i].pose[k] = pose[k]
+        img = np.ascontiguousarray(fr["img_pad"], np.uint8)
+        gx = np.ascontiguousarray(fr["gradx_pad"], np.float32)
+        gy = np.ascontiguousarray(fr["grady_pad"], np.float32)
+        keep += [img, gx, gy]
+        arr[i].img_pad = _u8(img)
+        arr[i].gradx_pad = _f(gx)
+        arr[i].grady_pad = _f(gy)
+    diag = np.zeros(feats.shape[0], DIAG_DTYPE)
+    n = ref().ref_update_feature_idepths(
+        C.byref(params), _f(K), _f(Kinv), width, height, pad, arr, len(frames), fnew, curr_pf,
+        feats.ctypes.data_as(C.c_void_p), feats.shape[0], diag.ctypes.data_as(C.c_void_p))
+    return int(n), diag
+
+
+def ref_epigeo_query(K, Kinv, q_wxyz, t, u, idepth):
+    """min/max depth projection, epiline (u_inf, epi), project(u, idepth), referenceEpiline."""
+    K = np.ascontiguousarray(K, np.float32).ravel()
+    Kinv = np.ascontiguousarray(Kinv, np.float32).ravel()
+    q = np.ascontiguousarray(q_wxyz, np.float32)
+    t = np.ascontiguousarray(t, np.float32)
+    out = np.zeros(12, np.float32)
+    fn = ref().ref_epigeo_query
+    fn.argtypes = [f32p, f32p, f32p, f32p, C.c_float, C.c_float, C.c_float, f32p]
+    fn(_f(K), _f(Kinv), _f(q), _f(t), u[0], u[1], idepth, _f(out))
+    return out

@@ -6,12 +6,17 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
 
+typedef unsigned char uchar;
+
 namespace cv {
+
+typedef unsigned char uchar;
 
 template <typename T> static inline T saturate_cast(float v) { return static_cast<T>(v); }
 template <> inline int saturate_cast<int>(float v) { return static_cast<int>(lrintf(v)); }
@@ -139,6 +144,12 @@ static inline size_t shim_elem_size(int type) {
   }
 }
 
+struct Size {
+  int width, height;
+  Size() : width(0), height(0) {}
+  Size(int w, int h) : width(w), height(h) {}
+};
+
 // Continuous row-major matrix header (optionally owning).
 struct Mat {
   uint8_t* data;
@@ -162,6 +173,8 @@ struct Mat {
     store.reset(new std::vector<uint8_t>(step * r + 64, 0));
     data = store->data();
   }
+  Size size() const { return Size(cols, rows); }
+  void create(Size sz, int type) { create(sz.height, sz.width, type); }
   int type() const { return type_; }
   int channels() const { return type_ == 16 ? 3 : 1; }
   bool isContinuous() const { return true; }
@@ -191,6 +204,7 @@ struct Mat_ : public Mat {
   Mat_(int r, int c, T* ext) : Mat(r, c, DataType<T>::type, ext) {}
   Mat_(const Mat& m) : Mat(m) {}
   void create(int r, int c) { Mat::create(r, c, DataType<T>::type); }
+  void create(Size sz) { Mat::create(sz.height, sz.width, DataType<T>::type); }
   T& operator()(int y, int x) { return this->template at<T>(y, x); }
   const T& operator()(int y, int x) const { return this->template at<T>(y, x); }
   T& operator()(int i) { return reinterpret_cast<T*>(data)[i]; }
@@ -218,6 +232,7 @@ struct LineIterator {
   }
   uint8_t* operator*() { return img_->data + p_.y * img_->step + p_.x * img_->elemSize(); }
   LineIterator operator++(int) { return *this; }
+  LineIterator& operator++() { return *this; }
   Point pos() const { return p_; }
 };
 

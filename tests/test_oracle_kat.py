@@ -244,3 +244,63 @@ def test_golden_graph_fixtures_match_reference_triangle(oracle):
         assert np.array_equal(tris, z["tris"]) and np.array_equal(edges, z["edges"])
         if name == "B":
             break  # A and B are enough for the CPU suite's time budget
+
+
+@pytest.mark.parametrize("cfg", ["A", "B"])
+def test_oracle_pd_equals_reference_verbatim(oracle, cfg):
+    """nltgv2_l1_graph_regularizer.cc compiled verbatim (Boost.Graph container shimmed) vs the flat
+    restatement: every state array bit-identical after the config's iteration count; costs equal."""
+    _need_ref(oracle)
+    g = synth.config_graph(cfg)
+    alpha, beta = oracle.edge_weights(g["edges"], g["pos"])
+    rng = np.random.default_rng(1)
+    g["data_weight"] = rng.uniform(0.5, 2.0, g["pos"].shape[0]).astype(np.float32)
+    a = synth.init_state(g, alpha, beta)
+    b = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in a.items()}
+    p = oracle.pd_default_params()
+    oracle.pd_run(a, p, g["pd_iters"])
+    oracle.ref_pd_run(b, p, g["pd_iters"])
+    for k in oracle.GRAPH_STATE:
+        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+    assert oracle.pd_costs(a, p) == oracle.ref_pd_costs(b, p)
+
+
+@pytest.mark.parametrize("t_world,yaw", [((0.10, 0.02, 0.01), 1.0), ((0.05, 0.01, 0.45), 0.5),
+                                         ((-0.08, 0.03, 0.0), -0.7), ((0.1, 0.02, -0.05), 1.0)])
+def test_oracle_stereo_equals_reference_verbatim(oracle, t_world, yaw):
+    """stereo/inverse_depth_filter.cc, inverse_depth_meas_model.cc, line_stereo.h, epipolar_geometry.h
+    compiled verbatim (types shimmed) vs the C restatement, per feature, bit-identical — covers
+    t_z > 0, t_z == 0, t_z < 0 and the re-parenting path."""
+    _need_ref(oracle)
+    W, H, V, _ = synth.CONFIGS["A"]
+    K, Kinv, frames = synth.make_stereo_pair(W, H, t_world=t_world, yaw_deg=yaw)
+    g = synth.config_graph("A")
+    feats = synth.make_features(g["pos"], W, H, rel_sigma=0.1)
+    p = oracle.track_default_params()
+    f1, f2 = feats.copy(), feats.copy()
+    n1, d1 = oracle.update_feature_idepths(p, K, Kinv, W, H, synth.PAD, frames, 1, 0, f1)
+    n2, d2 = oracle.ref_update_feature_idepths(p, K, Kinv, W, H, synth.PAD, frames, 1, 0, f2)
+    assert n1 == n2 and n1 > 0 and np.array_equal(d1["stage"], d2["stage"])
+    assert f1.tobytes() == f2.tobytes()
+    for k in ("flow_x", "flow_y", "mu_meas", "var_meas"):
+        m = ~np.isnan(d1[k])
+        assert np.array_equal(np.isnan(d1[k]), np.isnan(d2[k]))
+        assert np.array_equal(d1[k][m].view(np.uint32), d2[k][m].view(np.uint32)), k
+
+
+def test_epigeo_oracle_equals_reference_verbatim(oracle):
+    _need_ref(oracle)
+    K, Kinv = synth.camera(640, 480)
+    rng = np.random.default_rng(0)
+    for q, t in ((aa_quat(0.02, (0, 1, 0)), (0.1, 0.02, 0.01)), (aa_quat(-0.3, (1, 0, 0)), (0.2, -0.1, -0.3)),
+                 (np.array(I4, np.float32), (-0.5, 0.0, 0.0))):
+        e = oracle.Epi(K, Kinv)
+        e.load(q, t)
+        for _ in range(200):
+            u = (float(np.float32(rng.uniform(5, 635))), float(np.float32(rng.uniform(5, 475))))
+            idp = float(np.float32(rng.uniform(0.05, 1.5)))
+            r = oracle.ref_epigeo_query(K, Kinv, q, t, u, idp)
+            (ui, ep) = e.epiline(u)
+            o = np.array([*e.min_depth_projection(u), *e.max_depth_projection(u), *ui, *ep,
+                          *e.project(u, idp), *e.reference_epiline(u)], np.float32)
+            assert np.array_equal(o.view(np.uint32), r.view(np.uint32))
