@@ -27,8 +27,9 @@ void stereo_destroy(void* state);
 struct Slot {
   GraphDev g{};
   bool loaded = false;
-  // one device blob: [raw floats (13V + 5E) | ints: vperm V | eperm E | ends 2E | inc_off V+1 |
-  //                   inc 2E | esrc_off V+1], mirrored by one pinned host blob -> single H2D.
+  // one device blob: [raw floats (13V + 5E) | ints: vperm V | deg V | koff n_chunks*(max_deg+1) |
+  //                   chunk_base n_chunks+1 | inc_nbr 2E | inc_edge 2E | edges 2E],
+  // mirrored by one pinned host blob -> single H2D.
   unsigned char* d_blob = nullptr;
   size_t d_blob_cap = 0;
   unsigned char* h_blob = nullptr;
@@ -37,7 +38,7 @@ struct Slot {
   int capV = 0, capE = 0;
   float* d_pos = nullptr;           // 2V caller order (kept for the dense projection)
   float* d_values = nullptr;        // V caller order
-  std::vector<int> h_esrc_off, h_inc_off;  // host copies for resident planning
+  ResidentPlan plan{};              // chosen at upload (cluster == 0 -> streaming only)
   // mesh
   MeshDev m{};
   int capT = 0;
@@ -62,7 +63,7 @@ struct flame_b200_ctx {
   void* stereo = nullptr;
   // host scratch for graph prep
   std::vector<uint32_t> keys, keys2;
-  std::vector<int> idx, idx2, vinv, einv, cursor;
+  std::vector<int> idx, idx2, vinv, cursor, degv, order, koff_tmp;
 };
 
 namespace fb {
@@ -87,15 +88,25 @@ static inline uint32_t part1by1(uint32_t x) {
   return x;
 }
 
-static size_t ints_total(int V, int E) { return (size_t)3 * V + 2 + (size_t)5 * E; }
-static size_t blob_bytes(int V, int E) {
-  return (raw_f_total(V, E) + ints_total(V, E)) * 4 + 64;
+struct PrepOut {
+  int Vc = 0, n_chunks = 0, max_deg = 0;
+  ResidentPlan plan{};
+};
+
+static size_t ints_total(int V, int E, int n_chunks, int max_deg) {
+  return (size_t)2 * V + (size_t)n_chunks * (max_deg + 1) + (size_t)n_chunks + 1 + (size_t)6 * E;
+}
+static size_t blob_bytes(int V, int E, int n_chunks, int max_deg) {
+  return (raw_f_total(V, E) + ints_total(V, E, n_chunks, max_deg)) * 4 + 256;
 }
 
-// Spatial (Morton) vertex order, edges grouped by internal source vertex, per-vertex incidence
-// lists in ascending ORIGINAL edge id. O(V + E), deterministic.
-static int host_prep(flame_b200_ctx* c, int V, int E, const float* pos, const int32_t* edges,
-                     int* vperm, int* eperm, int* ends, int* inc_off, int* inc, int* esrc_off) {
+// Internal order + private incidence layout (see GraphDev). O(V + E), deterministic.
+//  1. Morton (Z-curve) order of the vertices -> spatially compact chunks of Vc vertices;
+//  2. cluster size C / chunk width Vc from the shared-memory footprint (0 -> streaming chunks);
+//  3. stable sort by descending degree inside each chunk (uniform warps);
+//  4. incidence slots in ascending ORIGINAL edge id per vertex (the reference's summation order).
+static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const int32_t* edges,
+                     PrepOut* out) {
   for (int e = 0; e < 2 * E; ++e)
     if (edges[e] < 0 || edges[e] >= V) {
       set_error("graph_upload: edge endpoint out of range");
@@ -122,12 +133,11 @@ static int host_prep(flame_b200_ctx* c, int V, int E, const float* pos, const in
     c->keys[v] = part1by1(qx) | (part1by1(qy) << 1);
     c->idx[v] = v;
   }
-  // LSD radix sort, 4 x 8 bits, stable
   uint32_t* ka = c->keys.data();
   uint32_t* kb = c->keys2.data();
   int* ia = c->idx.data();
   int* ib = c->idx2.data();
-  for (int pass = 0; pass < 4; ++pass) {
+  for (int pass = 0; pass < 4; ++pass) {  // LSD radix sort, 4 x 8 bits, stable
     size_t cnt[257] = {0};
     const int sh = 8 * pass;
     for (int v = 0; v < V; ++v) cnt[((ka[v] >> sh) & 255u) + 1]++;
@@ -140,39 +150,125 @@ static int host_prep(flame_b200_ctx* c, int V, int E, const float* pos, const in
     std::swap(ka, kb);
     std::swap(ia, ib);
   }
-  c->vinv.resize(V);
-  for (int i = 0; i < V; ++i) {
-    vperm[i] = ia[i];
-    c->vinv[ia[i]] = i;
+  c->order.assign(ia, ia + V);
+  const int* morton = c->order.data();  // morton[i] = caller vertex at Morton position i
+
+  // degrees (caller index)
+  c->degv.assign(V, 0);
+  for (int e = 0; e < 2 * E; ++e) c->degv[edges[e]]++;
+  int max_deg = 0;
+  for (int v = 0; v < V; ++v) max_deg = std::max(max_deg, c->degv[v]);
+
+  // 2. plan
+  int forced = 0, thr_env = 0;
+  if (const char* sv = getenv("FLAME_B200_CLUSTER")) forced = atoi(sv);
+  if (const char* sv = getenv("FLAME_B200_THREADS")) thr_env = atoi(sv);
+  ResidentPlan plan{};
+  if (V > 0 && V < (1 << 20) && max_deg <= FB_RESIDENT_MAX_DEG) {
+    ResidentPlan fallback{};
+    for (int C = 1; C <= 16; C *= 2) {
+      if (forced && C != forced) continue;
+      const int Vc = (V + C - 1) / C;
+      int maxInc = 0;
+      for (int k = 0; k < C; ++k) {
+        int inc = 0;
+        for (int i = std::min(k * Vc, V); i < std::min((k + 1) * Vc, V); ++i) inc += c->degv[morton[i]];
+        maxInc = std::max(maxInc, inc);
+      }
+      const size_t smem = pd_resident_smem(Vc, std::max(maxInc, 1), max_deg);
+      if (smem > 227 * 1024) continue;
+      ResidentPlan pl{};
+      pl.cluster = C;
+      pl.Vc = Vc;
+      pl.maxInc = std::max(maxInc, 1);
+      pl.max_deg = max_deg;
+      pl.smem_bytes = smem;
+      pl.threads = thr_env ? thr_env : std::min(1024, (Vc + 31) / 32 * 32);
+      if (fallback.cluster == 0) fallback = pl;
+      if (Vc <= 1024 || forced) {
+        plan = pl;
+        break;
+      }
+    }
+    if (plan.cluster == 0) plan = fallback;
   }
-  // 2. edges grouped by internal source (stable in original id)
-  for (int v = 0; v <= V; ++v) esrc_off[v] = 0;
-  for (int o = 0; o < E; ++o) esrc_off[c->vinv[edges[2 * o]] + 1]++;
-  for (int v = 0; v < V; ++v) esrc_off[v + 1] += esrc_off[v];
-  c->cursor.assign(esrc_off, esrc_off + V);
-  c->einv.resize(E);
-  for (int o = 0; o < E; ++o) {
-    const int s = c->vinv[edges[2 * o]], d = c->vinv[edges[2 * o + 1]];
-    const int p = c->cursor[s]++;
-    eperm[p] = o;
-    ends[2 * p] = s;
-    ends[2 * p + 1] = d;
-    c->einv[o] = p;
-  }
-  // 3. incidence lists, ascending original edge id
-  for (int v = 0; v <= V; ++v) inc_off[v] = 0;
-  for (int o = 0; o < E; ++o) {
-    inc_off[c->vinv[edges[2 * o]] + 1]++;
-    inc_off[c->vinv[edges[2 * o + 1]] + 1]++;
-  }
-  for (int v = 0; v < V; ++v) inc_off[v + 1] += inc_off[v];
-  c->cursor.assign(inc_off, inc_off + V);
-  for (int o = 0; o < E; ++o) {
-    const int s = c->vinv[edges[2 * o]], d = c->vinv[edges[2 * o + 1]];
-    inc[c->cursor[s]++] = (c->einv[o] << 1);
-    inc[c->cursor[d]++] = (c->einv[o] << 1) | 1;
-  }
+  const int Vc = plan.cluster ? plan.Vc : std::min(std::max(V, 1), 1024);
+  const int n_chunks = V > 0 ? (V + Vc - 1) / Vc : 0;
+  out->Vc = Vc;
+  out->n_chunks = n_chunks;
+  out->max_deg = max_deg;
+  out->plan = plan;
+
   return 0;
+}
+
+static void prep_fill(flame_b200_ctx* c, int V, int E, const int32_t* edges, const PrepOut& pr,
+                      int* ints, int** p_vperm, int** p_deg, int** p_koff, int** p_chunk_base,
+                      int** p_inc_nbr, int** p_inc_edge, int** p_edges) {
+  const int Vc = pr.Vc, n_chunks = pr.n_chunks, max_deg = pr.max_deg;
+  const int* morton = c->order.data();
+  // blob int regions
+  int* vperm = ints;
+  int* deg = vperm + V;
+  int* koff = deg + V;
+  int* chunk_base = koff + (size_t)n_chunks * (max_deg + 1);
+  int* inc_nbr = chunk_base + n_chunks + 1;
+  int* inc_edge = inc_nbr + 2 * (size_t)E;
+  int* edges_out = inc_edge + 2 * (size_t)E;
+  *p_vperm = vperm; *p_deg = deg; *p_koff = koff; *p_chunk_base = chunk_base;
+  *p_inc_nbr = inc_nbr; *p_inc_edge = inc_edge; *p_edges = edges_out;
+  std::memcpy(edges_out, edges, (size_t)2 * E * sizeof(int));
+
+  // 3. per chunk: stable counting sort by DESCENDING degree; koff; chunk_base
+  c->vinv.resize(V);
+  c->koff_tmp.assign(2 * (size_t)(max_deg + 2), 0);
+  int* cnt = c->koff_tmp.data();         // cnt[d]   = #vertices of degree d in the chunk
+  int* start = cnt + (max_deg + 2);      // start[d] = #vertices of degree > d (block start of d)
+  chunk_base[0] = 0;
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int a = ch * Vc, b = std::min(a + Vc, V);
+    std::fill(cnt, cnt + max_deg + 2, 0);
+    for (int i = a; i < b; ++i) cnt[c->degv[morton[i]]]++;
+    int run = 0;
+    for (int d = max_deg; d >= 0; --d) {
+      start[d] = run;
+      run += cnt[d];
+    }
+    // incidence k of a vertex exists iff deg > k; those vertices are the first start[k] of the chunk
+    int* ko = koff + (size_t)ch * (max_deg + 1);
+    int tot = 0;
+    for (int k = 0; k <= max_deg; ++k) {
+      ko[k] = tot;
+      tot += start[k];
+    }
+    chunk_base[ch + 1] = chunk_base[ch] + ko[max_deg];
+    for (int d = 0; d <= max_deg; ++d) cnt[d] = start[d];  // write cursors
+    for (int i = a; i < b; ++i) {
+      const int o = morton[i];
+      const int dst = a + cnt[c->degv[o]]++;
+      vperm[dst] = o;
+      c->vinv[o] = dst;
+      deg[dst] = c->degv[o];
+    }
+  }
+
+  // 4. incidences in ascending original edge id
+  c->cursor.assign(V, 0);  // next k per internal vertex
+  for (int o = 0; o < E; ++o) {
+    const int s = c->vinv[edges[2 * o]], d = c->vinv[edges[2 * o + 1]];
+    {
+      const int ch = s / Vc, i = s - ch * Vc, k = c->cursor[s]++;
+      const int slot = chunk_base[ch] + koff[(size_t)ch * (max_deg + 1) + k] + i;
+      inc_nbr[slot] = (d << 1);
+      inc_edge[slot] = o;
+    }
+    {
+      const int ch = d / Vc, i = d - ch * Vc, k = c->cursor[d]++;
+      const int slot = chunk_base[ch] + koff[(size_t)ch * (max_deg + 1) + k] + i;
+      inc_nbr[slot] = (s << 1) | 1;
+      inc_edge[slot] = o;
+    }
+  }
 }
 
 static int check_slot(flame_b200_ctx* c, int slot, int n = 1) {
@@ -197,8 +293,7 @@ static int wait_blob(Slot& s) {
   return 0;
 }
 
-static int ensure_blob(Slot& s, int V, int E) {
-  const size_t need = blob_bytes(V, E);
+static int ensure_blob(Slot& s, size_t need) {
   if (need > s.d_blob_cap) {
     if (s.d_blob) FB_CUDA(cudaFree(s.d_blob));
     s.d_blob = nullptr;
@@ -220,11 +315,12 @@ static int ensure_blob(Slot& s, int V, int E) {
 static int ensure_graph(Slot& s, int V, int E) {
   if (V > s.capV) {
     const int n = std::max(V, s.capV + s.capV / 2);
-    for (void* p : {(void*)s.g.vprim, (void*)s.g.vbar, (void*)s.g.vprev, (void*)s.g.vwt,
-                    (void*)s.d_pos, (void*)s.d_values})
+    for (void* p : {(void*)s.g.vprim, (void*)s.g.vbar, (void*)s.g.vbar2, (void*)s.g.vprev,
+                    (void*)s.g.vwt, (void*)s.d_pos, (void*)s.d_values})
       if (p) FB_CUDA(cudaFree(p));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.vprim), (size_t)n * sizeof(float4)));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.vbar), (size_t)n * sizeof(float4)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.vbar2), (size_t)n * sizeof(float4)));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.vprev), (size_t)n * sizeof(float4)));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.vwt), (size_t)n * sizeof(float)));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_pos), (size_t)n * 2 * sizeof(float)));
@@ -233,8 +329,10 @@ static int ensure_graph(Slot& s, int V, int E) {
   }
   if (E > s.capE) {
     const int n = std::max(E, s.capE + s.capE / 2);
-    if (s.g.erec) FB_CUDA(cudaFree(s.g.erec));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.erec), (size_t)n * sizeof(EdgeRec)));
+    if (s.g.inc_q) FB_CUDA(cudaFree(s.g.inc_q));
+    if (s.g.inc_s) FB_CUDA(cudaFree(s.g.inc_s));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.inc_q), (size_t)2 * n * sizeof(float4)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.inc_s), (size_t)2 * n * sizeof(float4)));
     s.capE = n;
   }
   return 0;
@@ -345,8 +443,9 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& s : c->slots) {
-    for (void* p : {(void*)s.g.vprim, (void*)s.g.vbar, (void*)s.g.vprev, (void*)s.g.vwt,
-                    (void*)s.g.erec, (void*)s.d_blob, (void*)s.d_pos, (void*)s.d_values,
+    for (void* p : {(void*)s.g.vprim, (void*)s.g.vbar, (void*)s.g.vbar2, (void*)s.g.vprev,
+                    (void*)s.g.vwt, (void*)s.g.inc_q, (void*)s.g.inc_s, (void*)s.d_blob,
+                    (void*)s.d_pos, (void*)s.d_values,
                     (void*)s.m.tris, (void*)s.m.tri_ok, (void*)s.m.img, (void*)s.m.win,
                     (void*)s.d_mpos, (void*)s.d_mvalues})
       if (p) cudaFree(p);
@@ -391,23 +490,18 @@ int flame_b200_graph_upload(flame_b200_ctx* c, int slot, const flame_b200_graph_
   if (int rc = use_device(c)) return rc;
   Slot& s = c->slots[slot];
   const int V = g->V, E = g->E;
+  PrepOut prep;
+  if (int rc = prep_plan(c, V, E, g->pos, g->edges, &prep)) return rc;
   if (int rc = wait_blob(s)) return rc;
-  if (int rc = ensure_blob(s, V, E)) return rc;
+  if (int rc = ensure_blob(s, blob_bytes(V, E, prep.n_chunks, prep.max_deg))) return rc;
   if (int rc = ensure_graph(s, V, E)) return rc;
 
   float* hf = reinterpret_cast<float*>(s.h_blob);
   int* hi = reinterpret_cast<int*>(hf + raw_f_total(V, E));
-  int* h_vperm = hi;
-  int* h_eperm = h_vperm + V;
-  int* h_ends = h_eperm + E;
-  int* h_inc_off = h_ends + 2 * (size_t)E;
-  int* h_inc = h_inc_off + V + 1;
-  int* h_esrc_off = h_inc + 2 * (size_t)E;
-  if (int rc = host_prep(c, V, E, g->pos, g->edges, h_vperm, h_eperm, h_ends, h_inc_off, h_inc,
-                         h_esrc_off))
-    return rc;
-  s.h_esrc_off.assign(h_esrc_off, h_esrc_off + V + 1);
-  s.h_inc_off.assign(h_inc_off, h_inc_off + V + 1);
+  int *h_vperm, *h_deg, *h_koff, *h_chunk_base, *h_inc_nbr, *h_inc_edge, *h_edges;
+  prep_fill(c, V, E, g->edges, prep, hi, &h_vperm, &h_deg, &h_koff, &h_chunk_base, &h_inc_nbr,
+            &h_inc_edge, &h_edges);
+  s.plan = prep.plan;
 
   std::memcpy(hf + raw_f_offset(RF_POS, V, E), g->pos, (size_t)2 * V * sizeof(float));
   fill_or_copy(hf + raw_f_offset(RF_X, V, E), g->x, V, 0.0f);
@@ -427,23 +521,30 @@ int flame_b200_graph_upload(flame_b200_ctx* c, int slot, const flame_b200_graph_
   fill_or_copy(hf + raw_f_offset(RF_Q2, V, E), g->q2, E, 0.0f);
   fill_or_copy(hf + raw_f_offset(RF_Q3, V, E), g->q3, E, 0.0f);
 
-  const size_t bytes = (raw_f_total(V, E) + ints_total(V, E)) * 4;
+  const size_t bytes = (raw_f_total(V, E) + ints_total(V, E, prep.n_chunks, prep.max_deg)) * 4;
+  if (bytes > s.d_blob_cap || bytes > s.h_blob_cap) {
+    set_error("internal: staging blob too small");
+    return FLAME_B200_ENOMEM;
+  }
   FB_CUDA(cudaMemcpyAsync(s.d_blob, s.h_blob, bytes, cudaMemcpyHostToDevice, c->stream));
   FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
   int* di = reinterpret_cast<int*>(s.d_raw() + raw_f_total(V, E));
   s.g.V = V;
   s.g.E = E;
-  s.g.vperm = di;
-  s.g.eperm = di + V;
-  s.g.ends = reinterpret_cast<int2*>(di + V + E);
-  s.g.inc_off = di + V + E + 2 * (size_t)E;
-  s.g.inc = s.g.inc_off + V + 1;
-  s.g.esrc_off = s.g.inc + 2 * (size_t)E;
-  // int offset of `ends` is 14V + 6E (even) and the blob is 256-byte aligned: int2 loads are aligned
+  s.g.Vc = prep.Vc;
+  s.g.n_chunks = prep.n_chunks;
+  s.g.max_deg = prep.max_deg;
+  s.g.vperm = di + (h_vperm - hi);
+  s.g.deg = di + (h_deg - hi);
+  s.g.koff = di + (h_koff - hi);
+  s.g.chunk_base = di + (h_chunk_base - hi);
+  s.g.inc_nbr = di + (h_inc_nbr - hi);
+  s.g.inc_edge = di + (h_inc_edge - hi);
+  s.g.edges = di + (h_edges - hi);
   if (V > 0)
     FB_CUDA(cudaMemcpyAsync(s.d_pos, s.d_raw(), (size_t)2 * V * sizeof(float),
                             cudaMemcpyDeviceToDevice, c->stream));
-  if (int rc = pd_pack(c->stream, s.g, s.d_raw(), g->alpha == nullptr, g->beta == nullptr)) return rc;
+  if (int rc = pd_pack(c->stream, s.g, s.d_raw(), g->alpha == nullptr)) return rc;
   s.loaded = true;
   return publish_graph(c, slot);
 }
@@ -543,55 +644,39 @@ int flame_b200_pd_run(flame_b200_ctx* c, int slot0, int n_slots, const flame_b20
     return FLAME_B200_EINVAL;
   }
   if (int rc = use_device(c)) return rc;
-  int maxV = 0, maxE = 0;
+  int maxV = 0, max_chunks = 0, maxVc = 0;
+  ResidentPlan plan{};
+  bool fits = true;
   for (int i = slot0; i < slot0 + n_slots; ++i) {
-    if (!c->slots[i].loaded) {
+    const Slot& s = c->slots[i];
+    if (!s.loaded) {
       set_error("pd_run: slot has no graph");
       return FLAME_B200_ESTATE;
     }
-    maxV = std::max(maxV, c->slots[i].g.V);
-    maxE = std::max(maxE, c->slots[i].g.E);
+    maxV = std::max(maxV, s.g.V);
+    max_chunks = std::max(max_chunks, s.g.n_chunks);
+    maxVc = std::max(maxVc, s.g.Vc);
+    if (s.g.V == 0) continue;
+    if (s.plan.cluster == 0) fits = false;
+    plan.cluster = std::max(plan.cluster, s.plan.cluster);
+    plan.Vc = std::max(plan.Vc, s.plan.Vc);
+    plan.maxInc = std::max(plan.maxInc, s.plan.maxInc);
+    plan.max_deg = std::max(plan.max_deg, s.plan.max_deg);
+    plan.threads = std::max(plan.threads, s.plan.threads);
   }
   if (n_iters == 0 || maxV == 0) return 0;
-  ResidentPlan plan{};
-  if (mode != FLAME_B200_PD_STREAM) {
-    // common plan for the batch: largest preferred cluster, then maxima of the per-CTA extents
-    int C = 0;
-    bool fits = true;
-    for (int i = slot0; i < slot0 + n_slots && fits; ++i) {
-      const Slot& s = c->slots[i];
-      ResidentPlan p1 = pd_plan_resident(s.g.V, s.g.E, s.h_esrc_off.data(), s.h_inc_off.data());
-      if (p1.cluster == 0) fits = false;
-      C = std::max(C, p1.cluster);
-      plan.threads = p1.threads;
-    }
-    if (fits) {
-      plan.cluster = C;
-      plan.Vc = (maxV + C - 1) / C;
-      plan.maxE = 1;
-      plan.maxInc = 1;
-      for (int i = slot0; i < slot0 + n_slots; ++i) {
-        const Slot& s = c->slots[i];
-        for (int k = 0; k < C; ++k) {
-          const int a = std::min(k * plan.Vc, s.g.V), b = std::min(a + plan.Vc, s.g.V);
-          plan.maxE = std::max(plan.maxE, s.h_esrc_off[b] - s.h_esrc_off[a]);
-          plan.maxInc = std::max(plan.maxInc, s.h_inc_off[b] - s.h_inc_off[a]);
-        }
-      }
-      plan.smem_bytes = pd_resident_smem(C, plan.Vc, plan.maxE, plan.maxInc);
-      if (plan.smem_bytes > 227 * 1024) fits = false;
-    }
-    if (!fits) {
-      if (mode == FLAME_B200_PD_RESIDENT) {
-        set_error("pd_run: graph does not fit the resident (cluster shared memory) mode");
-        return FLAME_B200_EINVAL;
-      }
-      plan.cluster = 0;
-    }
+  if (fits) {
+    plan.smem_bytes = pd_resident_smem(plan.Vc, plan.maxInc, plan.max_deg);
+    if (plan.smem_bytes > 227 * 1024) fits = false;
   }
-  if (plan.cluster > 0)
+  if (mode == FLAME_B200_PD_RESIDENT && !fits) {
+    set_error("pd_run: graph does not fit the resident (cluster shared memory) mode");
+    return FLAME_B200_EINVAL;
+  }
+  if (fits && mode != FLAME_B200_PD_STREAM)
     return pd_run_resident(c->stream, c->d_graphs + slot0, n_slots, plan, *params, n_iters);
-  return pd_run_stream(c->stream, c->d_graphs + slot0, n_slots, maxV, maxE, *params, n_iters);
+  const int threads = std::min(1024, (maxVc + 31) / 32 * 32);
+  return pd_run_stream(c->stream, c->d_graphs + slot0, n_slots, max_chunks, threads, *params, n_iters);
 }
 
 int flame_b200_pd_cost(flame_b200_ctx* c, int slot, const flame_b200_pd_params* params,

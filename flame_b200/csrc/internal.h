@@ -24,26 +24,29 @@ inline void count_launch(int n = 1) { g_kernel_launches.fetch_add(n, std::memory
     }                                                                                       \
   } while (0)
 
-// ---- device-side record layouts (internal vertex/edge order, see DESIGN.md "HBM layout") ----
-struct __align__(32) EdgeRec {
-  float4 q;  // q1, q2, q3, 0          (EdgeData::q1..q3)
-  float4 s;  // alpha, beta, dx, dy    (EdgeData::alpha/beta; dx = pos_i.x - pos_j.x)
-};
-
-// Plain-pointer view of one slot's graph, passed to kernels by value / in an array.
+// ---- device-side layout (see DESIGN.md "HBM layout") ----
+// Vertices are stored in an INTERNAL order: Morton-sorted, cut into chunks of Vc consecutive
+// vertices (one chunk per CTA), and sorted by descending degree inside each chunk so that the
+// lanes of a warp walk equally long incidence lists. Each vertex keeps a PRIVATE copy of the
+// state of its incident edges (q1..q3 and the static alpha, beta, dx, dy), one record per
+// incidence, in ascending ORIGINAL edge id k = 0..deg-1. Incidence k of the i-th vertex of chunk c
+// lives at slot chunk_base[c] + koff[c][k] + i, so a warp's k-th loads are contiguous 16-byte words.
 struct GraphDev {
-  int V, E;
-  float4* vprim;   // x, w1, w2, data_term
-  float4* vbar;    // x_bar, w1_bar, w2_bar, 0
-  float4* vprev;   // x_prev, w1_prev, w2_prev, 0
-  float* vwt;      // data_weight
-  EdgeRec* erec;
-  int2* ends;      // internal (source, target)
-  int* inc_off;    // V+1
-  int* inc;        // 2E entries: (internal edge << 1) | is_target, ascending ORIGINAL edge id
-  int* esrc_off;   // V+1: first internal edge whose source is >= v (edges sorted by source)
-  int* vperm;      // internal -> caller vertex index
-  int* eperm;      // internal -> caller edge index
+  int V, E, Vc, n_chunks, max_deg;
+  float4* vprim;    // [V] x, w1, w2, data_term
+  float4* vbar;     // [V] x_bar, w1_bar, w2_bar, 0   (current)
+  float4* vbar2;    // [V] ping-pong partner for the streaming kernel
+  float4* vprev;    // [V] x_prev, w1_prev, w2_prev, 0
+  float* vwt;       // [V] data_weight
+  float4* inc_q;    // [2E] q1, q2, q3, bits((neighbour internal index << 1) | is_target)
+  float4* inc_s;    // [2E] alpha, beta, dx, dy   (dx = pos_source.x - pos_target.x)
+  int* deg;         // [V] internal order
+  int* koff;        // [n_chunks][max_deg + 1]
+  int* chunk_base;  // [n_chunks + 1]
+  int* vperm;       // [V] internal -> caller vertex index
+  int* inc_nbr;     // [2E] (neighbour internal index << 1) | is_target   (pack input)
+  int* inc_edge;    // [2E] caller edge index of the incidence
+  int* edges;       // [2E] caller (source, target) pairs
 };
 
 struct MeshDev {
@@ -56,24 +59,23 @@ struct MeshDev {
 
 // ---- PD (pd.cu) ----
 struct ResidentPlan {
-  int cluster;        // CTAs per graph (0 = does not fit)
+  int cluster;        // CTAs per graph (0 = does not fit -> streaming)
   int threads;
   size_t smem_bytes;
-  int Vc, maxE, maxInc;
+  int Vc, maxInc, max_deg;
 };
+#define FB_RESIDENT_MAX_DEG 64
 
-int pd_pack(cudaStream_t st, const GraphDev& g, const float* raw_f, int alpha_on_device,
-            int beta_default);
+int pd_pack(cudaStream_t st, const GraphDev& g, const float* raw_f, int alpha_on_device);
 int pd_unpack(cudaStream_t st, const GraphDev& g, float* raw_f);
 int pd_set_data(cudaStream_t st, const GraphDev& g, const float* data_term, const float* data_weight);
-int pd_run_stream(cudaStream_t st, const GraphDev* gs_dev, int n, int maxV, int maxE,
+int pd_reset(cudaStream_t st, const GraphDev* gs_dev, int n, int maxV, int maxE);
+int pd_run_stream(cudaStream_t st, const GraphDev* gs_dev, int n, int max_chunks, int threads,
                   const flame_b200_pd_params& p, int n_iters);
-ResidentPlan pd_plan_resident(int V, int E, const int* esrc_off, const int* inc_off);
+size_t pd_resident_smem(int Vc, int maxInc, int max_deg);
 int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const ResidentPlan& plan,
                     const flame_b200_pd_params& p, int n_iters);
-int pd_reset(cudaStream_t st, const GraphDev* gs_dev, int n, int maxV, int maxE);
 int pd_resident_init();  // one-time function attributes
-size_t pd_resident_smem(int C, int Vc, int maxE, int maxInc);
 int pd_cost(cudaStream_t st, const GraphDev& g, const flame_b200_pd_params& p, int exact_order,
             float* terms_scratch, double* out_dev /*2 doubles*/);
 

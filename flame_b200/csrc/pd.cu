@@ -7,6 +7,15 @@
 // reference's x86-64 Release build has no FMA), and the per-vertex gather walks the
 // incident edges in ascending ORIGINAL edge id, which is the order the reference's sequential
 // edge scatter (cc:118-142) applies its rounded += / -= to each vertex.
+//
+// Formulation (both modes): VERTEX-CENTRIC. One thread owns one vertex and a private copy of the
+// dual variables of its incident edges. Per iteration it (1) recomputes the dual update of every
+// incident edge from the x_bar/w_bar of the two endpoints (both endpoints of an edge compute the
+// same rounded values, so the two copies stay bit-identical), (2) applies the primal scatter
+// contributions in order, (3) applies proxL1 and the extragradient step and publishes the new
+// x_bar/w_bar into the OTHER half of a double buffer. Only x_bar/w_bar (16 B per vertex) is shared
+// between threads, so an iteration needs ONE barrier (the reference's dual / primal / extragradient
+// passes collapse into one sweep) and no atomics.
 #include <cooperative_groups.h>
 
 #include <algorithm>
@@ -98,8 +107,10 @@ __device__ __forceinline__ VertexOut vertex_finish(float x, float w1, float w2, 
 }
 
 // ------------------------------------------------------------------------------------------
-// pack / unpack between the caller-order SoA staging image and the internal records
+// pack / unpack between the caller-order SoA staging image and the internal layout
 // ------------------------------------------------------------------------------------------
+static inline int nblk(int n, int t) { return (n + t - 1) / t; }
+
 __global__ void k_pack_vertices(GraphDev g, const float* __restrict__ raw) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= g.V) return;
@@ -112,28 +123,26 @@ __global__ void k_pack_vertices(GraphDev g, const float* __restrict__ raw) {
   g.vwt[v] = b[10 * V + o];
 }
 
-__global__ void k_pack_edges(GraphDev g, const float* __restrict__ raw, int alpha_on_device) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= g.E) return;
-  const int o = g.eperm[e];
-  const int V = g.V, E = g.E;
-  const int2 sd = g.ends[e];
-  const int os = g.vperm[sd.x], od = g.vperm[sd.y];
+// one thread per incidence slot
+__global__ void k_pack_incidences(GraphDev g, const float* __restrict__ raw, int alpha_on_device) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= 2 * g.E) return;
+  const int o = g.inc_edge[slot];
+  const size_t E = g.E;
+  const int os = g.edges[2 * o], od = g.edges[2 * o + 1];
   const float dx = sub(raw[2 * os], raw[2 * od]);          // pos_i.x - pos_j.x (cc:100)
   const float dy = sub(raw[2 * os + 1], raw[2 * od + 1]);
-  const float* b = raw + 13 * (size_t)V;
+  const float* b = raw + 13 * (size_t)g.V;
   float alpha;
   if (alpha_on_device) {
     // flame.cc:2089-2092, 2102: alpha = 1 / sqrt(dx*dx + dy*dy)
     const float len = __fsqrt_rn(add(mul(dx, dx), mul(dy, dy)));
     alpha = __fdiv_rn(1.0f, len);
   } else {
-    alpha = b[0 * (size_t)E + o];
+    alpha = b[0 * E + o];
   }
-  EdgeRec r;
-  r.q = make_float4(b[2 * (size_t)E + o], b[3 * (size_t)E + o], b[4 * (size_t)E + o], 0.0f);
-  r.s = make_float4(alpha, b[1 * (size_t)E + o], dx, dy);
-  g.erec[e] = r;
+  g.inc_s[slot] = make_float4(alpha, b[1 * E + o], dx, dy);
+  g.inc_q[slot] = make_float4(b[2 * E + o], b[3 * E + o], b[4 * E + o], __int_as_float(g.inc_nbr[slot]));
 }
 
 __global__ void k_unpack_vertices(GraphDev g, float* __restrict__ raw) {
@@ -150,15 +159,18 @@ __global__ void k_unpack_vertices(GraphDev g, float* __restrict__ raw) {
   b[10 * V + o] = g.vwt[v];
 }
 
-__global__ void k_unpack_edges(GraphDev g, float* __restrict__ raw) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= g.E) return;
-  const int o = g.eperm[e];
+// every edge has exactly one source-role incidence: that copy is written back
+__global__ void k_unpack_incidences(GraphDev g, float* __restrict__ raw) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= 2 * g.E) return;
+  const float4 q = g.inc_q[slot];
+  if (__float_as_int(q.w) & 1) return;
+  const int o = g.inc_edge[slot];
   const size_t E = g.E;
   float* b = raw + 13 * (size_t)g.V;
-  const EdgeRec r = g.erec[e];
-  b[0 * E + o] = r.s.x; b[1 * E + o] = r.s.y;
-  b[2 * E + o] = r.q.x; b[3 * E + o] = r.q.y; b[4 * E + o] = r.q.z;
+  const float4 s = g.inc_s[slot];
+  b[0 * E + o] = s.x; b[1 * E + o] = s.y;
+  b[2 * E + o] = q.x; b[3 * E + o] = q.y; b[4 * E + o] = q.z;
 }
 
 __global__ void k_set_data(GraphDev g, const float* __restrict__ data, const float* __restrict__ wt) {
@@ -169,39 +181,32 @@ __global__ void k_set_data(GraphDev g, const float* __restrict__ data, const flo
   if (wt) g.vwt[v] = wt[o];
 }
 
-static inline int nblk(int n, int t) { return (n + t - 1) / t; }
-
 // Fresh-graph rule of Flame::syncGraph (flame.cc:2039-2048): x = x_bar = x_prev = data_term,
 // w = w_bar = w_prev = 0, q = 0. blockIdx.y selects the graph of a batch.
 __global__ void k_graph_reset(const GraphDev* __restrict__ gs) {
   const GraphDev g = gs[blockIdx.y];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(g.V, g.E); i += gridDim.x * blockDim.x) {
+  const int n = max(g.V, 2 * g.E);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (i < g.V) {
       const float d = g.vprim[i].w;
       g.vprim[i] = make_float4(d, 0.0f, 0.0f, d);
       g.vbar[i] = make_float4(d, 0.0f, 0.0f, 0.0f);
       g.vprev[i] = make_float4(d, 0.0f, 0.0f, 0.0f);
     }
-    if (i < g.E) g.erec[i].q = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (i < 2 * g.E) {
+      const float w = g.inc_q[i].w;
+      g.inc_q[i] = make_float4(0.0f, 0.0f, 0.0f, w);
+    }
   }
 }
 
-int pd_reset(cudaStream_t st, const GraphDev* gs_dev, int n, int maxV, int maxE) {
-  const int m = std::max(maxV, maxE);
-  if (m == 0 || n == 0) return 0;
-  k_graph_reset<<<dim3(std::min(nblk(m, 256), 1024), n), 256, 0, st>>>(gs_dev);
-  count_launch();
-  FB_CUDA(cudaGetLastError());
-  return 0;
-}
-
-int pd_pack(cudaStream_t st, const GraphDev& g, const float* raw_f, int alpha_on_device, int) {
+int pd_pack(cudaStream_t st, const GraphDev& g, const float* raw_f, int alpha_on_device) {
   if (g.V > 0) {
     k_pack_vertices<<<nblk(g.V, 256), 256, 0, st>>>(g, raw_f);
     count_launch();
   }
   if (g.E > 0) {
-    k_pack_edges<<<nblk(g.E, 256), 256, 0, st>>>(g, raw_f, alpha_on_device);
+    k_pack_incidences<<<nblk(2 * g.E, 256), 256, 0, st>>>(g, raw_f, alpha_on_device);
     count_launch();
   }
   FB_CUDA(cudaGetLastError());
@@ -214,7 +219,7 @@ int pd_unpack(cudaStream_t st, const GraphDev& g, float* raw_f) {
     count_launch();
   }
   if (g.E > 0) {
-    k_unpack_edges<<<nblk(g.E, 256), 256, 0, st>>>(g, raw_f);
+    k_unpack_incidences<<<nblk(2 * g.E, 256), 256, 0, st>>>(g, raw_f);
     count_launch();
   }
   FB_CUDA(cudaGetLastError());
@@ -230,54 +235,84 @@ int pd_set_data(cudaStream_t st, const GraphDev& g, const float* data_term, cons
   return 0;
 }
 
-// ------------------------------------------------------------------------------------------
-// STREAM mode: state in HBM / L2, one edge pass + one vertex pass per iteration, any size.
-// blockIdx.y selects the graph of a batch.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_dual_stream(const GraphDev* __restrict__ gs, float step_q) {
-  const GraphDev g = gs[blockIdx.y];
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < g.E; e += gridDim.x * blockDim.x) {
-    const int2 sd = g.ends[e];
-    const float4 s = g.erec[e].s;
-    float4 q = g.erec[e].q;
-    const float4 bi = g.vbar[sd.x];
-    const float4 bj = g.vbar[sd.y];
-    g.erec[e].q = dual_update(q, s, bi, bj, step_q);
-  }
+int pd_reset(cudaStream_t st, const GraphDev* gs_dev, int n, int maxV, int maxE) {
+  const int m = std::max(maxV, 2 * maxE);
+  if (m == 0 || n == 0) return 0;
+  k_graph_reset<<<dim3(std::min(nblk(m, 256), 1024), n), 256, 0, st>>>(gs_dev);
+  count_launch();
+  FB_CUDA(cudaGetLastError());
+  return 0;
 }
 
-__global__ void __launch_bounds__(256)
-k_primal_stream(const GraphDev* __restrict__ gs, flame_b200_pd_params p, int write_prev) {
+// ------------------------------------------------------------------------------------------
+// STREAM mode: state in HBM / L2, ONE kernel per iteration (x_bar double-buffered), any size.
+// grid = (chunks, graphs); a CTA sweeps one chunk of Vc vertices.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_pd_stream(const GraphDev* __restrict__ gs, flame_b200_pd_params p, int parity, int write_prev) {
   const GraphDev g = gs[blockIdx.y];
-  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < g.V; v += gridDim.x * blockDim.x) {
+  const int c = blockIdx.x;
+  if (c >= g.n_chunks) return;
+  const float4* __restrict__ cur = parity ? g.vbar2 : g.vbar;
+  float4* __restrict__ nxt = parity ? g.vbar : g.vbar2;
+  const int v0 = c * g.Vc, nv = min(g.Vc, g.V - v0);
+  const int base = g.chunk_base[c];
+  const int* __restrict__ koff = g.koff + (size_t)c * (g.max_deg + 1);
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const int v = v0 + i;
     const float4 pr = g.vprim[v];
+    const float4 own = cur[v];
     float x = pr.x, w1 = pr.y, w2 = pr.z;
-    const int k0 = g.inc_off[v], k1 = g.inc_off[v + 1];
-    for (int k = k0; k < k1; ++k) {
-      const int ent = g.inc[k];
-      const EdgeRec* r = &g.erec[ent >> 1];
-      const float4 q = r->q;
-      const float4 s = r->s;
-      primal_apply(x, w1, w2, q, s, ent & 1, p.step_x);
+    const int d = g.deg[v];
+    for (int k = 0; k < d; ++k) {
+      const int slot = base + koff[k] + i;
+      float4 q = g.inc_q[slot];
+      const float4 s = g.inc_s[slot];
+      const int ent = __float_as_int(q.w);
+      const float4 nb = cur[ent >> 1];
+      const int is_target = ent & 1;
+      const float4 qn = is_target ? dual_update(q, s, nb, own, p.step_q) : dual_update(q, s, own, nb, p.step_q);
+      primal_apply(x, w1, w2, qn, s, is_target, p.step_x);
+      g.inc_q[slot] = make_float4(qn.x, qn.y, qn.z, q.w);
     }
     const VertexOut o = vertex_finish(x, w1, w2, pr.w, g.vwt[v], pr.x, pr.y, pr.z, p);
     g.vprim[v] = o.prim;
-    g.vbar[v] = o.bar;
+    nxt[v] = o.bar;
     if (write_prev) g.vprev[v] = make_float4(pr.x, pr.y, pr.z, 0.0f);
   }
 }
 
+__global__ void k_copy_bar(const GraphDev* __restrict__ gs) {
+  const GraphDev g = gs[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.V; i += gridDim.x * blockDim.x)
+    g.vbar[i] = g.vbar2[i];
+}
+
+int pd_run_stream(cudaStream_t st, const GraphDev* gs_dev, int n, int max_chunks, int threads,
+                  const flame_b200_pd_params& p, int n_iters) {
+  if (n_iters <= 0 || n <= 0 || max_chunks <= 0) return 0;
+  const dim3 grid(max_chunks, n);
+  for (int it = 0; it < n_iters; ++it)
+    k_pd_stream<<<grid, threads, 0, st>>>(gs_dev, p, it & 1, it == n_iters - 1);
+  count_launch(n_iters);
+  if (n_iters & 1) {  // result is in vbar2: bring it home
+    k_copy_bar<<<dim3(std::min(max_chunks, 64), n), 256, 0, st>>>(gs_dev);
+    count_launch();
+  }
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // RESIDENT mode: one thread-block cluster per graph; the whole PD state lives in the cluster's
-// distributed shared memory for all n_iters iterations. Edge (dual) and vertex (primal +
-// extragradient) phases are separated by barrier.cluster; cross-CTA operands are read through
-// DSMEM (ld.shared::cluster via mapa).
+// distributed shared memory for all n_iters iterations; one barrier.cluster per iteration.
+// A neighbour's x_bar/w_bar in another CTA is read through DSMEM (mapa + ld.shared::cluster).
 // ------------------------------------------------------------------------------------------
 struct ResidentArgs {
   const GraphDev* gs;
   flame_b200_pd_params p;
   int n_iters;
-  int Vc, maxE, maxInc;
+  int Vc, maxInc, max_deg;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -295,8 +330,14 @@ __device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr) {
                : "r"(addr));
   return v;
 }
+__device__ __forceinline__ void cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
-// Packed location of a vertex / edge inside the cluster: owner CTA in the top bits.
+// neighbour location inside the cluster: (owner CTA << LOC_SHIFT) | local vertex index
 #define LOC_SHIFT 20
 #define LOC_MASK ((1u << LOC_SHIFT) - 1u)
 
@@ -306,96 +347,110 @@ __global__ void __launch_bounds__(1024, 1) k_pd_resident(ResidentArgs a) {
   const int c = cluster.block_rank();
   const GraphDev g = a.gs[blockIdx.x / C];
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int Vc = a.Vc;
+  const int Vc = g.Vc;  // this graph's chunk width; a.Vc / a.maxInc are the batch maxima (carve)
 
   extern __shared__ __align__(128) unsigned char smem[];
   // identical carve in every CTA of the cluster (remote addressing relies on it)
-  EdgeRec* s_erec = reinterpret_cast<EdgeRec*>(smem);
-  float4* s_vbar = reinterpret_cast<float4*>(s_erec + a.maxE);
-  float4* s_vprim = s_vbar + Vc;
-  uint2* s_ends = reinterpret_cast<uint2*>(s_vprim + Vc);
-  float* s_vwt = reinterpret_cast<float*>(s_ends + a.maxE);
-  int* s_incoff = reinterpret_cast<int*>(s_vwt + Vc);
-  uint32_t* s_inc = reinterpret_cast<uint32_t*>(s_incoff + Vc + 1);
-  int* s_estart = reinterpret_cast<int*>(s_inc + a.maxInc);  // C + 1 entries (<= 17)
+  float4* s_q = reinterpret_cast<float4*>(smem);
+  float4* s_s = s_q + a.maxInc;
+  float4* s_bar0 = s_s + a.maxInc;
+  float4* s_bar1 = s_bar0 + a.Vc;
+  float4* s_prim = s_bar1 + a.Vc;
+  float* s_wt = reinterpret_cast<float*>(s_prim + a.Vc);
+  int* s_deg = reinterpret_cast<int*>(s_wt + a.Vc);
+  int* s_koff = s_deg + a.Vc;  // a.max_deg + 1
 
-  const int v0 = min(c * Vc, g.V), v1 = min(v0 + Vc, g.V), nv = v1 - v0;
-  const int e0 = g.esrc_off[v0], e1 = g.esrc_off[v1], ne = e1 - e0;
-  if (tid <= C) s_estart[tid] = g.esrc_off[min(tid * Vc, g.V)];
-  __syncthreads();
+  const bool have = c < g.n_chunks;
+  const int v0 = c * Vc;
+  const int nv = have ? min(Vc, g.V - v0) : 0;
+  const int base = have ? g.chunk_base[c] : 0;
+  const int ni = have ? g.chunk_base[c + 1] - base : 0;
 
-  // ---- load this CTA's partition ----
+  // ---- load this CTA's chunk ----
   for (int i = tid; i < nv; i += nt) {
-    s_vbar[i] = g.vbar[v0 + i];
-    s_vprim[i] = g.vprim[v0 + i];
-    s_vwt[i] = g.vwt[v0 + i];
+    s_bar0[i] = g.vbar[v0 + i];
+    s_prim[i] = g.vprim[v0 + i];
+    s_wt[i] = g.vwt[v0 + i];
+    s_deg[i] = g.deg[v0 + i];
   }
-  const int k0 = g.inc_off[v0];
-  for (int i = tid; i <= nv; i += nt) s_incoff[i] = g.inc_off[v0 + i] - k0;
-  const int nk = g.inc_off[v1] - k0;
-  for (int k = tid; k < nk; k += nt) {
-    const int ent = g.inc[k0 + k];
-    const int e = ent >> 1;
-    int owner = 0;
-    while (owner + 1 < C && s_estart[owner + 1] <= e) ++owner;
-    s_inc[k] = (uint32_t)(ent & 1) | ((uint32_t)(e - s_estart[owner]) << 1) |
-               ((uint32_t)owner << (LOC_SHIFT + 1));
-  }
-  for (int i = tid; i < ne; i += nt) {
-    s_erec[i] = g.erec[e0 + i];
-    const int2 sd = g.ends[e0 + i];
-    const int cs = sd.x / Vc, cd = sd.y / Vc;
-    s_ends[i] = make_uint2(((uint32_t)cs << LOC_SHIFT) | (uint32_t)(sd.x - cs * Vc),
-                           ((uint32_t)cd << LOC_SHIFT) | (uint32_t)(sd.y - cd * Vc));
+  if (have)
+    for (int k = tid; k <= g.max_deg; k += nt) s_koff[k] = g.koff[(size_t)c * (g.max_deg + 1) + k];
+  for (int k = tid; k < ni; k += nt) {
+    float4 q = g.inc_q[base + k];
+    const int ent = __float_as_int(q.w);
+    const int nbr = ent >> 1;
+    const int oc = nbr / Vc;
+    q.w = __uint_as_float((((uint32_t)oc << LOC_SHIFT) | (uint32_t)(nbr - oc * Vc)) << 1 | (uint32_t)(ent & 1));
+    s_q[k] = q;
+    s_s[k] = g.inc_s[base + k];
   }
   cluster.sync();
 
-  const uint32_t vbar_base = smem_u32(s_vbar);
-  const uint32_t erec_base = smem_u32(s_erec);
+  const uint32_t bar_base[2] = {smem_u32(s_bar0), smem_u32(s_bar1)};
+  float4* const bars[2] = {s_bar0, s_bar1};
   const flame_b200_pd_params p = a.p;
 
   for (int it = 0; it < a.n_iters; ++it) {
-    // ---- dual step: one thread per owned edge ----
-    for (int i = tid; i < ne; i += nt) {
-      const uint2 sd = s_ends[i];
-      const float4 bi = ld_cluster_f4(mapa(vbar_base + (sd.x & LOC_MASK) * 16u, sd.x >> LOC_SHIFT));
-      const float4 bj = ld_cluster_f4(mapa(vbar_base + (sd.y & LOC_MASK) * 16u, sd.y >> LOC_SHIFT));
-      s_erec[i].q = dual_update(s_erec[i].q, s_erec[i].s, bi, bj, p.step_q);
-    }
-    cluster.sync();
-    // ---- primal step + prox + extragradient: one thread per owned vertex ----
+    const int par = it & 1;
+    const uint32_t cur_base = bar_base[par];
+    const float4* cur = bars[par];
+    float4* nxt = bars[par ^ 1];
     const bool last = (it == a.n_iters - 1);
     for (int i = tid; i < nv; i += nt) {
-      const float4 pr = s_vprim[i];
+      const float4 pr = s_prim[i];
+      const float4 own = cur[i];
       float x = pr.x, w1 = pr.y, w2 = pr.z;
-      const int ka = s_incoff[i], kb = s_incoff[i + 1];
-      for (int k = ka; k < kb; ++k) {
-        const uint32_t ent = s_inc[k];
-        const uint32_t addr =
-            mapa(erec_base + ((ent >> 1) & LOC_MASK) * 32u, ent >> (LOC_SHIFT + 1));
-        const float4 q = ld_cluster_f4(addr);
-        const float4 s = ld_cluster_f4(addr + 16u);
-        primal_apply(x, w1, w2, q, s, ent & 1u, p.step_x);
+      const int d = s_deg[i];
+      // software pipeline: the loads of incidence k+1 are issued before the arithmetic of k
+      float4 qn, sn, nbn;
+      if (d > 0) {
+        qn = s_q[i];
+        sn = s_s[i];
+        const uint32_t e = __float_as_uint(qn.w) >> 1;
+        nbn = ld_cluster_f4(mapa(cur_base + (e & LOC_MASK) * 16u, e >> LOC_SHIFT));
       }
-      const VertexOut o = vertex_finish(x, w1, w2, pr.w, s_vwt[i], pr.x, pr.y, pr.z, p);
-      s_vprim[i] = o.prim;
-      s_vbar[i] = o.bar;
+      for (int k = 0; k < d; ++k) {
+        const float4 q = qn, s = sn, nb = nbn;
+        const int slot = s_koff[k] + i;
+        if (k + 1 < d) {
+          const int s2 = s_koff[k + 1] + i;
+          qn = s_q[s2];
+          sn = s_s[s2];
+          const uint32_t e = __float_as_uint(qn.w) >> 1;
+          nbn = ld_cluster_f4(mapa(cur_base + (e & LOC_MASK) * 16u, e >> LOC_SHIFT));
+        }
+        const int is_target = __float_as_int(q.w) & 1;
+        const float4 qu = is_target ? dual_update(q, s, nb, own, p.step_q) : dual_update(q, s, own, nb, p.step_q);
+        primal_apply(x, w1, w2, qu, s, is_target, p.step_x);
+        s_q[slot] = make_float4(qu.x, qu.y, qu.z, q.w);
+      }
+      const VertexOut o = vertex_finish(x, w1, w2, pr.w, s_wt[i], pr.x, pr.y, pr.z, p);
+      s_prim[i] = o.prim;
+      nxt[i] = o.bar;
       if (last) g.vprev[v0 + i] = make_float4(pr.x, pr.y, pr.z, 0.0f);
     }
-    cluster.sync();
+    cluster_arrive();
+    cluster_wait();
   }
 
   // ---- write back ----
+  const float4* fin = bars[a.n_iters & 1];
   for (int i = tid; i < nv; i += nt) {
-    g.vbar[v0 + i] = s_vbar[i];
-    g.vprim[v0 + i] = s_vprim[i];
+    g.vbar[v0 + i] = fin[i];
+    g.vprim[v0 + i] = s_prim[i];
   }
-  for (int i = tid; i < ne; i += nt) g.erec[e0 + i].q = s_erec[i].q;
+  for (int k = tid; k < ni; k += nt) {
+    float4 q = s_q[k];
+    const uint32_t ent = __float_as_uint(q.w);
+    const uint32_t e = ent >> 1;
+    const int nbr = (int)(e >> LOC_SHIFT) * Vc + (int)(e & LOC_MASK);
+    q.w = __int_as_float((nbr << 1) | (int)(ent & 1u));
+    g.inc_q[base + k] = q;
+  }
 }
 
-size_t pd_resident_smem(int C, int Vc, int maxE, int maxInc) {
-  return (size_t)maxE * 32 + (size_t)Vc * 32 + (size_t)maxE * 8 + (size_t)Vc * 4 +
-         (size_t)(Vc + 1) * 4 + (size_t)maxInc * 4 + (size_t)(C + 1) * 4 + 64;
+size_t pd_resident_smem(int Vc, int maxInc, int max_deg) {
+  return (size_t)maxInc * 32 + (size_t)Vc * (16 * 3 + 4 + 4) + (size_t)(max_deg + 1) * 4 + 128;
 }
 
 int pd_resident_init() {
@@ -408,41 +463,6 @@ int pd_resident_init() {
   return 0;
 }
 
-// Chooses the cluster size for one graph from its (host) offset tables.
-ResidentPlan pd_plan_resident(int V, int E, const int* esrc_off, const int* inc_off) {
-  ResidentPlan best{};
-  best.cluster = 0;
-  int forced = 0;
-  if (const char* s = getenv("FLAME_B200_CLUSTER")) forced = atoi(s);
-  int threads = 1024;
-  if (const char* s = getenv("FLAME_B200_THREADS")) threads = atoi(s);
-  if (V >= (1 << LOC_SHIFT) || E >= (1 << LOC_SHIFT)) return best;
-  for (int C = 1; C <= 16; C *= 2) {
-    if (forced && C != forced) continue;
-    const int Vc = (V + C - 1) / C;
-    if (Vc == 0) continue;
-    int maxE = 0, maxInc = 0;
-    for (int c = 0; c < C; ++c) {
-      const int a = std::min(c * Vc, V), b = std::min(a + Vc, V);
-      maxE = std::max(maxE, esrc_off[b] - esrc_off[a]);
-      maxInc = std::max(maxInc, inc_off[b] - inc_off[a]);
-    }
-    maxE = std::max(maxE, 1);
-    maxInc = std::max(maxInc, 1);
-    const size_t smem = pd_resident_smem(C, Vc, maxE, maxInc);
-    if (smem > 227 * 1024) continue;
-    best.cluster = C;
-    best.threads = threads;
-    best.smem_bytes = smem;
-    best.Vc = Vc;
-    best.maxE = maxE;
-    best.maxInc = maxInc;
-    // heuristic: stop growing once every thread has at most ~2 edges
-    if (forced || (E + C - 1) / C <= 2 * threads) break;
-  }
-  return best;
-}
-
 int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const ResidentPlan& plan,
                     const flame_b200_pd_params& p, int n_iters) {
   if (int rc = pd_resident_init()) return rc;
@@ -451,8 +471,8 @@ int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const Reside
   a.p = p;
   a.n_iters = n_iters;
   a.Vc = plan.Vc;
-  a.maxE = plan.maxE;
   a.maxInc = plan.maxInc;
+  a.max_deg = plan.max_deg;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n * plan.cluster);
   cfg.blockDim = dim3(plan.threads);
@@ -470,31 +490,24 @@ int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const Reside
   return 0;
 }
 
-// gs_dev: device array of n GraphDev; maxV/maxE = maxima over the batch.
-int pd_run_stream(cudaStream_t st, const GraphDev* gs_dev, int n, int maxV, int maxE,
-                       const flame_b200_pd_params& p, int n_iters) {
-  if (n_iters <= 0 || n <= 0) return 0;
-  const dim3 ge(std::max(1, std::min(nblk(maxE, 256), 65535)), n);
-  const dim3 gv(std::max(1, std::min(nblk(maxV, 256), 65535)), n);
-  for (int it = 0; it < n_iters; ++it) {
-    k_dual_stream<<<ge, 256, 0, st>>>(gs_dev, p.step_q);
-    k_primal_stream<<<gv, 256, 0, st>>>(gs_dev, p, it == n_iters - 1);
-  }
-  count_launch(2 * n_iters);
-  FB_CUDA(cudaGetLastError());
-  return 0;
-}
-
 // ------------------------------------------------------------------------------------------
 // Energies: smoothnessCost (cc:51-71), dataCost (cc:73-85)
 // ------------------------------------------------------------------------------------------
 // terms layout (floats, caller order): [0, 2E) smoothness pairs (t1, t2) per edge, [2E, 2E+V) data.
 __global__ void k_cost_terms(GraphDev g, float* __restrict__ terms) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < g.E) {
-    const int2 sd = g.ends[i];
-    const float4 s = g.erec[i].s;
-    const float4 pi = g.vprim[sd.x], pj = g.vprim[sd.y];
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= g.V) return;
+  const int c = v / g.Vc, i = v - c * g.Vc;
+  const int base = g.chunk_base[c];
+  const int* koff = g.koff + (size_t)c * (g.max_deg + 1);
+  const float4 pi = g.vprim[v];
+  const int d = g.deg[v];
+  for (int k = 0; k < d; ++k) {
+    const int slot = base + koff[k] + i;
+    const int ent = __float_as_int(g.inc_q[slot].w);
+    if (ent & 1) continue;  // the source endpoint evaluates the edge
+    const float4 s = g.inc_s[slot];
+    const float4 pj = g.vprim[ent >> 1];
     // cc:64-67: alpha*|x_i - x_j - w1_i*dx - w2_i*dy|;  beta*|w1_i-w1_j| + beta*|w2_i-w2_j|
     float a = sub(sub(sub(pi.x, pj.x), mul(pi.y, s.z)), mul(pi.z, s.w));
     a = (a >= 0) ? a : -a;
@@ -502,19 +515,16 @@ __global__ void k_cost_terms(GraphDev g, float* __restrict__ terms) {
     b1 = (b1 >= 0) ? b1 : -b1;
     float b2 = sub(pi.z, pj.z);
     b2 = (b2 >= 0) ? b2 : -b2;
-    const int o = g.eperm[i];
+    const int o = g.inc_edge[slot];
     terms[2 * (size_t)o] = mul(s.x, a);
     terms[2 * (size_t)o + 1] = add(mul(s.y, b1), mul(s.y, b2));
   }
-  if (i < g.V) {
-    const float4 pr = g.vprim[i];
-    float d = mul(sub(pr.x, pr.w), g.vwt[i]);  // cc:79-80
-    d = (d > 0) ? d : -d;
-    terms[2 * (size_t)g.E + g.vperm[i]] = d;
-  }
+  float dd = mul(sub(pi.x, pi.w), g.vwt[v]);  // cc:79-80
+  dd = (dd > 0) ? dd : -dd;
+  terms[2 * (size_t)g.E + g.vperm[v]] = dd;
 }
 
-// Sequential fp32 accumulation in the reference's order (one warp stages, lane 0 adds).
+// Sequential fp32 accumulation in the reference's order (the block stages, thread 0 adds).
 __global__ void k_cost_sum_exact(const float* __restrict__ terms, int nE2, int nV, float data_factor,
                                  double* out) {
   __shared__ float buf[1024];
@@ -557,12 +567,11 @@ __global__ void k_cost_sum_fast(const float* __restrict__ terms, int nE2, int nV
 
 int pd_cost(cudaStream_t st, const GraphDev& g, const flame_b200_pd_params& p, int exact_order,
             float* terms, double* out_dev) {
-  const int n = std::max(g.V, g.E);
-  if (n == 0) {
+  if (g.V == 0) {
     FB_CUDA(cudaMemsetAsync(out_dev, 0, 2 * sizeof(double), st));
     return 0;
   }
-  k_cost_terms<<<nblk(n, 256), 256, 0, st>>>(g, terms);
+  k_cost_terms<<<nblk(g.V, 256), 256, 0, st>>>(g, terms);
   count_launch();
   if (exact_order) {
     k_cost_sum_exact<<<1, 256, 0, st>>>(terms, 2 * g.E, g.V, p.data_factor, out_dev);
