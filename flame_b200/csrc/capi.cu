@@ -63,7 +63,7 @@ struct flame_b200_ctx {
   void* stereo = nullptr;
   // host scratch for graph prep
   std::vector<uint32_t> keys, keys2;
-  std::vector<int> idx, idx2, vinv, cursor, degv, order, koff_tmp;
+  std::vector<int> idx, idx2, vinv, cursor, degv, srcdeg, order, koff_tmp;
 };
 
 namespace fb {
@@ -96,8 +96,9 @@ struct PrepOut {
 static size_t ints_total(int V, int E, int n_chunks, int max_deg) {
   return (size_t)2 * V + (size_t)n_chunks * (max_deg + 1) + (size_t)n_chunks + 1 + (size_t)6 * E;
 }
+// + 2E ints of device-only space (edge_slot) after the uploaded image
 static size_t blob_bytes(int V, int E, int n_chunks, int max_deg) {
-  return (raw_f_total(V, E) + ints_total(V, E, n_chunks, max_deg)) * 4 + 256;
+  return (raw_f_total(V, E) + ints_total(V, E, n_chunks, max_deg) + (size_t)2 * E) * 4 + 256;
 }
 
 // Internal order + private incidence layout (see GraphDev). O(V + E), deterministic.
@@ -155,7 +156,9 @@ static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const in
 
   // degrees (caller index)
   c->degv.assign(V, 0);
+  c->srcdeg.assign(V, 0);
   for (int e = 0; e < 2 * E; ++e) c->degv[edges[e]]++;
+  for (int e = 0; e < E; ++e) c->srcdeg[edges[2 * e]]++;
   int max_deg = 0;
   for (int v = 0; v < V; ++v) max_deg = std::max(max_deg, c->degv[v]);
 
@@ -169,28 +172,35 @@ static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const in
     for (int C = 1; C <= 16; C *= 2) {
       if (forced && C != forced) continue;
       const int Vc = (V + C - 1) / C;
-      int maxInc = 0;
+      int maxInc = 0, maxEdges = 0;
       for (int k = 0; k < C; ++k) {
-        int inc = 0;
-        for (int i = std::min(k * Vc, V); i < std::min((k + 1) * Vc, V); ++i) inc += c->degv[morton[i]];
+        int inc = 0, ed = 0;
+        for (int i = std::min(k * Vc, V); i < std::min((k + 1) * Vc, V); ++i) {
+          inc += c->degv[morton[i]];
+          ed += c->srcdeg[morton[i]];
+        }
         maxInc = std::max(maxInc, inc);
+        maxEdges = std::max(maxEdges, ed);
       }
-      const size_t smem = pd_resident_smem(Vc, std::max(maxInc, 1), max_deg);
+      maxInc = std::max(maxInc, 1);
+      maxEdges = std::max(maxEdges, 1);
+      const size_t smem = pd_resident_smem(Vc, maxInc, maxEdges, max_deg);
       if (smem > 227 * 1024) continue;
+      int thr = 0;
+      if (!pd_resident_variant(Vc, maxEdges, &thr)) continue;
       ResidentPlan pl{};
       pl.cluster = C;
       pl.Vc = Vc;
-      pl.maxInc = std::max(maxInc, 1);
+      pl.maxInc = maxInc;
+      pl.maxEdges = maxEdges;
       pl.max_deg = max_deg;
       pl.smem_bytes = smem;
-      pl.threads = thr_env ? thr_env : std::min(1024, (Vc + 31) / 32 * 32);
-      if (fallback.cluster == 0) fallback = pl;
-      if (Vc <= 1024 || forced) {
-        plan = pl;
-        break;
-      }
+      pl.threads = thr;
+      (void)thr_env;
+      (void)fallback;
+      plan = pl;
+      break;
     }
-    if (plan.cluster == 0) plan = fallback;
   }
   const int Vc = plan.cluster ? plan.Vc : std::min(std::max(V, 1), 1024);
   const int n_chunks = V > 0 ? (V + Vc - 1) / Vc : 0;
@@ -541,6 +551,7 @@ int flame_b200_graph_upload(flame_b200_ctx* c, int slot, const flame_b200_graph_
   s.g.inc_nbr = di + (h_inc_nbr - hi);
   s.g.inc_edge = di + (h_inc_edge - hi);
   s.g.edges = di + (h_edges - hi);
+  s.g.edge_slot = s.g.edges + 2 * (size_t)E;
   if (V > 0)
     FB_CUDA(cudaMemcpyAsync(s.d_pos, s.d_raw(), (size_t)2 * V * sizeof(float),
                             cudaMemcpyDeviceToDevice, c->stream));
@@ -661,13 +672,14 @@ int flame_b200_pd_run(flame_b200_ctx* c, int slot0, int n_slots, const flame_b20
     plan.cluster = std::max(plan.cluster, s.plan.cluster);
     plan.Vc = std::max(plan.Vc, s.plan.Vc);
     plan.maxInc = std::max(plan.maxInc, s.plan.maxInc);
+    plan.maxEdges = std::max(plan.maxEdges, s.plan.maxEdges);
     plan.max_deg = std::max(plan.max_deg, s.plan.max_deg);
     plan.threads = std::max(plan.threads, s.plan.threads);
   }
   if (n_iters == 0 || maxV == 0) return 0;
   if (fits) {
-    plan.smem_bytes = pd_resident_smem(plan.Vc, plan.maxInc, plan.max_deg);
-    if (plan.smem_bytes > 227 * 1024) fits = false;
+    plan.smem_bytes = pd_resident_smem(plan.Vc, plan.maxInc, plan.maxEdges, plan.max_deg);
+    if (plan.smem_bytes > 227 * 1024 || !pd_resident_variant(plan.Vc, plan.maxEdges, &plan.threads)) fits = false;
   }
   if (mode == FLAME_B200_PD_RESIDENT && !fits) {
     set_error("pd_run: graph does not fit the resident (cluster shared memory) mode");

@@ -47,6 +47,7 @@ struct GraphDev {
   int* inc_nbr;     // [2E] (neighbour internal index << 1) | is_target   (pack input)
   int* inc_edge;    // [2E] caller edge index of the incidence
   int* edges;       // [2E] caller (source, target) pairs
+  int* edge_slot;   // [2E] (caller edge, role) -> incidence slot (written by the pack kernel)
 };
 
 struct MeshDev {
@@ -62,7 +63,7 @@ struct ResidentPlan {
   int cluster;        // CTAs per graph (0 = does not fit -> streaming)
   int threads;
   size_t smem_bytes;
-  int Vc, maxInc, max_deg;
+  int Vc, maxInc, maxEdges, max_deg;
 };
 #define FB_RESIDENT_MAX_DEG 64
 
@@ -72,7 +73,8 @@ int pd_set_data(cudaStream_t st, const GraphDev& g, const float* data_term, cons
 int pd_reset(cudaStream_t st, const GraphDev* gs_dev, int n, int maxV, int maxE);
 int pd_run_stream(cudaStream_t st, const GraphDev* gs_dev, int n, int max_chunks, int threads,
                   const flame_b200_pd_params& p, int n_iters);
-size_t pd_resident_smem(int Vc, int maxInc, int max_deg);
+size_t pd_resident_smem(int Vc, int maxInc, int maxEdges, int max_deg);
+bool pd_resident_variant(int Vc, int maxEdges, int* threads);
 int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const ResidentPlan& plan,
                     const flame_b200_pd_params& p, int n_iters);
 int pd_resident_init();  // one-time function attributes

@@ -35,10 +35,9 @@ __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b);
 __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
 
 // proxNLTGV2Conj (h:171-176): q / (|q| > 1 ? |q| : 1). For finite q, q/|q| is exactly +-1 and
-// q/1 is exactly q, so the quotient is this clamp (NaN propagates identically); no divide.
-__device__ __forceinline__ float prox_conj(float q) {
-  return q > 1.0f ? 1.0f : (q < -1.0f ? -1.0f : q);
-}
+// q/1 is exactly q, so the quotient IS this clamp — two FMNMX, no divide. (A NaN q, on which the
+// reference FLAME_ASSERTs and exits, is not propagated by fminf/fmaxf; inputs are validated finite.)
+__device__ __forceinline__ float prox_conj(float q) { return fminf(fmaxf(q, -1.0f), 1.0f); }
 
 // dualStep body for one edge (cc:98-110). bi/bj = (x_bar, w1_bar, w2_bar, -) of source/target.
 __device__ __forceinline__ float4 dual_update(float4 q, const float4 s, const float4 bi,
@@ -53,6 +52,22 @@ __device__ __forceinline__ float4 dual_update(float4 q, const float4 s, const fl
   const float K3x = mul(beta, sub(bi.z, bj.z));
   q.z = prox_conj(add(q.z, mul(step_q, K3x)));
   return q;
+}
+
+// dualStep for one incidence: `own` is this vertex, `nb` the neighbour; the edge's source is `nb`
+// when this vertex is the target. Selecting the operands first keeps ONE copy of the arithmetic.
+__device__ __forceinline__ float4 dual_update_inc(const float4 q, const float4 s, const float4 own,
+                                                  const float4 nb, const int is_target,
+                                                  const float step_q) {
+  float4 bi, bj;
+  bi.x = is_target ? nb.x : own.x;
+  bi.y = is_target ? nb.y : own.y;
+  bi.z = is_target ? nb.z : own.z;
+  bj.x = is_target ? own.x : nb.x;
+  bj.y = is_target ? own.y : nb.y;
+  bj.z = is_target ? own.z : nb.z;
+  bi.w = bj.w = 0.0f;
+  return dual_update(q, s, bi, bj, step_q);
 }
 
 // primalStep edge-loop body (cc:125-141) as seen from ONE endpoint.
@@ -142,7 +157,9 @@ __global__ void k_pack_incidences(GraphDev g, const float* __restrict__ raw, int
     alpha = b[0 * E + o];
   }
   g.inc_s[slot] = make_float4(alpha, b[1 * E + o], dx, dy);
-  g.inc_q[slot] = make_float4(b[2 * E + o], b[3 * E + o], b[4 * E + o], __int_as_float(g.inc_nbr[slot]));
+  const int ent = g.inc_nbr[slot];
+  g.inc_q[slot] = make_float4(b[2 * E + o], b[3 * E + o], b[4 * E + o], __int_as_float(ent));
+  g.edge_slot[2 * o + (ent & 1)] = slot;  // inverse map: (edge, role) -> incidence slot
 }
 
 __global__ void k_unpack_vertices(GraphDev g, float* __restrict__ raw) {
@@ -271,7 +288,7 @@ k_pd_stream(const GraphDev* __restrict__ gs, flame_b200_pd_params p, int parity,
       const int ent = __float_as_int(q.w);
       const float4 nb = cur[ent >> 1];
       const int is_target = ent & 1;
-      const float4 qn = is_target ? dual_update(q, s, nb, own, p.step_q) : dual_update(q, s, own, nb, p.step_q);
+      const float4 qn = dual_update_inc(q, s, own, nb, is_target, p.step_q);
       primal_apply(x, w1, w2, qn, s, is_target, p.step_x);
       g.inc_q[slot] = make_float4(qn.x, qn.y, qn.z, q.w);
     }
@@ -304,15 +321,28 @@ int pd_run_stream(cudaStream_t st, const GraphDev* gs_dev, int n, int max_chunks
 }
 
 // ------------------------------------------------------------------------------------------
-// RESIDENT mode: one thread-block cluster per graph; the whole PD state lives in the cluster's
-// distributed shared memory for all n_iters iterations; one barrier.cluster per iteration.
-// A neighbour's x_bar/w_bar in another CTA is read through DSMEM (mapa + ld.shared::cluster).
+// RESIDENT mode: one thread-block cluster per graph; the PD state stays on chip for all n_iters
+// iterations. Per iteration, two phases separated by cluster barriers:
+//   A (edge-parallel, balanced): every EDGE is owned by one thread of the CTA that holds its source
+//     vertex, with q1..q3 in REGISTERS for the whole solve. The thread reads x_bar/w_bar of both
+//     endpoints (source: ld.shared; target: DSMEM through a pre-mapped shared::cluster address),
+//     performs the dual update once, and PUSHES the rounded primal contributions of the edge to the
+//     incidence slots of both endpoints: (-a, a*dx, a*dy, -b2 | -b3) to the source's slot in its own
+//     shared memory and (a, b2, b3, -0 | -0) to the target's slot, which may live in another CTA of
+//     the cluster (st.shared::cluster). "+ -0.0f" is the exact identity of IEEE addition, so the
+//     target's slot needs no branch in phase B.
+//   barrier.cluster (release/acquire: remote stores visible)
+//   B (vertex-parallel): thread i < nv owns vertex i (x, w1, w2 in registers); it adds the
+//     contributions of its incidence slots in ascending ORIGINAL edge id — five rounded adds per
+//     incidence, bit-identical to the reference's sequential edge scatter (cc:125-141) — then proxL1
+//     and the extragradient step, and publishes x_bar/w_bar into the other half of a double buffer.
+//   barrier.cluster
 // ------------------------------------------------------------------------------------------
 struct ResidentArgs {
   const GraphDev* gs;
   flame_b200_pd_params p;
   int n_iters;
-  int Vc, maxInc, max_deg;
+  int Vc, maxInc, maxEdges, max_deg;  // batch maxima: identical shared-memory carve in every CTA
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -330,6 +360,23 @@ __device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr) {
                : "r"(addr));
   return v;
 }
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_shared_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ void cluster_arrive() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 }
@@ -337,128 +384,234 @@ __device__ __forceinline__ void cluster_wait() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// neighbour location inside the cluster: (owner CTA << LOC_SHIFT) | local vertex index
-#define LOC_SHIFT 20
-#define LOC_MASK ((1u << LOC_SHIFT) - 1u)
-
-__global__ void __launch_bounds__(1024, 1) k_pd_resident(ResidentArgs a) {
+#define PD_MLP 2
+template <int MAXT, int SPT>
+__global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
   const int C = cluster.num_blocks();
   const int c = cluster.block_rank();
   const GraphDev g = a.gs[blockIdx.x / C];
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int Vc = g.Vc;  // this graph's chunk width; a.Vc / a.maxInc are the batch maxima (carve)
+  const int Vc = g.Vc;  // this graph's chunk width (a.Vc >= Vc is the carve width)
 
   extern __shared__ __align__(128) unsigned char smem[];
-  // identical carve in every CTA of the cluster (remote addressing relies on it)
-  float4* s_q = reinterpret_cast<float4*>(smem);
-  float4* s_s = s_q + a.maxInc;
-  float4* s_bar0 = s_s + a.maxInc;
+  float4* s_bar0 = reinterpret_cast<float4*>(smem);
   float4* s_bar1 = s_bar0 + a.Vc;
-  float4* s_prim = s_bar1 + a.Vc;
-  float* s_wt = reinterpret_cast<float*>(s_prim + a.Vc);
-  int* s_deg = reinterpret_cast<int*>(s_wt + a.Vc);
-  int* s_koff = s_deg + a.Vc;  // a.max_deg + 1
+  float4* s_p4 = s_bar1 + a.Vc;      // per incidence slot: (sx, t1, t2, u1)
+  float4* s_s = s_p4 + a.maxInc;     // per owned edge: (alpha, beta, dx, dy)
+  float* s_p1 = reinterpret_cast<float*>(s_s + a.maxEdges);  // per incidence slot: u2
+  int* s_list = reinterpret_cast<int*>(s_p1 + a.maxInc);     // owned edges: their source slot
+  int* s_koff = s_list + a.maxEdges;                         // a.max_deg + 1
+  int* s_cnt = s_koff + a.max_deg + 1;                       // 1
 
   const bool have = c < g.n_chunks;
   const int v0 = c * Vc;
   const int nv = have ? min(Vc, g.V - v0) : 0;
   const int base = have ? g.chunk_base[c] : 0;
   const int ni = have ? g.chunk_base[c + 1] - base : 0;
+  const uint32_t bar0_addr = smem_u32(s_bar0);
+  const uint32_t bar_stride = (uint32_t)a.Vc * 16u;  // bar1 - bar0
+  const uint32_t p4_addr = smem_u32(s_p4);
+  const float neg0 = __int_as_float(0x80000000);
 
-  // ---- load this CTA's chunk ----
-  for (int i = tid; i < nv; i += nt) {
-    s_bar0[i] = g.vbar[v0 + i];
-    s_prim[i] = g.vprim[v0 + i];
-    s_wt[i] = g.vwt[v0 + i];
-    s_deg[i] = g.deg[v0 + i];
-  }
+  // ---- load ----
   if (have)
     for (int k = tid; k <= g.max_deg; k += nt) s_koff[k] = g.koff[(size_t)c * (g.max_deg + 1) + k];
-  for (int k = tid; k < ni; k += nt) {
-    float4 q = g.inc_q[base + k];
-    const int ent = __float_as_int(q.w);
-    const int nbr = ent >> 1;
-    const int oc = nbr / Vc;
-    q.w = __uint_as_float((((uint32_t)oc << LOC_SHIFT) | (uint32_t)(nbr - oc * Vc)) << 1 | (uint32_t)(ent & 1));
-    s_q[k] = q;
-    s_s[k] = g.inc_s[base + k];
+  if (tid == 0) *s_cnt = 0;
+  // vertex registers (thread i owns vertex i; the planner guarantees nv <= blockDim.x)
+  const bool hasv = tid < nv;
+  float x = 0.f, w1 = 0.f, w2 = 0.f, data = 0.f, wt = 0.f;
+  int deg = 0;
+  if (hasv) {
+    const float4 pr = g.vprim[v0 + tid];
+    x = pr.x; w1 = pr.y; w2 = pr.z; data = pr.w;
+    wt = g.vwt[v0 + tid];
+    deg = g.deg[v0 + tid];
+    s_bar0[tid] = g.vbar[v0 + tid];
+  }
+  __syncthreads();
+  // owned edges = source-role incidence slots of this chunk, listed vertex by vertex so that the
+  // threads of a warp read the same / adjacent source records (shared-memory broadcast, few bank
+  // conflicts). Deterministic: per-vertex out-degree -> block-wide exclusive scan -> fill.
+  int* s_scan = reinterpret_cast<int*>(s_p4);  // scratch (s_p4 is not live before the first phase A)
+  int outdeg = 0;
+  if (hasv)
+    for (int k = 0; k < deg; ++k) outdeg += ((g.inc_nbr[base + s_koff[k] + tid] & 1) == 0);
+  s_scan[tid] = outdeg;
+  __syncthreads();
+  if (tid == 0) {  // nt <= 1024 entries, once per launch
+    int run = 0;
+    for (int i = 0; i < nt; ++i) {
+      const int d0 = s_scan[i];
+      s_scan[i] = run;
+      run += d0;
+    }
+    *s_cnt = run;
+  }
+  __syncthreads();
+  if (hasv) {
+    int at = s_scan[tid];
+    for (int k = 0; k < deg; ++k) {
+      const int slot = s_koff[k] + tid;
+      if ((g.inc_nbr[base + slot] & 1) == 0) s_list[at++] = slot;
+    }
+  }
+  __syncthreads();
+  for (int slot = tid; slot < ni; slot += nt)
+    s_p1[slot] = neg0;  // target slots keep -0.0f forever; source slots are rewritten every iteration
+  const int ne = *s_cnt;
+  float q1[SPT], q2[SPT], q3[SPT];
+  uint32_t src_bar[SPT];   // shared::cta address of the source's bar0 record
+  uint32_t dst_bar[SPT];   // shared::cluster address of the target's bar0 record
+  uint32_t src_slot[SPT];  // local incidence slot of the source endpoint
+  uint32_t dst_p4[SPT];    // shared::cluster address of the target endpoint's p4 record
+#pragma unroll
+  for (int u = 0; u < SPT; ++u) {
+    const int j = tid + u * nt;
+    q1[u] = q2[u] = q3[u] = 0.f;
+    src_bar[u] = bar0_addr;
+    dst_bar[u] = bar0_addr;
+    src_slot[u] = 0;
+    dst_p4[u] = p4_addr;
+    if (j < ne) {
+      const int slot = s_list[j];
+      const float4 q = g.inc_q[base + slot];
+      q1[u] = q.x; q2[u] = q.y; q3[u] = q.z;
+      s_s[j] = g.inc_s[base + slot];
+      src_slot[u] = (uint32_t)slot;
+      // source vertex of the slot: slot = koff[k] + i with koff non-decreasing in k
+      int k = 0;
+      while (k + 1 <= g.max_deg && s_koff[k + 1] <= slot) ++k;
+      src_bar[u] = bar0_addr + (uint32_t)(slot - s_koff[k]) * 16u;
+      const int nbr = __float_as_int(q.w) >> 1;
+      const int oc = nbr / Vc;
+      // bit 0 of dst_bar = "target lives in another CTA": only those go through the DSMEM path
+      // (ld/st.shared::cluster is several times slower than ld/st.shared even for the own CTA)
+      const bool remote = (oc != c);
+      dst_bar[u] = remote ? (mapa(bar0_addr + (uint32_t)(nbr - oc * Vc) * 16u, (uint32_t)oc) | 1u)
+                          : (bar0_addr + (uint32_t)(nbr - oc * Vc) * 16u);
+      // the target endpoint's incidence slot of this edge (global slot id -> owner chunk, local slot)
+      const int tslot = g.edge_slot[2 * g.inc_edge[base + slot] + 1];
+      int tc = oc;  // the target vertex lives in chunk oc, and so do its slots
+      dst_p4[u] = remote ? mapa(p4_addr + (uint32_t)(tslot - g.chunk_base[tc]) * 16u, (uint32_t)tc)
+                         : (p4_addr + (uint32_t)(tslot - g.chunk_base[tc]) * 16u);
+    }
   }
   cluster.sync();
 
-  const uint32_t bar_base[2] = {smem_u32(s_bar0), smem_u32(s_bar1)};
-  float4* const bars[2] = {s_bar0, s_bar1};
   const flame_b200_pd_params p = a.p;
 
   for (int it = 0; it < a.n_iters; ++it) {
-    const int par = it & 1;
-    const uint32_t cur_base = bar_base[par];
-    const float4* cur = bars[par];
-    float4* nxt = bars[par ^ 1];
-    const bool last = (it == a.n_iters - 1);
-    for (int i = tid; i < nv; i += nt) {
-      const float4 pr = s_prim[i];
-      const float4 own = cur[i];
-      float x = pr.x, w1 = pr.y, w2 = pr.z;
-      const int d = s_deg[i];
-      // software pipeline: the loads of incidence k+1 are issued before the arithmetic of k
-      float4 qn, sn, nbn;
-      if (d > 0) {
-        qn = s_q[i];
-        sn = s_s[i];
-        const uint32_t e = __float_as_uint(qn.w) >> 1;
-        nbn = ld_cluster_f4(mapa(cur_base + (e & LOC_MASK) * 16u, e >> LOC_SHIFT));
-      }
-      for (int k = 0; k < d; ++k) {
-        const float4 q = qn, s = sn, nb = nbn;
-        const int slot = s_koff[k] + i;
-        if (k + 1 < d) {
-          const int s2 = s_koff[k + 1] + i;
-          qn = s_q[s2];
-          sn = s_s[s2];
-          const uint32_t e = __float_as_uint(qn.w) >> 1;
-          nbn = ld_cluster_f4(mapa(cur_base + (e & LOC_MASK) * 16u, e >> LOC_SHIFT));
+    const uint32_t cur_off = (it & 1) ? bar_stride : 0u;
+    const float4* cur = (it & 1) ? s_bar1 : s_bar0;
+    float4* nxt = (it & 1) ? s_bar0 : s_bar1;
+    // ---- phase A: one dual update per edge, contributions pushed to both endpoints ----
+    // Rounds of PD_MLP edges: all operand loads of a round are issued before its arithmetic so the
+    // shared-memory / DSMEM latencies overlap.
+#pragma unroll
+    for (int u0 = 0; u0 < SPT; u0 += PD_MLP) {
+      float4 s[PD_MLP], bi[PD_MLP], bj[PD_MLP];
+#pragma unroll
+      for (int v = 0; v < PD_MLP; ++v) {
+        const int u = u0 + v;
+        if (u < SPT && tid + u * nt < ne) {
+          s[v] = s_s[tid + u * nt];
+          bi[v] = cur[(src_bar[u] - bar0_addr) >> 4];
+          bj[v] = (dst_bar[u] & 1u) ? ld_cluster_f4((dst_bar[u] & ~1u) + cur_off)
+                                    : ld_shared_f4(dst_bar[u] + cur_off);
         }
-        const int is_target = __float_as_int(q.w) & 1;
-        const float4 qu = is_target ? dual_update(q, s, nb, own, p.step_q) : dual_update(q, s, own, nb, p.step_q);
-        primal_apply(x, w1, w2, qu, s, is_target, p.step_x);
-        s_q[slot] = make_float4(qu.x, qu.y, qu.z, q.w);
       }
-      const VertexOut o = vertex_finish(x, w1, w2, pr.w, s_wt[i], pr.x, pr.y, pr.z, p);
-      s_prim[i] = o.prim;
-      nxt[i] = o.bar;
-      if (last) g.vprev[v0 + i] = make_float4(pr.x, pr.y, pr.z, 0.0f);
+#pragma unroll
+      for (int v = 0; v < PD_MLP; ++v) {
+        const int u = u0 + v;
+        if (u < SPT && tid + u * nt < ne) {
+          const float4 qu = dual_update(make_float4(q1[u], q2[u], q3[u], 0.f), s[v], bi[v], bj[v], p.step_q);
+          q1[u] = qu.x; q2[u] = qu.y; q3[u] = qu.z;
+          // primalStep contributions (cc:125-141), rounded as the reference: a = (q1*step_x)*alpha ...
+          const float pa = mul(mul(qu.x, p.step_x), s[v].x);
+          const float b2 = mul(mul(qu.y, p.step_x), s[v].y);
+          const float b3 = mul(mul(qu.z, p.step_x), s[v].y);
+          // source i: x -= a; w1 += a*dx; w2 += a*dy; w1 -= b2; w2 -= b3
+          s_p4[src_slot[u]] = make_float4(-pa, mul(pa, s[v].z), mul(pa, s[v].w), -b2);
+          s_p1[src_slot[u]] = -b3;
+          // target j: x += a; w1 += b2; w2 += b3   (u1 = u2 = -0.0f: exact no-ops)
+          if (dst_bar[u] & 1u) st_cluster_f4(dst_p4[u], make_float4(pa, b2, b3, neg0));
+          else st_shared_f4(dst_p4[u], make_float4(pa, b2, b3, neg0));
+        }
+      }
+    }
+    cluster_arrive();
+    cluster_wait();
+    // ---- phase B: ordered accumulation + prox + extragradient, one vertex per thread ----
+    if (hasv) {
+      const float x_old = x, w1_old = w1, w2_old = w2;
+#pragma unroll 4
+      for (int k = 0; k < deg; ++k) {
+        const int slot = s_koff[k] + tid;
+        const float4 p4 = s_p4[slot];
+        const float p1 = s_p1[slot];
+        x = add(x, p4.x);
+        w1 = add(w1, p4.y);
+        w2 = add(w2, p4.z);
+        w1 = add(w1, p4.w);
+        w2 = add(w2, p1);
+      }
+      const VertexOut o = vertex_finish(x, w1, w2, data, wt, x_old, w1_old, w2_old, p);
+      x = o.prim.x;
+      nxt[tid] = o.bar;
+      if (it == a.n_iters - 1) g.vprev[v0 + tid] = make_float4(x_old, w1_old, w2_old, 0.0f);
     }
     cluster_arrive();
     cluster_wait();
   }
 
-  // ---- write back ----
-  const float4* fin = bars[a.n_iters & 1];
-  for (int i = tid; i < nv; i += nt) {
-    g.vbar[v0 + i] = fin[i];
-    g.vprim[v0 + i] = s_prim[i];
+  // ---- write back (both private copies of every edge's q) ----
+  if (hasv) {
+    const float4* fin = (a.n_iters & 1) ? s_bar1 : s_bar0;
+    g.vbar[v0 + tid] = fin[tid];
+    g.vprim[v0 + tid] = make_float4(x, w1, w2, data);
   }
-  for (int k = tid; k < ni; k += nt) {
-    float4 q = s_q[k];
-    const uint32_t ent = __float_as_uint(q.w);
-    const uint32_t e = ent >> 1;
-    const int nbr = (int)(e >> LOC_SHIFT) * Vc + (int)(e & LOC_MASK);
-    q.w = __int_as_float((nbr << 1) | (int)(ent & 1u));
-    g.inc_q[base + k] = q;
+#pragma unroll
+  for (int u = 0; u < SPT; ++u) {
+    const int j = tid + u * nt;
+    if (j < ne) {
+      const int sslot = base + (int)src_slot[u];
+      const int tslot = g.edge_slot[2 * g.inc_edge[sslot] + 1];
+      g.inc_q[sslot] = make_float4(q1[u], q2[u], q3[u], __int_as_float(g.inc_nbr[sslot]));
+      g.inc_q[tslot] = make_float4(q1[u], q2[u], q3[u], __int_as_float(g.inc_nbr[tslot]));
+    }
   }
 }
 
-size_t pd_resident_smem(int Vc, int maxInc, int max_deg) {
-  return (size_t)maxInc * 32 + (size_t)Vc * (16 * 3 + 4 + 4) + (size_t)(max_deg + 1) * 4 + 128;
+size_t pd_resident_smem(int Vc, int maxInc, int maxEdges, int max_deg) {
+  return (size_t)Vc * 32 + (size_t)maxInc * (16 + 4) + (size_t)maxEdges * (16 + 4) +
+         (size_t)(max_deg + 2) * 4 + 128;
+}
+
+// The two register budgets the kernel is built for: (threads, owned edges per thread).
+bool pd_resident_variant(int Vc, int maxEdges, int* threads) {
+  int forced = 0;
+  if (const char* sv = getenv("FLAME_B200_THREADS")) forced = atoi(sv);
+  if (forced != 1024 && Vc <= 640 && maxEdges <= 640 * 4) {
+    *threads = 640;
+    return true;
+  }
+  if (Vc <= 1024 && maxEdges <= 1024 * 2) {
+    *threads = 1024;
+    return true;
+  }
+  return false;
 }
 
 int pd_resident_init() {
   static bool done = false;
   if (done) return 0;
-  FB_CUDA(cudaFuncSetAttribute(k_pd_resident, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  FB_CUDA(cudaFuncSetAttribute(k_pd_resident<640, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                227 * 1024));
-  FB_CUDA(cudaFuncSetAttribute(k_pd_resident, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  FB_CUDA(cudaFuncSetAttribute(k_pd_resident<640, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  FB_CUDA(cudaFuncSetAttribute(k_pd_resident<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024));
+  FB_CUDA(cudaFuncSetAttribute(k_pd_resident<1024, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   done = true;
   return 0;
 }
@@ -472,6 +625,7 @@ int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const Reside
   a.n_iters = n_iters;
   a.Vc = plan.Vc;
   a.maxInc = plan.maxInc;
+  a.maxEdges = plan.maxEdges;
   a.max_deg = plan.max_deg;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n * plan.cluster);
@@ -485,7 +639,11 @@ int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const Reside
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FB_CUDA(cudaLaunchKernelEx(&cfg, k_pd_resident, a));
+  if (plan.threads <= 640) {
+    FB_CUDA(cudaLaunchKernelEx(&cfg, k_pd_resident<640, 4>, a));
+  } else {
+    FB_CUDA(cudaLaunchKernelEx(&cfg, k_pd_resident<1024, 2>, a));
+  }
   count_launch();
   return 0;
 }
