@@ -43,6 +43,9 @@ struct Slot {
   MeshDev m{};
   int capT = 0;
   size_t cap_pix = 0;
+  int cap_tiles = 0;
+  int* d_tris = nullptr;            // owning pointers behind the const views in `m`
+  unsigned char* d_tri_ok = nullptr;
   float* d_mpos = nullptr;          // interpolate_mesh(): caller-supplied pos / values
   float* d_mvalues = nullptr;
   int capMV = 0;
@@ -58,6 +61,8 @@ struct flame_b200_ctx {
   std::vector<fb::Slot> slots;
   fb::GraphDev* d_graphs = nullptr;  // n_slots entries, mirrors slots[i].g
   fb::GraphDev* h_graphs = nullptr;  // pinned
+  fb::MeshDev* d_meshes = nullptr;   // n_slots entries, mirrors slots[i].m
+  fb::MeshDev* h_meshes = nullptr;   // pinned
   double* d_cost = nullptr;
   double* h_cost = nullptr;          // pinned, 2 doubles
   void* stereo = nullptr;
@@ -353,6 +358,13 @@ static void fill_or_copy(float* dst, const float* src, size_t n, float fill) {
   else std::fill(dst, dst + n, fill);
 }
 
+static int publish_mesh(flame_b200_ctx* c, int slot) {
+  c->h_meshes[slot] = c->slots[slot].m;
+  FB_CUDA(cudaMemcpyAsync(c->d_meshes + slot, c->h_meshes + slot, sizeof(MeshDev),
+                          cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
 static int publish_graph(flame_b200_ctx* c, int slot) {
   c->h_graphs[slot] = c->slots[slot].g;
   FB_CUDA(cudaMemcpyAsync(c->d_graphs + slot, c->h_graphs + slot, sizeof(GraphDev),
@@ -441,6 +453,10 @@ int flame_b200_ctx_create(int device, int n_slots, flame_b200_ctx** out) {
   FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_graphs), sizeof(GraphDev) * n_slots));
   FB_CUDA(cudaMemset(c->d_graphs, 0, sizeof(GraphDev) * n_slots));
   std::memset(c->h_graphs, 0, sizeof(GraphDev) * n_slots);
+  FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_meshes), sizeof(MeshDev) * n_slots));
+  FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_meshes), sizeof(MeshDev) * n_slots));
+  FB_CUDA(cudaMemset(c->d_meshes, 0, sizeof(MeshDev) * n_slots));
+  std::memset(c->h_meshes, 0, sizeof(MeshDev) * n_slots);
   FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_cost), 2 * sizeof(double)));
   FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_cost), 2 * sizeof(double)));
   if (int rc = pd_resident_init()) return rc;
@@ -456,8 +472,9 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
     for (void* p : {(void*)s.g.vprim, (void*)s.g.vbar, (void*)s.g.vbar2, (void*)s.g.vprev,
                     (void*)s.g.vwt, (void*)s.g.inc_q, (void*)s.g.inc_s, (void*)s.d_blob,
                     (void*)s.d_pos, (void*)s.d_values,
-                    (void*)s.m.tris, (void*)s.m.tri_ok, (void*)s.m.img, (void*)s.m.win,
-                    (void*)s.d_mpos, (void*)s.d_mvalues})
+                    (void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.m.img, (void*)s.m.setup,
+                    (void*)s.m.tile_count, (void*)s.m.tile_off, (void*)s.m.pairs, (void*)s.m.large,
+                    (void*)s.m.n_large, (void*)s.d_mpos, (void*)s.d_mvalues})
       if (p) cudaFree(p);
     if (s.h_blob) cudaFreeHost(s.h_blob);
     if (s.blob_free) cudaEventDestroy(s.blob_free);
@@ -465,6 +482,8 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
   stereo_destroy(c->stereo);
   cudaFree(c->d_graphs);
   cudaFreeHost(c->h_graphs);
+  cudaFree(c->d_meshes);
+  cudaFreeHost(c->h_meshes);
   cudaFree(c->d_cost);
   cudaFreeHost(c->h_cost);
   cudaStreamDestroy(c->stream);
@@ -725,20 +744,37 @@ static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* 
     }
   if (T > s.capT) {
     const int n = std::max(T, s.capT + s.capT / 2);
-    if (s.m.tris) FB_CUDA(cudaFree(s.m.tris));
-    if (s.m.tri_ok) FB_CUDA(cudaFree(s.m.tri_ok));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.tris), (size_t)n * 3 * sizeof(int)));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.tri_ok), (size_t)n));
+    for (void* p : {(void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.m.setup, (void*)s.m.pairs, (void*)s.m.large})
+      if (p) FB_CUDA(cudaFree(p));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_tris), (size_t)n * 3 * sizeof(int)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_tri_ok), (size_t)n));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.setup), (size_t)n * sizeof(TriSetup)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.pairs), (size_t)n * FB_MAX_TILES_PER_TRI * sizeof(int)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.large), (size_t)n * sizeof(int)));
     s.capT = n;
   }
   const size_t npix = (size_t)rows * cols;
   if (npix > s.cap_pix) {
     if (s.m.img) FB_CUDA(cudaFree(s.m.img));
-    if (s.m.win) FB_CUDA(cudaFree(s.m.win));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.img), npix * sizeof(float)));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.win), npix * sizeof(unsigned long long)));
     s.cap_pix = npix;
   }
+  const int n_tiles = raster_tile_count(rows, cols);
+  if (n_tiles > s.cap_tiles) {
+    if (s.m.tile_count) FB_CUDA(cudaFree(s.m.tile_count));
+    if (s.m.tile_off) FB_CUDA(cudaFree(s.m.tile_off));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.tile_count), (size_t)n_tiles * sizeof(int)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.tile_off), (size_t)(n_tiles + 1) * sizeof(int)));
+    s.cap_tiles = n_tiles;
+    FB_CUDA(cudaMemsetAsync(s.m.tile_count, 0, (size_t)n_tiles * sizeof(int), c->stream));
+  }
+  if (!s.m.n_large) {
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.n_large), 2 * sizeof(int)));
+    FB_CUDA(cudaMemsetAsync(s.m.n_large, 0, 2 * sizeof(int), c->stream));
+  }
+  s.m.n_tiles = n_tiles;
+  s.m.tris = s.d_tris;
+  s.m.tri_ok = s.d_tri_ok;
   s.m.T = T;
   s.m.rows = rows;
   s.m.cols = cols;
@@ -762,8 +798,8 @@ static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* 
         ok = vtx_valid[tris[3 * t]] && vtx_valid[tris[3 * t + 1]] && vtx_valid[tris[3 * t + 2]];
       hok[t] = ok ? 1 : 0;
     }
-    FB_CUDA(cudaMemcpyAsync(s.m.tris, ht, (size_t)T * 12, cudaMemcpyHostToDevice, c->stream));
-    FB_CUDA(cudaMemcpyAsync(s.m.tri_ok, hok, (size_t)T, cudaMemcpyHostToDevice, c->stream));
+    FB_CUDA(cudaMemcpyAsync(s.d_tris, ht, (size_t)T * 12, cudaMemcpyHostToDevice, c->stream));
+    FB_CUDA(cudaMemcpyAsync(s.d_tri_ok, hok, (size_t)T, cudaMemcpyHostToDevice, c->stream));
     FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
   }
   return 0;
@@ -778,22 +814,30 @@ int flame_b200_mesh_bind(flame_b200_ctx* c, int slot, int32_t T, const int32_t* 
     set_error("mesh_bind: slot has no graph");
     return FLAME_B200_ESTATE;
   }
-  return mesh_bind_impl(c, s, T, tris, s.g.V, vtx_valid, tri_valid, rows, cols);
+  if (int rc = mesh_bind_impl(c, s, T, tris, s.g.V, vtx_valid, tri_valid, rows, cols)) return rc;
+  s.m.pos = s.d_pos;
+  s.m.values = s.d_values;
+  return publish_mesh(c, slot);
 }
 
 int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float scale) {
   if (int rc = check_slot(c, slot0, n_slots)) return rc;
   if (int rc = use_device(c)) return rc;
+  int maxV = 0, maxT = 0, max_tiles = 0;
   for (int i = slot0; i < slot0 + n_slots; ++i) {
     Slot& s = c->slots[i];
-    if (!s.loaded || !s.m.img) {
+    if (!s.loaded || !s.m.img || s.m.values != s.d_values || s.m.pos != s.d_pos) {
       set_error("mesh_project: slot has no graph / bound mesh");
       return FLAME_B200_ESTATE;
     }
-    if (int rc = raster_values_from_graph(c->stream, s.g, scale, s.d_values)) return rc;
-    if (int rc = raster_project(c->stream, s.m, s.d_pos, s.d_values, 1)) return rc;
+    maxV = std::max(maxV, s.g.V);
+    maxT = std::max(maxT, s.m.T);
+    max_tiles = std::max(max_tiles, s.m.n_tiles);
   }
-  return 0;
+  if (int rc = raster_values_from_graph(c->stream, c->d_graphs + slot0, c->d_meshes + slot0, n_slots,
+                                        maxV, scale))
+    return rc;
+  return raster_project(c->stream, c->d_meshes + slot0, n_slots, maxT, max_tiles, 1);
 }
 
 int flame_b200_mesh_download(flame_b200_ctx* c, int slot, float* out_host) {
@@ -836,16 +880,20 @@ int flame_b200_interpolate_mesh(flame_b200_ctx* c, int slot, int32_t T, const in
   if (int rc = mesh_bind_impl(c, s, T, tris, V, vtx_valid, tri_valid, rows, cols)) return rc;
   if (V > 0)
     FB_CUDA(cudaMemcpyAsync(s.d_mpos, pos, (size_t)2 * V * 4, cudaMemcpyHostToDevice, c->stream));
+  s.m.pos = s.d_mpos;
+  s.m.values = s.d_mvalues;
+  if (int rc = publish_mesh(c, slot)) return rc;
   if (values) {
     if (V > 0)
       FB_CUDA(cudaMemcpyAsync(s.d_mvalues, values, (size_t)V * 4, cudaMemcpyHostToDevice, c->stream));
   } else {
-    if (int rc = raster_values_from_graph(c->stream, s.g, scale, s.d_mvalues)) return rc;
+    if (int rc = raster_values_from_graph(c->stream, c->d_graphs + slot, c->d_meshes + slot, 1, s.g.V, scale))
+      return rc;
   }
   const size_t npix = (size_t)rows * cols;
   if (!fill_nan)
     FB_CUDA(cudaMemcpyAsync(s.m.img, out_host, npix * 4, cudaMemcpyHostToDevice, c->stream));
-  if (int rc = raster_project(c->stream, s.m, s.d_mpos, s.d_mvalues, fill_nan)) return rc;
+  if (int rc = raster_project(c->stream, c->d_meshes + slot, 1, s.m.T, s.m.n_tiles, fill_nan)) return rc;
   FB_CUDA(cudaMemcpyAsync(out_host, s.m.img, npix * 4, cudaMemcpyDeviceToHost, c->stream));
   FB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;

@@ -50,12 +50,28 @@ struct GraphDev {
   int* edge_slot;   // [2E] (caller edge, role) -> incidence slot (written by the pack kernel)
 };
 
+struct TriSetup {  // per triangle, written by k_tri_setup
+  float A1, B1, C1, A2, B2, C2, A3, B3, C3;  // edge functions w1 = e23, w2 = e31, w3 = e12
+  float v1, v2, v3;                          // values at p1, p2, p3 (reversed triangle order)
+  int xmin, xend;                            // sweep columns [xmin, xend) (4-px groups)
+  int ymin, ymax;
+  int fx1;                                   // last footprint column, clamped to the image
+  int flags;                                 // 1: in the large list, 2: sweep wraps past the border
+};
+
 struct MeshDev {
-  int T, rows, cols;
-  int* tris;                  // 3T caller vertex indices
-  unsigned char* tri_ok;      // T: tri_valid && all three vtx_valid
-  float* img;                 // rows*cols
-  unsigned long long* win;    // rows*cols: (tri+1) << 32 | value bits
+  int T, rows, cols, n_tiles;
+  const int* tris;             // 3T caller vertex indices
+  const unsigned char* tri_ok; // T: tri_valid && all three vtx_valid (nullable)
+  const float* pos;            // 2V caller order
+  float* values;               // V caller order
+  float* img;                  // rows*cols
+  TriSetup* setup;             // T
+  int* tile_count;             // n_tiles (zero between projections)
+  int* tile_off;               // n_tiles + 1
+  int* pairs;                  // MAX_TILES_PER_TRI * T
+  int* large;                  // T
+  int* n_large;                // [0] accumulating, [1] current
 };
 
 // ---- PD (pd.cu) ----
@@ -97,9 +113,11 @@ inline size_t raw_f_offset(int field, int V, int E) {
 inline size_t raw_f_total(int V, int E) { return (size_t)13 * V + (size_t)5 * E; }
 
 // ---- dense projection (raster.cu) ----
-int raster_project(cudaStream_t st, const MeshDev& m, const float* pos /*2V caller order*/,
-                   const float* values /*V caller order*/, int fill_nan);
+int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_tiles, int fill_nan);
 // values[vperm[v]] = vprim[v].x * scale  (vtx_idepths_ = x * graph_scale_, flame.cc:376)
-int raster_values_from_graph(cudaStream_t st, const GraphDev& g, float scale, float* values);
+int raster_values_from_graph(cudaStream_t st, const GraphDev* gs_dev, const MeshDev* ms_dev, int n,
+                             int maxV, float scale);
+int raster_tile_count(int rows, int cols);
+#define FB_MAX_TILES_PER_TRI 64
 
 }  // namespace fb

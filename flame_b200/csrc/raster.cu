@@ -7,7 +7,7 @@
 //  - vertices are rounded to integer pixels with round-half-to-even (cv::Point2f -> cv::Point);
 //  - the triangle is drawn with its vertices REVERSED (Triangle emits CW, the rasteriser wants CCW);
 //  - a pixel is covered when all three edge functions are >= 0 (inclusive: shared edges and
-//    vertices are written by every covering triangle) — LAST triangle in the list wins;
+//    vertices are written by every covering triangle) — the LAST triangle in the list wins;
 //  - value = (v1*w1 + (v2*w2 + v3*w3)) / (w1 + (w2 + w3)), one IEEE divide, this association;
 //  - the reference sweeps the bounding box 4 pixels at a time and addresses the image LINEARLY
 //    (p.y*cols + p.x), so a degenerate (zero-area) triangle, whose edge functions vanish on a
@@ -16,113 +16,230 @@
 // Edge functions are integer-valued and exact in fp32 for images up to ~2896 px on a side
 // (|A*x + B*y + C| < 2^24), so direct evaluation equals the reference's incremental stepping.
 //
-// Round-1 implementation: "last triangle wins" is resolved with one 64-bit atomicMax per covered
-// pixel on key = (triangle_index + 1) << 32 | value_bits, then a resolve pass writes the image.
+// Formulation: the reference scatters triangles in order with read-modify-write; here every PIXEL
+// gathers "the highest-index triangle that covers me" from a per-tile bin and is written exactly
+// once (4*W*H bytes of image traffic instead of fill + per-triangle RMW):
+//   k_tri_setup   one thread per triangle: rounding, edge coefficients, footprint -> tile counts
+//   k_tile_scan   one CTA: exclusive scan of the tile counts
+//   k_tri_fill    one thread per triangle: (tile, triangle) pairs
+//   k_tile_raster one CTA per 32x8 tile: pixels walk the tile's bin (+ the short "large" list)
+// Triangles whose footprint spans more than MAX_TILES_PER_TRI tiles (hull slivers) or wraps past the
+// right image border (degenerate) go to the large list, which every tile scans; this bounds the
+// pair buffer at MAX_TILES_PER_TRI * T entries.
 #include <algorithm>
 
 #include "internal.h"
 
 namespace fb {
 
+#define TILE_W 32
+#define TILE_H 8
+#define MAX_TILES_PER_TRI FB_MAX_TILES_PER_TRI
+
 __device__ __forceinline__ int min3(int a, int b, int c) { return min(a, min(b, c)); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return max(a, max(b, c)); }
 
 // Edge::init (rasterization.h:129-153): A*x + B*y + C with separately rounded mul/add.
-struct EdgeFn {
-  float A, B, C;
-  __device__ __forceinline__ void init(int v0x, int v0y, int v1x, int v1y) {
-    A = (float)(v1y - v0y);
-    B = (float)(v0x - v1x);
-    C = (float)(v1x * v0y - v0x * v1y);
-  }
-  __device__ __forceinline__ float at(int x, int y) const {
-    return __fadd_rn(__fadd_rn(__fmul_rn(A, (float)x), __fmul_rn(B, (float)y)), C);
-  }
-};
+__device__ __forceinline__ float edge_at(float A, float B, float C, int x, int y) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(A, (float)x), __fmul_rn(B, (float)y)), C);
+}
 
-// One warp per triangle; lanes stride over the (4-px padded) bounding box.
-__global__ void __launch_bounds__(256)
-k_raster_scatter(MeshDev m, const float* __restrict__ pos, const float* __restrict__ values) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= m.T) return;
-  const int t = warp;
-  if (m.tri_ok && !m.tri_ok[t]) return;
+// Coverage + value of triangle `s` at sweep position (x, y); x may exceed cols-1 (4-px overshoot).
+__device__ __forceinline__ bool tri_eval(const TriSetup& s, int x, int y, float* val) {
+  if (y < s.ymin || y > s.ymax || x < s.xmin || x >= s.xend) return false;
+  const float w1 = edge_at(s.A1, s.B1, s.C1, x, y);
+  const float w2 = edge_at(s.A2, s.B2, s.C2, x, y);
+  const float w3 = edge_at(s.A3, s.B3, s.C3, x, y);
+  if (!(w1 >= 0.0f && w2 >= 0.0f && w3 >= 0.0f)) return false;
+  const float norm = __fadd_rn(w1, __fadd_rn(w2, w3));
+  const float num = __fadd_rn(__fmul_rn(s.v1, w1), __fadd_rn(__fmul_rn(s.v2, w2), __fmul_rn(s.v3, w3)));
+  *val = __fdiv_rn(num, norm);
+  return true;
+}
+
+__global__ void __launch_bounds__(256) k_tri_setup(const MeshDev* __restrict__ ms) {
+  const MeshDev m = ms[blockIdx.y];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m.T) return;
+  TriSetup s;
+  s.flags = 0;
+  s.fx1 = -1;
+  if (m.tri_ok && !m.tri_ok[t]) {
+    s.ymin = 1; s.ymax = 0; s.xmin = 0; s.xend = 0;  // empty footprint
+    m.setup[t] = s;
+    return;
+  }
   const int ia = m.tris[3 * t], ib = m.tris[3 * t + 1], ic = m.tris[3 * t + 2];
   // image_utils.cc:385-391: p1 = vertices[tri[2]], p2 = vertices[tri[1]], p3 = vertices[tri[0]]
-  const int p1x = __float2int_rn(pos[2 * ic]), p1y = __float2int_rn(pos[2 * ic + 1]);
-  const int p2x = __float2int_rn(pos[2 * ib]), p2y = __float2int_rn(pos[2 * ib + 1]);
-  const int p3x = __float2int_rn(pos[2 * ia]), p3y = __float2int_rn(pos[2 * ia + 1]);
-  const float v1 = values[ic], v2 = values[ib], v3 = values[ia];
+  const int p1x = __float2int_rn(m.pos[2 * ic]), p1y = __float2int_rn(m.pos[2 * ic + 1]);
+  const int p2x = __float2int_rn(m.pos[2 * ib]), p2y = __float2int_rn(m.pos[2 * ib + 1]);
+  const int p3x = __float2int_rn(m.pos[2 * ia]), p3y = __float2int_rn(m.pos[2 * ia + 1]);
+  s.v1 = m.values[ic]; s.v2 = m.values[ib]; s.v3 = m.values[ia];
+  s.xmin = min3(p1x, p2x, p3x); s.ymin = min3(p1y, p2y, p3y);
+  const int xmax = max3(p1x, p2x, p3x);
+  s.ymax = max3(p1y, p2y, p3y);
+  s.xend = s.xmin + ((xmax - s.xmin) / 4 + 1) * 4;  // columns visited by the 4-wide sweep
+  // w1 = e23, w2 = e31, w3 = e12 (rasterization.cc:177-179)
+  s.A1 = (float)(p3y - p2y); s.B1 = (float)(p2x - p3x); s.C1 = (float)(p3x * p2y - p2x * p3y);
+  s.A2 = (float)(p1y - p3y); s.B2 = (float)(p3x - p1x); s.C2 = (float)(p1x * p3y - p3x * p1y);
+  s.A3 = (float)(p2y - p1y); s.B3 = (float)(p1x - p2x); s.C3 = (float)(p2x * p1y - p1x * p2y);
+  const long long area2 = (long long)(p2x - p1x) * (p3y - p1y) - (long long)(p2y - p1y) * (p3x - p1x);
+  const bool degenerate = (area2 == 0);
+  // footprint in pixels: a non-degenerate triangle covers nothing outside [xmin, xmax]
+  const int fx0 = max(s.xmin, 0), fy0 = max(s.ymin, 0);
+  const int fx1 = min(degenerate ? s.xend - 1 : xmax, m.cols - 1), fy1 = min(s.ymax, m.rows - 1);
+  const bool wraps = degenerate && (s.xend > m.cols);
+  s.fx1 = fx1;
+  const int tx0 = fx0 / TILE_W, tx1 = fx1 / TILE_W, ty0 = fy0 / TILE_H, ty1 = fy1 / TILE_H;
+  const long long ntiles = (fx1 >= fx0 && fy1 >= fy0) ? (long long)(tx1 - tx0 + 1) * (ty1 - ty0 + 1) : 0;
+  if (wraps || ntiles > MAX_TILES_PER_TRI) {
+    s.flags = 1 | (wraps ? 2 : 0);
+    m.large[atomicAdd(&m.n_large[0], 1)] = t;
+  } else {
+    const int tiles_x = (m.cols + TILE_W - 1) / TILE_W;
+    for (int ty = ty0; ty <= ty1 && ntiles > 0; ++ty)
+      for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&m.tile_count[ty * tiles_x + tx], 1);
+  }
+  m.setup[t] = s;
+}
 
-  const int xmin = min3(p1x, p2x, p3x), ymin = min3(p1y, p2y, p3y);
-  const int xmax = max3(p1x, p2x, p3x), ymax = max3(p1y, p2y, p3y);
-  EdgeFn e23, e31, e12;
-  e23.init(p2x, p2y, p3x, p3y);  // w1
-  e31.init(p3x, p3y, p1x, p1y);  // w2
-  e12.init(p1x, p1y, p2x, p2y);  // w3
-
-  const int wg = ((xmax - xmin) / 4 + 1) * 4;  // columns visited by the 4-wide sweep
-  const int hg = ymax - ymin + 1;
-  const long long npix = (long long)m.rows * m.cols;
-  const unsigned long long key_hi = (unsigned long long)(t + 1) << 32;
-  for (int idx = lane; idx < wg * hg; idx += 32) {
-    const int y = ymin + idx / wg;
-    const int x = xmin + idx % wg;
-    const float w1 = e23.at(x, y), w2 = e31.at(x, y), w3 = e12.at(x, y);
-    if (w1 >= 0.0f && w2 >= 0.0f && w3 >= 0.0f) {
-      const float norm = __fadd_rn(w1, __fadd_rn(w2, w3));
-      const float num =
-          __fadd_rn(__fmul_rn(v1, w1), __fadd_rn(__fmul_rn(v2, w2), __fmul_rn(v3, w3)));
-      const float val = __fdiv_rn(num, norm);
-      const long long addr = (long long)y * m.cols + x;  // linear, as the reference's pointer math
-      if (addr >= 0 && addr < npix)
-        atomicMax(&m.win[addr], key_hi | (unsigned long long)__float_as_uint(val));
-    }
+// one CTA of 1024 threads: exclusive scan of tile_count -> tile_off (n_tiles + 1), zero the cursors
+__global__ void __launch_bounds__(1024) k_tile_scan(const MeshDev* __restrict__ ms) {
+  const MeshDev m = ms[blockIdx.y];
+  __shared__ int s_part[1024];
+  const int n = m.n_tiles;
+  const int per = (n + 1023) / 1024;
+  const int a = min(threadIdx.x * per, n), b = min(a + per, n);
+  int sum = 0;
+  for (int i = a; i < b; ++i) sum += m.tile_count[i];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = (threadIdx.x >= o) ? s_part[threadIdx.x - o] : 0;
+    __syncthreads();
+    s_part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = s_part[threadIdx.x] - sum;  // exclusive prefix of this thread's range
+  for (int i = a; i < b; ++i) {
+    const int cnt = m.tile_count[i];
+    m.tile_off[i] = run;
+    m.tile_count[i] = 0;  // reused as the fill cursor
+    run += cnt;
+  }
+  if (threadIdx.x == 1023) m.tile_off[n] = s_part[1023];
+  if (threadIdx.x == 0) {  // latch the large-list length for this projection, re-arm the counter
+    m.n_large[1] = m.n_large[0];
+    m.n_large[0] = 0;
   }
 }
 
-__global__ void __launch_bounds__(256) k_raster_resolve(MeshDev m, int fill_nan) {
-  const long long n = (long long)m.rows * m.cols;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const unsigned long long k = m.win[i];
-    if (k != 0ull) {
-      m.img[i] = __uint_as_float((unsigned int)(k & 0xffffffffull));
-    } else if (fill_nan) {
-      m.img[i] = __uint_as_float(0x7fc00000u);  // std::numeric_limits<float>::quiet_NaN()
+__global__ void __launch_bounds__(256) k_tri_fill(const MeshDev* __restrict__ ms) {
+  const MeshDev m = ms[blockIdx.y];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m.T) return;
+  const TriSetup s = m.setup[t];
+  if (s.flags & 1) return;  // in the large list
+  if (s.ymin > s.ymax) return;
+  // exactly the footprint counted in k_tri_setup
+  const int fx0 = max(s.xmin, 0), fy0 = max(s.ymin, 0);
+  const int fx1 = s.fx1, fy1 = min(s.ymax, m.rows - 1);
+  if (fx1 < fx0 || fy1 < fy0) return;
+  const int tiles_x = (m.cols + TILE_W - 1) / TILE_W;
+  for (int ty = fy0 / TILE_H; ty <= fy1 / TILE_H; ++ty)
+    for (int tx = fx0 / TILE_W; tx <= fx1 / TILE_W; ++tx) {
+      const int tile = ty * tiles_x + tx;
+      m.pairs[m.tile_off[tile] + atomicAdd(&m.tile_count[tile], 1)] = t;
+    }
+}
+
+__global__ void __launch_bounds__(TILE_W * TILE_H) k_tile_raster(const MeshDev* __restrict__ ms, int fill_nan) {
+  const MeshDev m = ms[blockIdx.y];
+  const int tiles_x = (m.cols + TILE_W - 1) / TILE_W;
+  const int tile = blockIdx.x;
+  if (tile >= m.n_tiles) return;
+  const int tx = tile % tiles_x, ty = tile / tiles_x;
+  const int px = tx * TILE_W + (threadIdx.x % TILE_W), py = ty * TILE_H + (threadIdx.x / TILE_W);
+  __shared__ TriSetup s_tri[64];
+  __shared__ int s_id[64];
+  const int beg = m.tile_off[tile], n_bin = m.tile_off[tile + 1] - beg;
+  const int n_large = m.n_large[1];
+  const int n = n_bin + n_large;
+  int best = -1;
+  float best_val = 0.0f;
+  for (int c0 = 0; c0 < n; c0 += 64) {
+    const int nc = min(64, n - c0);
+    __syncthreads();
+    if (threadIdx.x < nc) {
+      const int e = c0 + threadIdx.x;
+      const int t = (e < n_bin) ? m.pairs[beg + e] : m.large[e - n_bin];
+      s_id[threadIdx.x] = t;
+      s_tri[threadIdx.x] = m.setup[t];
+    }
+    __syncthreads();
+    if (px < m.cols && py < m.rows) {
+      for (int j = 0; j < nc; ++j) {
+        const int t = s_id[j];
+        if (t < best) continue;  // a later triangle already owns this pixel
+        float v;
+        bool hit = tri_eval(s_tri[j], px, py, &v);
+        // degenerate triangle whose 4-px sweep ran past the right border: the reference's linear
+        // addressing lands on (x - cols, y + 1)
+        if (!hit && (s_tri[j].flags & 2)) hit = tri_eval(s_tri[j], px + m.cols, py - 1, &v);
+        if (hit) {
+          best = t;
+          best_val = v;
+        }
+      }
     }
   }
+  if (px < m.cols && py < m.rows) {
+    const size_t i = (size_t)py * m.cols + px;
+    if (best >= 0) m.img[i] = best_val;
+    else if (fill_nan) m.img[i] = __uint_as_float(0x7fc00000u);  // quiet_NaN, flame.cc:412
+  }
+  if (threadIdx.x == 0) m.tile_count[tile] = 0;  // fill cursor -> zero for the next projection
 }
 
-__global__ void k_values_from_graph(GraphDev g, float scale, float* __restrict__ values) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= g.V) return;
-  values[g.vperm[v]] = __fmul_rn(g.vprim[v].x, scale);  // flame.cc:376
+__global__ void k_values_from_graph(const GraphDev* __restrict__ gs, const MeshDev* __restrict__ ms,
+                                    float scale) {
+  const GraphDev g = gs[blockIdx.y];
+  const MeshDev m = ms[blockIdx.y];
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < g.V; v += gridDim.x * blockDim.x)
+    m.values[g.vperm[v]] = __fmul_rn(g.vprim[v].x, scale);  // vtx_idepths_ = x * graph_scale_, flame.cc:376
 }
 
-int raster_values_from_graph(cudaStream_t st, const GraphDev& g, float scale, float* values) {
-  if (g.V == 0) return 0;
-  k_values_from_graph<<<(g.V + 255) / 256, 256, 0, st>>>(g, scale, values);
+int raster_values_from_graph(cudaStream_t st, const GraphDev* gs_dev, const MeshDev* ms_dev, int n,
+                             int maxV, float scale) {
+  if (maxV == 0 || n == 0) return 0;
+  k_values_from_graph<<<dim3(std::min((maxV + 255) / 256, 64), n), 256, 0, st>>>(gs_dev, ms_dev, scale);
   count_launch();
   FB_CUDA(cudaGetLastError());
   return 0;
 }
 
-int raster_project(cudaStream_t st, const MeshDev& m, const float* pos, const float* values,
-                   int fill_nan) {
-  const size_t n = (size_t)m.rows * m.cols;
-  FB_CUDA(cudaMemsetAsync(m.win, 0, n * sizeof(unsigned long long), st));
-  if (m.T > 0) {
-    const int warps_per_block = 256 / 32;
-    k_raster_scatter<<<(m.T + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(m, pos, values);
+// ms_dev: device array of n MeshDev; the per-slot tile_count / n_large words are contiguous in
+// `zero_base` (zero_bytes per slot) so one memset clears the whole batch when `zero_stride` is 0.
+int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_tiles, int fill_nan) {
+  if (n == 0 || max_tiles == 0) return 0;
+  if (maxT > 0) {
+    k_tri_setup<<<dim3((maxT + 255) / 256, n), 256, 0, st>>>(ms_dev);
     count_launch();
   }
-  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
-  k_raster_resolve<<<blocks, 256, 0, st>>>(m, fill_nan);
+  k_tile_scan<<<dim3(1, n), 1024, 0, st>>>(ms_dev);
+  count_launch();
+  if (maxT > 0) {
+    k_tri_fill<<<dim3((maxT + 255) / 256, n), 256, 0, st>>>(ms_dev);
+    count_launch();
+  }
+  k_tile_raster<<<dim3(max_tiles, n), TILE_W * TILE_H, 0, st>>>(ms_dev, fill_nan);
   count_launch();
   FB_CUDA(cudaGetLastError());
   return 0;
+}
+
+int raster_tile_count(int rows, int cols) {
+  return ((cols + TILE_W - 1) / TILE_W) * ((rows + TILE_H - 1) / TILE_H);
 }
 
 }  // namespace fb
