@@ -350,7 +350,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
-    ap.add_argument("--pipelines", type=int, default=4, help="host threads / streams for the e2e leg")
+    ap.add_argument("--pipelines", type=int, default=16, help="host threads / streams for the e2e leg")
     ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 stream, 2 resident")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -832,7 +832,7 @@ int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float sca
     }
     maxV = std::max(maxV, s.g.V);
     maxT = std::max(maxT, s.m.T);
-    max_tiles = std::max(max_tiles, s.m.n_tiles);
+    max_tiles = std::max(max_tiles, raster_cta_count(s.m.rows, s.m.cols));
   }
   if (int rc = raster_values_from_graph(c->stream, c->d_graphs + slot0, c->d_meshes + slot0, n_slots,
                                         maxV, scale))
@@ -893,7 +893,7 @@ int flame_b200_interpolate_mesh(flame_b200_ctx* c, int slot, int32_t T, const in
   const size_t npix = (size_t)rows * cols;
   if (!fill_nan)
     FB_CUDA(cudaMemcpyAsync(s.m.img, out_host, npix * 4, cudaMemcpyHostToDevice, c->stream));
-  if (int rc = raster_project(c->stream, c->d_meshes + slot, 1, s.m.T, s.m.n_tiles, fill_nan)) return rc;
+  if (int rc = raster_project(c->stream, c->d_meshes + slot, 1, s.m.T, raster_cta_count(rows, cols), fill_nan)) return rc;
   FB_CUDA(cudaMemcpyAsync(out_host, s.m.img, npix * 4, cudaMemcpyDeviceToHost, c->stream));
   FB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;

@@ -113,11 +113,12 @@ inline size_t raw_f_offset(int field, int V, int E) {
 inline size_t raw_f_total(int V, int E) { return (size_t)13 * V + (size_t)5 * E; }
 
 // ---- dense projection (raster.cu) ----
-int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_tiles, int fill_nan);
+int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_ctas, int fill_nan);
 // values[vperm[v]] = vprim[v].x * scale  (vtx_idepths_ = x * graph_scale_, flame.cc:376)
 int raster_values_from_graph(cudaStream_t st, const GraphDev* gs_dev, const MeshDev* ms_dev, int n,
                              int maxV, float scale);
 int raster_tile_count(int rows, int cols);
-#define FB_MAX_TILES_PER_TRI 64
+int raster_cta_count(int rows, int cols);
+#define FB_MAX_TILES_PER_TRI 128
 
 }  // namespace fb

@@ -22,7 +22,9 @@
 //   k_tri_setup   one thread per triangle: rounding, edge coefficients, footprint -> tile counts
 //   k_tile_scan   one CTA: exclusive scan of the tile counts
 //   k_tri_fill    one thread per triangle: (tile, triangle) pairs
-//   k_tile_raster one CTA per 32x8 tile: pixels walk the tile's bin (+ the short "large" list)
+//   k_tile_raster one CTA per 32x8 pixel block = four 8x8 tiles, two warps per tile: pixels walk
+//                 their tile's bin (+ the short "large" list); bins hold only triangles whose
+//                 edge functions do not exclude the whole tile (exact integer box test)
 // Triangles whose footprint spans more than MAX_TILES_PER_TRI tiles (hull slivers) or wraps past the
 // right image border (degenerate) go to the large list, which every tile scans; this bounds the
 // pair buffer at MAX_TILES_PER_TRI * T entries.
@@ -32,8 +34,9 @@
 
 namespace fb {
 
-#define TILE_W 32
+#define TILE_W 8
 #define TILE_H 8
+#define CTA_TILES 4   // a CTA rasterises CTA_TILES horizontally adjacent tiles (32 x 8 pixels)
 #define MAX_TILES_PER_TRI FB_MAX_TILES_PER_TRI
 
 __device__ __forceinline__ int min3(int a, int b, int c) { return min(a, min(b, c)); }
@@ -55,6 +58,16 @@ __device__ __forceinline__ bool tri_eval(const TriSetup& s, int x, int y, float*
   const float num = __fadd_rn(__fmul_rn(s.v1, w1), __fadd_rn(__fmul_rn(s.v2, w2), __fmul_rn(s.v3, w3)));
   *val = __fdiv_rn(num, norm);
   return true;
+}
+
+// Conservative-exact test "does the closed triangle (all three w >= 0) miss the pixel box
+// [x0,x1] x [y0,y1] entirely?": an edge function that is negative at its most favourable corner is
+// negative on the whole box. Integer-valued floats: exact.
+__device__ __forceinline__ bool tile_outside(const TriSetup& s, int x0, int y0, int x1, int y1) {
+  const float m1 = edge_at(s.A1, s.B1, s.C1, s.A1 >= 0.0f ? x1 : x0, s.B1 >= 0.0f ? y1 : y0);
+  const float m2 = edge_at(s.A2, s.B2, s.C2, s.A2 >= 0.0f ? x1 : x0, s.B2 >= 0.0f ? y1 : y0);
+  const float m3 = edge_at(s.A3, s.B3, s.C3, s.A3 >= 0.0f ? x1 : x0, s.B3 >= 0.0f ? y1 : y0);
+  return (m1 < 0.0f) || (m2 < 0.0f) || (m3 < 0.0f);
 }
 
 __global__ void __launch_bounds__(256) k_tri_setup(const MeshDev* __restrict__ ms) {
@@ -98,8 +111,14 @@ __global__ void __launch_bounds__(256) k_tri_setup(const MeshDev* __restrict__ m
   } else {
     const int tiles_x = (m.cols + TILE_W - 1) / TILE_W;
     for (int ty = ty0; ty <= ty1 && ntiles > 0; ++ty)
-      for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&m.tile_count[ty * tiles_x + tx], 1);
+      for (int tx = tx0; tx <= tx1; ++tx) {
+        if (!degenerate && tile_outside(s, tx * TILE_W, ty * TILE_H, tx * TILE_W + TILE_W - 1,
+                                        ty * TILE_H + TILE_H - 1))
+          continue;
+        atomicAdd(&m.tile_count[ty * tiles_x + tx], 1);
+      }
   }
+  if (degenerate) s.flags |= 4;
   m.setup[t] = s;
 }
 
@@ -148,44 +167,63 @@ __global__ void __launch_bounds__(256) k_tri_fill(const MeshDev* __restrict__ ms
   const int tiles_x = (m.cols + TILE_W - 1) / TILE_W;
   for (int ty = fy0 / TILE_H; ty <= fy1 / TILE_H; ++ty)
     for (int tx = fx0 / TILE_W; tx <= fx1 / TILE_W; ++tx) {
+      if (!(s.flags & 4) && tile_outside(s, tx * TILE_W, ty * TILE_H, tx * TILE_W + TILE_W - 1,
+                                         ty * TILE_H + TILE_H - 1))
+        continue;
       const int tile = ty * tiles_x + tx;
       m.pairs[m.tile_off[tile] + atomicAdd(&m.tile_count[tile], 1)] = t;
     }
 }
 
-__global__ void __launch_bounds__(TILE_W * TILE_H) k_tile_raster(const MeshDev* __restrict__ ms, int fill_nan) {
+#define RCHUNK 16
+__global__ void __launch_bounds__(256) k_tile_raster(const MeshDev* __restrict__ ms, int fill_nan) {
   const MeshDev m = ms[blockIdx.y];
   const int tiles_x = (m.cols + TILE_W - 1) / TILE_W;
-  const int tile = blockIdx.x;
-  if (tile >= m.n_tiles) return;
-  const int tx = tile % tiles_x, ty = tile / tiles_x;
-  const int px = tx * TILE_W + (threadIdx.x % TILE_W), py = ty * TILE_H + (threadIdx.x / TILE_W);
-  __shared__ TriSetup s_tri[64];
-  __shared__ int s_id[64];
-  const int beg = m.tile_off[tile], n_bin = m.tile_off[tile + 1] - beg;
+  const int ctas_x = (tiles_x + CTA_TILES - 1) / CTA_TILES;
+  const int cy = blockIdx.x / ctas_x, cx = blockIdx.x % ctas_x;
+  if (cy * TILE_H >= m.rows) return;
+  const int sub = threadIdx.x >> 6;          // tile within the CTA (two warps each)
+  const int lt = threadIdx.x & 63;           // pixel within the tile
+  const int tx = cx * CTA_TILES + sub, ty = cy;
+  const bool tile_ok = tx < tiles_x;
+  const int tile = ty * tiles_x + tx;
+  const int px = tx * TILE_W + (lt & 7), py = ty * TILE_H + (lt >> 3);
+  __shared__ TriSetup s_tri[CTA_TILES][RCHUNK];
+  __shared__ int s_id[CTA_TILES][RCHUNK];
+  const int beg = tile_ok ? m.tile_off[tile] : 0;
+  const int n_bin = tile_ok ? m.tile_off[tile + 1] - beg : 0;
   const int n_large = m.n_large[1];
   const int n = n_bin + n_large;
+  // all four tiles iterate the same number of chunks (barriers are CTA-wide)
+  int n_max = n;
+  __shared__ int s_nmax;
+  if (threadIdx.x == 0) s_nmax = 0;
+  __syncthreads();
+  if (lt == 0) atomicMax(&s_nmax, n);
+  __syncthreads();
+  n_max = s_nmax;
   int best = -1;
   float best_val = 0.0f;
-  for (int c0 = 0; c0 < n; c0 += 64) {
-    const int nc = min(64, n - c0);
+  const bool live = tile_ok && px < m.cols && py < m.rows;
+  for (int c0 = 0; c0 < n_max; c0 += RCHUNK) {
+    const int nc = max(0, min(RCHUNK, n - c0));
     __syncthreads();
-    if (threadIdx.x < nc) {
-      const int e = c0 + threadIdx.x;
+    if (lt < nc) {
+      const int e = c0 + lt;
       const int t = (e < n_bin) ? m.pairs[beg + e] : m.large[e - n_bin];
-      s_id[threadIdx.x] = t;
-      s_tri[threadIdx.x] = m.setup[t];
+      s_id[sub][lt] = t;
+      s_tri[sub][lt] = m.setup[t];
     }
     __syncthreads();
-    if (px < m.cols && py < m.rows) {
+    if (live) {
       for (int j = 0; j < nc; ++j) {
-        const int t = s_id[j];
+        const int t = s_id[sub][j];
         if (t < best) continue;  // a later triangle already owns this pixel
         float v;
-        bool hit = tri_eval(s_tri[j], px, py, &v);
+        bool hit = tri_eval(s_tri[sub][j], px, py, &v);
         // degenerate triangle whose 4-px sweep ran past the right border: the reference's linear
         // addressing lands on (x - cols, y + 1)
-        if (!hit && (s_tri[j].flags & 2)) hit = tri_eval(s_tri[j], px + m.cols, py - 1, &v);
+        if (!hit && (s_tri[sub][j].flags & 2)) hit = tri_eval(s_tri[sub][j], px + m.cols, py - 1, &v);
         if (hit) {
           best = t;
           best_val = v;
@@ -193,12 +231,12 @@ __global__ void __launch_bounds__(TILE_W * TILE_H) k_tile_raster(const MeshDev* 
       }
     }
   }
-  if (px < m.cols && py < m.rows) {
+  if (live) {
     const size_t i = (size_t)py * m.cols + px;
     if (best >= 0) m.img[i] = best_val;
     else if (fill_nan) m.img[i] = __uint_as_float(0x7fc00000u);  // quiet_NaN, flame.cc:412
   }
-  if (threadIdx.x == 0) m.tile_count[tile] = 0;  // fill cursor -> zero for the next projection
+  if (tile_ok && lt == 0) m.tile_count[tile] = 0;  // fill cursor -> zero for the next projection
 }
 
 __global__ void k_values_from_graph(const GraphDev* __restrict__ gs, const MeshDev* __restrict__ ms,
@@ -220,8 +258,8 @@ int raster_values_from_graph(cudaStream_t st, const GraphDev* gs_dev, const Mesh
 
 // ms_dev: device array of n MeshDev; the per-slot tile_count / n_large words are contiguous in
 // `zero_base` (zero_bytes per slot) so one memset clears the whole batch when `zero_stride` is 0.
-int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_tiles, int fill_nan) {
-  if (n == 0 || max_tiles == 0) return 0;
+int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_ctas, int fill_nan) {
+  if (n == 0 || max_ctas == 0) return 0;
   if (maxT > 0) {
     k_tri_setup<<<dim3((maxT + 255) / 256, n), 256, 0, st>>>(ms_dev);
     count_launch();
@@ -232,7 +270,7 @@ int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int 
     k_tri_fill<<<dim3((maxT + 255) / 256, n), 256, 0, st>>>(ms_dev);
     count_launch();
   }
-  k_tile_raster<<<dim3(max_tiles, n), TILE_W * TILE_H, 0, st>>>(ms_dev, fill_nan);
+  k_tile_raster<<<dim3(max_ctas, n), 256, 0, st>>>(ms_dev, fill_nan);
   count_launch();
   FB_CUDA(cudaGetLastError());
   return 0;
@@ -240,6 +278,10 @@ int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int 
 
 int raster_tile_count(int rows, int cols) {
   return ((cols + TILE_W - 1) / TILE_W) * ((rows + TILE_H - 1) / TILE_H);
+}
+int raster_cta_count(int rows, int cols) {
+  const int tiles_x = (cols + TILE_W - 1) / TILE_W;
+  return ((tiles_x + CTA_TILES - 1) / CTA_TILES) * ((rows + TILE_H - 1) / TILE_H);
 }
 
 }  // namespace fb
