@@ -179,8 +179,10 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
 
+    from flame_b200 import shard
     B = args.batch
-    frames, (W, H, V, iters) = _frames(B, first=rank * B)
+    ids = shard.frames_for_rank(rank, world, B)  # frames shard by rank: no data-path collective
+    frames, (W, H, V, iters) = _frames(B, first=ids[0])
     p = _lib.default_pd_params()
     ctx = _lib.Context(local_rank, B)
     for i, g in enumerate(frames):
@@ -224,10 +226,7 @@ def run_ours(args, rank, world, local_rank):
     ms_total = e0.elapsed_time(e1)
     pd_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     clocks = sampler.stop()
-    if dist is not None:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_total = shard.max_over_ranks(ms_total, dev)
     value = world * B * args.steps / (ms_total * 1e-3)
 
     # ---- single-frame latency (one cluster per frame, B = 1) ----
@@ -245,11 +244,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- e2e: host buffers in, host buffers out, through the public C ABI ----
     e2e = run_e2e(args, local_rank, frames, (W, H, V, iters), barrier)
-    if dist is not None:
-        t = torch.tensor([e2e["seconds"]], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e["seconds"] = float(t.item())
-    e2e_value = world * e2e["frames"] / e2e["seconds"]
+    e2e_value = shard.aggregate_throughput(e2e["frames"], e2e["seconds"], dev)
 
     if rank == 0:
         E = int(np.mean([g["edges"].shape[0] for g in frames]))

@@ -137,3 +137,15 @@ def test_pd_errors(gpu_ctx):
     bad[0, 0] = 10 ** 6
     with pytest.raises(_lib.FlameB200Error):
         gpu_ctx.graph_init(0, g["pos"], g["data_term"], bad)
+
+
+def test_cpp_adapter_against_reference_code():
+    """include/flame_b200_adapter.hpp (the reference's call signatures over the C ABI) vs the
+    reference's own dgraph::step / DrawShadedTriangleBarycentric compiled verbatim, in one C++ binary."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "adapter_test")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/adapter_test not built (needs /root/reference at build time)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ADAPTER_OK" in out.stdout, out.stdout + out.stderr
