@@ -242,6 +242,28 @@ def run_ours(args, rank, world, local_rank):
         lat.append(a.elapsed_time(b))
     lat_ms = float(np.median(lat))
 
+    # ---- epipolar search (config C: 1280x720, 5000 features), reported as features/s ----
+    search = None
+    if rank == 0 and not args.no_search:
+        from flame_b200 import synth
+        Wc, Hc, Vc_, _ = synth.CONFIGS["C"]
+        K, Kinv, sframes = synth.make_stereo_pair(Wc, Hc)
+        feats0 = synth.make_features(synth.config_graph("C")["pos"], Wc, Hc)
+        ctx.set_camera(Wc, Hc, K, Kinv)
+        for i, fr in enumerate(sframes):
+            ctx.frame_upload(i, fr["img_pad"], fr["gradx_pad"], fr["grady_pad"], synth.PAD, fr["pose"])
+        tp = _lib.default_track_params()
+        ts = []
+        for _ in range(8):
+            f = feats0.copy()
+            t0 = time.perf_counter()
+            n_upd, _ = ctx.update_feature_idepths(tp, 1, 0, f, want_diag=False)
+            ts.append(time.perf_counter() - t0)
+        t_med = float(np.median(ts[2:]))
+        search = {"workload": "config C: 1280x720, %d features, host records in/out" % len(feats0),
+                  "ms_per_call": 1e3 * t_med, "features_per_s": len(feats0) / t_med, "updates": int(n_upd),
+                  "note": "latency/divergence-bound walk along the epipolar line; no HBM fraction quoted"}
+
     # ---- e2e: host buffers in, host buffers out, through the public C ABI ----
     e2e = run_e2e(args, local_rank, frames, (W, H, V, iters), barrier)
     e2e_value = shard.aggregate_throughput(e2e["frames"], e2e["seconds"], dev)
@@ -278,6 +300,8 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": e2e["d2h"], "frames_per_step": e2e["per_step"],
                     "pipelines": e2e["pipelines"]},
         }
+        if search is not None:
+            line["search"] = search
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
@@ -348,6 +372,7 @@ def main():
     ap.add_argument("--pipelines", type=int, default=16, help="host threads / streams for the e2e leg")
     ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 stream, 2 resident")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-search", action="store_true", help="skip the epipolar-search side measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
