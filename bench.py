@@ -127,23 +127,49 @@ def cpu_baseline(budget_s=12.0):
                       % (n, CFG, W, H, V, iters, _CPU_DESC[_cpu_kind(pyoracle)], dt)}
 
 
+def _ref_worker(conn, n_frames_max, iters):
+    """One worker PROCESS = one Flame instance on one core: runs whole frames until told to stop."""
+    from flame_b200 import synth
+    from oracle import pyoracle
+    frames, _ = _frames(1)
+    g = frames[0]
+    conn.send("ready")
+    while True:
+        n = conn.recv()
+        if n <= 0:
+            break
+        for _ in range(n):
+            _cpu_frame(pyoracle, synth, g, iters)
+        conn.send(n)
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path on the host cores: independent frames in
-    parallel, one thread per frame (each Flame instance runs step() on one thread)."""
+    parallel, one single-threaded worker process per core (each Flame instance runs step() on one
+    thread, flame.cc:100-111). A step = one frame per core."""
     if rank != 0:
         return
-    from concurrent.futures import ThreadPoolExecutor
-    from flame_b200 import synth
+    import multiprocessing as mp
     from oracle import pyoracle
     pyoracle.build()
     cores = os.cpu_count() or 1
-    frames, (W, H, V, iters) = _frames(min(cores, 8))
+    W, H, V, iters = __import__("flame_b200.synth", fromlist=["CONFIGS"]).CONFIGS[CFG]
+    ctx = mp.get_context("fork")
+    workers = []
+    for _ in range(cores):
+        a, b = ctx.Pipe()
+        p = ctx.Process(target=_ref_worker, args=(b, 0, iters), daemon=True)
+        p.start()
+        workers.append((p, a))
+    for _, a in workers:
+        a.recv()
     per_step = cores  # one frame per core per step
-    pool = ThreadPoolExecutor(cores)
 
     def step():
-        list(pool.map(lambda i: _cpu_frame(pyoracle, synth, frames[i % len(frames)], iters),
-                      range(per_step)))
+        for _, a in workers:
+            a.send(1)
+        for _, a in workers:
+            a.recv()
 
     for _ in range(args.warmup):
         step()
@@ -151,16 +177,21 @@ def run_reference(args, rank, world):
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
+    for p, a in workers:
+        a.send(0)
+    for p, _ in workers:
+        p.join(timeout=10)
     val = per_step * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "config D: 1920x1080, 10k vertices, 200 PD iters + dense projection",
+        "config": {"workload": "config D: 1920x1080, V=%d, %d PD iters + dense projection" % (V, iters),
                    "frames_per_step": per_step},
         "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": _cpu_kind(pyoracle),
-                         "sample": "%d frames per step (one per core, each frame on one thread), %s"
+                         "sample": "%d frames per step (one per core; one single-threaded worker process per "
+                                   "core, as each Flame instance runs step() on one thread), %s"
                                    % (per_step, _CPU_DESC[_cpu_kind(pyoracle)])},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

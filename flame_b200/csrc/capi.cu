@@ -168,12 +168,10 @@ static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const in
   for (int v = 0; v < V; ++v) max_deg = std::max(max_deg, c->degv[v]);
 
   // 2. plan
-  int forced = 0, thr_env = 0;
+  int forced = 0;
   if (const char* sv = getenv("FLAME_B200_CLUSTER")) forced = atoi(sv);
-  if (const char* sv = getenv("FLAME_B200_THREADS")) thr_env = atoi(sv);
   ResidentPlan plan{};
   if (V > 0 && V < (1 << 20) && max_deg <= FB_RESIDENT_MAX_DEG) {
-    ResidentPlan fallback{};
     for (int C = 1; C <= 16; C *= 2) {
       if (forced && C != forced) continue;
       const int Vc = (V + C - 1) / C;
@@ -201,8 +199,6 @@ static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const in
       pl.max_deg = max_deg;
       pl.smem_bytes = smem;
       pl.threads = thr;
-      (void)thr_env;
-      (void)fallback;
       plan = pl;
       break;
     }

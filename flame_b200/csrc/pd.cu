@@ -403,6 +403,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   int* s_list = reinterpret_cast<int*>(s_p1 + a.maxInc);     // owned edges: their source slot
   int* s_koff = s_list + a.maxEdges;                         // a.max_deg + 1
   int* s_cnt = s_koff + a.max_deg + 1;                       // 1
+  int* s_scan = s_cnt + 1;                                   // blockDim.x (<= 1024), load phase only
 
   const bool have = c < g.n_chunks;
   const int v0 = c * Vc;
@@ -433,7 +434,6 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   // owned edges = source-role incidence slots of this chunk, listed vertex by vertex so that the
   // threads of a warp read the same / adjacent source records (shared-memory broadcast, few bank
   // conflicts). Deterministic: per-vertex out-degree -> block-wide exclusive scan -> fill.
-  int* s_scan = reinterpret_cast<int*>(s_p4);  // scratch (s_p4 is not live before the first phase A)
   int outdeg = 0;
   if (hasv)
     for (int k = 0; k < deg; ++k) outdeg += ((g.inc_nbr[base + s_koff[k] + tid] & 1) == 0);
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
 
 size_t pd_resident_smem(int Vc, int maxInc, int maxEdges, int max_deg) {
   return (size_t)Vc * 32 + (size_t)maxInc * (16 + 4) + (size_t)maxEdges * (16 + 4) +
-         (size_t)(max_deg + 2) * 4 + 128;
+         (size_t)(max_deg + 2) * 4 + 1024 * 4 + 128;
 }
 
 // The two register budgets the kernel is built for: (threads, owned edges per thread).

@@ -149,3 +149,25 @@ def test_cpp_adapter_against_reference_code():
         pytest.skip("tests/cpp/adapter_test not built (needs /root/reference at build time)")
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "ADAPTER_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_pd_tiny_graphs(gpu_ctx, oracle):
+    """Graphs far smaller than a CTA (3 vertices / 2 edges, an isolated vertex, a self-contained
+    triangle) in both modes."""
+    cases = [
+        (np.array([[0, 0], [10, 3], [20, 12]], np.float32), np.array([[0, 1], [2, 1]], np.int32)),
+        (np.array([[5, 5], [9, 1], [2, 8], [30, 30]], np.float32), np.array([[0, 1], [1, 2], [2, 0]], np.int32)),
+        (np.array([[1, 1], [4, 4]], np.float32), np.array([[1, 0]], np.int32)),
+    ]
+    for pos, edges in cases:
+        V = pos.shape[0]
+        g = {"pos": pos, "edges": edges, "data_term": (0.4 + 0.1 * np.arange(V)).astype(np.float32),
+             "data_weight": np.ones(V, np.float32)}
+        alpha, beta = oracle.edge_weights(edges, pos)
+        want = synth.init_state(g, alpha, beta)
+        oracle.pd_run(want, oracle.pd_default_params(), 9)
+        for mode in (_lib.PD_STREAM, _lib.PD_RESIDENT):
+            gpu_ctx.graph_init(3, pos, g["data_term"], edges)
+            gpu_ctx.pd_run(_lib.default_pd_params(), 9, slot0=3, mode=mode)
+            got = gpu_ctx.graph_download(3, V, edges.shape[0])
+            _assert_bit_equal(got, want, STATE)
