@@ -44,6 +44,7 @@ struct Slot {
   int capT = 0;
   size_t cap_pix = 0;
   int cap_tiles = 0;
+  size_t cap_pairs = 0;
   int* d_tris = nullptr;            // owning pointers behind the const views in `m`
   unsigned char* d_tri_ok = nullptr;
   float* d_mpos = nullptr;          // interpolate_mesh(): caller-supplied pos / values
@@ -470,7 +471,7 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
                     (void*)s.d_pos, (void*)s.d_values,
                     (void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.m.img, (void*)s.m.setup,
                     (void*)s.m.tile_count, (void*)s.m.tile_off, (void*)s.m.pairs, (void*)s.m.large,
-                    (void*)s.m.n_large, (void*)s.d_mpos, (void*)s.d_mvalues})
+                    (void*)s.m.big, (void*)s.m.counters, (void*)s.d_mpos, (void*)s.d_mvalues})
       if (p) cudaFree(p);
     if (s.h_blob) cudaFreeHost(s.h_blob);
     if (s.blob_free) cudaEventDestroy(s.blob_free);
@@ -740,14 +741,15 @@ static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* 
     }
   if (T > s.capT) {
     const int n = std::max(T, s.capT + s.capT / 2);
-    for (void* p : {(void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.m.setup, (void*)s.m.pairs, (void*)s.m.large})
+    for (void* p : {(void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.m.setup, (void*)s.m.large, (void*)s.m.big})
       if (p) FB_CUDA(cudaFree(p));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_tris), (size_t)n * 3 * sizeof(int)));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_tri_ok), (size_t)n));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.setup), (size_t)n * sizeof(TriSetup)));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.pairs), (size_t)n * FB_MAX_TILES_PER_TRI * sizeof(int)));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.large), (size_t)n * sizeof(int)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.big), (size_t)n * sizeof(int)));
     s.capT = n;
+    s.cap_pairs = 0;  // pair buffer depends on capT: re-sized below
   }
   const size_t npix = (size_t)rows * cols;
   if (npix > s.cap_pix) {
@@ -764,9 +766,15 @@ static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* 
     s.cap_tiles = n_tiles;
     FB_CUDA(cudaMemsetAsync(s.m.tile_count, 0, (size_t)n_tiles * sizeof(int), c->stream));
   }
-  if (!s.m.n_large) {
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.n_large), 2 * sizeof(int)));
-    FB_CUDA(cudaMemsetAsync(s.m.n_large, 0, 2 * sizeof(int), c->stream));
+  if (!s.m.counters) {
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.counters), 8 * sizeof(int)));
+    FB_CUDA(cudaMemsetAsync(s.m.counters, 0, 8 * sizeof(int), c->stream));
+  }
+  const size_t need_pairs = (size_t)s.capT * FB_SMALL_TILES_PER_TRI + (size_t)s.cap_tiles * FB_BIG_BUDGET_PER_TILE;
+  if (need_pairs > s.cap_pairs) {
+    if (s.m.pairs) FB_CUDA(cudaFree(s.m.pairs));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.pairs), need_pairs * sizeof(int)));
+    s.cap_pairs = need_pairs;
   }
   s.m.n_tiles = n_tiles;
   s.m.tris = s.d_tris;

@@ -50,13 +50,14 @@ struct GraphDev {
   int* edge_slot;   // [2E] (caller edge, role) -> incidence slot (written by the pack kernel)
 };
 
-struct TriSetup {  // per triangle, written by k_tri_setup
-  float A1, B1, C1, A2, B2, C2, A3, B3, C3;  // edge functions w1 = e23, w2 = e31, w3 = e12
-  float v1, v2, v3;                          // values at p1, p2, p3 (reversed triangle order)
-  int xmin, xend;                            // sweep columns [xmin, xend) (4-px groups)
-  int ymin, ymax;
-  int fx1;                                   // last footprint column, clamped to the image
-  int flags;                                 // 1: in the large list, 2: sweep wraps past the border
+struct __align__(16) TriSetup {  // per triangle, written by k_tri_setup; 80 bytes = 5 x 128-bit loads
+  int xmin, xend, ymin, ymax;    // sweep columns [xmin, xend) (4-px groups), rows [ymin, ymax]
+  float A1, B1, C1, A2;          // edge functions w1 = e23, w2 = e31, w3 = e12
+  float B2, C2, A3, B3;
+  float C3, v1, v2, v3;          // values at p1, p2, p3 (reversed triangle order)
+  int fx1;                       // last footprint column, clamped to the image
+  int flags;                     // 1 large list, 2 sweep wraps past the border, 4 degenerate, 8 big bbox, 16 big & binned
+  int pad0, pad1;
 };
 
 struct MeshDev {
@@ -69,9 +70,10 @@ struct MeshDev {
   TriSetup* setup;             // T
   int* tile_count;             // n_tiles (zero between projections)
   int* tile_off;               // n_tiles + 1
-  int* pairs;                  // MAX_TILES_PER_TRI * T
-  int* large;                  // T
-  int* n_large;                // [0] accumulating, [1] current
+  int* pairs;                  // FB_SMALL_TILES_PER_TRI * T + FB_BIG_BUDGET_PER_TILE * n_tiles
+  int* large;                  // T: triangles every tile tests
+  int* big;                    // T: big-bounding-box triangles binned by a warp
+  int* counters;               // [0] n_large accumulating [1] current [2] n_big accumulating [3] current [4] big pair budget used
 };
 
 // ---- PD (pd.cu) ----
@@ -119,6 +121,7 @@ int raster_values_from_graph(cudaStream_t st, const GraphDev* gs_dev, const Mesh
                              int maxV, float scale);
 int raster_tile_count(int rows, int cols);
 int raster_cta_count(int rows, int cols);
-#define FB_MAX_TILES_PER_TRI 128
+#define FB_SMALL_TILES_PER_TRI 32
+#define FB_BIG_BUDGET_PER_TILE 8
 
 }  // namespace fb

@@ -25,9 +25,10 @@
 //   k_tile_raster one CTA per 32x8 pixel block = four 8x8 tiles, two warps per tile: pixels walk
 //                 their tile's bin (+ the short "large" list); bins hold only triangles whose
 //                 edge functions do not exclude the whole tile (exact integer box test)
-// Triangles whose footprint spans more than MAX_TILES_PER_TRI tiles (hull slivers) or wraps past the
-// right image border (degenerate) go to the large list, which every tile scans; this bounds the
-// pair buffer at MAX_TILES_PER_TRI * T entries.
+// Triangles with a big bounding box (hull slivers: few tiles actually overlapped) are binned by a
+// whole warp (k_big_count / k_big_fill) against a global pair budget; only what exceeds the budget,
+// or wraps past the right image border (degenerate), goes to the "large" list that every tile
+// scans. Pair buffer: SMALL_TILES * T + BIG_BUDGET_PER_TILE * n_tiles entries.
 #include <algorithm>
 
 #include "internal.h"
@@ -37,7 +38,8 @@ namespace fb {
 #define TILE_W 8
 #define TILE_H 8
 #define CTA_TILES 4   // a CTA rasterises CTA_TILES horizontally adjacent tiles (32 x 8 pixels)
-#define MAX_TILES_PER_TRI FB_MAX_TILES_PER_TRI
+#define SMALL_TILES FB_SMALL_TILES_PER_TRI
+#define BIG_BUDGET_PER_TILE FB_BIG_BUDGET_PER_TILE
 
 __device__ __forceinline__ int min3(int a, int b, int c) { return min(a, min(b, c)); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return max(a, max(b, c)); }
@@ -77,6 +79,7 @@ __global__ void __launch_bounds__(256) k_tri_setup(const MeshDev* __restrict__ m
   TriSetup s;
   s.flags = 0;
   s.fx1 = -1;
+  s.pad0 = s.pad1 = 0;
   if (m.tri_ok && !m.tri_ok[t]) {
     s.ymin = 1; s.ymax = 0; s.xmin = 0; s.xend = 0;  // empty footprint
     m.setup[t] = s;
@@ -105,9 +108,13 @@ __global__ void __launch_bounds__(256) k_tri_setup(const MeshDev* __restrict__ m
   s.fx1 = fx1;
   const int tx0 = fx0 / TILE_W, tx1 = fx1 / TILE_W, ty0 = fy0 / TILE_H, ty1 = fy1 / TILE_H;
   const long long ntiles = (fx1 >= fx0 && fy1 >= fy0) ? (long long)(tx1 - tx0 + 1) * (ty1 - ty0 + 1) : 0;
-  if (wraps || ntiles > MAX_TILES_PER_TRI) {
-    s.flags = 1 | (wraps ? 2 : 0);
-    m.large[atomicAdd(&m.n_large[0], 1)] = t;
+  if (degenerate) s.flags |= 4;
+  if (wraps) {
+    s.flags |= 1 | 2;
+    m.large[atomicAdd(&m.counters[0], 1)] = t;
+  } else if (ntiles > SMALL_TILES) {
+    s.flags |= 8;  // big bounding box: binned by a warp in k_big_count / k_big_fill
+    m.big[atomicAdd(&m.counters[2], 1)] = t;
   } else {
     const int tiles_x = (m.cols + TILE_W - 1) / TILE_W;
     for (int ty = ty0; ty <= ty1 && ntiles > 0; ++ty)
@@ -118,8 +125,77 @@ __global__ void __launch_bounds__(256) k_tri_setup(const MeshDev* __restrict__ m
         atomicAdd(&m.tile_count[ty * tiles_x + tx], 1);
       }
   }
-  if (degenerate) s.flags |= 4;
   m.setup[t] = s;
+}
+
+// One warp per big-bounding-box triangle: exact count of overlapped tiles, then either bin it
+// (flags |= 16) within the global pair budget or hand it to the large list (flags |= 1).
+__global__ void __launch_bounds__(256) k_big_count(const MeshDev* __restrict__ ms) {
+  const MeshDev m = ms[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_big = m.counters[2];
+  const int tiles_x = (m.cols + TILE_W - 1) / TILE_W;
+  const int budget = BIG_BUDGET_PER_TILE * m.n_tiles;
+  for (int b = warp; b < n_big; b += nwarps) {
+    const int t = m.big[b];
+    TriSetup s = m.setup[t];
+    const int fx0 = max(s.xmin, 0), fy0 = max(s.ymin, 0), fx1 = s.fx1, fy1 = min(s.ymax, m.rows - 1);
+    const int tx0 = fx0 / TILE_W, ty0 = fy0 / TILE_H;
+    const int nx = fx1 / TILE_W - tx0 + 1, ny = fy1 / TILE_H - ty0 + 1;
+    const bool exact = !(s.flags & 4);
+    int cnt = 0;
+    for (int i = lane; i < nx * ny; i += 32) {
+      const int tx = tx0 + i % nx, ty = ty0 + i / nx;
+      cnt += !(exact && tile_outside(s, tx * TILE_W, ty * TILE_H, tx * TILE_W + TILE_W - 1,
+                                     ty * TILE_H + TILE_H - 1));
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    int ok = 0;
+    if (lane == 0) {
+      const int old = atomicAdd(&m.counters[4], cnt);
+      ok = (old + cnt <= budget);
+      if (!ok) {
+        atomicSub(&m.counters[4], cnt);
+        m.large[atomicAdd(&m.counters[0], 1)] = t;
+      }
+      m.setup[t].flags = s.flags | (ok ? 16 : 1);
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (ok)
+      for (int i = lane; i < nx * ny; i += 32) {
+        const int tx = tx0 + i % nx, ty = ty0 + i / nx;
+        if (!(exact && tile_outside(s, tx * TILE_W, ty * TILE_H, tx * TILE_W + TILE_W - 1,
+                                    ty * TILE_H + TILE_H - 1)))
+          atomicAdd(&m.tile_count[ty * tiles_x + tx], 1);
+      }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_big_fill(const MeshDev* __restrict__ ms) {
+  const MeshDev m = ms[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_big = m.counters[3];
+  const int tiles_x = (m.cols + TILE_W - 1) / TILE_W;
+  for (int b = warp; b < n_big; b += nwarps) {
+    const int t = m.big[b];
+    const TriSetup s = m.setup[t];
+    if (!(s.flags & 16)) continue;
+    const int fx0 = max(s.xmin, 0), fy0 = max(s.ymin, 0), fx1 = s.fx1, fy1 = min(s.ymax, m.rows - 1);
+    const int tx0 = fx0 / TILE_W, ty0 = fy0 / TILE_H;
+    const int nx = fx1 / TILE_W - tx0 + 1, ny = fy1 / TILE_H - ty0 + 1;
+    const bool exact = !(s.flags & 4);
+    for (int i = lane; i < nx * ny; i += 32) {
+      const int tx = tx0 + i % nx, ty = ty0 + i / nx;
+      if (exact && tile_outside(s, tx * TILE_W, ty * TILE_H, tx * TILE_W + TILE_W - 1, ty * TILE_H + TILE_H - 1))
+        continue;
+      const int tile = ty * tiles_x + tx;
+      m.pairs[m.tile_off[tile] + atomicAdd(&m.tile_count[tile], 1)] = t;
+    }
+  }
 }
 
 // one CTA of 1024 threads: exclusive scan of tile_count -> tile_off (n_tiles + 1), zero the cursors
@@ -147,9 +223,12 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const MeshDev* __restrict__ 
     run += cnt;
   }
   if (threadIdx.x == 1023) m.tile_off[n] = s_part[1023];
-  if (threadIdx.x == 0) {  // latch the large-list length for this projection, re-arm the counter
-    m.n_large[1] = m.n_large[0];
-    m.n_large[0] = 0;
+  if (threadIdx.x == 0) {  // latch this projection's list lengths, re-arm the accumulators
+    m.counters[1] = m.counters[0];
+    m.counters[0] = 0;
+    m.counters[3] = m.counters[2];
+    m.counters[2] = 0;
+    m.counters[4] = 0;
   }
 }
 
@@ -158,7 +237,7 @@ __global__ void __launch_bounds__(256) k_tri_fill(const MeshDev* __restrict__ ms
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= m.T) return;
   const TriSetup s = m.setup[t];
-  if (s.flags & 1) return;  // in the large list
+  if (s.flags & (1 | 8)) return;  // large list / binned by k_big_fill
   if (s.ymin > s.ymax) return;
   // exactly the footprint counted in k_tri_setup
   const int fx0 = max(s.xmin, 0), fy0 = max(s.ymin, 0);
@@ -176,67 +255,91 @@ __global__ void __launch_bounds__(256) k_tri_fill(const MeshDev* __restrict__ ms
 }
 
 #define RCHUNK 16
-__global__ void __launch_bounds__(256) k_tile_raster(const MeshDev* __restrict__ ms, int fill_nan) {
+// CTA = 4 warps = 4 horizontally adjacent 8x8 tiles; a warp owns one tile, a lane two pixels
+// (x, y) and (x, y + 4) that share the A*x terms of the edge functions.
+__global__ void __launch_bounds__(128) k_tile_raster(const MeshDev* __restrict__ ms, int fill_nan) {
   const MeshDev m = ms[blockIdx.y];
   const int tiles_x = (m.cols + TILE_W - 1) / TILE_W;
   const int ctas_x = (tiles_x + CTA_TILES - 1) / CTA_TILES;
   const int cy = blockIdx.x / ctas_x, cx = blockIdx.x % ctas_x;
   if (cy * TILE_H >= m.rows) return;
-  const int sub = threadIdx.x >> 6;          // tile within the CTA (two warps each)
-  const int lt = threadIdx.x & 63;           // pixel within the tile
+  const int sub = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tx = cx * CTA_TILES + sub, ty = cy;
-  const bool tile_ok = tx < tiles_x;
+  if (tx >= tiles_x) return;  // whole warp: no CTA-wide barriers below
   const int tile = ty * tiles_x + tx;
-  const int px = tx * TILE_W + (lt & 7), py = ty * TILE_H + (lt >> 3);
+  const int px = tx * TILE_W + (lane & 7);
+  const int py0 = ty * TILE_H + (lane >> 3), py1 = py0 + 4;
   __shared__ TriSetup s_tri[CTA_TILES][RCHUNK];
   __shared__ int s_id[CTA_TILES][RCHUNK];
-  const int beg = tile_ok ? m.tile_off[tile] : 0;
-  const int n_bin = tile_ok ? m.tile_off[tile + 1] - beg : 0;
-  const int n_large = m.n_large[1];
+  const int beg = m.tile_off[tile], n_bin = m.tile_off[tile + 1] - beg;
+  const int n_large = m.counters[1];
   const int n = n_bin + n_large;
-  // all four tiles iterate the same number of chunks (barriers are CTA-wide)
-  int n_max = n;
-  __shared__ int s_nmax;
-  if (threadIdx.x == 0) s_nmax = 0;
-  __syncthreads();
-  if (lt == 0) atomicMax(&s_nmax, n);
-  __syncthreads();
-  n_max = s_nmax;
-  int best = -1;
-  float best_val = 0.0f;
-  const bool live = tile_ok && px < m.cols && py < m.rows;
-  for (int c0 = 0; c0 < n_max; c0 += RCHUNK) {
-    const int nc = max(0, min(RCHUNK, n - c0));
-    __syncthreads();
-    if (lt < nc) {
-      const int e = c0 + lt;
+  int best0 = -1, best1 = -1;
+  float val0 = 0.0f, val1 = 0.0f;
+  const float fx = (float)px, fy0 = (float)py0, fy1 = (float)py1;
+  for (int c0 = 0; c0 < n; c0 += RCHUNK) {
+    const int nc = min(RCHUNK, n - c0);
+    __syncwarp();
+    if (lane < nc) {
+      const int e = c0 + lane;
       const int t = (e < n_bin) ? m.pairs[beg + e] : m.large[e - n_bin];
-      s_id[sub][lt] = t;
-      s_tri[sub][lt] = m.setup[t];
+      s_id[sub][lane] = t;
+      s_tri[sub][lane] = m.setup[t];
     }
-    __syncthreads();
-    if (live) {
-      for (int j = 0; j < nc; ++j) {
-        const int t = s_id[sub][j];
-        if (t < best) continue;  // a later triangle already owns this pixel
-        float v;
-        bool hit = tri_eval(s_tri[sub][j], px, py, &v);
+    __syncwarp();
+    for (int j = 0; j < nc; ++j) {
+      const int t = s_id[sub][j];
+      const TriSetup& s = s_tri[sub][j];
+      const bool in_x = (px >= s.xmin) && (px < s.xend);
+      const bool c0ok = in_x && (t > best0) && (py0 >= s.ymin) && (py0 <= s.ymax);
+      const bool c1ok = in_x && (t > best1) && (py1 >= s.ymin) && (py1 <= s.ymax);
+      if (c0ok || c1ok) {
+        // (A*x + B*y) + C, each operation rounded (exact: integer-valued)
+        const float ax1 = __fmul_rn(s.A1, fx), ax2 = __fmul_rn(s.A2, fx), ax3 = __fmul_rn(s.A3, fx);
+        if (c0ok) {
+          const float w1 = __fadd_rn(__fadd_rn(ax1, __fmul_rn(s.B1, fy0)), s.C1);
+          const float w2 = __fadd_rn(__fadd_rn(ax2, __fmul_rn(s.B2, fy0)), s.C2);
+          const float w3 = __fadd_rn(__fadd_rn(ax3, __fmul_rn(s.B3, fy0)), s.C3);
+          if (w1 >= 0.0f && w2 >= 0.0f && w3 >= 0.0f) {
+            const float num = __fadd_rn(__fmul_rn(s.v1, w1), __fadd_rn(__fmul_rn(s.v2, w2), __fmul_rn(s.v3, w3)));
+            val0 = __fdiv_rn(num, __fadd_rn(w1, __fadd_rn(w2, w3)));
+            best0 = t;
+          }
+        }
+        if (c1ok) {
+          const float w1 = __fadd_rn(__fadd_rn(ax1, __fmul_rn(s.B1, fy1)), s.C1);
+          const float w2 = __fadd_rn(__fadd_rn(ax2, __fmul_rn(s.B2, fy1)), s.C2);
+          const float w3 = __fadd_rn(__fadd_rn(ax3, __fmul_rn(s.B3, fy1)), s.C3);
+          if (w1 >= 0.0f && w2 >= 0.0f && w3 >= 0.0f) {
+            const float num = __fadd_rn(__fmul_rn(s.v1, w1), __fadd_rn(__fmul_rn(s.v2, w2), __fmul_rn(s.v3, w3)));
+            val1 = __fdiv_rn(num, __fadd_rn(w1, __fadd_rn(w2, w3)));
+            best1 = t;
+          }
+        }
+      }
+      if (s.flags & 2) {
         // degenerate triangle whose 4-px sweep ran past the right border: the reference's linear
         // addressing lands on (x - cols, y + 1)
-        if (!hit && (s_tri[sub][j].flags & 2)) hit = tri_eval(s_tri[sub][j], px + m.cols, py - 1, &v);
-        if (hit) {
-          best = t;
-          best_val = v;
-        }
+        float v;
+        if (t > best0 && tri_eval(s, px + m.cols, py0 - 1, &v)) { best0 = t; val0 = v; }
+        if (t > best1 && tri_eval(s, px + m.cols, py1 - 1, &v)) { best1 = t; val1 = v; }
       }
     }
   }
-  if (live) {
-    const size_t i = (size_t)py * m.cols + px;
-    if (best >= 0) m.img[i] = best_val;
-    else if (fill_nan) m.img[i] = __uint_as_float(0x7fc00000u);  // quiet_NaN, flame.cc:412
+  if (px < m.cols) {
+    const unsigned int qnan = 0x7fc00000u;  // quiet_NaN, flame.cc:412
+    if (py0 < m.rows) {
+      const size_t i = (size_t)py0 * m.cols + px;
+      if (best0 >= 0) m.img[i] = val0;
+      else if (fill_nan) m.img[i] = __uint_as_float(qnan);
+    }
+    if (py1 < m.rows) {
+      const size_t i = (size_t)py1 * m.cols + px;
+      if (best1 >= 0) m.img[i] = val1;
+      else if (fill_nan) m.img[i] = __uint_as_float(qnan);
+    }
   }
-  if (tile_ok && lt == 0) m.tile_count[tile] = 0;  // fill cursor -> zero for the next projection
+  if (lane == 0) m.tile_count[tile] = 0;  // fill cursor -> zero for the next projection
 }
 
 __global__ void k_values_from_graph(const GraphDev* __restrict__ gs, const MeshDev* __restrict__ ms,
@@ -264,13 +367,18 @@ int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int 
     k_tri_setup<<<dim3((maxT + 255) / 256, n), 256, 0, st>>>(ms_dev);
     count_launch();
   }
+  if (maxT > 0) {
+    k_big_count<<<dim3(16, n), 256, 0, st>>>(ms_dev);
+    count_launch();
+  }
   k_tile_scan<<<dim3(1, n), 1024, 0, st>>>(ms_dev);
   count_launch();
   if (maxT > 0) {
     k_tri_fill<<<dim3((maxT + 255) / 256, n), 256, 0, st>>>(ms_dev);
-    count_launch();
+    k_big_fill<<<dim3(16, n), 256, 0, st>>>(ms_dev);
+    count_launch(2);
   }
-  k_tile_raster<<<dim3(max_ctas, n), 256, 0, st>>>(ms_dev, fill_nan);
+  k_tile_raster<<<dim3(max_ctas, n), 128, 0, st>>>(ms_dev, fill_nan);
   count_launch();
   FB_CUDA(cudaGetLastError());
   return 0;
