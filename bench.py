@@ -304,6 +304,12 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src = _peaks()
         alg_bytes = 76.0 * (V + E) * iters * B  # 76 B per vertex + 76 B per edge per iteration
         achieved = alg_bytes / (pd_ms * 1e-3) / 1e9
+        traffic = None
+        tp_ = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp_) and args.mode != 1:  # DRAM bytes of this kernel from the committed ncu capture
+            with open(tp_) as f:
+                tk = json.load(f)["k_pd_resident"]
+            traffic = (tk["dram_bytes_read"] + tk["dram_bytes_write"]) * B / tk["frames_per_launch"]
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -312,8 +318,8 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": "config D: 1920x1080, V=%d, E~%d, %d PD iters + dense projection; "
                                    "%d independent frames per GPU per step" % (V, E, iters, B),
                        "frames_per_step_per_gpu": B, "pd_mode": ["auto", "stream", "resident"][args.mode],
-                       "l2": "per-step working set %.0f MB per GPU (> 126 MB L2): inputs larger than L2"
-                             % (B * (76.0 * (V + E) / 2 + 12.0 * W * H) / 1e6),
+                       "l2": "per-step working set ~%.0f MB per GPU (PD state 2.4 MB + mesh/bins ~12 MB + 8.3 MB "
+                             "dense map per frame) > 126 MB L2: inputs larger than L2" % (B * 23.0),
                        "parallelism": "frames sharded by rank, no data-path collective"},
             "ms_per_pd_iter": pd_ms / iters / B,
             "single_frame_pd_latency_ms": lat_ms,
@@ -322,7 +328,8 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_pd_resident" if args.mode != 1 else "k_dual/primal_stream",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src, "traffic": traffic,
+                         "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": pd_ms,
                          "note": "algorithmic bytes = 76*(V+E) per PD iteration per frame; the resident kernel "
                                  "keeps the state in shared memory, so achieved is an EFFECTIVE bandwidth "
