@@ -265,38 +265,56 @@ int pd_reset(cudaStream_t st, const GraphDev* gs_dev, int n, int maxV, int maxE)
 // STREAM mode: state in HBM / L2, ONE kernel per iteration (x_bar double-buffered), any size.
 // grid = (chunks, graphs); a CTA sweeps one chunk of Vc vertices.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k_pd_stream(const GraphDev* __restrict__ gs, flame_b200_pd_params p, int parity, int write_prev) {
+#define STREAM_T 128
+// grid = (chunks * ceil(Vc / STREAM_T), graphs): warps are independent (no CTA-level sync), so small
+// CTAs keep the occupancy up; incidences are processed in groups of STREAM_U with all loads of a
+// group (private q / static data, then the neighbour gathers) issued before its arithmetic.
+template <int STREAM_U, int MINB>
+__global__ void __launch_bounds__(STREAM_T, MINB)
+k_pd_stream(const GraphDev* __restrict__ gs, flame_b200_pd_params p, int parity, int write_prev,
+            int ctas_per_chunk) {
   const GraphDev g = gs[blockIdx.y];
-  const int c = blockIdx.x;
+  const int c = blockIdx.x / ctas_per_chunk;
   if (c >= g.n_chunks) return;
   const float4* __restrict__ cur = parity ? g.vbar2 : g.vbar;
   float4* __restrict__ nxt = parity ? g.vbar : g.vbar2;
   const int v0 = c * g.Vc, nv = min(g.Vc, g.V - v0);
+  const int i = (blockIdx.x % ctas_per_chunk) * STREAM_T + threadIdx.x;
+  if (i >= nv) return;
   const int base = g.chunk_base[c];
   const int* __restrict__ koff = g.koff + (size_t)c * (g.max_deg + 1);
-  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-    const int v = v0 + i;
-    const float4 pr = g.vprim[v];
-    const float4 own = cur[v];
-    float x = pr.x, w1 = pr.y, w2 = pr.z;
-    const int d = g.deg[v];
-    for (int k = 0; k < d; ++k) {
-      const int slot = base + koff[k] + i;
-      float4 q = g.inc_q[slot];
-      const float4 s = g.inc_s[slot];
-      const int ent = __float_as_int(q.w);
-      const float4 nb = cur[ent >> 1];
-      const int is_target = ent & 1;
-      const float4 qn = dual_update_inc(q, s, own, nb, is_target, p.step_q);
-      primal_apply(x, w1, w2, qn, s, is_target, p.step_x);
-      g.inc_q[slot] = make_float4(qn.x, qn.y, qn.z, q.w);
-    }
-    const VertexOut o = vertex_finish(x, w1, w2, pr.w, g.vwt[v], pr.x, pr.y, pr.z, p);
-    g.vprim[v] = o.prim;
-    nxt[v] = o.bar;
-    if (write_prev) g.vprev[v] = make_float4(pr.x, pr.y, pr.z, 0.0f);
+  const int v = v0 + i;
+  const float4 pr = g.vprim[v];
+  const float4 own = cur[v];
+  const float wt = g.vwt[v];
+  float x = pr.x, w1 = pr.y, w2 = pr.z;
+  const int d = g.deg[v];
+  for (int k0 = 0; k0 < d; k0 += STREAM_U) {
+    float4 q[STREAM_U], s[STREAM_U], nb[STREAM_U];
+    int slot[STREAM_U];
+#pragma unroll
+    for (int u = 0; u < STREAM_U; ++u)
+      if (k0 + u < d) {
+        slot[u] = base + koff[k0 + u] + i;
+        q[u] = g.inc_q[slot[u]];
+        s[u] = g.inc_s[slot[u]];
+      }
+#pragma unroll
+    for (int u = 0; u < STREAM_U; ++u)
+      if (k0 + u < d) nb[u] = cur[__float_as_int(q[u].w) >> 1];
+#pragma unroll
+    for (int u = 0; u < STREAM_U; ++u)
+      if (k0 + u < d) {
+        const int is_target = __float_as_int(q[u].w) & 1;
+        const float4 qn = dual_update_inc(q[u], s[u], own, nb[u], is_target, p.step_q);
+        primal_apply(x, w1, w2, qn, s[u], is_target, p.step_x);
+        g.inc_q[slot[u]] = make_float4(qn.x, qn.y, qn.z, q[u].w);
+      }
   }
+  const VertexOut o = vertex_finish(x, w1, w2, pr.w, wt, pr.x, pr.y, pr.z, p);
+  g.vprim[v] = o.prim;
+  nxt[v] = o.bar;
+  if (write_prev) g.vprev[v] = make_float4(pr.x, pr.y, pr.z, 0.0f);
 }
 
 __global__ void k_copy_bar(const GraphDev* __restrict__ gs) {
@@ -308,9 +326,20 @@ __global__ void k_copy_bar(const GraphDev* __restrict__ gs) {
 int pd_run_stream(cudaStream_t st, const GraphDev* gs_dev, int n, int max_chunks, int threads,
                   const flame_b200_pd_params& p, int n_iters) {
   if (n_iters <= 0 || n <= 0 || max_chunks <= 0) return 0;
-  const dim3 grid(max_chunks, n);
-  for (int it = 0; it < n_iters; ++it)
-    k_pd_stream<<<grid, threads, 0, st>>>(gs_dev, p, it & 1, it == n_iters - 1);
+  const int ctas_per_chunk = (threads + STREAM_T - 1) / STREAM_T;  // threads = max chunk width (rounded)
+  const dim3 grid(max_chunks * ctas_per_chunk, n);
+  int variant = 2;  // 64 registers, 8 CTAs/SM measured best on B200 (FLAME_B200_STREAM_U=4|46|3 for experiments)
+  if (const char* sv = getenv("FLAME_B200_STREAM_U")) variant = atoi(sv);
+  for (int it = 0; it < n_iters; ++it) {
+    if (variant == 2)
+      k_pd_stream<2, 8><<<grid, STREAM_T, 0, st>>>(gs_dev, p, it & 1, it == n_iters - 1, ctas_per_chunk);
+    else if (variant == 46)
+      k_pd_stream<4, 6><<<grid, STREAM_T, 0, st>>>(gs_dev, p, it & 1, it == n_iters - 1, ctas_per_chunk);
+    else if (variant == 3)
+      k_pd_stream<3, 6><<<grid, STREAM_T, 0, st>>>(gs_dev, p, it & 1, it == n_iters - 1, ctas_per_chunk);
+    else
+      k_pd_stream<4, 5><<<grid, STREAM_T, 0, st>>>(gs_dev, p, it & 1, it == n_iters - 1, ctas_per_chunk);
+  }
   count_launch(n_iters);
   if (n_iters & 1) {  // result is in vbar2: bring it home
     k_copy_bar<<<dim3(std::min(max_chunks, 64), n), 256, 0, st>>>(gs_dev);
