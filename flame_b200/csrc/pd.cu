@@ -574,11 +574,23 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
     // ---- phase B: ordered accumulation + prox + extragradient, one vertex per thread ----
     if (hasv) {
       const float x_old = x, w1_old = w1, w2_old = w2;
-#pragma unroll 4
+      // software pipeline: the contribution record of incidence k+1 is in flight while k is added
+      float4 p4n = make_float4(0.f, 0.f, 0.f, 0.f);
+      float p1n = 0.f;
+      if (deg > 0) {
+        p4n = s_p4[tid];  // koff[0] == 0
+        p1n = s_p1[tid];
+      }
+      int ko = (deg > 1) ? s_koff[1] : 0;
       for (int k = 0; k < deg; ++k) {
-        const int slot = s_koff[k] + tid;
-        const float4 p4 = s_p4[slot];
-        const float p1 = s_p1[slot];
+        const float4 p4 = p4n;
+        const float p1 = p1n;
+        if (k + 1 < deg) {
+          const int slot = ko + tid;
+          p4n = s_p4[slot];
+          p1n = s_p1[slot];
+          ko = s_koff[k + 2];  // k + 2 <= max_deg: inside the table
+        }
         x = add(x, p4.x);
         w1 = add(w1, p4.y);
         w2 = add(w2, p4.z);
