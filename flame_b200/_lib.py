@@ -86,7 +86,8 @@ SYMBOLS = [
     "flame_b200_graph_set_data", "flame_b200_graph_reset", "flame_b200_graph_download", "flame_b200_pd_run",
     "flame_b200_pd_cost", "flame_b200_interpolate_mesh", "flame_b200_mesh_bind",
     "flame_b200_mesh_project", "flame_b200_mesh_download", "flame_b200_track_default_params",
-    "flame_b200_set_camera", "flame_b200_frame_upload", "flame_b200_update_feature_idepths",
+    "flame_b200_set_camera", "flame_b200_frame_upload", "flame_b200_frame_upload_raw",
+    "flame_b200_frame_download", "flame_b200_update_feature_idepths",
 ]
 
 
@@ -127,6 +128,8 @@ def lib():
     L.flame_b200_track_default_params.restype = None
     L.flame_b200_set_camera.argtypes = [vp, C.c_int, C.c_int, f32p, f32p]
     L.flame_b200_frame_upload.argtypes = [vp, C.c_int, u8p, f32p, f32p, C.c_int, f32p]
+    L.flame_b200_frame_upload_raw.argtypes = [vp, C.c_int, u8p, C.c_int, f32p]
+    L.flame_b200_frame_download.argtypes = [vp, C.c_int, u8p, f32p, f32p]
     L.flame_b200_update_feature_idepths.argtypes = [vp, C.POINTER(TrackParams), C.c_int, C.c_int, vp,
                                                     C.c_int32, vp, C.POINTER(C.c_int32)]
     _lib = L
@@ -309,6 +312,19 @@ class Context:
         check(lib().flame_b200_frame_upload(self._h, fslot, bptr(np.ascontiguousarray(img_pad)),
                                             fptr(np.ascontiguousarray(gradx_pad)),
                                             fptr(np.ascontiguousarray(grady_pad)), pad, fptr(pose)))
+
+    def frame_upload_raw(self, fslot, img, pad, pose):
+        pose = np.ascontiguousarray(pose, np.float32)
+        check(lib().flame_b200_frame_upload_raw(self._h, fslot, bptr(np.ascontiguousarray(img, np.uint8)),
+                                                pad, fptr(pose)))
+
+    def frame_download(self, fslot, height, width, pad):
+        shape = (height + 2 * pad, width + 2 * pad)
+        ip = np.empty(shape, np.uint8)
+        gx = np.empty(shape, np.float32)
+        gy = np.empty(shape, np.float32)
+        check(lib().flame_b200_frame_download(self._h, fslot, bptr(ip), fptr(gx), fptr(gy)))
+        return ip, gx, gy
 
     def update_feature_idepths(self, params, fnew, curr_pf, feats, want_diag=True):
         assert feats.dtype == FEATURE_DTYPE and feats.flags["C_CONTIGUOUS"]

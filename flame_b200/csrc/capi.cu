@@ -21,6 +21,10 @@ int stereo_frame_upload(void** state, cudaStream_t st, int fslot, const uint8_t*
 int stereo_update(void* state, cudaStream_t st, const flame_b200_track_params* params, int fnew,
                   int curr_pf, flame_b200_feature* feats, int32_t n_feats,
                   flame_b200_track_diag* diag, int32_t* n_updates);
+int stereo_frame_upload_raw(void** state, cudaStream_t st, int fslot, const uint8_t* img, int pad,
+                            const float pose[7]);
+int stereo_frame_download(void* state, cudaStream_t st, int fslot, uint8_t* img_pad, float* gradx_pad,
+                          float* grady_pad);
 void stereo_destroy(void* state);
 
 // ------------------------------------------------------------------------------------------
@@ -917,6 +921,20 @@ int flame_b200_frame_upload(flame_b200_ctx* c, int fslot, const uint8_t* img_pad
   if (!c || !img_pad || !gradx_pad || !grady_pad || !pose) return FLAME_B200_EINVAL;
   if (int rc = use_device(c)) return rc;
   return stereo_frame_upload(&c->stereo, c->stream, fslot, img_pad, gradx_pad, grady_pad, pad, pose);
+}
+
+int flame_b200_frame_upload_raw(flame_b200_ctx* c, int fslot, const uint8_t* img, int pad,
+                                const float pose[7]) {
+  if (!c || !img || !pose) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  return stereo_frame_upload_raw(&c->stereo, c->stream, fslot, img, pad, pose);
+}
+
+int flame_b200_frame_download(flame_b200_ctx* c, int fslot, uint8_t* img_pad, float* gradx_pad,
+                              float* grady_pad) {
+  if (!c) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  return stereo_frame_download(c->stereo, c->stream, fslot, img_pad, gradx_pad, grady_pad);
 }
 
 int flame_b200_update_feature_idepths(flame_b200_ctx* c, const flame_b200_track_params* params,

@@ -44,6 +44,8 @@ struct StereoState {
   float* d_gx[FB_MAX_FRAMES] = {nullptr};
   float* d_gy[FB_MAX_FRAMES] = {nullptr};
   size_t cap_pix[FB_MAX_FRAMES] = {0};
+  unsigned char* d_raw = nullptr;    // raw u8 image of the frame being prepared
+  size_t cap_raw = 0;
   unsigned char* h_stage = nullptr;  // pinned
   size_t h_stage_cap = 0;
   cudaEvent_t stage_free = nullptr;
@@ -814,6 +816,42 @@ __global__ void __launch_bounds__(128) k_update_feature_idepths(StereoArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Frame preparation: the padded level-0 buffers of utils::Frame::create
+// (src/flame/utils/frame.cc:54-63) from the raw u8 image, on the device: img_pad = REFLECT_101
+// border, gradients = getCentralGradient<uint8_t,float> (src/flame/utils/image_utils.cc:36-108:
+// 0.5*(right-left) inside, forward/backward differences on the first/last column/row) with a
+// zero (BORDER_CONSTANT) border. One thread per padded pixel; every output written once.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) p = (p < 0) ? -p : 2 * (len - 1) - p;
+  return p;
+}
+
+__global__ void __launch_bounds__(256)
+k_frame_prep(const unsigned char* __restrict__ img, int width, int height, int border,
+             unsigned char* __restrict__ img_pad, float* __restrict__ gx_pad, float* __restrict__ gy_pad) {
+  const int pw = width + 2 * border, ph = height + 2 * border;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= pw || y >= ph) return;
+  const int sx = x - border, sy = y - border;
+  const size_t o = (size_t)y * pw + x;
+  img_pad[o] = __ldg(img + (size_t)reflect101(sy, height) * width + reflect101(sx, width));
+  float gx = 0.0f, gy = 0.0f;
+  if (sx >= 0 && sx < width && sy >= 0 && sy < height) {
+    const unsigned char* r = img + (size_t)sy * width;
+    if (sx == 0) gx = (float)__ldg(r + 1) - (float)__ldg(r);
+    else if (sx == width - 1) gx = (float)__ldg(r + sx) - (float)__ldg(r + sx - 1);
+    else gx = 0.5f * ((float)__ldg(r + sx + 1) - (float)__ldg(r + sx - 1));
+    if (sy == 0) gy = (float)__ldg(r + width + sx) - (float)__ldg(r + sx);
+    else if (sy == height - 1) gy = (float)__ldg(r + sx) - (float)__ldg(r - width + sx);
+    else gy = 0.5f * ((float)__ldg(r + width + sx) - (float)__ldg(r - width + sx));
+  }
+  gx_pad[o] = gx;
+  gy_pad[o] = gy;
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static StereoState* get_state(void** st) {
@@ -889,6 +927,91 @@ int stereo_frame_upload(void** state, cudaStream_t st, int fslot, const uint8_t*
   FB_CUDA(cudaMemcpyAsync(s->d_img[fslot], hs + npix * 8, npix, cudaMemcpyHostToDevice, st));
   FB_CUDA(cudaMemcpyAsync(s->d_frames, hs + npix * 9, sizeof(s->h_frames), cudaMemcpyHostToDevice, st));
   FB_CUDA(cudaEventRecord(s->stage_free, st));
+  return 0;
+}
+
+static int frame_slot_prepare(StereoState* s, int fslot, int pad, size_t npix) {
+  if (s->width <= 0) {
+    set_error("frame_upload: call flame_b200_set_camera first");
+    return FLAME_B200_ESTATE;
+  }
+  if (fslot < 0 || fslot >= FB_MAX_FRAMES || pad < 0) {
+    set_error("frame_upload: frame slot out of range");
+    return FLAME_B200_EINVAL;
+  }
+  if (s->pad != 0 && s->pad != pad) {
+    bool any = false;
+    for (int i = 0; i < FB_MAX_FRAMES; ++i) any |= (s->h_frames[i].valid != 0 && i != fslot);
+    if (any) {
+      set_error("frame_upload: all frames must share one padding");
+      return FLAME_B200_EINVAL;
+    }
+  }
+  s->pad = pad;
+  if (npix > s->cap_pix[fslot]) {
+    if (s->d_img[fslot]) FB_CUDA(cudaFree(s->d_img[fslot]));
+    if (s->d_gx[fslot]) FB_CUDA(cudaFree(s->d_gx[fslot]));
+    if (s->d_gy[fslot]) FB_CUDA(cudaFree(s->d_gy[fslot]));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_img[fslot]), npix));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_gx[fslot]), npix * 4));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_gy[fslot]), npix * 4));
+    s->cap_pix[fslot] = npix;
+  }
+  if (!s->d_frames) FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_frames), sizeof(s->h_frames)));
+  if (!s->stage_free) FB_CUDA(cudaEventCreateWithFlags(&s->stage_free, cudaEventDisableTiming));
+  return 0;
+}
+
+// Raw (unpadded) u8 image in, padded image + gradients computed on the device.
+int stereo_frame_upload_raw(void** state, cudaStream_t st, int fslot, const uint8_t* img, int pad,
+                            const float pose[7]) {
+  StereoState* s = get_state(state);
+  const size_t npix = (size_t)(s->width + 2 * pad) * (s->height + 2 * pad);
+  if (int rc = frame_slot_prepare(s, fslot, pad, npix)) return rc;
+  const size_t nraw = (size_t)s->width * s->height;
+  const size_t need = nraw + sizeof(s->h_frames);
+  FB_CUDA(cudaEventSynchronize(s->stage_free));
+  if (need > s->h_stage_cap) {
+    if (s->h_stage) FB_CUDA(cudaFreeHost(s->h_stage));
+    FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s->h_stage), need));
+    s->h_stage_cap = need;
+  }
+  if (nraw > s->cap_raw) {
+    if (s->d_raw) FB_CUDA(cudaFree(s->d_raw));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_raw), nraw));
+    s->cap_raw = nraw;
+  }
+  std::memcpy(s->h_stage, img, nraw);
+  FrameDev& fr = s->h_frames[fslot];
+  fr.img = s->d_img[fslot];
+  fr.gx = s->d_gx[fslot];
+  fr.gy = s->d_gy[fslot];
+  std::memcpy(fr.pose, pose, sizeof(fr.pose));
+  fr.valid = 1;
+  std::memcpy(s->h_stage + nraw, s->h_frames, sizeof(s->h_frames));
+  FB_CUDA(cudaMemcpyAsync(s->d_raw, s->h_stage, nraw, cudaMemcpyHostToDevice, st));
+  FB_CUDA(cudaMemcpyAsync(s->d_frames, s->h_stage + nraw, sizeof(s->h_frames), cudaMemcpyHostToDevice, st));
+  FB_CUDA(cudaEventRecord(s->stage_free, st));
+  const int pw = s->width + 2 * pad, ph = s->height + 2 * pad;
+  k_frame_prep<<<dim3((pw + 255) / 256, ph), 256, 0, st>>>(s->d_raw, s->width, s->height, pad,
+                                                         s->d_img[fslot], s->d_gx[fslot], s->d_gy[fslot]);
+  count_launch();
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int stereo_frame_download(void* state, cudaStream_t st, int fslot, uint8_t* img_pad, float* gradx_pad,
+                          float* grady_pad) {
+  StereoState* s = static_cast<StereoState*>(state);
+  if (!s || fslot < 0 || fslot >= FB_MAX_FRAMES || !s->h_frames[fslot].valid) {
+    set_error("frame_download: frame slot not uploaded");
+    return FLAME_B200_EINVAL;
+  }
+  const size_t npix = (size_t)(s->width + 2 * s->pad) * (s->height + 2 * s->pad);
+  if (img_pad) FB_CUDA(cudaMemcpyAsync(img_pad, s->d_img[fslot], npix, cudaMemcpyDeviceToHost, st));
+  if (gradx_pad) FB_CUDA(cudaMemcpyAsync(gradx_pad, s->d_gx[fslot], npix * 4, cudaMemcpyDeviceToHost, st));
+  if (grady_pad) FB_CUDA(cudaMemcpyAsync(grady_pad, s->d_gy[fslot], npix * 4, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -970,6 +1093,7 @@ void stereo_destroy(void* state) {
     if (s->d_gy[i]) cudaFree(s->d_gy[i]);
   }
   if (s->d_frames) cudaFree(s->d_frames);
+  if (s->d_raw) cudaFree(s->d_raw);
   if (s->h_stage) cudaFreeHost(s->h_stage);
   if (s->stage_free) cudaEventDestroy(s->stage_free);
   if (s->d_feats) cudaFree(s->d_feats);

@@ -242,6 +242,17 @@ int flame_b200_frame_upload(flame_b200_ctx* ctx, int fslot, const uint8_t* img_p
                             const float* gradx_pad, const float* grady_pad, int pad,
                             const float pose[7]);
 
+/* SURVEY §8(f) rank 3 — frame preparation on the device: the same frame slot filled from the RAW
+ * (unpadded, height x width) u8 image; the padded image (cv::copyMakeBorder REFLECT_101) and the
+ * zero-padded central-difference gradients (utils::getCentralGradient<uint8_t,float>,
+ * utils/image_utils.cc:36-108) that utils::Frame::create builds on the host (utils/frame.cc:54-63,
+ * level 0) are computed by a kernel: 9x less host->device traffic per frame. Asynchronous. */
+int flame_b200_frame_upload_raw(flame_b200_ctx* ctx, int fslot, const uint8_t* img, int pad,
+                                const float pose[7]);
+/* Reads a frame slot's padded buffers back (any pointer may be NULL). Synchronises the stream. */
+int flame_b200_frame_download(flame_b200_ctx* ctx, int fslot, uint8_t* img_pad, float* gradx_pad,
+                              float* grady_pad);
+
 /* Replaces the loop body of Flame::updateFeatureIDepths (flame.cc:1308-1496) for n features:
  * feats is updated in place (host memory), diag (nullable) receives per-feature diagnostics.
  * fnew = frame slot of the new frame, curr_pf = frame slot of the current pose-frame.

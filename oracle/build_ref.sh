@@ -11,9 +11,10 @@ mkdir -p "$OBJ"
 CXXFLAGS="-O3 -std=c++11 -ffp-contract=off -fPIC -w -I$HERE/shim -I$REF/src"
 g++ -O2 -fPIC -w -I"$REF/src" -c "$REF/src/flame/external/triangle/triangle.cpp" -o "$OBJ/triangle.o"
 g++ $CXXFLAGS -c "$REF/src/flame/utils/rasterization.cc" -o "$OBJ/rasterization.o"
+g++ $CXXFLAGS -c "$REF/src/flame/utils/image_utils.cc" -o "$OBJ/image_utils.o"
 g++ $CXXFLAGS -c "$HERE/ref_capi/ref_triangle.cc" -o "$OBJ/ref_triangle.o"
 g++ $CXXFLAGS -c "$HERE/ref_capi/ref_raster.cc" -o "$OBJ/ref_raster.o"
-OBJS="$OBJ/triangle.o $OBJ/rasterization.o $OBJ/ref_triangle.o $OBJ/ref_raster.o"
+OBJS="$OBJ/triangle.o $OBJ/rasterization.o $OBJ/image_utils.o $OBJ/ref_triangle.o $OBJ/ref_raster.o"
 if [ -f "$HERE/ref_capi/ref_solver.cc" ]; then
   g++ $CXXFLAGS -c "$REF/src/flame/optimizers/nltgv2_l1_graph_regularizer.cc" -o "$OBJ/regularizer.o"
   g++ $CXXFLAGS -c "$HERE/ref_capi/ref_solver.cc" -o "$OBJ/ref_solver.o"

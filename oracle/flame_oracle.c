@@ -10,6 +10,7 @@
 #include <float.h>
 #include <math.h>
 #include <stddef.h>
+#include <stdlib.h>
 #include <string.h>
 
 /* utils/image_utils.h:91-94  fast_abs: (r > 0) ? r : -r */
@@ -336,6 +337,63 @@ int oracle_clip_line_liang_barsky(float xmin, float xmax, float ymin, float ymax
   if (b1 > ymax) b1 = ymax;
   *x0c = a0; *y0c = b0; *x1c = a1; *y1c = b1;
   return 1;
+}
+
+/* ====================================================================================
+ * Frame preparation — utils/image_utils.cc:36-108, utils/frame.cc:54-63
+ * ==================================================================================== */
+
+/* image_utils.cc:36-108 / image_utils.h:425-477: 0.5*(right-left) inside, forward / backward
+ * differences on the first / last column and row. */
+void oracle_central_gradient_u8(int width, int height, const uint8_t* img, float* gradx, float* grady) {
+  for (int ii = 0; ii < height; ++ii) {
+    for (int jj = 1; jj < width - 1; ++jj) {
+      int idx = ii * width + jj;
+      float left = img[idx - 1], right = img[idx + 1];
+      gradx[idx] = (float)(0.5 * (right - left));
+    }
+    gradx[ii * width] = (float)img[ii * width + 1] - (float)img[ii * width];
+    gradx[ii * width + width - 1] = (float)img[ii * width + width - 1] - (float)img[ii * width + width - 2];
+  }
+  for (int ii = 1; ii < height - 1; ++ii)
+    for (int jj = 0; jj < width; ++jj) {
+      int idx = ii * width + jj;
+      float up = img[idx - width], down = img[idx + width];
+      grady[idx] = (float)(0.5 * (down - up));
+    }
+  for (int jj = 0; jj < width; ++jj) {
+    grady[jj] = (float)img[jj + width] - (float)img[jj];
+    grady[(height - 1) * width + jj] = (float)img[(height - 1) * width + jj] - (float)img[(height - 2) * width + jj];
+  }
+}
+
+/* OpenCV borderInterpolate(p, len, BORDER_REFLECT_101): gfedcb|abcdefgh|gfedcba */
+static int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) {
+    if (p < 0) p = -p;
+    else p = 2 * (len - 1) - p;
+  }
+  return p;
+}
+
+/* utils/frame.cc:54-63 (level 0; Flame passes num_levels = 1, border = fparams.win_size, flame.cc:149-150) */
+void oracle_frame_prep(int width, int height, int border, const uint8_t* img, uint8_t* img_pad,
+                       float* gradx_pad, float* grady_pad) {
+  const int pw = width + 2 * border, ph = height + 2 * border;
+  float* gx = (float*)malloc(sizeof(float) * (size_t)width * height);
+  float* gy = (float*)malloc(sizeof(float) * (size_t)width * height);
+  oracle_central_gradient_u8(width, height, img, gx, gy);
+  for (int y = 0; y < ph; ++y)
+    for (int x = 0; x < pw; ++x) {
+      const int sx = x - border, sy = y - border;
+      img_pad[(size_t)y * pw + x] = img[(size_t)reflect101(sy, height) * width + reflect101(sx, width)];
+      const int inside = (sx >= 0 && sx < width && sy >= 0 && sy < height);
+      gradx_pad[(size_t)y * pw + x] = inside ? gx[(size_t)sy * width + sx] : 0.0f;
+      grady_pad[(size_t)y * pw + x] = inside ? gy[(size_t)sy * width + sx] : 0.0f;
+    }
+  free(gx);
+  free(gy);
 }
 
 /* ====================================================================================

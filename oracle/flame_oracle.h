@@ -86,6 +86,13 @@ int oracle_clip_line_liang_barsky(float xmin, float xmax, float ymin, float ymax
                                   float y0, float x1, float y1, float* x0c, float* y0c,
                                   float* x1c, float* y1c);
 
+/* ---- frame preparation: utils/image_utils.cc:36-108 (getCentralGradient<uint8_t,float>), utils/frame.cc:54-63 ---- */
+void oracle_central_gradient_u8(int width, int height, const uint8_t* img, float* gradx, float* grady);
+/* Level-0 buffers of utils::Frame::create: img_pad = copyMakeBorder(img, REFLECT_101), gradients of
+ * the unpadded image zero-padded (BORDER_CONSTANT), all (height+2*border) x (width+2*border). */
+void oracle_frame_prep(int width, int height, int border, const uint8_t* img, uint8_t* img_pad,
+                       float* gradx_pad, float* grady_pad);
+
 /* ---- stereo/epipolar_geometry.h ---- */
 typedef struct {
   float K[9], Kinv[9];           /* row-major 3x3 */

@@ -445,3 +445,33 @@ def ref_epigeo_query(K, Kinv, q_wxyz, t, u, idepth):
     fn.argtypes = [f32p, f32p, f32p, f32p, C.c_float, C.c_float, C.c_float, f32p]
     fn(_f(K), _f(Kinv), _f(q), _f(t), u[0], u[1], idepth, _f(out))
     return out
+
+
+# ---------------------------------------------------------------------------- frame preparation
+def central_gradient_u8(img, use_ref=False):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    gx = np.empty((h, w), np.float32)
+    gy = np.empty((h, w), np.float32)
+    fn = ref().ref_central_gradient_u8 if use_ref else lib().oracle_central_gradient_u8
+    fn(C.c_int(w), C.c_int(h), _u8(img), _f(gx), _f(gy))
+    return gx, gy
+
+
+def frame_prep(img, border):
+    """Padded level-0 buffers of utils::Frame::create (img REFLECT_101, gradients zero-padded)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    ip = np.empty((h + 2 * border, w + 2 * border), np.uint8)
+    gx = np.empty(ip.shape, np.float32)
+    gy = np.empty(ip.shape, np.float32)
+    lib().oracle_frame_prep(C.c_int(w), C.c_int(h), C.c_int(border), _u8(img), _u8(ip), _f(gx), _f(gy))
+    return ip, gx, gy
+
+
+def ref_clip_line(xmin, xmax, ymin, ymax, x0, y0, x1, y1):
+    out = np.zeros(4, np.float32)
+    fn = ref().ref_clip_line
+    fn.argtypes = [C.c_float] * 8 + [f32p]
+    ok = fn(xmin, xmax, ymin, ymax, x0, y0, x1, y1, _f(out))
+    return bool(ok), tuple(float(v) for v in out)

@@ -1,6 +1,7 @@
 // C entry points over the reference's stereo sources compiled VERBATIM against oracle/shim:
 // stereo/inverse_depth_filter.cc, stereo/inverse_depth_meas_model.cc, stereo/line_stereo.h,
-// stereo/epipolar_geometry.h, utils/image_utils.h (bilinearInterp). Test infrastructure only.
+// stereo/epipolar_geometry.h, utils/image_utils.{h,cc} (bilinearInterp, clipLineLiangBarsky). Test
+// infrastructure only.
 //
 // Flame::updateFeatureIDepths / Flame::trackFeature are private members of flame::Flame whose
 // translation unit (flame.cc) needs all of OpenCV/Boost; their control flow (flame.cc:1308-1496,
@@ -11,33 +12,6 @@
 
 #include "flame/stereo/inverse_depth_filter.h"
 #include "flame/stereo/inverse_depth_meas_model.h"
-
-// image_utils.cc needs the whole OpenCV API; the one function of it on this path is restated from
-// src/flame/utils/image_utils.cc:269-371 by the oracle. Here we need a definition for the linker:
-// forward to the oracle-independent verbatim copy below (kept in sync with the oracle's by tests).
-namespace flame { namespace utils {
-bool clipLineLiangBarsky(float xmin, float xmax, float ymin, float ymax, float x0, float y0, float x1,
-                         float y1, float* x0_clip, float* y0_clip, float* x1_clip, float* y1_clip) {
-  float t0 = 0.0f, t1 = 1.0f;
-  float xdelta = x1 - x0, ydelta = y1 - y0;
-  for (int edge = 0; edge < 4; edge++) {
-    float p = 1.0f, q = 0.0f, r = 0.0f;
-    if (edge == 0) { p = -xdelta; q = -(xmin - x0); }
-    else if (edge == 1) { p = xdelta; q = (xmax - x0); }
-    else if (edge == 2) { p = -ydelta; q = -(ymin - y0); }
-    else if (edge == 3) { p = ydelta; q = (ymax - y0); }
-    r = q / p;
-    if (p == 0 && q < 0) return false;
-    if (p < 0) { if (r > t1) return false; else if (r > t0) t0 = r; }
-    else if (p > 0) { if (r < t0) return false; else if (r < t1) t1 = r; }
-  }
-  float a0 = x0 + t0 * xdelta, b0 = y0 + t0 * ydelta, a1 = x0 + t1 * xdelta, b1 = y0 + t1 * ydelta;
-  if (a0 < xmin) a0 = xmin; if (a0 > xmax) a0 = xmax; if (b0 < ymin) b0 = ymin; if (b0 > ymax) b0 = ymax;
-  if (a1 < xmin) a1 = xmin; if (a1 > xmax) a1 = xmax; if (b1 < ymin) b1 = ymin; if (b1 > ymax) b1 = ymax;
-  *x0_clip = a0; *y0_clip = b0; *x1_clip = a1; *y1_clip = b1;
-  return true;
-}
-} }
 
 using flame::stereo::EpipolarGeometry;
 namespace idf = flame::stereo::inverse_depth_filter;

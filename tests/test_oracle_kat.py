@@ -304,3 +304,48 @@ def test_epigeo_oracle_equals_reference_verbatim(oracle):
             o = np.array([*e.min_depth_projection(u), *e.max_depth_projection(u), *ui, *ep,
                           *e.project(u, idp), *e.reference_epiline(u)], np.float32)
             assert np.array_equal(o.view(np.uint32), r.view(np.uint32))
+
+
+# ---------------------------------------------------------------- frame preparation
+@pytest.mark.parametrize("axis", [0, 1])
+def test_central_gradient_ramp_kat(oracle, axis):
+    """test/utils/image_utils_test.cc:171-330 (getCentralGradientHorizontal/Vertical): a 640x480 ramp,
+    0.5*(right-left) inside, forward/backward differences on the first/last column/row."""
+    W, H = 640, 480
+    slope = np.float32(255.0) / np.float32(W if axis == 0 else H)
+    idx = np.arange(W if axis == 0 else H, dtype=np.float32)
+    ramp = (slope * idx + np.float32(0.5)).astype(np.uint8)  # fast_roundf for positive values
+    img = np.tile(ramp, (H, 1)) if axis == 0 else np.tile(ramp[:, None], (1, W))
+    for use_ref in ([False, True] if oracle.have_ref() else [False]):
+        gx, gy = oracle.central_gradient_u8(img, use_ref=use_ref)
+        f = img.astype(np.float32)
+        assert np.allclose(gx[:, 1:-1], 0.5 * (f[:, 2:] - f[:, :-2]), atol=1e-6)
+        assert np.allclose(gx[:, 0], f[:, 1] - f[:, 0]) and np.allclose(gx[:, -1], f[:, -1] - f[:, -2])
+        assert np.allclose(gy[1:-1, :], 0.5 * (f[2:, :] - f[:-2, :]), atol=1e-6)
+        assert np.allclose(gy[0, :], f[1, :] - f[0, :]) and np.allclose(gy[-1, :], f[-1, :] - f[-2, :])
+
+
+def test_oracle_frame_prep_equals_reference_and_opencv(oracle):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(4)
+    for shape in ((97, 131), (480, 640), (6, 7)):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        ip, gx, gy = oracle.frame_prep(img, 5)
+        assert np.array_equal(ip, cv2.copyMakeBorder(img, 5, 5, 5, 5, cv2.BORDER_REFLECT_101))
+        g0 = oracle.central_gradient_u8(img)
+        if oracle.have_ref():  # utils/image_utils.cc compiled verbatim
+            r0 = oracle.central_gradient_u8(img, use_ref=True)
+            assert all(np.array_equal(a.view(np.uint32), b.view(np.uint32)) for a, b in zip(g0, r0))
+        assert np.array_equal(gx, cv2.copyMakeBorder(g0[0], 5, 5, 5, 5, cv2.BORDER_CONSTANT, value=0))
+        assert np.array_equal(gy, cv2.copyMakeBorder(g0[1], 5, 5, 5, 5, cv2.BORDER_CONSTANT, value=0))
+
+
+def test_oracle_clip_line_equals_reference_verbatim(oracle):
+    _need_ref(oracle)
+    rng = np.random.default_rng(2)
+    for _ in range(3000):
+        v = [float(np.float32(x)) for x in rng.uniform(-80, 720, 4)]
+        o, r = oracle.clip_line(1, 639, 1, 479, *v), oracle.ref_clip_line(1, 639, 1, 479, *v)
+        assert o[0] == r[0]
+        if o[0]:
+            assert np.array_equal(np.float32(o[1]).view(np.uint32), np.float32(r[1]).view(np.uint32))

@@ -120,3 +120,40 @@ def test_empty_and_errors(gpu_ctx):
     bad["frame_id"] = 40  # never uploaded
     with pytest.raises(_lib.FlameB200Error):
         gpu_ctx.update_feature_idepths(_lib.default_track_params(), 1, 0, bad)
+
+
+def test_frame_prep_on_device(gpu_ctx, oracle):
+    """flame_b200_frame_upload_raw: padded image (REFLECT_101) + zero-padded central gradients computed
+    by k_frame_prep == utils::Frame::create's level-0 buffers (oracle, pinned on the verbatim
+    getCentralGradient and on cv2.copyMakeBorder), bit-exact; the search gives identical results
+    whether the frames were prepared on the host or on the device."""
+    W, H, V, _ = synth.CONFIGS["A"]
+    K, Kinv, frames = synth.make_stereo_pair(W, H)
+    gpu_ctx.set_camera(W, H, K, Kinv)
+    for i, fr in enumerate(frames):
+        gpu_ctx.frame_upload_raw(10 + i, fr["img"], synth.PAD, fr["pose"])
+        ip, gx, gy = gpu_ctx.frame_download(10 + i, H, W, synth.PAD)
+        wp, wx, wy = oracle.frame_prep(fr["img"], synth.PAD)
+        assert np.array_equal(ip, wp)
+        assert np.array_equal(gx.view(np.uint32), wx.view(np.uint32))
+        assert np.array_equal(gy.view(np.uint32), wy.view(np.uint32))
+        gpu_ctx.frame_upload(i, fr["img_pad"], fr["gradx_pad"], fr["grady_pad"], synth.PAD, fr["pose"])
+    g = synth.config_graph("A")
+    feats = synth.make_features(g["pos"], W, H)
+    a = feats.copy()
+    b = feats.copy()
+    b["frame_id"] = 10
+    na, da = gpu_ctx.update_feature_idepths(_lib.default_track_params(), 1, 0, a)
+    nb, db = gpu_ctx.update_feature_idepths(_lib.default_track_params(), 11, 10, b)
+    assert na == nb and np.array_equal(da["stage"], db["stage"])
+    for k in ("x", "y", "idepth_mu", "idepth_var"):
+        assert _same_float(a[k], b[k])
+    # odd sizes / small images
+    rng = np.random.default_rng(1)
+    with _lib.Context(0, 1) as small:
+        small.set_camera(37, 23, K, Kinv)
+        img = rng.integers(0, 256, (23, 37), dtype=np.uint8)
+        small.frame_upload_raw(20, img, 3, frames[0]["pose"])
+        ip, gx, gy = small.frame_download(20, 23, 37, 3)
+        wp, wx, wy = oracle.frame_prep(img, 3)
+        assert np.array_equal(ip, wp) and np.array_equal(gx, wx) and np.array_equal(gy, wy)
