@@ -392,8 +392,8 @@ def run_e2e(args, local_rank, frames, dims, barrier):
     dt = time.perf_counter() - t0
     g = frames[0]
     E, T = g["edges"].shape[0], g["tris"].shape[0]
-    # graph_init: 13V+5E floats (caller-order state) + 2V+6E ints (+ ~300 of chunk tables); mesh_bind: 12T + T
-    h2d = per_step * (4 * (13 * V + 5 * E) + 4 * (2 * V + 6 * E + 300) + 13 * T)
+    # graph_init: pos 2V + data V + weight V floats, 2V+6E ints (+ ~300 of chunk tables); mesh_bind: 12T + T
+    h2d = per_step * (4 * (4 * V) + 4 * (2 * V + 6 * E + 300) + 13 * T)
     d2h = per_step * (4 * W * H + 12 * V)
     for c in ctxs:
         c.close()

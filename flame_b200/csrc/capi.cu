@@ -510,7 +510,11 @@ int flame_b200_host_free(void* p) {
   return 0;
 }
 
-int flame_b200_graph_upload(flame_b200_ctx* c, int slot, const flame_b200_graph_in* g) {
+}  // extern "C"
+
+// fresh != 0: g carries only pos / edges / data_term / data_weight (flame_b200_graph_init): the
+// fresh-vertex defaults are generated on the device and only 4V floats + the index tables cross PCIe.
+static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph_in* g, int fresh) {
   if (int rc = check_slot(c, slot)) return rc;
   if (!g || g->V < 0 || g->E < 0 || (g->V > 0 && (!g->pos || !g->data_term || !g->x)) ||
       (g->E > 0 && !g->edges)) {
@@ -534,6 +538,7 @@ int flame_b200_graph_upload(flame_b200_ctx* c, int slot, const flame_b200_graph_
   s.plan = prep.plan;
 
   std::memcpy(hf + raw_f_offset(RF_POS, V, E), g->pos, (size_t)2 * V * sizeof(float));
+  if (!fresh) {
   fill_or_copy(hf + raw_f_offset(RF_X, V, E), g->x, V, 0.0f);
   fill_or_copy(hf + raw_f_offset(RF_W1, V, E), g->w1, V, 0.0f);
   fill_or_copy(hf + raw_f_offset(RF_W2, V, E), g->w2, V, 0.0f);
@@ -543,20 +548,34 @@ int flame_b200_graph_upload(flame_b200_ctx* c, int slot, const flame_b200_graph_
   fill_or_copy(hf + raw_f_offset(RF_XP, V, E), g->x_prev ? g->x_prev : g->x, V, 0.0f);
   fill_or_copy(hf + raw_f_offset(RF_W1P, V, E), g->w1_prev, V, 0.0f);
   fill_or_copy(hf + raw_f_offset(RF_W2P, V, E), g->w2_prev, V, 0.0f);
+  }
   fill_or_copy(hf + raw_f_offset(RF_DATA, V, E), g->data_term, V, 0.0f);
   fill_or_copy(hf + raw_f_offset(RF_WT, V, E), g->data_weight, V, 1.0f);
+  if (!fresh) {
   fill_or_copy(hf + raw_f_offset(RF_ALPHA, V, E), g->alpha, E, 0.0f);
   fill_or_copy(hf + raw_f_offset(RF_BETA, V, E), g->beta, E, 1.0f);
   fill_or_copy(hf + raw_f_offset(RF_Q1, V, E), g->q1, E, 0.0f);
   fill_or_copy(hf + raw_f_offset(RF_Q2, V, E), g->q2, E, 0.0f);
   fill_or_copy(hf + raw_f_offset(RF_Q3, V, E), g->q3, E, 0.0f);
+  }
 
   const size_t bytes = (raw_f_total(V, E) + ints_total(V, E, prep.n_chunks, prep.max_deg)) * 4;
   if (bytes > s.d_blob_cap || bytes > s.h_blob_cap) {
     set_error("internal: staging blob too small");
     return FLAME_B200_ENOMEM;
   }
-  FB_CUDA(cudaMemcpyAsync(s.d_blob, s.h_blob, bytes, cudaMemcpyHostToDevice, c->stream));
+  if (!fresh) {
+    FB_CUDA(cudaMemcpyAsync(s.d_blob, s.h_blob, bytes, cudaMemcpyHostToDevice, c->stream));
+  } else {  // pos | data_term, data_weight | index tables
+    const size_t o_data = raw_f_offset(RF_DATA, V, E) * 4, o_int = raw_f_total(V, E) * 4;
+    if (V > 0) {
+      FB_CUDA(cudaMemcpyAsync(s.d_blob, s.h_blob, (size_t)2 * V * 4, cudaMemcpyHostToDevice, c->stream));
+      FB_CUDA(cudaMemcpyAsync(s.d_blob + o_data, s.h_blob + o_data, (size_t)2 * V * 4,
+                              cudaMemcpyHostToDevice, c->stream));
+    }
+    FB_CUDA(cudaMemcpyAsync(s.d_blob + o_int, s.h_blob + o_int, bytes - o_int, cudaMemcpyHostToDevice,
+                            c->stream));
+  }
   FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
   int* di = reinterpret_cast<int*>(s.d_raw() + raw_f_total(V, E));
   s.g.V = V;
@@ -575,9 +594,15 @@ int flame_b200_graph_upload(flame_b200_ctx* c, int slot, const flame_b200_graph_
   if (V > 0)
     FB_CUDA(cudaMemcpyAsync(s.d_pos, s.d_raw(), (size_t)2 * V * sizeof(float),
                             cudaMemcpyDeviceToDevice, c->stream));
-  if (int rc = pd_pack(c->stream, s.g, s.d_raw(), g->alpha == nullptr)) return rc;
+  if (int rc = pd_pack(c->stream, s.g, s.d_raw(), g->alpha == nullptr, fresh)) return rc;
   s.loaded = true;
   return publish_graph(c, slot);
+}
+
+extern "C" {
+
+int flame_b200_graph_upload(flame_b200_ctx* c, int slot, const flame_b200_graph_in* g) {
+  return graph_upload_impl(c, slot, g, 0);
 }
 
 int flame_b200_graph_init(flame_b200_ctx* c, int slot, int32_t V, const float* pos,
@@ -592,7 +617,7 @@ int flame_b200_graph_init(flame_b200_ctx* c, int slot, int32_t V, const float* p
   g.data_term = idepth;
   g.data_weight = weight;
   g.x = idepth;  // x = x_bar = x_prev = idepth (flame.cc:2045-2048)
-  return flame_b200_graph_upload(c, slot, &g);
+  return graph_upload_impl(c, slot, &g, 1);
 }
 
 int flame_b200_graph_set_data(flame_b200_ctx* c, int slot, const float* data_term,

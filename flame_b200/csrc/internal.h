@@ -85,7 +85,7 @@ struct ResidentPlan {
 };
 #define FB_RESIDENT_MAX_DEG 64
 
-int pd_pack(cudaStream_t st, const GraphDev& g, const float* raw_f, int alpha_on_device);
+int pd_pack(cudaStream_t st, const GraphDev& g, const float* raw_f, int alpha_on_device, int fresh);
 int pd_unpack(cudaStream_t st, const GraphDev& g, float* raw_f);
 int pd_set_data(cudaStream_t st, const GraphDev& g, const float* data_term, const float* data_weight);
 int pd_reset(cudaStream_t st, const GraphDev* gs_dev, int n, int maxV, int maxE);

@@ -126,12 +126,22 @@ __device__ __forceinline__ VertexOut vertex_finish(float x, float w1, float w2, 
 // ------------------------------------------------------------------------------------------
 static inline int nblk(int n, int t) { return (n + t - 1) / t; }
 
-__global__ void k_pack_vertices(GraphDev g, const float* __restrict__ raw) {
+// fresh != 0: only pos / data_term / data_weight were uploaded; the rest follows the fresh-vertex
+// rule of Flame::syncGraph (flame.cc:2039-2048): x = x_bar = x_prev = data_term, w* = 0, q* = 0, beta = 1.
+__global__ void k_pack_vertices(GraphDev g, const float* __restrict__ raw, int fresh) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= g.V) return;
   const int o = g.vperm[v];
   const int V = g.V;
   const float* b = raw + 2 * (size_t)V;
+  if (fresh) {
+    const float d = b[9 * V + o];
+    g.vprim[v] = make_float4(d, 0.0f, 0.0f, d);
+    g.vbar[v] = make_float4(d, 0.0f, 0.0f, 0.0f);
+    g.vprev[v] = make_float4(d, 0.0f, 0.0f, 0.0f);
+    g.vwt[v] = b[10 * V + o];
+    return;
+  }
   g.vprim[v] = make_float4(b[0 * V + o], b[1 * V + o], b[2 * V + o], b[9 * V + o]);
   g.vbar[v] = make_float4(b[3 * V + o], b[4 * V + o], b[5 * V + o], 0.0f);
   g.vprev[v] = make_float4(b[6 * V + o], b[7 * V + o], b[8 * V + o], 0.0f);
@@ -139,7 +149,8 @@ __global__ void k_pack_vertices(GraphDev g, const float* __restrict__ raw) {
 }
 
 // one thread per incidence slot
-__global__ void k_pack_incidences(GraphDev g, const float* __restrict__ raw, int alpha_on_device) {
+__global__ void k_pack_incidences(GraphDev g, const float* __restrict__ raw, int alpha_on_device,
+                                  int fresh) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= 2 * g.E) return;
   const int o = g.inc_edge[slot];
@@ -156,9 +167,14 @@ __global__ void k_pack_incidences(GraphDev g, const float* __restrict__ raw, int
   } else {
     alpha = b[0 * E + o];
   }
-  g.inc_s[slot] = make_float4(alpha, b[1 * E + o], dx, dy);
   const int ent = g.inc_nbr[slot];
-  g.inc_q[slot] = make_float4(b[2 * E + o], b[3 * E + o], b[4 * E + o], __int_as_float(ent));
+  if (fresh) {
+    g.inc_s[slot] = make_float4(alpha, 1.0f, dx, dy);
+    g.inc_q[slot] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(ent));
+  } else {
+    g.inc_s[slot] = make_float4(alpha, b[1 * E + o], dx, dy);
+    g.inc_q[slot] = make_float4(b[2 * E + o], b[3 * E + o], b[4 * E + o], __int_as_float(ent));
+  }
   g.edge_slot[2 * o + (ent & 1)] = slot;  // inverse map: (edge, role) -> incidence slot
 }
 
@@ -217,13 +233,13 @@ __global__ void k_graph_reset(const GraphDev* __restrict__ gs) {
   }
 }
 
-int pd_pack(cudaStream_t st, const GraphDev& g, const float* raw_f, int alpha_on_device) {
+int pd_pack(cudaStream_t st, const GraphDev& g, const float* raw_f, int alpha_on_device, int fresh) {
   if (g.V > 0) {
-    k_pack_vertices<<<nblk(g.V, 256), 256, 0, st>>>(g, raw_f);
+    k_pack_vertices<<<nblk(g.V, 256), 256, 0, st>>>(g, raw_f, fresh);
     count_launch();
   }
   if (g.E > 0) {
-    k_pack_incidences<<<nblk(2 * g.E, 256), 256, 0, st>>>(g, raw_f, alpha_on_device);
+    k_pack_incidences<<<nblk(2 * g.E, 256), 256, 0, st>>>(g, raw_f, alpha_on_device || fresh, fresh);
     count_launch();
   }
   FB_CUDA(cudaGetLastError());
