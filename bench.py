@@ -358,19 +358,17 @@ def run_e2e(args, local_rank, frames, dims, barrier):
     p = _lib.default_pd_params()
     ctxs = [_lib.Context(local_rank, 1) for _ in range(P)]
     outs = [_lib.PinnedArray((H, W)) for _ in range(P)]
+    vout = [tuple(np.empty(V, np.float32) for _ in range(3)) for _ in range(P)]
     per_step = len(frames)
 
     def one(job):
         k, i = job
         g = frames[i]
-        ctx, out = ctxs[k], outs[k]
-        ctx.graph_init(0, g["pos"], g["data_term"], g["edges"])
-        ctx.mesh_bind(0, g["tris"], H, W)
-        ctx.pd_run(p, iters, 0, 1, args.mode)
-        ctx.mesh_project(0, 1, 1.0)
-        ctx.mesh_download(0, out.array)
-        x = ctx.graph_download(0, V, g["edges"].shape[0], fields=("x", "w1", "w2"))  # syncs the stream
-        return float(x["x"][0]) + float(out.array[H // 2, W // 2])
+        ctx, out, (x, w1, w2) = ctxs[k], outs[k], vout[k]
+        # the public per-frame call: host arrays in (graph + triangles), host arrays out (dense map
+        # into pinned memory, smoothed vertex idepths and plane parameters); synchronises.
+        ctx.process_frame(0, g["pos"], g["data_term"], g["edges"], g["tris"], H, W, p, iters, out.array, x, w1, w2)
+        return float(x[0]) + float(out.array[H // 2, W // 2])
 
     pool = ThreadPoolExecutor(P)
 

@@ -85,7 +85,8 @@ SYMBOLS = [
     "flame_b200_pd_default_params", "flame_b200_graph_upload", "flame_b200_graph_init",
     "flame_b200_graph_set_data", "flame_b200_graph_reset", "flame_b200_graph_download", "flame_b200_pd_run",
     "flame_b200_pd_cost", "flame_b200_interpolate_mesh", "flame_b200_mesh_bind",
-    "flame_b200_mesh_project", "flame_b200_mesh_download", "flame_b200_track_default_params",
+    "flame_b200_mesh_project", "flame_b200_mesh_download", "flame_b200_process_frame",
+    "flame_b200_track_default_params",
     "flame_b200_set_camera", "flame_b200_frame_upload", "flame_b200_frame_upload_raw",
     "flame_b200_frame_download", "flame_b200_update_feature_idepths",
 ]
@@ -124,6 +125,9 @@ def lib():
     L.flame_b200_mesh_bind.argtypes = [vp, C.c_int, C.c_int32, i32p, u8p, u8p, C.c_int, C.c_int]
     L.flame_b200_mesh_project.argtypes = [vp, C.c_int, C.c_int, C.c_float]
     L.flame_b200_mesh_download.argtypes = [vp, C.c_int, vp]
+    L.flame_b200_process_frame.argtypes = [vp, C.c_int, C.c_int32, f32p, f32p, f32p, C.c_int32, i32p, C.c_int32,
+                                           i32p, C.c_int, C.c_int, C.POINTER(PDParams), C.c_int, C.c_float,
+                                           vp, f32p, f32p, f32p]
     L.flame_b200_track_default_params.argtypes = [C.POINTER(TrackParams)]
     L.flame_b200_track_default_params.restype = None
     L.flame_b200_set_camera.argtypes = [vp, C.c_int, C.c_int, f32p, f32p]
@@ -300,6 +304,15 @@ class Context:
     def mesh_download(self, slot, out):
         """Asynchronous; out: numpy array (ideally PinnedArray.array). Complete after sync()."""
         check(lib().flame_b200_mesh_download(self._h, slot, out.ctypes.data_as(C.c_void_p)))
+
+    def process_frame(self, slot, pos, idepth, edges, tris, rows, cols, params, n_iters, out_map, out_x,
+                      out_w1=None, out_w2=None, weight=None, scale=1.0):
+        """graph_init + mesh_bind + pd_run + mesh_project + downloads + sync in ONE C call."""
+        check(lib().flame_b200_process_frame(
+            self._h, slot, pos.shape[0], fptr(pos), fptr(idepth), fptr(weight), edges.shape[0], iptr(edges),
+            tris.shape[0], iptr(tris), rows, cols, C.byref(params), n_iters, scale,
+            out_map.ctypes.data_as(C.c_void_p) if out_map is not None else None, fptr(out_x), fptr(out_w1),
+            fptr(out_w2)))
 
     # ---- epipolar search ----
     def set_camera(self, width, height, K, Kinv):

@@ -932,6 +932,27 @@ int flame_b200_interpolate_mesh(flame_b200_ctx* c, int slot, int32_t T, const in
   return 0;
 }
 
+// ---- whole frame in one call ---------------------------------------------------------------------
+int flame_b200_process_frame(flame_b200_ctx* c, int slot, int32_t V, const float* pos,
+                             const float* idepth, const float* weight, int32_t E,
+                             const int32_t* edges, int32_t T, const int32_t* tris, int rows, int cols,
+                             const flame_b200_pd_params* params, int n_iters, float scale,
+                             float* out_map, float* out_x, float* out_w1, float* out_w2) {
+  if (int rc = flame_b200_graph_init(c, slot, V, pos, idepth, weight, E, edges)) return rc;
+  if (int rc = flame_b200_mesh_bind(c, slot, T, tris, nullptr, nullptr, rows, cols)) return rc;
+  if (int rc = flame_b200_pd_run(c, slot, 1, params, n_iters, FLAME_B200_PD_AUTO)) return rc;
+  if (int rc = flame_b200_mesh_project(c, slot, 1, scale)) return rc;
+  if (out_map)
+    if (int rc = flame_b200_mesh_download(c, slot, out_map)) return rc;
+  flame_b200_graph_out o;
+  std::memset(&o, 0, sizeof(o));
+  o.x = out_x;
+  o.w1 = out_w1;
+  o.w2 = out_w2;
+  if (out_x || out_w1 || out_w2) return flame_b200_graph_download(c, slot, &o);  // synchronises
+  return flame_b200_ctx_sync(c);
+}
+
 // ---- epipolar search ------------------------------------------------------------------------
 int flame_b200_set_camera(flame_b200_ctx* c, int width, int height, const float K[9],
                           const float Kinv[9]) {

@@ -169,6 +169,17 @@ int flame_b200_mesh_project(flame_b200_ctx* ctx, int slot0, int n_slots, float s
  * complete after flame_b200_ctx_sync(). */
 int flame_b200_mesh_download(flame_b200_ctx* ctx, int slot, float* out_host);
 
+/* ---- the per-frame tail of Flame::update in one call (flame.cc:312-415): fresh graph from the
+ *      features (syncGraph's init rule + edge weights), n_iters x step(), extraction of the smoothed
+ *      vertex idepths (x * scale) and plane parameters, interpolateMesh into a NaN-initialised map.
+ *      Host buffers in, host buffers out (any output pointer may be NULL); out_map should be
+ *      page-locked (flame_b200_host_alloc) for full PCIe speed. Synchronises the stream. */
+int flame_b200_process_frame(flame_b200_ctx* ctx, int slot, int32_t V, const float* pos,
+                             const float* idepth, const float* weight, int32_t E,
+                             const int32_t* edges, int32_t T, const int32_t* tris, int rows, int cols,
+                             const flame_b200_pd_params* params, int n_iters, float scale,
+                             float* out_map, float* out_x, float* out_w1, float* out_w2);
+
 /* ---- epipolar search + measurement + fusion: Flame::updateFeatureIDepths / trackFeature
  *      (flame.cc:1280-1752) over stereo::inverse_depth_filter::{predict,getSearchRegion,search,
  *      update} (stereo/inverse_depth_filter.h:73-107), stereo::line_stereo::match

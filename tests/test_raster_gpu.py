@@ -84,3 +84,20 @@ def test_project_from_graph_state(gpu_ctx, oracle):
     gpu_ctx.mesh_download(0, out.array)
     gpu_ctx.sync()
     _assert_same_image(out.array.copy(), want)
+
+
+def test_process_frame_one_call(gpu_ctx, oracle):
+    """flame_b200_process_frame == graph_init + pd_run + interpolateMesh of the oracle, bit-exact."""
+    g = synth.config_graph("B")
+    alpha, beta = oracle.edge_weights(g["edges"], g["pos"])
+    s = synth.init_state(g, alpha, beta)
+    oracle.pd_run(s, oracle.pd_default_params(), 30)
+    want = oracle.interpolate_mesh(g["tris"], g["pos"], s["x"], g["H"], g["W"])
+    out = _lib.PinnedArray((g["H"], g["W"]))
+    V = g["pos"].shape[0]
+    x, w1, w2 = (np.empty(V, np.float32) for _ in range(3))
+    gpu_ctx.process_frame(4, g["pos"], g["data_term"], g["edges"], g["tris"], g["H"], g["W"],
+                          _lib.default_pd_params(), 30, out.array, x, w1, w2)
+    _assert_same_image(out.array.copy(), want)
+    for a, b in ((x, s["x"]), (w1, s["w1"]), (w2, s["w2"])):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
