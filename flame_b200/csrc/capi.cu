@@ -78,17 +78,6 @@ struct flame_b200_ctx {
 
 namespace fb {
 
-template <typename T>
-static int grow(T** p, size_t* cap, size_t need) {
-  if (need <= *cap) return 0;
-  if (*p) FB_CUDA(cudaFree(*p));
-  *p = nullptr;
-  size_t n = std::max(need, *cap + *cap / 2);
-  FB_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
-  *cap = n;
-  return 0;
-}
-
 static inline uint32_t part1by1(uint32_t x) {
   x &= 0x0000ffffu;
   x = (x ^ (x << 8)) & 0x00ff00ffu;

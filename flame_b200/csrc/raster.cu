@@ -359,8 +359,8 @@ int raster_values_from_graph(cudaStream_t st, const GraphDev* gs_dev, const Mesh
   return 0;
 }
 
-// ms_dev: device array of n MeshDev; the per-slot tile_count / n_large words are contiguous in
-// `zero_base` (zero_bytes per slot) so one memset clears the whole batch when `zero_stride` is 0.
+// ms_dev: device array of n MeshDev. The tile counters / list lengths re-arm themselves (k_tile_scan,
+// k_tile_raster), so a projection needs no memset.
 int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_ctas, int fill_nan) {
   if (n == 0 || max_ctas == 0) return 0;
   if (maxT > 0) {

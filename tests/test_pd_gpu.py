@@ -171,3 +171,47 @@ def test_pd_tiny_graphs(gpu_ctx, oracle):
             gpu_ctx.pd_run(_lib.default_pd_params(), 9, slot0=3, mode=mode)
             got = gpu_ctx.graph_download(3, V, edges.shape[0])
             _assert_bit_equal(got, want, STATE)
+
+
+def test_pd_empty_and_edgeless_graphs(gpu_ctx, oracle):
+    """V = 0 and E = 0 (isolated vertices only: prox + extragradient with no coupling)."""
+    gpu_ctx.graph_init(5, np.zeros((0, 2), np.float32), np.zeros(0, np.float32), np.zeros((0, 2), np.int32))
+    gpu_ctx.pd_run(_lib.default_pd_params(), 5, slot0=5)
+    assert gpu_ctx.graph_download(5, 0, 0)["x"].shape == (0,)
+    pos = np.array([[3, 4], [50, 60], [7, 90]], np.float32)
+    data = np.array([0.2, 11.0, -1.0], np.float32)  # outside [x_min, x_max]: clamped by the prox
+    g = {"pos": pos, "edges": np.zeros((0, 2), np.int32), "data_term": data, "data_weight": np.ones(3, np.float32)}
+    want = synth.init_state(g, np.zeros(0, np.float32), np.zeros(0, np.float32))
+    oracle.pd_run(want, oracle.pd_default_params(), 4)
+    for mode in (_lib.PD_STREAM, _lib.PD_RESIDENT):
+        gpu_ctx.graph_init(5, pos, data, g["edges"])
+        gpu_ctx.pd_run(_lib.default_pd_params(), 4, slot0=5, mode=mode)
+        got = gpu_ctx.graph_download(5, 3, 0)
+        _assert_bit_equal(got, want, ("x", "w1", "w2", "x_bar", "w1_bar", "w2_bar", "x_prev"))
+
+
+def test_pd_graph_larger_than_a_cluster_streams(gpu_ctx, oracle):
+    """A graph beyond the resident kernel's capacity (V = 40k): AUTO must fall back to the streaming
+    kernel and stay bit-exact; RESIDENT must refuse loudly."""
+    g = synth.make_graph(2560, 1440, 40000, seed=3, noise_seed=4, triangulator="scipy")
+    V, E = g["pos"].shape[0], g["edges"].shape[0]
+    alpha, beta = oracle.edge_weights(g["edges"], g["pos"])
+    want = synth.init_state(g, alpha, beta)
+    oracle.pd_run(want, oracle.pd_default_params(), 12)
+    gpu_ctx.graph_init(6, g["pos"], g["data_term"], g["edges"])
+    with pytest.raises(_lib.FlameB200Error):
+        gpu_ctx.pd_run(_lib.default_pd_params(), 1, slot0=6, mode=_lib.PD_RESIDENT)
+    gpu_ctx.graph_init(6, g["pos"], g["data_term"], g["edges"])
+    gpu_ctx.pd_run(_lib.default_pd_params(), 12, slot0=6, mode=_lib.PD_AUTO)
+    got = gpu_ctx.graph_download(6, V, E)
+    _assert_bit_equal(got, want, STATE)
+    # dense projection at 2560x1440 (larger than any BASELINE config; still < 2896 px per side)
+    img_w = oracle.interpolate_mesh(g["tris"], g["pos"], want["x"], 1440, 2560)
+    gpu_ctx.mesh_bind(6, g["tris"], 1440, 2560)
+    gpu_ctx.mesh_project(6, 1, 1.0)
+    out = np.empty((1440, 2560), np.float32)
+    gpu_ctx.mesh_download(6, out)
+    gpu_ctx.sync()
+    assert np.array_equal(np.isnan(out), np.isnan(img_w))
+    m = ~np.isnan(out)
+    assert np.array_equal(out[m].view(np.uint32), img_w[m].view(np.uint32))
