@@ -37,6 +37,13 @@ class GraphIn(C.Structure):
                 ("alpha", f32p), ("beta", f32p), ("q1", f32p), ("q2", f32p), ("q3", f32p)]
 
 
+class GraphSync(C.Structure):
+    """flame_b200_graph_sync."""
+    _fields_ = [("V", C.c_int32), ("E", C.c_int32), ("pos", f32p), ("data_term", f32p),
+                ("data_weight", f32p), ("vtx_from", i32p), ("x_init", f32p), ("edges", i32p),
+                ("edge_from", i32p), ("check_sticky_obstacles", C.c_int32)]
+
+
 class GraphOut(C.Structure):
     _fields_ = [(k, f32p) for k in ("x", "w1", "w2", "x_bar", "w1_bar", "w2_bar", "x_prev",
                                     "w1_prev", "w2_prev", "alpha", "beta", "q1", "q2", "q3")]
@@ -83,7 +90,8 @@ SYMBOLS = [
     "flame_b200_ctx_create", "flame_b200_ctx_destroy", "flame_b200_ctx_sync", "flame_b200_ctx_stream",
     "flame_b200_host_alloc", "flame_b200_host_free",
     "flame_b200_pd_default_params", "flame_b200_graph_upload", "flame_b200_graph_init",
-    "flame_b200_graph_set_data", "flame_b200_graph_reset", "flame_b200_graph_download", "flame_b200_pd_run",
+    "flame_b200_graph_set_data", "flame_b200_graph_reset", "flame_b200_graph_download",
+    "flame_b200_graph_project", "flame_b200_graph_resync", "flame_b200_pd_run",
     "flame_b200_pd_cost", "flame_b200_interpolate_mesh", "flame_b200_mesh_bind",
     "flame_b200_mesh_project", "flame_b200_mesh_download", "flame_b200_process_frame",
     "flame_b200_track_default_params",
@@ -118,6 +126,8 @@ def lib():
     L.flame_b200_graph_set_data.argtypes = [vp, C.c_int, f32p, f32p]
     L.flame_b200_graph_reset.argtypes = [vp, C.c_int, C.c_int]
     L.flame_b200_graph_download.argtypes = [vp, C.c_int, C.POINTER(GraphOut)]
+    L.flame_b200_graph_project.argtypes = [vp, C.c_int, f32p, f32p, C.c_float, f32p, f32p]
+    L.flame_b200_graph_resync.argtypes = [vp, C.c_int, C.POINTER(GraphSync)]
     L.flame_b200_pd_run.argtypes = [vp, C.c_int, C.c_int, C.POINTER(PDParams), C.c_int, C.c_int]
     L.flame_b200_pd_cost.argtypes = [vp, C.c_int, C.POINTER(PDParams), C.c_int, f32p, f32p]
     L.flame_b200_interpolate_mesh.argtypes = [vp, C.c_int, C.c_int32, i32p, C.c_int32, f32p, f32p,
@@ -273,6 +283,32 @@ class Context:
             setattr(o, k, fptr(out[k]))
         check(lib().flame_b200_graph_download(self._h, slot, C.byref(o)))
         return out
+
+    def graph_project(self, slot, V, q_wxyz, t, graph_scale=1.0):
+        """Flame::projectGraph's vertex loop on the device; returns (u_new [V,2], idepth_new [V])."""
+        q = np.ascontiguousarray(q_wxyz, np.float32)
+        tt = np.ascontiguousarray(t, np.float32)
+        pos = np.empty((V, 2), np.float32)
+        idepth = np.empty(V, np.float32)
+        check(lib().flame_b200_graph_project(self._h, slot, fptr(q), fptr(tt), graph_scale, fptr(pos),
+                                             fptr(idepth)))
+        return pos, idepth
+
+    def graph_resync(self, slot, pos, data_term, edges, vtx_from, edge_from, data_weight=None,
+                     x_init=None, check_sticky_obstacles=False):
+        """Flame::syncGraph's graph edits with the solver state carried over on the device."""
+        s = GraphSync()
+        s.V = pos.shape[0]
+        s.E = edges.shape[0]
+        s.pos = fptr(pos)
+        s.data_term = fptr(data_term)
+        s.data_weight = fptr(data_weight)
+        s.vtx_from = iptr(vtx_from)
+        s.x_init = fptr(x_init)
+        s.edges = iptr(edges)
+        s.edge_from = iptr(edge_from)
+        s.check_sticky_obstacles = int(check_sticky_obstacles)
+        check(lib().flame_b200_graph_resync(self._h, slot, C.byref(s)))
 
     def pd_run(self, params, n_iters, slot0=0, n_slots=1, mode=PD_AUTO):
         check(lib().flame_b200_pd_run(self._h, slot0, n_slots, C.byref(params), n_iters, mode))

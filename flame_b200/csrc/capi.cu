@@ -26,6 +26,8 @@ int stereo_frame_upload_raw(void** state, cudaStream_t st, int fslot, const uint
 int stereo_frame_download(void* state, cudaStream_t st, int fslot, uint8_t* img_pad, float* gradx_pad,
                           float* grady_pad);
 void stereo_destroy(void* state);
+int stereo_graph_project(void* state, cudaStream_t st, const GraphDev& g, float* d_pos,
+                         const float q[4], const float t[3], float scale, float* d_out);
 
 // ------------------------------------------------------------------------------------------
 struct Slot {
@@ -43,6 +45,9 @@ struct Slot {
   float* d_pos = nullptr;           // 2V caller order (kept for the dense projection)
   float* d_values = nullptr;        // V caller order
   ResidentPlan plan{};              // chosen at upload (cluster == 0 -> streaming only)
+  bool stale = false;               // graph_project moved the vertices: edge records need a resync
+  float* d_carry = nullptr;         // graph_resync: unpacked state of the previous graph
+  size_t carry_cap = 0;             // floats
   // mesh
   MeshDev m{};
   int capT = 0;
@@ -464,7 +469,8 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
                     (void*)s.d_pos, (void*)s.d_values,
                     (void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.m.img, (void*)s.m.setup,
                     (void*)s.m.tile_count, (void*)s.m.tile_off, (void*)s.m.pairs, (void*)s.m.large,
-                    (void*)s.m.big, (void*)s.m.counters, (void*)s.d_mpos, (void*)s.d_mvalues})
+                    (void*)s.m.big, (void*)s.m.counters, (void*)s.d_mpos, (void*)s.d_mvalues,
+                    (void*)s.d_carry})
       if (p) cudaFree(p);
     if (s.h_blob) cudaFreeHost(s.h_blob);
     if (s.blob_free) cudaEventDestroy(s.blob_free);
@@ -503,7 +509,17 @@ int flame_b200_host_free(void* p) {
 
 // fresh != 0: g carries only pos / edges / data_term / data_weight (flame_b200_graph_init): the
 // fresh-vertex defaults are generated on the device and only 4V floats + the index tables cross PCIe.
-static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph_in* g, int fresh) {
+struct SyncMaps {
+  const int32_t* vtx_from;
+  const int32_t* edge_from;
+  const float* x_init;
+  int sticky;
+};
+
+// sync != nullptr (flame_b200_graph_resync): like fresh, plus the state of the slot's current graph is
+// unpacked into d_carry first and gathered into the new raw image on the device.
+static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph_in* g, int fresh,
+                             const SyncMaps* sync = nullptr) {
   if (int rc = check_slot(c, slot)) return rc;
   if (!g || g->V < 0 || g->E < 0 || (g->V > 0 && (!g->pos || !g->data_term || !g->x)) ||
       (g->E > 0 && !g->edges)) {
@@ -516,7 +532,20 @@ static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph
   PrepOut prep;
   if (int rc = prep_plan(c, V, E, g->pos, g->edges, &prep)) return rc;
   if (int rc = wait_blob(s)) return rc;
-  if (int rc = ensure_blob(s, blob_bytes(V, E, prep.n_chunks, prep.max_deg))) return rc;
+  const int Vold = s.g.V, Eold = s.g.E;
+  if (sync) {  // before any buffer of the old graph is touched
+    const size_t need = raw_f_total(Vold, Eold) + 1;
+    if (need > s.carry_cap) {
+      if (s.d_carry) FB_CUDA(cudaFree(s.d_carry));
+      s.d_carry = nullptr;
+      const size_t n = std::max(need, s.carry_cap + s.carry_cap / 2);
+      FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_carry), n * sizeof(float)));
+      s.carry_cap = n;
+    }
+    if (int rc = pd_unpack(c->stream, s.g, s.d_carry)) return rc;
+  }
+  if (int rc = ensure_blob(s, blob_bytes(V, E, prep.n_chunks, prep.max_deg) +
+                                  (sync ? ((size_t)V + E) * 4 : 0))) return rc;
   if (int rc = ensure_graph(s, V, E)) return rc;
 
   float* hf = reinterpret_cast<float*>(s.h_blob);
@@ -538,6 +567,7 @@ static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph
   fill_or_copy(hf + raw_f_offset(RF_W1P, V, E), g->w1_prev, V, 0.0f);
   fill_or_copy(hf + raw_f_offset(RF_W2P, V, E), g->w2_prev, V, 0.0f);
   }
+  if (sync && sync->x_init) fill_or_copy(hf + raw_f_offset(RF_X, V, E), sync->x_init, V, 0.0f);
   fill_or_copy(hf + raw_f_offset(RF_DATA, V, E), g->data_term, V, 0.0f);
   fill_or_copy(hf + raw_f_offset(RF_WT, V, E), g->data_weight, V, 1.0f);
   if (!fresh) {
@@ -549,7 +579,14 @@ static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph
   }
 
   const size_t bytes = (raw_f_total(V, E) + ints_total(V, E, prep.n_chunks, prep.max_deg)) * 4;
-  if (bytes > s.d_blob_cap || bytes > s.h_blob_cap) {
+  // resync maps live after the device-only edge_slot table: [vtx_from V | edge_from E]
+  const size_t o_maps = bytes + (size_t)2 * E * 4, maps_bytes = sync ? ((size_t)V + E) * 4 : 0;
+  if (sync) {
+    int* hm = reinterpret_cast<int*>(s.h_blob + o_maps);
+    if (V > 0) std::memcpy(hm, sync->vtx_from, (size_t)V * 4);
+    if (E > 0) std::memcpy(hm + V, sync->edge_from, (size_t)E * 4);
+  }
+  if (o_maps + maps_bytes > s.d_blob_cap || o_maps + maps_bytes > s.h_blob_cap) {
     set_error("internal: staging blob too small");
     return FLAME_B200_ENOMEM;
   }
@@ -564,6 +601,14 @@ static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph
     }
     FB_CUDA(cudaMemcpyAsync(s.d_blob + o_int, s.h_blob + o_int, bytes - o_int, cudaMemcpyHostToDevice,
                             c->stream));
+    if (sync && sync->x_init && V > 0) {
+      const size_t o_x = raw_f_offset(RF_X, V, E) * 4;
+      FB_CUDA(cudaMemcpyAsync(s.d_blob + o_x, s.h_blob + o_x, (size_t)V * 4, cudaMemcpyHostToDevice,
+                              c->stream));
+    }
+    if (maps_bytes)
+      FB_CUDA(cudaMemcpyAsync(s.d_blob + o_maps, s.h_blob + o_maps, maps_bytes, cudaMemcpyHostToDevice,
+                              c->stream));
   }
   FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
   int* di = reinterpret_cast<int*>(s.d_raw() + raw_f_total(V, E));
@@ -583,8 +628,15 @@ static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph
   if (V > 0)
     FB_CUDA(cudaMemcpyAsync(s.d_pos, s.d_raw(), (size_t)2 * V * sizeof(float),
                             cudaMemcpyDeviceToDevice, c->stream));
+  if (sync) {
+    const int* dm = reinterpret_cast<const int*>(s.d_blob + o_maps);
+    if (int rc = pd_resync_gather(c->stream, s.d_raw(), V, E, s.d_carry, Vold, Eold, dm, dm + V,
+                                  sync->x_init != nullptr, sync->sticky)) return rc;
+    fresh = 0;
+  }
   if (int rc = pd_pack(c->stream, s.g, s.d_raw(), g->alpha == nullptr, fresh)) return rc;
   s.loaded = true;
+  s.stale = false;
   return publish_graph(c, slot);
 }
 
@@ -607,6 +659,70 @@ int flame_b200_graph_init(flame_b200_ctx* c, int slot, int32_t V, const float* p
   g.data_weight = weight;
   g.x = idepth;  // x = x_bar = x_prev = idepth (flame.cc:2045-2048)
   return graph_upload_impl(c, slot, &g, 1);
+}
+
+int flame_b200_graph_project(flame_b200_ctx* c, int slot, const float q_wxyz[4], const float t[3],
+                             float graph_scale, float* pos_out, float* idepth_out) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (!q_wxyz || !t || !(graph_scale > 0.0f)) {
+    set_error("graph_project: bad arguments");
+    return FLAME_B200_EINVAL;
+  }
+  if (int rc = use_device(c)) return rc;
+  Slot& s = c->slots[slot];
+  if (!s.loaded) {
+    set_error("graph_project: slot has no graph");
+    return FLAME_B200_ESTATE;
+  }
+  const int V = s.g.V;
+  if (int rc = wait_blob(s)) return rc;
+  // the raw staging area (>= 13V floats) is scratch between uploads: [u_new 2V | idepth_new V]
+  if (int rc = stereo_graph_project(c->stereo, c->stream, s.g, s.d_pos, q_wxyz, t, graph_scale,
+                                    s.d_raw())) return rc;
+  s.stale = true;
+  if (V == 0) return 0;
+  FB_CUDA(cudaMemcpyAsync(s.h_blob, s.d_blob, (size_t)3 * V * 4, cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
+  FB_CUDA(cudaStreamSynchronize(c->stream));
+  const float* hf = reinterpret_cast<const float*>(s.h_blob);
+  if (pos_out) std::memcpy(pos_out, hf, (size_t)2 * V * 4);
+  if (idepth_out) std::memcpy(idepth_out, hf + 2 * (size_t)V, (size_t)V * 4);
+  return 0;
+}
+
+int flame_b200_graph_resync(flame_b200_ctx* c, int slot, const flame_b200_graph_sync* y) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (!y || y->V < 0 || y->E < 0 || (y->V > 0 && (!y->pos || !y->data_term || !y->vtx_from)) ||
+      (y->E > 0 && (!y->edges || !y->edge_from))) {
+    set_error("graph_resync: missing required array");
+    return FLAME_B200_EINVAL;
+  }
+  Slot& s = c->slots[slot];
+  if (!s.loaded) {
+    set_error("graph_resync: slot has no graph to carry state from (use flame_b200_graph_init)");
+    return FLAME_B200_ESTATE;
+  }
+  for (int v = 0; v < y->V; ++v)
+    if (y->vtx_from[v] < -1 || y->vtx_from[v] >= s.g.V) {
+      set_error("graph_resync: vtx_from out of range");
+      return FLAME_B200_EINVAL;
+    }
+  for (int e = 0; e < y->E; ++e)
+    if (y->edge_from[e] < -1 || y->edge_from[e] >= s.g.E) {
+      set_error("graph_resync: edge_from out of range");
+      return FLAME_B200_EINVAL;
+    }
+  flame_b200_graph_in g;
+  std::memset(&g, 0, sizeof(g));
+  g.V = y->V;
+  g.E = y->E;
+  g.pos = y->pos;
+  g.edges = y->edges;
+  g.data_term = y->data_term;
+  g.data_weight = y->data_weight;
+  g.x = y->data_term;
+  SyncMaps m{y->vtx_from, y->edge_from, y->x_init, y->check_sticky_obstacles != 0};
+  return graph_upload_impl(c, slot, &g, 1, &m);
 }
 
 int flame_b200_graph_set_data(flame_b200_ctx* c, int slot, const float* data_term,
@@ -696,6 +812,10 @@ int flame_b200_pd_run(flame_b200_ctx* c, int slot0, int n_slots, const flame_b20
     const Slot& s = c->slots[i];
     if (!s.loaded) {
       set_error("pd_run: slot has no graph");
+      return FLAME_B200_ESTATE;
+    }
+    if (s.stale) {
+      set_error("pd_run: vertices were moved by graph_project; call graph_resync (or upload) first");
       return FLAME_B200_ESTATE;
     }
     maxV = std::max(maxV, s.g.V);

@@ -87,6 +87,8 @@ struct ResidentPlan {
 
 int pd_pack(cudaStream_t st, const GraphDev& g, const float* raw_f, int alpha_on_device, int fresh);
 int pd_unpack(cudaStream_t st, const GraphDev& g, float* raw_f);
+int pd_resync_gather(cudaStream_t st, float* raw_f, int V, int E, const float* carry, int Vold,
+                     int Eold, const int* vtx_from, const int* edge_from, int has_init, int sticky);
 int pd_set_data(cudaStream_t st, const GraphDev& g, const float* data_term, const float* data_weight);
 int pd_reset(cudaStream_t st, const GraphDev* gs_dev, int n, int maxV, int maxE);
 int pd_run_stream(cudaStream_t st, const GraphDev* gs_dev, int n, int max_chunks, int threads,

@@ -233,6 +233,57 @@ __global__ void k_graph_reset(const GraphDev* __restrict__ gs) {
   }
 }
 
+// Device-side Flame::syncGraph state carry-over (flame.cc:1984-2048, 2084-2105): builds the raw
+// (caller-order) state of the NEW graph from the unpacked state of the OLD one.
+//   carried vertex (vtx_from >= 0): x, w, x_bar, w_bar, x_prev, w_prev are kept (:2003-2008 touch only
+//     pos / data_term / data_weight), optional sticky-obstacle reset of x (:2016-2019);
+//   new vertex: x = x_bar = x_prev = x_init (or data_term), w = 0 (:2046-2048, VertexData defaults);
+//   carried edge: q kept; new edge: q = 0 (EdgeData defaults); beta = 1 for all (:2103); alpha is
+//     recomputed from the new positions by the pack kernel (:2102).
+__global__ void k_resync_gather(float* __restrict__ raw, int V, int E, const float* __restrict__ carry,
+                                int Vold, int Eold, const int* __restrict__ vtx_from,
+                                const int* __restrict__ edge_from, int has_init, int sticky) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < V) {
+    float* b = raw + 2 * (size_t)V;
+    const float* bo = carry + 2 * (size_t)Vold;
+    const int from = vtx_from[i];
+    const float data = b[9 * (size_t)V + i];
+    if (from >= 0) {
+      float x = bo[from];
+      if (sticky && sub(x, data) > 0.25f) x = data;
+      b[i] = x;
+#pragma unroll
+      for (int f = 1; f < 9; ++f) b[f * (size_t)V + i] = bo[f * (size_t)Vold + from];
+    } else {
+      const float x = has_init ? b[i] : data;
+      b[0 * (size_t)V + i] = x; b[1 * (size_t)V + i] = 0.0f; b[2 * (size_t)V + i] = 0.0f;
+      b[3 * (size_t)V + i] = x; b[4 * (size_t)V + i] = 0.0f; b[5 * (size_t)V + i] = 0.0f;
+      b[6 * (size_t)V + i] = x; b[7 * (size_t)V + i] = 0.0f; b[8 * (size_t)V + i] = 0.0f;
+    }
+  }
+  if (i < E) {
+    float* e = raw + 13 * (size_t)V;
+    const float* eo = carry + 13 * (size_t)Vold;
+    const int from = edge_from[i];
+    e[1 * (size_t)E + i] = 1.0f;
+    e[2 * (size_t)E + i] = from >= 0 ? eo[2 * (size_t)Eold + from] : 0.0f;
+    e[3 * (size_t)E + i] = from >= 0 ? eo[3 * (size_t)Eold + from] : 0.0f;
+    e[4 * (size_t)E + i] = from >= 0 ? eo[4 * (size_t)Eold + from] : 0.0f;
+  }
+}
+
+int pd_resync_gather(cudaStream_t st, float* raw_f, int V, int E, const float* carry, int Vold,
+                     int Eold, const int* vtx_from, const int* edge_from, int has_init, int sticky) {
+  const int n = V > E ? V : E;
+  if (n == 0) return 0;
+  k_resync_gather<<<nblk(n, 256), 256, 0, st>>>(raw_f, V, E, carry, Vold, Eold, vtx_from, edge_from,
+                                                has_init, sticky);
+  count_launch();
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int pd_pack(cudaStream_t st, const GraphDev& g, const float* raw_f, int alpha_on_device, int fresh) {
   if (g.V > 0) {
     k_pack_vertices<<<nblk(g.V, 256), 256, 0, st>>>(g, raw_f, fresh);

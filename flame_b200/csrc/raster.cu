@@ -198,32 +198,50 @@ __global__ void __launch_bounds__(256) k_big_fill(const MeshDev* __restrict__ ms
   }
 }
 
-// one CTA of 1024 threads: exclusive scan of tile_count -> tile_off (n_tiles + 1), zero the cursors
+// one CTA of 1024 threads per slot: exclusive scan of tile_count -> tile_off (n_tiles + 1) in
+// coalesced chunks of 1024 tiles (warp-shuffle scan + one cross-warp step), zero the cursors
 __global__ void __launch_bounds__(1024) k_tile_scan(const MeshDev* __restrict__ ms) {
   const MeshDev m = ms[blockIdx.y];
-  __shared__ int s_part[1024];
+  __shared__ int s_warp[32];
+  __shared__ int s_run;
   const int n = m.n_tiles;
-  const int per = (n + 1023) / 1024;
-  const int a = min(threadIdx.x * per, n), b = min(a + per, n);
-  int sum = 0;
-  for (int i = a; i < b; ++i) sum += m.tile_count[i];
-  s_part[threadIdx.x] = sum;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_run = 0;
   __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    const int v = (threadIdx.x >= o) ? s_part[threadIdx.x - o] : 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int cnt = (i < n) ? m.tile_count[i] : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    s_part[threadIdx.x] += v;
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += v;
+      }
+      s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const int run = s_run;
+    const int excl = run + (warp > 0 ? s_warp[warp - 1] : 0) + incl - cnt;
+    if (i < n) {
+      m.tile_off[i] = excl;
+      m.tile_count[i] = 0;  // reused as the fill cursor
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) s_run = run + s_warp[31];
     __syncthreads();
   }
-  int run = s_part[threadIdx.x] - sum;  // exclusive prefix of this thread's range
-  for (int i = a; i < b; ++i) {
-    const int cnt = m.tile_count[i];
-    m.tile_off[i] = run;
-    m.tile_count[i] = 0;  // reused as the fill cursor
-    run += cnt;
-  }
-  if (threadIdx.x == 1023) m.tile_off[n] = s_part[1023];
-  if (threadIdx.x == 0) {  // latch this projection's list lengths, re-arm the accumulators
+  if (threadIdx.x == 0) {
+    m.tile_off[n] = s_run;
+    // latch this projection's list lengths, re-arm the accumulators
     m.counters[1] = m.counters[0];
     m.counters[0] = 0;
     m.counters[3] = m.counters[2];

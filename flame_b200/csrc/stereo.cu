@@ -1084,6 +1084,53 @@ int stereo_update(void* state, cudaStream_t st, const flame_b200_track_params* p
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Flame::projectGraph, per-vertex body (flame.cc:1892-1899): pos, x <- EpipolarGeometry::project
+// ------------------------------------------------------------------------------------------
+struct ProjectArgs {
+  float K[9], Kinv[9], q[4], t[3];
+  float scale;
+};
+
+__global__ void __launch_bounds__(128) k_graph_project(GraphDev g, float* __restrict__ pos,
+                                                       ProjectArgs a, float* __restrict__ out) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= g.V) return;
+  EpiGeo e;
+  e.init(a.K, a.Kinv);
+  e.load(a.q, a.t);
+  const int o = g.vperm[v];
+  const float x = g.vprim[v].x;
+  float cx, cy, idn;
+  e.project_idepth(pos[2 * o], pos[2 * o + 1], x * a.scale, &cx, &cy, &idn);
+  pos[2 * o] = cx;
+  pos[2 * o + 1] = cy;
+  g.vprim[v].x = idn / a.scale;
+  out[2 * o] = cx;
+  out[2 * o + 1] = cy;
+  out[2 * (size_t)g.V + o] = idn;
+}
+
+int stereo_graph_project(void* state, cudaStream_t st, const GraphDev& g, float* d_pos,
+                         const float q[4], const float t[3], float scale, float* d_out) {
+  StereoState* s = static_cast<StereoState*>(state);
+  if (!s || s->width <= 0) {
+    set_error("graph_project: camera not set (flame_b200_set_camera)");
+    return FLAME_B200_ESTATE;
+  }
+  if (g.V == 0) return 0;
+  ProjectArgs a;
+  std::memcpy(a.K, s->K, sizeof(a.K));
+  std::memcpy(a.Kinv, s->Kinv, sizeof(a.Kinv));
+  std::memcpy(a.q, q, sizeof(a.q));
+  std::memcpy(a.t, t, sizeof(a.t));
+  a.scale = scale;
+  k_graph_project<<<(g.V + 127) / 128, 128, 0, st>>>(g, d_pos, a, d_out);
+  count_launch();
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 void stereo_destroy(void* state) {
   StereoState* s = static_cast<StereoState*>(state);
   if (!s) return;

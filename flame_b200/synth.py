@@ -115,6 +115,71 @@ def init_state(g, alpha, beta):
     return s
 
 
+def sync_topology(old_edges, keep, pos_kept, pos_new, delaunay=None):
+    """Index bookkeeping of Flame::syncGraph (flame.cc:1984-2123) for flame_b200_graph_resync.
+
+    old_edges [E0,2]; keep [V0] bool; pos_kept [sum(keep),2] new positions of the kept vertices (old
+    order); pos_new [Vn,2] brand-new vertices. Vertices: kept ones in their old order, then the new ones
+    (boost::add_vertex appends). Edges follow Boost's edge list: edges of the old graph that are still in
+    the new triangulation keep their relative order AND orientation (boost::edge() finds the existing
+    descriptor, :2092-2100), edges new to the triangulation are appended in triangulation order.
+    Returns pos, tris, edges, vtx_from, edge_from.
+    """
+    keep = np.asarray(keep, bool)
+    old_to_new = np.full(keep.shape[0], -1, np.int64)
+    old_to_new[keep] = np.arange(int(keep.sum()))
+    pos = np.ascontiguousarray(np.concatenate([pos_kept, pos_new], 0), np.float32)
+    vtx_from = np.concatenate([np.flatnonzero(keep), np.full(pos_new.shape[0], -1)]).astype(np.int32)
+    tris, tedges = (delaunay or _scipy_delaunay)(pos)
+    want = {}
+    for i, (a, b) in enumerate(tedges.tolist()):
+        want[(min(a, b), max(a, b))] = i
+    edges, edge_from, used = [], [], set()
+    for e, (a, b) in enumerate(np.asarray(old_edges).tolist()):
+        na, nb = old_to_new[a], old_to_new[b]
+        if na < 0 or nb < 0:
+            continue
+        k = (min(na, nb), max(na, nb))
+        if k in want:
+            edges.append((na, nb))
+            edge_from.append(e)
+            used.add(k)
+    for (a, b) in tedges.tolist():
+        if (min(a, b), max(a, b)) not in used:
+            edges.append((a, b))
+            edge_from.append(-1)
+    return (pos, tris, np.ascontiguousarray(np.array(edges, np.int32).reshape(-1, 2)),
+            np.ascontiguousarray(vtx_from), np.array(edge_from, np.int32))
+
+
+def sync_state_host(old, pos, edges, vtx_from, edge_from, data_term, data_weight=None, x_init=None,
+                    check_sticky_obstacles=False):
+    """The host-side edits graph_resync replaces: full PD state dict of the new graph from the old one
+    (carried vertices / edges keep their state; defaults of flame.cc:2046-2048 and EdgeData otherwise).
+    alpha / beta are left to the caller (1/len, 1)."""
+    V, E = pos.shape[0], edges.shape[0]
+    s = {"pos": pos, "edges": edges, "data_term": np.ascontiguousarray(data_term, np.float32),
+         "data_weight": np.ones(V, np.float32) if data_weight is None else data_weight}
+    cv, ce = vtx_from >= 0, edge_from >= 0
+    init = s["data_term"] if x_init is None else x_init
+    for k in ("x", "x_bar", "x_prev"):
+        a = init.astype(np.float32).copy()
+        a[cv] = old[k][vtx_from[cv]]
+        s[k] = a
+    for k in ("w1", "w2", "w1_bar", "w2_bar", "w1_prev", "w2_prev"):
+        a = np.zeros(V, np.float32)
+        a[cv] = old[k][vtx_from[cv]]
+        s[k] = a
+    for k in ("q1", "q2", "q3"):
+        a = np.zeros(E, np.float32)
+        a[ce] = old[k][edge_from[ce]]
+        s[k] = a
+    if check_sticky_obstacles:
+        reset = cv & ((s["x"] - s["data_term"]) > np.float32(0.25))
+        s["x"][reset] = s["data_term"][reset]
+    return s
+
+
 def config_graph(name, frame=0):
     W, H, V, iters = CONFIGS[name]
     g = make_graph(W, H, V, seed=1 + 100 * frame, noise_seed=2 + 100 * frame)

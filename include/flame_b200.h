@@ -129,6 +129,46 @@ int flame_b200_graph_reset(flame_b200_ctx* ctx, int slot0, int n_slots);
 /* Replaces the property reads at flame.cc:372-380. Synchronises the stream. */
 int flame_b200_graph_download(flame_b200_ctx* ctx, int slot, const flame_b200_graph_out* out);
 
+/* ---- keeping the solver state on the device from frame to frame ----------------
+ * Flame::update (flame.cc:296-318) moves the graph into every new frame with projectGraph and then
+ * edits it in syncGraph; with the two calls below the primal/dual state never leaves the GPU: only
+ * the projected positions come back (the caller decides removals and re-triangulates on the host)
+ * and only the new topology plus two index maps go up. */
+
+/* Replaces the per-vertex body of Flame::projectGraph (flame.cc:1892-1899): for every vertex
+ * (u_new, idepth_new) = EpipolarGeometry::project(pos, x * graph_scale) (epipolar_geometry.h:153-181)
+ * with the geometry loaded from T_ref_to_new = (q_wxyz, t) (flame.cc:297-298); the slot keeps
+ * pos = u_new and x = idepth_new / graph_scale (x_bar / x_prev untouched, as in the reference), and
+ * pos_out[2V] / idepth_out[V] (either nullable) receive u_new / idepth_new so the caller can apply the
+ * removal rules (:1901-1917). Needs flame_b200_set_camera. The edge records of the slot are stale
+ * afterwards: flame_b200_pd_run refuses the slot until flame_b200_graph_resync (or a new upload).
+ * Synchronises the stream. */
+int flame_b200_graph_project(flame_b200_ctx* ctx, int slot, const float q_wxyz[4], const float t[3],
+                             float graph_scale, float* pos_out, float* idepth_out);
+
+typedef struct {
+  int32_t V, E;
+  const float* pos;          /* 2V  new positions (feat.xy, flame.cc:2005 / :2041)                   */
+  const float* data_term;    /* V   feat.idepth_mu / graph_scale (:2006 / :2042)                     */
+  const float* data_weight;  /* V or NULL -> 1 (:2007 / :2043)                                       */
+  const int32_t* vtx_from;   /* V   index of the vertex in the slot's CURRENT graph, or -1 if new    */
+  const float* x_init;       /* V or NULL: x = x_bar = x_prev of NEW vertices (:2127-2162); NULL ->
+                                data_term (:2046-2048). Ignored for carried vertices.               */
+  const int32_t* edges;      /* 2E  (source, target) in boost::edges order; a carried edge must keep
+                                the orientation it had in the current graph (boost::edge() finds the
+                                existing descriptor, :2092-2100)                                    */
+  const int32_t* edge_from;  /* E   index of the edge in the current graph, or -1 if new (q = 0)     */
+  int32_t check_sticky_obstacles; /* params.check_sticky_obstacles: x = data_term where
+                                x - data_term > 0.25 on carried vertices (:2016-2019)               */
+} flame_b200_graph_sync;
+
+/* Replaces the graph edits of Flame::syncGraph (flame.cc:1984-2162) for a slot that already holds
+ * the previous graph: carried vertices keep x, w, x_bar, w_bar, x_prev, w_prev, carried edges keep q,
+ * everything new gets the reference's defaults, alpha = 1/||u_i - u_j|| and beta = 1 are recomputed
+ * for every edge (:2089-2104). Equivalent, bit for bit, to flame_b200_graph_download + the same edits
+ * on the host + flame_b200_graph_upload. Asynchronous. */
+int flame_b200_graph_resync(flame_b200_ctx* ctx, int slot, const flame_b200_graph_sync* sync);
+
 enum {
   FLAME_B200_PD_AUTO = 0,     /* resident if the graph fits one cluster's shared memory */
   FLAME_B200_PD_STREAM = 1,   /* state in HBM/L2, two kernels per iteration, any size    */

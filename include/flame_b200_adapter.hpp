@@ -131,6 +131,82 @@ class DeviceGraph {
     check(flame_b200_graph_upload(s_->get(), slot_, &in), "flame_b200_graph_upload");
   }
 
+  // Flame::projectGraph's vertex loop (flame.cc:1892-1899) on the device, for the graph last passed to
+  // upload()/resync(): pos and x of every vertex are also written back into the Boost graph so that the
+  // removal rules (:1901-1917) and syncGraph run on the host as before. (q_wxyz, t) = T_prev_to_new
+  // (flame.cc:297-298). Needs flame_b200_set_camera on the session.
+  void project(const float q_wxyz[4], const float t[3], float graph_scale, Graph* g) {
+    std::vector<float> pos(static_cast<size_t>(2) * V_ + 2), idepth(static_cast<size_t>(V_) + 1);
+    check(flame_b200_graph_project(s_->get(), slot_, q_wxyz, t, graph_scale, pos.data(), idepth.data()),
+          "flame_b200_graph_project");
+    for (int32_t v = 0; v < V_; ++v) {
+      auto& d = (*g)[vh_[v]];
+      d.pos.x = pos[2 * v];
+      d.pos.y = pos[2 * v + 1];
+      d.x = idepth[v] / graph_scale;
+    }
+  }
+
+  // After Flame::syncGraph edited the Boost graph (vertices removed / added, edges re-triangulated,
+  // flame.cc:1984-2162): rebuild the device graph from it and carry the solver state of the surviving
+  // vertices and edges over ON THE DEVICE (no download / upload of x, w, q). `is_new(vertex)` must say
+  // whether the vertex was added by this syncGraph call (:2030-2049) - handle identity alone cannot,
+  // a list node address may be reused. A surviving edge is recognised by its (source, target) pair,
+  // which Boost keeps stable for an undirected edge that was not removed. New vertices take x = x_bar =
+  // x_prev from their VertexData::x (what :2160-2162 stored).
+  template <class IsNew>
+  void resync(const Graph& g, IsNew is_new, bool check_sticky_obstacles = false) {
+    std::unordered_map<typename std::decay<VH>::type, int32_t> old_index;
+    old_index.swap(index_);
+    std::unordered_map<uint64_t, int32_t> old_edge;
+    for (int32_t e = 0; e < E_; ++e)
+      old_edge[(static_cast<uint64_t>(static_cast<uint32_t>(ebuf_[2 * e])) << 32) |
+               static_cast<uint32_t>(ebuf_[2 * e + 1])] = e;
+    vh_.clear();
+    eh_.clear();
+    std::vector<int32_t> vtx_from, edge_from;
+    auto vr = vertices(g);
+    for (auto it = vr.first; it != vr.second; ++it) {
+      index_[*it] = static_cast<int32_t>(vh_.size());
+      vh_.push_back(*it);
+      auto f = old_index.find(*it);
+      vtx_from.push_back((f == old_index.end() || is_new(*it)) ? -1 : f->second);
+    }
+    auto er = edges(g);
+    for (auto it = er.first; it != er.second; ++it) eh_.push_back(*it);
+    V_ = static_cast<int32_t>(vh_.size());
+    E_ = static_cast<int32_t>(eh_.size());
+    buf_.assign(static_cast<size_t>(13) * V_ + static_cast<size_t>(5) * E_, 0.0f);
+    ebuf_.assign(static_cast<size_t>(2) * E_, 0);
+    float* pos = buf_.data();
+    float* data = pos + 2 * static_cast<size_t>(V_);
+    float* wt = data + V_;
+    float* xi = wt + V_;
+    for (int32_t v = 0; v < V_; ++v) {
+      const auto& d = g[vh_[v]];
+      pos[2 * v] = d.pos.x; pos[2 * v + 1] = d.pos.y;
+      data[v] = d.data_term; wt[v] = d.data_weight; xi[v] = d.x;
+    }
+    edge_from.assign(E_, -1);
+    for (int32_t e = 0; e < E_; ++e) {
+      const int32_t a = index_[source(eh_[e], g)], b = index_[target(eh_[e], g)];
+      ebuf_[2 * e] = a;
+      ebuf_[2 * e + 1] = b;
+      if (vtx_from[a] >= 0 && vtx_from[b] >= 0) {
+        auto f = old_edge.find((static_cast<uint64_t>(static_cast<uint32_t>(vtx_from[a])) << 32) |
+                               static_cast<uint32_t>(vtx_from[b]));
+        if (f != old_edge.end()) edge_from[e] = f->second;
+      }
+    }
+    flame_b200_graph_sync y;
+    y.V = V_; y.E = E_;
+    y.pos = pos; y.data_term = data; y.data_weight = wt;
+    y.vtx_from = vtx_from.data(); y.x_init = xi;
+    y.edges = ebuf_.data(); y.edge_from = edge_from.data();
+    y.check_sticky_obstacles = check_sticky_obstacles ? 1 : 0;
+    check(flame_b200_graph_resync(s_->get(), slot_, &y), "flame_b200_graph_resync");
+  }
+
   void step(const Params& params, int n_iters = 1, int mode = FLAME_B200_PD_AUTO) {
     const flame_b200_pd_params p = params.c();
     check(flame_b200_pd_run(s_->get(), slot_, 1, &p, n_iters, mode), "flame_b200_pd_run");

@@ -1,8 +1,9 @@
 // Minimal stand-in for boost::adjacency_list<hash_setS, hash_setS, undirectedS, VP, EP> with the
 // free functions the reference's regulariser uses (vertices, edges, source, target, add_vertex,
-// add_edge, tie, operator[]). Edge iteration walks the global edge list in insertion order, as
-// Boost's undirected adjacency_list does (its m_edges is a std::list appended by add_edge; SURVEY
-// N3). Vertex iteration is insertion order (Boost's hash_setS order is address dependent and does
+// add_edge, tie, operator[]) plus the edit calls Flame::syncGraph makes (edge, remove_edge,
+// clear_vertex, remove_vertex), which tests/cpp uses to replay a graph sync. Edge iteration walks
+// the global edge list in insertion order, as Boost's undirected adjacency_list does (its m_edges
+// is a std::list appended by add_edge). Vertex iteration is insertion order (Boost's hash_setS order is address dependent and does
 // not affect per-vertex arithmetic). Test infrastructure only (oracle/_ref).
 #pragma once
 #include <cstddef>
@@ -81,6 +82,28 @@ std::pair<typename FB_AL::edge_descriptor, bool> add_edge(typename FB_AL::vertex
                                                           const EP& p, FB_AL& g) {
   typename FB_AL::ENode n; n.s = s; n.t = t; n.prop = p; g.elist.push_back(n);
   return std::make_pair(&g.elist.back(), true);
+}
+template <typename O, typename V, typename D, typename VP, typename EP>
+std::pair<typename FB_AL::edge_descriptor, bool> edge(typename FB_AL::vertex_descriptor s,
+                                                      typename FB_AL::vertex_descriptor t, const FB_AL& g) {
+  for (auto it = g.elist.begin(); it != g.elist.end(); ++it)
+    if ((it->s == s && it->t == t) || (it->s == t && it->t == s)) return std::make_pair(&*it, true);
+  return std::make_pair(static_cast<typename FB_AL::edge_descriptor>(nullptr), false);
+}
+template <typename O, typename V, typename D, typename VP, typename EP>
+void remove_edge(typename FB_AL::edge_descriptor e, FB_AL& g) {
+  for (auto it = g.elist.begin(); it != g.elist.end(); ++it)
+    if (&*it == e) { g.elist.erase(it); return; }
+}
+template <typename O, typename V, typename D, typename VP, typename EP>
+void clear_vertex(typename FB_AL::vertex_descriptor v, FB_AL& g) {
+  for (auto it = g.elist.begin(); it != g.elist.end();)
+    if (it->s == v || it->t == v) it = g.elist.erase(it); else ++it;
+}
+template <typename O, typename V, typename D, typename VP, typename EP>
+void remove_vertex(typename FB_AL::vertex_descriptor v, FB_AL& g) {
+  for (auto it = g.vlist.begin(); it != g.vlist.end(); ++it)
+    if (&*it == v) { g.vlist.erase(it); return; }
 }
 template <typename O, typename V, typename D, typename VP, typename EP>
 std::size_t num_vertices(const FB_AL& g) { return g.vlist.size(); }
