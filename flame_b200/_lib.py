@@ -88,6 +88,7 @@ _lib = None
 SYMBOLS = [
     "flame_b200_last_error", "flame_b200_version", "flame_b200_kernel_launches",
     "flame_b200_ctx_create", "flame_b200_ctx_destroy", "flame_b200_ctx_sync", "flame_b200_ctx_stream",
+    "flame_b200_ctx_set_async_projection", "flame_b200_ctx_join",
     "flame_b200_host_alloc", "flame_b200_host_free",
     "flame_b200_pd_default_params", "flame_b200_graph_upload", "flame_b200_graph_init",
     "flame_b200_graph_set_data", "flame_b200_graph_reset", "flame_b200_graph_download",
@@ -115,6 +116,8 @@ def lib():
     L.flame_b200_ctx_destroy.argtypes = [vp]
     L.flame_b200_ctx_destroy.restype = None
     L.flame_b200_ctx_sync.argtypes = [vp]
+    L.flame_b200_ctx_set_async_projection.argtypes = [vp, C.c_int]
+    L.flame_b200_ctx_join.argtypes = [vp]
     L.flame_b200_ctx_stream.argtypes = [vp]
     L.flame_b200_ctx_stream.restype = vp
     L.flame_b200_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -244,6 +247,13 @@ class Context:
     @property
     def stream(self):
         return lib().flame_b200_ctx_stream(self._h)
+
+    def set_async_projection(self, on=True):
+        check(lib().flame_b200_ctx_set_async_projection(self._h, int(on)))
+
+    def join(self):
+        """Device-side: order the pending (asynchronous) projection before later work on `stream`."""
+        check(lib().flame_b200_ctx_join(self._h))
 
     def sync(self):
         check(lib().flame_b200_ctx_sync(self._h))

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -52,8 +53,7 @@ struct Slot {
   MeshDev m{};
   int capT = 0;
   size_t cap_pix = 0;
-  int cap_tiles = 0;
-  size_t cap_pairs = 0;
+  size_t bound_pix = 0;             // rows*cols of the last bind (owner words are per linear pixel)
   int* d_tris = nullptr;            // owning pointers behind the const views in `m`
   unsigned char* d_tri_ok = nullptr;
   float* d_mpos = nullptr;          // interpolate_mesh(): caller-supplied pos / values
@@ -76,6 +76,12 @@ struct flame_b200_ctx {
   double* d_cost = nullptr;
   double* h_cost = nullptr;          // pinned, 2 doubles
   void* stereo = nullptr;
+  // asynchronous dense projection (flame_b200_ctx_set_async_projection): the projection kernels run on
+  // `side` so that the next frames' solver launches on `stream` overlap them
+  bool async_proj = false;
+  bool side_busy = false;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_vals = nullptr, ev_side = nullptr;
   // host scratch for graph prep
   std::vector<uint32_t> keys, keys2;
   std::vector<int> idx, idx2, vinv, cursor, degv, srcdeg, order, koff_tmp;
@@ -367,6 +373,25 @@ static int publish_graph(flame_b200_ctx* c, int slot) {
   return 0;
 }
 
+// Orders everything issued so far on the projection stream before whatever is issued next on the
+// main stream (device-side wait, the host does not block).
+static int join_side(flame_b200_ctx* c) {
+  if (c->side_busy) {
+    FB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_side, 0));
+    c->side_busy = false;
+  }
+  return 0;
+}
+
+static int raster_sub_batch() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("FLAME_B200_RASTER_SUB");
+    v = e ? std::max(0, std::atoi(e)) : 0;
+  }
+  return v;
+}
+
 }  // namespace fb
 
 using namespace fb;
@@ -462,13 +487,17 @@ int flame_b200_ctx_create(int device, int n_slots, flame_b200_ctx** out) {
 void flame_b200_ctx_destroy(flame_b200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->side) cudaStreamSynchronize(c->side);
   cudaStreamSynchronize(c->stream);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ev_vals) cudaEventDestroy(c->ev_vals);
+  if (c->ev_side) cudaEventDestroy(c->ev_side);
   for (auto& s : c->slots) {
     for (void* p : {(void*)s.g.vprim, (void*)s.g.vbar, (void*)s.g.vbar2, (void*)s.g.vprev,
                     (void*)s.g.vwt, (void*)s.g.inc_q, (void*)s.g.inc_s, (void*)s.d_blob,
                     (void*)s.d_pos, (void*)s.d_values,
                     (void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.m.img, (void*)s.m.setup,
-                    (void*)s.m.tile_count, (void*)s.m.tile_off, (void*)s.m.pairs, (void*)s.m.large,
+                    (void*)s.m.owner,
                     (void*)s.m.big, (void*)s.m.counters, (void*)s.d_mpos, (void*)s.d_mvalues,
                     (void*)s.d_carry})
       if (p) cudaFree(p);
@@ -489,8 +518,28 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
 int flame_b200_ctx_sync(flame_b200_ctx* c) {
   if (!c) return FLAME_B200_EINVAL;
   if (int rc = use_device(c)) return rc;
+  if (int rc = join_side(c)) return rc;
   FB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+int flame_b200_ctx_set_async_projection(flame_b200_ctx* c, int on) {
+  if (!c) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  if (int rc = join_side(c)) return rc;
+  if (on && !c->side) {
+    FB_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    FB_CUDA(cudaEventCreateWithFlags(&c->ev_vals, cudaEventDisableTiming));
+    FB_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+  }
+  c->async_proj = on != 0;
+  return 0;
+}
+
+int flame_b200_ctx_join(flame_b200_ctx* c) {
+  if (!c) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  return join_side(c);
 }
 
 void* flame_b200_ctx_stream(flame_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
@@ -527,6 +576,7 @@ static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph
     return FLAME_B200_EINVAL;
   }
   if (int rc = use_device(c)) return rc;
+  if (int rc = join_side(c)) return rc;
   Slot& s = c->slots[slot];
   const int V = g->V, E = g->E;
   PrepOut prep;
@@ -669,6 +719,7 @@ int flame_b200_graph_project(flame_b200_ctx* c, int slot, const float q_wxyz[4],
     return FLAME_B200_EINVAL;
   }
   if (int rc = use_device(c)) return rc;
+  if (int rc = join_side(c)) return rc;
   Slot& s = c->slots[slot];
   if (!s.loaded) {
     set_error("graph_project: slot has no graph");
@@ -877,44 +928,41 @@ static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* 
       set_error("mesh: triangle vertex index out of range");
       return FLAME_B200_EINVAL;
     }
+  if (T > FB_MAX_TRIANGLES) {
+    set_error("mesh: more than 2^20 - 1 triangles");
+    return FLAME_B200_EINVAL;
+  }
   if (T > s.capT) {
     const int n = std::max(T, s.capT + s.capT / 2);
-    for (void* p : {(void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.m.setup, (void*)s.m.large, (void*)s.m.big})
+    for (void* p : {(void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.m.setup, (void*)s.m.big})
       if (p) FB_CUDA(cudaFree(p));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_tris), (size_t)n * 3 * sizeof(int)));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_tri_ok), (size_t)n));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.setup), (size_t)n * sizeof(TriSetup)));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.large), (size_t)n * sizeof(int)));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.big), (size_t)n * sizeof(int)));
     s.capT = n;
-    s.cap_pairs = 0;  // pair buffer depends on capT: re-sized below
   }
   const size_t npix = (size_t)rows * cols;
+  if (npix >= ((size_t)1 << 31)) {
+    set_error("mesh: image too large");
+    return FLAME_B200_EINVAL;
+  }
   if (npix > s.cap_pix) {
     if (s.m.img) FB_CUDA(cudaFree(s.m.img));
+    if (s.m.owner) FB_CUDA(cudaFree(s.m.owner));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.img), npix * sizeof(float)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.owner), npix * sizeof(unsigned int)));
     s.cap_pix = npix;
+    s.bound_pix = 0;
   }
-  const int n_tiles = raster_tile_count(rows, cols);
-  if (n_tiles > s.cap_tiles) {
-    if (s.m.tile_count) FB_CUDA(cudaFree(s.m.tile_count));
-    if (s.m.tile_off) FB_CUDA(cudaFree(s.m.tile_off));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.tile_count), (size_t)n_tiles * sizeof(int)));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.tile_off), (size_t)(n_tiles + 1) * sizeof(int)));
-    s.cap_tiles = n_tiles;
-    FB_CUDA(cudaMemsetAsync(s.m.tile_count, 0, (size_t)n_tiles * sizeof(int), c->stream));
-  }
-  if (!s.m.counters) {
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.counters), 8 * sizeof(int)));
+  if (!s.m.counters) FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.counters), 8 * sizeof(int)));
+  if (npix != s.bound_pix) {
+    // owner words are indexed by linear pixel and tagged with the projection epoch: a different image
+    // size restarts both (stream-ordered, so earlier projections are unaffected)
+    FB_CUDA(cudaMemsetAsync(s.m.owner, 0, s.cap_pix * sizeof(unsigned int), c->stream));
     FB_CUDA(cudaMemsetAsync(s.m.counters, 0, 8 * sizeof(int), c->stream));
+    s.bound_pix = npix;
   }
-  const size_t need_pairs = (size_t)s.capT * FB_SMALL_TILES_PER_TRI + (size_t)s.cap_tiles * FB_BIG_BUDGET_PER_TILE;
-  if (need_pairs > s.cap_pairs) {
-    if (s.m.pairs) FB_CUDA(cudaFree(s.m.pairs));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.pairs), need_pairs * sizeof(int)));
-    s.cap_pairs = need_pairs;
-  }
-  s.m.n_tiles = n_tiles;
   s.m.tris = s.d_tris;
   s.m.tri_ok = s.d_tri_ok;
   s.m.T = T;
@@ -951,6 +999,7 @@ int flame_b200_mesh_bind(flame_b200_ctx* c, int slot, int32_t T, const int32_t* 
                          const uint8_t* vtx_valid, const uint8_t* tri_valid, int rows, int cols) {
   if (int rc = check_slot(c, slot)) return rc;
   if (int rc = use_device(c)) return rc;
+  if (int rc = join_side(c)) return rc;
   Slot& s = c->slots[slot];
   if (!s.loaded) {
     set_error("mesh_bind: slot has no graph");
@@ -965,7 +1014,7 @@ int flame_b200_mesh_bind(flame_b200_ctx* c, int slot, int32_t T, const int32_t* 
 int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float scale) {
   if (int rc = check_slot(c, slot0, n_slots)) return rc;
   if (int rc = use_device(c)) return rc;
-  int maxV = 0, maxT = 0, max_tiles = 0;
+  int maxV = 0, maxT = 0, max_pix = 0;
   for (int i = slot0; i < slot0 + n_slots; ++i) {
     Slot& s = c->slots[i];
     if (!s.loaded || !s.m.img || s.m.values != s.d_values || s.m.pos != s.d_pos) {
@@ -974,18 +1023,35 @@ int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float sca
     }
     maxV = std::max(maxV, s.g.V);
     maxT = std::max(maxT, s.m.T);
-    max_tiles = std::max(max_tiles, raster_cta_count(s.m.rows, s.m.cols));
+    max_pix = std::max(max_pix, s.m.rows * s.m.cols);
   }
+  // values_from_graph overwrites what the previous projection's setup kernel reads
+  if (int rc = join_side(c)) return rc;
   if (int rc = raster_values_from_graph(c->stream, c->d_graphs + slot0, c->d_meshes + slot0, n_slots,
                                         maxV, scale))
     return rc;
-  return raster_project(c->stream, c->d_meshes + slot0, n_slots, maxT, max_tiles, 1);
+  cudaStream_t rs = c->stream;
+  if (c->async_proj) {
+    FB_CUDA(cudaEventRecord(c->ev_vals, c->stream));
+    FB_CUDA(cudaStreamWaitEvent(c->side, c->ev_vals, 0));
+    rs = c->side;
+  }
+  const int sub = raster_sub_batch() > 0 ? raster_sub_batch() : n_slots;
+  for (int i = 0; i < n_slots; i += sub)
+    if (int rc = raster_project(rs, c->d_meshes + slot0 + i, std::min(sub, n_slots - i), maxT, max_pix, 1))
+      return rc;
+  if (c->async_proj) {
+    FB_CUDA(cudaEventRecord(c->ev_side, c->side));
+    c->side_busy = true;
+  }
+  return 0;
 }
 
 int flame_b200_mesh_download(flame_b200_ctx* c, int slot, float* out_host) {
   if (int rc = check_slot(c, slot)) return rc;
   if (!out_host) return FLAME_B200_EINVAL;
   if (int rc = use_device(c)) return rc;
+  if (int rc = join_side(c)) return rc;
   Slot& s = c->slots[slot];
   if (!s.m.img) {
     set_error("mesh_download: no dense map in this slot");
@@ -1006,6 +1072,7 @@ int flame_b200_interpolate_mesh(flame_b200_ctx* c, int slot, int32_t T, const in
     return FLAME_B200_EINVAL;
   }
   if (int rc = use_device(c)) return rc;
+  if (int rc = join_side(c)) return rc;
   Slot& s = c->slots[slot];
   if (!values && (!s.loaded || s.g.V != V)) {
     set_error("interpolate_mesh: values == NULL needs a graph with V vertices in the slot");
@@ -1035,7 +1102,7 @@ int flame_b200_interpolate_mesh(flame_b200_ctx* c, int slot, int32_t T, const in
   const size_t npix = (size_t)rows * cols;
   if (!fill_nan)
     FB_CUDA(cudaMemcpyAsync(s.m.img, out_host, npix * 4, cudaMemcpyHostToDevice, c->stream));
-  if (int rc = raster_project(c->stream, c->d_meshes + slot, 1, s.m.T, raster_cta_count(rows, cols), fill_nan)) return rc;
+  if (int rc = raster_project(c->stream, c->d_meshes + slot, 1, s.m.T, rows * cols, fill_nan)) return rc;
   FB_CUDA(cudaMemcpyAsync(out_host, s.m.img, npix * 4, cudaMemcpyDeviceToHost, c->stream));
   FB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;

@@ -56,24 +56,21 @@ struct __align__(16) TriSetup {  // per triangle, written by k_tri_setup; 80 byt
   float B2, C2, A3, B3;
   float C3, v1, v2, v3;          // values at p1, p2, p3 (reversed triangle order)
   int fx1;                       // last footprint column, clamped to the image
-  int flags;                     // 1 large list, 2 sweep wraps past the border, 4 degenerate, 8 big bbox, 16 big & binned
+  int flags;                     // 2 sweep wraps past the right border, 4 degenerate, 8 large footprint
   int pad0, pad1;
 };
 
 struct MeshDev {
-  int T, rows, cols, n_tiles;
+  int T, rows, cols, pad;
   const int* tris;             // 3T caller vertex indices
   const unsigned char* tri_ok; // T: tri_valid && all three vtx_valid (nullable)
   const float* pos;            // 2V caller order
   float* values;               // V caller order
   float* img;                  // rows*cols
   TriSetup* setup;             // T
-  int* tile_count;             // n_tiles (zero between projections)
-  int* tile_off;               // n_tiles + 1
-  int* pairs;                  // FB_SMALL_TILES_PER_TRI * T + FB_BIG_BUDGET_PER_TILE * n_tiles
-  int* large;                  // T: triangles every tile tests
-  int* big;                    // T: big-bounding-box triangles binned by a warp
-  int* counters;               // [0] n_large accumulating [1] current [2] n_big accumulating [3] current [4] big pair budget used
+  unsigned int* owner;         // rows*cols: (epoch << 20) | highest covering triangle of that epoch
+  int* big;                    // T: triangles with a large sweep footprint (one CTA each)
+  int* counters;               // [0] big-list length (re-armed by k_resolve) [1] projection epoch
 };
 
 // ---- PD (pd.cu) ----
@@ -117,13 +114,10 @@ inline size_t raw_f_offset(int field, int V, int E) {
 inline size_t raw_f_total(int V, int E) { return (size_t)13 * V + (size_t)5 * E; }
 
 // ---- dense projection (raster.cu) ----
-int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_ctas, int fill_nan);
+int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_pix, int fill_nan);
 // values[vperm[v]] = vprim[v].x * scale  (vtx_idepths_ = x * graph_scale_, flame.cc:376)
 int raster_values_from_graph(cudaStream_t st, const GraphDev* gs_dev, const MeshDev* ms_dev, int n,
                              int maxV, float scale);
-int raster_tile_count(int rows, int cols);
-int raster_cta_count(int rows, int cols);
-#define FB_SMALL_TILES_PER_TRI 32
-#define FB_BIG_BUDGET_PER_TILE 8
+#define FB_MAX_TRIANGLES ((1 << 20) - 1)  // triangle id field of the owner word
 
 }  // namespace fb

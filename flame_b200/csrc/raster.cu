@@ -16,30 +16,26 @@
 // Edge functions are integer-valued and exact in fp32 for images up to ~2896 px on a side
 // (|A*x + B*y + C| < 2^24), so direct evaluation equals the reference's incremental stepping.
 //
-// Formulation: the reference scatters triangles in order with read-modify-write; here every PIXEL
-// gathers "the highest-index triangle that covers me" from a per-tile bin and is written exactly
-// once (4*W*H bytes of image traffic instead of fill + per-triangle RMW):
-//   k_tri_setup   one thread per triangle: rounding, edge coefficients, footprint -> tile counts
-//   k_tile_scan   one CTA: exclusive scan of the tile counts
-//   k_tri_fill    one thread per triangle: (tile, triangle) pairs
-//   k_tile_raster one CTA per 32x8 pixel block = four 8x8 tiles, two warps per tile: pixels walk
-//                 their tile's bin (+ the short "large" list); bins hold only triangles whose
-//                 edge functions do not exclude the whole tile (exact integer box test)
-// Triangles with a big bounding box (hull slivers: few tiles actually overlapped) are binned by a
-// whole warp (k_big_count / k_big_fill) against a global pair budget; only what exceeds the budget,
-// or wraps past the right image border (degenerate), goes to the "large" list that every tile
-// scans. Pair buffer: SMALL_TILES * T + BIG_BUDGET_PER_TILE * n_tiles entries.
+// Formulation: the reference scatters triangles in order with read-modify-write, so the LAST
+// (highest-index) covering triangle wins. Here coverage and shading are split:
+//   k_tri_setup    one thread per triangle: rounding, edge coefficients, sweep footprint
+//   k_owner_small  one warp per triangle (16 x 2 pixel steps over its footprint): exact integer
+//                  coverage test, atomicMax((epoch << 20) | triangle) into a per-pixel owner word
+//   k_owner_big    one CTA per large-footprint triangle (hull slivers, texture-poor regions): rows
+//                  over warps, each row clipped to a conservative span from the three edge functions
+//   k_resolve      four pixels per thread: read the owner, shade that one triangle, write the pixel once
+// The owner word carries the projection's epoch, so the buffer never needs clearing between
+// projections (stale words lose every atomicMax and are ignored by k_resolve); when the 12-bit epoch
+// is about to wrap k_resolve zeroes the words it reads. Triangle ids use 20 bits (T < 2^20).
 #include <algorithm>
 
 #include "internal.h"
 
 namespace fb {
 
-#define TILE_W 8
-#define TILE_H 8
-#define CTA_TILES 4   // a CTA rasterises CTA_TILES horizontally adjacent tiles (32 x 8 pixels)
-#define SMALL_TILES FB_SMALL_TILES_PER_TRI
-#define BIG_BUDGET_PER_TILE FB_BIG_BUDGET_PER_TILE
+#define OWNER_T_BITS 20
+#define EPOCH_MAX 4095u
+#define BIG_AREA 1024   // sweep-footprint pixels above which a triangle goes to k_owner_big
 
 __device__ __forceinline__ int min3(int a, int b, int c) { return min(a, min(b, c)); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return max(a, max(b, c)); }
@@ -62,19 +58,13 @@ __device__ __forceinline__ bool tri_eval(const TriSetup& s, int x, int y, float*
   return true;
 }
 
-// Conservative-exact test "does the closed triangle (all three w >= 0) miss the pixel box
-// [x0,x1] x [y0,y1] entirely?": an edge function that is negative at its most favourable corner is
-// negative on the whole box. Integer-valued floats: exact.
-__device__ __forceinline__ bool tile_outside(const TriSetup& s, int x0, int y0, int x1, int y1) {
-  const float m1 = edge_at(s.A1, s.B1, s.C1, s.A1 >= 0.0f ? x1 : x0, s.B1 >= 0.0f ? y1 : y0);
-  const float m2 = edge_at(s.A2, s.B2, s.C2, s.A2 >= 0.0f ? x1 : x0, s.B2 >= 0.0f ? y1 : y0);
-  const float m3 = edge_at(s.A3, s.B3, s.C3, s.A3 >= 0.0f ? x1 : x0, s.B3 >= 0.0f ? y1 : y0);
-  return (m1 < 0.0f) || (m2 < 0.0f) || (m3 < 0.0f);
-}
-
 __global__ void __launch_bounds__(256) k_tri_setup(const MeshDev* __restrict__ ms) {
   const MeshDev m = ms[blockIdx.y];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) {  // open a new epoch for this projection (read by the later kernels only)
+    const unsigned e = (unsigned)m.counters[1];
+    m.counters[1] = (int)(e >= EPOCH_MAX ? 1u : e + 1u);
+  }
   if (t >= m.T) return;
   TriSetup s;
   s.flags = 0;
@@ -82,6 +72,7 @@ __global__ void __launch_bounds__(256) k_tri_setup(const MeshDev* __restrict__ m
   s.pad0 = s.pad1 = 0;
   if (m.tri_ok && !m.tri_ok[t]) {
     s.ymin = 1; s.ymax = 0; s.xmin = 0; s.xend = 0;  // empty footprint
+    s.A1 = s.B1 = s.C1 = s.A2 = s.B2 = s.C2 = s.A3 = s.B3 = s.C3 = s.v1 = s.v2 = s.v3 = 0.0f;
     m.setup[t] = s;
     return;
   }
@@ -101,263 +92,149 @@ __global__ void __launch_bounds__(256) k_tri_setup(const MeshDev* __restrict__ m
   s.A3 = (float)(p2y - p1y); s.B3 = (float)(p1x - p2x); s.C3 = (float)(p2x * p1y - p1x * p2y);
   const long long area2 = (long long)(p2x - p1x) * (p3y - p1y) - (long long)(p2y - p1y) * (p3x - p1x);
   const bool degenerate = (area2 == 0);
-  // footprint in pixels: a non-degenerate triangle covers nothing outside [xmin, xmax]
+  // footprint in pixels: a non-degenerate triangle covers nothing outside [xmin, xmax]; a degenerate
+  // one (edge functions vanish on a line) also covers the sweep's overshoot columns up to xend - 1
   const int fx0 = max(s.xmin, 0), fy0 = max(s.ymin, 0);
   const int fx1 = min(degenerate ? s.xend - 1 : xmax, m.cols - 1), fy1 = min(s.ymax, m.rows - 1);
   const bool wraps = degenerate && (s.xend > m.cols);
   s.fx1 = fx1;
-  const int tx0 = fx0 / TILE_W, tx1 = fx1 / TILE_W, ty0 = fy0 / TILE_H, ty1 = fy1 / TILE_H;
-  const long long ntiles = (fx1 >= fx0 && fy1 >= fy0) ? (long long)(tx1 - tx0 + 1) * (ty1 - ty0 + 1) : 0;
   if (degenerate) s.flags |= 4;
-  if (wraps) {
-    s.flags |= 1 | 2;
-    m.large[atomicAdd(&m.counters[0], 1)] = t;
-  } else if (ntiles > SMALL_TILES) {
-    s.flags |= 8;  // big bounding box: binned by a warp in k_big_count / k_big_fill
-    m.big[atomicAdd(&m.counters[2], 1)] = t;
-  } else {
-    const int tiles_x = (m.cols + TILE_W - 1) / TILE_W;
-    for (int ty = ty0; ty <= ty1 && ntiles > 0; ++ty)
-      for (int tx = tx0; tx <= tx1; ++tx) {
-        if (!degenerate && tile_outside(s, tx * TILE_W, ty * TILE_H, tx * TILE_W + TILE_W - 1,
-                                        ty * TILE_H + TILE_H - 1))
-          continue;
-        atomicAdd(&m.tile_count[ty * tiles_x + tx], 1);
-      }
+  if (wraps) s.flags |= 2;
+  const long long w = (wraps ? s.xend - 1 : fx1) - fx0 + 1, h = fy1 - fy0 + 1;
+  if (w > 0 && h > 0 && w * h > BIG_AREA) {
+    s.flags |= 8;
+    m.big[atomicAdd(&m.counters[0], 1)] = t;
   }
   m.setup[t] = s;
 }
 
-// One warp per big-bounding-box triangle: exact count of overlapped tiles, then either bin it
-// (flags |= 16) within the global pair budget or hand it to the large list (flags |= 1).
-__global__ void __launch_bounds__(256) k_big_count(const MeshDev* __restrict__ ms) {
+// coverage at sweep position (x, y) -> owner word of the pixel the reference's linear addressing
+// (p.y * cols + p.x) lands on
+__device__ __forceinline__ void claim(const MeshDev& m, int x, int y, unsigned key) {
+  if (x >= m.cols) {  // degenerate triangle whose 4-px sweep ran past the right border
+    x -= m.cols;
+    y += 1;
+    if (y >= m.rows) return;
+  }
+  atomicMax(&m.owner[(size_t)y * m.cols + x], key);
+}
+
+__global__ void __launch_bounds__(256) k_owner_small(const MeshDev* __restrict__ ms) {
   const MeshDev m = ms[blockIdx.y];
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (t >= m.T) return;
   const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int n_big = m.counters[2];
-  const int tiles_x = (m.cols + TILE_W - 1) / TILE_W;
-  const int budget = BIG_BUDGET_PER_TILE * m.n_tiles;
-  for (int b = warp; b < n_big; b += nwarps) {
-    const int t = m.big[b];
-    TriSetup s = m.setup[t];
-    const int fx0 = max(s.xmin, 0), fy0 = max(s.ymin, 0), fx1 = s.fx1, fy1 = min(s.ymax, m.rows - 1);
-    const int tx0 = fx0 / TILE_W, ty0 = fy0 / TILE_H;
-    const int nx = fx1 / TILE_W - tx0 + 1, ny = fy1 / TILE_H - ty0 + 1;
-    const bool exact = !(s.flags & 4);
-    int cnt = 0;
-    for (int i = lane; i < nx * ny; i += 32) {
-      const int tx = tx0 + i % nx, ty = ty0 + i / nx;
-      cnt += !(exact && tile_outside(s, tx * TILE_W, ty * TILE_H, tx * TILE_W + TILE_W - 1,
-                                     ty * TILE_H + TILE_H - 1));
+  const TriSetup s = m.setup[t];
+  if ((s.flags & 8) || s.ymin > s.ymax) return;
+  const unsigned key = ((unsigned)m.counters[1] << OWNER_T_BITS) | (unsigned)t;
+  const int fx0 = max(s.xmin, 0), fy0 = max(s.ymin, 0), fy1 = min(s.ymax, m.rows - 1);
+  const int fx1 = (s.flags & 2) ? s.xend - 1 : s.fx1;
+  for (int y = fy0 + (lane >> 4); y <= fy1; y += 2) {
+    const float fy = (float)y;
+    const float b1 = __fmul_rn(s.B1, fy), b2 = __fmul_rn(s.B2, fy), b3 = __fmul_rn(s.B3, fy);
+    for (int x = fx0 + (lane & 15); x <= fx1; x += 16) {
+      const float fx = (float)x;
+      const float w1 = __fadd_rn(__fadd_rn(__fmul_rn(s.A1, fx), b1), s.C1);
+      const float w2 = __fadd_rn(__fadd_rn(__fmul_rn(s.A2, fx), b2), s.C2);
+      const float w3 = __fadd_rn(__fadd_rn(__fmul_rn(s.A3, fx), b3), s.C3);
+      if (w1 >= 0.0f && w2 >= 0.0f && w3 >= 0.0f) claim(m, x, y, key);
     }
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    int ok = 0;
-    if (lane == 0) {
-      const int old = atomicAdd(&m.counters[4], cnt);
-      ok = (old + cnt <= budget);
-      if (!ok) {
-        atomicSub(&m.counters[4], cnt);
-        m.large[atomicAdd(&m.counters[0], 1)] = t;
-      }
-      m.setup[t].flags = s.flags | (ok ? 16 : 1);
-    }
-    ok = __shfl_sync(0xffffffffu, ok, 0);
-    if (ok)
-      for (int i = lane; i < nx * ny; i += 32) {
-        const int tx = tx0 + i % nx, ty = ty0 + i / nx;
-        if (!(exact && tile_outside(s, tx * TILE_W, ty * TILE_H, tx * TILE_W + TILE_W - 1,
-                                    ty * TILE_H + TILE_H - 1)))
-          atomicAdd(&m.tile_count[ty * tiles_x + tx], 1);
-      }
   }
 }
 
-__global__ void __launch_bounds__(256) k_big_fill(const MeshDev* __restrict__ ms) {
+// conservative integer bounds of { x : A*x + d >= 0 } (exact test follows); false = empty row
+__device__ __forceinline__ bool clip_span(float A, float d, int* lo, int* hi) {
+  if (A == 0.0f) return d >= 0.0f;
+  const float q = fminf(fmaxf(__fdiv_rn(-d, A), -1.0e6f), 1.0e6f);
+  const int f = (int)floorf(q);
+  if (A > 0.0f) *lo = max(*lo, f - 1);
+  else *hi = min(*hi, f + 1);
+  return true;
+}
+
+__global__ void __launch_bounds__(256) k_owner_big(const MeshDev* __restrict__ ms) {
   const MeshDev m = ms[blockIdx.y];
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int n_big = m.counters[3];
-  const int tiles_x = (m.cols + TILE_W - 1) / TILE_W;
-  for (int b = warp; b < n_big; b += nwarps) {
+  const int n_big = m.counters[0];
+  const unsigned epoch = (unsigned)m.counters[1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = blockIdx.x; b < n_big; b += gridDim.x) {
     const int t = m.big[b];
     const TriSetup s = m.setup[t];
-    if (!(s.flags & 16)) continue;
-    const int fx0 = max(s.xmin, 0), fy0 = max(s.ymin, 0), fx1 = s.fx1, fy1 = min(s.ymax, m.rows - 1);
-    const int tx0 = fx0 / TILE_W, ty0 = fy0 / TILE_H;
-    const int nx = fx1 / TILE_W - tx0 + 1, ny = fy1 / TILE_H - ty0 + 1;
-    const bool exact = !(s.flags & 4);
-    for (int i = lane; i < nx * ny; i += 32) {
-      const int tx = tx0 + i % nx, ty = ty0 + i / nx;
-      if (exact && tile_outside(s, tx * TILE_W, ty * TILE_H, tx * TILE_W + TILE_W - 1, ty * TILE_H + TILE_H - 1))
-        continue;
-      const int tile = ty * tiles_x + tx;
-      m.pairs[m.tile_off[tile] + atomicAdd(&m.tile_count[tile], 1)] = t;
-    }
-  }
-}
-
-// one CTA of 1024 threads per slot: exclusive scan of tile_count -> tile_off (n_tiles + 1) in
-// coalesced chunks of 1024 tiles (warp-shuffle scan + one cross-warp step), zero the cursors
-__global__ void __launch_bounds__(1024) k_tile_scan(const MeshDev* __restrict__ ms) {
-  const MeshDev m = ms[blockIdx.y];
-  __shared__ int s_warp[32];
-  __shared__ int s_run;
-  const int n = m.n_tiles;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_run = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int cnt = (i < n) ? m.tile_count[i] : 0;
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int w = s_warp[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += v;
+    const unsigned key = (epoch << OWNER_T_BITS) | (unsigned)t;
+    const int fx0 = max(s.xmin, 0), fy0 = max(s.ymin, 0), fy1 = min(s.ymax, m.rows - 1);
+    const int fx1 = (s.flags & 2) ? s.xend - 1 : s.fx1;
+    for (int y = fy0 + warp; y <= fy1; y += 8) {
+      const float fy = (float)y;
+      int lo = fx0, hi = fx1;
+      if (!clip_span(s.A1, __fadd_rn(__fmul_rn(s.B1, fy), s.C1), &lo, &hi)) continue;
+      if (!clip_span(s.A2, __fadd_rn(__fmul_rn(s.B2, fy), s.C2), &lo, &hi)) continue;
+      if (!clip_span(s.A3, __fadd_rn(__fmul_rn(s.B3, fy), s.C3), &lo, &hi)) continue;
+      for (int x = lo + lane; x <= hi; x += 32) {
+        const float w1 = edge_at(s.A1, s.B1, s.C1, x, y);
+        const float w2 = edge_at(s.A2, s.B2, s.C2, x, y);
+        const float w3 = edge_at(s.A3, s.B3, s.C3, x, y);
+        if (w1 >= 0.0f && w2 >= 0.0f && w3 >= 0.0f) claim(m, x, y, key);
       }
-      s_warp[lane] = w;  // inclusive over warps
     }
-    __syncthreads();
-    const int run = s_run;
-    const int excl = run + (warp > 0 ? s_warp[warp - 1] : 0) + incl - cnt;
-    if (i < n) {
-      m.tile_off[i] = excl;
-      m.tile_count[i] = 0;  // reused as the fill cursor
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) s_run = run + s_warp[31];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    m.tile_off[n] = s_run;
-    // latch this projection's list lengths, re-arm the accumulators
-    m.counters[1] = m.counters[0];
-    m.counters[0] = 0;
-    m.counters[3] = m.counters[2];
-    m.counters[2] = 0;
-    m.counters[4] = 0;
   }
 }
 
-__global__ void __launch_bounds__(256) k_tri_fill(const MeshDev* __restrict__ ms) {
+// Four consecutive (linear) pixels per thread: shade each with its owner triangle.
+__global__ void __launch_bounds__(256) k_resolve(const MeshDev* __restrict__ ms, int fill_nan) {
   const MeshDev m = ms[blockIdx.y];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= m.T) return;
-  const TriSetup s = m.setup[t];
-  if (s.flags & (1 | 8)) return;  // large list / binned by k_big_fill
-  if (s.ymin > s.ymax) return;
-  // exactly the footprint counted in k_tri_setup
-  const int fx0 = max(s.xmin, 0), fy0 = max(s.ymin, 0);
-  const int fx1 = s.fx1, fy1 = min(s.ymax, m.rows - 1);
-  if (fx1 < fx0 || fy1 < fy0) return;
-  const int tiles_x = (m.cols + TILE_W - 1) / TILE_W;
-  for (int ty = fy0 / TILE_H; ty <= fy1 / TILE_H; ++ty)
-    for (int tx = fx0 / TILE_W; tx <= fx1 / TILE_W; ++tx) {
-      if (!(s.flags & 4) && tile_outside(s, tx * TILE_W, ty * TILE_H, tx * TILE_W + TILE_W - 1,
-                                         ty * TILE_H + TILE_H - 1))
-        continue;
-      const int tile = ty * tiles_x + tx;
-      m.pairs[m.tile_off[tile] + atomicAdd(&m.tile_count[tile], 1)] = t;
-    }
-}
-
-#define RCHUNK 16
-// CTA = 4 warps = 4 horizontally adjacent 8x8 tiles; a warp owns one tile, a lane two pixels
-// (x, y) and (x, y + 4) that share the A*x terms of the edge functions.
-__global__ void __launch_bounds__(128) k_tile_raster(const MeshDev* __restrict__ ms, int fill_nan) {
-  const MeshDev m = ms[blockIdx.y];
-  const int tiles_x = (m.cols + TILE_W - 1) / TILE_W;
-  const int ctas_x = (tiles_x + CTA_TILES - 1) / CTA_TILES;
-  const int cy = blockIdx.x / ctas_x, cx = blockIdx.x % ctas_x;
-  if (cy * TILE_H >= m.rows) return;
-  const int sub = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tx = cx * CTA_TILES + sub, ty = cy;
-  if (tx >= tiles_x) return;  // whole warp: no CTA-wide barriers below
-  const int tile = ty * tiles_x + tx;
-  const int px = tx * TILE_W + (lane & 7);
-  const int py0 = ty * TILE_H + (lane >> 3), py1 = py0 + 4;
-  __shared__ TriSetup s_tri[CTA_TILES][RCHUNK];
-  __shared__ int s_id[CTA_TILES][RCHUNK];
-  const int beg = m.tile_off[tile], n_bin = m.tile_off[tile + 1] - beg;
-  const int n_large = m.counters[1];
-  const int n = n_bin + n_large;
-  int best0 = -1, best1 = -1;
-  float val0 = 0.0f, val1 = 0.0f;
-  const float fx = (float)px, fy0 = (float)py0, fy1 = (float)py1;
-  for (int c0 = 0; c0 < n; c0 += RCHUNK) {
-    const int nc = min(RCHUNK, n - c0);
-    __syncwarp();
-    if (lane < nc) {
-      const int e = c0 + lane;
-      const int t = (e < n_bin) ? m.pairs[beg + e] : m.large[e - n_bin];
-      s_id[sub][lane] = t;
-      s_tri[sub][lane] = m.setup[t];
-    }
-    __syncwarp();
-    for (int j = 0; j < nc; ++j) {
-      const int t = s_id[sub][j];
-      const TriSetup& s = s_tri[sub][j];
-      const bool in_x = (px >= s.xmin) && (px < s.xend);
-      const bool c0ok = in_x && (t > best0) && (py0 >= s.ymin) && (py0 <= s.ymax);
-      const bool c1ok = in_x && (t > best1) && (py1 >= s.ymin) && (py1 <= s.ymax);
-      if (c0ok || c1ok) {
-        // (A*x + B*y) + C, each operation rounded (exact: integer-valued)
-        const float ax1 = __fmul_rn(s.A1, fx), ax2 = __fmul_rn(s.A2, fx), ax3 = __fmul_rn(s.A3, fx);
-        if (c0ok) {
-          const float w1 = __fadd_rn(__fadd_rn(ax1, __fmul_rn(s.B1, fy0)), s.C1);
-          const float w2 = __fadd_rn(__fadd_rn(ax2, __fmul_rn(s.B2, fy0)), s.C2);
-          const float w3 = __fadd_rn(__fadd_rn(ax3, __fmul_rn(s.B3, fy0)), s.C3);
-          if (w1 >= 0.0f && w2 >= 0.0f && w3 >= 0.0f) {
-            const float num = __fadd_rn(__fmul_rn(s.v1, w1), __fadd_rn(__fmul_rn(s.v2, w2), __fmul_rn(s.v3, w3)));
-            val0 = __fdiv_rn(num, __fadd_rn(w1, __fadd_rn(w2, w3)));
-            best0 = t;
-          }
-        }
-        if (c1ok) {
-          const float w1 = __fadd_rn(__fadd_rn(ax1, __fmul_rn(s.B1, fy1)), s.C1);
-          const float w2 = __fadd_rn(__fadd_rn(ax2, __fmul_rn(s.B2, fy1)), s.C2);
-          const float w3 = __fadd_rn(__fadd_rn(ax3, __fmul_rn(s.B3, fy1)), s.C3);
-          if (w1 >= 0.0f && w2 >= 0.0f && w3 >= 0.0f) {
-            const float num = __fadd_rn(__fmul_rn(s.v1, w1), __fadd_rn(__fmul_rn(s.v2, w2), __fmul_rn(s.v3, w3)));
-            val1 = __fdiv_rn(num, __fadd_rn(w1, __fadd_rn(w2, w3)));
-            best1 = t;
-          }
-        }
+  const unsigned epoch = (unsigned)m.counters[1];
+  const bool wipe = (epoch >= EPOCH_MAX);  // the next projection restarts at epoch 1
+  const int n = m.rows * m.cols;
+  if (blockIdx.x == 0 && threadIdx.x == 0) m.counters[0] = 0;  // re-arm the big list
+  const float qnan = __uint_as_float(0x7fc00000u);  // quiet_NaN, flame.cc:412
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += gridDim.x * blockDim.x * 4) {
+    unsigned o[4];
+    const bool full = (i + 4 <= n);
+    if (full) {
+      const uint4 v = *reinterpret_cast<const uint4*>(m.owner + i);
+      o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+      if (wipe) *reinterpret_cast<uint4*>(m.owner + i) = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      for (int k = 0; k < 4; ++k) {
+        o[k] = (i + k < n) ? m.owner[i + k] : 0u;
+        if (wipe && i + k < n) m.owner[i + k] = 0u;
       }
-      if (s.flags & 2) {
-        // degenerate triangle whose 4-px sweep ran past the right border: the reference's linear
-        // addressing lands on (x - cols, y + 1)
+    }
+    int py = i / m.cols, px = i - py * m.cols;
+    float out[4];
+    bool have[4];
+    int last_t = -1;
+    TriSetup s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      have[k] = false;
+      out[k] = qnan;
+      if ((o[k] >> OWNER_T_BITS) == epoch) {
+        const int t = (int)(o[k] & ((1u << OWNER_T_BITS) - 1u));
+        if (t != last_t) {
+          s = m.setup[t];
+          last_t = t;
+        }
         float v;
-        if (t > best0 && tri_eval(s, px + m.cols, py0 - 1, &v)) { best0 = t; val0 = v; }
-        if (t > best1 && tri_eval(s, px + m.cols, py1 - 1, &v)) { best1 = t; val1 = v; }
+        // the sweep row itself wins over the wrapped tail of the row above (written later)
+        if (tri_eval(s, px, py, &v) || ((s.flags & 2) && tri_eval(s, px + m.cols, py - 1, &v))) {
+          have[k] = true;
+          out[k] = v;
+        }
+      }
+      if (++px == m.cols) {
+        px = 0;
+        ++py;
       }
     }
-  }
-  if (px < m.cols) {
-    const unsigned int qnan = 0x7fc00000u;  // quiet_NaN, flame.cc:412
-    if (py0 < m.rows) {
-      const size_t i = (size_t)py0 * m.cols + px;
-      if (best0 >= 0) m.img[i] = val0;
-      else if (fill_nan) m.img[i] = __uint_as_float(qnan);
-    }
-    if (py1 < m.rows) {
-      const size_t i = (size_t)py1 * m.cols + px;
-      if (best1 >= 0) m.img[i] = val1;
-      else if (fill_nan) m.img[i] = __uint_as_float(qnan);
+    if (full && (fill_nan || (have[0] && have[1] && have[2] && have[3]))) {
+      *reinterpret_cast<float4*>(m.img + i) = make_float4(out[0], out[1], out[2], out[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (i + k < n && (have[k] || fill_nan)) m.img[i + k] = out[k];
     }
   }
-  if (lane == 0) m.tile_count[tile] = 0;  // fill cursor -> zero for the next projection
 }
 
 __global__ void k_values_from_graph(const GraphDev* __restrict__ gs, const MeshDev* __restrict__ ms,
@@ -377,37 +254,21 @@ int raster_values_from_graph(cudaStream_t st, const GraphDev* gs_dev, const Mesh
   return 0;
 }
 
-// ms_dev: device array of n MeshDev. The tile counters / list lengths re-arm themselves (k_tile_scan,
-// k_tile_raster), so a projection needs no memset.
-int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_ctas, int fill_nan) {
-  if (n == 0 || max_ctas == 0) return 0;
-  if (maxT > 0) {
-    k_tri_setup<<<dim3((maxT + 255) / 256, n), 256, 0, st>>>(ms_dev);
-    count_launch();
-  }
-  if (maxT > 0) {
-    k_big_count<<<dim3(16, n), 256, 0, st>>>(ms_dev);
-    count_launch();
-  }
-  k_tile_scan<<<dim3(1, n), 1024, 0, st>>>(ms_dev);
+// ms_dev: device array of n MeshDev. Epoch and big-list counter re-arm themselves on the device, so a
+// projection needs no memset and no host round trip.
+int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_pix, int fill_nan) {
+  if (n == 0 || max_pix == 0) return 0;
+  k_tri_setup<<<dim3(std::max(1, (maxT + 255) / 256), n), 256, 0, st>>>(ms_dev);
   count_launch();
   if (maxT > 0) {
-    k_tri_fill<<<dim3((maxT + 255) / 256, n), 256, 0, st>>>(ms_dev);
-    k_big_fill<<<dim3(16, n), 256, 0, st>>>(ms_dev);
+    k_owner_small<<<dim3((maxT + 7) / 8, n), 256, 0, st>>>(ms_dev);
+    k_owner_big<<<dim3(32, n), 256, 0, st>>>(ms_dev);
     count_launch(2);
   }
-  k_tile_raster<<<dim3(max_ctas, n), 128, 0, st>>>(ms_dev, fill_nan);
+  k_resolve<<<dim3((max_pix / 4 + 255) / 256 + 1, n), 256, 0, st>>>(ms_dev, fill_nan);
   count_launch();
   FB_CUDA(cudaGetLastError());
   return 0;
-}
-
-int raster_tile_count(int rows, int cols) {
-  return ((cols + TILE_W - 1) / TILE_W) * ((rows + TILE_H - 1) / TILE_H);
-}
-int raster_cta_count(int rows, int cols) {
-  const int tiles_x = (cols + TILE_W - 1) / TILE_W;
-  return ((tiles_x + CTA_TILES - 1) / CTA_TILES) * ((rows + TILE_H - 1) / TILE_H);
 }
 
 }  // namespace fb

@@ -56,6 +56,16 @@ uint64_t flame_b200_kernel_launches(void);
 int flame_b200_ctx_create(int device, int n_slots, flame_b200_ctx** out);
 void flame_b200_ctx_destroy(flame_b200_ctx* ctx);
 int flame_b200_ctx_sync(flame_b200_ctx* ctx);
+
+/* Optional pipelining of the dense projection. With on != 0, flame_b200_mesh_project issues its kernels
+ * on a second stream of the context, so that the solver launches of the NEXT frames (graph_reset,
+ * pd_run on flame_b200_ctx_stream) overlap them: a frame cluster occupies 16 SMs and at most 7 clusters
+ * are resident on a B200, the projection fills the remaining SMs. Every library call that reads or
+ * replaces projection inputs/outputs (mesh_download, mesh_bind, interpolate_mesh, graph uploads,
+ * ctx_sync) orders itself after the pending projection; callers that put their OWN work or events on
+ * flame_b200_ctx_stream call flame_b200_ctx_join first (device-side wait, does not block the host). */
+int flame_b200_ctx_set_async_projection(flame_b200_ctx* ctx, int on);
+int flame_b200_ctx_join(flame_b200_ctx* ctx);
 /* cudaStream_t of the context, as an opaque pointer (for CUDA-event timing by the caller). */
 void* flame_b200_ctx_stream(flame_b200_ctx* ctx);
 

@@ -101,3 +101,96 @@ def test_process_frame_one_call(gpu_ctx, oracle):
     _assert_same_image(out.array.copy(), want)
     for a, b in ((x, s["x"]), (w1, s["w1"]), (w2, s["w2"])):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_large_footprints_slivers_and_wrapping_lines(gpu_ctx, oracle):
+    """Triangles with a large sweep footprint take the CTA-per-triangle path (row spans clipped by the
+    edge functions): long hull slivers, big interior triangles, long degenerate lines (diagonal,
+    horizontal, vertical), and degenerate lines whose 4-px sweep overshoot runs past the right border and
+    lands on the next row (linear addressing, rasterization.cc:206-236), incl. on the last row."""
+    W, H = 200, 120
+    pos = np.array([[2, 3], [197, 5], [100, 7],          # 0-2 thin sliver across the image
+                    [10, 20], [190, 25], [90, 110],      # 3-5 big interior triangle
+                    [5, 100], [150, 30], [77.5, 65],     # 6-8 diagonal line (set to exact collinear points below)
+                    [3, 50], [199, 50], [120, 50],       # 9-11 horizontal line touching the right border
+                    [60, 2], [60, 118], [60, 40],        # 12-14 vertical line
+                    [150, 119], [199, 119], [170, 119],  # 15-17 horizontal line on the LAST row, wraps off-image
+                    [193, 80], [198, 80], [196, 80],     # 18-20 short line at the border (small path, wraps)
+                    [0, 0], [199, 0], [0, 119], [199, 119]], np.float32)
+    pos[6], pos[7], pos[8] = (4, 100), (152, 26), (78, 63)   # integer collinear points on one line
+    tris = np.array([[21, 22, 23], [23, 22, 24], [21, 23, 22], [24, 22, 23],   # both windings: full cover
+                     [0, 1, 2], [0, 2, 1], [3, 4, 5], [3, 5, 4], [6, 7, 8], [8, 7, 6], [9, 10, 11],
+                     [11, 10, 9], [12, 13, 14], [15, 16, 17], [18, 19, 20], [20, 19, 18]], np.int32)
+    rng = np.random.default_rng(9)
+    vals = rng.uniform(0.1, 2.0, pos.shape[0]).astype(np.float32)
+    want = oracle.interpolate_mesh(tris, pos, vals, H, W)
+    got = gpu_ctx.interpolate_mesh(0, tris, pos, vals, H, W)
+    _assert_same_image(got, want)
+    assert np.isnan(want).sum() < W * H
+    # the same with a background image instead of the NaN fill, and width not a multiple of 4
+    for (w2, h2) in ((199, 120), (201, 77)):
+        p2 = np.minimum(pos, np.array([w2 - 1, h2 - 1], np.float32))
+        base = rng.uniform(size=(h2, w2)).astype(np.float32)
+        want = oracle.interpolate_mesh(tris, p2, vals, h2, w2, None, None, base.copy())
+        got = gpu_ctx.interpolate_mesh(0, tris, p2, vals, h2, w2, None, None, base.copy())
+        _assert_same_image(got, want)
+
+
+def test_owner_epoch_wrap_and_rebinding(gpu_ctx, oracle):
+    """The per-pixel owner words are tagged with a 12-bit projection epoch instead of being cleared:
+    run past the wrap, re-bind the slot to other image sizes in between, and compare with the oracle."""
+    rng = np.random.default_rng(4)
+    g = synth.make_graph(64, 48, 60, seed=31, noise_seed=32, triangulator="scipy")
+    big = synth.config_graph("A")
+    tris_half = np.ascontiguousarray(g["tris"][::2])
+    for it in range(4200):
+        if it in (1000, 4090):  # other size in the same slot, then back
+            v = big["data_term"]
+            got = gpu_ctx.interpolate_mesh(5, big["tris"], big["pos"], v, big["H"], big["W"])
+            _assert_same_image(got, oracle.interpolate_mesh(big["tris"], big["pos"], v, big["H"], big["W"]))
+        vals = rng.uniform(0.1, 2.0, g["pos"].shape[0]).astype(np.float32)
+        tris = g["tris"] if it % 3 else tris_half  # coverage shrinks and grows again
+        got = gpu_ctx.interpolate_mesh(5, tris, g["pos"], vals, 48, 64)
+        if it % 500 == 0 or it > 4080:
+            _assert_same_image(got, oracle.interpolate_mesh(tris, g["pos"], vals, 48, 64))
+
+
+def test_async_projection_pipeline(oracle):
+    """flame_b200_ctx_set_async_projection: the projection runs on the context's second stream while the
+    next solver launches proceed; downloads / re-binds / uploads order themselves after it."""
+    gs = [synth.make_graph(640, 480, 500 + 100 * i, seed=50 + i, noise_seed=60 + i, triangulator="scipy")
+          for i in range(3)]
+    p = _lib.default_pd_params()
+    with _lib.Context(0, 3) as ctx:
+        ctx.set_async_projection(True)
+        for i, g in enumerate(gs):
+            ctx.graph_init(i, g["pos"], g["data_term"], g["edges"])
+            ctx.mesh_bind(i, g["tris"], g["H"], g["W"])
+        outs = [_lib.PinnedArray((g["H"], g["W"])) for g in gs]
+        for rep, iters in enumerate((5, 9, 14)):
+            ctx.graph_reset(0, 3)
+            ctx.pd_run(p, iters, 0, 3)
+            ctx.mesh_project(0, 3, 1.0)
+            # no sync: the next round's reset + solver overlap this projection
+        for i in range(3):
+            ctx.mesh_download(i, outs[i].array)
+        ctx.sync()
+        for i, g in enumerate(gs):
+            alpha, beta = oracle.edge_weights(g["edges"], g["pos"])
+            s = synth.init_state(g, alpha, beta)
+            oracle.pd_run(s, oracle.pd_default_params(), 14)
+            _assert_same_image(outs[i].array.copy(), oracle.interpolate_mesh(g["tris"], g["pos"], s["x"], g["H"], g["W"]))
+        # a re-bind + upload while a projection is pending must not corrupt it
+        ctx.graph_reset(0, 3)
+        ctx.pd_run(p, 4, 0, 3)
+        ctx.mesh_project(0, 3, 2.0)
+        ctx.mesh_download(1, outs[1].array)
+        ctx.graph_init(1, gs[0]["pos"], gs[0]["data_term"], gs[0]["edges"])
+        ctx.mesh_bind(1, gs[0]["tris"], gs[0]["H"], gs[0]["W"])
+        ctx.sync()
+        g = gs[1]
+        alpha, beta = oracle.edge_weights(g["edges"], g["pos"])
+        s = synth.init_state(g, alpha, beta)
+        oracle.pd_run(s, oracle.pd_default_params(), 4)
+        want = oracle.interpolate_mesh(g["tris"], g["pos"], (s["x"] * np.float32(2.0)).astype(np.float32), g["H"], g["W"])
+        _assert_same_image(outs[1].array.copy(), want)
