@@ -92,7 +92,7 @@ SYMBOLS = [
     "flame_b200_host_alloc", "flame_b200_host_free",
     "flame_b200_pd_default_params", "flame_b200_graph_upload", "flame_b200_graph_init",
     "flame_b200_graph_set_data", "flame_b200_graph_reset", "flame_b200_graph_download",
-    "flame_b200_graph_project", "flame_b200_graph_resync", "flame_b200_pd_run",
+    "flame_b200_graph_project", "flame_b200_graph_resync", "flame_b200_pd_run", "flame_b200_pd_wave",
     "flame_b200_pd_cost", "flame_b200_interpolate_mesh", "flame_b200_mesh_bind",
     "flame_b200_mesh_project", "flame_b200_mesh_download", "flame_b200_process_frame",
     "flame_b200_track_default_params",
@@ -132,6 +132,7 @@ def lib():
     L.flame_b200_graph_project.argtypes = [vp, C.c_int, f32p, f32p, C.c_float, f32p, f32p]
     L.flame_b200_graph_resync.argtypes = [vp, C.c_int, C.POINTER(GraphSync)]
     L.flame_b200_pd_run.argtypes = [vp, C.c_int, C.c_int, C.POINTER(PDParams), C.c_int, C.c_int]
+    L.flame_b200_pd_wave.argtypes = [vp, C.c_int, C.POINTER(C.c_int32)]
     L.flame_b200_pd_cost.argtypes = [vp, C.c_int, C.POINTER(PDParams), C.c_int, f32p, f32p]
     L.flame_b200_interpolate_mesh.argtypes = [vp, C.c_int, C.c_int32, i32p, C.c_int32, f32p, f32p,
                                               C.c_float, u8p, u8p, C.c_int, C.c_int, C.c_int, f32p]
@@ -322,6 +323,11 @@ class Context:
 
     def pd_run(self, params, n_iters, slot0=0, n_slots=1, mode=PD_AUTO):
         check(lib().flame_b200_pd_run(self._h, slot0, n_slots, C.byref(params), n_iters, mode))
+
+    def pd_wave(self, slot=0):
+        n = C.c_int32(0)
+        check(lib().flame_b200_pd_wave(self._h, slot, C.byref(n)))
+        return n.value
 
     def pd_cost(self, slot, params, exact_order=False):
         a, b = C.c_float(), C.c_float()

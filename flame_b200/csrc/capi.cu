@@ -79,9 +79,11 @@ struct flame_b200_ctx {
   // asynchronous dense projection (flame_b200_ctx_set_async_projection): the projection kernels run on
   // `side` so that the next frames' solver launches on `stream` overlap them
   bool async_proj = false;
-  bool side_busy = false;
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_vals = nullptr, ev_side = nullptr;
+  cudaEvent_t ev_vals = nullptr;
+  struct Pending { int lo, hi; cudaEvent_t done; };  // projections of slots [lo, hi) issued on `side`
+  std::vector<Pending> pending;                      // in issue order (the side stream is in-order)
+  std::vector<cudaEvent_t> ev_pool;
   // host scratch for graph prep
   std::vector<uint32_t> keys, keys2;
   std::vector<int> idx, idx2, vinv, cursor, degv, srcdeg, order, koff_tmp;
@@ -373,15 +375,23 @@ static int publish_graph(flame_b200_ctx* c, int slot) {
   return 0;
 }
 
-// Orders everything issued so far on the projection stream before whatever is issued next on the
-// main stream (device-side wait, the host does not block).
-static int join_side(flame_b200_ctx* c) {
-  if (c->side_busy) {
-    FB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_side, 0));
-    c->side_busy = false;
-  }
+// Orders the pending projections that touch slots [lo, hi) - and, the projection stream being in-order,
+// everything issued before them - ahead of whatever is issued next on the main stream (device-side
+// wait, the host does not block).
+static int join_range(flame_b200_ctx* c, int lo, int hi) {
+  int last = -1;
+  for (int i = (int)c->pending.size() - 1; i >= 0; --i)
+    if (c->pending[i].lo < hi && lo < c->pending[i].hi) {
+      last = i;
+      break;
+    }
+  if (last < 0) return 0;
+  FB_CUDA(cudaStreamWaitEvent(c->stream, c->pending[last].done, 0));
+  for (int i = 0; i <= last; ++i) c->ev_pool.push_back(c->pending[i].done);
+  c->pending.erase(c->pending.begin(), c->pending.begin() + last + 1);
   return 0;
 }
+static int join_side(flame_b200_ctx* c) { return join_range(c, 0, c->n_slots); }
 
 static int raster_sub_batch() {
   static int v = -1;
@@ -491,7 +501,8 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
   cudaStreamSynchronize(c->stream);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->ev_vals) cudaEventDestroy(c->ev_vals);
-  if (c->ev_side) cudaEventDestroy(c->ev_side);
+  for (auto& pnd : c->pending) cudaEventDestroy(pnd.done);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   for (auto& s : c->slots) {
     for (void* p : {(void*)s.g.vprim, (void*)s.g.vbar, (void*)s.g.vbar2, (void*)s.g.vprev,
                     (void*)s.g.vwt, (void*)s.g.inc_q, (void*)s.g.inc_s, (void*)s.d_blob,
@@ -530,7 +541,6 @@ int flame_b200_ctx_set_async_projection(flame_b200_ctx* c, int on) {
   if (on && !c->side) {
     FB_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     FB_CUDA(cudaEventCreateWithFlags(&c->ev_vals, cudaEventDisableTiming));
-    FB_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
   }
   c->async_proj = on != 0;
   return 0;
@@ -576,7 +586,7 @@ static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph
     return FLAME_B200_EINVAL;
   }
   if (int rc = use_device(c)) return rc;
-  if (int rc = join_side(c)) return rc;
+  if (int rc = join_range(c, slot, slot + 1)) return rc;
   Slot& s = c->slots[slot];
   const int V = g->V, E = g->E;
   PrepOut prep;
@@ -719,7 +729,7 @@ int flame_b200_graph_project(flame_b200_ctx* c, int slot, const float q_wxyz[4],
     return FLAME_B200_EINVAL;
   }
   if (int rc = use_device(c)) return rc;
-  if (int rc = join_side(c)) return rc;
+  if (int rc = join_range(c, slot, slot + 1)) return rc;
   Slot& s = c->slots[slot];
   if (!s.loaded) {
     set_error("graph_project: slot has no graph");
@@ -896,6 +906,26 @@ int flame_b200_pd_run(flame_b200_ctx* c, int slot0, int n_slots, const flame_b20
   return pd_run_stream(c->stream, c->d_graphs + slot0, n_slots, max_chunks, threads, *params, n_iters);
 }
 
+int flame_b200_pd_wave(flame_b200_ctx* c, int slot, int32_t* frames) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (!frames) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  const Slot& s = c->slots[slot];
+  if (!s.loaded) {
+    set_error("pd_wave: slot has no graph");
+    return FLAME_B200_ESTATE;
+  }
+  *frames = 0;
+  if (s.g.V == 0 || s.plan.cluster == 0) return 0;
+  ResidentPlan plan = s.plan;
+  plan.smem_bytes = pd_resident_smem(plan.Vc, plan.maxInc, plan.maxEdges, plan.max_deg);
+  if (plan.smem_bytes > 227 * 1024 || !pd_resident_variant(plan.Vc, plan.maxEdges, &plan.threads)) return 0;
+  int n = 0;
+  if (int rc = pd_resident_capacity(plan, &n)) return rc;
+  *frames = n;
+  return 0;
+}
+
 int flame_b200_pd_cost(flame_b200_ctx* c, int slot, const flame_b200_pd_params* params,
                        int exact_order, float* smoothness_cost, float* data_cost) {
   if (int rc = check_slot(c, slot)) return rc;
@@ -999,7 +1029,7 @@ int flame_b200_mesh_bind(flame_b200_ctx* c, int slot, int32_t T, const int32_t* 
                          const uint8_t* vtx_valid, const uint8_t* tri_valid, int rows, int cols) {
   if (int rc = check_slot(c, slot)) return rc;
   if (int rc = use_device(c)) return rc;
-  if (int rc = join_side(c)) return rc;
+  if (int rc = join_range(c, slot, slot + 1)) return rc;
   Slot& s = c->slots[slot];
   if (!s.loaded) {
     set_error("mesh_bind: slot has no graph");
@@ -1025,8 +1055,10 @@ int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float sca
     maxT = std::max(maxT, s.m.T);
     max_pix = std::max(max_pix, s.m.rows * s.m.cols);
   }
-  // values_from_graph overwrites what the previous projection's setup kernel reads
-  if (int rc = join_side(c)) return rc;
+  // values_from_graph overwrites what a pending projection of the same slots still reads
+  if (int rc = join_range(c, slot0, slot0 + n_slots)) return rc;
+  if (c->pending.size() >= 64)
+    if (int rc = join_side(c)) return rc;
   if (int rc = raster_values_from_graph(c->stream, c->d_graphs + slot0, c->d_meshes + slot0, n_slots,
                                         maxV, scale))
     return rc;
@@ -1041,8 +1073,15 @@ int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float sca
     if (int rc = raster_project(rs, c->d_meshes + slot0 + i, std::min(sub, n_slots - i), maxT, max_pix, 1))
       return rc;
   if (c->async_proj) {
-    FB_CUDA(cudaEventRecord(c->ev_side, c->side));
-    c->side_busy = true;
+    cudaEvent_t done = nullptr;
+    if (!c->ev_pool.empty()) {
+      done = c->ev_pool.back();
+      c->ev_pool.pop_back();
+    } else {
+      FB_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    }
+    FB_CUDA(cudaEventRecord(done, c->side));
+    c->pending.push_back({slot0, slot0 + n_slots, done});
   }
   return 0;
 }
@@ -1051,7 +1090,7 @@ int flame_b200_mesh_download(flame_b200_ctx* c, int slot, float* out_host) {
   if (int rc = check_slot(c, slot)) return rc;
   if (!out_host) return FLAME_B200_EINVAL;
   if (int rc = use_device(c)) return rc;
-  if (int rc = join_side(c)) return rc;
+  if (int rc = join_range(c, slot, slot + 1)) return rc;
   Slot& s = c->slots[slot];
   if (!s.m.img) {
     set_error("mesh_download: no dense map in this slot");
@@ -1072,7 +1111,7 @@ int flame_b200_interpolate_mesh(flame_b200_ctx* c, int slot, int32_t T, const in
     return FLAME_B200_EINVAL;
   }
   if (int rc = use_device(c)) return rc;
-  if (int rc = join_side(c)) return rc;
+  if (int rc = join_range(c, slot, slot + 1)) return rc;
   Slot& s = c->slots[slot];
   if (!values && (!s.loaded || s.g.V != V)) {
     set_error("interpolate_mesh: values == NULL needs a graph with V vertices in the slot");

@@ -95,6 +95,7 @@ bool pd_resident_variant(int Vc, int maxEdges, int* threads);
 int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const ResidentPlan& plan,
                     const flame_b200_pd_params& p, int n_iters);
 int pd_resident_init();  // one-time function attributes
+int pd_resident_capacity(const ResidentPlan& plan, int* n_clusters);
 int pd_cost(cudaStream_t st, const GraphDev& g, const flame_b200_pd_params& p, int exact_order,
             float* terms_scratch, double* out_dev /*2 doubles*/);
 

@@ -756,6 +756,28 @@ int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const Reside
   return 0;
 }
 
+// How many frame clusters of this plan the device keeps resident at once (one wave of pd_run_resident).
+int pd_resident_capacity(const ResidentPlan& plan, int* n_clusters) {
+  if (int rc = pd_resident_init()) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(64 * plan.cluster);
+  cfg.blockDim = dim3(plan.threads);
+  cfg.dynamicSmemBytes = plan.smem_bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = plan.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (plan.threads <= 640) {
+    FB_CUDA(cudaOccupancyMaxActiveClusters(n_clusters, k_pd_resident<640, 4>, &cfg));
+  } else {
+    FB_CUDA(cudaOccupancyMaxActiveClusters(n_clusters, k_pd_resident<1024, 2>, &cfg));
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // Energies: smoothnessCost (cc:51-71), dataCost (cc:73-85)
 // ------------------------------------------------------------------------------------------

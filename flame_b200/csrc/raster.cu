@@ -128,15 +128,39 @@ __global__ void __launch_bounds__(256) k_owner_small(const MeshDev* __restrict__
   if ((s.flags & 8) || s.ymin > s.ymax) return;
   const unsigned key = ((unsigned)m.counters[1] << OWNER_T_BITS) | (unsigned)t;
   const int fx0 = max(s.xmin, 0), fy0 = max(s.ymin, 0), fy1 = min(s.ymax, m.rows - 1);
-  const int fx1 = (s.flags & 2) ? s.xend - 1 : s.fx1;
-  for (int y = fy0 + (lane >> 4); y <= fy1; y += 2) {
-    const float fy = (float)y;
-    const float b1 = __fmul_rn(s.B1, fy), b2 = __fmul_rn(s.B2, fy), b3 = __fmul_rn(s.B3, fy);
-    for (int x = fx0 + (lane & 15); x <= fx1; x += 16) {
+  if (!(s.flags & 2)) {
+    // 8 x 4 lanes; a lane walks down its column in steps of 4 rows, stepping the (integer-valued, hence
+    // exactly representable) edge functions by 4*B
+    const int fx1 = s.fx1;
+    const int y0 = fy0 + (lane >> 3);
+    const float fy = (float)y0;
+    const float b1 = __fadd_rn(__fmul_rn(s.B1, fy), s.C1), b2 = __fadd_rn(__fmul_rn(s.B2, fy), s.C2),
+                b3 = __fadd_rn(__fmul_rn(s.B3, fy), s.C3);
+    const float s1 = __fmul_rn(s.B1, 4.0f), s2 = __fmul_rn(s.B2, 4.0f), s3 = __fmul_rn(s.B3, 4.0f);
+    const size_t pstep = (size_t)4 * m.cols;
+    for (int x = fx0 + (lane & 7); x <= fx1; x += 8) {
       const float fx = (float)x;
-      const float w1 = __fadd_rn(__fadd_rn(__fmul_rn(s.A1, fx), b1), s.C1);
-      const float w2 = __fadd_rn(__fadd_rn(__fmul_rn(s.A2, fx), b2), s.C2);
-      const float w3 = __fadd_rn(__fadd_rn(__fmul_rn(s.A3, fx), b3), s.C3);
+      float w1 = __fadd_rn(__fmul_rn(s.A1, fx), b1);
+      float w2 = __fadd_rn(__fmul_rn(s.A2, fx), b2);
+      float w3 = __fadd_rn(__fmul_rn(s.A3, fx), b3);
+      unsigned int* ptr = m.owner + (size_t)y0 * m.cols + x;
+      for (int y = y0; y <= fy1; y += 4) {
+        if (w1 >= 0.0f && w2 >= 0.0f && w3 >= 0.0f) atomicMax(ptr, key);
+        w1 = __fadd_rn(w1, s1);
+        w2 = __fadd_rn(w2, s2);
+        w3 = __fadd_rn(w3, s3);
+        ptr += pstep;
+      }
+    }
+    return;
+  }
+  // degenerate triangle whose sweep overshoot crosses the right border: generic positions + wrap
+  const int fx1 = s.xend - 1;
+  for (int y = fy0 + (lane >> 4); y <= fy1; y += 2) {
+    for (int x = fx0 + (lane & 15); x <= fx1; x += 16) {
+      const float w1 = edge_at(s.A1, s.B1, s.C1, x, y);
+      const float w2 = edge_at(s.A2, s.B2, s.C2, x, y);
+      const float w3 = edge_at(s.A3, s.B3, s.C3, x, y);
       if (w1 >= 0.0f && w2 >= 0.0f && w3 >= 0.0f) claim(m, x, y, key);
     }
   }
@@ -205,6 +229,8 @@ __global__ void __launch_bounds__(256) k_resolve(const MeshDev* __restrict__ ms,
     bool have[4];
     int last_t = -1;
     TriSetup s;
+    float w1 = 0.0f, w2 = 0.0f, w3 = 0.0f;
+    bool stepping = false;  // w1..w3 hold the edge functions of triangle last_t at (px, py)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       have[k] = false;
@@ -214,17 +240,40 @@ __global__ void __launch_bounds__(256) k_resolve(const MeshDev* __restrict__ ms,
         if (t != last_t) {
           s = m.setup[t];
           last_t = t;
+          stepping = false;
         }
-        float v;
-        // the sweep row itself wins over the wrapped tail of the row above (written later)
-        if (tri_eval(s, px, py, &v) || ((s.flags & 2) && tri_eval(s, px + m.cols, py - 1, &v))) {
+        if (!(s.flags & 2)) {
+          // the owner word says this triangle covers (px, py): shade without re-testing
+          if (!stepping) {
+            w1 = edge_at(s.A1, s.B1, s.C1, px, py);
+            w2 = edge_at(s.A2, s.B2, s.C2, px, py);
+            w3 = edge_at(s.A3, s.B3, s.C3, px, py);
+            stepping = true;
+          }
+          const float norm = __fadd_rn(w1, __fadd_rn(w2, w3));
+          const float num = __fadd_rn(__fmul_rn(s.v1, w1), __fadd_rn(__fmul_rn(s.v2, w2), __fmul_rn(s.v3, w3)));
+          out[k] = __fdiv_rn(num, norm);
           have[k] = true;
-          out[k] = v;
+        } else {
+          float v;
+          // the sweep row itself wins over the wrapped tail of the row above (written later)
+          if (tri_eval(s, px, py, &v) || tri_eval(s, px + m.cols, py - 1, &v)) {
+            have[k] = true;
+            out[k] = v;
+          }
         }
+      } else {
+        stepping = false;
+      }
+      if (stepping) {  // one pixel to the right: exact for integer-valued edge functions
+        w1 = __fadd_rn(w1, s.A1);
+        w2 = __fadd_rn(w2, s.A2);
+        w3 = __fadd_rn(w3, s.A3);
       }
       if (++px == m.cols) {
         px = 0;
         ++py;
+        stepping = false;
       }
     }
     if (full && (fill_nan || (have[0] && have[1] && have[2] && have[3]))) {

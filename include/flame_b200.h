@@ -190,6 +190,12 @@ enum {
 int flame_b200_pd_run(flame_b200_ctx* ctx, int slot0, int n_slots,
                       const flame_b200_pd_params* params, int n_iters, int mode);
 
+/* Number of frames like the one in `slot` that the resident solver runs CONCURRENTLY: one frame is one
+ * thread-block cluster, and the GPU holds a limited number of clusters at a time (7 of 16 CTAs on a
+ * B200: cudaOccupancyMaxActiveClusters). pd_run over more slots proceeds in waves of this size; batches
+ * that are a multiple of it waste no wave. 0 = the slot's graph takes the streaming path. */
+int flame_b200_pd_wave(flame_b200_ctx* ctx, int slot, int32_t* frames);
+
 /* Replaces smoothnessCost / dataCost (h:139,144; cc:51-85). exact_order != 0 reproduces the
  * reference's sequential fp32 accumulation order bit-for-bit (slower); 0 uses a tree reduction
  * in fp64. Synchronises the stream. */
