@@ -87,6 +87,7 @@ struct flame_b200_ctx {
   // host scratch for graph prep
   std::vector<uint32_t> keys, keys2;
   std::vector<int> idx, idx2, vinv, cursor, degv, srcdeg, order, koff_tmp;
+  std::vector<uint64_t> halo_keys;
 };
 
 namespace fb {
@@ -109,8 +110,10 @@ static size_t ints_total(int V, int E, int n_chunks, int max_deg) {
   return (size_t)2 * V + (size_t)n_chunks * (max_deg + 1) + (size_t)n_chunks + 1 + (size_t)6 * E;
 }
 // + 2E ints of device-only space (edge_slot) after the uploaded image
+// then the resync maps (V + E) and the halo tables (2 (n_chunks + 1) + 2 H, H <= E)
 static size_t blob_bytes(int V, int E, int n_chunks, int max_deg) {
-  return (raw_f_total(V, E) + ints_total(V, E, n_chunks, max_deg) + (size_t)2 * E) * 4 + 256;
+  return (raw_f_total(V, E) + ints_total(V, E, n_chunks, max_deg) + (size_t)2 * E + (size_t)V + E +
+          (size_t)2 * (n_chunks + 1) + (size_t)2 * E) * 4 + 256;
 }
 
 // Internal order + private incidence layout (see GraphDev). O(V + E), deterministic.
@@ -194,7 +197,9 @@ static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const in
       }
       maxInc = std::max(maxInc, 1);
       maxEdges = std::max(maxEdges, 1);
-      const size_t smem = pd_resident_smem(Vc, maxInc, maxEdges, max_deg);
+      // the halo / push tables are only known after the layout is built: budget 24 KB for them here,
+      // graph_upload_impl re-checks with the real sizes
+      const size_t smem = pd_resident_smem(Vc, maxInc, maxEdges, max_deg, 0, 0) + (C > 1 ? 24 * 1024 : 0);
       if (smem > 227 * 1024) continue;
       int thr = 0;
       if (!pd_resident_variant(Vc, maxEdges, &thr)) continue;
@@ -287,6 +292,49 @@ static void prep_fill(flame_b200_ctx* c, int V, int E, const int32_t* edges, con
       inc_edge[slot] = o;
     }
   }
+}
+
+// Halo tables of the resident solver (GraphDev::halo_*, push_*), written to `out` as
+// [halo_off n_chunks+1 | push_off n_chunks+1 | halo_vtx H | push_ent H]. Needs c->vinv from prep_fill.
+static void prep_halo(flame_b200_ctx* c, int E, const int32_t* edges, const PrepOut& pr, int* out, int* H_out,
+                      int* max_halo, int* max_push) {
+  const int Vc = pr.Vc, n_chunks = pr.n_chunks;
+  std::vector<uint64_t>& keys = c->halo_keys;
+  keys.clear();
+  for (int o = 0; o < E; ++o) {
+    const int s = c->vinv[edges[2 * o]], d = c->vinv[edges[2 * o + 1]];
+    if (s / Vc != d / Vc) keys.push_back(((uint64_t)(s / Vc) << 32) | (uint32_t)d);
+  }
+  std::sort(keys.begin(), keys.end());
+  keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+  const int H = (int)keys.size();
+  int* halo_off = out;
+  int* push_off = out + n_chunks + 1;
+  int* halo_vtx = push_off + n_chunks + 1;
+  int* push_ent = halo_vtx + H;
+  std::fill(halo_off, halo_off + 2 * (n_chunks + 1), 0);
+  for (int i = 0; i < H; ++i) {
+    halo_off[(keys[i] >> 32) + 1]++;
+    push_off[(int)(uint32_t)keys[i] / Vc + 1]++;
+  }
+  int mh = 0, mp = 0;
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    mh = std::max(mh, halo_off[ch + 1]);
+    mp = std::max(mp, push_off[ch + 1]);
+    halo_off[ch + 1] += halo_off[ch];
+    push_off[ch + 1] += push_off[ch];
+  }
+  c->cursor.assign(n_chunks, 0);
+  for (int i = 0; i < H; ++i) {
+    const int ch = (int)(keys[i] >> 32), g = (int)(uint32_t)keys[i];
+    const int h = i - halo_off[ch];  // keys are sorted by (chunk, vertex): position inside the chunk
+    halo_vtx[i] = g;
+    const int r = g / Vc, il = g - r * Vc;
+    push_ent[push_off[r] + c->cursor[r]++] = il | (h << 11) | (ch << 27);
+  }
+  *H_out = H;
+  *max_halo = mh;
+  *max_push = mp;
 }
 
 static int check_slot(flame_b200_ctx* c, int slot, int n = 1) {
@@ -641,12 +689,22 @@ static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph
   const size_t bytes = (raw_f_total(V, E) + ints_total(V, E, prep.n_chunks, prep.max_deg)) * 4;
   // resync maps live after the device-only edge_slot table: [vtx_from V | edge_from E]
   const size_t o_maps = bytes + (size_t)2 * E * 4, maps_bytes = sync ? ((size_t)V + E) * 4 : 0;
+  // halo tables of the resident solver after the (reserved) map area
+  const size_t o_halo = o_maps + ((size_t)V + E) * 4;
+  int H = 0;
+  prep_halo(c, E, g->edges, prep, reinterpret_cast<int*>(s.h_blob + o_halo), &H, &s.plan.maxHalo,
+            &s.plan.maxPush);
+  const size_t halo_bytes = ((size_t)2 * (prep.n_chunks + 1) + (size_t)2 * H) * 4;
+  if (s.plan.cluster > 0 &&
+      pd_resident_smem(s.plan.Vc, s.plan.maxInc, s.plan.maxEdges, s.plan.max_deg, s.plan.maxHalo,
+                       s.plan.maxPush) > 227 * 1024)
+    s.plan.cluster = 0;  // tables larger than budgeted: streaming path
   if (sync) {
     int* hm = reinterpret_cast<int*>(s.h_blob + o_maps);
     if (V > 0) std::memcpy(hm, sync->vtx_from, (size_t)V * 4);
     if (E > 0) std::memcpy(hm + V, sync->edge_from, (size_t)E * 4);
   }
-  if (o_maps + maps_bytes > s.d_blob_cap || o_maps + maps_bytes > s.h_blob_cap) {
+  if (o_halo + halo_bytes > s.d_blob_cap || o_halo + halo_bytes > s.h_blob_cap) {
     set_error("internal: staging blob too small");
     return FLAME_B200_ENOMEM;
   }
@@ -670,7 +728,13 @@ static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph
       FB_CUDA(cudaMemcpyAsync(s.d_blob + o_maps, s.h_blob + o_maps, maps_bytes, cudaMemcpyHostToDevice,
                               c->stream));
   }
+  FB_CUDA(cudaMemcpyAsync(s.d_blob + o_halo, s.h_blob + o_halo, halo_bytes, cudaMemcpyHostToDevice, c->stream));
   FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
+  int* dh = reinterpret_cast<int*>(s.d_blob + o_halo);
+  s.g.halo_off = dh;
+  s.g.push_off = dh + prep.n_chunks + 1;
+  s.g.halo_vtx = s.g.push_off + prep.n_chunks + 1;
+  s.g.push_ent = s.g.halo_vtx + H;
   int* di = reinterpret_cast<int*>(s.d_raw() + raw_f_total(V, E));
   s.g.V = V;
   s.g.E = E;
@@ -889,11 +953,13 @@ int flame_b200_pd_run(flame_b200_ctx* c, int slot0, int n_slots, const flame_b20
     plan.maxInc = std::max(plan.maxInc, s.plan.maxInc);
     plan.maxEdges = std::max(plan.maxEdges, s.plan.maxEdges);
     plan.max_deg = std::max(plan.max_deg, s.plan.max_deg);
+    plan.maxHalo = std::max(plan.maxHalo, s.plan.maxHalo);
+    plan.maxPush = std::max(plan.maxPush, s.plan.maxPush);
     plan.threads = std::max(plan.threads, s.plan.threads);
   }
   if (n_iters == 0 || maxV == 0) return 0;
   if (fits) {
-    plan.smem_bytes = pd_resident_smem(plan.Vc, plan.maxInc, plan.maxEdges, plan.max_deg);
+    plan.smem_bytes = pd_resident_smem(plan.Vc, plan.maxInc, plan.maxEdges, plan.max_deg, plan.maxHalo, plan.maxPush);
     if (plan.smem_bytes > 227 * 1024 || !pd_resident_variant(plan.Vc, plan.maxEdges, &plan.threads)) fits = false;
   }
   if (mode == FLAME_B200_PD_RESIDENT && !fits) {
@@ -918,7 +984,7 @@ int flame_b200_pd_wave(flame_b200_ctx* c, int slot, int32_t* frames) {
   *frames = 0;
   if (s.g.V == 0 || s.plan.cluster == 0) return 0;
   ResidentPlan plan = s.plan;
-  plan.smem_bytes = pd_resident_smem(plan.Vc, plan.maxInc, plan.maxEdges, plan.max_deg);
+  plan.smem_bytes = pd_resident_smem(plan.Vc, plan.maxInc, plan.maxEdges, plan.max_deg, plan.maxHalo, plan.maxPush);
   if (plan.smem_bytes > 227 * 1024 || !pd_resident_variant(plan.Vc, plan.maxEdges, &plan.threads)) return 0;
   int n = 0;
   if (int rc = pd_resident_capacity(plan, &n)) return rc;

@@ -48,6 +48,12 @@ struct GraphDev {
   int* inc_edge;    // [2E] caller edge index of the incidence
   int* edges;       // [2E] caller (source, target) pairs
   int* edge_slot;   // [2E] (caller edge, role) -> incidence slot (written by the pack kernel)
+  // resident solver, halo exchange: chunk c keeps a local copy ("halo") of x_bar/w_bar of every vertex of
+  // another chunk that is the TARGET of an edge it owns; the owning chunk pushes the new values each iteration
+  int* halo_off;    // [n_chunks + 1]
+  int* halo_vtx;    // [H] internal vertex ids, ascending inside a chunk
+  int* push_off;    // [n_chunks + 1]
+  int* push_ent;    // [H] local vertex (bits 0-10) | halo index in the destination (11-26) | destination chunk (27-30)
 };
 
 struct __align__(16) TriSetup {  // per triangle, written by k_tri_setup; 80 bytes = 5 x 128-bit loads
@@ -79,6 +85,7 @@ struct ResidentPlan {
   int threads;
   size_t smem_bytes;
   int Vc, maxInc, maxEdges, max_deg;
+  int maxHalo, maxPush;  // per-CTA maxima of the halo / push tables
 };
 #define FB_RESIDENT_MAX_DEG 64
 
@@ -90,7 +97,7 @@ int pd_set_data(cudaStream_t st, const GraphDev& g, const float* data_term, cons
 int pd_reset(cudaStream_t st, const GraphDev* gs_dev, int n, int maxV, int maxE);
 int pd_run_stream(cudaStream_t st, const GraphDev* gs_dev, int n, int max_chunks, int threads,
                   const flame_b200_pd_params& p, int n_iters);
-size_t pd_resident_smem(int Vc, int maxInc, int maxEdges, int max_deg);
+size_t pd_resident_smem(int Vc, int maxInc, int maxEdges, int max_deg, int maxHalo, int maxPush);
 bool pd_resident_variant(int Vc, int maxEdges, int* threads);
 int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const ResidentPlan& plan,
                     const flame_b200_pd_params& p, int n_iters);

@@ -439,6 +439,7 @@ struct ResidentArgs {
   flame_b200_pd_params p;
   int n_iters;
   int Vc, maxInc, maxEdges, max_deg;  // batch maxima: identical shared-memory carve in every CTA
+  int maxHalo, maxPush;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -478,6 +479,30 @@ __device__ __forceinline__ void cluster_arrive() {
 }
 __device__ __forceinline__ void cluster_wait() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---- mbarrier + st.async (halo exchange of k_pd_resident_mb) ----
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+// remote arrival (release at cluster scope: everything this CTA wrote - by any of its threads, ordered
+// before this one by __syncthreads - is visible to whoever observes the phase with acquire.cluster)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      " selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
+  for (unsigned spin = 0; !mbar_try_wait(addr, parity); ++spin)
+    if (spin > (1u << 22)) __trap();  // a lost arrival must not hang the device
 }
 
 #define PD_MLP 2
@@ -691,9 +716,286 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   }
 }
 
-size_t pd_resident_smem(int Vc, int maxInc, int maxEdges, int max_deg) {
-  return (size_t)Vc * 32 + (size_t)maxInc * (16 + 4) + (size_t)maxEdges * (16 + 4) +
-         (size_t)(max_deg + 2) * 4 + 1024 * 4 + 128;
+// ------------------------------------------------------------------------------------------
+// RESIDENT mode, halo exchange (experimental, FLAME_B200_PD_SYNC=p2p). Same phases and arithmetic as
+// k_pd_resident, but no
+// cluster-wide barrier and no remote LOADS inside the iteration:
+//   * every CTA keeps a local copy ("halo") of x_bar/w_bar of the remote target vertices of its edges,
+//     laid out behind its own vertices ([bar0 | halo0 | bar1 | halo1]), so phase A reads only its own
+//     shared memory; the owners store the new values into their neighbours' halos after phase B;
+//   * synchronisation is point to point: after its remote stores (target contributions of cut edges in
+//     phase A, halo values after phase B) a CTA arrives - release.cluster, one thread per neighbour -
+//     on an mbarrier of each CTA it wrote to; a CTA waits - acquire.cluster, one lane per warp - until
+//     all of its in-neighbours have arrived: contributions before phase B, halos before the next phase
+//     A. Neighbours are never more than one phase apart because each direction of traffic gates the
+//     other (S's contributions gate R's phase B, R's halo gates S's next phase A), so one mbarrier per
+//     direction and double-buffered x_bar/halo records suffice.
+// ------------------------------------------------------------------------------------------
+template <int MAXT, int SPT>
+__global__ void __launch_bounds__(MAXT, 1) k_pd_resident_mb(ResidentArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = cluster.num_blocks();
+  const int c = cluster.block_rank();
+  const GraphDev g = a.gs[blockIdx.x / C];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int Vc = g.Vc;  // this graph's chunk width (a.Vc >= Vc is the carve width)
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int row = a.Vc + a.maxHalo;  // vertices + halo entries of one buffer
+  float4* s_bar0 = reinterpret_cast<float4*>(smem);
+  float4* s_bar1 = s_bar0 + row;
+  float4* s_p4 = s_bar1 + row;       // per incidence slot: (sx, t1, t2, u1)
+  float4* s_s = s_p4 + a.maxInc;     // per owned edge: (alpha, beta, dx, dy)
+  float* s_p1 = reinterpret_cast<float*>(s_s + a.maxEdges);  // per incidence slot: u2
+  int* s_list = reinterpret_cast<int*>(s_p1 + a.maxInc);     // owned edges: their source slot
+  int* s_koff = s_list + a.maxEdges;                         // a.max_deg + 1
+  int* s_cnt = s_koff + a.max_deg + 1;                       // 2: owned edges, expected contribution slots
+  int* s_scan = s_cnt + 2;                                   // blockDim.x (<= 1024), load phase only
+  int* s_push_v = s_scan + 1024;                             // a.maxPush: local vertex to publish
+  uint32_t* s_push_addr = reinterpret_cast<uint32_t*>(s_push_v + a.maxPush);  // its halo record (buffer 0) there
+  unsigned int* s_mask = s_push_addr + a.maxPush;            // 2: ranks holding my halos' owners / my push targets
+  unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(
+      (reinterpret_cast<uintptr_t>(s_mask + 2) + 7) & ~uintptr_t(7));  // [0] contributions, [1] halos
+
+  const bool have = c < g.n_chunks;
+  const int v0 = c * Vc;
+  const int nv = have ? min(Vc, g.V - v0) : 0;
+  const int base = have ? g.chunk_base[c] : 0;
+  const int ni = have ? g.chunk_base[c + 1] - base : 0;
+  const int h0 = have ? g.halo_off[c] : 0;
+  const int nh = have ? g.halo_off[c + 1] - h0 : 0;
+  const int np = have ? g.push_off[c + 1] - g.push_off[c] : 0;
+  const uint32_t bar0_addr = smem_u32(s_bar0);
+  const uint32_t bar_stride = (uint32_t)row * 16u;  // bar1 - bar0
+  const uint32_t p4_addr = smem_u32(s_p4);
+  const uint32_t mbc_addr = smem_u32(s_mbar), mbh_addr = mbc_addr + 8u;
+  const float neg0 = __int_as_float(0x80000000);
+
+  // ---- load ----
+  if (have)
+    for (int k = tid; k <= g.max_deg; k += nt) s_koff[k] = g.koff[(size_t)c * (g.max_deg + 1) + k];
+  if (tid == 0) {
+    s_cnt[0] = 0;
+    s_mask[0] = 0u;
+    s_mask[1] = 0u;
+  }
+  __syncthreads();
+  const bool hasv = tid < nv;
+  float x = 0.f, w1 = 0.f, w2 = 0.f, data = 0.f, wt = 0.f;
+  int deg = 0;
+  if (hasv) {
+    const float4 pr = g.vprim[v0 + tid];
+    x = pr.x; w1 = pr.y; w2 = pr.z; data = pr.w;
+    wt = g.vwt[v0 + tid];
+    deg = g.deg[v0 + tid];
+    s_bar0[tid] = g.vbar[v0 + tid];
+  }
+  for (int h = tid; h < nh; h += nt) {  // first halo: from HBM
+    const int hv = g.halo_vtx[h0 + h];
+    s_bar0[a.Vc + h] = g.vbar[hv];
+    atomicOr(&s_mask[0], 1u << (hv / Vc));  // that CTA receives my contributions and sends me halos
+  }
+  for (int e = tid; e < np; e += nt) {
+    const int ent = g.push_ent[g.push_off[c] + e];
+    const uint32_t dc = (uint32_t)ent >> 27;
+    s_push_v[e] = ent & 0x7FF;
+    s_push_addr[e] = mapa(bar0_addr + (uint32_t)(a.Vc + ((ent >> 11) & 0xFFFF)) * 16u, dc);
+    atomicOr(&s_mask[1], 1u << dc);         // that CTA receives my halos and sends me contributions
+  }
+  __syncthreads();
+  const unsigned int mask_p = s_mask[0], mask_d = s_mask[1];
+  const bool wait_c = mask_d != 0u, wait_h = mask_p != 0u;
+  if (tid == 0) {
+    mbar_init(mbc_addr, max(__popc(mask_d), 1));
+    mbar_init(mbh_addr, max(__popc(mask_p), 1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // thread t < 16 signals rank t
+  const bool sig_c = tid < 16 && ((mask_p >> tid) & 1u), sig_h = tid < 16 && ((mask_d >> tid) & 1u);
+  const uint32_t rmb_c = (tid < C) ? mapa(mbc_addr, (uint32_t)tid) : 0u;
+  const uint32_t rmb_h = (tid < C) ? mapa(mbh_addr, (uint32_t)tid) : 0u;
+  const bool poller = (tid & 31) == 0;
+  // owned edges = source-role incidence slots of this chunk, listed vertex by vertex (see k_pd_resident)
+  int outdeg = 0;
+  if (hasv)
+    for (int k = 0; k < deg; ++k) outdeg += ((g.inc_nbr[base + s_koff[k] + tid] & 1) == 0);
+  s_scan[tid] = outdeg;
+  __syncthreads();
+  if (tid == 0) {  // nt <= 1024 entries, once per launch
+    int run = 0;
+    for (int i = 0; i < nt; ++i) {
+      const int d0 = s_scan[i];
+      s_scan[i] = run;
+      run += d0;
+    }
+    s_cnt[0] = run;
+  }
+  __syncthreads();
+  if (hasv) {
+    int at = s_scan[tid];
+    for (int k = 0; k < deg; ++k) {
+      const int slot = s_koff[k] + tid;
+      if ((g.inc_nbr[base + slot] & 1) == 0) s_list[at++] = slot;
+    }
+  }
+  __syncthreads();
+  for (int slot = tid; slot < ni; slot += nt)
+    s_p1[slot] = neg0;  // target slots keep -0.0f forever; source slots are rewritten every iteration
+  const int ne = s_cnt[0];
+  float q1[SPT], q2[SPT], q3[SPT];
+  uint32_t src_bar[SPT];   // own bar0 record of the source
+  uint32_t dst_bar[SPT];   // own bar0 / halo0 record of the target
+  uint32_t src_slot[SPT];  // local incidence slot of the source | remote flag (bit 19)
+  uint32_t dst_p4[SPT];    // p4 record of the target endpoint: shared::cta, or shared::cluster if remote
+#pragma unroll
+  for (int u = 0; u < SPT; ++u) {
+    const int j = tid + u * nt;
+    q1[u] = q2[u] = q3[u] = 0.f;
+    src_bar[u] = bar0_addr;
+    dst_bar[u] = bar0_addr;
+    src_slot[u] = 0;
+    dst_p4[u] = p4_addr;
+    if (j < ne) {
+      const int slot = s_list[j];
+      const float4 q = g.inc_q[base + slot];
+      q1[u] = q.x; q2[u] = q.y; q3[u] = q.z;
+      s_s[j] = g.inc_s[base + slot];
+      // source vertex of the slot: slot = koff[k] + i with koff non-decreasing in k
+      int k = 0;
+      while (k + 1 <= g.max_deg && s_koff[k + 1] <= slot) ++k;
+      src_bar[u] = bar0_addr + (uint32_t)(slot - s_koff[k]) * 16u;
+      const int nbr = __float_as_int(q.w) >> 1;
+      const int oc = nbr / Vc;
+      const bool remote = (oc != c);
+      int idx = nbr - oc * Vc;
+      if (remote) {  // position of nbr in this chunk's (ascending) halo list
+        int lo = 0, hi = nh - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (g.halo_vtx[h0 + mid] < nbr) lo = mid + 1;
+          else hi = mid;
+        }
+        idx = a.Vc + lo;
+      }
+      dst_bar[u] = bar0_addr + (uint32_t)idx * 16u;
+      src_slot[u] = (uint32_t)slot | (remote ? (1u << 19) : 0u);
+      // the target endpoint's incidence slot of this edge (global slot id -> owner chunk, local slot)
+      const int tslot = g.edge_slot[2 * g.inc_edge[base + slot] + 1];
+      dst_p4[u] = remote ? mapa(p4_addr + (uint32_t)(tslot - g.chunk_base[oc]) * 16u, (uint32_t)oc)
+                         : (p4_addr + (uint32_t)(tslot - g.chunk_base[oc]) * 16u);
+    }
+  }
+  cluster.sync();
+
+  const flame_b200_pd_params p = a.p;
+
+  for (int it = 0; it < a.n_iters; ++it) {
+    const uint32_t cur_off = (it & 1) ? bar_stride : 0u;
+    float4* nxt = (it & 1) ? s_bar0 : s_bar1;
+    if (it > 0 && wait_h) {  // the halos this iteration reads (iteration 0: loaded from HBM above)
+      if (poller) mbar_wait(mbh_addr, (uint32_t)(it - 1) & 1u);
+      __syncwarp();
+    }
+    // ---- phase A: one dual update per edge, contributions pushed to both endpoints ----
+#pragma unroll
+    for (int u0 = 0; u0 < SPT; u0 += PD_MLP) {
+      float4 s[PD_MLP], bi[PD_MLP], bj[PD_MLP];
+#pragma unroll
+      for (int v = 0; v < PD_MLP; ++v) {
+        const int u = u0 + v;
+        if (u < SPT && tid + u * nt < ne) {
+          s[v] = s_s[tid + u * nt];
+          bi[v] = ld_shared_f4(src_bar[u] + cur_off);
+          bj[v] = ld_shared_f4(dst_bar[u] + cur_off);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < PD_MLP; ++v) {
+        const int u = u0 + v;
+        if (u < SPT && tid + u * nt < ne) {
+          const float4 qu = dual_update(make_float4(q1[u], q2[u], q3[u], 0.f), s[v], bi[v], bj[v], p.step_q);
+          q1[u] = qu.x; q2[u] = qu.y; q3[u] = qu.z;
+          // primalStep contributions (cc:125-141), rounded as the reference: a = (q1*step_x)*alpha ...
+          const float pa = mul(mul(qu.x, p.step_x), s[v].x);
+          const float b2 = mul(mul(qu.y, p.step_x), s[v].y);
+          const float b3 = mul(mul(qu.z, p.step_x), s[v].y);
+          const uint32_t sl = src_slot[u] & 0x7FFFFu;
+          // source i: x -= a; w1 += a*dx; w2 += a*dy; w1 -= b2; w2 -= b3
+          s_p4[sl] = make_float4(-pa, mul(pa, s[v].z), mul(pa, s[v].w), -b2);
+          s_p1[sl] = -b3;
+          // target j: x += a; w1 += b2; w2 += b3   (u1 = u2 = -0.0f: exact no-ops)
+          if (src_slot[u] & (1u << 19)) st_cluster_f4(dst_p4[u], make_float4(pa, b2, b3, neg0));
+          else st_shared_f4(dst_p4[u], make_float4(pa, b2, b3, neg0));
+        }
+      }
+    }
+    __syncthreads();  // every contribution of this CTA - local and remote - has been issued
+    if (sig_c) mbar_arrive_remote(rmb_c);
+    if (wait_c) {     // all CTAs that own edges into this one have arrived
+      if (poller) mbar_wait(mbc_addr, (uint32_t)it & 1u);
+      __syncwarp();
+    }
+    // ---- phase B: ordered accumulation + prox + extragradient, one vertex per thread ----
+    if (hasv) {
+      const float x_old = x, w1_old = w1, w2_old = w2;
+      float4 p4n = make_float4(0.f, 0.f, 0.f, 0.f);
+      float p1n = 0.f;
+      if (deg > 0) {
+        p4n = s_p4[tid];  // koff[0] == 0
+        p1n = s_p1[tid];
+      }
+      int ko = (deg > 1) ? s_koff[1] : 0;
+      for (int k = 0; k < deg; ++k) {
+        const float4 p4 = p4n;
+        const float p1 = p1n;
+        if (k + 1 < deg) {
+          const int slot = ko + tid;
+          p4n = s_p4[slot];
+          p1n = s_p1[slot];
+          ko = s_koff[k + 2];  // k + 2 <= max_deg: inside the table
+        }
+        x = add(x, p4.x);
+        w1 = add(w1, p4.y);
+        w2 = add(w2, p4.z);
+        w1 = add(w1, p4.w);
+        w2 = add(w2, p1);
+      }
+      const VertexOut o = vertex_finish(x, w1, w2, data, wt, x_old, w1_old, w2_old, p);
+      x = o.prim.x;
+      nxt[tid] = o.bar;
+      if (it == a.n_iters - 1) g.vprev[v0 + tid] = make_float4(x_old, w1_old, w2_old, 0.0f);
+    }
+    __syncthreads();  // the new x_bar/w_bar of this CTA are complete (and its p4 records consumed)
+    if (it + 1 < a.n_iters) {
+      const uint32_t nxt_off = (it & 1) ? 0u : bar_stride;
+      for (int e = tid; e < np; e += nt) st_cluster_f4(s_push_addr[e] + nxt_off, nxt[s_push_v[e]]);
+      if (np > 0) __syncthreads();  // uniform per CTA
+      if (sig_h) mbar_arrive_remote(rmb_h);
+    }
+  }
+  cluster.sync();  // no CTA leaves while a neighbour could still address its shared memory
+
+  // ---- write back (both private copies of every edge's q) ----
+  if (hasv) {
+    const float4* fin = (a.n_iters & 1) ? s_bar1 : s_bar0;
+    g.vbar[v0 + tid] = fin[tid];
+    g.vprim[v0 + tid] = make_float4(x, w1, w2, data);
+  }
+#pragma unroll
+  for (int u = 0; u < SPT; ++u) {
+    const int j = tid + u * nt;
+    if (j < ne) {
+      const int sslot = base + (int)(src_slot[u] & 0x7FFFFu);
+      const int tslot = g.edge_slot[2 * g.inc_edge[sslot] + 1];
+      g.inc_q[sslot] = make_float4(q1[u], q2[u], q3[u], __int_as_float(g.inc_nbr[sslot]));
+      g.inc_q[tslot] = make_float4(q1[u], q2[u], q3[u], __int_as_float(g.inc_nbr[tslot]));
+    }
+  }
+}
+
+size_t pd_resident_smem(int Vc, int maxInc, int maxEdges, int max_deg, int maxHalo, int maxPush) {
+  return (size_t)(Vc + maxHalo) * 32 + (size_t)maxInc * (16 + 4) + (size_t)maxEdges * (16 + 4) +
+         (size_t)(max_deg + 3) * 4 + 1024 * 4 + (size_t)maxPush * 8 + 2 * 4 + 2 * 8 + 8 + 128;
 }
 
 // The two register budgets the kernel is built for: (threads, owned edges per thread).
@@ -720,6 +1022,12 @@ int pd_resident_init() {
   FB_CUDA(cudaFuncSetAttribute(k_pd_resident<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                227 * 1024));
   FB_CUDA(cudaFuncSetAttribute(k_pd_resident<1024, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  FB_CUDA(cudaFuncSetAttribute(k_pd_resident_mb<640, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024));
+  FB_CUDA(cudaFuncSetAttribute(k_pd_resident_mb<640, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  FB_CUDA(cudaFuncSetAttribute(k_pd_resident_mb<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024));
+  FB_CUDA(cudaFuncSetAttribute(k_pd_resident_mb<1024, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   done = true;
   return 0;
 }
@@ -735,6 +1043,17 @@ int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const Reside
   a.maxInc = plan.maxInc;
   a.maxEdges = plan.maxEdges;
   a.max_deg = plan.max_deg;
+  a.maxHalo = plan.maxHalo;
+  a.maxPush = plan.maxPush;
+  // Default: k_pd_resident (two hardware cluster barriers per iteration, remote loads), the fastest of
+  // the three synchronisation schemes measured on B200 (single frame, config D, 200 iterations):
+  //   barrier.cluster + remote loads ............................ 0.617 ms
+  //   local halos, st.async + mbarrier transaction bytes (16 B) .. 0.720 ms
+  //   local halos, plain DSMEM stores + point-to-point mbarrier
+  //     arrive.release.cluster / try_wait.acquire.cluster ........ 0.974 ms   (k_pd_resident_mb)
+  // FLAME_B200_PD_SYNC=p2p selects the last one (kept bit-exact and tested).
+  const char* sv = getenv("FLAME_B200_PD_SYNC");
+  const bool use_barrier = !(sv && sv[0] == 'p');
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n * plan.cluster);
   cfg.blockDim = dim3(plan.threads);
@@ -747,10 +1066,16 @@ int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const Reside
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (plan.threads <= 640) {
-    FB_CUDA(cudaLaunchKernelEx(&cfg, k_pd_resident<640, 4>, a));
+  if (use_barrier) {
+    if (plan.threads <= 640) {
+      FB_CUDA(cudaLaunchKernelEx(&cfg, k_pd_resident<640, 4>, a));
+    } else {
+      FB_CUDA(cudaLaunchKernelEx(&cfg, k_pd_resident<1024, 2>, a));
+    }
+  } else if (plan.threads <= 640) {
+    FB_CUDA(cudaLaunchKernelEx(&cfg, k_pd_resident_mb<640, 4>, a));
   } else {
-    FB_CUDA(cudaLaunchKernelEx(&cfg, k_pd_resident<1024, 2>, a));
+    FB_CUDA(cudaLaunchKernelEx(&cfg, k_pd_resident_mb<1024, 2>, a));
   }
   count_launch();
   return 0;

@@ -215,3 +215,18 @@ def test_pd_graph_larger_than_a_cluster_streams(gpu_ctx, oracle):
     assert np.array_equal(np.isnan(out), np.isnan(img_w))
     m = ~np.isnan(out)
     assert np.array_equal(out[m].view(np.uint32), img_w[m].view(np.uint32))
+
+
+@pytest.mark.parametrize("cfg", ["A", "B", "D"])
+def test_pd_halo_exchange_variant(gpu_ctx, oracle, cfg, monkeypatch):
+    """FLAME_B200_PD_SYNC=p2p selects the experimental resident kernel (local halos, point-to-point
+    mbarrier synchronisation instead of cluster barriers): slower on B200, but it must stay bit-exact."""
+    monkeypatch.setenv("FLAME_B200_PD_SYNC", "p2p")
+    g = synth.config_graph(cfg)
+    n = 40
+    want = _oracle_state(oracle, g, n)
+    V, E = g["pos"].shape[0], g["edges"].shape[0]
+    gpu_ctx.graph_init(0, g["pos"], g["data_term"], g["edges"])
+    gpu_ctx.pd_run(_lib.default_pd_params(), n, mode=_lib.PD_RESIDENT)
+    got = gpu_ctx.graph_download(0, V, E)
+    _assert_bit_equal(got, want, STATE)
