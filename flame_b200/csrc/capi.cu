@@ -182,38 +182,43 @@ static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const in
   if (const char* sv = getenv("FLAME_B200_CLUSTER")) forced = atoi(sv);
   ResidentPlan plan{};
   if (V > 0 && V < (1 << 20) && max_deg <= FB_RESIDENT_MAX_DEG) {
-    for (int C = 1; C <= 16; C *= 2) {
-      if (forced && C != forced) continue;
-      const int Vc = (V + C - 1) / C;
-      int maxInc = 0, maxEdges = 0;
-      for (int k = 0; k < C; ++k) {
-        int inc = 0, ed = 0;
-        for (int i = std::min(k * Vc, V); i < std::min((k + 1) * Vc, V); ++i) {
-          inc += c->degv[morton[i]];
-          ed += c->srcdeg[morton[i]];
+    // smallest cluster that holds the graph (any size, not only powers of two); the 640-thread variant
+    // (4 edges per thread in registers) is markedly faster than the 1024-thread one, so a larger cluster
+    // with the former beats a smaller one with the latter
+    for (int pass = 0; pass < 2 && !plan.cluster; ++pass)
+      for (int C = 1; C <= 16; ++C) {
+        if (forced && C != forced) continue;
+        const int Vc = (V + C - 1) / C;
+        int maxInc = 0, maxEdges = 0;
+        for (int k = 0; k < C; ++k) {
+          int inc = 0, ed = 0;
+          for (int i = std::min(k * Vc, V); i < std::min((k + 1) * Vc, V); ++i) {
+            inc += c->degv[morton[i]];
+            ed += c->srcdeg[morton[i]];
+          }
+          maxInc = std::max(maxInc, inc);
+          maxEdges = std::max(maxEdges, ed);
         }
-        maxInc = std::max(maxInc, inc);
-        maxEdges = std::max(maxEdges, ed);
+        maxInc = std::max(maxInc, 1);
+        maxEdges = std::max(maxEdges, 1);
+        // the halo / push tables are only known after the layout is built: budget 24 KB for them here,
+        // graph_upload_impl re-checks with the real sizes
+        const size_t smem = pd_resident_smem(Vc, maxInc, maxEdges, max_deg, 0, 0) + (C > 1 ? 24 * 1024 : 0);
+        if (smem > 227 * 1024) continue;
+        int thr = 0;
+        if (!pd_resident_variant(Vc, maxEdges, &thr)) continue;
+        if (pass == 0 && thr != 640) continue;
+        ResidentPlan pl{};
+        pl.cluster = C;
+        pl.Vc = Vc;
+        pl.maxInc = maxInc;
+        pl.maxEdges = maxEdges;
+        pl.max_deg = max_deg;
+        pl.smem_bytes = smem;
+        pl.threads = thr;
+        plan = pl;
+        break;
       }
-      maxInc = std::max(maxInc, 1);
-      maxEdges = std::max(maxEdges, 1);
-      // the halo / push tables are only known after the layout is built: budget 24 KB for them here,
-      // graph_upload_impl re-checks with the real sizes
-      const size_t smem = pd_resident_smem(Vc, maxInc, maxEdges, max_deg, 0, 0) + (C > 1 ? 24 * 1024 : 0);
-      if (smem > 227 * 1024) continue;
-      int thr = 0;
-      if (!pd_resident_variant(Vc, maxEdges, &thr)) continue;
-      ResidentPlan pl{};
-      pl.cluster = C;
-      pl.Vc = Vc;
-      pl.maxInc = maxInc;
-      pl.maxEdges = maxEdges;
-      pl.max_deg = max_deg;
-      pl.smem_bytes = smem;
-      pl.threads = thr;
-      plan = pl;
-      break;
-    }
   }
   const int Vc = plan.cluster ? plan.Vc : std::min(std::max(V, 1), 1024);
   const int n_chunks = V > 0 ? (V + Vc - 1) / Vc : 0;
@@ -440,15 +445,6 @@ static int join_range(flame_b200_ctx* c, int lo, int hi) {
   return 0;
 }
 static int join_side(flame_b200_ctx* c) { return join_range(c, 0, c->n_slots); }
-
-static int raster_sub_batch() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = std::getenv("FLAME_B200_RASTER_SUB");
-    v = e ? std::max(0, std::atoi(e)) : 0;
-  }
-  return v;
-}
 
 }  // namespace fb
 
@@ -1134,10 +1130,7 @@ int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float sca
     FB_CUDA(cudaStreamWaitEvent(c->side, c->ev_vals, 0));
     rs = c->side;
   }
-  const int sub = raster_sub_batch() > 0 ? raster_sub_batch() : n_slots;
-  for (int i = 0; i < n_slots; i += sub)
-    if (int rc = raster_project(rs, c->d_meshes + slot0 + i, std::min(sub, n_slots - i), maxT, max_pix, 1))
-      return rc;
+  if (int rc = raster_project(rs, c->d_meshes + slot0, n_slots, maxT, max_pix, 1)) return rc;
   if (c->async_proj) {
     cudaEvent_t done = nullptr;
     if (!c->ev_pool.empty()) {

@@ -1,6 +1,6 @@
 """Experiment: one context, dense projection on the context's second stream (flame_b200_ctx_set_async_projection)
-vs in-order, for several batch sizes. FLAME_B200_RASTER_SUB=<n> splits the projection launches into
-sub-batches of n frames. Run under gpurun."""
+vs in-order, for several batch sizes. Run under gpurun. (An earlier variant also split the projection
+launches into sub-batches of 4 / 7 frames to keep the owner words in L2: slower, removed.)"""
 import os
 import sys
 
@@ -26,7 +26,6 @@ def main():
         ctx.mesh_bind(i, g["tris"], H, W)
     ctx.sync()
     st = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    print("FLAME_B200_RASTER_SUB =", os.environ.get("FLAME_B200_RASTER_SUB", "(unset)"))
     for B in (7, 14, 28, 35, 42, 56):
         for on in (0, 1):
             ctx.set_async_projection(on)

@@ -230,3 +230,16 @@ def test_pd_halo_exchange_variant(gpu_ctx, oracle, cfg, monkeypatch):
     gpu_ctx.pd_run(_lib.default_pd_params(), n, mode=_lib.PD_RESIDENT)
     got = gpu_ctx.graph_download(0, V, E)
     _assert_bit_equal(got, want, STATE)
+
+
+@pytest.mark.parametrize("V", [1400, 3000, 5600, 7000])
+def test_pd_cluster_sizes_not_powers_of_two(gpu_ctx, oracle, V, monkeypatch):
+    """The planner takes the smallest cluster that holds the graph (3, 5, 9, 12 CTAs for these sizes)."""
+    g = synth.make_graph(1280, 720, V, seed=70 + V, noise_seed=71 + V, triangulator="scipy")
+    want = _oracle_state(oracle, g, 30)
+    E = g["edges"].shape[0]
+    for sync in ("barrier", "p2p"):
+        monkeypatch.setenv("FLAME_B200_PD_SYNC", sync)
+        gpu_ctx.graph_init(6, g["pos"], g["data_term"], g["edges"])
+        gpu_ctx.pd_run(_lib.default_pd_params(), 30, slot0=6, mode=_lib.PD_RESIDENT)
+        _assert_bit_equal(gpu_ctx.graph_download(6, V, E), want, STATE)
