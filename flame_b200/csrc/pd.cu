@@ -363,19 +363,19 @@ k_pd_stream(const GraphDev* __restrict__ gs, flame_b200_pd_params p, int parity,
     for (int u = 0; u < STREAM_U; ++u)
       if (k0 + u < d) {
         slot[u] = base + koff[k0 + u] + i;
-        q[u] = g.inc_q[slot[u]];
-        s[u] = g.inc_s[slot[u]];
+        q[u] = __ldcs(&g.inc_q[slot[u]]);  // streamed once per iteration: do not displace the gathered x_bar
+        s[u] = __ldcs(&g.inc_s[slot[u]]);
       }
 #pragma unroll
     for (int u = 0; u < STREAM_U; ++u)
-      if (k0 + u < d) nb[u] = cur[__float_as_int(q[u].w) >> 1];
+      if (k0 + u < d) nb[u] = __ldg(&cur[__float_as_int(q[u].w) >> 1]);
 #pragma unroll
     for (int u = 0; u < STREAM_U; ++u)
       if (k0 + u < d) {
         const int is_target = __float_as_int(q[u].w) & 1;
         const float4 qn = dual_update_inc(q[u], s[u], own, nb[u], is_target, p.step_q);
         primal_apply(x, w1, w2, qn, s[u], is_target, p.step_x);
-        g.inc_q[slot[u]] = make_float4(qn.x, qn.y, qn.z, q[u].w);
+        __stcs(&g.inc_q[slot[u]], make_float4(qn.x, qn.y, qn.z, q[u].w));
       }
   }
   const VertexOut o = vertex_finish(x, w1, w2, pr.w, wt, pr.x, pr.y, pr.z, p);
