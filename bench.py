@@ -352,7 +352,10 @@ def run_ours(args, rank, world, local_rank):
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": pd_ms,
                          "note": "algorithmic bytes = 76*(V+E) per PD iteration per frame; the resident kernel "
                                  "keeps the state in shared memory, so achieved is an EFFECTIVE bandwidth "
-                                 "(DRAM traffic is far below the algorithmic bytes; see DESIGN.md)"},
+                                 "(DRAM traffic is far below the algorithmic bytes; see DESIGN.md). The HBM-streaming variant of "
+                                 "the same iteration (--mode 1, graphs too large for a cluster) moves 410 MB of DRAM "
+                                 "traffic per 128-frame launch at 4.59 TB/s = 0.70 of this peak (ncu, "
+                                 "profiles/r1_pd_stream_b128.txt)"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": e2e["h2d"],
                     "d2h_bytes_per_step": e2e["d2h"], "frames_per_step": e2e["per_step"],
                     "pipelines": e2e["pipelines"]},
