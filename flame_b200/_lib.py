@@ -44,6 +44,14 @@ class GraphSync(C.Structure):
                 ("edge_from", i32p), ("check_sticky_obstacles", C.c_int32)]
 
 
+class TriFilterParams(C.Structure):
+    """flame_b200_tri_filter_params (params.h:70-85)."""
+    _fields_ = [("do_oblique_triangle_filter", C.c_int32), ("oblique_normal_thresh", C.c_float),
+                ("oblique_idepth_diff_factor", C.c_float), ("oblique_idepth_diff_abs", C.c_float),
+                ("do_edge_length_filter", C.c_int32), ("edge_length_thresh", C.c_float),
+                ("do_idepth_triangle_filter", C.c_int32), ("min_triangle_idepth", C.c_float)]
+
+
 class GraphOut(C.Structure):
     _fields_ = [(k, f32p) for k in ("x", "w1", "w2", "x_bar", "w1_bar", "w2_bar", "x_prev",
                                     "w1_prev", "w2_prev", "alpha", "beta", "q1", "q2", "q3")]
@@ -95,6 +103,7 @@ SYMBOLS = [
     "flame_b200_graph_project", "flame_b200_graph_resync", "flame_b200_pd_run", "flame_b200_pd_wave",
     "flame_b200_pd_cost", "flame_b200_interpolate_mesh", "flame_b200_mesh_bind",
     "flame_b200_mesh_project", "flame_b200_mesh_download", "flame_b200_process_frame",
+    "flame_b200_tri_filter_default_params", "flame_b200_mesh_filter", "flame_b200_mesh_coverage",
     "flame_b200_track_default_params",
     "flame_b200_set_camera", "flame_b200_frame_upload", "flame_b200_frame_upload_raw",
     "flame_b200_frame_download", "flame_b200_update_feature_idepths",
@@ -139,6 +148,10 @@ def lib():
     L.flame_b200_mesh_bind.argtypes = [vp, C.c_int, C.c_int32, i32p, u8p, u8p, C.c_int, C.c_int]
     L.flame_b200_mesh_project.argtypes = [vp, C.c_int, C.c_int, C.c_float]
     L.flame_b200_mesh_download.argtypes = [vp, C.c_int, vp]
+    L.flame_b200_tri_filter_default_params.argtypes = [C.POINTER(TriFilterParams)]
+    L.flame_b200_tri_filter_default_params.restype = None
+    L.flame_b200_mesh_filter.argtypes = [vp, C.c_int, C.POINTER(TriFilterParams), f32p, C.c_float, u8p, C.c_int]
+    L.flame_b200_mesh_coverage.argtypes = [vp, C.c_int, C.POINTER(C.c_int64)]
     L.flame_b200_process_frame.argtypes = [vp, C.c_int, C.c_int32, f32p, f32p, f32p, C.c_int32, i32p, C.c_int32,
                                            i32p, C.c_int, C.c_int, C.POINTER(PDParams), C.c_int, C.c_float,
                                            vp, f32p, f32p, f32p]
@@ -356,6 +369,21 @@ class Context:
     def mesh_download(self, slot, out):
         """Asynchronous; out: numpy array (ideally PinnedArray.array). Complete after sync()."""
         check(lib().flame_b200_mesh_download(self._h, slot, out.ctypes.data_as(C.c_void_p)))
+
+    def mesh_filter(self, slot, T, Kinv, params=None, scale=1.0, apply=True, want=True):
+        """Display filters of flame.cc:389-407 on the slot's mesh; returns tri_validity (u8[T]) if want."""
+        if params is None:
+            params = TriFilterParams()
+            lib().flame_b200_tri_filter_default_params(C.byref(params))
+        Kinv = np.ascontiguousarray(Kinv, np.float32).ravel()
+        out = np.empty(T, np.uint8) if want else None
+        check(lib().flame_b200_mesh_filter(self._h, slot, C.byref(params), fptr(Kinv), scale, bptr(out), int(apply)))
+        return out
+
+    def mesh_coverage(self, slot):
+        n = C.c_int64(0)
+        check(lib().flame_b200_mesh_coverage(self._h, slot, C.byref(n)))
+        return n.value
 
     def process_frame(self, slot, pos, idepth, edges, tris, rows, cols, params, n_iters, out_map, out_x,
                       out_w1=None, out_w2=None, weight=None, scale=1.0):

@@ -56,6 +56,7 @@ struct Slot {
   size_t bound_pix = 0;             // rows*cols of the last bind (owner words are per linear pixel)
   int* d_tris = nullptr;            // owning pointers behind the const views in `m`
   unsigned char* d_tri_ok = nullptr;
+  unsigned char* d_tri_filt = nullptr;  // flame_b200_mesh_filter result (capT bytes)
   float* d_mpos = nullptr;          // interpolate_mesh(): caller-supplied pos / values
   float* d_mvalues = nullptr;
   int capMV = 0;
@@ -551,7 +552,7 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
     for (void* p : {(void*)s.g.vprim, (void*)s.g.vbar, (void*)s.g.vbar2, (void*)s.g.vprev,
                     (void*)s.g.vwt, (void*)s.g.inc_q, (void*)s.g.inc_s, (void*)s.d_blob,
                     (void*)s.d_pos, (void*)s.d_values,
-                    (void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.m.img, (void*)s.m.setup,
+                    (void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.d_tri_filt, (void*)s.m.img, (void*)s.m.setup,
                     (void*)s.m.owner,
                     (void*)s.m.big, (void*)s.m.counters, (void*)s.d_mpos, (void*)s.d_mvalues,
                     (void*)s.d_carry})
@@ -1026,10 +1027,11 @@ static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* 
   }
   if (T > s.capT) {
     const int n = std::max(T, s.capT + s.capT / 2);
-    for (void* p : {(void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.m.setup, (void*)s.m.big})
+    for (void* p : {(void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.d_tri_filt, (void*)s.m.setup, (void*)s.m.big})
       if (p) FB_CUDA(cudaFree(p));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_tris), (size_t)n * 3 * sizeof(int)));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_tri_ok), (size_t)n));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_tri_filt), (size_t)n));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.setup), (size_t)n * sizeof(TriSetup)));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.big), (size_t)n * sizeof(int)));
     s.capT = n;
@@ -1057,6 +1059,7 @@ static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* 
   }
   s.m.tris = s.d_tris;
   s.m.tri_ok = s.d_tri_ok;
+  s.m.tri_filt = nullptr;  // a new triangulation starts unfiltered
   s.m.T = T;
   s.m.rows = rows;
   s.m.cols = cols;
@@ -1157,6 +1160,72 @@ int flame_b200_mesh_download(flame_b200_ctx* c, int slot, float* out_host) {
   }
   FB_CUDA(cudaMemcpyAsync(out_host, s.m.img, (size_t)s.m.rows * s.m.cols * sizeof(float),
                           cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+
+void flame_b200_tri_filter_default_params(flame_b200_tri_filter_params* p) {
+  if (!p) return;
+  p->do_oblique_triangle_filter = 1;  // params.h:70-85
+  p->oblique_normal_thresh = 1.39626f;
+  p->oblique_idepth_diff_factor = 0.35f;
+  p->oblique_idepth_diff_abs = 0.1f;
+  p->do_edge_length_filter = 1;
+  p->edge_length_thresh = 0.333f;
+  p->do_idepth_triangle_filter = 1;
+  p->min_triangle_idepth = 0.01f;
+}
+
+int flame_b200_mesh_filter(flame_b200_ctx* c, int slot, const flame_b200_tri_filter_params* params,
+                           const float Kinv[9], float scale, uint8_t* tri_valid_out, int apply) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (!params || !Kinv) {
+    set_error("mesh_filter: bad arguments");
+    return FLAME_B200_EINVAL;
+  }
+  if (int rc = use_device(c)) return rc;
+  if (int rc = join_range(c, slot, slot + 1)) return rc;
+  Slot& s = c->slots[slot];
+  if (!s.loaded || !s.m.img || s.m.values != s.d_values || s.m.pos != s.d_pos) {
+    set_error("mesh_filter: slot has no graph / bound mesh");
+    return FLAME_B200_ESTATE;
+  }
+  const int T = s.m.T;
+  if (int rc = raster_values_from_graph(c->stream, c->d_graphs + slot, c->d_meshes + slot, 1, s.g.V, scale))
+    return rc;
+  if (int rc = raster_tri_filter(c->stream, s.m, *params, Kinv, s.d_tri_filt)) return rc;
+  if (apply) {
+    s.m.tri_filt = s.d_tri_filt;
+    if (int rc = publish_mesh(c, slot)) return rc;
+  }
+  if (tri_valid_out && T > 0) {
+    if (int rc = wait_blob(s)) return rc;
+    if ((size_t)T > s.h_blob_cap) {
+      set_error("internal: staging blob too small");
+      return FLAME_B200_ENOMEM;
+    }
+    FB_CUDA(cudaMemcpyAsync(s.h_blob, s.d_tri_filt, (size_t)T, cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    std::memcpy(tri_valid_out, s.h_blob, (size_t)T);
+  }
+  return 0;
+}
+
+int flame_b200_mesh_coverage(flame_b200_ctx* c, int slot, int64_t* covered) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (!covered) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  if (int rc = join_range(c, slot, slot + 1)) return rc;
+  Slot& s = c->slots[slot];
+  if (!s.m.img) {
+    set_error("mesh_coverage: no dense map in this slot");
+    return FLAME_B200_ESTATE;
+  }
+  unsigned long long* d_count = reinterpret_cast<unsigned long long*>(c->d_cost);
+  if (int rc = raster_coverage(c->stream, s.m, d_count)) return rc;
+  FB_CUDA(cudaMemcpyAsync(c->h_cost, c->d_cost, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(cudaStreamSynchronize(c->stream));
+  *covered = (int64_t)*reinterpret_cast<unsigned long long*>(c->h_cost);
   return 0;
 }
 

@@ -70,6 +70,7 @@ struct MeshDev {
   int T, rows, cols, pad;
   const int* tris;             // 3T caller vertex indices
   const unsigned char* tri_ok; // T: tri_valid && all three vtx_valid (nullable)
+  const unsigned char* tri_filt; // T: display filters of flame_b200_mesh_filter (nullable)
   const float* pos;            // 2V caller order
   float* values;               // V caller order
   float* img;                  // rows*cols
@@ -123,6 +124,9 @@ inline size_t raw_f_total(int V, int E) { return (size_t)13 * V + (size_t)5 * E;
 
 // ---- dense projection (raster.cu) ----
 int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_pix, int fill_nan);
+int raster_tri_filter(cudaStream_t st, const MeshDev& m, const flame_b200_tri_filter_params& p,
+                      const float Kinv[9], unsigned char* out);
+int raster_coverage(cudaStream_t st, const MeshDev& m, unsigned long long* d_count);
 // values[vperm[v]] = vprim[v].x * scale  (vtx_idepths_ = x * graph_scale_, flame.cc:376)
 int raster_values_from_graph(cudaStream_t st, const GraphDev* gs_dev, const MeshDev* ms_dev, int n,
                              int maxV, float scale);

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) k_tri_setup(const MeshDev* __restrict__ m
   s.flags = 0;
   s.fx1 = -1;
   s.pad0 = s.pad1 = 0;
-  if (m.tri_ok && !m.tri_ok[t]) {
+  if ((m.tri_ok && !m.tri_ok[t]) || (m.tri_filt && !m.tri_filt[t])) {
     s.ymin = 1; s.ymax = 0; s.xmin = 0; s.xend = 0;  // empty footprint
     s.A1 = s.B1 = s.C1 = s.A2 = s.B2 = s.C2 = s.A3 = s.B3 = s.C3 = s.v1 = s.v2 = s.v3 = 0.0f;
     m.setup[t] = s;
@@ -299,6 +299,122 @@ int raster_values_from_graph(cudaStream_t st, const GraphDev* gs_dev, const Mesh
   if (maxV == 0 || n == 0) return 0;
   k_values_from_graph<<<dim3(std::min((maxV + 255) / 256, 64), n), 256, 0, st>>>(gs_dev, ms_dev, scale);
   count_launch();
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Display filters (Flame::obliqueTriangleFilter / edgeLengthFilter / idepthTriangleFilter,
+// flame.cc:2207-2356, combined as at flame.cc:389-407) and the coverage statistic (flame.cc:434-443)
+// ------------------------------------------------------------------------------------------
+struct TriFilterArgs {
+  flame_b200_tri_filter_params p;
+  float Kinv[9];
+};
+
+// p = Kinv * (x, y, 1) / idepth, Eigen's evaluation order (flame.cc:2226-2239)
+__device__ __forceinline__ void backproject(const float* Kinv, float x, float y, float id, float out[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float r = __fmul_rn(Kinv[3 * i], x);
+    r = __fadd_rn(r, __fmul_rn(Kinv[3 * i + 1], y));
+    r = __fadd_rn(r, __fmul_rn(Kinv[3 * i + 2], 1.0f));
+    out[i] = __fdiv_rn(r, id);
+  }
+}
+__device__ __forceinline__ void normalize3(float v[3]) {  // Eigen 3.2: *this /= norm()
+  float n2 = __fmul_rn(v[0], v[0]);
+  n2 = __fadd_rn(n2, __fmul_rn(v[1], v[1]));
+  n2 = __fadd_rn(n2, __fmul_rn(v[2], v[2]));
+  const float n = __fsqrt_rn(n2);
+  v[0] = __fdiv_rn(v[0], n); v[1] = __fdiv_rn(v[1], n); v[2] = __fdiv_rn(v[2], n);
+}
+
+__global__ void __launch_bounds__(256) k_tri_filter(MeshDev m, TriFilterArgs a, unsigned char* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m.T) return;
+  const int ia = m.tris[3 * t], ib = m.tris[3 * t + 1], ic = m.tris[3 * t + 2];
+  const float id0 = m.values[ia], id1 = m.values[ib], id2 = m.values[ic];
+  const float ax = m.pos[2 * ia], ay = m.pos[2 * ia + 1];
+  const float bx = m.pos[2 * ib], by = m.pos[2 * ib + 1];
+  const float cx = m.pos[2 * ic], cy = m.pos[2 * ic + 1];
+  bool ok = true;
+  if (a.p.do_oblique_triangle_filter) {
+    float p0[3], p1[3], p2[3];
+    backproject(a.Kinv, ax, ay, id0, p0);
+    backproject(a.Kinv, bx, by, id1, p1);
+    backproject(a.Kinv, cx, cy, id2, p2);
+    const float d1[3] = {__fsub_rn(p1[0], p0[0]), __fsub_rn(p1[1], p0[1]), __fsub_rn(p1[2], p0[2])};
+    const float d2[3] = {__fsub_rn(p2[0], p0[0]), __fsub_rn(p2[1], p0[1]), __fsub_rn(p2[2], p0[2])};
+    float n[3] = {__fsub_rn(__fmul_rn(d1[1], d2[2]), __fmul_rn(d1[2], d2[1])),
+                  __fsub_rn(__fmul_rn(d1[2], d2[0]), __fmul_rn(d1[0], d2[2])),
+                  __fsub_rn(__fmul_rn(d1[0], d2[1]), __fmul_rn(d1[1], d2[0]))};
+    normalize3(n);
+    float ray[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ray[i] = __fdiv_rn(__fadd_rn(__fadd_rn(p0[i], p1[i]), p2[i]), 3.0f);
+    normalize3(ray);
+    float dot = __fmul_rn(ray[0], n[0]);
+    dot = __fadd_rn(dot, __fmul_rn(ray[1], n[1]));
+    dot = __fadd_rn(dot, __fmul_rn(ray[2], n[2]));
+    const float angle = fabsf(acosf(dot));  // libdevice acosf: within 2 ulp of libm's (see the test)
+    if (angle > a.p.oblique_normal_thresh) ok = false;
+    float min_id = (id0 < id1) ? id0 : id1;
+    min_id = (min_id < id2) ? min_id : id2;
+    float max_id = (id0 > id1) ? id0 : id1;
+    max_id = (max_id > id2) ? max_id : id2;
+    const float diff = __fsub_rn(max_id, min_id);
+    if (__fdiv_rn(diff, max_id) > a.p.oblique_idepth_diff_factor) ok = false;
+    if (diff > a.p.oblique_idepth_diff_abs) ok = false;
+  }
+  if (a.p.do_edge_length_filter) {
+    float thr = __fmul_rn(a.p.edge_length_thresh, (float)m.cols);
+    thr = __fmul_rn(thr, thr);
+    const float d01x = __fsub_rn(ax, bx), d01y = __fsub_rn(ay, by);
+    const float d02x = __fsub_rn(ax, cx), d02y = __fsub_rn(ay, cy);
+    const float d12x = __fsub_rn(bx, cx), d12y = __fsub_rn(by, cy);
+    const float dist01 = __fadd_rn(__fmul_rn(d01x, d01x), __fmul_rn(d01y, d01y));
+    const float dist02 = __fadd_rn(__fmul_rn(d02x, d02x), __fmul_rn(d02y, d02y));
+    const float dist12 = __fadd_rn(__fmul_rn(d12x, d12x), __fmul_rn(d12y, d12y));
+    if (dist01 > thr || dist02 > thr || dist12 > thr) ok = false;
+  }
+  if (a.p.do_idepth_triangle_filter) {
+    const float mean = __fdiv_rn(__fadd_rn(__fadd_rn(id0, id1), id2), 3.0f);
+    if (mean < a.p.min_triangle_idepth) ok = false;
+  }
+  out[t] = ok ? 1 : 0;
+}
+
+int raster_tri_filter(cudaStream_t st, const MeshDev& m, const flame_b200_tri_filter_params& p,
+                      const float Kinv[9], unsigned char* out) {
+  if (m.T == 0) return 0;
+  TriFilterArgs a;
+  a.p = p;
+  for (int i = 0; i < 9; ++i) a.Kinv[i] = Kinv[i];
+  k_tri_filter<<<(m.T + 255) / 256, 256, 0, st>>>(m, a, out);
+  count_launch();
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) k_coverage(MeshDev m, unsigned long long* __restrict__ count) {
+  const int n = m.rows * m.cols;
+  int mine = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float v = m.img[i];
+    mine += !(v != v);
+  }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(count, (unsigned long long)mine);
+}
+
+int raster_coverage(cudaStream_t st, const MeshDev& m, unsigned long long* d_count) {
+  FB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
+  const int n = m.rows * m.cols;
+  if (n > 0) {
+    k_coverage<<<std::min((n + 255) / 256, 148 * 8), 256, 0, st>>>(m, d_count);
+    count_launch();
+  }
   FB_CUDA(cudaGetLastError());
   return 0;
 }

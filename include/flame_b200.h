@@ -225,6 +225,35 @@ int flame_b200_mesh_project(flame_b200_ctx* ctx, int slot0, int n_slots, float s
  * complete after flame_b200_ctx_sync(). */
 int flame_b200_mesh_download(flame_b200_ctx* ctx, int slot, float* out_host);
 
+/* ---- display filters and coverage ----------------------------------------
+ * Flame::update filters triangles "for display" (flame.cc:389-407) and getFilteredInverseDepthMap
+ * (flame.h:217-228) projects the mesh again honouring them. */
+typedef struct { /* params.h:70-85 */
+  int32_t do_oblique_triangle_filter;
+  float oblique_normal_thresh;      /* max angle [rad] between the triangle normal and the viewing ray */
+  float oblique_idepth_diff_factor; /* (max - min) / max of the corner idepths                         */
+  float oblique_idepth_diff_abs;    /* max - min                                                       */
+  int32_t do_edge_length_filter;
+  float edge_length_thresh;         /* fraction of the image width                                     */
+  int32_t do_idepth_triangle_filter;
+  float min_triangle_idepth;
+} flame_b200_tri_filter_params;
+void flame_b200_tri_filter_default_params(flame_b200_tri_filter_params* p);
+
+/* Replaces obliqueTriangleFilter + edgeLengthFilter + idepthTriangleFilter (flame.cc:2207-2356) as combined
+ * at flame.cc:389-407, on the slot's bound mesh with vtx_idepths = x * scale of the slot's graph (flame.cc:376).
+ * tri_valid_out (T bytes, nullable) receives tri_validity_. apply != 0 installs the result on the device as the
+ * mesh's triangle validity (in addition to what mesh_bind was given) for the following projections - i.e.
+ * mesh_project then produces getFilteredInverseDepthMap's image; the next mesh_bind removes it.
+ * The angle test uses the GPU's acosf: a triangle whose angle is within a few ulp of the threshold can
+ * differ from libm's decision; everything else is exact. Synchronises if tri_valid_out != NULL. */
+int flame_b200_mesh_filter(flame_b200_ctx* ctx, int slot, const flame_b200_tri_filter_params* params,
+                           const float Kinv[9], float scale, uint8_t* tri_valid_out, int apply);
+
+/* The coverage statistic of flame.cc:434-443: number of non-NaN pixels of the slot's dense map.
+ * Synchronises. */
+int flame_b200_mesh_coverage(flame_b200_ctx* ctx, int slot, int64_t* covered);
+
 /* ---- the per-frame tail of Flame::update in one call (flame.cc:312-415): fresh graph from the
  *      features (syncGraph's init rule + edge weights), n_iters x step(), extraction of the smoothed
  *      vertex idepths (x * scale) and plane parameters, interpolateMesh into a NaN-initialised map.

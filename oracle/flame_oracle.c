@@ -261,6 +261,99 @@ void oracle_interpolate_mesh(int32_t T, const int32_t* tris, int32_t V, const fl
 }
 
 /* ====================================================================================
+ * Display filters — flame.cc:389-407, 2207-2356 (PARITY UNPINNED restatement, see header)
+ * ==================================================================================== */
+void oracle_tri_filter_default_params(oracle_tri_filter_params* p) { /* params.h:70-85 */
+  p->do_oblique_triangle_filter = 1;
+  p->oblique_normal_thresh = 1.39626f;
+  p->oblique_idepth_diff_factor = 0.35f;
+  p->oblique_idepth_diff_abs = 0.1f;
+  p->do_edge_length_filter = 1;
+  p->edge_length_thresh = 0.333f;
+  p->do_idepth_triangle_filter = 1;
+  p->min_triangle_idepth = 0.01f;
+}
+
+/* p = Kinv * (x, y, 1) / idepth (flame.cc:2226-2239) */
+static void backproject(const float Kinv[9], float x, float y, float id, float out[3]) {
+  for (int i = 0; i < 3; ++i) {
+    float r = Kinv[3 * i] * x;
+    r += Kinv[3 * i + 1] * y;
+    r += Kinv[3 * i + 2] * 1.0f;
+    out[i] = r / id;
+  }
+}
+
+static void normalize3(float v[3]) { /* Eigen 3.2: *this /= norm() */
+  float n2 = v[0] * v[0];
+  n2 += v[1] * v[1];
+  n2 += v[2] * v[2];
+  const float n = sqrtf(n2);
+  v[0] /= n; v[1] /= n; v[2] /= n;
+}
+
+void oracle_triangle_filters(const oracle_tri_filter_params* p, const float Kinv[9], int width, int32_t T,
+                             const int32_t* tris, const float* pos, const float* idepths,
+                             uint8_t* validity, float* angle_out) {
+  for (int32_t ii = 0; ii < T; ++ii) validity[ii] = 1; /* flame.cc:389 */
+  float dist_thresh2 = p->edge_length_thresh * width;  /* flame.cc:2298-2299 */
+  dist_thresh2 *= dist_thresh2;
+  for (int32_t ii = 0; ii < T; ++ii) {
+    const int32_t a = tris[3 * ii], b = tris[3 * ii + 1], c = tris[3 * ii + 2];
+    const float id0 = idepths[a], id1 = idepths[b], id2 = idepths[c];
+    if (angle_out) angle_out[ii] = 0.0f;
+    if (p->do_oblique_triangle_filter) { /* flame.cc:2220-2268 */
+      float p0[3], p1[3], p2[3];
+      backproject(Kinv, pos[2 * a], pos[2 * a + 1], id0, p0);
+      backproject(Kinv, pos[2 * b], pos[2 * b + 1], id1, p1);
+      backproject(Kinv, pos[2 * c], pos[2 * c + 1], id2, p2);
+      const float d1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+      const float d2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+      float n[3] = {d1[1] * d2[2] - d1[2] * d2[1], d1[2] * d2[0] - d1[0] * d2[2],
+                    d1[0] * d2[1] - d1[1] * d2[0]};
+      normalize3(n);
+      float ray[3] = {((p0[0] + p1[0]) + p2[0]) / 3, ((p0[1] + p1[1]) + p2[1]) / 3,
+                      ((p0[2] + p1[2]) + p2[2]) / 3};
+      normalize3(ray);
+      float dot = ray[0] * n[0];
+      dot += ray[1] * n[1];
+      dot += ray[2] * n[2];
+      const float angle = fabsf(acosf(dot));
+      if (angle_out) angle_out[ii] = angle;
+      if (angle > p->oblique_normal_thresh) validity[ii] = 0;
+      float min_id = (id0 < id1) ? id0 : id1;
+      min_id = (min_id < id2) ? min_id : id2;
+      float max_id = (id0 > id1) ? id0 : id1;
+      max_id = (max_id > id2) ? max_id : id2;
+      if ((max_id - min_id) / max_id > p->oblique_idepth_diff_factor) validity[ii] = 0;
+      if (max_id - min_id > p->oblique_idepth_diff_abs) validity[ii] = 0;
+    }
+    if (p->do_edge_length_filter) { /* flame.cc:2301-2317 */
+      const float d01x = pos[2 * a] - pos[2 * b], d01y = pos[2 * a + 1] - pos[2 * b + 1];
+      const float d02x = pos[2 * a] - pos[2 * c], d02y = pos[2 * a + 1] - pos[2 * c + 1];
+      const float d12x = pos[2 * b] - pos[2 * c], d12y = pos[2 * b + 1] - pos[2 * c + 1];
+      const float dist01 = d01x * d01x + d01y * d01y;
+      const float dist02 = d02x * d02x + d02y * d02y;
+      const float dist12 = d12x * d12x + d12y * d12y;
+      if ((dist01 > dist_thresh2) || (dist02 > dist_thresh2) || (dist12 > dist_thresh2)) validity[ii] = 0;
+    }
+    if (p->do_idepth_triangle_filter) { /* flame.cc:2341-2349 */
+      const float mean_idepth = (id0 + id1 + id2) / 3;
+      if (mean_idepth < p->min_triangle_idepth) validity[ii] = 0;
+    }
+  }
+}
+
+/* flame.cc:434-443 */
+int64_t oracle_coverage(int rows, int cols, const float* img) {
+  int64_t coverage = 0;
+  for (int ii = 0; ii < rows; ++ii)
+    for (int jj = 0; jj < cols; ++jj)
+      if (!isnan(img[(size_t)ii * cols + jj])) coverage++;
+  return coverage;
+}
+
+/* ====================================================================================
  * Image helpers — utils/image_utils.h:199-272, utils/image_utils.cc:269-371
  * ==================================================================================== */
 

@@ -77,6 +77,26 @@ void oracle_interpolate_mesh(int32_t T, const int32_t* tris, int32_t V, const fl
                              const float* values, const uint8_t* vtx_valid,
                              const uint8_t* tri_valid, float* img, int rows, int cols);
 
+/* ---- display filters (flame.cc:389-407) and the coverage statistic (flame.cc:434-443) ----
+ * PARITY UNPINNED: Flame::obliqueTriangleFilter / edgeLengthFilter / idepthTriangleFilter are static
+ * members inside flame.cc, which cannot be compiled here (OpenCV/Boost/Sophus); this is a restatement
+ * with Eigen 3.2's evaluation order (3x3 * 3x1 as ((a0 b0 + a1 b1) + a2 b2), normalize() = v / sqrt(
+ * squaredNorm), no zero check) and libm's acosf. */
+typedef struct { /* params.h:70-85 */
+  int32_t do_oblique_triangle_filter;
+  float oblique_normal_thresh, oblique_idepth_diff_factor, oblique_idepth_diff_abs;
+  int32_t do_edge_length_filter;
+  float edge_length_thresh;
+  int32_t do_idepth_triangle_filter;
+  float min_triangle_idepth;
+} oracle_tri_filter_params;
+void oracle_tri_filter_default_params(oracle_tri_filter_params* p);
+/* validity[T] (1 = keep); angle[T] (nullable) receives fabs(acos(ray . normal)) of the oblique test. */
+void oracle_triangle_filters(const oracle_tri_filter_params* p, const float Kinv[9], int width, int32_t T,
+                             const int32_t* tris, const float* pos, const float* idepths,
+                             uint8_t* validity, float* angle);
+int64_t oracle_coverage(int rows, int cols, const float* img);
+
 /* ---- image helpers: utils/image_utils.h:199-272, utils/image_utils.cc:269-371 ---- */
 float oracle_bilinear_u8(int rows, int cols, int step_bytes, const uint8_t* data, float x,
                          float y);

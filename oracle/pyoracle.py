@@ -220,6 +220,36 @@ def interpolate_mesh(tris, pos, values, rows, cols, vtx_valid=None, tri_valid=No
     return img
 
 
+class TriFilterParams(C.Structure):
+    _fields_ = [("do_oblique_triangle_filter", C.c_int32), ("oblique_normal_thresh", C.c_float),
+                ("oblique_idepth_diff_factor", C.c_float), ("oblique_idepth_diff_abs", C.c_float),
+                ("do_edge_length_filter", C.c_int32), ("edge_length_thresh", C.c_float),
+                ("do_idepth_triangle_filter", C.c_int32), ("min_triangle_idepth", C.c_float)]
+
+
+def tri_filter_default_params():
+    p = TriFilterParams()
+    lib().oracle_tri_filter_default_params(C.byref(p))
+    return p
+
+
+def triangle_filters(params, Kinv, width, tris, pos, idepths):
+    """flame.cc:389-407 (restatement, parity unpinned): returns (validity u8[T], angle f32[T])."""
+    T = tris.shape[0]
+    valid = np.empty(T, np.uint8)
+    angle = np.empty(T, np.float32)
+    Kinv = np.ascontiguousarray(Kinv, np.float32).ravel()
+    lib().oracle_triangle_filters(C.byref(params), _f(Kinv), C.c_int(width), C.c_int32(T), _i(tris), _f(pos),
+                                  _f(idepths), _u8(valid), _f(angle))
+    return valid, angle
+
+
+def coverage(img):
+    lib().oracle_coverage.restype = C.c_int64
+    img = np.ascontiguousarray(img, np.float32)
+    return int(lib().oracle_coverage(C.c_int(img.shape[0]), C.c_int(img.shape[1]), _f(img)))
+
+
 # ---------------------------------------------------------------------------- Delaunay (reference Triangle)
 def ref_delaunay(xy):
     """Shewchuk Triangle exactly as utils/delaunay.cc calls it. Returns (tris, edges, neighbors)."""

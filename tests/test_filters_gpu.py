@@ -1,0 +1,103 @@
+"""GPU parity for the display filters (flame.cc:389-407, 2207-2356) and the coverage statistic
+(flame.cc:434-443): flame_b200_mesh_filter / mesh_coverage vs the oracle restatement. Everything is exact
+except the angle test, which calls acosf (libdevice vs libm): a decision may differ only when the angle is
+within 4e-6 rad of the threshold."""
+import numpy as np
+import pytest
+
+from flame_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+ANGLE_TOL = 4e-6
+
+
+def _same_image(got, want):
+    gn, wn = np.isnan(got), np.isnan(want)
+    return np.array_equal(gn, wn) and np.array_equal(got[~gn].view(np.uint32), want[~wn].view(np.uint32))
+
+
+def _oracle_params(oracle, gp):
+    import ctypes
+    op = oracle.tri_filter_default_params()
+    ctypes.memmove(ctypes.byref(op), ctypes.byref(gp), ctypes.sizeof(op))
+    return op
+
+
+def _default():
+    p = _lib.TriFilterParams()
+    _lib.lib().flame_b200_tri_filter_default_params(p)
+    return p
+
+
+@pytest.mark.parametrize("variant", ["default", "oblique_only", "edge_only", "idepth_only", "scaled"])
+def test_filters_filtered_map_and_coverage(gpu_ctx, oracle, variant):
+    g = synth.config_graph("C")
+    W, H = g["W"], g["H"]
+    V, E, T = g["pos"].shape[0], g["edges"].shape[0], g["tris"].shape[0]
+    K, Kinv = synth.camera(W, H)
+    data = g["data_term"].copy()
+    data[::97] = 0.004   # some triangles below min_triangle_idepth
+    gp = _default()
+    scale = 1.0
+    if variant == "oblique_only":
+        gp.do_edge_length_filter = gp.do_idepth_triangle_filter = 0
+        gp.oblique_normal_thresh = 1.2
+    elif variant == "edge_only":
+        gp.do_oblique_triangle_filter = gp.do_idepth_triangle_filter = 0
+        gp.edge_length_thresh = 0.02
+    elif variant == "idepth_only":
+        gp.do_oblique_triangle_filter = gp.do_edge_length_filter = 0
+        gp.min_triangle_idepth = 0.4
+    elif variant == "scaled":
+        scale = 0.6
+    gpu_ctx.graph_init(2, g["pos"], data, g["edges"])
+    gpu_ctx.mesh_bind(2, g["tris"], H, W)
+    gpu_ctx.pd_run(_lib.default_pd_params(), 25, slot0=2)
+    x = gpu_ctx.graph_download(2, V, E, fields=("x",))["x"]
+    idepths = (x * np.float32(scale)).astype(np.float32)
+
+    got = gpu_ctx.mesh_filter(2, T, Kinv, gp, scale=scale, apply=True)
+    want, angle = oracle.triangle_filters(_oracle_params(oracle, gp), Kinv, W, g["tris"], g["pos"], idepths)
+    diff = np.flatnonzero(got != want)
+    assert 0 < want.sum() < T, "the filter should remove some, not all, triangles in this scene"
+    if diff.size:
+        assert gp.do_oblique_triangle_filter
+        assert np.all(np.abs(angle[diff] - gp.oblique_normal_thresh) < ANGLE_TOL), \
+            "%d decisions differ away from the acos threshold" % diff.size
+
+    # getFilteredInverseDepthMap (flame.h:217-228): the projection now honours the validity on the device
+    gpu_ctx.mesh_project(2, 1, scale)
+    out = _lib.PinnedArray((H, W))
+    gpu_ctx.mesh_download(2, out.array)
+    gpu_ctx.sync()
+    img = out.array.copy()
+    assert _same_image(img, oracle.interpolate_mesh(g["tris"], g["pos"], idepths, H, W, None, got))
+    assert gpu_ctx.mesh_coverage(2) == oracle.coverage(img) == int((~np.isnan(img)).sum())
+
+    # compute-only call leaves the installed validity alone; a new bind removes it
+    gp2 = _default()
+    gp2.do_oblique_triangle_filter = gp2.do_idepth_triangle_filter = 0
+    gp2.edge_length_thresh = 1e-4
+    none_valid = gpu_ctx.mesh_filter(2, T, Kinv, gp2, scale=scale, apply=False)
+    assert none_valid.sum() == 0
+    gpu_ctx.mesh_filter(2, T, Kinv, gp, scale=scale, apply=True, want=False)
+    gpu_ctx.mesh_project(2, 1, scale)
+    gpu_ctx.mesh_download(2, out.array)
+    gpu_ctx.sync()
+    assert _same_image(out.array, img)
+    gpu_ctx.mesh_bind(2, g["tris"], H, W)
+    gpu_ctx.mesh_project(2, 1, scale)
+    gpu_ctx.mesh_download(2, out.array)
+    gpu_ctx.sync()
+    assert _same_image(out.array.copy(), oracle.interpolate_mesh(g["tris"], g["pos"], idepths, H, W))
+    assert gpu_ctx.mesh_coverage(2) > oracle.coverage(img)
+
+
+def test_filter_errors(gpu_ctx):
+    K, Kinv = synth.camera(640, 480)
+    with _lib.Context(0, 1) as ctx:
+        with pytest.raises(_lib.FlameB200Error):
+            ctx.mesh_filter(0, 1, Kinv)
+        with pytest.raises(_lib.FlameB200Error):
+            ctx.mesh_coverage(0)

@@ -349,3 +349,32 @@ def test_oracle_clip_line_equals_reference_verbatim(oracle):
         assert o[0] == r[0]
         if o[0]:
             assert np.array_equal(np.float32(o[1]).view(np.uint32), np.float32(r[1]).view(np.uint32))
+
+
+def test_display_filter_restatement_sanity(oracle):
+    """flame.cc:2207-2356 (restatement, parity unpinned): hand-checkable cases."""
+    from flame_b200 import synth
+    K, Kinv = synth.camera(640, 480)
+    pos = np.array([[100, 100], [140, 100], [100, 140], [400, 100], [100, 300]], np.float32)
+    tris = np.array([[0, 1, 2], [0, 3, 4], [0, 1, 2]], np.int32)
+    p = oracle.tri_filter_default_params()
+    # fronto-parallel plane: the inward normal is the viewing direction up to the pixel's bearing
+    v, a = oracle.triangle_filters(p, Kinv, 640, tris, pos, np.full(5, 0.5, np.float32))
+    assert v.tolist() == [1, 0, 1]            # the second triangle has a 300-px edge > 0.333 * 640
+    for t in range(2):  # angle between the optical axis and the ray through the triangle's centroid
+        cx, cy = pos[tris[t]].mean(0)
+        want = np.arctan(np.hypot((cx - 320.0) / 525.0, (cy - 240.0) / 525.0))
+        assert abs(a[t] - want) < 1e-4
+    # one corner much closer: relative and absolute idepth spread exceed 0.35 / 0.1
+    v, _ = oracle.triangle_filters(p, Kinv, 640, tris, pos, np.array([0.5, 0.9, 0.5, 0.5, 0.5], np.float32))
+    assert v.tolist() == [0, 0, 0]
+    # mean idepth below min_triangle_idepth
+    v, _ = oracle.triangle_filters(p, Kinv, 640, tris, pos, np.full(5, 0.005, np.float32))
+    assert v.tolist() == [0, 0, 0]
+    p.do_idepth_triangle_filter = 0
+    v, _ = oracle.triangle_filters(p, Kinv, 640, tris, pos, np.full(5, 0.005, np.float32))
+    assert v.tolist() == [1, 0, 1]
+    img = np.full((4, 5), np.nan, np.float32)
+    img[1, 2] = 0.0
+    img[3, 4] = 7.0
+    assert oracle.coverage(img) == 2
