@@ -54,9 +54,12 @@ struct Slot {
   int capT = 0;
   size_t cap_pix = 0;
   size_t bound_pix = 0;             // rows*cols of the last bind (owner words are per linear pixel)
+  int mesh_V = -1;                  // vertex count the triangle indices were validated against at bind time
   int* d_tris = nullptr;            // owning pointers behind the const views in `m`
   unsigned char* d_tri_ok = nullptr;
   unsigned char* d_tri_filt = nullptr;  // flame_b200_mesh_filter result (capT bytes)
+  int* d_vt = nullptr;                  // flame_b200_mesh_normals scratch: vertex -> triangle lists
+  size_t vt_cap = 0;                    // ints
   float* d_mpos = nullptr;          // interpolate_mesh(): caller-supplied pos / values
   float* d_mvalues = nullptr;
   int capMV = 0;
@@ -555,7 +558,7 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
                     (void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.d_tri_filt, (void*)s.m.img, (void*)s.m.setup,
                     (void*)s.m.owner,
                     (void*)s.m.big, (void*)s.m.counters, (void*)s.d_mpos, (void*)s.d_mvalues,
-                    (void*)s.d_carry})
+                    (void*)s.d_carry, (void*)s.d_vt})
       if (p) cudaFree(p);
     if (s.h_blob) cudaFreeHost(s.h_blob);
     if (s.blob_free) cudaEventDestroy(s.blob_free);
@@ -1103,6 +1106,7 @@ int flame_b200_mesh_bind(flame_b200_ctx* c, int slot, int32_t T, const int32_t* 
   if (int rc = mesh_bind_impl(c, s, T, tris, s.g.V, vtx_valid, tri_valid, rows, cols)) return rc;
   s.m.pos = s.d_pos;
   s.m.values = s.d_values;
+  s.mesh_V = s.g.V;
   return publish_mesh(c, slot);
 }
 
@@ -1114,6 +1118,10 @@ int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float sca
     Slot& s = c->slots[i];
     if (!s.loaded || !s.m.img || s.m.values != s.d_values || s.m.pos != s.d_pos) {
       set_error("mesh_project: slot has no graph / bound mesh");
+      return FLAME_B200_ESTATE;
+    }
+    if (s.mesh_V != s.g.V) {
+      set_error("mesh_project: the graph changed size since mesh_bind; bind the new triangulation first");
       return FLAME_B200_ESTATE;
     }
     maxV = std::max(maxV, s.g.V);
@@ -1185,8 +1193,8 @@ int flame_b200_mesh_filter(flame_b200_ctx* c, int slot, const flame_b200_tri_fil
   if (int rc = use_device(c)) return rc;
   if (int rc = join_range(c, slot, slot + 1)) return rc;
   Slot& s = c->slots[slot];
-  if (!s.loaded || !s.m.img || s.m.values != s.d_values || s.m.pos != s.d_pos) {
-    set_error("mesh_filter: slot has no graph / bound mesh");
+  if (!s.loaded || !s.m.img || s.m.values != s.d_values || s.m.pos != s.d_pos || s.mesh_V != s.g.V) {
+    set_error("mesh_filter: slot has no graph / mesh bound to the current graph");
     return FLAME_B200_ESTATE;
   }
   const int T = s.m.T;
@@ -1208,6 +1216,39 @@ int flame_b200_mesh_filter(flame_b200_ctx* c, int slot, const flame_b200_tri_fil
     FB_CUDA(cudaStreamSynchronize(c->stream));
     std::memcpy(tri_valid_out, s.h_blob, (size_t)T);
   }
+  return 0;
+}
+
+int flame_b200_mesh_normals(flame_b200_ctx* c, int slot, const float Kinv[9], float scale, float* normals_out) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (!Kinv || !normals_out) {
+    set_error("mesh_normals: bad arguments");
+    return FLAME_B200_EINVAL;
+  }
+  if (int rc = use_device(c)) return rc;
+  if (int rc = join_range(c, slot, slot + 1)) return rc;
+  Slot& s = c->slots[slot];
+  if (!s.loaded || !s.m.img || s.m.values != s.d_values || s.m.pos != s.d_pos || s.mesh_V != s.g.V) {
+    set_error("mesh_normals: slot has no graph / mesh bound to the current graph");
+    return FLAME_B200_ESTATE;
+  }
+  const int V = s.g.V, T = s.m.T;
+  if (V == 0) return 0;
+  const size_t need = (size_t)2 * (V + 1) + (size_t)3 * T;
+  if (need > s.vt_cap) {
+    if (s.d_vt) FB_CUDA(cudaFree(s.d_vt));
+    s.d_vt = nullptr;
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_vt), need * sizeof(int)));
+    s.vt_cap = need;
+  }
+  if (int rc = wait_blob(s)) return rc;
+  if (int rc = raster_values_from_graph(c->stream, c->d_graphs + slot, c->d_meshes + slot, 1, V, scale)) return rc;
+  // the raw staging area (>= 13V floats) is scratch between uploads
+  if (int rc = raster_vertex_normals(c->stream, s.m, V, Kinv, s.d_vt, s.d_raw())) return rc;
+  FB_CUDA(cudaMemcpyAsync(s.h_blob, s.d_blob, (size_t)3 * V * 4, cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
+  FB_CUDA(cudaStreamSynchronize(c->stream));
+  std::memcpy(normals_out, s.h_blob, (size_t)3 * V * 4);
   return 0;
 }
 

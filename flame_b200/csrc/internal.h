@@ -127,6 +127,8 @@ int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int 
 int raster_tri_filter(cudaStream_t st, const MeshDev& m, const flame_b200_tri_filter_params& p,
                       const float Kinv[9], unsigned char* out);
 int raster_coverage(cudaStream_t st, const MeshDev& m, unsigned long long* d_count);
+int raster_vertex_normals(cudaStream_t st, const MeshDev& m, int V, const float Kinv[9], int* scratch,
+                          float* d_normals);
 // values[vperm[v]] = vprim[v].x * scale  (vtx_idepths_ = x * graph_scale_, flame.cc:376)
 int raster_values_from_graph(cudaStream_t st, const GraphDev* gs_dev, const MeshDev* ms_dev, int n,
                              int maxV, float scale);

@@ -397,6 +397,136 @@ int raster_tri_filter(cudaStream_t st, const MeshDev& m, const flame_b200_tri_fi
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Flame::getVertexNormals (flame.cc:2554-2640): per vertex, the running average of the outward normals of
+// its triangles IN TRIANGLE ORDER, re-normalised after every update. Vertex -> triangle lists are built on
+// the device (count / scan / fill); a vertex thread walks its list in ascending triangle id.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_vt_count(MeshDev m, int* __restrict__ cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 3 * m.T) atomicAdd(&cnt[m.tris[i]], 1);
+}
+
+// one CTA of 1024 threads: exclusive scan of cnt[0..n) into off[0..n], zero cnt (reused as fill cursor)
+__global__ void __launch_bounds__(1024) k_vt_scan(int* __restrict__ cnt, int* __restrict__ off, int n) {
+  __shared__ int s_warp[32];
+  __shared__ int s_run;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_run = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int c = (i < n) ? cnt[i] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += v;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int run = s_run;
+    if (i < n) {
+      off[i] = run + (warp > 0 ? s_warp[warp - 1] : 0) + incl - c;
+      cnt[i] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) s_run = run + s_warp[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) off[n] = s_run;
+}
+
+__global__ void __launch_bounds__(256) k_vt_fill(MeshDev m, int* __restrict__ cursor, const int* __restrict__ off,
+                                                 int* __restrict__ list) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * m.T) return;
+  const int v = m.tris[i];
+  list[off[v] + atomicAdd(&cursor[v], 1)] = i / 3;
+}
+
+__global__ void __launch_bounds__(128) k_vertex_normals(MeshDev m, TriFilterArgs a, int V,
+                                                        const int* __restrict__ off, const int* __restrict__ list,
+                                                        float* __restrict__ normals) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  float nx = 0.0f, ny = 0.0f, nz = 0.0f;
+  int count = 0, last = -1;
+  const int b = off[v], e = off[v + 1];
+  for (int step = b; step < e; ++step) {
+    int t = 0x7fffffff;  // next triangle of this vertex in ascending id (lists are short: selection)
+    for (int j = b; j < e; ++j) {
+      const int c = list[j];
+      if (c > last && c < t) t = c;
+    }
+    if (t == 0x7fffffff) break;  // a triangle that names the vertex twice appears twice in the list
+    last = t;
+    const int ia = m.tris[3 * t], ib = m.tris[3 * t + 1], ic = m.tris[3 * t + 2];
+    const float id0 = m.values[ia], id1 = m.values[ib], id2 = m.values[ic];
+    if ((id0 <= 0) || (id1 <= 0) || (id2 <= 0)) continue;
+    float p0[3], p1[3], p2[3];
+    backproject(a.Kinv, m.pos[2 * ia], m.pos[2 * ia + 1], id0, p0);
+    backproject(a.Kinv, m.pos[2 * ib], m.pos[2 * ib + 1], id1, p1);
+    backproject(a.Kinv, m.pos[2 * ic], m.pos[2 * ic + 1], id2, p2);
+    const float d1[3] = {__fsub_rn(p1[0], p0[0]), __fsub_rn(p1[1], p0[1]), __fsub_rn(p1[2], p0[2])};
+    const float d2[3] = {__fsub_rn(p2[0], p0[0]), __fsub_rn(p2[1], p0[1]), __fsub_rn(p2[2], p0[2])};
+    float n[3] = {__fsub_rn(__fmul_rn(d2[1], d1[2]), __fmul_rn(d2[2], d1[1])),
+                  __fsub_rn(__fmul_rn(d2[2], d1[0]), __fmul_rn(d2[0], d1[2])),
+                  __fsub_rn(__fmul_rn(d2[0], d1[1]), __fmul_rn(d2[1], d1[0]))};  // delta2 x delta1: outward
+    normalize3(n);
+    // a triangle that lists this vertex k times updates it k times (flame.cc:2607-2625)
+    const int reps = (ia == v) + (ib == v) + (ic == v);
+    for (int r = 0; r < reps; ++r) {
+      const float c = (float)count, c1 = (float)(count + 1);
+      float nv[3] = {__fdiv_rn(__fadd_rn(__fmul_rn(c, nx), n[0]), c1), __fdiv_rn(__fadd_rn(__fmul_rn(c, ny), n[1]), c1),
+                     __fdiv_rn(__fadd_rn(__fmul_rn(c, nz), n[2]), c1)};
+      normalize3(nv);
+      nx = nv[0]; ny = nv[1]; nz = nv[2];
+      ++count;
+    }
+  }
+  normals[3 * (size_t)v] = nx;
+  normals[3 * (size_t)v + 1] = ny;
+  normals[3 * (size_t)v + 2] = nz;
+}
+
+// scratch: 2 (V + 1) + 3 T ints [cnt | off | list]
+int raster_vertex_normals(cudaStream_t st, const MeshDev& m, int V, const float Kinv[9], int* scratch,
+                          float* d_normals) {
+  if (V == 0) return 0;
+  int* cnt = scratch;
+  int* off = scratch + (V + 1);
+  int* list = off + (V + 1);
+  FB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(V + 1) * sizeof(int), st));
+  if (m.T > 0) {
+    k_vt_count<<<(3 * m.T + 255) / 256, 256, 0, st>>>(m, cnt);
+    count_launch();
+  }
+  k_vt_scan<<<1, 1024, 0, st>>>(cnt, off, V);
+  count_launch();
+  if (m.T > 0) {
+    k_vt_fill<<<(3 * m.T + 255) / 256, 256, 0, st>>>(m, cnt, off, list);
+    count_launch();
+  }
+  TriFilterArgs a;
+  flame_b200_tri_filter_default_params(&a.p);
+  for (int i = 0; i < 9; ++i) a.Kinv[i] = Kinv[i];
+  k_vertex_normals<<<(V + 127) / 128, 128, 0, st>>>(m, a, V, off, list, d_normals);
+  count_launch();
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 __global__ void __launch_bounds__(256) k_coverage(MeshDev m, unsigned long long* __restrict__ count) {
   const int n = m.rows * m.cols;
   int mine = 0;

@@ -250,6 +250,12 @@ void flame_b200_tri_filter_default_params(flame_b200_tri_filter_params* p);
 int flame_b200_mesh_filter(flame_b200_ctx* ctx, int slot, const flame_b200_tri_filter_params* params,
                            const float Kinv[9], float scale, uint8_t* tri_valid_out, int apply);
 
+/* Replaces Flame::getVertexNormals (flame.cc:2554-2640, called at flame.cc:385): per vertex the running,
+ * re-normalised average of the outward normals of its triangles in triangle order, with
+ * vtx_idepths = x * scale of the slot's graph; triangles with a non-positive corner idepth are skipped.
+ * normals_out: 3V floats (x, y, z per vertex, caller order). Synchronises. */
+int flame_b200_mesh_normals(flame_b200_ctx* ctx, int slot, const float Kinv[9], float scale, float* normals_out);
+
 /* The coverage statistic of flame.cc:434-443: number of non-NaN pixels of the slot's dense map.
  * Synchronises. */
 int flame_b200_mesh_coverage(flame_b200_ctx* ctx, int slot, int64_t* covered);

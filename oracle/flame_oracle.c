@@ -344,6 +344,38 @@ void oracle_triangle_filters(const oracle_tri_filter_params* p, const float Kinv
   }
 }
 
+/* flame.cc:2554-2640: running average of the (outward) normals of the triangles around each vertex, in
+ * triangle order, re-normalised after every update */
+void oracle_vertex_normals(const float Kinv[9], int32_t V, const float* pos, const float* idepths, int32_t T,
+                           const int32_t* tris, float* normals) {
+  int* counts = (int*)calloc((size_t)(V > 0 ? V : 1), sizeof(int));
+  for (int32_t ii = 0; ii < 3 * V; ++ii) normals[ii] = 0.0f;
+  for (int32_t ii = 0; ii < T; ++ii) {
+    const int32_t v[3] = {tris[3 * ii], tris[3 * ii + 1], tris[3 * ii + 2]};
+    const float id0 = idepths[v[0]], id1 = idepths[v[1]], id2 = idepths[v[2]];
+    if ((id0 <= 0) || (id1 <= 0) || (id2 <= 0)) continue;
+    float p0[3], p1[3], p2[3];
+    backproject(Kinv, pos[2 * v[0]], pos[2 * v[0] + 1], id0, p0);
+    backproject(Kinv, pos[2 * v[1]], pos[2 * v[1] + 1], id1, p1);
+    backproject(Kinv, pos[2 * v[2]], pos[2 * v[2] + 1], id2, p2);
+    const float d1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+    const float d2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+    float n[3] = {d2[1] * d1[2] - d2[2] * d1[1], d2[2] * d1[0] - d2[0] * d1[2],
+                  d2[0] * d1[1] - d2[1] * d1[0]}; /* delta2.cross(delta1): outward */
+    normalize3(n);
+    for (int k = 0; k < 3; ++k) {
+      float* nv = normals + 3 * (size_t)v[k];
+      const float c = (float)counts[v[k]], c1 = (float)(counts[v[k]] + 1);
+      nv[0] = (c * nv[0] + n[0]) / c1;
+      nv[1] = (c * nv[1] + n[1]) / c1;
+      nv[2] = (c * nv[2] + n[2]) / c1;
+      normalize3(nv);
+      counts[v[k]]++;
+    }
+  }
+  free(counts);
+}
+
 /* flame.cc:434-443 */
 int64_t oracle_coverage(int rows, int cols, const float* img) {
   int64_t coverage = 0;

@@ -96,6 +96,9 @@ void oracle_triangle_filters(const oracle_tri_filter_params* p, const float Kinv
                              const int32_t* tris, const float* pos, const float* idepths,
                              uint8_t* validity, float* angle);
 int64_t oracle_coverage(int rows, int cols, const float* img);
+/* Flame::getVertexNormals (flame.cc:2554-2640), same caveat (PARITY UNPINNED). normals: 3V floats. */
+void oracle_vertex_normals(const float Kinv[9], int32_t V, const float* pos, const float* idepths, int32_t T,
+                           const int32_t* tris, float* normals);
 
 /* ---- image helpers: utils/image_utils.h:199-272, utils/image_utils.cc:269-371 ---- */
 float oracle_bilinear_u8(int rows, int cols, int step_bytes, const uint8_t* data, float x,

@@ -244,6 +244,16 @@ def triangle_filters(params, Kinv, width, tris, pos, idepths):
     return valid, angle
 
 
+def vertex_normals(Kinv, pos, idepths, tris):
+    """Flame::getVertexNormals (flame.cc:2554-2640), restatement (parity unpinned): [V, 3] float32."""
+    V = pos.shape[0]
+    out = np.empty((V, 3), np.float32)
+    Kinv = np.ascontiguousarray(Kinv, np.float32).ravel()
+    lib().oracle_vertex_normals(_f(Kinv), C.c_int32(V), _f(pos), _f(idepths), C.c_int32(tris.shape[0]), _i(tris),
+                                _f(out))
+    return out
+
+
 def coverage(img):
     lib().oracle_coverage.restype = C.c_int64
     img = np.ascontiguousarray(img, np.float32)

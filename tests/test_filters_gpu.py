@@ -101,3 +101,29 @@ def test_filter_errors(gpu_ctx):
             ctx.mesh_filter(0, 1, Kinv)
         with pytest.raises(_lib.FlameB200Error):
             ctx.mesh_coverage(0)
+
+
+@pytest.mark.parametrize("iters", [0, 25])
+def test_vertex_normals_match_oracle(gpu_ctx, oracle, iters):
+    """flame_b200_mesh_normals vs the restated Flame::getVertexNormals (flame.cc:2554-2640): only IEEE
+    mul/add/div/sqrt are involved, so the comparison is bit-for-bit (NaN == NaN)."""
+    g = synth.config_graph("C")
+    W, H = g["W"], g["H"]
+    V, E = g["pos"].shape[0], g["edges"].shape[0]
+    K, Kinv = synth.camera(W, H)
+    data = g["data_term"].copy()
+    data[::41] = 0.0  # triangles with a non-positive corner idepth are skipped (flame.cc:2586-2588)
+    for scale in (1.0, 0.8):
+        gpu_ctx.graph_init(2, g["pos"], data, g["edges"])
+        gpu_ctx.mesh_bind(2, g["tris"], H, W)
+        gpu_ctx.pd_run(_lib.default_pd_params(), iters, slot0=2)
+        x = gpu_ctx.graph_download(2, V, E, fields=("x",))["x"]
+        got = gpu_ctx.mesh_normals(2, V, Kinv, scale)
+        want = oracle.vertex_normals(Kinv, g["pos"], (x * np.float32(scale)).astype(np.float32), g["tris"])
+        gn, wn = np.isnan(got), np.isnan(want)
+        assert np.array_equal(gn, wn)
+        assert np.array_equal(got[~gn].view(np.uint32), want[~wn].view(np.uint32))
+        if iters == 0:
+            assert (np.abs(want).sum(1) == 0).any()  # vertices all of whose triangles were skipped
+        norms = np.linalg.norm(want[~wn.any(1) & (np.abs(want).sum(1) > 0)], axis=1)
+        assert np.allclose(norms, 1.0, atol=1e-5)

@@ -153,6 +153,15 @@ def test_graph_resync_grow_shrink_and_errors(gpu_ctx, oracle):
     gpu_ctx.pd_run(p, 6, slot0=4)
     oracle.pd_run(want, oracle.pd_default_params(), 6)
     _assert_state(gpu_ctx.graph_download(4, V, E), want, STATE + ("alpha", "beta"))
+    # a mesh bound before the sync refers to the old vertex set: projecting it must be refused
+    gpu_ctx.mesh_bind(4, big["tris"], big["H"], big["W"])
+    gpu_ctx.mesh_project(4, 1, 1.0)
+    gpu_ctx.graph_resync(4, small["pos"], small["data_term"], small["edges"], np.full(300, -1, np.int32),
+                         np.full(small["edges"].shape[0], -1, np.int32))
+    with pytest.raises(_lib.FlameB200Error):
+        gpu_ctx.mesh_project(4, 1, 1.0)
+    gpu_ctx.graph_resync(4, big["pos"], big["data_term"], big["edges"], vtx_from, edge_from)  # not carried: new state
+    gpu_ctx.graph_upload(4, dict(want, data_weight=np.ones(V, np.float32)))
     # out-of-range maps are rejected and leave the slot usable
     bad = vtx_from.copy()
     bad[7] = V

@@ -378,3 +378,23 @@ def test_display_filter_restatement_sanity(oracle):
     img[1, 2] = 0.0
     img[3, 4] = 7.0
     assert oracle.coverage(img) == 2
+
+
+def test_vertex_normals_restatement_sanity(oracle):
+    """flame.cc:2554-2640 (restatement, parity unpinned): a fronto-parallel mesh has outward normals
+    (0, 0, -1); a plane tilted about the vertical axis tilts them in x only."""
+    from flame_b200 import synth
+    g = synth.config_graph("A")
+    K, Kinv = synth.camera(g["W"], g["H"])
+    V = g["pos"].shape[0]
+    n = oracle.vertex_normals(Kinv, g["pos"], np.full(V, 0.5, np.float32), g["tris"])
+    assert np.allclose(n, [0, 0, -1], atol=1e-4)
+    # plane z = z0 + s * X  <=>  idepth(u) = (1 - s * (u - cx) / f) / z0 : normal proportional to (s, 0, -1)
+    s_, z0 = 0.3, 2.0
+    idepth = ((1.0 - s_ * (g["pos"][:, 0] - 320.0) / 525.0) / z0).astype(np.float32)
+    n = oracle.vertex_normals(Kinv, g["pos"], idepth, g["tris"])
+    want = np.array([s_, 0.0, -1.0]) / np.hypot(s_, 1.0)
+    assert np.allclose(n, want, atol=2e-3)
+    idepth[::3] = 0.0  # every triangle touching such a vertex is skipped
+    n = oracle.vertex_normals(Kinv, g["pos"], idepth, g["tris"])
+    assert np.all(n[::3] == 0)
