@@ -101,3 +101,37 @@ def test_oracle_edge_weights(oracle):
     edges = np.array([[0, 1], [2, 0]], np.int32)
     a, b = oracle.edge_weights(edges, pos)
     assert np.allclose(a, [0.2, 0.1]) and np.all(b == 1)
+
+
+def test_sync_topology_bookkeeping():
+    """synth.sync_topology mirrors Flame::syncGraph's index bookkeeping (flame.cc:1984-2123): kept vertices
+    first in their old order, surviving edges keep order and orientation, new edges are appended."""
+    import numpy as np
+    from flame_b200 import synth
+    g = synth.make_graph(640, 480, 400, seed=3, noise_seed=4, triangulator="scipy")
+    rng = np.random.default_rng(0)
+    keep = rng.uniform(size=400) > 0.2
+    pos_kept = (g["pos"][keep] + rng.normal(0, 0.3, (int(keep.sum()), 2))).astype(np.float32)
+    pos_new = synth.make_vertices(640, 480, 50, seed=9)
+    pos, tris, edges, vtx_from, edge_from = synth.sync_topology(g["edges"], keep, pos_kept, pos_new)
+    nk = int(keep.sum())
+    assert pos.shape[0] == nk + 50 and np.array_equal(vtx_from[:nk], np.flatnonzero(keep)) and (vtx_from[nk:] == -1).all()
+    carried = edge_from >= 0
+    # carried edges: same endpoints (through vtx_from) in the same orientation, old relative order preserved
+    assert np.array_equal(vtx_from[edges[carried]], g["edges"][edge_from[carried]])
+    assert (np.diff(edge_from[carried]) > 0).all()
+    # carried edges come first, new ones after
+    assert not carried[np.argmax(~carried):].any()
+    # the edge set is exactly the triangulation's
+    und = {tuple(sorted(e)) for e in edges.tolist()}
+    tri_e = {tuple(sorted((int(t[i]), int(t[(i + 1) % 3])))) for t in tris for i in range(3)}
+    assert und == tri_e and len(und) == edges.shape[0]
+    # host-side state edits: carried values move, new ones get the defaults
+    old = {k: rng.uniform(size=400).astype(np.float32) for k in
+           ("x", "w1", "w2", "x_bar", "w1_bar", "w2_bar", "x_prev", "w1_prev", "w2_prev")}
+    old.update({k: rng.uniform(size=g["edges"].shape[0]).astype(np.float32) for k in ("q1", "q2", "q3")})
+    data = rng.uniform(0.2, 1.0, pos.shape[0]).astype(np.float32)
+    s = synth.sync_state_host(old, pos, edges, vtx_from, edge_from, data)
+    assert np.array_equal(s["w1"][:nk], old["w1"][keep]) and (s["w1"][nk:] == 0).all()
+    assert np.array_equal(s["x"][nk:], data[nk:]) and np.array_equal(s["x_prev"][nk:], data[nk:])
+    assert np.array_equal(s["q2"][carried], old["q2"][edge_from[carried]]) and (s["q2"][~carried] == 0).all()
