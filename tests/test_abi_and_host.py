@@ -40,6 +40,8 @@ def test_struct_layouts_match_oracle_and_numpy():
     assert ctypes.sizeof(_lib.PDParams) == 24
     assert _lib.FEATURE_DTYPE.itemsize == 40 and _lib.DIAG_DTYPE.itemsize == 20
     assert _lib.FEATURE_DTYPE == pyoracle.FEATURE_DTYPE == synth.FEATURE_DTYPE
+    assert ctypes.sizeof(_lib.TriFilterParams) == ctypes.sizeof(pyoracle.TriFilterParams) == 32
+    assert ctypes.sizeof(_lib.GraphSync) == 72  # 2 x int32 + 7 pointers + int32 (+ padding)
 
 
 def test_no_cpu_fallback_without_gpu():
