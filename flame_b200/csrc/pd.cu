@@ -8,14 +8,19 @@
 // incident edges in ascending ORIGINAL edge id, which is the order the reference's sequential
 // edge scatter (cc:118-142) applies its rounded += / -= to each vertex.
 //
-// Formulation (both modes): VERTEX-CENTRIC. One thread owns one vertex and a private copy of the
-// dual variables of its incident edges. Per iteration it (1) recomputes the dual update of every
-// incident edge from the x_bar/w_bar of the two endpoints (both endpoints of an edge compute the
-// same rounded values, so the two copies stay bit-identical), (2) applies the primal scatter
-// contributions in order, (3) applies proxL1 and the extragradient step and publishes the new
-// x_bar/w_bar into the OTHER half of a double buffer. Only x_bar/w_bar (16 B per vertex) is shared
-// between threads, so an iteration needs ONE barrier (the reference's dual / primal / extragradient
-// passes collapse into one sweep) and no atomics.
+// Three kernels share the arithmetic helpers below:
+//   k_pd_stream       state in HBM, one launch per iteration, VERTEX-CENTRIC: one thread owns one vertex
+//                     and a private copy of the dual variables of its incident edges; per iteration it
+//                     recomputes the dual update of every incident edge from the x_bar/w_bar of the two
+//                     endpoints (both endpoints compute the same rounded values, so the two copies stay
+//                     bit-identical), applies the primal contributions in order, then proxL1 + the
+//                     extragradient step into the other half of a double buffer. Any graph size.
+//   k_pd_resident     one thread-block cluster per graph, state on chip for all iterations: edge-parallel
+//                     dual phase (q in registers, contributions pushed to both endpoints' shared-memory
+//                     slots, remote ones through DSMEM), vertex-parallel primal phase, two cluster barriers
+//                     per iteration. The default whenever the graph fits a cluster.
+//   k_pd_resident_mb  the same with local halo copies and point-to-point mbarrier synchronisation
+//                     (experimental, slower on B200; FLAME_B200_PD_SYNC=p2p).
 #include <cooperative_groups.h>
 
 #include <algorithm>
