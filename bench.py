@@ -121,10 +121,28 @@ def cpu_baseline(budget_s=12.0):
         _cpu_frame(pyoracle, synth, frames[0], iters)
         n += 1
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": _cpu_kind(pyoracle),
-            "sample": "%d frames of config %s (%dx%d, V=%d, %d PD iters + dense projection), %s, "
-                      "1 thread (the reference runs step() on one thread), %.1f s"
-                      % (n, CFG, W, H, V, iters, _CPU_DESC[_cpu_kind(pyoracle)], dt)}
+    out = {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": _cpu_kind(pyoracle),
+           "sample": "%d frames of config %s (%dx%d, V=%d, %d PD iters + dense projection), %s, "
+                     "1 thread (the reference runs step() on one thread), %.1f s"
+                     % (n, CFG, W, H, V, iters, _CPU_DESC[_cpu_kind(pyoracle)], dt)}
+    try:  # the epipolar search of the `search` side measurement on one CPU thread (OpenMP is inert in the
+        # reference build): same workload, config C
+        Wc, Hc, _, _ = synth.CONFIGS["C"]
+        K, Kinv, sframes = synth.make_stereo_pair(Wc, Hc)
+        feats0 = synth.make_features(synth.config_graph("C")["pos"], Wc, Hc)
+        fn = pyoracle.ref_update_feature_idepths if pyoracle.have_ref() else pyoracle.update_feature_idepths
+        tp = pyoracle.track_default_params()
+        ts = []
+        for _ in range(3):
+            f = feats0.copy()
+            t0 = time.perf_counter()
+            fn(tp, K, Kinv, Wc, Hc, synth.PAD, sframes, 1, 0, f)
+            ts.append(time.perf_counter() - t0)
+        out["search"] = {"ms_per_call": 1e3 * min(ts), "features_per_s": len(feats0) / min(ts), "cores": 1,
+                         "workload": "config C: %dx%d, %d features" % (Wc, Hc, len(feats0))}
+    except Exception as e:  # the headline baseline above does not depend on it
+        out["search"] = {"unavailable": repr(e)}
+    return out
 
 
 def _ref_worker(conn, n_frames_max, iters):
