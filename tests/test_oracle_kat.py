@@ -398,3 +398,64 @@ def test_vertex_normals_restatement_sanity(oracle):
     idepth[::3] = 0.0  # every triangle touching such a vertex is skipped
     n = oracle.vertex_normals(Kinv, g["pos"], idepth, g["tris"])
     assert np.all(n[::3] == 0)
+
+
+def test_oracle_raster_equals_reference_on_random_soups(oracle):
+    """Arbitrary triangle lists - overlapping, both windings, collinear, repeated vertices, lines touching the
+    right border (sweep overshoot), with validity masks and a pre-initialised image: the restatement and
+    rasterization.cc / interpolateMesh compiled verbatim agree pixel for pixel."""
+    _need_ref(oracle)
+    rng = np.random.default_rng(123)
+    for case in range(25):
+        W, H = int(rng.integers(17, 90)), int(rng.integers(9, 70))
+        V, T = int(rng.integers(3, 40)), int(rng.integers(1, 60))
+        pos = np.stack([rng.uniform(0, W - 1, V), rng.uniform(0, H - 1, V)], 1).astype(np.float32)
+        if case % 3 == 0:
+            pos = np.rint(pos).astype(np.float32)          # many exactly collinear / coincident points
+        if case % 4 == 1:
+            pos[: V // 2, 1] = pos[0, 1]                   # horizontal lines
+            pos[V // 2 - 1, 0] = W - 1                     # ... reaching the right border
+        tris = rng.integers(0, V, (T, 3)).astype(np.int32)
+        vals = rng.uniform(0.05, 3.0, V).astype(np.float32)
+        vv = (rng.uniform(size=V) > 0.1).astype(np.uint8) if case % 2 else None
+        tv = (rng.uniform(size=T) > 0.2).astype(np.uint8) if case % 5 else None
+        base = rng.uniform(size=(H, W)).astype(np.float32) if case % 2 == 0 else None
+        a = oracle.interpolate_mesh(tris, pos, vals, H, W, vv, tv, None if base is None else base.copy())
+        b = oracle.interpolate_mesh(tris, pos, vals, H, W, vv, tv, None if base is None else base.copy(),
+                                    use_ref=True)
+        assert np.array_equal(np.isnan(a), np.isnan(b)), case
+        m = ~np.isnan(a)
+        assert np.array_equal(a[m].view(np.uint32), b[m].view(np.uint32)), case
+
+
+def test_oracle_pd_equals_reference_on_random_graphs(oracle):
+    """Random multigraphs (parallel edges, isolated vertices, mixed orientations), random positions,
+    weights, parameters and a random warm state: restatement == nltgv2_l1_graph_regularizer.cc verbatim."""
+    _need_ref(oracle)
+    rng = np.random.default_rng(321)
+    for case in range(12):
+        V, E = int(rng.integers(2, 60)), int(rng.integers(0, 200))
+        pos = rng.uniform(0, 300, (V, 2)).astype(np.float32)
+        src = rng.integers(0, V, E)
+        dst = (src + rng.integers(1, V, E)) % V            # no self loops (Delaunay never produces them)
+        edges = np.ascontiguousarray(np.stack([src, dst], 1).astype(np.int32)).reshape(-1, 2)
+        g = {"pos": pos, "edges": edges,
+             "data_term": rng.uniform(0.0, 2.0, V).astype(np.float32),
+             "data_weight": rng.uniform(0.0, 3.0, V).astype(np.float32)}
+        a = synth.init_state(g, rng.uniform(0.01, 2.0, E).astype(np.float32),
+                             rng.uniform(0.1, 2.0, E).astype(np.float32))
+        for k in ("x", "w1", "w2", "x_bar", "w1_bar", "w2_bar", "x_prev", "w1_prev", "w2_prev"):
+            a[k] = rng.normal(0.5, 0.5, V).astype(np.float32)
+        for k in ("q1", "q2", "q3"):
+            a[k] = rng.uniform(-1, 1, E).astype(np.float32)
+        b = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in a.items()}
+        p = oracle.pd_default_params()
+        p.data_factor, p.step_x, p.step_q, p.theta = (float(rng.uniform(0.05, 1.0)), float(rng.uniform(1e-3, 0.05)),
+                                                      float(rng.uniform(1.0, 200.0)), float(rng.uniform(0.0, 1.0)))
+        p.x_min, p.x_max = 0.05, 1.8
+        n = int(rng.integers(1, 40))
+        oracle.pd_run(a, p, n)
+        oracle.ref_pd_run(b, p, n)
+        for k in oracle.GRAPH_STATE:
+            assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), (case, k)
+        assert oracle.pd_costs(a, p) == oracle.ref_pd_costs(b, p), case
