@@ -180,6 +180,29 @@ def sync_state_host(old, pos, edges, vtx_from, edge_from, data_term, data_weight
     return s
 
 
+def triangle_soups(n=25, seed=123):
+    """Random triangle lists outside the benchmark's shape for the dense projection: overlapping triangles of
+    both windings, collinear / coincident vertices, horizontal lines reaching the right border (the 4-px sweep
+    overshoot), validity masks and pre-initialised images. Yields dicts (W, H, pos, tris, vals, vv, tv, base)."""
+    rng = np.random.default_rng(seed)
+    for case in range(n):
+        W, H = int(rng.integers(17, 90)), int(rng.integers(9, 70))
+        V, T = int(rng.integers(3, 40)), int(rng.integers(1, 60))
+        pos = np.stack([rng.uniform(0, W - 1, V), rng.uniform(0, H - 1, V)], 1).astype(np.float32)
+        if case % 3 == 0:
+            pos = np.rint(pos).astype(np.float32)          # many exactly collinear / coincident points
+        if case % 4 == 1:
+            pos[: V // 2, 1] = pos[0, 1]                   # horizontal lines
+            pos[V // 2 - 1, 0] = W - 1                     # ... reaching the right border
+        tris = rng.integers(0, V, (T, 3)).astype(np.int32)
+        vals = rng.uniform(0.05, 3.0, V).astype(np.float32)
+        vv = (rng.uniform(size=V) > 0.1).astype(np.uint8) if case % 2 else None
+        tv = (rng.uniform(size=T) > 0.2).astype(np.uint8) if case % 5 else None
+        base = rng.uniform(size=(H, W)).astype(np.float32) if case % 2 == 0 else None
+        yield {"case": case, "W": W, "H": H, "pos": pos, "tris": tris, "vals": vals, "vv": vv, "tv": tv,
+               "base": base}
+
+
 def config_graph(name, frame=0):
     W, H, V, iters = CONFIGS[name]
     g = make_graph(W, H, V, seed=1 + 100 * frame, noise_seed=2 + 100 * frame)

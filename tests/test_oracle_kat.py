@@ -405,27 +405,15 @@ def test_oracle_raster_equals_reference_on_random_soups(oracle):
     right border (sweep overshoot), with validity masks and a pre-initialised image: the restatement and
     rasterization.cc / interpolateMesh compiled verbatim agree pixel for pixel."""
     _need_ref(oracle)
-    rng = np.random.default_rng(123)
-    for case in range(25):
-        W, H = int(rng.integers(17, 90)), int(rng.integers(9, 70))
-        V, T = int(rng.integers(3, 40)), int(rng.integers(1, 60))
-        pos = np.stack([rng.uniform(0, W - 1, V), rng.uniform(0, H - 1, V)], 1).astype(np.float32)
-        if case % 3 == 0:
-            pos = np.rint(pos).astype(np.float32)          # many exactly collinear / coincident points
-        if case % 4 == 1:
-            pos[: V // 2, 1] = pos[0, 1]                   # horizontal lines
-            pos[V // 2 - 1, 0] = W - 1                     # ... reaching the right border
-        tris = rng.integers(0, V, (T, 3)).astype(np.int32)
-        vals = rng.uniform(0.05, 3.0, V).astype(np.float32)
-        vv = (rng.uniform(size=V) > 0.1).astype(np.uint8) if case % 2 else None
-        tv = (rng.uniform(size=T) > 0.2).astype(np.uint8) if case % 5 else None
-        base = rng.uniform(size=(H, W)).astype(np.float32) if case % 2 == 0 else None
-        a = oracle.interpolate_mesh(tris, pos, vals, H, W, vv, tv, None if base is None else base.copy())
-        b = oracle.interpolate_mesh(tris, pos, vals, H, W, vv, tv, None if base is None else base.copy(),
-                                    use_ref=True)
-        assert np.array_equal(np.isnan(a), np.isnan(b)), case
+    for c in synth.triangle_soups():
+        W, H, base = c["W"], c["H"], c["base"]
+        a = oracle.interpolate_mesh(c["tris"], c["pos"], c["vals"], H, W, c["vv"], c["tv"],
+                                    None if base is None else base.copy())
+        b = oracle.interpolate_mesh(c["tris"], c["pos"], c["vals"], H, W, c["vv"], c["tv"],
+                                    None if base is None else base.copy(), use_ref=True)
+        assert np.array_equal(np.isnan(a), np.isnan(b)), c["case"]
         m = ~np.isnan(a)
-        assert np.array_equal(a[m].view(np.uint32), b[m].view(np.uint32)), case
+        assert np.array_equal(a[m].view(np.uint32), b[m].view(np.uint32)), c["case"]
 
 
 def test_oracle_pd_equals_reference_on_random_graphs(oracle):

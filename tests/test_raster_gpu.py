@@ -194,3 +194,16 @@ def test_async_projection_pipeline(oracle):
         oracle.pd_run(s, oracle.pd_default_params(), 4)
         want = oracle.interpolate_mesh(g["tris"], g["pos"], (s["x"] * np.float32(2.0)).astype(np.float32), g["H"], g["W"])
         _assert_same_image(outs[1].array.copy(), want)
+
+
+def test_random_triangle_soups(oracle):
+    """The soups on which the oracle is pinned against rasterization.cc compiled verbatim
+    (tests/test_oracle_kat.py::test_oracle_raster_equals_reference_on_random_soups), on the device."""
+    with _lib.Context(0, 1) as ctx:
+        for c in synth.triangle_soups():
+            W, H, base = c["W"], c["H"], c["base"]
+            want = oracle.interpolate_mesh(c["tris"], c["pos"], c["vals"], H, W, c["vv"], c["tv"],
+                                           None if base is None else base.copy())
+            got = ctx.interpolate_mesh(0, c["tris"], c["pos"], c["vals"], H, W, c["vv"], c["tv"],
+                                       None if base is None else base.copy())
+            _assert_same_image(got, want)
