@@ -1,16 +1,19 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the FLaME variational-depth hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config B|C|D]
 
-Workload (BASELINE.json configs[3], the one `metric` is quoted on): 1920x1080 frames, 10 000
-Delaunay vertices each, 200 primal-dual iterations + dense inverse-depth projection.
-A "step" is one pass of the hot path over one batch of B independent synthetic frames per GPU:
-    graph_reset (fresh-vertex rule)  ->  200 x step()  ->  interpolateMesh
+Workload (default: BASELINE.json configs[3], the one `metric` is quoted on): 1920x1080 frames, 10 000
+Delaunay vertices each, 200 primal-dual iterations + dense inverse-depth projection. `--config B` / `C`
+run configs[1] / configs[2] (640x480 / 2k vertices / 100 iterations; 1280x720 / 5k vertices / epipolar
+search + 100 iterations) the same way.
+A "step" is one pass of the hot path over one batch of independent synthetic frames per GPU:
+    [epipolar search (C)] -> graph_reset (fresh-vertex rule) -> n x step() -> interpolateMesh
 `value`  = frames/s with inputs resident in HBM (CUDA events on the library's stream, max over ranks).
 `e2e`    = the same metric through the public C ABI with HOST buffers: per frame, upload of the
-           graph + triangles (H2D), PD, projection, download of the dense map + vertex idepths (D2H).
-`roofline` is for the dominant kernel (the resident PD solver) — see DESIGN.md for the byte model.
+           graph + triangles (H2D), PD, projection, download of the dense map + vertex idepths (D2H),
+           as a pipeline of frames driven through flame_b200_process_frame_submit / _wait.
+`roofline` is for the dominant kernel (the resident PD solver; `--mode 1` = the HBM-streaming solver).
 Multi-GPU: frames shard by rank (weak scaling), no data-path collective; torch.distributed (NCCL)
 is only used for the barrier and the max-over-ranks reduction.
 """
@@ -27,7 +30,45 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG = "D"
-METRIC = "frames/sec at 1080p (10k vertices, 200 PD iters + dense projection)"
+_METRICS = {
+    "D": "frames/sec at 1080p (10k vertices, 200 PD iters + dense projection)",
+    "C": "frames/sec at 720p (5k vertices, epipolar search + 100 PD iters + dense projection)",
+    "B": "frames/sec at VGA (2k vertices, 100 PD iters + dense projection)",
+}
+_WORK = {
+    "D": "config D: 1920x1080, V=10000, 200 PD iters + dense projection",
+    "C": "config C: 1280x720, V=5000, epipolar search + 100 PD iters + dense projection",
+    "B": "config B: 640x480, V=2000, 100 PD iters + dense projection",
+}
+N_DISTINCT = 30  # distinct synthetic frames; the slots of a batch cycle through them
+
+
+def _metric():
+    return _METRICS[CFG]
+
+
+def _config():
+    """The `config` object is the same in both arms (the driver compares them)."""
+    return {"workload": _WORK[CFG]}
+
+
+def _usable_cpus():
+    """CPUs this process may really use: its affinity mask, capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
 
 
 def _peaks():
@@ -39,13 +80,11 @@ def _peaks():
 
 
 def _frames(n, first=0):
+    """n frame descriptions; at most N_DISTINCT distinct ones (generated once), cycled."""
     from flame_b200 import synth
     W, H, V, iters = synth.CONFIGS[CFG]
-    out = []
-    for f in range(first, first + n):
-        g = synth.config_graph(CFG, frame=f)
-        out.append(g)
-    return out, (W, H, V, iters)
+    distinct = [synth.config_graph(CFG, frame=first + f) for f in range(min(n, N_DISTINCT))]
+    return [distinct[i % len(distinct)] for i in range(n)], (W, H, V, iters)
 
 
 class ClockSampler(threading.Thread):
@@ -77,7 +116,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.05)
+                time.sleep(0.01)
         except Exception as e:  # pragma: no cover
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
 
@@ -88,9 +127,28 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
 
 
+_SEARCH = {}
+
+
+def _search_inputs():
+    """Config C's stereo pair + features (the epipolar search that seeds the frame), built once."""
+    if not _SEARCH:
+        from flame_b200 import synth
+        Wc, Hc, _, _ = synth.CONFIGS["C"]
+        K, Kinv, sframes = synth.make_stereo_pair(Wc, Hc)
+        feats0 = synth.make_features(synth.config_graph("C")["pos"], Wc, Hc)
+        _SEARCH.update(W=Wc, H=Hc, K=K, Kinv=Kinv, frames=sframes, feats=feats0)
+    return _SEARCH
+
+
 def _cpu_frame(pyoracle, synth, g, iters):
     """One frame of the hot path on one CPU thread (the reference runs step() on exactly one thread,
-    flame.cc:100-111): edge weights, 200 x step, interpolateMesh."""
+    flame.cc:100-111): [epipolar search (config C)], edge weights, n x step, interpolateMesh."""
+    if CFG == "C":
+        si = _search_inputs()
+        fn = pyoracle.ref_update_feature_idepths if pyoracle.have_ref() else pyoracle.update_feature_idepths
+        fn(pyoracle.track_default_params(), si["K"], si["Kinv"], si["W"], si["H"], synth.PAD, si["frames"], 1, 0,
+           si["feats"].copy())
     alpha, beta = pyoracle.edge_weights(g["edges"], g["pos"])
     s = synth.init_state(g, alpha, beta)
     if pyoracle.have_ref():  # the reference's own sources compiled verbatim (oracle/_ref)
@@ -122,35 +180,35 @@ def cpu_baseline(budget_s=12.0):
         n += 1
     dt = time.perf_counter() - t0
     out = {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": _cpu_kind(pyoracle),
-           "sample": "%d frames of config %s (%dx%d, V=%d, %d PD iters + dense projection), %s, "
-                     "1 thread (the reference runs step() on one thread), %.1f s"
-                     % (n, CFG, W, H, V, iters, _CPU_DESC[_cpu_kind(pyoracle)], dt)}
-    try:  # the epipolar search of the `search` side measurement on one CPU thread (OpenMP is inert in the
-        # reference build): same workload, config C
-        Wc, Hc, _, _ = synth.CONFIGS["C"]
-        K, Kinv, sframes = synth.make_stereo_pair(Wc, Hc)
-        feats0 = synth.make_features(synth.config_graph("C")["pos"], Wc, Hc)
+           "sample": "%d frames of %s, %s, 1 thread (the reference runs step() on one thread), %.1f s"
+                     % (n, _WORK[CFG], _CPU_DESC[_cpu_kind(pyoracle)], dt)}
+    try:  # the epipolar search alone on one CPU thread (OpenMP is inert in the reference build)
+        si = _search_inputs()
         fn = pyoracle.ref_update_feature_idepths if pyoracle.have_ref() else pyoracle.update_feature_idepths
         tp = pyoracle.track_default_params()
         ts = []
         for _ in range(3):
-            f = feats0.copy()
+            f = si["feats"].copy()
             t0 = time.perf_counter()
-            fn(tp, K, Kinv, Wc, Hc, synth.PAD, sframes, 1, 0, f)
+            fn(tp, si["K"], si["Kinv"], si["W"], si["H"], synth.PAD, si["frames"], 1, 0, f)
             ts.append(time.perf_counter() - t0)
-        out["search"] = {"ms_per_call": 1e3 * min(ts), "features_per_s": len(feats0) / min(ts), "cores": 1,
-                         "workload": "config C: %dx%d, %d features" % (Wc, Hc, len(feats0))}
+        out["search"] = {"ms_per_call": 1e3 * min(ts), "features_per_s": len(si["feats"]) / min(ts), "cores": 1,
+                         "workload": "config C: %dx%d, %d features" % (si["W"], si["H"], len(si["feats"]))}
     except Exception as e:  # the headline baseline above does not depend on it
         out["search"] = {"unavailable": repr(e)}
     return out
 
 
-def _ref_worker(conn, n_frames_max, iters):
+def _ref_worker(conn, cfg):
     """One worker PROCESS = one Flame instance on one core: runs whole frames until told to stop."""
+    global CFG
+    CFG = cfg
     from flame_b200 import synth
     from oracle import pyoracle
-    frames, _ = _frames(1)
+    frames, (_, _, _, iters) = _frames(1)
     g = frames[0]
+    if CFG == "C":
+        _search_inputs()
     conn.send("ready")
     while True:
         n = conn.recv()
@@ -163,20 +221,19 @@ def _ref_worker(conn, n_frames_max, iters):
 
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path on the host cores: independent frames in
-    parallel, one single-threaded worker process per core (each Flame instance runs step() on one
+    parallel, one single-threaded worker process per USABLE core (each Flame instance runs step() on one
     thread, flame.cc:100-111). A step = one frame per core."""
     if rank != 0:
         return
     import multiprocessing as mp
     from oracle import pyoracle
     pyoracle.build()
-    cores = os.cpu_count() or 1
-    W, H, V, iters = __import__("flame_b200.synth", fromlist=["CONFIGS"]).CONFIGS[CFG]
+    cores = _usable_cpus()
     ctx = mp.get_context("fork")
     workers = []
     for _ in range(cores):
         a, b = ctx.Pipe()
-        p = ctx.Process(target=_ref_worker, args=(b, 0, iters), daemon=True)
+        p = ctx.Process(target=_ref_worker, args=(b, CFG), daemon=True)
         p.start()
         workers.append((p, a))
     for _, a in workers:
@@ -201,40 +258,51 @@ def run_reference(args, rank, world):
         p.join(timeout=10)
     val = per_step * args.steps / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": _metric(), "value": val, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": "config D: 1920x1080, V=%d, %d PD iters + dense projection" % (V, iters),
-                   "frames_per_step": per_step},
+        "data": "synthetic", "config": _config(),
+        "details": {"frames_per_step": per_step, "os_cpu_count": os.cpu_count(),
+                    "affinity_cpus": len(os.sched_getaffinity(0))},
         "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": _cpu_kind(pyoracle),
-                         "sample": "%d frames per step (one per core; one single-threaded worker process per "
-                                   "core, as each Flame instance runs step() on one thread), %s"
-                                   % (per_step, _CPU_DESC[_cpu_kind(pyoracle)])},
+                         "per_core": val / cores,
+                         "sample": "%d frames per step (one per usable core = affinity mask capped by the cgroup CPU "
+                                   "quota; one single-threaded worker process per core, as each Flame instance runs "
+                                   "step() on one thread), %s" % (per_step, _CPU_DESC[_cpu_kind(pyoracle)])},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
 def _pin_to_gpu_node(index):
-    """Run this rank on the CPUs of its GPU's NUMA node: the pinned host buffers of the e2e leg are then
-    allocated next to the GPU's PCIe root (measured: 36 -> 39 GB/s D2H on the 2-socket bench box)."""
+    """Run this rank on the CPUs of its GPU's NUMA node (nvml's ideal CPU affinity of the device): host
+    threads and the pinned buffers they allocate (first touch) then sit next to the GPU's PCIe root.
+    Returns (cpus in the mask, numa node of the first one) for the bench line."""
+    info = {"cpus": len(os.sched_getaffinity(0)), "numa_node": None, "pinned": False}
     try:
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
         n = os.cpu_count()
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
-        cpus = [i for i in range(n) if (words[i // 64] >> (i % 64)) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [i for i in range(n) if (words[i // 64] >> (i % 64)) & 1 and i in allowed]
         if cpus:
             os.sched_setaffinity(0, cpus)
+            info["cpus"] = len(cpus)
+            info["pinned"] = True
+            for node in sorted(os.listdir("/sys/devices/system/node")):
+                if node.startswith("node") and os.path.exists("/sys/devices/system/node/%s/cpu%d" % (node, cpus[0])):
+                    info["numa_node"] = int(node[4:])
+                    break
     except Exception:
         pass
+    return info
 
 
 def run_ours(args, rank, world, local_rank):
     import torch
-    from flame_b200 import _lib
+    from flame_b200 import _lib, synth
 
     dist = None
     if world > 1:
@@ -243,28 +311,43 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    _pin_to_gpu_node(local_rank)
+    numa = _pin_to_gpu_node(local_rank)
 
     from flame_b200 import shard
-    B = args.batch
-    ids = shard.frames_for_rank(rank, world, B)  # frames shard by rank: no data-path collective
-    frames, (W, H, V, iters) = _frames(B, first=ids[0])
+    W, H, V, iters = synth.CONFIGS[CFG]
     p = _lib.default_pd_params()
+    # ---- how many frames the device solves concurrently (one thread-block cluster per frame) ----
+    probe, _ = _frames(1)
+    with _lib.Context(local_rank, 1) as c0:
+        c0.graph_init(0, probe[0]["pos"], probe[0]["data_term"], probe[0]["edges"])
+        wave = c0.pd_wave(0) if args.mode != 1 else 0
+    if args.wave > 0:
+        wave = args.wave
+    B = args.batch if args.batch > 0 else (40 * wave if wave > 0 else 128)
+    if wave <= 0:
+        wave = B
+    wave = min(wave, B)
+    ids = shard.frames_for_rank(rank, world, B)  # frames shard by rank: no data-path collective
+    frames, _ = _frames(B, first=ids[0] % 1000)
     ctx = _lib.Context(local_rank, B)
     for i, g in enumerate(frames):
         ctx.graph_init(i, g["pos"], g["data_term"], g["edges"])
         ctx.mesh_bind(i, g["tris"], H, W)
     ctx.sync()
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    # A frame is one 16-CTA cluster; the device keeps `wave` of them resident (7 on a B200). A step walks its
-    # B frames wave by wave; the projection of a wave runs on the context's second stream and overlaps the
-    # solver of the next wave (the clusters leave 36 of 148 SMs free).
-    wave = args.wave if args.wave > 0 else (ctx.pd_wave(0) if args.mode != 1 else 0)
-    if wave <= 0:
-        wave = B
-    wave = min(wave, B)
+    # A frame is one cluster; the device keeps `wave` of them resident. A step walks its B frames wave by
+    # wave; the projection of a wave runs on the context's second stream and overlaps the solver of the next.
     ctx.set_async_projection(not args.no_async)
     waves = [(s0, min(wave, B - s0)) for s0 in range(0, B, wave)]
+    search_dev = None
+    if CFG == "C":  # the epipolar search is part of the frame: device-resident features, one launch per frame
+        si = _search_inputs()
+        ctx.set_camera(si["W"], si["H"], si["K"], si["Kinv"])
+        for i, fr in enumerate(si["frames"]):
+            ctx.frame_upload(i, fr["img_pad"], fr["gradx_pad"], fr["grady_pad"], synth.PAD, fr["pose"])
+        tp = _lib.default_track_params()
+        ctx.features_upload(si["feats"])
+        search_dev = (tp, len(si["feats"]))
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -274,6 +357,9 @@ def run_ours(args, rank, world, local_rank):
 
     def step(ev=None):
         for w, (s0, n) in enumerate(waves):
+            if search_dev is not None:
+                for _ in range(n):  # one search per frame of the wave (5 000 device-resident features each)
+                    ctx.features_track(search_dev[0], 1, 0)
             ctx.graph_reset(s0, n)
             if ev is not None:
                 ev[w][0].record(stream)
@@ -307,93 +393,120 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop()
     ms_total = shard.max_over_ranks(ms_total, dev)
     value = world * B * args.steps / (ms_total * 1e-3)
+    ctx.set_async_projection(False)
 
-    # ---- single-frame latency (one cluster per frame, B = 1) ----
-    lat = []
-    for _ in range(5):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ctx.graph_reset(0, 1)
-        a.record(stream)
-        ctx.pd_run(p, iters, 0, 1, args.mode)
-        b.record(stream)
-        ctx.mesh_project(0, 1, 1.0)
-        ctx.sync()
-        lat.append(a.elapsed_time(b))
-    lat_ms = float(np.median(lat))
+    # ---- single-frame latency: the latency layout (frame spread over up to 16 SMs), B = 1 ----
+    lat_ms = None
+    if args.mode != 1:
+        with _lib.Context(local_rank, 1) as cl:
+            cl.set_pd_preference(_lib.PREF_LATENCY)
+            cl.graph_init(0, frames[0]["pos"], frames[0]["data_term"], frames[0]["edges"])
+            ls = torch.cuda.ExternalStream(cl.stream, device=dev)
+            lat = []
+            for _ in range(6):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                cl.graph_reset(0, 1)
+                a.record(ls)
+                cl.pd_run(p, iters, 0, 1, args.mode)
+                b.record(ls)
+                cl.sync()
+                lat.append(a.elapsed_time(b))
+            lat_ms = float(np.median(lat[1:]))
 
     # ---- epipolar search (config C: 1280x720, 5000 features), reported as features/s ----
     search = None
     if rank == 0 and not args.no_search:
-        from flame_b200 import synth
-        Wc, Hc, Vc_, _ = synth.CONFIGS["C"]
-        K, Kinv, sframes = synth.make_stereo_pair(Wc, Hc)
-        feats0 = synth.make_features(synth.config_graph("C")["pos"], Wc, Hc)
-        ctx.set_camera(Wc, Hc, K, Kinv)
-        for i, fr in enumerate(sframes):
+        si = _search_inputs()
+        ctx.set_camera(si["W"], si["H"], si["K"], si["Kinv"])
+        for i, fr in enumerate(si["frames"]):
             ctx.frame_upload(i, fr["img_pad"], fr["gradx_pad"], fr["grady_pad"], synth.PAD, fr["pose"])
         tp = _lib.default_track_params()
         ts = []
         for _ in range(8):
-            f = feats0.copy()
+            f = si["feats"].copy()
             t0 = time.perf_counter()
             n_upd, _ = ctx.update_feature_idepths(tp, 1, 0, f, want_diag=False)
             ts.append(time.perf_counter() - t0)
         t_med = float(np.median(ts[2:]))
-        search = {"workload": "config C: 1280x720, %d features, host records in/out" % len(feats0),
-                  "ms_per_call": 1e3 * t_med, "features_per_s": len(feats0) / t_med, "updates": int(n_upd),
-                  "note": "latency/divergence-bound walk along the epipolar line; no HBM fraction quoted"}
+        search = {"workload": "config C: 1280x720, %d features" % len(si["feats"]),
+                  "host_call_ms": 1e3 * t_med, "host_call_features_per_s": len(si["feats"]) / t_med,
+                  "updates": int(n_upd)}
+        # device-timed: features resident, CUDA events around 20 launches
+        ctx.features_upload(si["feats"])
+        ctx.sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        for _ in range(3):
+            ctx.features_track(tp, 1, 0)
+        a.record(stream)
+        for _ in range(reps):
+            ctx.features_track(tp, 1, 0)
+        b.record(stream)
+        ctx.sync()
+        k_ms = a.elapsed_time(b) / reps
+        search.update({"kernel_ms": k_ms, "features_per_s": len(si["feats"]) / (k_ms * 1e-3),
+                       "note": "device-timed (CUDA events, features resident in HBM: geometry-table + tracking kernel); "
+                               "one warp per feature, patches staged in shared memory; latency-bound, no HBM fraction quoted"})
 
     # ---- e2e: host buffers in, host buffers out, through the public C ABI ----
+    ctx.close()
     e2e = run_e2e(args, local_rank, frames, (W, H, V, iters), barrier)
     e2e_value = shard.aggregate_throughput(e2e["frames"], e2e["seconds"], dev)
 
     if rank == 0:
-        E = int(np.mean([g["edges"].shape[0] for g in frames]))
+        E = int(np.mean([g["edges"].shape[0] for g in frames[:N_DISTINCT]]))
         peak, peak_src = _peaks()
-        alg_bytes = 76.0 * (V + E) * iters * wave  # 76 B per vertex + 76 B per edge per iteration
-        achieved = alg_bytes / (pd_ms * 1e-3) / 1e9
-        traffic = None
-        tp_ = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tp_) and args.mode != 1:  # DRAM bytes of this kernel from the committed ncu capture
+        # 76 B per vertex + 76 B per edge per iteration
+        if args.mode == 1:
+            kernel, alg_bytes, launch_ms = "k_pd_stream", 76.0 * (V + E) * wave, pd_ms / iters
+            tkey = "k_pd_stream"
+        else:
+            kernel, alg_bytes, launch_ms = "k_pd_resident", 76.0 * (V + E) * iters * wave, pd_ms
+            tkey = "k_pd_resident"
+        achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+        traffic, tsrc = None, None
+        tp_ = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        if os.path.exists(tp_) and CFG == "D":  # DRAM bytes of this kernel from the committed ncu capture
             with open(tp_) as f:
-                tk = json.load(f)["k_pd_resident"]
-            traffic = (tk["dram_bytes_read"] + tk["dram_bytes_write"]) * wave / tk["frames_per_launch"]
+                tk = json.load(f).get(tkey)
+            if tk:
+                traffic = (tk["dram_bytes_read"] + tk["dram_bytes_write"]) * wave / tk["frames_per_launch"]
+                tsrc = "profiles/r2_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, %s)" % tk["capture"]
         line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
+            "metric": _metric(), "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config D: 1920x1080, V=%d, E~%d, %d PD iters + dense projection; "
-                                   "%d independent frames per GPU per step, issued as waves of %d (one solver "
-                                   "launch per wave = the frame clusters the device keeps resident); the "
-                                   "projection of a wave %s" % (V, E, iters, B, wave,
-                                                                "runs in stream order" if args.no_async else
-                                                                "overlaps the solver of the next wave (second stream)"),
-                       "frames_per_step_per_gpu": B, "frames_per_solver_launch": wave,
-                       "async_projection": not args.no_async,
-                       "pd_mode": ["auto", "stream", "resident"][args.mode],
-                       "l2": "per-step working set ~%.0f MB per GPU (PD state 2.4 MB + mesh/bins ~12 MB + 8.3 MB "
-                             "dense map per frame) > 126 MB L2: inputs larger than L2" % (B * 23.0),
-                       "parallelism": "frames sharded by rank, no data-path collective"},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _config(),
+            "details": {"E": E, "frames_per_step_per_gpu": B, "frames_per_solver_launch": wave,
+                        "distinct_synthetic_frames": min(B, N_DISTINCT),
+                        "async_projection": not args.no_async,
+                        "pd_mode": ["auto", "stream", "resident"][args.mode],
+                        "issue": "a step walks its frames in waves of %d (one solver launch per wave = the frame "
+                                 "clusters the device keeps resident); the projection of a wave %s" % (
+                                     wave, "runs in stream order" if args.no_async else
+                                     "overlaps the solver of the next wave (second stream)"),
+                        "l2": "per-step working set ~%.1f GB per GPU (PD state + mesh + dense map per frame) > 126 MB L2: "
+                              "inputs larger than L2" % (B * (4.0 * W * H * 2 + 300.0 * V) / 1e9),
+                        "parallelism": "frames sharded by rank, no data-path collective",
+                        "host": numa},
             "ms_per_pd_iter": pd_ms / iters / wave,
             "single_frame_pd_latency_ms": lat_ms,
-            "single_frame_ms_per_pd_iter": lat_ms / iters,
+            "single_frame_ms_per_pd_iter": (lat_ms / iters) if lat_ms else None,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_pd_resident" if args.mode != 1 else "k_dual/primal_stream",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": traffic,
-                         "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
-                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": pd_ms,
-                         "note": "algorithmic bytes = 76*(V+E) per PD iteration per frame; the resident kernel "
-                                 "keeps the state in shared memory, so achieved is an EFFECTIVE bandwidth "
-                                 "(DRAM traffic is far below the algorithmic bytes; see DESIGN.md). The HBM-streaming variant of "
-                                 "the same iteration (--mode 1, graphs too large for a cluster) moves 410 MB of DRAM "
-                                 "traffic per 128-frame launch at 4.59 TB/s = 0.70 of this peak (ncu, "
-                                 "profiles/r1_pd_stream_b128.txt)"},
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                         "traffic_source": tsrc, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
+                         "note": ("algorithmic bytes = 76*(V+E) per PD iteration per frame; one launch = one iteration of "
+                                  "%d frames with the state in HBM" % wave) if args.mode == 1 else
+                                 ("algorithmic bytes = 76*(V+E) per PD iteration per frame; the resident kernel keeps the "
+                                  "state in shared memory for all %d iterations, so achieved is an EFFECTIVE bandwidth "
+                                  "(DRAM traffic is far below the algorithmic bytes; see DESIGN.md). `--mode 1 --batch 128` "
+                                  "prints the same line for the HBM-streaming solver, whose HBM fraction ncu evidences" % iters)},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": e2e["h2d"],
                     "d2h_bytes_per_step": e2e["d2h"], "frames_per_step": e2e["per_step"],
-                    "pipelines": e2e["pipelines"]},
+                    "host_threads": e2e["threads"], "frames_in_flight": e2e["in_flight"],
+                    "host_breakdown": e2e["breakdown"]},
         }
         if search is not None:
             line["search"] = search
@@ -406,71 +519,111 @@ def run_ours(args, rank, world, local_rank):
 
 
 def run_e2e(args, local_rank, frames, dims, barrier):
-    """Per frame: graph_init + mesh_bind (H2D) -> pd_run -> mesh_project -> dense map + x (D2H).
-    `pipelines` host threads each drive their own context/stream so copies overlap compute."""
+    """Per frame: graph + triangles up (H2D) -> PD -> projection -> dense map + x, w1, w2 down (D2H), through
+    flame_b200_process_frame_submit / _wait. `pipelines` host threads, each driving ONE context with a ring of
+    `ring` slots: while the device works on the frames in flight, the thread prepares and submits the next."""
     from concurrent.futures import ThreadPoolExecutor
     from flame_b200 import _lib
     W, H, V, iters = dims
-    P = args.pipelines
+    P, R = args.pipelines, args.ring
     p = _lib.default_pd_params()
-    ctxs = [_lib.Context(local_rank, 1) for _ in range(P)]
-    outs = [_lib.PinnedArray((H, W)) for _ in range(P)]
+    ctxs = [_lib.Context(local_rank, R) for _ in range(P)]
+    outs = [[_lib.PinnedArray((H, W)) for _ in range(R)] for _ in range(P)]
     vout = [tuple(np.empty(V, np.float32) for _ in range(3)) for _ in range(P)]
-    per_step = len(frames)
-
-    def one(job):
-        k, i = job
-        g = frames[i]
-        ctx, out, (x, w1, w2) = ctxs[k], outs[k], vout[k]
-        # the public per-frame call: host arrays in (graph + triangles), host arrays out (dense map
-        # into pinned memory, smoothed vertex idepths and plane parameters); synchronises.
-        ctx.process_frame(0, g["pos"], g["data_term"], g["edges"], g["tris"], H, W, p, iters, out.array, x, w1, w2)
-        return float(x[0]) + float(out.array[H // 2, W // 2])
-
-    pool = ThreadPoolExecutor(P)
+    per_step = args.e2e_batch
+    search = CFG == "C"
+    if search:
+        from flame_b200 import synth
+        si = _search_inputs()
+        tp = _lib.default_track_params()
+        for c in ctxs:
+            c.set_camera(si["W"], si["H"], si["K"], si["Kinv"])
+            for i, fr in enumerate(si["frames"]):
+                c.frame_upload(i, fr["img_pad"], fr["gradx_pad"], fr["grady_pad"], synth.PAD, fr["pose"])
 
     def worker(k, n_steps):
-        acc = 0.0
+        ctx, (x, w1, w2) = ctxs[k], vout[k]
+        busy = [False] * R
+        acc, j = 0.0, 0
         for s in range(n_steps):
             for i in range(k, per_step, P):
-                acc += one((k, i))
+                slot = j % R
+                if busy[slot]:
+                    ctx.process_frame_wait(slot, x, w1, w2)
+                    acc += float(x[0]) + float(outs[k][slot].array[H // 2, W // 2])
+                g = frames[i % len(frames)]
+                if search:  # host feature records in and out (5 000 x 40 B each way), synchronous
+                    f = si["feats"].copy()
+                    ctx.update_feature_idepths(tp, 1, 0, f, want_diag=False)
+                ctx.process_frame_submit(slot, g["pos"], g["data_term"], g["edges"], g["tris"], H, W, p, iters,
+                                         outs[k][slot].array)
+                busy[slot] = True
+                j += 1
+        for slot in range(R):
+            if busy[slot]:
+                ctx.process_frame_wait(slot, x, w1, w2)
+                acc += float(x[0]) + float(outs[k][slot].array[H // 2, W // 2])
         return acc
+
+    pool = ThreadPoolExecutor(P)
 
     def run(n_steps):
         return sum(pool.map(lambda k: worker(k, n_steps), range(P)))
 
     run(1)  # warm-up (allocations)
+    for c in ctxs:
+        c.stats(reset=True)
     barrier()
     t0 = time.perf_counter()
     run(args.steps)
     barrier()
     dt = time.perf_counter() - t0
+    st = [c.stats() for c in ctxs]
+    nfr = max(1, sum(x["frames"] for x in st))
+    tot = lambda key: sum(x[key] for x in st)
     g = frames[0]
     E, T = g["edges"].shape[0], g["tris"].shape[0]
-    # graph_init: pos 2V + data V + weight V floats, 2V+6E ints (+ ~300 of chunk tables); mesh_bind: 12T + T
-    h2d = per_step * (4 * (4 * V) + 4 * (2 * V + 6 * E + 300) + 13 * T)
-    d2h = per_step * (4 * W * H + 12 * V)
+    # graph: pos 2V + data V + weight V floats, vertex order V + edges 2E ints (+ chunk tables); mesh: 12T
+    h2d = per_step * (4 * (4 * V) + 4 * (V + 2 * E + 300) + 12 * T + (5000 * 40 if search else 0))
+    d2h = per_step * (4 * W * H + 12 * V + (5000 * 40 if search else 0))
+    breakdown = {
+        "per_frame_us": {"vertex_order_and_plan": 1e6 * tot("prep_seconds") / nfr,
+                         "staging_and_upload_calls": 1e6 * (tot("stage_seconds") - tot("prep_seconds")) / nfr,
+                         "launches_and_download_calls": 1e6 * tot("enqueue_seconds") / nfr,
+                         "blocked_in_wait": 1e6 * tot("wait_seconds") / nfr},
+        "host_thread_busy_frac": (tot("stage_seconds") + tot("enqueue_seconds")) / (P * dt),
+        "h2d_GBps": h2d * args.steps / dt / 1e9, "d2h_GBps": d2h * args.steps / dt / 1e9,
+    }
     for c in ctxs:
         c.close()
+    for row in outs:
+        for o in row:
+            o.free()
     return {"seconds": dt, "frames": per_step * args.steps, "h2d": h2d, "d2h": d2h,
-            "per_step": per_step, "pipelines": P}
+            "per_step": per_step, "threads": P, "in_flight": P * R, "breakdown": breakdown}
 
 
 def main():
+    global CFG
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=56, help="frames per GPU per step")
+    ap.add_argument("--config", default="D", choices=["B", "C", "D"])
+    ap.add_argument("--batch", type=int, default=0,
+                    help="frames per GPU per step (0 = 40 waves of what the device keeps resident)")
     ap.add_argument("--wave", type=int, default=0,
                     help="frames per solver launch inside a step (0 = what the device keeps resident: pd_wave)")
     ap.add_argument("--no-async", action="store_true", help="projection in stream order (no second stream)")
-    ap.add_argument("--pipelines", type=int, default=16, help="host threads / streams for the e2e leg")
+    ap.add_argument("--pipelines", type=int, default=3, help="host threads (one context each) of the e2e leg")
+    ap.add_argument("--ring", type=int, default=8, help="frame slots in flight per e2e host thread")
+    ap.add_argument("--e2e-batch", type=int, default=480, help="frames per GPU per step of the e2e leg")
     ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 stream, 2 resident")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-search", action="store_true", help="skip the epipolar-search side measurement")
     args = ap.parse_args()
+    CFG = args.config
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -28,6 +28,13 @@ class PDParams(C.Structure):
                 ("theta", C.c_float), ("x_min", C.c_float), ("x_max", C.c_float)]
 
 
+class Stats(C.Structure):
+    """flame_b200_stats: host-side accounting of the frame pipeline."""
+    _fields_ = [("frames", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("prep_seconds", C.c_double), ("stage_seconds", C.c_double),
+                ("enqueue_seconds", C.c_double), ("wait_seconds", C.c_double)]
+
+
 class GraphIn(C.Structure):
     _fields_ = [("V", C.c_int32), ("E", C.c_int32), ("pos", f32p), ("edges", i32p),
                 ("data_term", f32p), ("data_weight", f32p),
@@ -89,6 +96,7 @@ DIAG_DTYPE = np.dtype([("flow_x", "<f4"), ("flow_y", "<f4"), ("mu_meas", "<f4"),
                        ("var_meas", "<f4"), ("stage", "<i4")])
 
 PD_AUTO, PD_STREAM, PD_RESIDENT = 0, 1, 2
+PREF_THROUGHPUT, PREF_LATENCY = 0, 1
 
 _lib = None
 
@@ -96,18 +104,20 @@ _lib = None
 SYMBOLS = [
     "flame_b200_last_error", "flame_b200_version", "flame_b200_kernel_launches",
     "flame_b200_ctx_create", "flame_b200_ctx_destroy", "flame_b200_ctx_sync", "flame_b200_ctx_stream",
-    "flame_b200_ctx_set_async_projection", "flame_b200_ctx_join",
+    "flame_b200_ctx_set_async_projection", "flame_b200_ctx_join", "flame_b200_ctx_set_pd_preference",
     "flame_b200_host_alloc", "flame_b200_host_free",
     "flame_b200_pd_default_params", "flame_b200_graph_upload", "flame_b200_graph_init",
     "flame_b200_graph_set_data", "flame_b200_graph_reset", "flame_b200_graph_download",
     "flame_b200_graph_project", "flame_b200_graph_resync", "flame_b200_pd_run", "flame_b200_pd_wave",
     "flame_b200_pd_cost", "flame_b200_interpolate_mesh", "flame_b200_mesh_bind",
     "flame_b200_mesh_project", "flame_b200_mesh_download", "flame_b200_process_frame",
+    "flame_b200_process_frame_submit", "flame_b200_process_frame_wait", "flame_b200_ctx_stats",
     "flame_b200_tri_filter_default_params", "flame_b200_mesh_filter", "flame_b200_mesh_coverage",
     "flame_b200_mesh_normals",
     "flame_b200_track_default_params",
     "flame_b200_set_camera", "flame_b200_frame_upload", "flame_b200_frame_upload_raw",
     "flame_b200_frame_download", "flame_b200_update_feature_idepths",
+    "flame_b200_features_upload", "flame_b200_features_track", "flame_b200_features_download",
 ]
 
 
@@ -128,6 +138,7 @@ def lib():
     L.flame_b200_ctx_sync.argtypes = [vp]
     L.flame_b200_ctx_set_async_projection.argtypes = [vp, C.c_int]
     L.flame_b200_ctx_join.argtypes = [vp]
+    L.flame_b200_ctx_set_pd_preference.argtypes = [vp, C.c_int]
     L.flame_b200_ctx_stream.argtypes = [vp]
     L.flame_b200_ctx_stream.restype = vp
     L.flame_b200_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -157,6 +168,11 @@ def lib():
     L.flame_b200_process_frame.argtypes = [vp, C.c_int, C.c_int32, f32p, f32p, f32p, C.c_int32, i32p, C.c_int32,
                                            i32p, C.c_int, C.c_int, C.POINTER(PDParams), C.c_int, C.c_float,
                                            vp, f32p, f32p, f32p]
+    L.flame_b200_process_frame_submit.argtypes = [vp, C.c_int, C.c_int32, f32p, f32p, f32p, C.c_int32, i32p,
+                                                  C.c_int32, i32p, C.c_int, C.c_int, C.POINTER(PDParams), C.c_int,
+                                                  C.c_float, vp]
+    L.flame_b200_process_frame_wait.argtypes = [vp, C.c_int, f32p, f32p, f32p]
+    L.flame_b200_ctx_stats.argtypes = [vp, C.POINTER(Stats), C.c_int]
     L.flame_b200_track_default_params.argtypes = [C.POINTER(TrackParams)]
     L.flame_b200_track_default_params.restype = None
     L.flame_b200_set_camera.argtypes = [vp, C.c_int, C.c_int, f32p, f32p]
@@ -165,6 +181,9 @@ def lib():
     L.flame_b200_frame_download.argtypes = [vp, C.c_int, u8p, f32p, f32p]
     L.flame_b200_update_feature_idepths.argtypes = [vp, C.POINTER(TrackParams), C.c_int, C.c_int, vp,
                                                     C.c_int32, vp, C.POINTER(C.c_int32)]
+    L.flame_b200_features_upload.argtypes = [vp, vp, C.c_int32]
+    L.flame_b200_features_track.argtypes = [vp, C.POINTER(TrackParams), C.c_int, C.c_int]
+    L.flame_b200_features_download.argtypes = [vp, vp, vp, C.POINTER(C.c_int32), C.c_int]
     _lib = L
     return L
 
@@ -266,6 +285,10 @@ class Context:
 
     def set_async_projection(self, on=True):
         check(lib().flame_b200_ctx_set_async_projection(self._h, int(on)))
+
+    def set_pd_preference(self, pref):
+        """PREF_THROUGHPUT (smallest cluster per frame) or PREF_LATENCY; applies to later uploads."""
+        check(lib().flame_b200_ctx_set_pd_preference(self._h, int(pref)))
 
     def join(self):
         """Device-side: order the pending (asynchronous) projection before later work on `stream`."""
@@ -403,6 +426,23 @@ class Context:
             out_map.ctypes.data_as(C.c_void_p) if out_map is not None else None, fptr(out_x), fptr(out_w1),
             fptr(out_w2)))
 
+    def process_frame_submit(self, slot, pos, idepth, edges, tris, rows, cols, params, n_iters, out_map,
+                             weight=None, scale=1.0):
+        """Enqueue a whole frame on the slot's own stream; inputs are consumed on return, out_map (pinned)
+        is written asynchronously and is valid after process_frame_wait(slot)."""
+        check(lib().flame_b200_process_frame_submit(
+            self._h, slot, pos.shape[0], fptr(pos), fptr(idepth), fptr(weight), edges.shape[0], iptr(edges),
+            tris.shape[0], iptr(tris), rows, cols, C.byref(params), n_iters, scale,
+            out_map.ctypes.data_as(C.c_void_p) if out_map is not None else None))
+
+    def process_frame_wait(self, slot, out_x=None, out_w1=None, out_w2=None):
+        check(lib().flame_b200_process_frame_wait(self._h, slot, fptr(out_x), fptr(out_w1), fptr(out_w2)))
+
+    def stats(self, reset=False):
+        st = Stats()
+        check(lib().flame_b200_ctx_stats(self._h, C.byref(st), int(reset)))
+        return {k: getattr(st, k) for k, _ in Stats._fields_}
+
     # ---- epipolar search ----
     def set_camera(self, width, height, K, Kinv):
         K = np.ascontiguousarray(K, np.float32).ravel()
@@ -436,3 +476,22 @@ class Context:
             self._h, C.byref(params), fnew, curr_pf, feats.ctypes.data_as(C.c_void_p), feats.shape[0],
             diag.ctypes.data_as(C.c_void_p) if want_diag else None, C.byref(n)))
         return n.value, diag
+
+    def features_upload(self, feats):
+        """Replace the device-resident feature set."""
+        assert feats.dtype == FEATURE_DTYPE and feats.flags["C_CONTIGUOUS"]
+        check(lib().flame_b200_features_upload(self._h, feats.ctypes.data_as(C.c_void_p), feats.shape[0]))
+        self._n_feats = feats.shape[0]
+
+    def features_track(self, params, fnew, curr_pf):
+        """Asynchronous, out-of-place search + measurement + fusion on the resident set."""
+        check(lib().flame_b200_features_track(self._h, C.byref(params), fnew, curr_pf))
+
+    def features_download(self, commit=True, want_diag=True):
+        feats = np.zeros(self._n_feats, FEATURE_DTYPE)
+        diag = np.zeros(self._n_feats, DIAG_DTYPE) if want_diag else None
+        n = C.c_int32()
+        check(lib().flame_b200_features_download(
+            self._h, feats.ctypes.data_as(C.c_void_p), diag.ctypes.data_as(C.c_void_p) if want_diag else None,
+            C.byref(n), int(commit)))
+        return n.value, feats, diag

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <memory>
 #include <mutex>
 
@@ -26,6 +27,11 @@ int stereo_frame_upload_raw(void** state, cudaStream_t st, int fslot, const uint
                             const float pose[7]);
 int stereo_frame_download(void* state, cudaStream_t st, int fslot, uint8_t* img_pad, float* gradx_pad,
                           float* grady_pad);
+int stereo_features_upload(void* state, cudaStream_t st, const flame_b200_feature* feats, int32_t n_feats);
+int stereo_features_track(void* state, cudaStream_t st, const flame_b200_track_params* params, int fnew,
+                          int curr_pf);
+int stereo_features_download(void* state, cudaStream_t st, flame_b200_feature* feats,
+                             flame_b200_track_diag* diag, int32_t* n_updates, int commit);
 void stereo_destroy(void* state);
 int stereo_graph_project(void* state, cudaStream_t st, const GraphDev& g, float* d_pos,
                          const float q[4], const float t[3], float scale, float* d_out);
@@ -42,6 +48,14 @@ struct Slot {
   unsigned char* h_blob = nullptr;
   size_t h_blob_cap = 0;
   cudaEvent_t blob_free = nullptr;  // recorded after the last async op that reads/writes h_blob
+  size_t stage_extra = 0;           // bytes the next graph upload reserves behind its own staging image
+  size_t stage_used = 0;            // end of the last graph upload's staging image inside h_blob
+  // asynchronous whole-frame pipeline (flame_b200_process_frame_submit / _wait)
+  cudaStream_t stream = nullptr;    // the slot's own stream: frames in different slots overlap
+  cudaEvent_t done = nullptr;       // recorded after the frame's last device->host copy
+  bool in_flight = false;
+  int out_V = 0;                    // vertex count of the frame in flight (x | w1 | w2 staged in h_blob)
+  size_t out_off = 0;               // where in h_blob
   int capV = 0, capE = 0;
   float* d_pos = nullptr;           // 2V caller order (kept for the dense projection)
   float* d_values = nullptr;        // V caller order
@@ -74,9 +88,7 @@ struct flame_b200_ctx {
   cudaStream_t stream = nullptr;
   std::vector<fb::Slot> slots;
   fb::GraphDev* d_graphs = nullptr;  // n_slots entries, mirrors slots[i].g
-  fb::GraphDev* h_graphs = nullptr;  // pinned
   fb::MeshDev* d_meshes = nullptr;   // n_slots entries, mirrors slots[i].m
-  fb::MeshDev* h_meshes = nullptr;   // pinned
   double* d_cost = nullptr;
   double* h_cost = nullptr;          // pinned, 2 doubles
   void* stereo = nullptr;
@@ -90,8 +102,11 @@ struct flame_b200_ctx {
   std::vector<cudaEvent_t> ev_pool;
   // host scratch for graph prep
   std::vector<uint32_t> keys, keys2;
-  std::vector<int> idx, idx2, vinv, cursor, degv, srcdeg, order, koff_tmp;
-  std::vector<uint64_t> halo_keys;
+  std::vector<int> idx, idx2, degv, srcdeg, order, koff_tmp, pre_deg, pre_src;
+  int pd_pref = 0;                   // FLAME_B200_PREF_*: how prep_plan sizes the frame clusters
+  // host-side accounting of the frame pipeline (flame_b200_ctx_stats)
+  double t_prep = 0, t_stage = 0, t_enqueue = 0, t_wait = 0;
+  uint64_t n_frames = 0, h2d_bytes = 0, d2h_bytes = 0;
 };
 
 namespace fb {
@@ -110,29 +125,41 @@ struct PrepOut {
   ResidentPlan plan{};
 };
 
-static size_t ints_total(int V, int E, int n_chunks, int max_deg) {
-  return (size_t)2 * V + (size_t)n_chunks * (max_deg + 1) + (size_t)n_chunks + 1 + (size_t)6 * E;
+// uploaded ints: [vperm V | koff n_chunks*(max_deg+1) | chunk_base n_chunks+1 | edges 2E]
+static size_t ints_uploaded(int V, int E, int n_chunks, int max_deg) {
+  return (size_t)V + (size_t)n_chunks * (max_deg + 1) + (size_t)n_chunks + 1 + (size_t)2 * E;
 }
-// + 2E ints of device-only space (edge_slot) after the uploaded image
-// then the resync maps (V + E) and the halo tables (2 (n_chunks + 1) + 2 H, H <= E)
+// device-built ints behind them: [vinv V | deg V | inc_nbr 2E | inc_edge 2E | edge_slot 2E],
+// then the resync maps [vtx_from V | edge_from E]
 static size_t blob_bytes(int V, int E, int n_chunks, int max_deg) {
-  return (raw_f_total(V, E) + ints_total(V, E, n_chunks, max_deg) + (size_t)2 * E + (size_t)V + E +
-          (size_t)2 * (n_chunks + 1) + (size_t)2 * E) * 4 + 256;
+  return (raw_f_total(V, E) + ints_uploaded(V, E, n_chunks, max_deg) + (size_t)2 * V + (size_t)6 * E +
+          (size_t)V + E) * 4 + 256;
 }
 
-// Internal order + private incidence layout (see GraphDev). O(V + E), deterministic.
+// Host side of the graph preparation: only the VERTEX order and the launch plan - O(V) work plus one
+// pass over the edge list for validation and degrees. (The launch configuration of the resident solver -
+// cluster size, shared-memory carve - has to be known on the host, which is why this part is not a kernel.)
+// The O(E) incidence layout is built on the device (pd.cu: k_layout_*).
 //  1. Morton (Z-curve) order of the vertices -> spatially compact chunks of Vc vertices;
-//  2. cluster size C / chunk width Vc from the shared-memory footprint (0 -> streaming chunks);
-//  3. stable sort by descending degree inside each chunk (uniform warps);
-//  4. incidence slots in ascending ORIGINAL edge id per vertex (the reference's summation order).
+//  2. cluster size C / chunk width Vc from the shared-memory footprint (0 -> streaming chunks).
 static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const int32_t* edges,
                      PrepOut* out) {
-  for (int e = 0; e < 2 * E; ++e)
-    if (edges[e] < 0 || edges[e] >= V) {
+  c->degv.assign(V, 0);
+  c->srcdeg.assign(V, 0);
+  for (int e = 0; e < E; ++e) {
+    const int s = edges[2 * e], d = edges[2 * e + 1];
+    if ((unsigned)s >= (unsigned)V || (unsigned)d >= (unsigned)V) {
       set_error("graph_upload: edge endpoint out of range");
       return FLAME_B200_EINVAL;
     }
-  // 1. Morton keys on the bounding box
+    c->degv[s]++;
+    c->degv[d]++;
+    c->srcdeg[s]++;
+  }
+  int max_deg = 0;
+  for (int v = 0; v < V; ++v) max_deg = std::max(max_deg, c->degv[v]);
+
+  // 1. Morton keys on the bounding box, 11 bits per axis; LSD radix sort, 2 x 11 bits, stable
   float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
   for (int v = 0; v < V; ++v) {
     xmin = std::min(xmin, pos[2 * v]);
@@ -141,15 +168,15 @@ static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const in
     ymax = std::max(ymax, pos[2 * v + 1]);
   }
   const float span = std::max(std::max(xmax - xmin, ymax - ymin), 1e-6f);
-  const float sc = 65535.0f / span;
+  const float sc = 2047.0f / span;
   c->keys.resize(V);
   c->keys2.resize(V);
   c->idx.resize(V);
   c->idx2.resize(V);
   for (int v = 0; v < V; ++v) {
     float fx = (pos[2 * v] - xmin) * sc, fy = (pos[2 * v + 1] - ymin) * sc;
-    uint32_t qx = (fx >= 0 && fx <= 65535.0f) ? (uint32_t)fx : 0u;  // NaN-safe
-    uint32_t qy = (fy >= 0 && fy <= 65535.0f) ? (uint32_t)fy : 0u;
+    uint32_t qx = (fx >= 0 && fx <= 2047.0f) ? (uint32_t)fx : 0u;  // NaN-safe
+    uint32_t qy = (fy >= 0 && fy <= 2047.0f) ? (uint32_t)fy : 0u;
     c->keys[v] = part1by1(qx) | (part1by1(qy) << 1);
     c->idx[v] = v;
   }
@@ -157,13 +184,13 @@ static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const in
   uint32_t* kb = c->keys2.data();
   int* ia = c->idx.data();
   int* ib = c->idx2.data();
-  for (int pass = 0; pass < 4; ++pass) {  // LSD radix sort, 4 x 8 bits, stable
-    size_t cnt[257] = {0};
-    const int sh = 8 * pass;
-    for (int v = 0; v < V; ++v) cnt[((ka[v] >> sh) & 255u) + 1]++;
-    for (int b = 0; b < 256; ++b) cnt[b + 1] += cnt[b];
+  for (int pass = 0; pass < 2; ++pass) {
+    int cnt[2049] = {0};
+    const int sh = 11 * pass;
+    for (int v = 0; v < V; ++v) cnt[((ka[v] >> sh) & 2047u) + 1]++;
+    for (int b = 0; b < 2048; ++b) cnt[b + 1] += cnt[b];
     for (int v = 0; v < V; ++v) {
-      const size_t d = cnt[(ka[v] >> sh) & 255u]++;
+      const int d = cnt[(ka[v] >> sh) & 2047u]++;
       kb[d] = ka[v];
       ib[d] = ia[v];
     }
@@ -173,54 +200,45 @@ static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const in
   c->order.assign(ia, ia + V);
   const int* morton = c->order.data();  // morton[i] = caller vertex at Morton position i
 
-  // degrees (caller index)
-  c->degv.assign(V, 0);
-  c->srcdeg.assign(V, 0);
-  for (int e = 0; e < 2 * E; ++e) c->degv[edges[e]]++;
-  for (int e = 0; e < E; ++e) c->srcdeg[edges[2 * e]]++;
-  int max_deg = 0;
-  for (int v = 0; v < V; ++v) max_deg = std::max(max_deg, c->degv[v]);
-
-  // 2. plan
+  // 2. plan: per-chunk incidence / owned-edge counts from prefix sums over the Morton order
+  c->pre_deg.resize(V + 1);
+  c->pre_src.resize(V + 1);
+  c->pre_deg[0] = c->pre_src[0] = 0;
+  for (int i = 0; i < V; ++i) {
+    c->pre_deg[i + 1] = c->pre_deg[i] + c->degv[morton[i]];
+    c->pre_src[i + 1] = c->pre_src[i] + c->srcdeg[morton[i]];
+  }
   int forced = 0;
   if (const char* sv = getenv("FLAME_B200_CLUSTER")) forced = atoi(sv);
   ResidentPlan plan{};
   if (V > 0 && V < (1 << 20) && max_deg <= FB_RESIDENT_MAX_DEG) {
-    // smallest cluster that holds the graph (any size, not only powers of two); the 640-thread variant
-    // (4 edges per thread in registers) is markedly faster than the 1024-thread one, so a larger cluster
-    // with the former beats a smaller one with the latter
-    for (int pass = 0; pass < 2 && !plan.cluster; ++pass)
+    // throughput (default): the smallest cluster that holds the graph - any size, not only powers of two -
+    // so that as many frames as possible are resident at once; latency: the smallest cluster of the
+    // 640-thread build (a frame spread over more SMs finishes sooner), falling back to the former
+    for (int pass = (c->pd_pref == FLAME_B200_PREF_LATENCY ? 0 : 1); pass < 2 && !plan.cluster; ++pass)
       for (int C = 1; C <= 16; ++C) {
         if (forced && C != forced) continue;
         const int Vc = (V + C - 1) / C;
-        int maxInc = 0, maxEdges = 0;
+        int maxInc = 1, maxEdges = 1;
         for (int k = 0; k < C; ++k) {
-          int inc = 0, ed = 0;
-          for (int i = std::min(k * Vc, V); i < std::min((k + 1) * Vc, V); ++i) {
-            inc += c->degv[morton[i]];
-            ed += c->srcdeg[morton[i]];
-          }
-          maxInc = std::max(maxInc, inc);
-          maxEdges = std::max(maxEdges, ed);
+          const int a = std::min(k * Vc, V), b = std::min((k + 1) * Vc, V);
+          maxInc = std::max(maxInc, c->pre_deg[b] - c->pre_deg[a]);
+          maxEdges = std::max(maxEdges, c->pre_src[b] - c->pre_src[a]);
         }
-        maxInc = std::max(maxInc, 1);
-        maxEdges = std::max(maxEdges, 1);
-        // the halo / push tables are only known after the layout is built: budget 24 KB for them here,
-        // graph_upload_impl re-checks with the real sizes
-        const size_t smem = pd_resident_smem(Vc, maxInc, maxEdges, max_deg, 0, 0) + (C > 1 ? 24 * 1024 : 0);
+        const size_t smem = pd_resident_smem(Vc, maxInc, maxEdges, max_deg);
         if (smem > 227 * 1024) continue;
         int thr = 0;
-        if (!pd_resident_variant(Vc, maxEdges, &thr)) continue;
-        if (pass == 0 && thr != 640) continue;
-        ResidentPlan pl{};
-        pl.cluster = C;
-        pl.Vc = Vc;
-        pl.maxInc = maxInc;
-        pl.maxEdges = maxEdges;
-        pl.max_deg = max_deg;
-        pl.smem_bytes = smem;
-        pl.threads = thr;
-        plan = pl;
+        const int variant = pd_resident_variant(Vc, maxEdges, &thr);
+        if (variant < 0) continue;
+        if (pass == 0 && variant != 0) continue;
+        plan.cluster = C;
+        plan.variant = variant;
+        plan.Vc = Vc;
+        plan.maxInc = maxInc;
+        plan.maxEdges = maxEdges;
+        plan.max_deg = max_deg;
+        plan.smem_bytes = smem;
+        plan.threads = thr;
         break;
       }
   }
@@ -230,29 +248,21 @@ static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const in
   out->n_chunks = n_chunks;
   out->max_deg = max_deg;
   out->plan = plan;
-
   return 0;
 }
 
+//  3. stable sort by descending degree inside each chunk (uniform warps) -> vperm; the slot tables
+//     koff / chunk_base: incidence k of the i-th vertex of chunk c lives at chunk_base[c] + koff[c][k] + i.
 static void prep_fill(flame_b200_ctx* c, int V, int E, const int32_t* edges, const PrepOut& pr,
-                      int* ints, int** p_vperm, int** p_deg, int** p_koff, int** p_chunk_base,
-                      int** p_inc_nbr, int** p_inc_edge, int** p_edges) {
+                      int* ints, int** p_vperm, int** p_koff, int** p_chunk_base, int** p_edges) {
   const int Vc = pr.Vc, n_chunks = pr.n_chunks, max_deg = pr.max_deg;
   const int* morton = c->order.data();
-  // blob int regions
   int* vperm = ints;
-  int* deg = vperm + V;
-  int* koff = deg + V;
+  int* koff = vperm + V;
   int* chunk_base = koff + (size_t)n_chunks * (max_deg + 1);
-  int* inc_nbr = chunk_base + n_chunks + 1;
-  int* inc_edge = inc_nbr + 2 * (size_t)E;
-  int* edges_out = inc_edge + 2 * (size_t)E;
-  *p_vperm = vperm; *p_deg = deg; *p_koff = koff; *p_chunk_base = chunk_base;
-  *p_inc_nbr = inc_nbr; *p_inc_edge = inc_edge; *p_edges = edges_out;
-  std::memcpy(edges_out, edges, (size_t)2 * E * sizeof(int));
-
-  // 3. per chunk: stable counting sort by DESCENDING degree; koff; chunk_base
-  c->vinv.resize(V);
+  int* edges_out = chunk_base + n_chunks + 1;
+  *p_vperm = vperm; *p_koff = koff; *p_chunk_base = chunk_base; *p_edges = edges_out;
+  if (E > 0) std::memcpy(edges_out, edges, (size_t)2 * E * sizeof(int));
   c->koff_tmp.assign(2 * (size_t)(max_deg + 2), 0);
   int* cnt = c->koff_tmp.data();         // cnt[d]   = #vertices of degree d in the chunk
   int* start = cnt + (max_deg + 2);      // start[d] = #vertices of degree > d (block start of d)
@@ -277,73 +287,9 @@ static void prep_fill(flame_b200_ctx* c, int V, int E, const int32_t* edges, con
     for (int d = 0; d <= max_deg; ++d) cnt[d] = start[d];  // write cursors
     for (int i = a; i < b; ++i) {
       const int o = morton[i];
-      const int dst = a + cnt[c->degv[o]]++;
-      vperm[dst] = o;
-      c->vinv[o] = dst;
-      deg[dst] = c->degv[o];
+      vperm[a + cnt[c->degv[o]]++] = o;
     }
   }
-
-  // 4. incidences in ascending original edge id
-  c->cursor.assign(V, 0);  // next k per internal vertex
-  for (int o = 0; o < E; ++o) {
-    const int s = c->vinv[edges[2 * o]], d = c->vinv[edges[2 * o + 1]];
-    {
-      const int ch = s / Vc, i = s - ch * Vc, k = c->cursor[s]++;
-      const int slot = chunk_base[ch] + koff[(size_t)ch * (max_deg + 1) + k] + i;
-      inc_nbr[slot] = (d << 1);
-      inc_edge[slot] = o;
-    }
-    {
-      const int ch = d / Vc, i = d - ch * Vc, k = c->cursor[d]++;
-      const int slot = chunk_base[ch] + koff[(size_t)ch * (max_deg + 1) + k] + i;
-      inc_nbr[slot] = (s << 1) | 1;
-      inc_edge[slot] = o;
-    }
-  }
-}
-
-// Halo tables of the resident solver (GraphDev::halo_*, push_*), written to `out` as
-// [halo_off n_chunks+1 | push_off n_chunks+1 | halo_vtx H | push_ent H]. Needs c->vinv from prep_fill.
-static void prep_halo(flame_b200_ctx* c, int E, const int32_t* edges, const PrepOut& pr, int* out, int* H_out,
-                      int* max_halo, int* max_push) {
-  const int Vc = pr.Vc, n_chunks = pr.n_chunks;
-  std::vector<uint64_t>& keys = c->halo_keys;
-  keys.clear();
-  for (int o = 0; o < E; ++o) {
-    const int s = c->vinv[edges[2 * o]], d = c->vinv[edges[2 * o + 1]];
-    if (s / Vc != d / Vc) keys.push_back(((uint64_t)(s / Vc) << 32) | (uint32_t)d);
-  }
-  std::sort(keys.begin(), keys.end());
-  keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-  const int H = (int)keys.size();
-  int* halo_off = out;
-  int* push_off = out + n_chunks + 1;
-  int* halo_vtx = push_off + n_chunks + 1;
-  int* push_ent = halo_vtx + H;
-  std::fill(halo_off, halo_off + 2 * (n_chunks + 1), 0);
-  for (int i = 0; i < H; ++i) {
-    halo_off[(keys[i] >> 32) + 1]++;
-    push_off[(int)(uint32_t)keys[i] / Vc + 1]++;
-  }
-  int mh = 0, mp = 0;
-  for (int ch = 0; ch < n_chunks; ++ch) {
-    mh = std::max(mh, halo_off[ch + 1]);
-    mp = std::max(mp, push_off[ch + 1]);
-    halo_off[ch + 1] += halo_off[ch];
-    push_off[ch + 1] += push_off[ch];
-  }
-  c->cursor.assign(n_chunks, 0);
-  for (int i = 0; i < H; ++i) {
-    const int ch = (int)(keys[i] >> 32), g = (int)(uint32_t)keys[i];
-    const int h = i - halo_off[ch];  // keys are sorted by (chunk, vertex): position inside the chunk
-    halo_vtx[i] = g;
-    const int r = g / Vc, il = g - r * Vc;
-    push_ent[push_off[r] + c->cursor[r]++] = il | (h << 11) | (ch << 27);
-  }
-  *H_out = H;
-  *max_halo = mh;
-  *max_push = mp;
 }
 
 static int check_slot(flame_b200_ctx* c, int slot, int n = 1) {
@@ -368,18 +314,40 @@ static int wait_blob(Slot& s) {
   return 0;
 }
 
+// Grow-only buffers. A pointer is nulled and its capacity zeroed right after the free, and the new
+// capacity is committed only once the allocation succeeded: a failed cudaMalloc leaves the slot empty
+// but consistent (no dangling pointer for a later call, no double free in ctx_destroy).
+template <typename T>
+static int regrow(T** p, size_t bytes) {
+  if (*p) {
+    cudaError_t e = cudaFree(*p);
+    *p = nullptr;
+    if (e != cudaSuccess) {
+      set_error(std::string("cudaFree: ") + cudaGetErrorString(e));
+      return FLAME_B200_ECUDA;
+    }
+  }
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes);
+  if (e != cudaSuccess) {
+    *p = nullptr;
+    set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? FLAME_B200_ENOMEM : FLAME_B200_ECUDA;
+  }
+  return 0;
+}
+
 static int ensure_blob(Slot& s, size_t need) {
   if (need > s.d_blob_cap) {
-    if (s.d_blob) FB_CUDA(cudaFree(s.d_blob));
-    s.d_blob = nullptr;
     const size_t n = std::max(need, s.d_blob_cap + s.d_blob_cap / 2);
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_blob), n));
+    s.d_blob_cap = 0;
+    if (int rc = regrow(&s.d_blob, n)) return rc;
     s.d_blob_cap = n;
   }
   if (need > s.h_blob_cap) {
+    const size_t n = std::max(need, s.h_blob_cap + s.h_blob_cap / 2);
+    s.h_blob_cap = 0;
     if (s.h_blob) FB_CUDA(cudaFreeHost(s.h_blob));
     s.h_blob = nullptr;
-    const size_t n = std::max(need, s.h_blob_cap + s.h_blob_cap / 2);
     FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s.h_blob), n));
     s.h_blob_cap = n;
   }
@@ -390,24 +358,23 @@ static int ensure_blob(Slot& s, size_t need) {
 static int ensure_graph(Slot& s, int V, int E) {
   if (V > s.capV) {
     const int n = std::max(V, s.capV + s.capV / 2);
-    for (void* p : {(void*)s.g.vprim, (void*)s.g.vbar, (void*)s.g.vbar2, (void*)s.g.vprev,
-                    (void*)s.g.vwt, (void*)s.d_pos, (void*)s.d_values})
-      if (p) FB_CUDA(cudaFree(p));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.vprim), (size_t)n * sizeof(float4)));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.vbar), (size_t)n * sizeof(float4)));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.vbar2), (size_t)n * sizeof(float4)));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.vprev), (size_t)n * sizeof(float4)));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.vwt), (size_t)n * sizeof(float)));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_pos), (size_t)n * 2 * sizeof(float)));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_values), (size_t)n * sizeof(float)));
+    s.capV = 0;
+    s.loaded = false;
+    if (int rc = regrow(&s.g.vprim, (size_t)n * sizeof(float4))) return rc;
+    if (int rc = regrow(&s.g.vbar, (size_t)n * sizeof(float4))) return rc;
+    if (int rc = regrow(&s.g.vbar2, (size_t)n * sizeof(float4))) return rc;
+    if (int rc = regrow(&s.g.vprev, (size_t)n * sizeof(float4))) return rc;
+    if (int rc = regrow(&s.g.vwt, (size_t)n * sizeof(float))) return rc;
+    if (int rc = regrow(&s.d_pos, (size_t)n * 2 * sizeof(float))) return rc;
+    if (int rc = regrow(&s.d_values, (size_t)n * sizeof(float))) return rc;
     s.capV = n;
   }
   if (E > s.capE) {
     const int n = std::max(E, s.capE + s.capE / 2);
-    if (s.g.inc_q) FB_CUDA(cudaFree(s.g.inc_q));
-    if (s.g.inc_s) FB_CUDA(cudaFree(s.g.inc_s));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.inc_q), (size_t)2 * n * sizeof(float4)));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.g.inc_s), (size_t)2 * n * sizeof(float4)));
+    s.capE = 0;
+    s.loaded = false;
+    if (int rc = regrow(&s.g.inc_q, (size_t)2 * n * sizeof(float4))) return rc;
+    if (int rc = regrow(&s.g.inc_s, (size_t)2 * n * sizeof(float4))) return rc;
     s.capE = n;
   }
   return 0;
@@ -418,17 +385,23 @@ static void fill_or_copy(float* dst, const float* src, size_t n, float fill) {
   else std::fill(dst, dst + n, fill);
 }
 
+// The device-side descriptor tables are written by a one-thread kernel whose argument IS the
+// descriptor: captured at launch, so there is no pinned staging copy a later call could overwrite
+// while an earlier copy is still queued.
+template <typename T>
+__global__ void k_publish(T* dst, T v) { *dst = v; }
+
 static int publish_mesh(flame_b200_ctx* c, int slot) {
-  c->h_meshes[slot] = c->slots[slot].m;
-  FB_CUDA(cudaMemcpyAsync(c->d_meshes + slot, c->h_meshes + slot, sizeof(MeshDev),
-                          cudaMemcpyHostToDevice, c->stream));
+  k_publish<MeshDev><<<1, 1, 0, c->stream>>>(c->d_meshes + slot, c->slots[slot].m);
+  count_launch();
+  FB_CUDA(cudaGetLastError());
   return 0;
 }
 
 static int publish_graph(flame_b200_ctx* c, int slot) {
-  c->h_graphs[slot] = c->slots[slot].g;
-  FB_CUDA(cudaMemcpyAsync(c->d_graphs + slot, c->h_graphs + slot, sizeof(GraphDev),
-                          cudaMemcpyHostToDevice, c->stream));
+  k_publish<GraphDev><<<1, 1, 0, c->stream>>>(c->d_graphs + slot, c->slots[slot].g);
+  count_launch();
+  FB_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -528,13 +501,9 @@ int flame_b200_ctx_create(int device, int n_slots, flame_b200_ctx** out) {
   c->slots.resize(n_slots);
   FB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_graphs), sizeof(GraphDev) * n_slots));
-  FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_graphs), sizeof(GraphDev) * n_slots));
   FB_CUDA(cudaMemset(c->d_graphs, 0, sizeof(GraphDev) * n_slots));
-  std::memset(c->h_graphs, 0, sizeof(GraphDev) * n_slots);
   FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_meshes), sizeof(MeshDev) * n_slots));
-  FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_meshes), sizeof(MeshDev) * n_slots));
   FB_CUDA(cudaMemset(c->d_meshes, 0, sizeof(MeshDev) * n_slots));
-  std::memset(c->h_meshes, 0, sizeof(MeshDev) * n_slots);
   FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_cost), 2 * sizeof(double)));
   FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_cost), 2 * sizeof(double)));
   if (int rc = pd_resident_init()) return rc;
@@ -547,6 +516,8 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
   cudaSetDevice(c->device);
   if (c->side) cudaStreamSynchronize(c->side);
   cudaStreamSynchronize(c->stream);
+  for (auto& sl : c->slots)
+    if (sl.stream) cudaStreamSynchronize(sl.stream);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->ev_vals) cudaEventDestroy(c->ev_vals);
   for (auto& pnd : c->pending) cudaEventDestroy(pnd.done);
@@ -562,12 +533,12 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
       if (p) cudaFree(p);
     if (s.h_blob) cudaFreeHost(s.h_blob);
     if (s.blob_free) cudaEventDestroy(s.blob_free);
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.stream) cudaStreamDestroy(s.stream);
   }
   stereo_destroy(c->stereo);
   cudaFree(c->d_graphs);
-  cudaFreeHost(c->h_graphs);
   cudaFree(c->d_meshes);
-  cudaFreeHost(c->h_meshes);
   cudaFree(c->d_cost);
   cudaFreeHost(c->h_cost);
   cudaStreamDestroy(c->stream);
@@ -579,6 +550,8 @@ int flame_b200_ctx_sync(flame_b200_ctx* c) {
   if (int rc = use_device(c)) return rc;
   if (int rc = join_side(c)) return rc;
   FB_CUDA(cudaStreamSynchronize(c->stream));
+  for (auto& sl : c->slots)
+    if (sl.stream) FB_CUDA(cudaStreamSynchronize(sl.stream));
   return 0;
 }
 
@@ -601,6 +574,15 @@ int flame_b200_ctx_join(flame_b200_ctx* c) {
 }
 
 void* flame_b200_ctx_stream(flame_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int flame_b200_ctx_set_pd_preference(flame_b200_ctx* c, int pref) {
+  if (!c || (pref != FLAME_B200_PREF_THROUGHPUT && pref != FLAME_B200_PREF_LATENCY)) {
+    set_error("ctx_set_pd_preference: bad arguments");
+    return FLAME_B200_EINVAL;
+  }
+  c->pd_pref = pref;
+  return 0;
+}
 
 int flame_b200_host_alloc(size_t bytes, void** out) {
   if (!out) return FLAME_B200_EINVAL;
@@ -638,7 +620,11 @@ static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph
   Slot& s = c->slots[slot];
   const int V = g->V, E = g->E;
   PrepOut prep;
+  timespec tp0, tp1;
+  clock_gettime(CLOCK_MONOTONIC, &tp0);
   if (int rc = prep_plan(c, V, E, g->pos, g->edges, &prep)) return rc;
+  clock_gettime(CLOCK_MONOTONIC, &tp1);
+  c->t_prep += (double)(tp1.tv_sec - tp0.tv_sec) + 1e-9 * (double)(tp1.tv_nsec - tp0.tv_nsec);
   if (int rc = wait_blob(s)) return rc;
   const int Vold = s.g.V, Eold = s.g.E;
   if (sync) {  // before any buffer of the old graph is touched
@@ -652,59 +638,54 @@ static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph
     }
     if (int rc = pd_unpack(c->stream, s.g, s.d_carry)) return rc;
   }
-  if (int rc = ensure_blob(s, blob_bytes(V, E, prep.n_chunks, prep.max_deg) +
-                                  (sync ? ((size_t)V + E) * 4 : 0))) return rc;
+  const size_t graph_stage = (blob_bytes(V, E, prep.n_chunks, prep.max_deg) + 255) & ~(size_t)255;
+  if (int rc = ensure_blob(s, graph_stage + s.stage_extra)) return rc;
+  s.stage_used = graph_stage;
   if (int rc = ensure_graph(s, V, E)) return rc;
 
   float* hf = reinterpret_cast<float*>(s.h_blob);
   int* hi = reinterpret_cast<int*>(hf + raw_f_total(V, E));
-  int *h_vperm, *h_deg, *h_koff, *h_chunk_base, *h_inc_nbr, *h_inc_edge, *h_edges;
-  prep_fill(c, V, E, g->edges, prep, hi, &h_vperm, &h_deg, &h_koff, &h_chunk_base, &h_inc_nbr,
-            &h_inc_edge, &h_edges);
+  int *h_vperm, *h_koff, *h_chunk_base, *h_edges;
+  clock_gettime(CLOCK_MONOTONIC, &tp0);
+  prep_fill(c, V, E, g->edges, prep, hi, &h_vperm, &h_koff, &h_chunk_base, &h_edges);
+  clock_gettime(CLOCK_MONOTONIC, &tp1);
+  c->t_prep += (double)(tp1.tv_sec - tp0.tv_sec) + 1e-9 * (double)(tp1.tv_nsec - tp0.tv_nsec);
   s.plan = prep.plan;
 
-  std::memcpy(hf + raw_f_offset(RF_POS, V, E), g->pos, (size_t)2 * V * sizeof(float));
+  if (V > 0) std::memcpy(hf + raw_f_offset(RF_POS, V, E), g->pos, (size_t)2 * V * sizeof(float));
   if (!fresh) {
-  fill_or_copy(hf + raw_f_offset(RF_X, V, E), g->x, V, 0.0f);
-  fill_or_copy(hf + raw_f_offset(RF_W1, V, E), g->w1, V, 0.0f);
-  fill_or_copy(hf + raw_f_offset(RF_W2, V, E), g->w2, V, 0.0f);
-  fill_or_copy(hf + raw_f_offset(RF_XB, V, E), g->x_bar ? g->x_bar : g->x, V, 0.0f);
-  fill_or_copy(hf + raw_f_offset(RF_W1B, V, E), g->w1_bar, V, 0.0f);
-  fill_or_copy(hf + raw_f_offset(RF_W2B, V, E), g->w2_bar, V, 0.0f);
-  fill_or_copy(hf + raw_f_offset(RF_XP, V, E), g->x_prev ? g->x_prev : g->x, V, 0.0f);
-  fill_or_copy(hf + raw_f_offset(RF_W1P, V, E), g->w1_prev, V, 0.0f);
-  fill_or_copy(hf + raw_f_offset(RF_W2P, V, E), g->w2_prev, V, 0.0f);
+    fill_or_copy(hf + raw_f_offset(RF_X, V, E), g->x, V, 0.0f);
+    fill_or_copy(hf + raw_f_offset(RF_W1, V, E), g->w1, V, 0.0f);
+    fill_or_copy(hf + raw_f_offset(RF_W2, V, E), g->w2, V, 0.0f);
+    fill_or_copy(hf + raw_f_offset(RF_XB, V, E), g->x_bar ? g->x_bar : g->x, V, 0.0f);
+    fill_or_copy(hf + raw_f_offset(RF_W1B, V, E), g->w1_bar, V, 0.0f);
+    fill_or_copy(hf + raw_f_offset(RF_W2B, V, E), g->w2_bar, V, 0.0f);
+    fill_or_copy(hf + raw_f_offset(RF_XP, V, E), g->x_prev ? g->x_prev : g->x, V, 0.0f);
+    fill_or_copy(hf + raw_f_offset(RF_W1P, V, E), g->w1_prev, V, 0.0f);
+    fill_or_copy(hf + raw_f_offset(RF_W2P, V, E), g->w2_prev, V, 0.0f);
   }
   if (sync && sync->x_init) fill_or_copy(hf + raw_f_offset(RF_X, V, E), sync->x_init, V, 0.0f);
   fill_or_copy(hf + raw_f_offset(RF_DATA, V, E), g->data_term, V, 0.0f);
   fill_or_copy(hf + raw_f_offset(RF_WT, V, E), g->data_weight, V, 1.0f);
   if (!fresh) {
-  fill_or_copy(hf + raw_f_offset(RF_ALPHA, V, E), g->alpha, E, 0.0f);
-  fill_or_copy(hf + raw_f_offset(RF_BETA, V, E), g->beta, E, 1.0f);
-  fill_or_copy(hf + raw_f_offset(RF_Q1, V, E), g->q1, E, 0.0f);
-  fill_or_copy(hf + raw_f_offset(RF_Q2, V, E), g->q2, E, 0.0f);
-  fill_or_copy(hf + raw_f_offset(RF_Q3, V, E), g->q3, E, 0.0f);
+    fill_or_copy(hf + raw_f_offset(RF_ALPHA, V, E), g->alpha, E, 0.0f);
+    fill_or_copy(hf + raw_f_offset(RF_BETA, V, E), g->beta, E, 1.0f);
+    fill_or_copy(hf + raw_f_offset(RF_Q1, V, E), g->q1, E, 0.0f);
+    fill_or_copy(hf + raw_f_offset(RF_Q2, V, E), g->q2, E, 0.0f);
+    fill_or_copy(hf + raw_f_offset(RF_Q3, V, E), g->q3, E, 0.0f);
   }
 
-  const size_t bytes = (raw_f_total(V, E) + ints_total(V, E, prep.n_chunks, prep.max_deg)) * 4;
-  // resync maps live after the device-only edge_slot table: [vtx_from V | edge_from E]
-  const size_t o_maps = bytes + (size_t)2 * E * 4, maps_bytes = sync ? ((size_t)V + E) * 4 : 0;
-  // halo tables of the resident solver after the (reserved) map area
-  const size_t o_halo = o_maps + ((size_t)V + E) * 4;
-  int H = 0;
-  prep_halo(c, E, g->edges, prep, reinterpret_cast<int*>(s.h_blob + o_halo), &H, &s.plan.maxHalo,
-            &s.plan.maxPush);
-  const size_t halo_bytes = ((size_t)2 * (prep.n_chunks + 1) + (size_t)2 * H) * 4;
-  if (s.plan.cluster > 0 &&
-      pd_resident_smem(s.plan.Vc, s.plan.maxInc, s.plan.maxEdges, s.plan.max_deg, s.plan.maxHalo,
-                       s.plan.maxPush) > 227 * 1024)
-    s.plan.cluster = 0;  // tables larger than budgeted: streaming path
+  const size_t n_up = ints_uploaded(V, E, prep.n_chunks, prep.max_deg);
+  const size_t bytes = (raw_f_total(V, E) + n_up) * 4;
+  // device-built tables, then the resync maps [vtx_from V | edge_from E]
+  const size_t o_dev = bytes;
+  const size_t o_maps = o_dev + ((size_t)2 * V + (size_t)6 * E) * 4, maps_bytes = sync ? ((size_t)V + E) * 4 : 0;
   if (sync) {
     int* hm = reinterpret_cast<int*>(s.h_blob + o_maps);
     if (V > 0) std::memcpy(hm, sync->vtx_from, (size_t)V * 4);
     if (E > 0) std::memcpy(hm + V, sync->edge_from, (size_t)E * 4);
   }
-  if (o_halo + halo_bytes > s.d_blob_cap || o_halo + halo_bytes > s.h_blob_cap) {
+  if (o_maps + maps_bytes > s.d_blob_cap || o_maps + maps_bytes > s.h_blob_cap) {
     set_error("internal: staging blob too small");
     return FLAME_B200_ENOMEM;
   }
@@ -724,17 +705,11 @@ static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph
       FB_CUDA(cudaMemcpyAsync(s.d_blob + o_x, s.h_blob + o_x, (size_t)V * 4, cudaMemcpyHostToDevice,
                               c->stream));
     }
-    if (maps_bytes)
-      FB_CUDA(cudaMemcpyAsync(s.d_blob + o_maps, s.h_blob + o_maps, maps_bytes, cudaMemcpyHostToDevice,
-                              c->stream));
   }
-  FB_CUDA(cudaMemcpyAsync(s.d_blob + o_halo, s.h_blob + o_halo, halo_bytes, cudaMemcpyHostToDevice, c->stream));
+  if (maps_bytes)
+    FB_CUDA(cudaMemcpyAsync(s.d_blob + o_maps, s.h_blob + o_maps, maps_bytes, cudaMemcpyHostToDevice,
+                            c->stream));
   FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
-  int* dh = reinterpret_cast<int*>(s.d_blob + o_halo);
-  s.g.halo_off = dh;
-  s.g.push_off = dh + prep.n_chunks + 1;
-  s.g.halo_vtx = s.g.push_off + prep.n_chunks + 1;
-  s.g.push_ent = s.g.halo_vtx + H;
   int* di = reinterpret_cast<int*>(s.d_raw() + raw_f_total(V, E));
   s.g.V = V;
   s.g.E = E;
@@ -742,13 +717,15 @@ static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph
   s.g.n_chunks = prep.n_chunks;
   s.g.max_deg = prep.max_deg;
   s.g.vperm = di + (h_vperm - hi);
-  s.g.deg = di + (h_deg - hi);
   s.g.koff = di + (h_koff - hi);
   s.g.chunk_base = di + (h_chunk_base - hi);
-  s.g.inc_nbr = di + (h_inc_nbr - hi);
-  s.g.inc_edge = di + (h_inc_edge - hi);
   s.g.edges = di + (h_edges - hi);
-  s.g.edge_slot = s.g.edges + 2 * (size_t)E;
+  int* dd = reinterpret_cast<int*>(s.d_blob + o_dev);
+  s.g.vinv = dd;
+  s.g.deg = dd + V;
+  s.g.inc_nbr = s.g.deg + V;
+  s.g.inc_edge = s.g.inc_nbr + 2 * (size_t)E;
+  s.g.edge_slot = s.g.inc_edge + 2 * (size_t)E;
   if (V > 0)
     FB_CUDA(cudaMemcpyAsync(s.d_pos, s.d_raw(), (size_t)2 * V * sizeof(float),
                             cudaMemcpyDeviceToDevice, c->stream));
@@ -953,14 +930,13 @@ int flame_b200_pd_run(flame_b200_ctx* c, int slot0, int n_slots, const flame_b20
     plan.maxInc = std::max(plan.maxInc, s.plan.maxInc);
     plan.maxEdges = std::max(plan.maxEdges, s.plan.maxEdges);
     plan.max_deg = std::max(plan.max_deg, s.plan.max_deg);
-    plan.maxHalo = std::max(plan.maxHalo, s.plan.maxHalo);
-    plan.maxPush = std::max(plan.maxPush, s.plan.maxPush);
     plan.threads = std::max(plan.threads, s.plan.threads);
   }
   if (n_iters == 0 || maxV == 0) return 0;
   if (fits) {
-    plan.smem_bytes = pd_resident_smem(plan.Vc, plan.maxInc, plan.maxEdges, plan.max_deg, plan.maxHalo, plan.maxPush);
-    if (plan.smem_bytes > 227 * 1024 || !pd_resident_variant(plan.Vc, plan.maxEdges, &plan.threads)) fits = false;
+    plan.smem_bytes = pd_resident_smem(plan.Vc, plan.maxInc, plan.maxEdges, plan.max_deg);
+    plan.variant = pd_resident_variant(plan.Vc, plan.maxEdges, &plan.threads);
+    if (plan.smem_bytes > 227 * 1024 || plan.variant < 0) fits = false;
   }
   if (mode == FLAME_B200_PD_RESIDENT && !fits) {
     set_error("pd_run: graph does not fit the resident (cluster shared memory) mode");
@@ -968,7 +944,7 @@ int flame_b200_pd_run(flame_b200_ctx* c, int slot0, int n_slots, const flame_b20
   }
   if (fits && mode != FLAME_B200_PD_STREAM)
     return pd_run_resident(c->stream, c->d_graphs + slot0, n_slots, plan, *params, n_iters);
-  const int threads = std::min(1024, (maxVc + 31) / 32 * 32);
+  const int threads = (maxVc + 31) / 32 * 32;  // widest chunk; the kernel covers it with 128-thread CTAs
   return pd_run_stream(c->stream, c->d_graphs + slot0, n_slots, max_chunks, threads, *params, n_iters);
 }
 
@@ -984,8 +960,9 @@ int flame_b200_pd_wave(flame_b200_ctx* c, int slot, int32_t* frames) {
   *frames = 0;
   if (s.g.V == 0 || s.plan.cluster == 0) return 0;
   ResidentPlan plan = s.plan;
-  plan.smem_bytes = pd_resident_smem(plan.Vc, plan.maxInc, plan.maxEdges, plan.max_deg, plan.maxHalo, plan.maxPush);
-  if (plan.smem_bytes > 227 * 1024 || !pd_resident_variant(plan.Vc, plan.maxEdges, &plan.threads)) return 0;
+  plan.smem_bytes = pd_resident_smem(plan.Vc, plan.maxInc, plan.maxEdges, plan.max_deg);
+  plan.variant = pd_resident_variant(plan.Vc, plan.maxEdges, &plan.threads);
+  if (plan.smem_bytes > 227 * 1024 || plan.variant < 0) return 0;
   int n = 0;
   if (int rc = pd_resident_capacity(plan, &n)) return rc;
   *frames = n;
@@ -1013,8 +990,11 @@ int flame_b200_pd_cost(flame_b200_ctx* c, int slot, const flame_b200_pd_params* 
 }
 
 // ---- dense projection ---------------------------------------------------------------------
+static inline size_t mesh_stage_bytes(int T) { return ((size_t)T * 13 + 64 + 255) & ~(size_t)255; }
+
 static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* tris, int32_t V,
-                          const uint8_t* vtx_valid, const uint8_t* tri_valid, int rows, int cols) {
+                          const uint8_t* vtx_valid, const uint8_t* tri_valid, int rows, int cols,
+                          bool behind_graph = false) {
   if (T < 0 || rows <= 0 || cols <= 0 || (T > 0 && !tris)) {
     set_error("mesh: bad arguments");
     return FLAME_B200_EINVAL;
@@ -1030,13 +1010,12 @@ static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* 
   }
   if (T > s.capT) {
     const int n = std::max(T, s.capT + s.capT / 2);
-    for (void* p : {(void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.d_tri_filt, (void*)s.m.setup, (void*)s.m.big})
-      if (p) FB_CUDA(cudaFree(p));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_tris), (size_t)n * 3 * sizeof(int)));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_tri_ok), (size_t)n));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_tri_filt), (size_t)n));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.setup), (size_t)n * sizeof(TriSetup)));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.big), (size_t)n * sizeof(int)));
+    s.capT = 0;
+    if (int rc = regrow(&s.d_tris, (size_t)n * 3 * sizeof(int))) return rc;
+    if (int rc = regrow(&s.d_tri_ok, (size_t)n)) return rc;
+    if (int rc = regrow(&s.d_tri_filt, (size_t)n)) return rc;
+    if (int rc = regrow(&s.m.setup, (size_t)n * sizeof(TriSetup))) return rc;
+    if (int rc = regrow(&s.m.big, (size_t)n * sizeof(int))) return rc;
     s.capT = n;
   }
   const size_t npix = (size_t)rows * cols;
@@ -1045,12 +1024,11 @@ static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* 
     return FLAME_B200_EINVAL;
   }
   if (npix > s.cap_pix) {
-    if (s.m.img) FB_CUDA(cudaFree(s.m.img));
-    if (s.m.owner) FB_CUDA(cudaFree(s.m.owner));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.img), npix * sizeof(float)));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.owner), npix * sizeof(unsigned int)));
-    s.cap_pix = npix;
+    s.cap_pix = 0;
     s.bound_pix = 0;
+    if (int rc = regrow(&s.m.img, npix * sizeof(float))) return rc;
+    if (int rc = regrow(&s.m.owner, npix * sizeof(unsigned int))) return rc;
+    s.cap_pix = npix;
   }
   if (!s.m.counters) FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.counters), 8 * sizeof(int)));
   if (npix != s.bound_pix) {
@@ -1067,34 +1045,47 @@ static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* 
   s.m.rows = rows;
   s.m.cols = cols;
   if (T > 0) {
-    // staged through the slot's pinned blob (tris + combined validity)
-    const size_t need = (size_t)T * 13 + 64;
-    if (int rc = wait_blob(s)) return rc;
-    if (need > s.h_blob_cap) {
-      if (s.h_blob) FB_CUDA(cudaFreeHost(s.h_blob));
-      s.h_blob = nullptr;
-      FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s.h_blob), need));
-      s.h_blob_cap = need;
+    // staged through the slot's pinned blob (tris + combined validity): at its start after waiting for the
+    // blob's previous use, or - behind_graph - in the space the graph upload of the SAME frame reserved
+    // behind its own staging image (Slot::stage_extra), which needs no wait
+    const size_t need = mesh_stage_bytes(T);
+    size_t off = 0;
+    if (behind_graph && s.stage_used + need <= s.h_blob_cap) {
+      off = s.stage_used;
+    } else {
+      if (int rc = wait_blob(s)) return rc;
+      if (need > s.h_blob_cap) {
+        s.h_blob_cap = 0;
+        if (s.h_blob) FB_CUDA(cudaFreeHost(s.h_blob));
+        s.h_blob = nullptr;
+        FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s.h_blob), need));
+        s.h_blob_cap = need;
+      }
     }
     if (!s.blob_free) FB_CUDA(cudaEventCreateWithFlags(&s.blob_free, cudaEventDisableTiming));
-    int* ht = reinterpret_cast<int*>(s.h_blob);
-    unsigned char* hok = s.h_blob + (size_t)T * 12;
+    int* ht = reinterpret_cast<int*>(s.h_blob + off);
     std::memcpy(ht, tris, (size_t)T * 12);
-    for (int t = 0; t < T; ++t) {
-      bool ok = !tri_valid || tri_valid[t];
-      if (ok && vtx_valid)
-        ok = vtx_valid[tris[3 * t]] && vtx_valid[tris[3 * t + 1]] && vtx_valid[tris[3 * t + 2]];
-      hok[t] = ok ? 1 : 0;
-    }
     FB_CUDA(cudaMemcpyAsync(s.d_tris, ht, (size_t)T * 12, cudaMemcpyHostToDevice, c->stream));
-    FB_CUDA(cudaMemcpyAsync(s.d_tri_ok, hok, (size_t)T, cudaMemcpyHostToDevice, c->stream));
+    if (!tri_valid && !vtx_valid) {
+      FB_CUDA(cudaMemsetAsync(s.d_tri_ok, 1, (size_t)T, c->stream));
+    } else {
+      unsigned char* hok = s.h_blob + off + (size_t)T * 12;
+      for (int t = 0; t < T; ++t) {
+        bool ok = !tri_valid || tri_valid[t];
+        if (ok && vtx_valid)
+          ok = vtx_valid[tris[3 * t]] && vtx_valid[tris[3 * t + 1]] && vtx_valid[tris[3 * t + 2]];
+        hok[t] = ok ? 1 : 0;
+      }
+      FB_CUDA(cudaMemcpyAsync(s.d_tri_ok, hok, (size_t)T, cudaMemcpyHostToDevice, c->stream));
+    }
     FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
   }
   return 0;
 }
 
-int flame_b200_mesh_bind(flame_b200_ctx* c, int slot, int32_t T, const int32_t* tris,
-                         const uint8_t* vtx_valid, const uint8_t* tri_valid, int rows, int cols) {
+static int mesh_bind_slot(flame_b200_ctx* c, int slot, int32_t T, const int32_t* tris,
+                          const uint8_t* vtx_valid, const uint8_t* tri_valid, int rows, int cols,
+                          bool behind_graph) {
   if (int rc = check_slot(c, slot)) return rc;
   if (int rc = use_device(c)) return rc;
   if (int rc = join_range(c, slot, slot + 1)) return rc;
@@ -1103,11 +1094,16 @@ int flame_b200_mesh_bind(flame_b200_ctx* c, int slot, int32_t T, const int32_t* 
     set_error("mesh_bind: slot has no graph");
     return FLAME_B200_ESTATE;
   }
-  if (int rc = mesh_bind_impl(c, s, T, tris, s.g.V, vtx_valid, tri_valid, rows, cols)) return rc;
+  if (int rc = mesh_bind_impl(c, s, T, tris, s.g.V, vtx_valid, tri_valid, rows, cols, behind_graph)) return rc;
   s.m.pos = s.d_pos;
   s.m.values = s.d_values;
   s.mesh_V = s.g.V;
   return publish_mesh(c, slot);
+}
+
+int flame_b200_mesh_bind(flame_b200_ctx* c, int slot, int32_t T, const int32_t* tris,
+                         const uint8_t* vtx_valid, const uint8_t* tri_valid, int rows, int cols) {
+  return mesh_bind_slot(c, slot, T, tris, vtx_valid, tri_valid, rows, cols, false);
 }
 
 int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float scale) {
@@ -1317,24 +1313,131 @@ int flame_b200_interpolate_mesh(flame_b200_ctx* c, int slot, int32_t T, const in
 }
 
 // ---- whole frame in one call ---------------------------------------------------------------------
+namespace {
+inline double now_s() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+// Library calls issue their work on c->stream; inside a frame submission that is the slot's own stream,
+// in stream order (no second projection stream: other slots' frames fill the machine instead).
+struct StreamScope {
+  flame_b200_ctx* c;
+  cudaStream_t saved;
+  bool saved_async;
+  StreamScope(flame_b200_ctx* c_, cudaStream_t st) : c(c_), saved(c_->stream), saved_async(c_->async_proj) {
+    c->stream = st;
+    c->async_proj = false;
+  }
+  ~StreamScope() {
+    c->stream = saved;
+    c->async_proj = saved_async;
+  }
+};
+}  // namespace
+
+int flame_b200_process_frame_submit(flame_b200_ctx* c, int slot, int32_t V, const float* pos,
+                                    const float* idepth, const float* weight, int32_t E,
+                                    const int32_t* edges, int32_t T, const int32_t* tris, int rows, int cols,
+                                    const flame_b200_pd_params* params, int n_iters, float scale,
+                                    float* out_map) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (int rc = use_device(c)) return rc;
+  Slot& s = c->slots[slot];
+  if (s.in_flight) {
+    set_error("process_frame_submit: the slot still has a frame in flight (call flame_b200_process_frame_wait)");
+    return FLAME_B200_ESTATE;
+  }
+  if (T < 0 || V < 0) {
+    set_error("process_frame_submit: bad arguments");
+    return FLAME_B200_EINVAL;
+  }
+  if (!s.stream) FB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  if (!s.done) FB_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  // work issued on the context's main stream for this slot earlier (uploads, projections) comes first
+  if (int rc = join_range(c, slot, slot + 1)) return rc;
+  FB_CUDA(cudaEventRecord(s.done, c->stream));
+  FB_CUDA(cudaStreamWaitEvent(s.stream, s.done, 0));
+  const double t0 = now_s();
+  StreamScope scope(c, s.stream);
+  // one pinned staging blob per slot: [graph image | triangles | x, w1, w2 coming back]
+  s.stage_extra = mesh_stage_bytes(T) + (((size_t)3 * V * 4 + 255) & ~(size_t)255);
+  int rc = flame_b200_graph_init(c, slot, V, pos, idepth, weight, E, edges);
+  s.stage_extra = 0;
+  if (rc) return rc;
+  if ((rc = mesh_bind_slot(c, slot, T, tris, nullptr, nullptr, rows, cols, true))) return rc;
+  const double t1 = now_s();
+  if ((rc = flame_b200_pd_run(c, slot, 1, params, n_iters, FLAME_B200_PD_AUTO))) return rc;
+  if ((rc = flame_b200_mesh_project(c, slot, 1, scale))) return rc;
+  if (out_map) {
+    if ((rc = flame_b200_mesh_download(c, slot, out_map))) return rc;
+    c->d2h_bytes += (uint64_t)rows * cols * 4;
+  }
+  // x | w1 | w2 (caller order) through the raw staging area, which is scratch between uploads
+  s.out_V = V;
+  s.out_off = s.stage_used + mesh_stage_bytes(T);
+  if (V > 0) {
+    if ((rc = pd_unpack_xw(c->stream, s.g, s.d_raw()))) return rc;
+    FB_CUDA(cudaMemcpyAsync(s.h_blob + s.out_off, s.d_raw(), (size_t)3 * V * 4, cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
+    c->d2h_bytes += (uint64_t)3 * V * 4;
+  }
+  FB_CUDA(cudaEventRecord(s.done, c->stream));
+  s.in_flight = true;
+  c->n_frames++;
+  c->h2d_bytes += (uint64_t)V * 16 + (uint64_t)V * 4 + (uint64_t)E * 8 + (uint64_t)T * 12;
+  c->t_enqueue += now_s() - t1;
+  c->t_stage += t1 - t0;  // includes t_prep (accounted separately inside graph_upload_impl)
+  return 0;
+}
+
+int flame_b200_process_frame_wait(flame_b200_ctx* c, int slot, float* out_x, float* out_w1, float* out_w2) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (int rc = use_device(c)) return rc;
+  Slot& s = c->slots[slot];
+  if (!s.in_flight) {
+    set_error("process_frame_wait: no frame in flight in this slot");
+    return FLAME_B200_ESTATE;
+  }
+  const double t0 = now_s();
+  s.in_flight = false;
+  FB_CUDA(cudaEventSynchronize(s.done));
+  c->t_wait += now_s() - t0;
+  const size_t V = (size_t)s.out_V;
+  const float* hf = reinterpret_cast<const float*>(s.h_blob + s.out_off);
+  if (V > 0) {
+    if (out_x) std::memcpy(out_x, hf, V * 4);
+    if (out_w1) std::memcpy(out_w1, hf + V, V * 4);
+    if (out_w2) std::memcpy(out_w2, hf + 2 * V, V * 4);
+  }
+  return 0;
+}
+
 int flame_b200_process_frame(flame_b200_ctx* c, int slot, int32_t V, const float* pos,
                              const float* idepth, const float* weight, int32_t E,
                              const int32_t* edges, int32_t T, const int32_t* tris, int rows, int cols,
                              const flame_b200_pd_params* params, int n_iters, float scale,
                              float* out_map, float* out_x, float* out_w1, float* out_w2) {
-  if (int rc = flame_b200_graph_init(c, slot, V, pos, idepth, weight, E, edges)) return rc;
-  if (int rc = flame_b200_mesh_bind(c, slot, T, tris, nullptr, nullptr, rows, cols)) return rc;
-  if (int rc = flame_b200_pd_run(c, slot, 1, params, n_iters, FLAME_B200_PD_AUTO)) return rc;
-  if (int rc = flame_b200_mesh_project(c, slot, 1, scale)) return rc;
-  if (out_map)
-    if (int rc = flame_b200_mesh_download(c, slot, out_map)) return rc;
-  flame_b200_graph_out o;
-  std::memset(&o, 0, sizeof(o));
-  o.x = out_x;
-  o.w1 = out_w1;
-  o.w2 = out_w2;
-  if (out_x || out_w1 || out_w2) return flame_b200_graph_download(c, slot, &o);  // synchronises
-  return flame_b200_ctx_sync(c);
+  if (int rc = flame_b200_process_frame_submit(c, slot, V, pos, idepth, weight, E, edges, T, tris, rows, cols,
+                                               params, n_iters, scale, out_map))
+    return rc;
+  return flame_b200_process_frame_wait(c, slot, out_x, out_w1, out_w2);
+}
+
+int flame_b200_ctx_stats(flame_b200_ctx* c, flame_b200_stats* out, int reset) {
+  if (!c || !out) return FLAME_B200_EINVAL;
+  out->frames = c->n_frames;
+  out->h2d_bytes = c->h2d_bytes;
+  out->d2h_bytes = c->d2h_bytes;
+  out->prep_seconds = c->t_prep;
+  out->stage_seconds = c->t_stage;
+  out->enqueue_seconds = c->t_enqueue;
+  out->wait_seconds = c->t_wait;
+  if (reset) {
+    c->n_frames = c->h2d_bytes = c->d2h_bytes = 0;
+    c->t_prep = c->t_stage = c->t_enqueue = c->t_wait = 0;
+  }
+  return 0;
 }
 
 // ---- epipolar search ------------------------------------------------------------------------
@@ -1365,6 +1468,25 @@ int flame_b200_frame_download(flame_b200_ctx* c, int fslot, uint8_t* img_pad, fl
   if (!c) return FLAME_B200_EINVAL;
   if (int rc = use_device(c)) return rc;
   return stereo_frame_download(c->stereo, c->stream, fslot, img_pad, gradx_pad, grady_pad);
+}
+
+int flame_b200_features_upload(flame_b200_ctx* c, const flame_b200_feature* feats, int32_t n_feats) {
+  if (!c || (n_feats > 0 && !feats) || n_feats < 0) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  return stereo_features_upload(c->stereo, c->stream, feats, n_feats);
+}
+
+int flame_b200_features_track(flame_b200_ctx* c, const flame_b200_track_params* params, int fnew, int curr_pf) {
+  if (!c || !params) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  return stereo_features_track(c->stereo, c->stream, params, fnew, curr_pf);
+}
+
+int flame_b200_features_download(flame_b200_ctx* c, flame_b200_feature* feats, flame_b200_track_diag* diag,
+                                 int32_t* n_updates, int commit) {
+  if (!c) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  return stereo_features_download(c->stereo, c->stream, feats, diag, n_updates, commit);
 }
 
 int flame_b200_update_feature_idepths(flame_b200_ctx* c, const flame_b200_track_params* params,

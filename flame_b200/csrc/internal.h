@@ -40,20 +40,15 @@ struct GraphDev {
   float* vwt;       // [V] data_weight
   float4* inc_q;    // [2E] q1, q2, q3, bits((neighbour internal index << 1) | is_target)
   float4* inc_s;    // [2E] alpha, beta, dx, dy   (dx = pos_source.x - pos_target.x)
-  int* deg;         // [V] internal order
+  int* deg;         // [V] internal order (device-built: the layout kernels' cursors)
   int* koff;        // [n_chunks][max_deg + 1]
   int* chunk_base;  // [n_chunks + 1]
   int* vperm;       // [V] internal -> caller vertex index
-  int* inc_nbr;     // [2E] (neighbour internal index << 1) | is_target   (pack input)
-  int* inc_edge;    // [2E] caller edge index of the incidence
+  int* vinv;        // [V] caller -> internal vertex index                      (device-built)
+  int* inc_nbr;     // [2E] (neighbour internal index << 1) | is_target          (device-built)
+  int* inc_edge;    // [2E] caller edge index of the incidence                   (device-built)
   int* edges;       // [2E] caller (source, target) pairs
-  int* edge_slot;   // [2E] (caller edge, role) -> incidence slot (written by the pack kernel)
-  // resident solver, halo exchange: chunk c keeps a local copy ("halo") of x_bar/w_bar of every vertex of
-  // another chunk that is the TARGET of an edge it owns; the owning chunk pushes the new values each iteration
-  int* halo_off;    // [n_chunks + 1]
-  int* halo_vtx;    // [H] internal vertex ids, ascending inside a chunk
-  int* push_off;    // [n_chunks + 1]
-  int* push_ent;    // [H] local vertex (bits 0-10) | halo index in the destination (11-26) | destination chunk (27-30)
+  int* edge_slot;   // [2E] (caller edge, role) -> incidence slot                (device-built)
 };
 
 struct __align__(16) TriSetup {  // per triangle, written by k_tri_setup; 80 bytes = 5 x 128-bit loads
@@ -83,26 +78,28 @@ struct MeshDev {
 // ---- PD (pd.cu) ----
 struct ResidentPlan {
   int cluster;        // CTAs per graph (0 = does not fit -> streaming)
+  int variant;        // index of the (threads, edges/thread, vertices/thread) build of k_pd_resident
   int threads;
   size_t smem_bytes;
   int Vc, maxInc, maxEdges, max_deg;
-  int maxHalo, maxPush;  // per-CTA maxima of the halo / push tables
 };
 #define FB_RESIDENT_MAX_DEG 64
+#define FB_RESIDENT_VARIANTS 3
 
 int pd_pack(cudaStream_t st, const GraphDev& g, const float* raw_f, int alpha_on_device, int fresh);
 int pd_unpack(cudaStream_t st, const GraphDev& g, float* raw_f);
+int pd_unpack_xw(cudaStream_t st, const GraphDev& g, float* out /*3V: x | w1 | w2, caller order*/);
 int pd_resync_gather(cudaStream_t st, float* raw_f, int V, int E, const float* carry, int Vold,
                      int Eold, const int* vtx_from, const int* edge_from, int has_init, int sticky);
 int pd_set_data(cudaStream_t st, const GraphDev& g, const float* data_term, const float* data_weight);
 int pd_reset(cudaStream_t st, const GraphDev* gs_dev, int n, int maxV, int maxE);
 int pd_run_stream(cudaStream_t st, const GraphDev* gs_dev, int n, int max_chunks, int threads,
                   const flame_b200_pd_params& p, int n_iters);
-size_t pd_resident_smem(int Vc, int maxInc, int maxEdges, int max_deg, int maxHalo, int maxPush);
-bool pd_resident_variant(int Vc, int maxEdges, int* threads);
+size_t pd_resident_smem(int Vc, int maxInc, int maxEdges, int max_deg);
+int pd_resident_variant(int Vc, int maxEdges, int* threads);  // -1: none fits
 int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const ResidentPlan& plan,
                     const flame_b200_pd_params& p, int n_iters);
-int pd_resident_init();  // one-time function attributes
+int pd_resident_init();  // function attributes, once per device
 int pd_resident_capacity(const ResidentPlan& plan, int* n_clusters);
 int pd_cost(cudaStream_t st, const GraphDev& g, const flame_b200_pd_params& p, int exact_order,
             float* terms_scratch, double* out_dev /*2 doubles*/);

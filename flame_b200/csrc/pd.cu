@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
 #include "internal.h"
 
@@ -131,56 +132,107 @@ __device__ __forceinline__ VertexOut vertex_finish(float x, float w1, float w2, 
 // ------------------------------------------------------------------------------------------
 static inline int nblk(int n, int t) { return (n + t - 1) / t; }
 
-// fresh != 0: only pos / data_term / data_weight were uploaded; the rest follows the fresh-vertex
-// rule of Flame::syncGraph (flame.cc:2039-2048): x = x_bar = x_prev = data_term, w* = 0, q* = 0, beta = 1.
-__global__ void k_pack_vertices(GraphDev g, const float* __restrict__ raw, int fresh) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= g.V) return;
-  const int o = g.vperm[v];
-  const int V = g.V;
-  const float* b = raw + 2 * (size_t)V;
-  if (fresh) {
-    const float d = b[9 * V + o];
-    g.vprim[v] = make_float4(d, 0.0f, 0.0f, d);
-    g.vbar[v] = make_float4(d, 0.0f, 0.0f, 0.0f);
-    g.vprev[v] = make_float4(d, 0.0f, 0.0f, 0.0f);
-    g.vwt[v] = b[10 * V + o];
-    return;
-  }
-  g.vprim[v] = make_float4(b[0 * V + o], b[1 * V + o], b[2 * V + o], b[9 * V + o]);
-  g.vbar[v] = make_float4(b[3 * V + o], b[4 * V + o], b[5 * V + o], 0.0f);
-  g.vprev[v] = make_float4(b[6 * V + o], b[7 * V + o], b[8 * V + o], 0.0f);
-  g.vwt[v] = b[10 * V + o];
+// ------------------------------------------------------------------------------------------
+// Device-side incidence layout. The host only orders the VERTICES (vperm, chunk tables: O(V)); the
+// O(E) part - which incidence slot every (edge, endpoint) gets - is built here:
+//   k_layout_begin    vinv = vperm^-1, per-vertex cursors = 0
+//   k_layout_scatter  one thread per edge claims a slot at each endpoint (atomic cursor: arbitrary k)
+//   k_layout_finish   one thread per vertex sorts its <= deg claimed (edge, role) keys into ascending
+//                     ORIGINAL edge id - the order in which the reference's sequential edge loop
+//                     (cc:118-142) applies its rounded += / -= to that vertex - and writes the
+//                     incidence records (q, alpha/beta/dx/dy, neighbour, edge <-> slot maps) and the
+//                     vertex records.
+// The final layout does not depend on the order in which the atomics were served.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ const int* koff_row(const GraphDev& g, int ch) {
+  return g.koff + (size_t)ch * (g.max_deg + 1);
+}
+__device__ __forceinline__ int inc_slot(const GraphDev& g, int v, int k) {
+  const int ch = v / g.Vc;
+  return g.chunk_base[ch] + koff_row(g, ch)[k] + (v - ch * g.Vc);
 }
 
-// one thread per incidence slot
-__global__ void k_pack_incidences(GraphDev g, const float* __restrict__ raw, int alpha_on_device,
-                                  int fresh) {
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= 2 * g.E) return;
-  const int o = g.inc_edge[slot];
+__global__ void k_layout_begin(GraphDev g) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= g.V) return;
+  g.vinv[g.vperm[v]] = v;
+  g.deg[v] = 0;
+}
+
+__global__ void k_layout_scatter(GraphDev g) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= g.E) return;
+  const int s = g.vinv[g.edges[2 * o]], d = g.vinv[g.edges[2 * o + 1]];
+  g.inc_edge[inc_slot(g, s, atomicAdd(&g.deg[s], 1))] = 2 * o;      // key = (edge << 1) | is_target
+  g.inc_edge[inc_slot(g, d, atomicAdd(&g.deg[d], 1))] = 2 * o + 1;
+}
+
+// fresh != 0: only pos / data_term / data_weight were uploaded; the rest follows the fresh-vertex
+// rule of Flame::syncGraph (flame.cc:2039-2048): x = x_bar = x_prev = data_term, w* = 0, q* = 0, beta = 1.
+__global__ void k_layout_finish(GraphDev g, const float* __restrict__ raw, int alpha_on_device, int fresh) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= g.V) return;
+  const int V = g.V;
   const size_t E = g.E;
-  const int os = g.edges[2 * o], od = g.edges[2 * o + 1];
-  const float dx = sub(raw[2 * os], raw[2 * od]);          // pos_i.x - pos_j.x (cc:100)
-  const float dy = sub(raw[2 * os + 1], raw[2 * od + 1]);
-  const float* b = raw + 13 * (size_t)g.V;
-  float alpha;
-  if (alpha_on_device) {
-    // flame.cc:2089-2092, 2102: alpha = 1 / sqrt(dx*dx + dy*dy)
-    const float len = __fsqrt_rn(add(mul(dx, dx), mul(dy, dy)));
-    alpha = __fdiv_rn(1.0f, len);
-  } else {
-    alpha = b[0 * E + o];
+  {  // vertex records
+    const int o = g.vperm[v];
+    const float* b = raw + 2 * (size_t)V;
+    if (fresh) {
+      const float d = b[9 * V + o];
+      g.vprim[v] = make_float4(d, 0.0f, 0.0f, d);
+      g.vbar[v] = make_float4(d, 0.0f, 0.0f, 0.0f);
+      g.vprev[v] = make_float4(d, 0.0f, 0.0f, 0.0f);
+    } else {
+      g.vprim[v] = make_float4(b[0 * V + o], b[1 * V + o], b[2 * V + o], b[9 * V + o]);
+      g.vbar[v] = make_float4(b[3 * V + o], b[4 * V + o], b[5 * V + o], 0.0f);
+      g.vprev[v] = make_float4(b[6 * V + o], b[7 * V + o], b[8 * V + o], 0.0f);
+    }
+    g.vwt[v] = b[10 * V + o];
   }
-  const int ent = g.inc_nbr[slot];
-  if (fresh) {
-    g.inc_s[slot] = make_float4(alpha, 1.0f, dx, dy);
-    g.inc_q[slot] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(ent));
-  } else {
-    g.inc_s[slot] = make_float4(alpha, b[1 * E + o], dx, dy);
-    g.inc_q[slot] = make_float4(b[2 * E + o], b[3 * E + o], b[4 * E + o], __int_as_float(ent));
+  const int ch = v / g.Vc, i = v - ch * g.Vc;
+  const int base = g.chunk_base[ch] + i;
+  const int* __restrict__ koff = koff_row(g, ch);
+  const int d = g.deg[v];
+  // insertion sort of the claimed keys (typical degree 6), in place: element k lives at base + koff[k]
+  for (int k = 1; k < d; ++k) {
+    const int key = g.inc_edge[base + koff[k]];
+    int j = k - 1;
+    while (j >= 0) {
+      const int kj = g.inc_edge[base + koff[j]];
+      if (kj <= key) break;
+      g.inc_edge[base + koff[j + 1]] = kj;
+      --j;
+    }
+    g.inc_edge[base + koff[j + 1]] = key;
   }
-  g.edge_slot[2 * o + (ent & 1)] = slot;  // inverse map: (edge, role) -> incidence slot
+  const float* eb = raw + 13 * (size_t)V;
+  for (int k = 0; k < d; ++k) {
+    const int slot = base + koff[k];
+    const int key = g.inc_edge[slot];
+    const int o = key >> 1, role = key & 1;
+    const int os = g.edges[2 * o], od = g.edges[2 * o + 1];
+    const float dx = sub(raw[2 * os], raw[2 * od]);          // pos_i.x - pos_j.x (cc:100)
+    const float dy = sub(raw[2 * os + 1], raw[2 * od + 1]);
+    float alpha;
+    if (alpha_on_device) {
+      // flame.cc:2089-2092, 2102: alpha = 1 / sqrt(dx*dx + dy*dy)
+      const float len = __fsqrt_rn(add(mul(dx, dx), mul(dy, dy)));
+      alpha = __fdiv_rn(1.0f, len);
+    } else {
+      alpha = eb[0 * E + o];
+    }
+    const int ent = (g.vinv[role ? os : od] << 1) | role;  // (neighbour internal index << 1) | is_target
+    if (fresh) {
+      g.inc_s[slot] = make_float4(alpha, 1.0f, dx, dy);
+      g.inc_q[slot] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(ent));
+    } else {
+      g.inc_s[slot] = make_float4(alpha, eb[1 * E + o], dx, dy);
+      g.inc_q[slot] = make_float4(eb[2 * E + o], eb[3 * E + o], eb[4 * E + o], __int_as_float(ent));
+    }
+    g.inc_nbr[slot] = ent;
+    g.inc_edge[slot] = o;
+    g.edge_slot[2 * o + role] = slot;  // inverse map: (edge, role) -> incidence slot
+  }
 }
 
 __global__ void k_unpack_vertices(GraphDev g, float* __restrict__ raw) {
@@ -290,14 +342,15 @@ int pd_resync_gather(cudaStream_t st, float* raw_f, int V, int E, const float* c
 }
 
 int pd_pack(cudaStream_t st, const GraphDev& g, const float* raw_f, int alpha_on_device, int fresh) {
-  if (g.V > 0) {
-    k_pack_vertices<<<nblk(g.V, 256), 256, 0, st>>>(g, raw_f, fresh);
-    count_launch();
-  }
+  if (g.V == 0) return 0;
+  k_layout_begin<<<nblk(g.V, 256), 256, 0, st>>>(g);
+  count_launch();
   if (g.E > 0) {
-    k_pack_incidences<<<nblk(2 * g.E, 256), 256, 0, st>>>(g, raw_f, alpha_on_device || fresh, fresh);
+    k_layout_scatter<<<nblk(g.E, 256), 256, 0, st>>>(g);
     count_launch();
   }
+  k_layout_finish<<<nblk(g.V, 128), 128, 0, st>>>(g, raw_f, alpha_on_device || fresh, fresh);
+  count_launch();
   FB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -311,6 +364,25 @@ int pd_unpack(cudaStream_t st, const GraphDev& g, float* raw_f) {
     k_unpack_incidences<<<nblk(2 * g.E, 256), 256, 0, st>>>(g, raw_f);
     count_launch();
   }
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// x, w1, w2 only, caller order, into out[0..3V) - what Flame::update reads back per frame (flame.cc:372-380)
+__global__ void k_unpack_xw(GraphDev g, float* __restrict__ out) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= g.V) return;
+  const int o = g.vperm[v];
+  const float4 p = g.vprim[v];
+  out[o] = p.x;
+  out[g.V + o] = p.y;
+  out[2 * (size_t)g.V + o] = p.z;
+}
+
+int pd_unpack_xw(cudaStream_t st, const GraphDev& g, float* out) {
+  if (g.V == 0) return 0;
+  k_unpack_xw<<<nblk(g.V, 256), 256, 0, st>>>(g, out);
+  count_launch();
   FB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -354,7 +426,7 @@ k_pd_stream(const GraphDev* __restrict__ gs, flame_b200_pd_params p, int parity,
   const int i = (blockIdx.x % ctas_per_chunk) * STREAM_T + threadIdx.x;
   if (i >= nv) return;
   const int base = g.chunk_base[c];
-  const int* __restrict__ koff = g.koff + (size_t)c * (g.max_deg + 1);
+  const int* __restrict__ koff = koff_row(g, c);
   const int v = v0 + i;
   const float4 pr = g.vprim[v];
   const float4 own = cur[v];
@@ -433,18 +505,23 @@ int pd_run_stream(cudaStream_t st, const GraphDev* gs_dev, int n, int max_chunks
 //     the cluster (st.shared::cluster). "+ -0.0f" is the exact identity of IEEE addition, so the
 //     target's slot needs no branch in phase B.
 //   barrier.cluster (release/acquire: remote stores visible)
-//   B (vertex-parallel): thread i < nv owns vertex i (x, w1, w2 in registers); it adds the
-//     contributions of its incidence slots in ascending ORIGINAL edge id — five rounded adds per
+//   B (vertex-parallel): a thread owns up to VPT vertices (x, w1, w2 in registers); it adds the
+//     contributions of their incidence slots in ascending ORIGINAL edge id — five rounded adds per
 //     incidence, bit-identical to the reference's sequential edge scatter (cc:125-141) — then proxL1
-//     and the extragradient step, and publishes x_bar/w_bar into the other half of a double buffer.
+//     and the extragradient step, and publishes x_bar/w_bar.
 //   barrier.cluster
+// Nobody reads x_bar between the two barriers, so ONE x_bar buffer suffices.
+//
+// The template parameters are the register budgets the kernel is built for: MAXT threads, SPT owned
+// edges and VPT vertices per thread. <1024,4,2> holds a 10 000-vertex Delaunay graph in a cluster of
+// NINE CTAs (two such clusters fit every GPC with >= 18 SMs: 15 frames in flight on 135 of the 148 SMs);
+// <640,4,1> is the low-latency variant for 16-CTA clusters (one frame spread over 16 SMs).
 // ------------------------------------------------------------------------------------------
 struct ResidentArgs {
   const GraphDev* gs;
   flame_b200_pd_params p;
   int n_iters;
   int Vc, maxInc, maxEdges, max_deg;  // batch maxima: identical shared-memory carve in every CTA
-  int maxHalo, maxPush;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -485,512 +562,244 @@ __device__ __forceinline__ void cluster_arrive() {
 __device__ __forceinline__ void cluster_wait() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-
-// ---- mbarrier + st.async (halo exchange of k_pd_resident_mb) ----
-__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
-}
-// remote arrival (release at cluster scope: everything this CTA wrote - by any of its threads, ordered
-// before this one by __syncthreads - is visible to whoever observes the phase with acquire.cluster)
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-      " selp.u32 %0, 1, 0, p;\n}"
-      : "=r"(ok)
-      : "r"(addr), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
-  for (unsigned spin = 0; !mbar_try_wait(addr, parity); ++spin)
-    if (spin > (1u << 22)) __trap();  // a lost arrival must not hang the device
+// Contribution records double as load-phase scratch (owned-edge list + per-vertex scan): the region
+// holds max(maxInc records, that scratch).
+__host__ __device__ inline int resident_p4_records(int maxInc, int maxEdges, int Vc) {
+  const int scratch = (maxEdges + Vc + 3) / 4;
+  return maxInc > scratch ? maxInc : scratch;
 }
 
-#define PD_MLP 2
-template <int MAXT, int SPT>
+template <int MAXT, int SPT, int VPT, int PD_MLP>
 __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
   const int C = cluster.num_blocks();
   const int c = cluster.block_rank();
   const GraphDev g = a.gs[blockIdx.x / C];
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x;
   const int Vc = g.Vc;  // this graph's chunk width (a.Vc >= Vc is the carve width)
 
   extern __shared__ __align__(128) unsigned char smem[];
-  float4* s_bar0 = reinterpret_cast<float4*>(smem);
-  float4* s_bar1 = s_bar0 + a.Vc;
-  float4* s_p4 = s_bar1 + a.Vc;      // per incidence slot: (sx, t1, t2, u1)
-  float4* s_s = s_p4 + a.maxInc;     // per owned edge: (alpha, beta, dx, dy)
-  float* s_p1 = reinterpret_cast<float*>(s_s + a.maxEdges);  // per incidence slot: u2
-  int* s_list = reinterpret_cast<int*>(s_p1 + a.maxInc);     // owned edges: their source slot
-  int* s_koff = s_list + a.maxEdges;                         // a.max_deg + 1
-  int* s_cnt = s_koff + a.max_deg + 1;                       // 1
-  int* s_scan = s_cnt + 1;                                   // blockDim.x (<= 1024), load phase only
+  float4* s_bar = reinterpret_cast<float4*>(smem);  // x_bar, w1_bar, w2_bar of the chunk's vertices
+  float4* s_p4 = s_bar + a.Vc;                      // per incidence slot: (sx, t1, t2, u1)
+  float4* s_s = s_p4 + resident_p4_records(a.maxInc, a.maxEdges, a.Vc);  // per owned edge: (alpha, beta, dx, dy)
+  float* s_p1 = reinterpret_cast<float*>(s_s + a.maxEdges);             // per incidence slot: u2
+  int* s_koff = reinterpret_cast<int*>(s_p1 + a.maxInc);                // a.max_deg + 1
+  int* s_cnt = s_koff + a.max_deg + 1;                                  // 1
+  unsigned int* s_list = reinterpret_cast<unsigned int*>(s_p4);  // load phase only: owned edges (vertex << 16 | slot)
+  int* s_scan = reinterpret_cast<int*>(s_list + a.maxEdges);     // load phase only: first owned edge of every vertex
 
   const bool have = c < g.n_chunks;
   const int v0 = c * Vc;
   const int nv = have ? min(Vc, g.V - v0) : 0;
   const int base = have ? g.chunk_base[c] : 0;
   const int ni = have ? g.chunk_base[c + 1] - base : 0;
-  const uint32_t bar0_addr = smem_u32(s_bar0);
-  const uint32_t bar_stride = (uint32_t)a.Vc * 16u;  // bar1 - bar0
+  const uint32_t bar_addr = smem_u32(s_bar);
   const uint32_t p4_addr = smem_u32(s_p4);
   const float neg0 = __int_as_float(0x80000000);
 
   // ---- load ----
   if (have)
-    for (int k = tid; k <= g.max_deg; k += nt) s_koff[k] = g.koff[(size_t)c * (g.max_deg + 1) + k];
-  if (tid == 0) *s_cnt = 0;
-  // vertex registers (thread i owns vertex i; the planner guarantees nv <= blockDim.x)
-  const bool hasv = tid < nv;
-  float x = 0.f, w1 = 0.f, w2 = 0.f, data = 0.f, wt = 0.f;
-  int deg = 0;
-  if (hasv) {
-    const float4 pr = g.vprim[v0 + tid];
-    x = pr.x; w1 = pr.y; w2 = pr.z; data = pr.w;
-    wt = g.vwt[v0 + tid];
-    deg = g.deg[v0 + tid];
-    s_bar0[tid] = g.vbar[v0 + tid];
+    for (int k = tid; k <= g.max_deg; k += MAXT) s_koff[k] = koff_row(g, c)[k];
+  __syncthreads();
+  // vertex registers: thread t owns vertices t, t + MAXT, ... of the chunk (nv <= MAXT * VPT)
+  float x[VPT], w1[VPT], w2[VPT], data[VPT], wt[VPT];
+  int deg[VPT];
+#pragma unroll
+  for (int v = 0; v < VPT; ++v) {
+    const int i = tid + v * MAXT;
+    x[v] = w1[v] = w2[v] = data[v] = wt[v] = 0.f;
+    deg[v] = 0;
+    if (i < nv) {
+      const float4 pr = g.vprim[v0 + i];
+      x[v] = pr.x; w1[v] = pr.y; w2[v] = pr.z; data[v] = pr.w;
+      wt[v] = g.vwt[v0 + i];
+      deg[v] = g.deg[v0 + i];
+      s_bar[i] = g.vbar[v0 + i];
+    }
+  }
+  // Owned edges = source-role incidence slots of this chunk, listed vertex by vertex (threads of a warp
+  // read the same / adjacent source records): per-vertex out-degree -> exclusive scan by warp 0 -> fill.
+#pragma unroll
+  for (int v = 0; v < VPT; ++v) {
+    const int i = tid + v * MAXT;
+    if (i < nv) {
+      int cnt = 0;
+      for (int k = 0; k < deg[v]; ++k) cnt += ((g.inc_nbr[base + s_koff[k] + i] & 1) == 0);
+      s_scan[i] = cnt;
+    }
   }
   __syncthreads();
-  // owned edges = source-role incidence slots of this chunk, listed vertex by vertex so that the
-  // threads of a warp read the same / adjacent source records (shared-memory broadcast, few bank
-  // conflicts). Deterministic: per-vertex out-degree -> block-wide exclusive scan -> fill.
-  int outdeg = 0;
-  if (hasv)
-    for (int k = 0; k < deg; ++k) outdeg += ((g.inc_nbr[base + s_koff[k] + tid] & 1) == 0);
-  s_scan[tid] = outdeg;
-  __syncthreads();
-  if (tid == 0) {  // nt <= 1024 entries, once per launch
+  if (tid < 32) {
     int run = 0;
-    for (int i = 0; i < nt; ++i) {
-      const int d0 = s_scan[i];
-      s_scan[i] = run;
-      run += d0;
+    for (int b = 0; b < nv; b += 32) {
+      const int i = b + tid;
+      const int d0 = (i < nv) ? s_scan[i] : 0;
+      int inc = d0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (tid >= o) inc += n;
+      }
+      if (i < nv) s_scan[i] = run + inc - d0;
+      run += __shfl_sync(0xffffffffu, inc, 31);
     }
-    *s_cnt = run;
+    if (tid == 0) *s_cnt = run;
   }
   __syncthreads();
-  if (hasv) {
-    int at = s_scan[tid];
-    for (int k = 0; k < deg; ++k) {
-      const int slot = s_koff[k] + tid;
-      if ((g.inc_nbr[base + slot] & 1) == 0) s_list[at++] = slot;
+  const int ne = *s_cnt;  // <= MAXT * SPT (planner)
+#pragma unroll
+  for (int v = 0; v < VPT; ++v) {
+    const int i = tid + v * MAXT;
+    if (i < nv) {
+      int at = s_scan[i];
+      for (int k = 0; k < deg[v]; ++k) {
+        const int slot = s_koff[k] + i;
+        if ((g.inc_nbr[base + slot] & 1) == 0) s_list[at++] = ((unsigned int)i << 16) | (unsigned int)slot;
+      }
     }
   }
   __syncthreads();
-  for (int slot = tid; slot < ni; slot += nt)
-    s_p1[slot] = neg0;  // target slots keep -0.0f forever; source slots are rewritten every iteration
-  const int ne = *s_cnt;
   float q1[SPT], q2[SPT], q3[SPT];
-  uint32_t src_bar[SPT];   // shared::cta address of the source's bar0 record
-  uint32_t dst_bar[SPT];   // shared::cluster address of the target's bar0 record
-  uint32_t src_slot[SPT];  // local incidence slot of the source endpoint
-  uint32_t dst_p4[SPT];    // shared::cluster address of the target endpoint's p4 record
+  uint32_t src[SPT];      // (local index of the source vertex << 16) | local incidence slot of the source
+  uint32_t dst_bar[SPT];  // address of the target's x_bar record: shared::cta, or shared::cluster | 1 if remote
+  uint32_t dst_p4[SPT];   // address of the target endpoint's p4 record (same address space as dst_bar)
 #pragma unroll
   for (int u = 0; u < SPT; ++u) {
-    const int j = tid + u * nt;
+    const int j = tid + u * MAXT;
     q1[u] = q2[u] = q3[u] = 0.f;
-    src_bar[u] = bar0_addr;
-    dst_bar[u] = bar0_addr;
-    src_slot[u] = 0;
+    src[u] = 0;
+    dst_bar[u] = bar_addr;
     dst_p4[u] = p4_addr;
     if (j < ne) {
-      const int slot = s_list[j];
+      src[u] = s_list[j];
+      const int slot = (int)(src[u] & 0xFFFFu);
       const float4 q = g.inc_q[base + slot];
       q1[u] = q.x; q2[u] = q.y; q3[u] = q.z;
       s_s[j] = g.inc_s[base + slot];
-      src_slot[u] = (uint32_t)slot;
-      // source vertex of the slot: slot = koff[k] + i with koff non-decreasing in k
-      int k = 0;
-      while (k + 1 <= g.max_deg && s_koff[k + 1] <= slot) ++k;
-      src_bar[u] = bar0_addr + (uint32_t)(slot - s_koff[k]) * 16u;
       const int nbr = __float_as_int(q.w) >> 1;
-      const int oc = nbr / Vc;
+      const int oc = nbr / Vc;  // the target vertex lives in chunk oc, and so do its slots
       // bit 0 of dst_bar = "target lives in another CTA": only those go through the DSMEM path
       // (ld/st.shared::cluster is several times slower than ld/st.shared even for the own CTA)
       const bool remote = (oc != c);
-      dst_bar[u] = remote ? (mapa(bar0_addr + (uint32_t)(nbr - oc * Vc) * 16u, (uint32_t)oc) | 1u)
-                          : (bar0_addr + (uint32_t)(nbr - oc * Vc) * 16u);
-      // the target endpoint's incidence slot of this edge (global slot id -> owner chunk, local slot)
+      const uint32_t tb = bar_addr + (uint32_t)(nbr - oc * Vc) * 16u;
       const int tslot = g.edge_slot[2 * g.inc_edge[base + slot] + 1];
-      int tc = oc;  // the target vertex lives in chunk oc, and so do its slots
-      dst_p4[u] = remote ? mapa(p4_addr + (uint32_t)(tslot - g.chunk_base[tc]) * 16u, (uint32_t)tc)
-                         : (p4_addr + (uint32_t)(tslot - g.chunk_base[tc]) * 16u);
+      const uint32_t tp = p4_addr + (uint32_t)(tslot - g.chunk_base[oc]) * 16u;
+      dst_bar[u] = remote ? (mapa(tb, (uint32_t)oc) | 1u) : tb;
+      dst_p4[u] = remote ? mapa(tp, (uint32_t)oc) : tp;
     }
   }
+  __syncthreads();  // s_list / s_scan (aliases of s_p4) are dead from here on
+  for (int slot = tid; slot < ni; slot += MAXT)
+    s_p1[slot] = neg0;  // target slots keep -0.0f forever; source slots are rewritten every iteration
   cluster.sync();
 
   const flame_b200_pd_params p = a.p;
 
-  for (int it = 0; it < a.n_iters; ++it) {
-    const uint32_t cur_off = (it & 1) ? bar_stride : 0u;
-    const float4* cur = (it & 1) ? s_bar1 : s_bar0;
-    float4* nxt = (it & 1) ? s_bar0 : s_bar1;
-    // ---- phase A: one dual update per edge, contributions pushed to both endpoints ----
-    // Rounds of PD_MLP edges: all operand loads of a round are issued before its arithmetic so the
-    // shared-memory / DSMEM latencies overlap.
+  // ---- phase A: one dual update per edge, contributions pushed to both endpoints ----
+  // Rounds of PD_MLP edges: all operand loads of a round are issued before its arithmetic so the
+  // shared-memory / DSMEM latencies overlap.
+  auto phase_a = [&]() {
 #pragma unroll
     for (int u0 = 0; u0 < SPT; u0 += PD_MLP) {
       float4 s[PD_MLP], bi[PD_MLP], bj[PD_MLP];
 #pragma unroll
       for (int v = 0; v < PD_MLP; ++v) {
         const int u = u0 + v;
-        if (u < SPT && tid + u * nt < ne) {
-          s[v] = s_s[tid + u * nt];
-          bi[v] = cur[(src_bar[u] - bar0_addr) >> 4];
-          bj[v] = (dst_bar[u] & 1u) ? ld_cluster_f4((dst_bar[u] & ~1u) + cur_off)
-                                    : ld_shared_f4(dst_bar[u] + cur_off);
+        if (u < SPT && tid + u * MAXT < ne) {
+          s[v] = s_s[tid + u * MAXT];
+          bi[v] = s_bar[src[u] >> 16];
+          bj[v] = (dst_bar[u] & 1u) ? ld_cluster_f4(dst_bar[u] & ~1u) : ld_shared_f4(dst_bar[u]);
         }
       }
 #pragma unroll
       for (int v = 0; v < PD_MLP; ++v) {
         const int u = u0 + v;
-        if (u < SPT && tid + u * nt < ne) {
+        if (u < SPT && tid + u * MAXT < ne) {
           const float4 qu = dual_update(make_float4(q1[u], q2[u], q3[u], 0.f), s[v], bi[v], bj[v], p.step_q);
           q1[u] = qu.x; q2[u] = qu.y; q3[u] = qu.z;
           // primalStep contributions (cc:125-141), rounded as the reference: a = (q1*step_x)*alpha ...
           const float pa = mul(mul(qu.x, p.step_x), s[v].x);
           const float b2 = mul(mul(qu.y, p.step_x), s[v].y);
           const float b3 = mul(mul(qu.z, p.step_x), s[v].y);
+          const uint32_t sl = src[u] & 0xFFFFu;
           // source i: x -= a; w1 += a*dx; w2 += a*dy; w1 -= b2; w2 -= b3
-          s_p4[src_slot[u]] = make_float4(-pa, mul(pa, s[v].z), mul(pa, s[v].w), -b2);
-          s_p1[src_slot[u]] = -b3;
+          s_p4[sl] = make_float4(-pa, mul(pa, s[v].z), mul(pa, s[v].w), -b2);
+          s_p1[sl] = -b3;
           // target j: x += a; w1 += b2; w2 += b3   (u1 = u2 = -0.0f: exact no-ops)
           if (dst_bar[u] & 1u) st_cluster_f4(dst_p4[u], make_float4(pa, b2, b3, neg0));
           else st_shared_f4(dst_p4[u], make_float4(pa, b2, b3, neg0));
         }
       }
     }
-    cluster_arrive();
-    cluster_wait();
-    // ---- phase B: ordered accumulation + prox + extragradient, one vertex per thread ----
-    if (hasv) {
-      const float x_old = x, w1_old = w1, w2_old = w2;
-      // software pipeline: the contribution record of incidence k+1 is in flight while k is added
-      float4 p4n = make_float4(0.f, 0.f, 0.f, 0.f);
-      float p1n = 0.f;
-      if (deg > 0) {
-        p4n = s_p4[tid];  // koff[0] == 0
-        p1n = s_p1[tid];
-      }
-      int ko = (deg > 1) ? s_koff[1] : 0;
-      for (int k = 0; k < deg; ++k) {
-        const float4 p4 = p4n;
-        const float p1 = p1n;
-        if (k + 1 < deg) {
-          const int slot = ko + tid;
-          p4n = s_p4[slot];
-          p1n = s_p1[slot];
-          ko = s_koff[k + 2];  // k + 2 <= max_deg: inside the table
-        }
-        x = add(x, p4.x);
-        w1 = add(w1, p4.y);
-        w2 = add(w2, p4.z);
-        w1 = add(w1, p4.w);
-        w2 = add(w2, p1);
-      }
-      const VertexOut o = vertex_finish(x, w1, w2, data, wt, x_old, w1_old, w2_old, p);
-      x = o.prim.x;
-      nxt[tid] = o.bar;
-      if (it == a.n_iters - 1) g.vprev[v0 + tid] = make_float4(x_old, w1_old, w2_old, 0.0f);
-    }
-    cluster_arrive();
-    cluster_wait();
-  }
+  };
 
-  // ---- write back (both private copies of every edge's q) ----
-  if (hasv) {
-    const float4* fin = (a.n_iters & 1) ? s_bar1 : s_bar0;
-    g.vbar[v0 + tid] = fin[tid];
-    g.vprim[v0 + tid] = make_float4(x, w1, w2, data);
-  }
+  // ---- phase B: ordered accumulation + prox + extragradient ----
+  auto phase_b = [&](const bool last) {
+    const int* kr = s_koff;
 #pragma unroll
-  for (int u = 0; u < SPT; ++u) {
-    const int j = tid + u * nt;
-    if (j < ne) {
-      const int sslot = base + (int)src_slot[u];
-      const int tslot = g.edge_slot[2 * g.inc_edge[sslot] + 1];
-      g.inc_q[sslot] = make_float4(q1[u], q2[u], q3[u], __int_as_float(g.inc_nbr[sslot]));
-      g.inc_q[tslot] = make_float4(q1[u], q2[u], q3[u], __int_as_float(g.inc_nbr[tslot]));
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// RESIDENT mode, halo exchange (experimental, FLAME_B200_PD_SYNC=p2p). Same phases and arithmetic as
-// k_pd_resident, but no
-// cluster-wide barrier and no remote LOADS inside the iteration:
-//   * every CTA keeps a local copy ("halo") of x_bar/w_bar of the remote target vertices of its edges,
-//     laid out behind its own vertices ([bar0 | halo0 | bar1 | halo1]), so phase A reads only its own
-//     shared memory; the owners store the new values into their neighbours' halos after phase B;
-//   * synchronisation is point to point: after its remote stores (target contributions of cut edges in
-//     phase A, halo values after phase B) a CTA arrives - release.cluster, one thread per neighbour -
-//     on an mbarrier of each CTA it wrote to; a CTA waits - acquire.cluster, one lane per warp - until
-//     all of its in-neighbours have arrived: contributions before phase B, halos before the next phase
-//     A. Neighbours are never more than one phase apart because each direction of traffic gates the
-//     other (S's contributions gate R's phase B, R's halo gates S's next phase A), so one mbarrier per
-//     direction and double-buffered x_bar/halo records suffice.
-// ------------------------------------------------------------------------------------------
-template <int MAXT, int SPT>
-__global__ void __launch_bounds__(MAXT, 1) k_pd_resident_mb(ResidentArgs a) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int C = cluster.num_blocks();
-  const int c = cluster.block_rank();
-  const GraphDev g = a.gs[blockIdx.x / C];
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int Vc = g.Vc;  // this graph's chunk width (a.Vc >= Vc is the carve width)
-
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int row = a.Vc + a.maxHalo;  // vertices + halo entries of one buffer
-  float4* s_bar0 = reinterpret_cast<float4*>(smem);
-  float4* s_bar1 = s_bar0 + row;
-  float4* s_p4 = s_bar1 + row;       // per incidence slot: (sx, t1, t2, u1)
-  float4* s_s = s_p4 + a.maxInc;     // per owned edge: (alpha, beta, dx, dy)
-  float* s_p1 = reinterpret_cast<float*>(s_s + a.maxEdges);  // per incidence slot: u2
-  int* s_list = reinterpret_cast<int*>(s_p1 + a.maxInc);     // owned edges: their source slot
-  int* s_koff = s_list + a.maxEdges;                         // a.max_deg + 1
-  int* s_cnt = s_koff + a.max_deg + 1;                       // 2: owned edges, expected contribution slots
-  int* s_scan = s_cnt + 2;                                   // blockDim.x (<= 1024), load phase only
-  int* s_push_v = s_scan + 1024;                             // a.maxPush: local vertex to publish
-  uint32_t* s_push_addr = reinterpret_cast<uint32_t*>(s_push_v + a.maxPush);  // its halo record (buffer 0) there
-  unsigned int* s_mask = s_push_addr + a.maxPush;            // 2: ranks holding my halos' owners / my push targets
-  unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(
-      (reinterpret_cast<uintptr_t>(s_mask + 2) + 7) & ~uintptr_t(7));  // [0] contributions, [1] halos
-
-  const bool have = c < g.n_chunks;
-  const int v0 = c * Vc;
-  const int nv = have ? min(Vc, g.V - v0) : 0;
-  const int base = have ? g.chunk_base[c] : 0;
-  const int ni = have ? g.chunk_base[c + 1] - base : 0;
-  const int h0 = have ? g.halo_off[c] : 0;
-  const int nh = have ? g.halo_off[c + 1] - h0 : 0;
-  const int np = have ? g.push_off[c + 1] - g.push_off[c] : 0;
-  const uint32_t bar0_addr = smem_u32(s_bar0);
-  const uint32_t bar_stride = (uint32_t)row * 16u;  // bar1 - bar0
-  const uint32_t p4_addr = smem_u32(s_p4);
-  const uint32_t mbc_addr = smem_u32(s_mbar), mbh_addr = mbc_addr + 8u;
-  const float neg0 = __int_as_float(0x80000000);
-
-  // ---- load ----
-  if (have)
-    for (int k = tid; k <= g.max_deg; k += nt) s_koff[k] = g.koff[(size_t)c * (g.max_deg + 1) + k];
-  if (tid == 0) {
-    s_cnt[0] = 0;
-    s_mask[0] = 0u;
-    s_mask[1] = 0u;
-  }
-  __syncthreads();
-  const bool hasv = tid < nv;
-  float x = 0.f, w1 = 0.f, w2 = 0.f, data = 0.f, wt = 0.f;
-  int deg = 0;
-  if (hasv) {
-    const float4 pr = g.vprim[v0 + tid];
-    x = pr.x; w1 = pr.y; w2 = pr.z; data = pr.w;
-    wt = g.vwt[v0 + tid];
-    deg = g.deg[v0 + tid];
-    s_bar0[tid] = g.vbar[v0 + tid];
-  }
-  for (int h = tid; h < nh; h += nt) {  // first halo: from HBM
-    const int hv = g.halo_vtx[h0 + h];
-    s_bar0[a.Vc + h] = g.vbar[hv];
-    atomicOr(&s_mask[0], 1u << (hv / Vc));  // that CTA receives my contributions and sends me halos
-  }
-  for (int e = tid; e < np; e += nt) {
-    const int ent = g.push_ent[g.push_off[c] + e];
-    const uint32_t dc = (uint32_t)ent >> 27;
-    s_push_v[e] = ent & 0x7FF;
-    s_push_addr[e] = mapa(bar0_addr + (uint32_t)(a.Vc + ((ent >> 11) & 0xFFFF)) * 16u, dc);
-    atomicOr(&s_mask[1], 1u << dc);         // that CTA receives my halos and sends me contributions
-  }
-  __syncthreads();
-  const unsigned int mask_p = s_mask[0], mask_d = s_mask[1];
-  const bool wait_c = mask_d != 0u, wait_h = mask_p != 0u;
-  if (tid == 0) {
-    mbar_init(mbc_addr, max(__popc(mask_d), 1));
-    mbar_init(mbh_addr, max(__popc(mask_p), 1));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  // thread t < 16 signals rank t
-  const bool sig_c = tid < 16 && ((mask_p >> tid) & 1u), sig_h = tid < 16 && ((mask_d >> tid) & 1u);
-  const uint32_t rmb_c = (tid < C) ? mapa(mbc_addr, (uint32_t)tid) : 0u;
-  const uint32_t rmb_h = (tid < C) ? mapa(mbh_addr, (uint32_t)tid) : 0u;
-  const bool poller = (tid & 31) == 0;
-  // owned edges = source-role incidence slots of this chunk, listed vertex by vertex (see k_pd_resident)
-  int outdeg = 0;
-  if (hasv)
-    for (int k = 0; k < deg; ++k) outdeg += ((g.inc_nbr[base + s_koff[k] + tid] & 1) == 0);
-  s_scan[tid] = outdeg;
-  __syncthreads();
-  if (tid == 0) {  // nt <= 1024 entries, once per launch
-    int run = 0;
-    for (int i = 0; i < nt; ++i) {
-      const int d0 = s_scan[i];
-      s_scan[i] = run;
-      run += d0;
-    }
-    s_cnt[0] = run;
-  }
-  __syncthreads();
-  if (hasv) {
-    int at = s_scan[tid];
-    for (int k = 0; k < deg; ++k) {
-      const int slot = s_koff[k] + tid;
-      if ((g.inc_nbr[base + slot] & 1) == 0) s_list[at++] = slot;
-    }
-  }
-  __syncthreads();
-  for (int slot = tid; slot < ni; slot += nt)
-    s_p1[slot] = neg0;  // target slots keep -0.0f forever; source slots are rewritten every iteration
-  const int ne = s_cnt[0];
-  float q1[SPT], q2[SPT], q3[SPT];
-  uint32_t src_bar[SPT];   // own bar0 record of the source
-  uint32_t dst_bar[SPT];   // own bar0 / halo0 record of the target
-  uint32_t src_slot[SPT];  // local incidence slot of the source | remote flag (bit 19)
-  uint32_t dst_p4[SPT];    // p4 record of the target endpoint: shared::cta, or shared::cluster if remote
-#pragma unroll
-  for (int u = 0; u < SPT; ++u) {
-    const int j = tid + u * nt;
-    q1[u] = q2[u] = q3[u] = 0.f;
-    src_bar[u] = bar0_addr;
-    dst_bar[u] = bar0_addr;
-    src_slot[u] = 0;
-    dst_p4[u] = p4_addr;
-    if (j < ne) {
-      const int slot = s_list[j];
-      const float4 q = g.inc_q[base + slot];
-      q1[u] = q.x; q2[u] = q.y; q3[u] = q.z;
-      s_s[j] = g.inc_s[base + slot];
-      // source vertex of the slot: slot = koff[k] + i with koff non-decreasing in k
-      int k = 0;
-      while (k + 1 <= g.max_deg && s_koff[k + 1] <= slot) ++k;
-      src_bar[u] = bar0_addr + (uint32_t)(slot - s_koff[k]) * 16u;
-      const int nbr = __float_as_int(q.w) >> 1;
-      const int oc = nbr / Vc;
-      const bool remote = (oc != c);
-      int idx = nbr - oc * Vc;
-      if (remote) {  // position of nbr in this chunk's (ascending) halo list
-        int lo = 0, hi = nh - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (g.halo_vtx[h0 + mid] < nbr) lo = mid + 1;
-          else hi = mid;
+    for (int v = 0; v < VPT; ++v) {
+      const int i = tid + v * MAXT;
+      if (i < nv) {
+        const float x_old = x[v], w1_old = w1[v], w2_old = w2[v];
+        float xx = x_old, ww1 = w1_old, ww2 = w2_old;
+        const int d = deg[v];
+        // software pipeline: the contribution record of incidence k+1 is in flight while k is added
+        float4 p4n = make_float4(0.f, 0.f, 0.f, 0.f);
+        float p1n = 0.f;
+        if (d > 0) {
+          p4n = s_p4[kr[0] + i];
+          p1n = s_p1[kr[0] + i];
         }
-        idx = a.Vc + lo;
+        int ko = (d > 1) ? kr[1] : 0;
+        for (int k = 0; k < d; ++k) {
+          const float4 p4 = p4n;
+          const float p1 = p1n;
+          if (k + 1 < d) {
+            const int slot = ko + i;
+            p4n = s_p4[slot];
+            p1n = s_p1[slot];
+            ko = kr[k + 2];  // k + 2 <= max_deg: inside the row
+          }
+          xx = add(xx, p4.x);
+          ww1 = add(ww1, p4.y);
+          ww2 = add(ww2, p4.z);
+          ww1 = add(ww1, p4.w);
+          ww2 = add(ww2, p1);
+        }
+        const VertexOut o = vertex_finish(xx, ww1, ww2, data[v], wt[v], x_old, w1_old, w2_old, p);
+        x[v] = o.prim.x; w1[v] = ww1; w2[v] = ww2;
+        s_bar[i] = o.bar;
+        if (last) g.vprev[v0 + i] = make_float4(x_old, w1_old, w2_old, 0.0f);
       }
-      dst_bar[u] = bar0_addr + (uint32_t)idx * 16u;
-      src_slot[u] = (uint32_t)slot | (remote ? (1u << 19) : 0u);
-      // the target endpoint's incidence slot of this edge (global slot id -> owner chunk, local slot)
-      const int tslot = g.edge_slot[2 * g.inc_edge[base + slot] + 1];
-      dst_p4[u] = remote ? mapa(p4_addr + (uint32_t)(tslot - g.chunk_base[oc]) * 16u, (uint32_t)oc)
-                         : (p4_addr + (uint32_t)(tslot - g.chunk_base[oc]) * 16u);
     }
-  }
-  cluster.sync();
+  };
 
-  const flame_b200_pd_params p = a.p;
-
+  // Measured alternatives (all bit-exact, all slower on B200): splitting the barriers into
+  // arrive / wait around the work that needs no other CTA (interior vertices, local edges) - the extra
+  // __syncthreads and the second pass over the vertex registers cost more than the hidden barrier latency.
   for (int it = 0; it < a.n_iters; ++it) {
-    const uint32_t cur_off = (it & 1) ? bar_stride : 0u;
-    float4* nxt = (it & 1) ? s_bar0 : s_bar1;
-    if (it > 0 && wait_h) {  // the halos this iteration reads (iteration 0: loaded from HBM above)
-      if (poller) mbar_wait(mbh_addr, (uint32_t)(it - 1) & 1u);
-      __syncwarp();
-    }
-    // ---- phase A: one dual update per edge, contributions pushed to both endpoints ----
-#pragma unroll
-    for (int u0 = 0; u0 < SPT; u0 += PD_MLP) {
-      float4 s[PD_MLP], bi[PD_MLP], bj[PD_MLP];
-#pragma unroll
-      for (int v = 0; v < PD_MLP; ++v) {
-        const int u = u0 + v;
-        if (u < SPT && tid + u * nt < ne) {
-          s[v] = s_s[tid + u * nt];
-          bi[v] = ld_shared_f4(src_bar[u] + cur_off);
-          bj[v] = ld_shared_f4(dst_bar[u] + cur_off);
-        }
-      }
-#pragma unroll
-      for (int v = 0; v < PD_MLP; ++v) {
-        const int u = u0 + v;
-        if (u < SPT && tid + u * nt < ne) {
-          const float4 qu = dual_update(make_float4(q1[u], q2[u], q3[u], 0.f), s[v], bi[v], bj[v], p.step_q);
-          q1[u] = qu.x; q2[u] = qu.y; q3[u] = qu.z;
-          // primalStep contributions (cc:125-141), rounded as the reference: a = (q1*step_x)*alpha ...
-          const float pa = mul(mul(qu.x, p.step_x), s[v].x);
-          const float b2 = mul(mul(qu.y, p.step_x), s[v].y);
-          const float b3 = mul(mul(qu.z, p.step_x), s[v].y);
-          const uint32_t sl = src_slot[u] & 0x7FFFFu;
-          // source i: x -= a; w1 += a*dx; w2 += a*dy; w1 -= b2; w2 -= b3
-          s_p4[sl] = make_float4(-pa, mul(pa, s[v].z), mul(pa, s[v].w), -b2);
-          s_p1[sl] = -b3;
-          // target j: x += a; w1 += b2; w2 += b3   (u1 = u2 = -0.0f: exact no-ops)
-          if (src_slot[u] & (1u << 19)) st_cluster_f4(dst_p4[u], make_float4(pa, b2, b3, neg0));
-          else st_shared_f4(dst_p4[u], make_float4(pa, b2, b3, neg0));
-        }
-      }
-    }
-    __syncthreads();  // every contribution of this CTA - local and remote - has been issued
-    if (sig_c) mbar_arrive_remote(rmb_c);
-    if (wait_c) {     // all CTAs that own edges into this one have arrived
-      if (poller) mbar_wait(mbc_addr, (uint32_t)it & 1u);
-      __syncwarp();
-    }
-    // ---- phase B: ordered accumulation + prox + extragradient, one vertex per thread ----
-    if (hasv) {
-      const float x_old = x, w1_old = w1, w2_old = w2;
-      float4 p4n = make_float4(0.f, 0.f, 0.f, 0.f);
-      float p1n = 0.f;
-      if (deg > 0) {
-        p4n = s_p4[tid];  // koff[0] == 0
-        p1n = s_p1[tid];
-      }
-      int ko = (deg > 1) ? s_koff[1] : 0;
-      for (int k = 0; k < deg; ++k) {
-        const float4 p4 = p4n;
-        const float p1 = p1n;
-        if (k + 1 < deg) {
-          const int slot = ko + tid;
-          p4n = s_p4[slot];
-          p1n = s_p1[slot];
-          ko = s_koff[k + 2];  // k + 2 <= max_deg: inside the table
-        }
-        x = add(x, p4.x);
-        w1 = add(w1, p4.y);
-        w2 = add(w2, p4.z);
-        w1 = add(w1, p4.w);
-        w2 = add(w2, p1);
-      }
-      const VertexOut o = vertex_finish(x, w1, w2, data, wt, x_old, w1_old, w2_old, p);
-      x = o.prim.x;
-      nxt[tid] = o.bar;
-      if (it == a.n_iters - 1) g.vprev[v0 + tid] = make_float4(x_old, w1_old, w2_old, 0.0f);
-    }
-    __syncthreads();  // the new x_bar/w_bar of this CTA are complete (and its p4 records consumed)
-    if (it + 1 < a.n_iters) {
-      const uint32_t nxt_off = (it & 1) ? 0u : bar_stride;
-      for (int e = tid; e < np; e += nt) st_cluster_f4(s_push_addr[e] + nxt_off, nxt[s_push_v[e]]);
-      if (np > 0) __syncthreads();  // uniform per CTA
-      if (sig_h) mbar_arrive_remote(rmb_h);
-    }
+    phase_a();
+    cluster_arrive();  // release: this CTA's contributions, local and remote, are visible
+    cluster_wait();
+    phase_b(it == a.n_iters - 1);
+    cluster_arrive();  // x_bar published (nobody reads it between the two barriers: one buffer suffices)
+    cluster_wait();
   }
-  cluster.sync();  // no CTA leaves while a neighbour could still address its shared memory
 
   // ---- write back (both private copies of every edge's q) ----
-  if (hasv) {
-    const float4* fin = (a.n_iters & 1) ? s_bar1 : s_bar0;
-    g.vbar[v0 + tid] = fin[tid];
-    g.vprim[v0 + tid] = make_float4(x, w1, w2, data);
+#pragma unroll
+  for (int v = 0; v < VPT; ++v) {
+    const int i = tid + v * MAXT;
+    if (i < nv) {
+      g.vbar[v0 + i] = s_bar[i];
+      g.vprim[v0 + i] = make_float4(x[v], w1[v], w2[v], data[v]);
+    }
   }
 #pragma unroll
   for (int u = 0; u < SPT; ++u) {
-    const int j = tid + u * nt;
+    const int j = tid + u * MAXT;
     if (j < ne) {
-      const int sslot = base + (int)(src_slot[u] & 0x7FFFFu);
+      const int sslot = base + (int)(src[u] & 0xFFFFu);
       const int tslot = g.edge_slot[2 * g.inc_edge[sslot] + 1];
       g.inc_q[sslot] = make_float4(q1[u], q2[u], q3[u], __int_as_float(g.inc_nbr[sslot]));
       g.inc_q[tslot] = make_float4(q1[u], q2[u], q3[u], __int_as_float(g.inc_nbr[tslot]));
@@ -998,43 +807,68 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident_mb(ResidentArgs a) {
   }
 }
 
-size_t pd_resident_smem(int Vc, int maxInc, int maxEdges, int max_deg, int maxHalo, int maxPush) {
-  return (size_t)(Vc + maxHalo) * 32 + (size_t)maxInc * (16 + 4) + (size_t)maxEdges * (16 + 4) +
-         (size_t)(max_deg + 3) * 4 + 1024 * 4 + (size_t)maxPush * 8 + 2 * 4 + 2 * 8 + 8 + 128;
+size_t pd_resident_smem(int Vc, int maxInc, int maxEdges, int max_deg) {
+  return (size_t)Vc * 16 + (size_t)resident_p4_records(maxInc, maxEdges, Vc) * 16 + (size_t)maxEdges * 16 +
+         (size_t)maxInc * 4 + (size_t)(max_deg + 2) * 4 + 128;
 }
 
-// The two register budgets the kernel is built for: (threads, owned edges per thread).
-bool pd_resident_variant(int Vc, int maxEdges, int* threads) {
-  int forced = 0;
-  if (const char* sv = getenv("FLAME_B200_THREADS")) forced = atoi(sv);
-  if (forced != 1024 && Vc <= 640 && maxEdges <= 640 * 4) {
-    *threads = 640;
-    return true;
+// The register budgets the kernel is built for: (threads, owned edges per thread, vertices per thread).
+struct ResidentVariant { int threads, spt, vpt; };
+static const ResidentVariant kVariants[FB_RESIDENT_VARIANTS] = {{640, 4, 1}, {768, 5, 2}, {1024, 4, 2}};
+
+// Smallest variant that holds chunks of Vc vertices / maxEdges owned edges; -1 = none.
+int pd_resident_variant(int Vc, int maxEdges, int* threads) {
+  int forced = -1;
+  if (const char* sv = getenv("FLAME_B200_VARIANT")) forced = atoi(sv);
+  for (int i = 0; i < FB_RESIDENT_VARIANTS; ++i) {
+    if (forced >= 0 && i != forced) continue;
+    const ResidentVariant& r = kVariants[i];
+    if (Vc <= r.threads * r.vpt && maxEdges <= r.threads * r.spt) {
+      if (threads) *threads = r.threads;
+      return i;
+    }
   }
-  if (Vc <= 1024 && maxEdges <= 1024 * 2) {
-    *threads = 1024;
-    return true;
-  }
-  return false;
+  return -1;
 }
 
+typedef void (*ResidentKernel)(ResidentArgs);
+static ResidentKernel resident_kernel(int variant) {
+  switch (variant) {
+    case 0: return k_pd_resident<640, 4, 1, 2>;
+    case 1: return k_pd_resident<768, 5, 2, 1>;
+    default: return k_pd_resident<1024, 4, 2, 1>;
+  }
+}
+
+// cudaFuncSetAttribute applies per device: done once for every device a context is created on.
 int pd_resident_init() {
-  static bool done = false;
-  if (done) return 0;
-  FB_CUDA(cudaFuncSetAttribute(k_pd_resident<640, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               227 * 1024));
-  FB_CUDA(cudaFuncSetAttribute(k_pd_resident<640, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  FB_CUDA(cudaFuncSetAttribute(k_pd_resident<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               227 * 1024));
-  FB_CUDA(cudaFuncSetAttribute(k_pd_resident<1024, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  FB_CUDA(cudaFuncSetAttribute(k_pd_resident_mb<640, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               227 * 1024));
-  FB_CUDA(cudaFuncSetAttribute(k_pd_resident_mb<640, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  FB_CUDA(cudaFuncSetAttribute(k_pd_resident_mb<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               227 * 1024));
-  FB_CUDA(cudaFuncSetAttribute(k_pd_resident_mb<1024, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  done = true;
+  static std::mutex mu;
+  static bool done[64] = {false};
+  int dev = 0;
+  FB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev >= 0 && dev < 64 && done[dev]) return 0;
+  for (int i = 0; i < FB_RESIDENT_VARIANTS; ++i) {
+    FB_CUDA(cudaFuncSetAttribute(resident_kernel(i), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FB_CUDA(cudaFuncSetAttribute(resident_kernel(i), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  }
+  if (dev >= 0 && dev < 64) done[dev] = true;
   return 0;
+}
+
+static void resident_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int n, const ResidentPlan& plan,
+                            cudaStream_t st) {
+  *cfg = cudaLaunchConfig_t{};
+  cfg->gridDim = dim3(n * plan.cluster);
+  cfg->blockDim = dim3(kVariants[plan.variant].threads);
+  cfg->dynamicSmemBytes = plan.smem_bytes;
+  cfg->stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = plan.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg->attrs = attr;
+  cfg->numAttrs = 1;
 }
 
 int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const ResidentPlan& plan,
@@ -1048,40 +882,10 @@ int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const Reside
   a.maxInc = plan.maxInc;
   a.maxEdges = plan.maxEdges;
   a.max_deg = plan.max_deg;
-  a.maxHalo = plan.maxHalo;
-  a.maxPush = plan.maxPush;
-  // Default: k_pd_resident (two hardware cluster barriers per iteration, remote loads), the fastest of
-  // the three synchronisation schemes measured on B200 (single frame, config D, 200 iterations):
-  //   barrier.cluster + remote loads ............................ 0.617 ms
-  //   local halos, st.async + mbarrier transaction bytes (16 B) .. 0.720 ms
-  //   local halos, plain DSMEM stores + point-to-point mbarrier
-  //     arrive.release.cluster / try_wait.acquire.cluster ........ 0.974 ms   (k_pd_resident_mb)
-  // FLAME_B200_PD_SYNC=p2p selects the last one (kept bit-exact and tested).
-  const char* sv = getenv("FLAME_B200_PD_SYNC");
-  const bool use_barrier = !(sv && sv[0] == 'p');
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(n * plan.cluster);
-  cfg.blockDim = dim3(plan.threads);
-  cfg.dynamicSmemBytes = plan.smem_bytes;
-  cfg.stream = st;
+  cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = plan.cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (use_barrier) {
-    if (plan.threads <= 640) {
-      FB_CUDA(cudaLaunchKernelEx(&cfg, k_pd_resident<640, 4>, a));
-    } else {
-      FB_CUDA(cudaLaunchKernelEx(&cfg, k_pd_resident<1024, 2>, a));
-    }
-  } else if (plan.threads <= 640) {
-    FB_CUDA(cudaLaunchKernelEx(&cfg, k_pd_resident_mb<640, 4>, a));
-  } else {
-    FB_CUDA(cudaLaunchKernelEx(&cfg, k_pd_resident_mb<1024, 2>, a));
-  }
+  resident_config(&cfg, attr, n, plan, st);
+  FB_CUDA(cudaLaunchKernelEx(&cfg, resident_kernel(plan.variant), a));
   count_launch();
   return 0;
 }
@@ -1089,22 +893,10 @@ int pd_run_resident(cudaStream_t st, const GraphDev* gs_dev, int n, const Reside
 // How many frame clusters of this plan the device keeps resident at once (one wave of pd_run_resident).
 int pd_resident_capacity(const ResidentPlan& plan, int* n_clusters) {
   if (int rc = pd_resident_init()) return rc;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(64 * plan.cluster);
-  cfg.blockDim = dim3(plan.threads);
-  cfg.dynamicSmemBytes = plan.smem_bytes;
+  cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = plan.cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (plan.threads <= 640) {
-    FB_CUDA(cudaOccupancyMaxActiveClusters(n_clusters, k_pd_resident<640, 4>, &cfg));
-  } else {
-    FB_CUDA(cudaOccupancyMaxActiveClusters(n_clusters, k_pd_resident<1024, 2>, &cfg));
-  }
+  resident_config(&cfg, attr, 64, plan, nullptr);
+  FB_CUDA(cudaOccupancyMaxActiveClusters(n_clusters, resident_kernel(plan.variant), &cfg));
   return 0;
 }
 
@@ -1117,7 +909,7 @@ __global__ void k_cost_terms(GraphDev g, float* __restrict__ terms) {
   if (v >= g.V) return;
   const int c = v / g.Vc, i = v - c * g.Vc;
   const int base = g.chunk_base[c];
-  const int* koff = g.koff + (size_t)c * (g.max_deg + 1);
+  const int* koff = koff_row(g, c);
   const float4 pi = g.vprim[v];
   const int d = g.deg[v];
   for (int k = 0; k < d; ++k) {

@@ -1,4 +1,4 @@
-// Epipolar inverse-depth search + measurement model + fusion for sm_100a: one thread per feature.
+// Epipolar inverse-depth search + measurement model + fusion for sm_100a: one WARP per feature.
 //
 // Replaces the loop body of Flame::updateFeatureIDepths / Flame::trackFeature
 // (src/flame/flame.cc:1280-1752) and everything it calls:
@@ -10,33 +10,56 @@
 //   utils::bilinearInterp / bilinearWeights    src/flame/utils/image_utils.h:199-272
 //   utils::clipLineLiangBarsky                 src/flame/utils/image_utils.cc:269-371
 //
+// Design (the reference walks the epipolar line with a scalar sliding window, one feature at a time):
+//   * k_epigeo_table: the geometry of a (parent frame -> new frame) pair depends on the frame, not on the
+//     feature; one thread per frame slot builds it once per call instead of once per feature.
+//   * k_track_features: one warp per feature. The scalar stages (predict, search region, clipping,
+//     measurement model, fusion) are evaluated uniformly by the warp. The SSD walk is done in parallel:
+//     the bounding patch of the clipped epipolar segment in the padded u8 comparison image is staged into
+//     shared memory with ONE TMA tile load (cp.async.bulk.tensor.2d + mbarrier); lane k computes sample
+//     position k (the reference's running sum cp += inc, so the same rounded positions), takes its
+//     bilinear tap from the staged patch, forms the 5-tap SSD of step k from the shared samples in the
+//     reference's summation order, and a warp arg-min with first-index tie-break (plus a second pass
+//     excluding the winner) yields best / second-best / neighbours exactly as the sequential scan does.
+//
 // This translation unit is compiled with -fmad=false: every expression below is evaluated with
 // separately rounded fp32 operations in the association order of the reference's C++ (its
 // x86-64 Release build has no FMA); '/' and sqrt are IEEE-correct (-prec-div/-prec-sqrt
 // defaults). The matcher is SSD, not NCC; the gradient tap uses offset 3 on the
 // 5-px-padded gradient images.
-//
-// The walk along the epipolar line is latency-bound (<= ~36 dependent bilinear taps per feature on
-// L2-resident u8 images), not bandwidth-bound; see DESIGN.md.
+#include <cuda.h>
+
 #include <cfloat>
+#include <cmath>
 #include <cstring>
+#include <string>
 
 #include "internal.h"
 
 namespace fb {
 
 struct FrameDev {
-  const unsigned char* img;  // (H + 2 pad) x (W + 2 pad) u8
-  const float* gx;           // same size f32
+  const unsigned char* img;  // (H + 2 pad) rows of `pitch` bytes, (W + 2 pad) valid
+  const float* gx;           // same geometry, f32 (pitch in elements)
   const float* gy;
   float pose[7];             // camera-to-world: qw qx qy qz tx ty tz
   int valid;
 };
 
 #define FB_MAX_FRAMES 64
+#define FB_SEARCH_MAX_STEPS 128  // SSD positions per feature the warp kernel holds (default params: <= 36)
+#define FB_TILE 48               // side of the staged comparison-image patch [px]; inner extent multiple of 16 B
+
+// Geometry of one (parent frame -> target frame) pair: stereo::EpipolarGeometry<float> after loadGeometry.
+struct GeoDev {
+  float q[4], t[3], t_cmp_to_ref[3];
+  float KRKinv[9], Kt[3], epipole[2];
+  float baseline;  // |t| (flame.cc:1320)
+  int pad_;
+};
 
 struct StereoState {
-  int width = 0, height = 0, pad = 0;
+  int width = 0, height = 0, pad = 0, pitch = 0;
   float K[9], Kinv[9];
   FrameDev h_frames[FB_MAX_FRAMES];
   FrameDev* d_frames = nullptr;
@@ -44,27 +67,36 @@ struct StereoState {
   float* d_gx[FB_MAX_FRAMES] = {nullptr};
   float* d_gy[FB_MAX_FRAMES] = {nullptr};
   size_t cap_pix[FB_MAX_FRAMES] = {0};
+  int slot_w[FB_MAX_FRAMES] = {0}, slot_h[FB_MAX_FRAMES] = {0}, slot_pad[FB_MAX_FRAMES] = {0};
+  CUtensorMap tmap[FB_MAX_FRAMES];   // TMA descriptor of every frame slot's padded u8 image
   unsigned char* d_raw = nullptr;    // raw u8 image of the frame being prepared
   size_t cap_raw = 0;
   unsigned char* h_stage = nullptr;  // pinned
   size_t h_stage_cap = 0;
   cudaEvent_t stage_free = nullptr;
+  GeoDev* d_geo = nullptr;           // [2][FB_MAX_FRAMES]: parent -> new frame, parent -> current pose-frame
+  // the resident feature set: in (read by the search), out (written), swapped by a committing download
   flame_b200_feature* d_feats = nullptr;
+  flame_b200_feature* d_feats_out = nullptr;
   flame_b200_track_diag* d_diag = nullptr;
   int* d_count = nullptr;
-  int cap_feats = 0;
+  int cap_feats = 0, n_feats = 0;
+  bool tracked = false;
   flame_b200_feature* h_feats = nullptr;  // pinned mirrors
   flame_b200_track_diag* h_diag = nullptr;
   int* h_count = nullptr;
+  cudaEvent_t feats_free = nullptr;
 };
 
 struct StereoArgs {
   flame_b200_track_params P;
   float K[9], Kinv[9];
-  int width, height, pad;
+  int width, height, pad, pitch;
   int fnew, curr_pf;
   const FrameDev* frames;
-  flame_b200_feature* feats;
+  const GeoDev* geo;
+  const flame_b200_feature* feats;
+  flame_b200_feature* feats_out;
   flame_b200_track_diag* diag;
   int n;
   int* count;
@@ -259,6 +291,22 @@ struct EpiGeo {
       epipole[1] = (K[4] * t[1] + K[5] * t[2]) / t[2];
     }
   }
+  // geometry precomputed by k_epigeo_table (bit-identical to load(): same expressions, evaluated once)
+  __device__ void load_table(const GeoDev& g) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = g.q[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      t[i] = g.t[i];
+      t_cmp_to_ref[i] = g.t_cmp_to_ref[i];
+      Kt[i] = g.Kt[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) KRKinv[i] = g.KRKinv[i];
+    KRKinv3[0] = KRKinv[6]; KRKinv3[1] = KRKinv[7]; KRKinv3[2] = KRKinv[8];
+    epipole[0] = g.epipole[0];
+    epipole[1] = g.epipole[1];
+  }
   // :191-201
   __device__ void max_depth_projection(float ux, float uy, float* ix, float* iy) const {
     const float h[3] = {ux, uy, 1.0f};
@@ -367,141 +415,180 @@ struct EpiGeo {
 };
 
 // ------------------------------------------------------------------------------------------
-// stereo::line_stereo::match (line_stereo.h:75-385)
+// stereo::line_stereo::match (line_stereo.h:75-385), warp-parallel.
+//
+// The reference slides a 5-tap window along the line: at step k (k = 0, 1, ...) the window holds the
+// samples S[k-2] .. S[k+2], where S[-2], S[-1], S[0], S[1] are taken at cp0 - 2 inc, cp0 - inc, cp0,
+// cp0 + inc and S[k+2] at cp_k + 2 inc, cp_k being the running sum cp_{k-1} + inc. The SSD of step k is
+// ee_k = sum_{i=+2..-2} (S[k+i] - ref[i])^2 in that order. The window is an optimisation, not a dependency:
+// here lane k forms cp_k with the same k rounded additions, takes S[k+2] from the staged patch, and ee_k
+// from the shared sample array. best = first minimum of ee, second = first minimum of the others - what
+// the sequential "if (ee < best) ... else if (ee < second)" scan produces.
 // ------------------------------------------------------------------------------------------
-__device__ int line_stereo_match(float rescale_factor, const float ref_patch[5],
-                                 const unsigned char* __restrict__ img, int step, float sx, float sy,
-                                 float ex, float ey, float* ucx, float* ucy, float* residual,
-                                 const flame_b200_ls_params& params) {
-  const float realVal_m2 = ref_patch[0], realVal_m1 = ref_patch[1], realVal = ref_patch[2];
-  const float realVal_p1 = ref_patch[3], realVal_p2 = ref_patch[4];
+struct WarpScratch {               // per warp, shared memory
+  float samp[FB_SEARCH_MAX_STEPS + 4];  // samp[j + 2] = S[j]
+  float ee[FB_SEARCH_MAX_STEPS];
+  float cx[FB_SEARCH_MAX_STEPS], cy[FB_SEARCH_MAX_STEPS];
+};
 
+struct PatchView {  // where the bilinear taps of the comparison image come from
+  const unsigned char* base;
+  int pitch;        // bytes per row
+  int x0, y0;       // image coordinates of base[0]
+};
+
+__device__ __forceinline__ float tap_u8(const PatchView& v, float x, float y) {
+  const int xf = (int)x, yf = (int)y;
+  const float dx = x - xf, dy = y - yf;
+  const float w11 = dx * dy;
+  const float w01 = dx - w11;
+  const float w10 = dy - w11;
+  const float w00 = 1.0f - dx - dy + w11;
+  const unsigned char* d = v.base + (yf - v.y0) * v.pitch + (xf - v.x0);
+  return w00 * d[0] + w01 * d[1] + w10 * d[v.pitch] + w11 * d[1 + v.pitch];
+}
+
+// SSD of the 5-tap window at step k and its residuals (order p2, p1, c, m1, m2 as in :160-176)
+__device__ __forceinline__ float window_ssd(const float* samp, int k, const float ref[5], float e[5]) {
+  float ee = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    e[i] = samp[k + 4 - i] - ref[4 - i];  // S[k + 2 - i] - ref[+2 - i]
+    ee += e[i] * e[i];
+  }
+  return ee;
+}
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w < v ? w : v;
+  }
+  return v;
+}
+
+// Returns 0 SUCCESS, 1 FAIL_AMBIGUOUS_MATCH, 2 FAIL_MAX_COST (line_stereo.h:38-43), 3 = more than
+// FB_SEARCH_MAX_STEPS positions (rejected on the host before the launch). All arguments warp-uniform.
+// `view` must cover every tap of the walk: the staged patch when the walk's bounding box fits it,
+// otherwise the image itself.
+__device__ int warp_line_match(const flame_b200_ls_params& params, float rescale_factor, const float ref[5],
+                               const PatchView& view, float sx, float sy, float ex, float ey, WarpScratch& ws,
+                               float* ucx, float* ucy) {
+  const int lane = threadIdx.x & 31;
   float incx = ex - sx, incy = ey - sy;
-  const float eplLength = sqrt_rn(incx * incx + incy * incy);
-  incx *= params.sample_dist / eplLength;
-  incy *= params.sample_dist / eplLength;
+  const float epl = sqrt_rn(incx * incx + incy * incy);
+  incx *= params.sample_dist / epl;
+  incy *= params.sample_dist / epl;
 
-  float cpx = sx, cpy = sy;
-  float val_cp_m2 = bilinear_u8(img, step, cpx - 2.0f * incx, cpy - 2.0f * incy);
-  float val_cp_m1 = bilinear_u8(img, step, cpx - incx, cpy - incy);
-  float val_cp = bilinear_u8(img, step, cpx, cpy);
-  float val_cp_p1 = bilinear_u8(img, step, cpx + incx, cpy + incy);
-  float val_cp_p2;
-
-  int loopCounter = 0;
-  float best_match_x = -1, best_match_y = -1;
-  float best_match_err = FLT_MAX;
-  float second_best_match_err = FLT_MAX;
-  const float qnan = __uint_as_float(0x7fc00000u);
-  float best_match_errPre = qnan, best_match_errPost = qnan;
-  float best_match_DiffErrPre = qnan, best_match_DiffErrPost = qnan;
-  bool bestWasLastLoop = false;
-  float eeLast = -1;
-  float e1A = qnan, e1B = qnan, e2A = qnan, e2B = qnan, e3A = qnan, e3B = qnan, e4A = qnan,
-        e4B = qnan, e5A = qnan, e5B = qnan;
-  int loopCBest = -1, loopCSecond = -1;
-
-  while ((((incx < 0) == (cpx > ex)) && ((incy < 0) == (cpy > ey))) || loopCounter == 0) {
-    val_cp_p2 = bilinear_u8(img, step, cpx + 2 * incx, cpy + 2 * incy);
-    float ee = 0.0f;
-    if (loopCounter % 2 == 0) {
-      e1A = val_cp_p2 - realVal_p2; ee += e1A * e1A;
-      e2A = val_cp_p1 - realVal_p1; ee += e2A * e2A;
-      e3A = val_cp - realVal;       ee += e3A * e3A;
-      e4A = val_cp_m1 - realVal_m1; ee += e4A * e4A;
-      e5A = val_cp_m2 - realVal_m2; ee += e5A * e5A;
-    } else {
-      e1B = val_cp_p2 - realVal_p2; ee += e1B * e1B;
-      e2B = val_cp_p1 - realVal_p1; ee += e2B * e2B;
-      e3B = val_cp - realVal;       ee += e3B * e3B;
-      e4B = val_cp_m1 - realVal_m1; ee += e4B * e4B;
-      e5B = val_cp_m2 - realVal_m2; ee += e5B * e5B;
-    }
-    if (ee < best_match_err) {
-      second_best_match_err = best_match_err;
-      loopCSecond = loopCBest;
-      best_match_err = ee;
-      loopCBest = loopCounter;
-      best_match_errPre = eeLast;
-      best_match_DiffErrPre = e1A * e1B + e2A * e2B + e3A * e3B + e4A * e4B + e5A * e5B;
-      best_match_errPost = -1;
-      best_match_DiffErrPost = -1;
-      best_match_x = cpx;
-      best_match_y = cpy;
-      bestWasLastLoop = true;
-    } else {
-      if (bestWasLastLoop) {
-        best_match_errPost = ee;
-        best_match_DiffErrPost = e1A * e1B + e2A * e2B + e3A * e3B + e4A * e4B + e5A * e5B;
-        bestWasLastLoop = false;
+  // the four samples in front of the first window
+  if (lane < 4) {
+    float px = sx, py = sy;
+    if (lane == 0) { px = sx - 2.0f * incx; py = sy - 2.0f * incy; }
+    if (lane == 1) { px = sx - incx; py = sy - incy; }
+    if (lane == 3) { px = sx + incx; py = sy + incy; }
+    ws.samp[lane] = tap_u8(view, px, py);
+  }
+  // positions cp_k, the loop condition of every step, and the leading sample of every executed step
+  int n = -1;  // number of executed steps
+  float bx = sx, by = sy;  // cp at the first step of the round
+  for (int k0 = 0; k0 < FB_SEARCH_MAX_STEPS && n < 0; k0 += 32) {
+    float cx = bx, cy = by;
+    for (int i = 0; i < 31; ++i)
+      if (i < lane) {
+        cx += incx;
+        cy += incy;
       }
-      if (ee < second_best_match_err) {
-        second_best_match_err = ee;
-        loopCSecond = loopCounter;
-      }
+    const int k = k0 + lane;
+    const bool go = (((incx < 0) == (cx > ex)) && ((incy < 0) == (cy > ey))) || k == 0;  // :150
+    const unsigned stop = __ballot_sync(0xffffffffu, !go);
+    const int first_stop = stop ? (__ffs(stop) - 1) : 32;
+    if (lane < first_stop) {
+      ws.cx[k] = cx;
+      ws.cy[k] = cy;
+      ws.samp[k + 4] = tap_u8(view, cx + 2.0f * incx, cy + 2.0f * incy);
     }
-    eeLast = ee;
-    val_cp_m2 = val_cp_m1;
-    val_cp_m1 = val_cp;
-    val_cp = val_cp_p1;
-    val_cp_p1 = val_cp_p2;
-    cpx += incx;
-    cpy += incy;
-    loopCounter++;
+    if (stop) n = k0 + first_stop;
+    bx = __shfl_sync(0xffffffffu, cx, 31) + incx;
+    by = __shfl_sync(0xffffffffu, cy, 31) + incy;
+  }
+  if (n < 0) return 3;
+  __syncwarp();
+  // SSD of every step; first minimum
+  unsigned long long best_key = ~0ull;
+  for (int k = lane; k < n; k += 32) {
+    float e[5];
+    const float ee = window_ssd(ws.samp, k, ref, e);
+    ws.ee[k] = ee;
+    const unsigned long long key = ((unsigned long long)__float_as_uint(ee) << 32) | (unsigned)k;  // ee >= 0
+    best_key = key < best_key ? key : best_key;
+  }
+  best_key = warp_min_u64(best_key);
+  const int kb = (int)(best_key & 0xffffffffu);
+  float best = __uint_as_float((unsigned)(best_key >> 32));
+  __syncwarp();
+  // first minimum among the other steps
+  unsigned long long second_key = ((unsigned long long)__float_as_uint(FLT_MAX) << 32) | 0xffffffffu;
+  for (int k = lane; k < n; k += 32)
+    if (k != kb) {
+      const unsigned long long key = ((unsigned long long)__float_as_uint(ws.ee[k]) << 32) | (unsigned)k;
+      second_key = key < second_key ? key : second_key;
+    }
+  second_key = warp_min_u64(second_key);
+  const float second = __uint_as_float((unsigned)(second_key >> 32));
+  const int ks = (int)(second_key & 0xffffffffu);  // 0xffffffff == -1: no second candidate
+
+  if (best > 4.0f * params.max_cost) return 2;  // :261
+  int dl = kb - ks;
+  dl = dl > 0 ? dl : -dl;
+  if (((float)dl > 1.0f) && (params.second_best_factor * best > second)) return 1;  // :275
+
+  float mx = ws.cx[kb], my = ws.cy[kb];
+  if (params.do_subpixel && kb > 0 && kb + 1 < n) {  // otherwise one of the neighbour errors is the -1 sentinel (:287)
+    // errors of the neighbours and the residual cross terms with them (:187-206)
+    float e0[5], ep[5], en[5];
+    window_ssd(ws.samp, kb, ref, e0);
+    const float err_pre = window_ssd(ws.samp, kb - 1, ref, ep);
+    const float err_post = window_ssd(ws.samp, kb + 1, ref, en);
+    float cross_pre = e0[0] * ep[0], cross_post = e0[0] * en[0];
+#pragma unroll
+    for (int i = 1; i < 5; ++i) {
+      cross_pre += e0[i] * ep[i];
+      cross_post += e0[i] * en[i];
+    }
+    // derivatives of the SSD parabola pieces left and right of the minimum (:281-284)
+    const float g_pre_pre = -(err_pre - cross_pre);
+    const float g_pre_this = +(best - cross_pre);
+    const float g_post_this = -(best - cross_post);
+    const float g_post_post = +(err_post - cross_post);
+    const bool flip_mid = (g_post_this < 0) != (g_pre_this < 0);
+    const bool flip_pre = (g_pre_pre < 0) != (g_pre_this < 0);
+    const bool flip_post = (g_post_post < 0) != (g_post_this < 0);
+    if (!flip_mid && flip_pre && !flip_post) {  // zero crossing on the left piece only (:299-306)
+      const float d = g_pre_this / (g_pre_this - g_pre_pre);
+      mx -= d * incx;
+      my -= d * incy;
+      best = best - 2 * d * g_pre_this - (g_pre_pre - g_pre_this) * d * d;
+    } else if (!flip_mid && !flip_pre && flip_post) {  // on the right piece only (:308-313)
+      const float d = g_post_this / (g_post_this - g_post_post);
+      mx += d * incx;
+      my += d * incy;
+      best = best + 2 * d * g_post_this + (g_post_post - g_post_this) * d * d;
+    }
   }
 
-  *residual = best_match_err;
-  if (best_match_err > 4.0f * params.max_cost) return 2;  // FAIL_MAX_COST (:261)
-  int dl = loopCBest - loopCSecond;
-  dl = (dl > 0) ? dl : -dl;
-  if (((float)dl > 1.0f) && (params.second_best_factor * best_match_err > second_best_match_err))
-    return 1;  // FAIL_AMBIGUOUS_MATCH (:275)
-
-  if (params.do_subpixel) {
-    const float gradPre_pre = -(best_match_errPre - best_match_DiffErrPre);
-    const float gradPre_this = +(best_match_err - best_match_DiffErrPre);
-    const float gradPost_this = -(best_match_err - best_match_DiffErrPost);
-    const float gradPost_post = +(best_match_errPost - best_match_DiffErrPost);
-    bool interpPost = false, interpPre = false;
-    if (best_match_errPre < 0 || best_match_errPost < 0) {
-    } else if ((gradPost_this < 0) ^ (gradPre_this < 0)) {
-    } else if ((gradPre_pre < 0) ^ (gradPre_this < 0)) {
-      if ((gradPost_post < 0) ^ (gradPost_this < 0)) {
-      } else {
-        interpPre = true;
-      }
-    } else if ((gradPost_post < 0) ^ (gradPost_this < 0)) {
-      interpPost = true;
-    }
-    if (interpPre) {
-      const float d = gradPre_this / (gradPre_this - gradPre_pre);
-      best_match_x -= d * incx;
-      best_match_y -= d * incy;
-      best_match_err = best_match_err - 2 * d * gradPre_this - (gradPre_pre - gradPre_this) * d * d;
-    } else if (interpPost) {
-      const float d = gradPost_this / (gradPost_this - gradPost_post);
-      best_match_x += d * incx;
-      best_match_y += d * incy;
-      best_match_err = best_match_err + 2 * d * gradPost_this + (gradPost_post - gradPost_this) * d * d;
-    }
+  // acceptance against the texture of the reference patch (:352-372)
+  const float sd = params.sample_dist * rescale_factor;
+  float grad2 = 0.0f;
+#pragma unroll
+  for (int i = 4; i >= 1; --i) {
+    const float d = ref[i] - ref[i - 1];
+    grad2 += d * d;
   }
-  *residual = best_match_err;
-
-  const float sampleDist = params.sample_dist * rescale_factor;
-  float gradAlongLine = 0;
-  float tmp = realVal_p2 - realVal_p1;
-  gradAlongLine += tmp * tmp;
-  tmp = realVal_p1 - realVal;
-  gradAlongLine += tmp * tmp;
-  tmp = realVal - realVal_m1;
-  gradAlongLine += tmp * tmp;
-  tmp = realVal_m1 - realVal_m2;
-  gradAlongLine += tmp * tmp;
-  gradAlongLine /= sampleDist * sampleDist;
-  if (best_match_err > params.max_cost + sqrt_rn(gradAlongLine) * 20) return 2;  // :370
-
-  *ucx = best_match_x;
-  *ucy = best_match_y;
+  grad2 /= sd * sd;
+  if (best > params.max_cost + sqrt_rn(grad2) * 20) return 2;
+  *ucx = mx;
+  *ucy = my;
   return 0;
 }
 
@@ -569,34 +656,6 @@ __device__ bool filter_get_search_region(const flame_b200_filter_params& p, cons
   return true;
 }
 
-// .cc:184-266
-__device__ int filter_search(const flame_b200_filter_params& p, const EpiGeo& g,
-                             float rescale_factor, const unsigned char* img_ref,
-                             const unsigned char* img_cmp, int step, float urx, float ury, float sx,
-                             float sy, float ex, float ey, float* ucx, float* ucy) {
-  float erx, ery;
-  g.reference_epiline(urx, ury, &erx, &ery);
-  float ref_patch[5];
-  ref_patch[0] = bilinear_u8(img_ref, step, urx - 2 * erx * rescale_factor, ury - 2 * ery * rescale_factor);
-  ref_patch[1] = bilinear_u8(img_ref, step, urx - erx * rescale_factor, ury - ery * rescale_factor);
-  ref_patch[2] = bilinear_u8(img_ref, step, urx, ury);
-  ref_patch[3] = bilinear_u8(img_ref, step, urx + erx * rescale_factor, ury + ery * rescale_factor);
-  ref_patch[4] = bilinear_u8(img_ref, step, urx + 2 * erx * rescale_factor, ury + 2 * ery * rescale_factor);
-  float ref_patch_grad = 0.0f;
-#pragma unroll
-  for (int ii = 1; ii < 5; ++ii) {
-    const float abs_grad = fast_absf(ref_patch[ii] - ref_patch[ii - 1]);
-    if (abs_grad > ref_patch_grad) ref_patch_grad = abs_grad;
-  }
-  if (ref_patch_grad < p.min_grad_mag) return 1;  // FAIL_REF_PATCH_GRADIENT
-  float residual = FLT_MAX;
-  const int result = line_stereo_match(rescale_factor, ref_patch, img_cmp, step, sx, sy, ex, ey, ucx,
-                                       ucy, &residual, p.sparams);
-  if (result == 1) return 2;  // FAIL_AMBIGUOUS_MATCH
-  if (result == 2) return 3;  // FAIL_MAX_COST
-  return 0;
-}
-
 // .cc:268-305
 __device__ bool filter_update(float mu_pred, float var_pred, float mu_meas, float var_meas,
                               float* mu_post, float* var_post, float outlier_sigma_thresh) {
@@ -657,9 +716,63 @@ __device__ bool meas_idepth(const flame_b200_meas_params& p, const EpiGeo& g, co
   return true;
 }
 
-// cv::Rect_<int>::contains(Point2f)
-__device__ __forceinline__ bool rect_contains(int rx, int ry, int rw, int rh, float px, float py) {
-  return (float)rx <= px && px < (float)(rx + rw) && (float)ry <= py && py < (float)(ry + rh);
+// ------------------------------------------------------------------------------------------
+// Per-frame geometry table: EpipolarGeometry::loadGeometry (epipolar_geometry.h:86-103) of
+// T = target^-1 * parent (flame.cc:1314, :1610) for every uploaded parent frame slot and the two targets
+// (row 0: the new frame, row 1: the current pose-frame used for re-parenting).
+// ------------------------------------------------------------------------------------------
+__global__ void k_epigeo_table(StereoArgs a, GeoDev* __restrict__ out) {
+  const int f = threadIdx.x, which = blockIdx.x;
+  if (f >= FB_MAX_FRAMES || !a.frames[f].valid) return;
+  const FrameDev target = a.frames[which == 0 ? a.fnew : a.curr_pf];
+  const FrameDev parent = a.frames[f];
+  float T[7];
+  se3_inv_mul(target.pose, parent.pose, T);
+  EpiGeo e;
+  e.init(a.K, a.Kinv);
+  e.load(T, T + 4);
+  GeoDev g;
+  for (int i = 0; i < 4; ++i) g.q[i] = e.q[i];
+  for (int i = 0; i < 3; ++i) {
+    g.t[i] = e.t[i];
+    g.t_cmp_to_ref[i] = e.t_cmp_to_ref[i];
+    g.Kt[i] = e.Kt[i];
+  }
+  for (int i = 0; i < 9; ++i) g.KRKinv[i] = e.KRKinv[i];
+  g.epipole[0] = e.epipole[0];
+  g.epipole[1] = e.epipole[1];
+  g.baseline = sqrt_rn(T[4] * T[4] + T[5] * T[5] + T[6] * T[6]);  // flame.cc:1320
+  g.pad_ = 0;
+  out[which * FB_MAX_FRAMES + f] = g;
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA + mbarrier helpers (one patch per warp)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void patch_load_issue(const CUtensorMap* tmap, void* dst, unsigned long long* bar,
+                                                 int x0, int y0) {
+  const uint32_t b = smem_addr(bar), d = smem_addr(dst);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(FB_TILE * FB_TILE) : "memory");
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(d),
+      "l"(tmap), "r"(x0), "r"(y0), "r"(b)
+      : "memory");
+}
+__device__ __forceinline__ void patch_load_wait(unsigned long long* bar) {
+  const uint32_t b = smem_addr(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(b)
+        : "memory");
+  }
 }
 
 // flame.cc:1344-1376
@@ -670,46 +783,46 @@ __device__ __forceinline__ void feature_fail(const flame_b200_track_params& P, f
   if (f.num_dropouts > (uint32_t)P.max_dropouts) f.valid = 0;
 }
 
+// cv::Rect_<int>::contains takes a Point_<int>: the Point2f is converted with saturate_cast<int>
+// (cvRound, round half to even) first and the rounded point is tested (OpenCV 3.2 core/types.hpp)
+__device__ __forceinline__ bool rect_contains(int rx, int ry, int rw, int rh, float px, float py) {
+  const int ix = __float2int_rn(px), iy = __float2int_rn(py);
+  return rx <= ix && ix < rx + rw && ry <= iy && iy < ry + rh;
+}
+
 // ------------------------------------------------------------------------------------------
-// Flame::updateFeatureIDepths loop body (flame.cc:1308-1496) + Flame::trackFeature (:1536-1752)
+// Flame::updateFeatureIDepths loop body (flame.cc:1308-1496) + Flame::trackFeature (:1536-1752):
+// one warp per feature, all scalar stages evaluated uniformly by the warp, lane 0 writes.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_update_feature_idepths(StereoArgs a) {
-  const int ii = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ii >= a.n) return;
+#define TRACK_WARPS 4
+__global__ void __launch_bounds__(32 * TRACK_WARPS)
+k_track_features(StereoArgs a, const __grid_constant__ CUtensorMap tmap_cmp) {
+  __shared__ __align__(128) unsigned char s_tile[TRACK_WARPS][FB_TILE * FB_TILE];
+  __shared__ WarpScratch s_ws[TRACK_WARPS];
+  __shared__ __align__(8) unsigned long long s_bar[TRACK_WARPS];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ii = blockIdx.x * TRACK_WARPS + w;
+  if (ii >= a.n) return;  // warps are independent: no CTA-wide synchronisation below
   const flame_b200_track_params& P = a.P;
   flame_b200_feature f = a.feats[ii];
   const float qnan = __uint_as_float(0x7fc00000u);
   flame_b200_track_diag dg = {qnan, qnan, qnan, qnan, 0};
-  const int step = a.width + 2 * a.pad;
   const FrameDev fnew = a.frames[a.fnew];
+  const GeoDev& geo = a.geo[f.frame_id];
 
-  EpiGeo epigeo;
-  epigeo.init(a.K, a.Kinv);
-  float T[7];
-  {
-    const FrameDev fref = a.frames[f.frame_id];
-    se3_inv_mul(fnew.pose, fref.pose, T);  // :1314
-  }
-  epigeo.load(T, T + 4);
-
-  bool done = false;
-  const float baseline = sqrt_rn(T[4] * T[4] + T[5] * T[5] + T[6] * T[6]);  // :1320
-  if (baseline < P.min_baseline) done = true;  // skipped: feature untouched
-
-  float flow_x = qnan, flow_y = qnan;
-  if (!done) {
+  if (!(geo.baseline < P.min_baseline)) {  // :1320-1324: too little parallax -> feature untouched
+    EpiGeo epigeo;
+    epigeo.init(a.K, a.Kinv);
+    epigeo.load_table(geo);
     // ---------------- trackFeature ----------------
-    bool track_success = false;
-    int stage = 0;
+    int stage = 0;  // 0 = tracked; otherwise where it stopped
+    float flow_x = qnan, flow_y = qnan;
     float ucx, ucy, idepth_cmp, var_cmp;
-    const bool pred_success = filter_predict(epigeo, P.fparams.process_var_factor, f.x, f.y,
-                                             f.idepth_mu, f.idepth_var, &ucx, &ucy, &idepth_cmp,
-                                             &var_cmp);  // :1553
-    if (!pred_success) {
+    if (!filter_predict(epigeo, P.fparams.process_var_factor, f.x, f.y, f.idepth_mu, f.idepth_var, &ucx, &ucy,
+                        &idepth_cmp, &var_cmp)) {  // :1553
       stage = 1;
     } else {
-      int row_offset = 0;
-      if (P.do_letterbox) row_offset = a.height / 3;
+      const int row_offset = P.do_letterbox ? a.height / 3 : 0;
       const int border = (int)(P.rescale_factor_max * P.fparams.win_size / 2 + 1);  // :1576
       const int vr_x = border, vr_y = border + row_offset;
       const int vr_w = a.width - 2 * border, vr_h = a.height - 2 * border - 2 * row_offset;
@@ -717,19 +830,14 @@ __global__ void __launch_bounds__(128) k_update_feature_idepths(StereoArgs a) {
       if ((f.idepth_mu > 0.0f) && (idepth_cmp > 0.0f)) rescale_factor = idepth_cmp / f.idepth_mu;
 
       if ((rescale_factor <= P.rescale_factor_min) || (rescale_factor >= P.rescale_factor_max)) {
-        // :1604-1659 re-parent to the current pose-frame
+        // :1604-1659 the patch scale changed too much: move the feature to the current pose-frame
         EpiGeo epipf;
         epipf.init(a.K, a.Kinv);
-        float Tp[7];
-        const FrameDev fpf = a.frames[a.curr_pf];
-        const FrameDev fref = a.frames[f.frame_id];
-        se3_inv_mul(fpf.pose, fref.pose, Tp);
-        epipf.load(Tp, Tp + 4);
+        epipf.load_table(a.geo[FB_MAX_FRAMES + f.frame_id]);
         float upx, upy, idepth_pf, var_pf;
-        const bool move_success = filter_predict(epipf, P.fparams.process_var_factor, f.x, f.y,
-                                                 f.idepth_mu, f.idepth_var, &upx, &upy, &idepth_pf,
-                                                 &var_pf);
-        if (!move_success || !rect_contains(vr_x, vr_y, vr_w, vr_h, upx, upy)) {
+        const bool moved = filter_predict(epipf, P.fparams.process_var_factor, f.x, f.y, f.idepth_mu,
+                                          f.idepth_var, &upx, &upy, &idepth_pf, &var_pf);
+        if (!moved || !rect_contains(vr_x, vr_y, vr_w, vr_h, upx, upy)) {
           f.valid = 0;
           stage = 3;
         } else {
@@ -747,72 +855,115 @@ __global__ void __launch_bounds__(128) k_update_feature_idepths(StereoArgs a) {
         }
       } else {
         float sx, sy, ex, ey;
-        const bool region_success = filter_get_search_region(P.fparams, epigeo, a.width, a.height, f.x,
-                                                             f.y, f.idepth_mu, f.idepth_var, &sx, &sy,
-                                                             &ex, &ey);  // :1663
-        if (!region_success) {
+        if (!filter_get_search_region(P.fparams, epigeo, a.width, a.height, f.x, f.y, f.idepth_mu, f.idepth_var,
+                                      &sx, &sy, &ex, &ey)) {  // :1663
           stage = 4;
         } else if (!rect_contains(vr_x, vr_y, vr_w, vr_h, f.x, f.y)) {
           stage = 5;
         } else {
-          const float off = (float)a.pad;  // :1677-1678
+          // ---- inverse_depth_filter::search (.cc:184-266) in padded image coordinates (:1677-1678) ----
+          const float off = (float)a.pad;
+          const float urx = f.x + off, ury = f.y + off;
+          sx += off; sy += off; ex += off; ey += off;
+          // stage the bounding patch of the walk while the reference patch is gathered: the taps reach from
+          // start - 2 inc to end + 2 inc (+1 px for the bilinear footprint, +1 px of rounding slack)
+          float incx = ex - sx, incy = ey - sy;
+          const float epl = sqrt_rn(incx * incx + incy * incy);
+          incx *= P.fparams.sparams.sample_dist / epl;
+          incy *= P.fparams.sparams.sample_dist / epl;
+          const float ax = sx - 2.0f * incx, ay = sy - 2.0f * incy, bx = ex + 2.0f * incx, by = ey + 2.0f * incy;
+          const int tx0 = (int)fminf(ax, bx) - 1, ty0 = (int)fminf(ay, by) - 1;
+          PatchView view;
+          view.base = fnew.img;  // the image itself unless the walk fits the staged patch
+          view.pitch = a.pitch;
+          view.x0 = 0;
+          view.y0 = 0;
+          const bool staged = (int)fmaxf(ax, bx) + 2 - tx0 < FB_TILE && (int)fmaxf(ay, by) + 2 - ty0 < FB_TILE &&
+                              tx0 >= 0 && ty0 >= 0;
+          if (staged && lane == 0) patch_load_issue(&tmap_cmp, s_tile[w], &s_bar[w], tx0, ty0);
+          // reference patch: 5 samples along the epipolar line of the parent image (lanes 0..4)
+          float erx, ery;
+          epigeo.reference_epiline(urx, ury, &erx, &ery);
           const FrameDev fref = a.frames[f.frame_id];
-          const int status = filter_search(P.fparams, epigeo, rescale_factor, fref.img, fnew.img, step,
-                                           f.x + off, f.y + off, sx + off, sy + off, ex + off,
-                                           ey + off, &ucx, &ucy);  // :1690
+          float rv = 0.0f;
+          if (lane < 5) {
+            float px = urx, py = ury;
+            if (lane == 0) { px = urx - 2 * erx * rescale_factor; py = ury - 2 * ery * rescale_factor; }
+            if (lane == 1) { px = urx - erx * rescale_factor; py = ury - ery * rescale_factor; }
+            if (lane == 3) { px = urx + erx * rescale_factor; py = ury + ery * rescale_factor; }
+            if (lane == 4) { px = urx + 2 * erx * rescale_factor; py = ury + 2 * ery * rescale_factor; }
+            rv = bilinear_u8(fref.img, a.pitch, px, py);
+          }
+          float ref[5];
+#pragma unroll
+          for (int i = 0; i < 5; ++i) ref[i] = __shfl_sync(0xffffffffu, rv, i);
+          float ref_grad = 0.0f;
+#pragma unroll
+          for (int i = 1; i < 5; ++i) {
+            const float g = fast_absf(ref[i] - ref[i - 1]);
+            if (g > ref_grad) ref_grad = g;
+          }
+          __syncwarp();
+          if (staged) {  // the patch is consumed (or at least awaited) on every path: the CTA may not retire under it
+            patch_load_wait(&s_bar[w]);
+            view.base = s_tile[w];
+            view.pitch = FB_TILE;
+            view.x0 = tx0;
+            view.y0 = ty0;
+          }
+          int status;
+          if (ref_grad < P.fparams.min_grad_mag) {
+            status = 1;  // FAIL_REF_PATCH_GRADIENT
+          } else {
+            const int r = warp_line_match(P.fparams.sparams, rescale_factor, ref, view, sx, sy, ex, ey, s_ws[w],
+                                          &ucx, &ucy);
+            status = (r == 0) ? 0 : (r == 1 ? 2 : 3);  // SUCCESS / FAIL_AMBIGUOUS_MATCH / FAIL_MAX_COST
+          }
           f.search_status = status;
           if (status != 0) {
             stage = 6;
           } else {
             flow_x = ucx - off;
             flow_y = ucy - off;
-            track_success = true;
           }
         }
       }
     }
 
-    if (!track_success) {
+    if (stage != 0) {
       feature_fail(P, f);
       dg.stage = stage;
     } else {
       dg.flow_x = flow_x;
       dg.flow_y = flow_y;
-      // ---------------- measurement (:1380-1390) ----------------
-      float mu_meas, var_meas;
-      const bool sense_success = meas_idepth(P.zparams, epigeo, fnew.gx, fnew.gy, step, f.x, f.y,
-                                             flow_x, flow_y, &mu_meas, &var_meas);
+      // ---------------- measurement (:1380-1390) and fusion (:1436) ----------------
+      float mu_meas, var_meas, mu_post, var_post;
+      const bool sensed = meas_idepth(P.zparams, epigeo, fnew.gx, fnew.gy, a.pitch, f.x, f.y, flow_x, flow_y,
+                                      &mu_meas, &var_meas);
       dg.mu_meas = mu_meas;
       dg.var_meas = var_meas;
-      if (!sense_success) {
+      if (!sensed) {
         feature_fail(P, f);
         dg.stage = 7;
+      } else if (!filter_update(f.idepth_mu, f.idepth_var, mu_meas, var_meas, &mu_post, &var_post,
+                                P.outlier_sigma_thresh)) {
+        feature_fail(P, f);
+        dg.stage = 8;
       } else {
-        float mu_post, var_post;
-        const bool fuse_success = filter_update(f.idepth_mu, f.idepth_var, mu_meas, var_meas, &mu_post,
-                                                &var_post, P.outlier_sigma_thresh);  // :1436
-        if (!fuse_success) {
-          feature_fail(P, f);
-          dg.stage = 8;
-        } else {
-          if (P.do_meas_fusion) {
-            f.idepth_mu = mu_post;
-            f.idepth_var = var_post;
-          } else {
-            f.idepth_mu = mu_meas;
-            f.idepth_var = var_meas;
-          }
-          f.valid = 1;
-          f.num_updates++;
-          f.num_dropouts = 0;
-          dg.stage = 9;
-          atomicAdd(a.count, 1);
-        }
+        f.idepth_mu = P.do_meas_fusion ? mu_post : mu_meas;
+        f.idepth_var = P.do_meas_fusion ? var_post : var_meas;
+        f.valid = 1;
+        f.num_updates++;
+        f.num_dropouts = 0;
+        dg.stage = 9;
+        if (lane == 0) atomicAdd(a.count, 1);
       }
     }
-    a.feats[ii] = f;
   }
-  if (a.diag) a.diag[ii] = dg;
+  if (lane == 0) {
+    a.feats_out[ii] = f;
+    if (a.diag) a.diag[ii] = dg;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -829,13 +980,13 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 }
 
 __global__ void __launch_bounds__(256)
-k_frame_prep(const unsigned char* __restrict__ img, int width, int height, int border,
+k_frame_prep(const unsigned char* __restrict__ img, int width, int height, int border, int pitch,
              unsigned char* __restrict__ img_pad, float* __restrict__ gx_pad, float* __restrict__ gy_pad) {
   const int pw = width + 2 * border, ph = height + 2 * border;
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= pw || y >= ph) return;
   const int sx = x - border, sy = y - border;
-  const size_t o = (size_t)y * pw + x;
+  const size_t o = (size_t)y * pitch + x;
   img_pad[o] = __ldg(img + (size_t)reflect101(sy, height) * width + reflect101(sx, width));
   float gx = 0.0f, gy = 0.0f;
   if (sx >= 0 && sx < width && sy >= 0 && sy < height) {
@@ -858,6 +1009,7 @@ static StereoState* get_state(void** st) {
   if (!*st) {
     StereoState* s = new StereoState();
     std::memset(s->h_frames, 0, sizeof(s->h_frames));
+    std::memset(s->tmap, 0, sizeof(s->tmap));
     *st = s;
   }
   return static_cast<StereoState*>(*st);
@@ -865,6 +1017,11 @@ static StereoState* get_state(void** st) {
 
 int stereo_set_camera(void** state, int width, int height, const float K[9], const float Kinv[9]) {
   StereoState* s = get_state(state);
+  if (width != s->width || height != s->height) {
+    // frame slots uploaded under another image size no longer match: they have to be uploaded again
+    for (int i = 0; i < FB_MAX_FRAMES; ++i) s->h_frames[i].valid = 0;
+    s->pad = 0;
+  }
   s->width = width;
   s->height = height;
   std::memcpy(s->K, K, sizeof(s->K));
@@ -872,9 +1029,39 @@ int stereo_set_camera(void** state, int width, int height, const float K[9], con
   return 0;
 }
 
-int stereo_frame_upload(void** state, cudaStream_t st, int fslot, const uint8_t* img_pad,
-                        const float* gradx_pad, const float* grady_pad, int pad, const float pose[7]) {
-  StereoState* s = get_state(state);
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int encode_image_map(CUtensorMap* out, unsigned char* img, int valid_w, int rows, int pitch) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    FB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available in this driver");
+      return FLAME_B200_ECUDA;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)valid_w, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch};
+  const cuuint32_t box[2] = {FB_TILE, FB_TILE};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, img, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return FLAME_B200_ECUDA;
+  }
+  return 0;
+}
+
+// Validates the slot / padding, sizes the slot's pitched buffers (pitch = padded width rounded up to 64
+// bytes: TMA needs 16-byte row strides) and (re)builds its TMA descriptor.
+static int frame_slot_prepare(StereoState* s, int fslot, int pad) {
   if (s->width <= 0) {
     set_error("frame_upload: call flame_b200_set_camera first");
     return FLAME_B200_ESTATE;
@@ -892,73 +1079,76 @@ int stereo_frame_upload(void** state, cudaStream_t st, int fslot, const uint8_t*
     }
   }
   s->pad = pad;
-  const size_t npix = (size_t)(s->width + 2 * pad) * (s->height + 2 * pad);
+  s->pitch = (s->width + 2 * pad + 63) / 64 * 64;
+  const int rows = s->height + 2 * pad;
+  const size_t npix = (size_t)s->pitch * rows;
   if (npix > s->cap_pix[fslot]) {
-    if (s->d_img[fslot]) FB_CUDA(cudaFree(s->d_img[fslot]));
-    if (s->d_gx[fslot]) FB_CUDA(cudaFree(s->d_gx[fslot]));
-    if (s->d_gy[fslot]) FB_CUDA(cudaFree(s->d_gy[fslot]));
+    s->h_frames[fslot].valid = 0;
+    s->cap_pix[fslot] = 0;
+    for (void** p : {(void**)&s->d_img[fslot], (void**)&s->d_gx[fslot], (void**)&s->d_gy[fslot]}) {
+      if (*p) FB_CUDA(cudaFree(*p));
+      *p = nullptr;
+    }
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_img[fslot]), npix));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_gx[fslot]), npix * 4));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_gy[fslot]), npix * 4));
     s->cap_pix[fslot] = npix;
+    s->slot_w[fslot] = 0;
+  }
+  if (s->slot_w[fslot] != s->width || s->slot_h[fslot] != s->height || s->slot_pad[fslot] != pad) {
+    if (int rc = encode_image_map(&s->tmap[fslot], s->d_img[fslot], s->width + 2 * pad, rows, s->pitch)) return rc;
+    s->slot_w[fslot] = s->width;
+    s->slot_h[fslot] = s->height;
+    s->slot_pad[fslot] = pad;
   }
   if (!s->d_frames) FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_frames), sizeof(s->h_frames)));
   if (!s->stage_free) FB_CUDA(cudaEventCreateWithFlags(&s->stage_free, cudaEventDisableTiming));
-  const size_t need = npix * 9 + sizeof(s->h_frames);
+  return 0;
+}
+
+static int stage_reserve(StereoState* s, size_t need) {
   FB_CUDA(cudaEventSynchronize(s->stage_free));
   if (need > s->h_stage_cap) {
+    s->h_stage_cap = 0;
     if (s->h_stage) FB_CUDA(cudaFreeHost(s->h_stage));
+    s->h_stage = nullptr;
     FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s->h_stage), need));
     s->h_stage_cap = need;
   }
-  unsigned char* hs = s->h_stage;
-  std::memcpy(hs, gradx_pad, npix * 4);
-  std::memcpy(hs + npix * 4, grady_pad, npix * 4);
-  std::memcpy(hs + npix * 8, img_pad, npix);
+  return 0;
+}
+
+static void frame_publish(StereoState* s, int fslot, const float pose[7], unsigned char* hs_frames) {
   FrameDev& fr = s->h_frames[fslot];
   fr.img = s->d_img[fslot];
   fr.gx = s->d_gx[fslot];
   fr.gy = s->d_gy[fslot];
   std::memcpy(fr.pose, pose, sizeof(fr.pose));
   fr.valid = 1;
-  std::memcpy(hs + npix * 9, s->h_frames, sizeof(s->h_frames));
-  FB_CUDA(cudaMemcpyAsync(s->d_gx[fslot], hs, npix * 4, cudaMemcpyHostToDevice, st));
-  FB_CUDA(cudaMemcpyAsync(s->d_gy[fslot], hs + npix * 4, npix * 4, cudaMemcpyHostToDevice, st));
-  FB_CUDA(cudaMemcpyAsync(s->d_img[fslot], hs + npix * 8, npix, cudaMemcpyHostToDevice, st));
-  FB_CUDA(cudaMemcpyAsync(s->d_frames, hs + npix * 9, sizeof(s->h_frames), cudaMemcpyHostToDevice, st));
-  FB_CUDA(cudaEventRecord(s->stage_free, st));
-  return 0;
+  std::memcpy(hs_frames, s->h_frames, sizeof(s->h_frames));
 }
 
-static int frame_slot_prepare(StereoState* s, int fslot, int pad, size_t npix) {
-  if (s->width <= 0) {
-    set_error("frame_upload: call flame_b200_set_camera first");
-    return FLAME_B200_ESTATE;
-  }
-  if (fslot < 0 || fslot >= FB_MAX_FRAMES || pad < 0) {
-    set_error("frame_upload: frame slot out of range");
-    return FLAME_B200_EINVAL;
-  }
-  if (s->pad != 0 && s->pad != pad) {
-    bool any = false;
-    for (int i = 0; i < FB_MAX_FRAMES; ++i) any |= (s->h_frames[i].valid != 0 && i != fslot);
-    if (any) {
-      set_error("frame_upload: all frames must share one padding");
-      return FLAME_B200_EINVAL;
-    }
-  }
-  s->pad = pad;
-  if (npix > s->cap_pix[fslot]) {
-    if (s->d_img[fslot]) FB_CUDA(cudaFree(s->d_img[fslot]));
-    if (s->d_gx[fslot]) FB_CUDA(cudaFree(s->d_gx[fslot]));
-    if (s->d_gy[fslot]) FB_CUDA(cudaFree(s->d_gy[fslot]));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_img[fslot]), npix));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_gx[fslot]), npix * 4));
-    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_gy[fslot]), npix * 4));
-    s->cap_pix[fslot] = npix;
-  }
-  if (!s->d_frames) FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_frames), sizeof(s->h_frames)));
-  if (!s->stage_free) FB_CUDA(cudaEventCreateWithFlags(&s->stage_free, cudaEventDisableTiming));
+int stereo_frame_upload(void** state, cudaStream_t st, int fslot, const uint8_t* img_pad,
+                        const float* gradx_pad, const float* grady_pad, int pad, const float pose[7]) {
+  StereoState* s = get_state(state);
+  if (int rc = frame_slot_prepare(s, fslot, pad)) return rc;
+  const int pw = s->width + 2 * pad, rows = s->height + 2 * pad;
+  const size_t n = (size_t)pw * rows;
+  if (int rc = stage_reserve(s, n * 9 + sizeof(s->h_frames))) return rc;
+  unsigned char* hs = s->h_stage;
+  std::memcpy(hs, gradx_pad, n * 4);
+  std::memcpy(hs + n * 4, grady_pad, n * 4);
+  std::memcpy(hs + n * 8, img_pad, n);
+  frame_publish(s, fslot, pose, hs + n * 9);
+  const size_t pitch = (size_t)s->pitch;
+  FB_CUDA(cudaMemcpy2DAsync(s->d_gx[fslot], pitch * 4, hs, (size_t)pw * 4, (size_t)pw * 4, rows,
+                            cudaMemcpyHostToDevice, st));
+  FB_CUDA(cudaMemcpy2DAsync(s->d_gy[fslot], pitch * 4, hs + n * 4, (size_t)pw * 4, (size_t)pw * 4, rows,
+                            cudaMemcpyHostToDevice, st));
+  FB_CUDA(cudaMemcpy2DAsync(s->d_img[fslot], pitch, hs + n * 8, (size_t)pw, (size_t)pw, rows,
+                            cudaMemcpyHostToDevice, st));
+  FB_CUDA(cudaMemcpyAsync(s->d_frames, hs + n * 9, sizeof(s->h_frames), cudaMemcpyHostToDevice, st));
+  FB_CUDA(cudaEventRecord(s->stage_free, st));
   return 0;
 }
 
@@ -966,34 +1156,23 @@ static int frame_slot_prepare(StereoState* s, int fslot, int pad, size_t npix) {
 int stereo_frame_upload_raw(void** state, cudaStream_t st, int fslot, const uint8_t* img, int pad,
                             const float pose[7]) {
   StereoState* s = get_state(state);
-  const size_t npix = (size_t)(s->width + 2 * pad) * (s->height + 2 * pad);
-  if (int rc = frame_slot_prepare(s, fslot, pad, npix)) return rc;
+  if (int rc = frame_slot_prepare(s, fslot, pad)) return rc;
   const size_t nraw = (size_t)s->width * s->height;
-  const size_t need = nraw + sizeof(s->h_frames);
-  FB_CUDA(cudaEventSynchronize(s->stage_free));
-  if (need > s->h_stage_cap) {
-    if (s->h_stage) FB_CUDA(cudaFreeHost(s->h_stage));
-    FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s->h_stage), need));
-    s->h_stage_cap = need;
-  }
+  if (int rc = stage_reserve(s, nraw + sizeof(s->h_frames))) return rc;
   if (nraw > s->cap_raw) {
+    s->cap_raw = 0;
     if (s->d_raw) FB_CUDA(cudaFree(s->d_raw));
+    s->d_raw = nullptr;
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_raw), nraw));
     s->cap_raw = nraw;
   }
   std::memcpy(s->h_stage, img, nraw);
-  FrameDev& fr = s->h_frames[fslot];
-  fr.img = s->d_img[fslot];
-  fr.gx = s->d_gx[fslot];
-  fr.gy = s->d_gy[fslot];
-  std::memcpy(fr.pose, pose, sizeof(fr.pose));
-  fr.valid = 1;
-  std::memcpy(s->h_stage + nraw, s->h_frames, sizeof(s->h_frames));
+  frame_publish(s, fslot, pose, s->h_stage + nraw);
   FB_CUDA(cudaMemcpyAsync(s->d_raw, s->h_stage, nraw, cudaMemcpyHostToDevice, st));
   FB_CUDA(cudaMemcpyAsync(s->d_frames, s->h_stage + nraw, sizeof(s->h_frames), cudaMemcpyHostToDevice, st));
   FB_CUDA(cudaEventRecord(s->stage_free, st));
   const int pw = s->width + 2 * pad, ph = s->height + 2 * pad;
-  k_frame_prep<<<dim3((pw + 255) / 256, ph), 256, 0, st>>>(s->d_raw, s->width, s->height, pad,
+  k_frame_prep<<<dim3((pw + 255) / 256, ph), 256, 0, st>>>(s->d_raw, s->width, s->height, pad, s->pitch,
                                                          s->d_img[fslot], s->d_gx[fslot], s->d_gy[fslot]);
   count_launch();
   FB_CUDA(cudaGetLastError());
@@ -1007,41 +1186,32 @@ int stereo_frame_download(void* state, cudaStream_t st, int fslot, uint8_t* img_
     set_error("frame_download: frame slot not uploaded");
     return FLAME_B200_EINVAL;
   }
-  const size_t npix = (size_t)(s->width + 2 * s->pad) * (s->height + 2 * s->pad);
-  if (img_pad) FB_CUDA(cudaMemcpyAsync(img_pad, s->d_img[fslot], npix, cudaMemcpyDeviceToHost, st));
-  if (gradx_pad) FB_CUDA(cudaMemcpyAsync(gradx_pad, s->d_gx[fslot], npix * 4, cudaMemcpyDeviceToHost, st));
-  if (grady_pad) FB_CUDA(cudaMemcpyAsync(grady_pad, s->d_gy[fslot], npix * 4, cudaMemcpyDeviceToHost, st));
+  const size_t pw = (size_t)(s->width + 2 * s->pad), rows = (size_t)(s->height + 2 * s->pad), pitch = (size_t)s->pitch;
+  if (img_pad) FB_CUDA(cudaMemcpy2DAsync(img_pad, pw, s->d_img[fslot], pitch, pw, rows, cudaMemcpyDeviceToHost, st));
+  if (gradx_pad)
+    FB_CUDA(cudaMemcpy2DAsync(gradx_pad, pw * 4, s->d_gx[fslot], pitch * 4, pw * 4, rows, cudaMemcpyDeviceToHost, st));
+  if (grady_pad)
+    FB_CUDA(cudaMemcpy2DAsync(grady_pad, pw * 4, s->d_gy[fslot], pitch * 4, pw * 4, rows, cudaMemcpyDeviceToHost, st));
   FB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 
-int stereo_update(void* state, cudaStream_t st, const flame_b200_track_params* params, int fnew,
-                  int curr_pf, flame_b200_feature* feats, int32_t n_feats,
-                  flame_b200_track_diag* diag, int32_t* n_updates) {
-  StereoState* s = static_cast<StereoState*>(state);
-  if (!s || s->width <= 0) {
-    set_error("update_feature_idepths: camera / frames not set");
-    return FLAME_B200_ESTATE;
-  }
-  if (fnew < 0 || fnew >= FB_MAX_FRAMES || curr_pf < 0 || curr_pf >= FB_MAX_FRAMES ||
-      !s->h_frames[fnew].valid || !s->h_frames[curr_pf].valid) {
-    set_error("update_feature_idepths: frame slot not uploaded");
-    return FLAME_B200_EINVAL;
-  }
-  for (int i = 0; i < n_feats; ++i)
-    if (feats[i].frame_id >= FB_MAX_FRAMES || !s->h_frames[feats[i].frame_id].valid) {
-      set_error("update_feature_idepths: feature parented to a frame slot that was not uploaded");
-      return FLAME_B200_EINVAL;
-    }
-  if (n_updates) *n_updates = 0;
-  if (n_feats == 0) return 0;
+// ---- the resident feature set -------------------------------------------------------------------
+static int feats_reserve(StereoState* s, int n_feats) {
   if (n_feats > s->cap_feats) {
     const int n = n_feats + n_feats / 2;
-    if (s->d_feats) FB_CUDA(cudaFree(s->d_feats));
-    if (s->d_diag) FB_CUDA(cudaFree(s->d_diag));
+    s->cap_feats = 0;
+    s->n_feats = 0;
+    for (void** p : {(void**)&s->d_feats, (void**)&s->d_feats_out, (void**)&s->d_diag}) {
+      if (*p) FB_CUDA(cudaFree(*p));
+      *p = nullptr;
+    }
     if (s->h_feats) FB_CUDA(cudaFreeHost(s->h_feats));
     if (s->h_diag) FB_CUDA(cudaFreeHost(s->h_diag));
+    s->h_feats = nullptr;
+    s->h_diag = nullptr;
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_feats), (size_t)n * sizeof(flame_b200_feature)));
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_feats_out), (size_t)n * sizeof(flame_b200_feature)));
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_diag), (size_t)n * sizeof(flame_b200_track_diag)));
     FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s->h_feats), (size_t)n * sizeof(flame_b200_feature)));
     FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s->h_diag), (size_t)n * sizeof(flame_b200_track_diag)));
@@ -1051,10 +1221,57 @@ int stereo_update(void* state, cudaStream_t st, const flame_b200_track_params* p
     FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_count), sizeof(int)));
     FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s->h_count), sizeof(int)));
   }
+  if (!s->d_geo) FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_geo), 2 * FB_MAX_FRAMES * sizeof(GeoDev)));
+  if (!s->feats_free) FB_CUDA(cudaEventCreateWithFlags(&s->feats_free, cudaEventDisableTiming));
+  return 0;
+}
+
+int stereo_features_upload(void* state, cudaStream_t st, const flame_b200_feature* feats, int32_t n_feats) {
+  StereoState* s = static_cast<StereoState*>(state);
+  if (!s || s->width <= 0) {
+    set_error("features_upload: camera / frames not set");
+    return FLAME_B200_ESTATE;
+  }
+  for (int i = 0; i < n_feats; ++i)
+    if (feats[i].frame_id >= FB_MAX_FRAMES || !s->h_frames[feats[i].frame_id].valid) {
+      set_error("update_feature_idepths: feature parented to a frame slot that was not uploaded");
+      return FLAME_B200_EINVAL;
+    }
+  if (int rc = feats_reserve(s, n_feats)) return rc;
+  FB_CUDA(cudaEventSynchronize(s->feats_free));
+  s->n_feats = n_feats;
+  s->tracked = false;
+  if (n_feats == 0) return 0;
   std::memcpy(s->h_feats, feats, (size_t)n_feats * sizeof(flame_b200_feature));
   FB_CUDA(cudaMemcpyAsync(s->d_feats, s->h_feats, (size_t)n_feats * sizeof(flame_b200_feature),
                           cudaMemcpyHostToDevice, st));
+  FB_CUDA(cudaEventRecord(s->feats_free, st));
+  return 0;
+}
+
+// Asynchronous: resident set (in) -> results (out) + diagnostics + update count, all on the device.
+int stereo_features_track(void* state, cudaStream_t st, const flame_b200_track_params* params, int fnew,
+                          int curr_pf) {
+  StereoState* s = static_cast<StereoState*>(state);
+  if (!s || s->width <= 0 || !s->d_feats) {
+    set_error("features_track: camera / frames / features not set");
+    return FLAME_B200_ESTATE;
+  }
+  if (fnew < 0 || fnew >= FB_MAX_FRAMES || curr_pf < 0 || curr_pf >= FB_MAX_FRAMES ||
+      !s->h_frames[fnew].valid || !s->h_frames[curr_pf].valid) {
+    set_error("update_feature_idepths: frame slot not uploaded");
+    return FLAME_B200_EINVAL;
+  }
+  const flame_b200_filter_params& fp = params->fparams;
+  if (!(fp.sparams.sample_dist > 0.0f) ||
+      !(std::fmax(fp.epilength_max, fp.epilength_min) / fp.sparams.sample_dist + 4.0f <= (float)FB_SEARCH_MAX_STEPS)) {
+    set_error("update_feature_idepths: epilength / sample_dist allows more than " +
+              std::to_string(FB_SEARCH_MAX_STEPS - 4) + " SSD positions per feature");
+    return FLAME_B200_EINVAL;
+  }
+  s->tracked = true;
   FB_CUDA(cudaMemsetAsync(s->d_count, 0, sizeof(int), st));
+  if (s->n_feats == 0) return 0;
   StereoArgs a;
   a.P = *params;
   std::memcpy(a.K, s->K, sizeof(a.K));
@@ -1062,26 +1279,65 @@ int stereo_update(void* state, cudaStream_t st, const flame_b200_track_params* p
   a.width = s->width;
   a.height = s->height;
   a.pad = s->pad;
+  a.pitch = s->pitch;
   a.fnew = fnew;
   a.curr_pf = curr_pf;
   a.frames = s->d_frames;
+  a.geo = s->d_geo;
   a.feats = s->d_feats;
+  a.feats_out = s->d_feats_out;
   a.diag = s->d_diag;
-  a.n = n_feats;
+  a.n = s->n_feats;
   a.count = s->d_count;
-  k_update_feature_idepths<<<(n_feats + 127) / 128, 128, 0, st>>>(a);
-  count_launch();
+  k_epigeo_table<<<2, FB_MAX_FRAMES, 0, st>>>(a, s->d_geo);
+  k_track_features<<<(s->n_feats + TRACK_WARPS - 1) / TRACK_WARPS, 32 * TRACK_WARPS, 0, st>>>(a, s->tmap[fnew]);
+  count_launch(2);
   FB_CUDA(cudaGetLastError());
-  FB_CUDA(cudaMemcpyAsync(s->h_feats, s->d_feats, (size_t)n_feats * sizeof(flame_b200_feature),
-                          cudaMemcpyDeviceToHost, st));
-  FB_CUDA(cudaMemcpyAsync(s->h_diag, s->d_diag, (size_t)n_feats * sizeof(flame_b200_track_diag),
-                          cudaMemcpyDeviceToHost, st));
-  FB_CUDA(cudaMemcpyAsync(s->h_count, s->d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
-  FB_CUDA(cudaStreamSynchronize(st));
-  std::memcpy(feats, s->h_feats, (size_t)n_feats * sizeof(flame_b200_feature));
-  if (diag) std::memcpy(diag, s->h_diag, (size_t)n_feats * sizeof(flame_b200_track_diag));
-  if (n_updates) *n_updates = *s->h_count;
   return 0;
+}
+
+// Synchronises. commit != 0: the results become the resident set (the next track continues from them).
+int stereo_features_download(void* state, cudaStream_t st, flame_b200_feature* feats,
+                             flame_b200_track_diag* diag, int32_t* n_updates, int commit) {
+  StereoState* s = static_cast<StereoState*>(state);
+  if (!s || !s->d_feats) {
+    set_error("features_download: no resident feature set");
+    return FLAME_B200_ESTATE;
+  }
+  const int n = s->n_feats;
+  const flame_b200_feature* src = s->tracked ? s->d_feats_out : s->d_feats;
+  if (n > 0 && feats)
+    FB_CUDA(cudaMemcpyAsync(s->h_feats, src, (size_t)n * sizeof(flame_b200_feature), cudaMemcpyDeviceToHost, st));
+  if (n > 0 && diag && s->tracked)
+    FB_CUDA(cudaMemcpyAsync(s->h_diag, s->d_diag, (size_t)n * sizeof(flame_b200_track_diag),
+                            cudaMemcpyDeviceToHost, st));
+  if (n_updates && s->tracked)
+    FB_CUDA(cudaMemcpyAsync(s->h_count, s->d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaEventRecord(s->feats_free, st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  if (n > 0 && feats) std::memcpy(feats, s->h_feats, (size_t)n * sizeof(flame_b200_feature));
+  if (n > 0 && diag && s->tracked) std::memcpy(diag, s->h_diag, (size_t)n * sizeof(flame_b200_track_diag));
+  if (n_updates) *n_updates = s->tracked ? *s->h_count : 0;
+  if (commit && s->tracked) {
+    std::swap(s->d_feats, s->d_feats_out);
+    s->tracked = false;
+  }
+  return 0;
+}
+
+int stereo_features_count(void* state) {
+  StereoState* s = static_cast<StereoState*>(state);
+  return s ? s->n_feats : 0;
+}
+
+int stereo_update(void* state, cudaStream_t st, const flame_b200_track_params* params, int fnew,
+                  int curr_pf, flame_b200_feature* feats, int32_t n_feats,
+                  flame_b200_track_diag* diag, int32_t* n_updates) {
+  if (n_updates) *n_updates = 0;
+  if (int rc = stereo_features_upload(state, st, feats, n_feats)) return rc;
+  if (int rc = stereo_features_track(state, st, params, fnew, curr_pf)) return rc;
+  if (n_feats == 0) return 0;
+  return stereo_features_download(state, st, feats, diag, n_updates, 1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1144,6 +1400,9 @@ void stereo_destroy(void* state) {
   if (s->h_stage) cudaFreeHost(s->h_stage);
   if (s->stage_free) cudaEventDestroy(s->stage_free);
   if (s->d_feats) cudaFree(s->d_feats);
+  if (s->d_feats_out) cudaFree(s->d_feats_out);
+  if (s->d_geo) cudaFree(s->d_geo);
+  if (s->feats_free) cudaEventDestroy(s->feats_free);
   if (s->d_diag) cudaFree(s->d_diag);
   if (s->d_count) cudaFree(s->d_count);
   if (s->h_feats) cudaFreeHost(s->h_feats);

@@ -69,6 +69,16 @@ int flame_b200_ctx_join(flame_b200_ctx* ctx);
 /* cudaStream_t of the context, as an opaque pointer (for CUDA-event timing by the caller). */
 void* flame_b200_ctx_stream(flame_b200_ctx* ctx);
 
+/* How graphs uploaded AFTER this call are laid out for the resident solver. A frame's primal-dual state
+ * lives in the shared memory of one thread-block cluster for the whole solve:
+ *   FLAME_B200_PREF_THROUGHPUT (default)  the smallest cluster that holds the graph (9 CTAs for 10 000
+ *       Delaunay vertices), so that as many frames as possible are solved concurrently (flame_b200_pd_wave);
+ *   FLAME_B200_PREF_LATENCY               the frame is spread over more SMs (up to 16): a single frame
+ *       finishes sooner, fewer frames are resident at once.
+ * Results are bit-identical either way. */
+enum { FLAME_B200_PREF_THROUGHPUT = 0, FLAME_B200_PREF_LATENCY = 1 };
+int flame_b200_ctx_set_pd_preference(flame_b200_ctx* ctx, int pref);
+
 /* Pinned (page-locked) host memory for buffers handed to the asynchronous download calls. */
 int flame_b200_host_alloc(size_t bytes, void** out);
 int flame_b200_host_free(void* p);
@@ -264,12 +274,41 @@ int flame_b200_mesh_coverage(flame_b200_ctx* ctx, int slot, int64_t* covered);
  *      features (syncGraph's init rule + edge weights), n_iters x step(), extraction of the smoothed
  *      vertex idepths (x * scale) and plane parameters, interpolateMesh into a NaN-initialised map.
  *      Host buffers in, host buffers out (any output pointer may be NULL); out_map should be
- *      page-locked (flame_b200_host_alloc) for full PCIe speed. Synchronises the stream. */
+ *      page-locked (flame_b200_host_alloc) for full PCIe speed. Synchronises. */
 int flame_b200_process_frame(flame_b200_ctx* ctx, int slot, int32_t V, const float* pos,
                              const float* idepth, const float* weight, int32_t E,
                              const int32_t* edges, int32_t T, const int32_t* tris, int rows, int cols,
                              const flame_b200_pd_params* params, int n_iters, float scale,
                              float* out_map, float* out_x, float* out_w1, float* out_w2);
+
+/* The same call split in two, for a pipeline of frames driven by ONE host thread: _submit copies the
+ * inputs into the slot's pinned staging area (the caller's input buffers are free on return) and only
+ * ENQUEUES the upload, the solve, the projection and the downloads on the slot's own CUDA stream; frames
+ * submitted to different slots of a context overlap (upload of frame k+1, solve of k, download of k-1, and
+ * as many concurrent solves as clusters fit the device). out_map (nullable; page-locked memory for a truly
+ * asynchronous copy) is written by the device->host copy and must stay valid until _wait returns.
+ * _wait blocks until the slot's frame is complete and copies x, w1, w2 (V floats each, any may be NULL) out.
+ * A slot holds one frame in flight: submit - wait - submit ...; until _wait, no other call may use the slot.
+ * The frame's graph and dense map stay in the slot afterwards (flame_b200_graph_download, mesh_download,
+ * mesh_filter ... work as after flame_b200_process_frame). */
+int flame_b200_process_frame_submit(flame_b200_ctx* ctx, int slot, int32_t V, const float* pos,
+                                    const float* idepth, const float* weight, int32_t E,
+                                    const int32_t* edges, int32_t T, const int32_t* tris, int rows, int cols,
+                                    const flame_b200_pd_params* params, int n_iters, float scale,
+                                    float* out_map);
+int flame_b200_process_frame_wait(flame_b200_ctx* ctx, int slot, float* out_x, float* out_w1, float* out_w2);
+
+/* Host-side accounting of the frame pipeline since context creation / the last reset: where the calling
+ * thread's time went (vertex ordering + launch plan, staging copies, enqueueing, waiting) and the bytes
+ * queued over PCIe. */
+typedef struct {
+  uint64_t frames, h2d_bytes, d2h_bytes;
+  double prep_seconds;    /* vertex order + launch plan (the only per-graph host computation)     */
+  double stage_seconds;   /* process_frame_submit up to the solver launch: prep + staging memcpys + upload calls */
+  double enqueue_seconds; /* solver / projection / download launches                               */
+  double wait_seconds;    /* blocked in process_frame_wait                                         */
+} flame_b200_stats;
+int flame_b200_ctx_stats(flame_b200_ctx* ctx, flame_b200_stats* out, int reset);
 
 /* ---- epipolar search + measurement + fusion: Flame::updateFeatureIDepths / trackFeature
  *      (flame.cc:1280-1752) over stereo::inverse_depth_filter::{predict,getSearchRegion,search,
@@ -358,11 +397,28 @@ int flame_b200_frame_download(flame_b200_ctx* ctx, int fslot, uint8_t* img_pad, 
 /* Replaces the loop body of Flame::updateFeatureIDepths (flame.cc:1308-1496) for n features:
  * feats is updated in place (host memory), diag (nullable) receives per-feature diagnostics.
  * fnew = frame slot of the new frame, curr_pf = frame slot of the current pose-frame.
- * Returns the number of successful updates in *n_updates. Synchronises the stream. */
+ * Returns the number of successful updates in *n_updates. Synchronises the stream.
+ * The SSD walk of a feature is held in shared memory by one warp: parameter sets that allow more than 124
+ * positions per feature (max(epilength_max, epilength_min) / sample_dist + 4 > 128; the defaults give 36)
+ * are rejected with FLAME_B200_EINVAL. */
 int flame_b200_update_feature_idepths(flame_b200_ctx* ctx, const flame_b200_track_params* params,
                                       int fnew, int curr_pf, flame_b200_feature* feats,
                                       int32_t n_feats, flame_b200_track_diag* diag,
                                       int32_t* n_updates);
+
+/* The same with the feature set RESIDENT on the device (features stay in HBM from frame to frame, as the
+ * graph does with flame_b200_graph_resync):
+ *   _upload   replaces the resident set with n host records (validated against the uploaded frame slots);
+ *   _track    runs the loop body of Flame::updateFeatureIDepths on the resident set. Asynchronous, and
+ *             out-of-place: the results, diagnostics and update count are written next to the set, so a
+ *             repeated call recomputes the same results from the same inputs;
+ *   _download copies the results (or, before any _track, the set itself) to host memory; any pointer may be
+ *             NULL. commit != 0 makes the results the resident set: the next _track continues from them,
+ *             as the reference's in-place update does (flame.cc:1308-1496). Synchronises. */
+int flame_b200_features_upload(flame_b200_ctx* ctx, const flame_b200_feature* feats, int32_t n_feats);
+int flame_b200_features_track(flame_b200_ctx* ctx, const flame_b200_track_params* params, int fnew, int curr_pf);
+int flame_b200_features_download(flame_b200_ctx* ctx, flame_b200_feature* feats, flame_b200_track_diag* diag,
+                                 int32_t* n_updates, int commit);
 
 #ifdef __cplusplus
 }

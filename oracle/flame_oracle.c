@@ -1147,9 +1147,12 @@ void oracle_track_default_params(oracle_track_params* p) {
   p->do_letterbox = 0;
 }
 
-/* cv::Rect_<int>::contains(Point2f): x <= pt.x < x+width && y <= pt.y < y+height (int->float) */
+/* cv::Rect_<int>::contains takes a Point_<int> (OpenCV 3.2 core/types.hpp): the Point2f handed to it at
+ * flame.cc:1624,1680 is first converted with saturate_cast<int> = cvRound (round half to even), and the
+ * ROUNDED point is tested: x <= pt.x < x+width && y <= pt.y < y+height. */
 static int rect_contains(int rx, int ry, int rw, int rh, float px, float py) {
-  return (float)rx <= px && px < (float)(rx + rw) && (float)ry <= py && py < (float)(ry + rh);
+  const int ix = (int)lrintf(px), iy = (int)lrintf(py);
+  return rx <= ix && ix < rx + rw && ry <= iy && iy < ry + rh;
 }
 
 /* flame.cc:1536-1752. Returns 1 on success (flow valid). *stage gets the exit point. */

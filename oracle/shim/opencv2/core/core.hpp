@@ -86,7 +86,9 @@ struct Rect_ {
   Rect_(T x_, T y_, T w_, T h_) : x(x_), y(y_), width(w_), height(h_) {}
   Point_<T> tl() const { return Point_<T>(x, y); }
   Point_<T> br() const { return Point_<T>(x + width, y + height); }
-  template <typename U> bool contains(const Point_<U>& pt) const {
+  // OpenCV 3.2 (core/types.hpp): contains() takes Point_<T>, so a Point2f handed to a cv::Rect is first
+  // converted with saturate_cast<int> (round half to even) and the ROUNDED point is tested.
+  bool contains(const Point_<T>& pt) const {
     return x <= pt.x && pt.x < x + width && y <= pt.y && pt.y < y + height;
   }
 };

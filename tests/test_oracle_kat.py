@@ -288,6 +288,47 @@ def test_oracle_stereo_equals_reference_verbatim(oracle, t_world, yaw):
         assert np.array_equal(d1[k][m].view(np.uint32), d2[k][m].view(np.uint32)), k
 
 
+def _border_features(W, H, border=4):
+    """Features within +-0.4 px of the valid-region border (cv::Rect::contains rounds the Point2f first)."""
+    from flame_b200 import synth as _s
+    g = _s.config_graph("A")
+    feats = _s.make_features(g["pos"], W, H, rel_sigma=0.1)
+    n = len(feats)
+    offs = np.array([-0.6, -0.5, -0.4, -0.1, 0.0, 0.4, 0.5, 0.6], np.float32)
+    q = n // 4
+    feats["x"][:q] = border + offs[np.arange(q) % 8]
+    feats["x"][q:2 * q] = (W - border) + offs[np.arange(q) % 8]
+    feats["y"][2 * q:3 * q] = border + offs[np.arange(q) % 8]
+    feats["y"][3 * q:4 * q] = (H - border) + offs[np.arange(q) % 8]
+    return feats
+
+
+def test_valid_region_rounds_like_opencv(oracle):
+    """cv::Rect_<int>::contains(Point_<int>) — a Point2f is saturate_cast to int (round half to even)
+    BEFORE the comparison (flame.cc:1624,1680): x = 3.6 with border 4 is inside, x = 3.4 is not; the
+    right edge W - 4 excludes x = W - 4.4 .. (rounds to W - 4) but keeps W - 4.6."""
+    W, H, V, _ = synth.CONFIGS["A"]
+    K, Kinv, frames = synth.make_stereo_pair(W, H)
+    feats = _border_features(W, H)
+    p = oracle.track_default_params()
+    f1 = feats.copy()
+    n1, d1 = oracle.update_feature_idepths(p, K, Kinv, W, H, synth.PAD, frames, 1, 0, f1)
+    # border = int(rescale_factor_max * win_size / 2 + 1) = 4 (flame.cc:1576); stage 5 = "outside the valid region"
+    ix, iy = np.rint(feats["x"]).astype(int), np.rint(feats["y"]).astype(int)  # np.rint: half to even
+    inside = (ix >= 4) & (ix < W - 4) & (iy >= 4) & (iy < H - 4)
+    reached = d1["stage"] >= 5  # earlier exits (predict / search-region failures) never get to the test
+    assert np.array_equal(d1["stage"][reached] != 5, inside[reached])
+    near = (np.abs(feats["x"] - (W - 4)) < 0.7) | (np.abs(feats["y"] - 4) < 0.7) | (np.abs(feats["y"] - (H - 4)) < 0.7)
+    assert (inside & reached & near).sum() > 20 and (~inside & reached & near).sum() > 20
+    # the unrounded comparison would decide differently for some of them
+    naive = (feats["x"] >= 4) & (feats["x"] < W - 4) & (feats["y"] >= 4) & (feats["y"] < H - 4)
+    assert (naive != inside)[reached].any()
+    if oracle.have_ref():
+        f2 = feats.copy()
+        n2, d2 = oracle.ref_update_feature_idepths(p, K, Kinv, W, H, synth.PAD, frames, 1, 0, f2)
+        assert n1 == n2 and np.array_equal(d1["stage"], d2["stage"]) and f1.tobytes() == f2.tobytes()
+
+
 def test_epigeo_oracle_equals_reference_verbatim(oracle):
     _need_ref(oracle)
     K, Kinv = synth.camera(640, 480)

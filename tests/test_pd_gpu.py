@@ -218,28 +218,59 @@ def test_pd_graph_larger_than_a_cluster_streams(gpu_ctx, oracle):
 
 
 @pytest.mark.parametrize("cfg", ["A", "B", "D"])
-def test_pd_halo_exchange_variant(gpu_ctx, oracle, cfg, monkeypatch):
-    """FLAME_B200_PD_SYNC=p2p selects the experimental resident kernel (local halos, point-to-point
-    mbarrier synchronisation instead of cluster barriers): slower on B200, but it must stay bit-exact."""
-    monkeypatch.setenv("FLAME_B200_PD_SYNC", "p2p")
+@pytest.mark.parametrize("pref", [_lib.PREF_THROUGHPUT, _lib.PREF_LATENCY])
+def test_pd_cluster_preference(gpu_ctx, oracle, cfg, pref):
+    """Throughput layout (smallest cluster: 9 CTAs x 1024 threads for config D) and latency layout
+    (16 CTAs x 640 threads) give the same bits."""
     g = synth.config_graph(cfg)
     n = 40
     want = _oracle_state(oracle, g, n)
     V, E = g["pos"].shape[0], g["edges"].shape[0]
-    gpu_ctx.graph_init(0, g["pos"], g["data_term"], g["edges"])
-    gpu_ctx.pd_run(_lib.default_pd_params(), n, mode=_lib.PD_RESIDENT)
-    got = gpu_ctx.graph_download(0, V, E)
+    gpu_ctx.set_pd_preference(pref)
+    try:
+        gpu_ctx.graph_init(0, g["pos"], g["data_term"], g["edges"])
+        gpu_ctx.pd_run(_lib.default_pd_params(), n, mode=_lib.PD_RESIDENT)
+        got = gpu_ctx.graph_download(0, V, E)
+    finally:
+        gpu_ctx.set_pd_preference(_lib.PREF_THROUGHPUT)
     _assert_bit_equal(got, want, STATE)
 
 
 @pytest.mark.parametrize("V", [1400, 3000, 5600, 7000])
-def test_pd_cluster_sizes_not_powers_of_two(gpu_ctx, oracle, V, monkeypatch):
-    """The planner takes the smallest cluster that holds the graph (3, 5, 9, 12 CTAs for these sizes)."""
+def test_pd_cluster_sizes_not_powers_of_two(gpu_ctx, oracle, V):
+    """The planner takes the smallest cluster that holds the graph (any size, not only powers of two)."""
     g = synth.make_graph(1280, 720, V, seed=70 + V, noise_seed=71 + V, triangulator="scipy")
     want = _oracle_state(oracle, g, 30)
     E = g["edges"].shape[0]
-    for sync in ("barrier", "p2p"):
-        monkeypatch.setenv("FLAME_B200_PD_SYNC", sync)
-        gpu_ctx.graph_init(6, g["pos"], g["data_term"], g["edges"])
-        gpu_ctx.pd_run(_lib.default_pd_params(), 30, slot0=6, mode=_lib.PD_RESIDENT)
-        _assert_bit_equal(gpu_ctx.graph_download(6, V, E), want, STATE)
+    for pref in (_lib.PREF_THROUGHPUT, _lib.PREF_LATENCY):
+        gpu_ctx.set_pd_preference(pref)
+        try:
+            gpu_ctx.graph_init(6, g["pos"], g["data_term"], g["edges"])
+            gpu_ctx.pd_run(_lib.default_pd_params(), 30, slot0=6, mode=_lib.PD_RESIDENT)
+            got = gpu_ctx.graph_download(6, V, E)
+        finally:
+            gpu_ctx.set_pd_preference(_lib.PREF_THROUGHPUT)
+        _assert_bit_equal(got, want, STATE)
+
+
+def test_pd_layout_with_multi_edges_and_self_loops(gpu_ctx, oracle):
+    """The device-built incidence layout orders a vertex's incidences by edge id: a random multigraph with
+    parallel edges (same and reversed orientation) keeps the reference's summation order."""
+    rng = np.random.default_rng(77)
+    V = 700
+    pos = rng.uniform(4, 600, (V, 2)).astype(np.float32)
+    edges = rng.integers(0, V, (2600, 2)).astype(np.int32)
+    edges[5] = edges[4]          # parallel edge, same orientation
+    edges[9] = edges[8][::-1]    # parallel edge, reversed
+    keep = edges[:, 0] != edges[:, 1]
+    edges = np.ascontiguousarray(edges[keep])
+    g = {"pos": pos, "edges": edges, "data_term": rng.uniform(0.1, 2.0, V).astype(np.float32),
+         "data_weight": np.ones(V, np.float32)}
+    alpha, beta = oracle.edge_weights(edges, pos)
+    want = synth.init_state(g, alpha, beta)
+    oracle.pd_run(want, oracle.pd_default_params(), 15)
+    for mode in (_lib.PD_STREAM, _lib.PD_RESIDENT):
+        gpu_ctx.graph_init(3, pos, g["data_term"], edges)
+        gpu_ctx.pd_run(_lib.default_pd_params(), 15, slot0=3, mode=mode)
+        got = gpu_ctx.graph_download(3, V, edges.shape[0])
+        _assert_bit_equal(got, want, STATE)

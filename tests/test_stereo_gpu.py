@@ -89,6 +89,17 @@ def test_failure_and_reparent_paths(gpu_ctx, oracle):
     assert (want[1]["valid"] == 0).any()
 
 
+def test_valid_region_border_rounding(gpu_ctx, oracle):
+    """Features within +-0.6 px of the valid-region border: cv::Rect::contains tests the ROUNDED point."""
+    from test_oracle_kat import _border_features
+    W, H, V, _ = synth.CONFIGS["A"]
+    K, Kinv, frames = synth.make_stereo_pair(W, H)
+    feats = _border_features(W, H)
+    got, want = _run_both(gpu_ctx, oracle, W, H, K, Kinv, frames, feats, 1, 0)
+    _assert_equal(got, want)
+    assert (want[2]["stage"] == 5).any()
+
+
 def test_nondefault_params(gpu_ctx, oracle):
     W, H, V, _ = synth.CONFIGS["A"]
     K, Kinv, frames = synth.make_stereo_pair(W, H, t_world=(-0.08, 0.03, 0.0), yaw_deg=-0.7)  # t_z == 0 branch
