@@ -31,6 +31,7 @@
 
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -48,7 +49,12 @@ struct FrameDev {
 
 #define FB_MAX_FRAMES 64
 #define FB_SEARCH_MAX_STEPS 128  // SSD positions per feature the warp kernel holds (default params: <= 36)
-#define FB_TILE 48               // side of the staged comparison-image patch [px]; inner extent multiple of 16 B
+// The staged comparison-image patch: FB_TILE_W x FB_TILE_H bytes. A TMA tile load needs the box to START on
+// a 16-byte boundary of the row (measured: an unaligned inner coordinate raises an illegal-instruction
+// fault), so the patch origin is rounded down to a multiple of 16 px and the box is 64 wide: >= 49 usable
+// columns, 48 rows - the default parameters need at most 43 x 43.
+#define FB_TILE_W 64
+#define FB_TILE_H 48
 
 // Geometry of one (parent frame -> target frame) pair: stereo::EpipolarGeometry<float> after loadGeometry.
 struct GeoDev {
@@ -100,6 +106,7 @@ struct StereoArgs {
   flame_b200_track_diag* diag;
   int n;
   int* count;
+  int stage_patches;  // 0: taps straight from the image (FLAME_B200_SEARCH_TMA=0, for A/B measurements)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -757,7 +764,7 @@ __device__ __forceinline__ void patch_load_issue(const CUtensorMap* tmap, void* 
   const uint32_t b = smem_addr(bar), d = smem_addr(dst);
   asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(FB_TILE * FB_TILE) : "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(FB_TILE_W * FB_TILE_H) : "memory");
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(d),
       "l"(tmap), "r"(x0), "r"(y0), "r"(b)
@@ -797,7 +804,7 @@ __device__ __forceinline__ bool rect_contains(int rx, int ry, int rw, int rh, fl
 #define TRACK_WARPS 4
 __global__ void __launch_bounds__(32 * TRACK_WARPS)
 k_track_features(StereoArgs a, const __grid_constant__ CUtensorMap tmap_cmp) {
-  __shared__ __align__(128) unsigned char s_tile[TRACK_WARPS][FB_TILE * FB_TILE];
+  __shared__ __align__(128) unsigned char s_tile[TRACK_WARPS][FB_TILE_W * FB_TILE_H];
   __shared__ WarpScratch s_ws[TRACK_WARPS];
   __shared__ __align__(8) unsigned long long s_bar[TRACK_WARPS];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -872,14 +879,14 @@ k_track_features(StereoArgs a, const __grid_constant__ CUtensorMap tmap_cmp) {
           incx *= P.fparams.sparams.sample_dist / epl;
           incy *= P.fparams.sparams.sample_dist / epl;
           const float ax = sx - 2.0f * incx, ay = sy - 2.0f * incy, bx = ex + 2.0f * incx, by = ey + 2.0f * incy;
-          const int tx0 = (int)fminf(ax, bx) - 1, ty0 = (int)fminf(ay, by) - 1;
+          const int tx0 = ((int)fminf(ax, bx) - 1) & ~15, ty0 = (int)fminf(ay, by) - 1;
           PatchView view;
           view.base = fnew.img;  // the image itself unless the walk fits the staged patch
           view.pitch = a.pitch;
           view.x0 = 0;
           view.y0 = 0;
-          const bool staged = (int)fmaxf(ax, bx) + 2 - tx0 < FB_TILE && (int)fmaxf(ay, by) + 2 - ty0 < FB_TILE &&
-                              tx0 >= 0 && ty0 >= 0;
+          const bool staged = a.stage_patches && (int)fmaxf(ax, bx) + 2 - tx0 < FB_TILE_W &&
+                              (int)fmaxf(ay, by) + 2 - ty0 < FB_TILE_H && tx0 >= 0 && ty0 >= 0;
           if (staged && lane == 0) patch_load_issue(&tmap_cmp, s_tile[w], &s_bar[w], tx0, ty0);
           // reference patch: 5 samples along the epipolar line of the parent image (lanes 0..4)
           float erx, ery;
@@ -907,7 +914,7 @@ k_track_features(StereoArgs a, const __grid_constant__ CUtensorMap tmap_cmp) {
           if (staged) {  // the patch is consumed (or at least awaited) on every path: the CTA may not retire under it
             patch_load_wait(&s_bar[w]);
             view.base = s_tile[w];
-            view.pitch = FB_TILE;
+            view.pitch = FB_TILE_W;
             view.x0 = tx0;
             view.y0 = ty0;
           }
@@ -1047,7 +1054,7 @@ static int encode_image_map(CUtensorMap* out, unsigned char* img, int valid_w, i
   }
   const cuuint64_t dims[2] = {(cuuint64_t)valid_w, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)pitch};
-  const cuuint32_t box[2] = {FB_TILE, FB_TILE};
+  const cuuint32_t box[2] = {FB_TILE_W, FB_TILE_H};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, img, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -1289,6 +1296,8 @@ int stereo_features_track(void* state, cudaStream_t st, const flame_b200_track_p
   a.diag = s->d_diag;
   a.n = s->n_feats;
   a.count = s->d_count;
+  a.stage_patches = 1;
+  if (const char* sv = getenv("FLAME_B200_SEARCH_TMA")) a.stage_patches = atoi(sv);
   k_epigeo_table<<<2, FB_MAX_FRAMES, 0, st>>>(a, s->d_geo);
   k_track_features<<<(s->n_feats + TRACK_WARPS - 1) / TRACK_WARPS, 32 * TRACK_WARPS, 0, st>>>(a, s->tmap[fnew]);
   count_launch(2);
