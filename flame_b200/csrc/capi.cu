@@ -67,7 +67,9 @@ struct Slot {
   MeshDev m{};
   int capT = 0;
   size_t cap_pix = 0;
-  size_t bound_pix = 0;             // rows*cols of the last bind (owner words are per linear pixel)
+  int cap_tiles = 0;                // screen tiles the bin tables are sized for
+  size_t cap_bins = 0;              // ints in m.bins
+  bool bins_dirty = true;           // topology / positions changed since the tile bins were built
   int mesh_V = -1;                  // vertex count the triangle indices were validated against at bind time
   int* d_tris = nullptr;            // owning pointers behind the const views in `m`
   unsigned char* d_tri_ok = nullptr;
@@ -526,9 +528,8 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
     for (void* p : {(void*)s.g.vprim, (void*)s.g.vbar, (void*)s.g.vbar2, (void*)s.g.vprev,
                     (void*)s.g.vwt, (void*)s.g.inc_q, (void*)s.g.inc_s, (void*)s.d_blob,
                     (void*)s.d_pos, (void*)s.d_values,
-                    (void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.d_tri_filt, (void*)s.m.img, (void*)s.m.setup,
-                    (void*)s.m.owner,
-                    (void*)s.m.big, (void*)s.m.counters, (void*)s.d_mpos, (void*)s.d_mvalues,
+                    (void*)s.d_tris, (void*)s.d_tri_ok, (void*)s.d_tri_filt, (void*)s.m.img, (void*)s.m.stat,
+                    (void*)s.m.bins, (void*)s.m.wide, (void*)s.m.counters, (void*)s.d_mpos, (void*)s.d_mvalues,
                     (void*)s.d_carry, (void*)s.d_vt})
       if (p) cudaFree(p);
     if (s.h_blob) cudaFreeHost(s.h_blob);
@@ -738,6 +739,7 @@ static int graph_upload_impl(flame_b200_ctx* c, int slot, const flame_b200_graph
   if (int rc = pd_pack(c->stream, s.g, s.d_raw(), g->alpha == nullptr, fresh)) return rc;
   s.loaded = true;
   s.stale = false;
+  s.bins_dirty = true;  // the dense projection bins triangles by vertex position
   return publish_graph(c, slot);
 }
 
@@ -782,6 +784,7 @@ int flame_b200_graph_project(flame_b200_ctx* c, int slot, const float q_wxyz[4],
   if (int rc = stereo_graph_project(c->stereo, c->stream, s.g, s.d_pos, q_wxyz, t, graph_scale,
                                     s.d_raw())) return rc;
   s.stale = true;
+  s.bins_dirty = true;
   if (V == 0) return 0;
   FB_CUDA(cudaMemcpyAsync(s.h_blob, s.d_blob, (size_t)3 * V * 4, cudaMemcpyDeviceToHost, c->stream));
   FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
@@ -1004,8 +1007,8 @@ static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* 
       set_error("mesh: triangle vertex index out of range");
       return FLAME_B200_EINVAL;
     }
-  if (T > FB_MAX_TRIANGLES) {
-    set_error("mesh: more than 2^20 - 1 triangles");
+  if (rows > FB_MAX_IMAGE_SIDE || cols > FB_MAX_IMAGE_SIDE) {
+    set_error("mesh: image side above 2896 px (the reference's fp32 edge functions stop being exact there)");
     return FLAME_B200_EINVAL;
   }
   if (T > s.capT) {
@@ -1014,30 +1017,32 @@ static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* 
     if (int rc = regrow(&s.d_tris, (size_t)n * 3 * sizeof(int))) return rc;
     if (int rc = regrow(&s.d_tri_ok, (size_t)n)) return rc;
     if (int rc = regrow(&s.d_tri_filt, (size_t)n)) return rc;
-    if (int rc = regrow(&s.m.setup, (size_t)n * sizeof(TriSetup))) return rc;
-    if (int rc = regrow(&s.m.big, (size_t)n * sizeof(int))) return rc;
+    if (int rc = regrow(&s.m.stat, (size_t)n * sizeof(TriStatic))) return rc;
+    if (int rc = regrow(&s.m.wide, (size_t)n * sizeof(int))) return rc;
     s.capT = n;
   }
   const size_t npix = (size_t)rows * cols;
-  if (npix >= ((size_t)1 << 31)) {
-    set_error("mesh: image too large");
-    return FLAME_B200_EINVAL;
-  }
   if (npix > s.cap_pix) {
     s.cap_pix = 0;
-    s.bound_pix = 0;
     if (int rc = regrow(&s.m.img, npix * sizeof(float))) return rc;
-    if (int rc = regrow(&s.m.owner, npix * sizeof(unsigned int))) return rc;
     s.cap_pix = npix;
   }
-  if (!s.m.counters) FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.m.counters), 8 * sizeof(int)));
-  if (npix != s.bound_pix) {
-    // owner words are indexed by linear pixel and tagged with the projection epoch: a different image
-    // size restarts both (stream-ordered, so earlier projections are unaffected)
-    FB_CUDA(cudaMemsetAsync(s.m.owner, 0, s.cap_pix * sizeof(unsigned int), c->stream));
-    FB_CUDA(cudaMemsetAsync(s.m.counters, 0, 8 * sizeof(int), c->stream));
-    s.bound_pix = npix;
+  const int n_tiles = raster_tiles(rows, cols);
+  if (n_tiles > s.cap_tiles) {
+    s.cap_tiles = 0;
+    // [counters 8 | tile_cnt n_tiles]
+    if (int rc = regrow(&s.m.counters, ((size_t)n_tiles + 8) * sizeof(int))) return rc;
+    s.cap_tiles = n_tiles;
   }
+  s.m.tile_cnt = s.m.counters + 8;
+  s.m.bin_cap = raster_bin_cap(T, rows, cols);
+  const size_t bin_ints = (size_t)n_tiles * s.m.bin_cap;
+  if (bin_ints > s.cap_bins) {
+    s.cap_bins = 0;
+    if (int rc = regrow(&s.m.bins, bin_ints * sizeof(int))) return rc;
+    s.cap_bins = bin_ints;
+  }
+  s.bins_dirty = true;
   s.m.tris = s.d_tris;
   s.m.tri_ok = s.d_tri_ok;
   s.m.tri_filt = nullptr;  // a new triangulation starts unfiltered
@@ -1109,7 +1114,8 @@ int flame_b200_mesh_bind(flame_b200_ctx* c, int slot, int32_t T, const int32_t* 
 int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float scale) {
   if (int rc = check_slot(c, slot0, n_slots)) return rc;
   if (int rc = use_device(c)) return rc;
-  int maxV = 0, maxT = 0, max_pix = 0;
+  int maxV = 0, maxT = 0, max_tiles = 0;
+  bool rebuild = false;
   for (int i = slot0; i < slot0 + n_slots; ++i) {
     Slot& s = c->slots[i];
     if (!s.loaded || !s.m.img || s.m.values != s.d_values || s.m.pos != s.d_pos) {
@@ -1122,7 +1128,8 @@ int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float sca
     }
     maxV = std::max(maxV, s.g.V);
     maxT = std::max(maxT, s.m.T);
-    max_pix = std::max(max_pix, s.m.rows * s.m.cols);
+    max_tiles = std::max(max_tiles, raster_tiles(s.m.rows, s.m.cols));
+    rebuild |= s.bins_dirty;
   }
   // values_from_graph overwrites what a pending projection of the same slots still reads
   if (int rc = join_range(c, slot0, slot0 + n_slots)) return rc;
@@ -1137,7 +1144,13 @@ int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float sca
     FB_CUDA(cudaStreamWaitEvent(c->side, c->ev_vals, 0));
     rs = c->side;
   }
-  if (int rc = raster_project(rs, c->d_meshes + slot0, n_slots, maxT, max_pix, 1)) return rc;
+  if (rebuild)  // re-arm [wide-list counter | per-tile counts] of every mesh of the batch (all are rebuilt)
+    for (int i = slot0; i < slot0 + n_slots; ++i) {
+      Slot& s = c->slots[i];
+      FB_CUDA(cudaMemsetAsync(s.m.counters, 0, ((size_t)raster_tiles(s.m.rows, s.m.cols) + 8) * sizeof(int), rs));
+      s.bins_dirty = false;
+    }
+  if (int rc = raster_project(rs, c->d_meshes + slot0, n_slots, maxT, max_tiles, 1, rebuild)) return rc;
   if (c->async_proj) {
     cudaEvent_t done = nullptr;
     if (!c->ev_pool.empty()) {
@@ -1306,7 +1319,9 @@ int flame_b200_interpolate_mesh(flame_b200_ctx* c, int slot, int32_t T, const in
   const size_t npix = (size_t)rows * cols;
   if (!fill_nan)
     FB_CUDA(cudaMemcpyAsync(s.m.img, out_host, npix * 4, cudaMemcpyHostToDevice, c->stream));
-  if (int rc = raster_project(c->stream, c->d_meshes + slot, 1, s.m.T, rows * cols, fill_nan)) return rc;
+  FB_CUDA(cudaMemsetAsync(s.m.counters, 0, ((size_t)raster_tiles(rows, cols) + 8) * sizeof(int), c->stream));
+  if (int rc = raster_project(c->stream, c->d_meshes + slot, 1, s.m.T, raster_tiles(rows, cols), fill_nan, 1)) return rc;
+  s.bins_dirty = true;  // bound to caller-supplied positions: never reused
   FB_CUDA(cudaMemcpyAsync(out_host, s.m.img, npix * 4, cudaMemcpyDeviceToHost, c->stream));
   FB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;

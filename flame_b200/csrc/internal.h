@@ -51,28 +51,28 @@ struct GraphDev {
   int* edge_slot;   // [2E] (caller edge, role) -> incidence slot                (device-built)
 };
 
-struct __align__(16) TriSetup {  // per triangle, written by k_tri_setup; 80 bytes = 5 x 128-bit loads
-  int xmin, xend, ymin, ymax;    // sweep columns [xmin, xend) (4-px groups), rows [ymin, ymax]
-  float A1, B1, C1, A2;          // edge functions w1 = e23, w2 = e31, w3 = e12
-  float B2, C2, A3, B3;
-  float C3, v1, v2, v3;          // values at p1, p2, p3 (reversed triangle order)
-  int fx1;                       // last footprint column, clamped to the image
-  int flags;                     // 2 sweep wraps past the right border, 4 degenerate, 8 large footprint
-  int pad0, pad1;
+struct __align__(16) TriStatic {  // per triangle, written by k_tri_static; 64 bytes; depends on topology + positions
+  int A1, B1, C1, A2;             // integer edge functions w1 = e23, w2 = e31, w3 = e12
+  int B2, C2, A3, B3;
+  int C3, xmin, xend, ymin;       // sweep columns [xmin, xend) (4-px groups), rows [ymin, ymax]
+  int ymax, fx1;                  // last column the triangle may write (before clipping to the image)
+  int flags;                      // 1 writes nothing, 2 sweep wraps past the right border, 4 degenerate, 8 wide list
+  int pad;
 };
 
 struct MeshDev {
-  int T, rows, cols, pad;
+  int T, rows, cols, bin_cap;  // bin_cap: triangle ids a screen tile's bin holds
   const int* tris;             // 3T caller vertex indices
   const unsigned char* tri_ok; // T: tri_valid && all three vtx_valid (nullable)
   const unsigned char* tri_filt; // T: display filters of flame_b200_mesh_filter (nullable)
   const float* pos;            // 2V caller order
   float* values;               // V caller order
   float* img;                  // rows*cols
-  TriSetup* setup;             // T
-  unsigned int* owner;         // rows*cols: (epoch << 20) | highest covering triangle of that epoch
-  int* big;                    // T: triangles with a large sweep footprint (one CTA each)
-  int* counters;               // [0] big-list length (re-armed by k_resolve) [1] projection epoch
+  TriStatic* stat;             // T
+  int* counters;               // [0] wide-list length; followed in memory by tile_cnt (zeroed together)
+  int* tile_cnt;               // n_tiles: triangles that asked for the tile's bin (may exceed bin_cap)
+  int* bins;                   // n_tiles x bin_cap triangle ids
+  int* wide;                   // <= T triangles reachable from every tile: many tiles, wrapping, or a full bin
 };
 
 // ---- PD (pd.cu) ----
@@ -120,7 +120,10 @@ inline size_t raw_f_offset(int field, int V, int E) {
 inline size_t raw_f_total(int V, int E) { return (size_t)13 * V + (size_t)5 * E; }
 
 // ---- dense projection (raster.cu) ----
-int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_pix, int fill_nan);
+int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_tiles, int fill_nan,
+                   int rebuild);
+int raster_tiles(int rows, int cols);  // screen tiles of an image (size of tile_cnt)
+int raster_bin_cap(int T, int rows, int cols);
 int raster_tri_filter(cudaStream_t st, const MeshDev& m, const flame_b200_tri_filter_params& p,
                       const float Kinv[9], unsigned char* out);
 int raster_coverage(cudaStream_t st, const MeshDev& m, unsigned long long* d_count);
@@ -129,6 +132,6 @@ int raster_vertex_normals(cudaStream_t st, const MeshDev& m, int V, const float 
 // values[vperm[v]] = vprim[v].x * scale  (vtx_idepths_ = x * graph_scale_, flame.cc:376)
 int raster_values_from_graph(cudaStream_t st, const GraphDev* gs_dev, const MeshDev* ms_dev, int n,
                              int maxV, float scale);
-#define FB_MAX_TRIANGLES ((1 << 20) - 1)  // triangle id field of the owner word
+#define FB_MAX_IMAGE_SIDE 2896  // |edge function| < 2^24: the reference's fp32 evaluation is exact up to here
 
 }  // namespace fb

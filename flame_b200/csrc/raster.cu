@@ -13,276 +13,239 @@
 //    (p.y*cols + p.x), so a degenerate (zero-area) triangle, whose edge functions vanish on a
 //    whole line, also writes NaN up to 3 pixels past xmax (possibly wrapping to the next row).
 //
-// Edge functions are integer-valued and exact in fp32 for images up to ~2896 px on a side
-// (|A*x + B*y + C| < 2^24), so direct evaluation equals the reference's incremental stepping.
+// Edge functions are integer-valued: the reference's fp32 evaluation is exact while
+// |A*x + B*y + C| < 2^24, i.e. for images up to 2896 px on a side (enforced at mesh_bind), so they are
+// evaluated here in int32 and converted (exactly) to fp32 for the shading.
 //
-// Formulation: the reference scatters triangles in order with read-modify-write, so the LAST
-// (highest-index) covering triangle wins. Here coverage and shading are split:
-//   k_tri_setup    one thread per triangle: rounding, edge coefficients, sweep footprint
-//   k_owner_small  one warp per triangle (16 x 2 pixel steps over its footprint): exact integer
-//                  coverage test, atomicMax((epoch << 20) | triangle) into a per-pixel owner word
-//   k_owner_big    one CTA per large-footprint triangle (hull slivers, texture-poor regions): rows
-//                  over warps, each row clipped to a conservative span from the three edge functions
-//   k_resolve      four pixels per thread: read the owner, shade that one triangle, write the pixel once
-// The owner word carries the projection's epoch, so the buffer never needs clearing between
-// projections (stale words lose every atomicMax and are ignored by k_resolve); when the 12-bit epoch
-// is about to wrap k_resolve zeroes the words it reads. Triangle ids use 20 bits (T < 2^20).
+// Formulation. The reference scatters triangles in list order with read-modify-write; the result at a
+// pixel is the shading of the HIGHEST-index triangle that covers it. Here every pixel is written once:
+//   k_tri_static  one thread per triangle, only when the mesh or its vertex positions changed: integer edge
+//                 coefficients, sweep footprint, and insertion of the triangle into the fixed-capacity bins
+//                 of the 16x8-pixel screen tiles its footprint overlaps. A triangle that overlaps more than
+//                 256 tiles, wraps past the right border, or finds a bin full goes to the mesh's "wide"
+//                 list instead (hull slivers; every tile tests that short list against its rectangle).
+//   k_tiles       one WARP per tile, 4 pixels per lane: the tile's triangles are staged through shared
+//                 memory (ballot-compacted, no block barrier), every pixel keeps the highest covering
+//                 triangle id in a register, shades once from that triangle's record and is stored with
+//                 128-bit writes. No atomics, no per-pixel owner buffer in HBM: the DRAM traffic of a
+//                 projection is the image plus the (cached, L2-resident) bins.
+// The bins depend on topology and positions only, so a slot that is projected repeatedly (new x, same
+// graph) pays for k_tiles alone.
 #include <algorithm>
+#include <cmath>
 
 #include "internal.h"
 
 namespace fb {
 
-#define OWNER_T_BITS 20
-#define EPOCH_MAX 4095u
-#define BIG_AREA 1024   // sweep-footprint pixels above which a triangle goes to k_owner_big
+#define TILE_W 16
+#define TILE_H 8
+#define TILE_WARPS 4       // tiles per CTA
+#define MAX_BIN_TILES 256  // a triangle overlapping more tiles goes to the wide list
+#define COORD_LIM 8191     // |rounded vertex coordinate| clamp: keeps the int32 edge functions overflow-free
 
 __device__ __forceinline__ int min3(int a, int b, int c) { return min(a, min(b, c)); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return max(a, max(b, c)); }
 
-// Edge::init (rasterization.h:129-153): A*x + B*y + C with separately rounded mul/add.
-__device__ __forceinline__ float edge_at(float A, float B, float C, int x, int y) {
-  return __fadd_rn(__fadd_rn(__fmul_rn(A, (float)x), __fmul_rn(B, (float)y)), C);
+__device__ __forceinline__ int tiles_x(const MeshDev& m) { return (m.cols + TILE_W - 1) / TILE_W; }
+__device__ __forceinline__ int tiles_y(const MeshDev& m) { return (m.rows + TILE_H - 1) / TILE_H; }
+
+__device__ __forceinline__ int round_coord(float v) {
+  return max(-COORD_LIM, min(COORD_LIM, __float2int_rn(v)));  // cv::Point2f -> cv::Point (half to even)
 }
 
-// Coverage + value of triangle `s` at sweep position (x, y); x may exceed cols-1 (4-px overshoot).
-__device__ __forceinline__ bool tri_eval(const TriSetup& s, int x, int y, float* val) {
-  if (y < s.ymin || y > s.ymax || x < s.xmin || x >= s.xend) return false;
-  const float w1 = edge_at(s.A1, s.B1, s.C1, x, y);
-  const float w2 = edge_at(s.A2, s.B2, s.C2, x, y);
-  const float w3 = edge_at(s.A3, s.B3, s.C3, x, y);
-  if (!(w1 >= 0.0f && w2 >= 0.0f && w3 >= 0.0f)) return false;
-  const float norm = __fadd_rn(w1, __fadd_rn(w2, w3));
-  const float num = __fadd_rn(__fmul_rn(s.v1, w1), __fadd_rn(__fmul_rn(s.v2, w2), __fmul_rn(s.v3, w3)));
-  *val = __fdiv_rn(num, norm);
-  return true;
+// Footprint of the pixels triangle s may WRITE, clipped to the image: columns [fx0, fx1], rows [fy0, fy1];
+// empty when fx0 > fx1 or fy0 > fy1. (A wrapping triangle additionally writes the head of the next rows.)
+__device__ __forceinline__ void footprint(const TriStatic& s, const MeshDev& m, int* fx0, int* fx1, int* fy0,
+                                          int* fy1) {
+  *fx0 = max(s.xmin, 0);
+  *fy0 = max(s.ymin, 0);
+  *fx1 = min(s.fx1, m.cols - 1);
+  *fy1 = min(s.ymax, m.rows - 1);
 }
 
-__global__ void __launch_bounds__(256) k_tri_setup(const MeshDev* __restrict__ ms) {
+// Eight lanes per triangle: the record is computed redundantly, the footprint's tiles are spread over the lanes.
+__global__ void __launch_bounds__(256) k_tri_static(const MeshDev* __restrict__ ms) {
   const MeshDev m = ms[blockIdx.y];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t == 0) {  // open a new epoch for this projection (read by the later kernels only)
-    const unsigned e = (unsigned)m.counters[1];
-    m.counters[1] = (int)(e >= EPOCH_MAX ? 1u : e + 1u);
-  }
-  if (t >= m.T) return;
-  TriSetup s;
-  s.flags = 0;
-  s.fx1 = -1;
-  s.pad0 = s.pad1 = 0;
-  if ((m.tri_ok && !m.tri_ok[t]) || (m.tri_filt && !m.tri_filt[t])) {
-    s.ymin = 1; s.ymax = 0; s.xmin = 0; s.xend = 0;  // empty footprint
-    s.A1 = s.B1 = s.C1 = s.A2 = s.B2 = s.C2 = s.A3 = s.B3 = s.C3 = s.v1 = s.v2 = s.v3 = 0.0f;
-    m.setup[t] = s;
-    return;
-  }
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
+  const unsigned group = 0xffu << (threadIdx.x & 24);  // the eight lanes of this triangle
+  if (t >= m.T) return;  // whole groups leave together (T is a per-group bound)
+  TriStatic s;
   const int ia = m.tris[3 * t], ib = m.tris[3 * t + 1], ic = m.tris[3 * t + 2];
   // image_utils.cc:385-391: p1 = vertices[tri[2]], p2 = vertices[tri[1]], p3 = vertices[tri[0]]
-  const int p1x = __float2int_rn(m.pos[2 * ic]), p1y = __float2int_rn(m.pos[2 * ic + 1]);
-  const int p2x = __float2int_rn(m.pos[2 * ib]), p2y = __float2int_rn(m.pos[2 * ib + 1]);
-  const int p3x = __float2int_rn(m.pos[2 * ia]), p3y = __float2int_rn(m.pos[2 * ia + 1]);
-  s.v1 = m.values[ic]; s.v2 = m.values[ib]; s.v3 = m.values[ia];
+  const int p1x = round_coord(m.pos[2 * ic]), p1y = round_coord(m.pos[2 * ic + 1]);
+  const int p2x = round_coord(m.pos[2 * ib]), p2y = round_coord(m.pos[2 * ib + 1]);
+  const int p3x = round_coord(m.pos[2 * ia]), p3y = round_coord(m.pos[2 * ia + 1]);
   s.xmin = min3(p1x, p2x, p3x); s.ymin = min3(p1y, p2y, p3y);
   const int xmax = max3(p1x, p2x, p3x);
   s.ymax = max3(p1y, p2y, p3y);
   s.xend = s.xmin + ((xmax - s.xmin) / 4 + 1) * 4;  // columns visited by the 4-wide sweep
-  // w1 = e23, w2 = e31, w3 = e12 (rasterization.cc:177-179)
-  s.A1 = (float)(p3y - p2y); s.B1 = (float)(p2x - p3x); s.C1 = (float)(p3x * p2y - p2x * p3y);
-  s.A2 = (float)(p1y - p3y); s.B2 = (float)(p3x - p1x); s.C2 = (float)(p1x * p3y - p3x * p1y);
-  s.A3 = (float)(p2y - p1y); s.B3 = (float)(p1x - p2x); s.C3 = (float)(p2x * p1y - p1x * p2y);
+  // w1 = e23, w2 = e31, w3 = e12 (rasterization.cc:177-179; Edge::init rasterization.h:129-153)
+  s.A1 = p3y - p2y; s.B1 = p2x - p3x; s.C1 = p3x * p2y - p2x * p3y;
+  s.A2 = p1y - p3y; s.B2 = p3x - p1x; s.C2 = p1x * p3y - p3x * p1y;
+  s.A3 = p2y - p1y; s.B3 = p1x - p2x; s.C3 = p2x * p1y - p1x * p2y;
   const long long area2 = (long long)(p2x - p1x) * (p3y - p1y) - (long long)(p2y - p1y) * (p3x - p1x);
   const bool degenerate = (area2 == 0);
-  // footprint in pixels: a non-degenerate triangle covers nothing outside [xmin, xmax]; a degenerate
-  // one (edge functions vanish on a line) also covers the sweep's overshoot columns up to xend - 1
-  const int fx0 = max(s.xmin, 0), fy0 = max(s.ymin, 0);
-  const int fx1 = min(degenerate ? s.xend - 1 : xmax, m.cols - 1), fy1 = min(s.ymax, m.rows - 1);
-  const bool wraps = degenerate && (s.xend > m.cols);
-  s.fx1 = fx1;
-  if (degenerate) s.flags |= 4;
-  if (wraps) s.flags |= 2;
-  const long long w = (wraps ? s.xend - 1 : fx1) - fx0 + 1, h = fy1 - fy0 + 1;
-  if (w > 0 && h > 0 && w * h > BIG_AREA) {
-    s.flags |= 8;
-    m.big[atomicAdd(&m.counters[0], 1)] = t;
-  }
-  m.setup[t] = s;
-}
-
-// coverage at sweep position (x, y) -> owner word of the pixel the reference's linear addressing
-// (p.y * cols + p.x) lands on
-__device__ __forceinline__ void claim(const MeshDev& m, int x, int y, unsigned key) {
-  if (x >= m.cols) {  // degenerate triangle whose 4-px sweep ran past the right border
-    x -= m.cols;
-    y += 1;
-    if (y >= m.rows) return;
-  }
-  atomicMax(&m.owner[(size_t)y * m.cols + x], key);
-}
-
-__global__ void __launch_bounds__(256) k_owner_small(const MeshDev* __restrict__ ms) {
-  const MeshDev m = ms[blockIdx.y];
-  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (t >= m.T) return;
-  const int lane = threadIdx.x & 31;
-  const TriSetup s = m.setup[t];
-  if ((s.flags & 8) || s.ymin > s.ymax) return;
-  const unsigned key = ((unsigned)m.counters[1] << OWNER_T_BITS) | (unsigned)t;
-  const int fx0 = max(s.xmin, 0), fy0 = max(s.ymin, 0), fy1 = min(s.ymax, m.rows - 1);
-  if (!(s.flags & 2)) {
-    // 8 x 4 lanes; a lane walks down its column in steps of 4 rows, stepping the (integer-valued, hence
-    // exactly representable) edge functions by 4*B
-    const int fx1 = s.fx1;
-    const int y0 = fy0 + (lane >> 3);
-    const float fy = (float)y0;
-    const float b1 = __fadd_rn(__fmul_rn(s.B1, fy), s.C1), b2 = __fadd_rn(__fmul_rn(s.B2, fy), s.C2),
-                b3 = __fadd_rn(__fmul_rn(s.B3, fy), s.C3);
-    const float s1 = __fmul_rn(s.B1, 4.0f), s2 = __fmul_rn(s.B2, 4.0f), s3 = __fmul_rn(s.B3, 4.0f);
-    const size_t pstep = (size_t)4 * m.cols;
-    for (int x = fx0 + (lane & 7); x <= fx1; x += 8) {
-      const float fx = (float)x;
-      float w1 = __fadd_rn(__fmul_rn(s.A1, fx), b1);
-      float w2 = __fadd_rn(__fmul_rn(s.A2, fx), b2);
-      float w3 = __fadd_rn(__fmul_rn(s.A3, fx), b3);
-      unsigned int* ptr = m.owner + (size_t)y0 * m.cols + x;
-      for (int y = y0; y <= fy1; y += 4) {
-        if (w1 >= 0.0f && w2 >= 0.0f && w3 >= 0.0f) atomicMax(ptr, key);
-        w1 = __fadd_rn(w1, s1);
-        w2 = __fadd_rn(w2, s2);
-        w3 = __fadd_rn(w3, s3);
-        ptr += pstep;
+  // a non-degenerate triangle covers nothing outside [xmin, xmax]; a degenerate one (edge functions vanish
+  // on a line) also covers the sweep's overshoot columns up to xend - 1
+  s.fx1 = degenerate ? s.xend - 1 : xmax;
+  const bool wraps = degenerate && (s.xend > m.cols);  // overshoot columns land on the head of the next row
+  s.flags = (degenerate ? 4 : 0) | (wraps ? 2 : 0);
+  s.pad = 0;
+  int fx0, fx1, fy0, fy1;
+  footprint(s, m, &fx0, &fx1, &fy0, &fy1);
+  if (fy0 > fy1 || (!wraps && fx0 > fx1)) {
+    s.flags |= 1;  // writes nothing
+  } else {
+    const int tx0 = fx0 / TILE_W, tx1 = fx1 / TILE_W, ty0 = fy0 / TILE_H, ty1 = fy1 / TILE_H;
+    const int nx = tx1 - tx0 + 1, n = nx * (ty1 - ty0 + 1);
+    bool wide = wraps || n > MAX_BIN_TILES;
+    if (!wide) {
+      const int ntx = tiles_x(m);
+      for (int i = sub; i < n; i += 8) {
+        const int tile = (ty0 + i / nx) * ntx + tx0 + i % nx;
+        const int at = atomicAdd(&m.tile_cnt[tile], 1);
+        if (at < m.bin_cap) m.bins[(size_t)tile * m.bin_cap + at] = t;
+        else wide = true;  // bin full: the wide list keeps the triangle reachable from every tile
       }
+      wide = __any_sync(group, wide);
     }
-    return;
-  }
-  // degenerate triangle whose sweep overshoot crosses the right border: generic positions + wrap
-  const int fx1 = s.xend - 1;
-  for (int y = fy0 + (lane >> 4); y <= fy1; y += 2) {
-    for (int x = fx0 + (lane & 15); x <= fx1; x += 16) {
-      const float w1 = edge_at(s.A1, s.B1, s.C1, x, y);
-      const float w2 = edge_at(s.A2, s.B2, s.C2, x, y);
-      const float w3 = edge_at(s.A3, s.B3, s.C3, x, y);
-      if (w1 >= 0.0f && w2 >= 0.0f && w3 >= 0.0f) claim(m, x, y, key);
+    if (wide) {
+      s.flags |= 8;
+      if (sub == 0) m.wide[atomicAdd(&m.counters[0], 1)] = t;
     }
   }
+  if (sub == 0) m.stat[t] = s;
 }
 
-// conservative integer bounds of { x : A*x + d >= 0 } (exact test follows); false = empty row
-__device__ __forceinline__ bool clip_span(float A, float d, int* lo, int* hi) {
-  if (A == 0.0f) return d >= 0.0f;
-  const float q = fminf(fmaxf(__fdiv_rn(-d, A), -1.0e6f), 1.0e6f);
-  const int f = (int)floorf(q);
-  if (A > 0.0f) *lo = max(*lo, f - 1);
-  else *hi = min(*hi, f + 1);
-  return true;
+struct StagedTri {  // shared-memory copy of one triangle of the current chunk
+  int A1, B1, C1, A2, B2, C2, A3, B3, C3;
+  int xmin, xend, ymin, ymax, flags, id;
+};
+
+// coverage of sweep position (x, y) by a DEGENERATE triangle: the edge test alone is true on the whole
+// line, the sweep only visits [xmin, xend) x [ymin, ymax] (x may exceed cols - 1: 4-px overshoot)
+template <typename Tri>
+__device__ __forceinline__ bool degenerate_covers(const Tri& s, int x, int y, int* w1, int* w2, int* w3) {
+  if (y < s.ymin || y > s.ymax || x < s.xmin || x >= s.xend) return false;
+  *w1 = s.A1 * x + s.B1 * y + s.C1;
+  *w2 = s.A2 * x + s.B2 * y + s.C2;
+  *w3 = s.A3 * x + s.B3 * y + s.C3;
+  return (*w1 | *w2 | *w3) >= 0;
 }
 
-__global__ void __launch_bounds__(256) k_owner_big(const MeshDev* __restrict__ ms) {
+__global__ void __launch_bounds__(32 * TILE_WARPS, 10) k_tiles(const MeshDev* __restrict__ ms, int fill_nan) {
   const MeshDev m = ms[blockIdx.y];
-  const int n_big = m.counters[0];
-  const unsigned epoch = (unsigned)m.counters[1];
+  const int ntx = tiles_x(m), nty = tiles_y(m);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int b = blockIdx.x; b < n_big; b += gridDim.x) {
-    const int t = m.big[b];
-    const TriSetup s = m.setup[t];
-    const unsigned key = (epoch << OWNER_T_BITS) | (unsigned)t;
-    const int fx0 = max(s.xmin, 0), fy0 = max(s.ymin, 0), fy1 = min(s.ymax, m.rows - 1);
-    const int fx1 = (s.flags & 2) ? s.xend - 1 : s.fx1;
-    for (int y = fy0 + warp; y <= fy1; y += 8) {
-      const float fy = (float)y;
-      int lo = fx0, hi = fx1;
-      if (!clip_span(s.A1, __fadd_rn(__fmul_rn(s.B1, fy), s.C1), &lo, &hi)) continue;
-      if (!clip_span(s.A2, __fadd_rn(__fmul_rn(s.B2, fy), s.C2), &lo, &hi)) continue;
-      if (!clip_span(s.A3, __fadd_rn(__fmul_rn(s.B3, fy), s.C3), &lo, &hi)) continue;
-      for (int x = lo + lane; x <= hi; x += 32) {
-        const float w1 = edge_at(s.A1, s.B1, s.C1, x, y);
-        const float w2 = edge_at(s.A2, s.B2, s.C2, x, y);
-        const float w3 = edge_at(s.A3, s.B3, s.C3, x, y);
-        if (w1 >= 0.0f && w2 >= 0.0f && w3 >= 0.0f) claim(m, x, y, key);
+  const int tile = blockIdx.x * TILE_WARPS + warp;
+  if (tile >= ntx * nty) return;  // warps are independent: no block-wide barrier below
+  const int ty = tile / ntx, tx = tile - ty * ntx;
+  const int px = tx * TILE_W + (lane & 3) * 4, py = ty * TILE_H + (lane >> 2);
+  __shared__ StagedTri s_all[TILE_WARPS][32];
+  StagedTri* s_tri = s_all[warp];
+  int best[4] = {-1, -1, -1, -1};  // per pixel: highest covering triangle so far
+  const int nbin = m.T > 0 ? min(m.tile_cnt[tile], m.bin_cap) : 0;
+  const int nwide = m.T > 0 ? m.counters[0] : 0;
+  const int* bin = m.bins + (size_t)tile * m.bin_cap;
+  const int x_lo = tx * TILE_W, x_hi = x_lo + TILE_W - 1, y_lo = ty * TILE_H, y_hi = y_lo + TILE_H - 1;
+  for (int e0 = 0; e0 < nbin + nwide; e0 += 32) {
+    const int e = e0 + lane;
+    bool use = e < nbin + nwide;
+    int t = 0;
+    TriStatic s;
+    if (use) {
+      t = e < nbin ? bin[e] : m.wide[e - nbin];
+      use = !((m.tri_ok && !m.tri_ok[t]) || (m.tri_filt && !m.tri_filt[t]));
+    }
+    if (use) {
+      s = m.stat[t];
+      if (e >= nbin) {  // wide list: does its footprint touch this tile at all?
+        int fx0, fx1, fy0, fy1;
+        footprint(s, m, &fx0, &fx1, &fy0, &fy1);
+        use = fx0 <= x_hi && fx1 >= x_lo && fy0 <= y_hi && fy1 >= y_lo;
+        if ((s.flags & 2) && !use)  // wrapped tail: columns [0, xend - 1 - cols] of rows fy0 + 1 .. fy1 + 1
+          use = x_lo <= s.xend - 1 - m.cols && fy0 + 1 <= y_hi && fy1 + 1 >= y_lo;
       }
     }
-  }
-}
-
-// Four consecutive (linear) pixels per thread: shade each with its owner triangle.
-__global__ void __launch_bounds__(256) k_resolve(const MeshDev* __restrict__ ms, int fill_nan) {
-  const MeshDev m = ms[blockIdx.y];
-  const unsigned epoch = (unsigned)m.counters[1];
-  const bool wipe = (epoch >= EPOCH_MAX);  // the next projection restarts at epoch 1
-  const int n = m.rows * m.cols;
-  if (blockIdx.x == 0 && threadIdx.x == 0) m.counters[0] = 0;  // re-arm the big list
-  const float qnan = __uint_as_float(0x7fc00000u);  // quiet_NaN, flame.cc:412
-  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += gridDim.x * blockDim.x * 4) {
-    unsigned o[4];
-    const bool full = (i + 4 <= n);
-    if (full) {
-      const uint4 v = *reinterpret_cast<const uint4*>(m.owner + i);
-      o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-      if (wipe) *reinterpret_cast<uint4*>(m.owner + i) = make_uint4(0u, 0u, 0u, 0u);
-    } else {
-      for (int k = 0; k < 4; ++k) {
-        o[k] = (i + k < n) ? m.owner[i + k] : 0u;
-        if (wipe && i + k < n) m.owner[i + k] = 0u;
-      }
+    const unsigned mask = __ballot_sync(0xffffffffu, use);
+    __syncwarp();  // the previous chunk has been consumed
+    if (use) {
+      StagedTri& d = s_tri[__popc(mask & ((1u << lane) - 1u))];
+      d.A1 = s.A1; d.B1 = s.B1; d.C1 = s.C1; d.A2 = s.A2; d.B2 = s.B2; d.C2 = s.C2;
+      d.A3 = s.A3; d.B3 = s.B3; d.C3 = s.C3;
+      d.xmin = s.xmin; d.xend = s.xend; d.ymin = s.ymin; d.ymax = s.ymax; d.flags = s.flags; d.id = t;
     }
-    int py = i / m.cols, px = i - py * m.cols;
-    float out[4];
-    bool have[4];
-    int last_t = -1;
-    TriSetup s;
-    float w1 = 0.0f, w2 = 0.0f, w3 = 0.0f;
-    bool stepping = false;  // w1..w3 hold the edge functions of triangle last_t at (px, py)
+    __syncwarp();
+    const int n = __popc(mask);
+    for (int j = 0; j < n; ++j) {
+      const StagedTri& q = s_tri[j];
+      if (!(q.flags & 4)) {
+        // edge functions at the lane's first pixel; one step to the right adds A (integers: exact)
+        int w1 = q.A1 * px + q.B1 * py + q.C1;
+        int w2 = q.A2 * px + q.B2 * py + q.C2;
+        int w3 = q.A3 * px + q.B3 * py + q.C3;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      have[k] = false;
-      out[k] = qnan;
-      if ((o[k] >> OWNER_T_BITS) == epoch) {
-        const int t = (int)(o[k] & ((1u << OWNER_T_BITS) - 1u));
-        if (t != last_t) {
-          s = m.setup[t];
-          last_t = t;
-          stepping = false;
-        }
-        if (!(s.flags & 2)) {
-          // the owner word says this triangle covers (px, py): shade without re-testing
-          if (!stepping) {
-            w1 = edge_at(s.A1, s.B1, s.C1, px, py);
-            w2 = edge_at(s.A2, s.B2, s.C2, px, py);
-            w3 = edge_at(s.A3, s.B3, s.C3, px, py);
-            stepping = true;
-          }
-          const float norm = __fadd_rn(w1, __fadd_rn(w2, w3));
-          const float num = __fadd_rn(__fmul_rn(s.v1, w1), __fadd_rn(__fmul_rn(s.v2, w2), __fmul_rn(s.v3, w3)));
-          out[k] = __fdiv_rn(num, norm);
-          have[k] = true;
-        } else {
-          float v;
-          // the sweep row itself wins over the wrapped tail of the row above (written later)
-          if (tri_eval(s, px, py, &v) || tri_eval(s, px + m.cols, py - 1, &v)) {
-            have[k] = true;
-            out[k] = v;
-          }
+        for (int k = 0; k < 4; ++k) {
+          best[k] = max(best[k], (w1 | w2 | w3) >= 0 ? q.id : -1);
+          w1 += q.A1; w2 += q.A2; w3 += q.A3;
         }
       } else {
-        stepping = false;
-      }
-      if (stepping) {  // one pixel to the right: exact for integer-valued edge functions
-        w1 = __fadd_rn(w1, s.A1);
-        w2 = __fadd_rn(w2, s.A2);
-        w3 = __fadd_rn(w3, s.A3);
-      }
-      if (++px == m.cols) {
-        px = 0;
-        ++py;
-        stepping = false;
-      }
-    }
-    if (full && (fill_nan || (have[0] && have[1] && have[2] && have[3]))) {
-      *reinterpret_cast<float4*>(m.img + i) = make_float4(out[0], out[1], out[2], out[3]);
-    } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (i + k < n && (have[k] || fill_nan)) m.img[i + k] = out[k];
+        for (int k = 0; k < 4; ++k) {
+          int w1, w2, w3;
+          bool hit = degenerate_covers(q, px + k, py, &w1, &w2, &w3);
+          if (!hit && (q.flags & 2)) hit = degenerate_covers(q, px + k + m.cols, py - 1, &w1, &w2, &w3);
+          if (hit) best[k] = max(best[k], q.id);
+        }
+      }
     }
+  }
+  if (py >= m.rows || px >= m.cols) return;
+  // shade every pixel once with its winner (neighbouring pixels mostly share it: the record stays in L1)
+  const float qnan = __uint_as_float(0x7fc00000u);  // quiet_NaN, flame.cc:412
+  float out[4];
+  bool all = true;
+  int last = -1;
+  TriStatic s;
+  float v1 = 0.f, v2 = 0.f, v3 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    out[k] = qnan;
+    const int t = best[k];
+    if (t < 0) {
+      all = false;
+      continue;
+    }
+    if (t != last) {
+      s = m.stat[t];
+      // values at p1, p2, p3 = reversed triangle order (image_utils.cc:385-391)
+      v1 = m.values[m.tris[3 * t + 2]];
+      v2 = m.values[m.tris[3 * t + 1]];
+      v3 = m.values[m.tris[3 * t]];
+      last = t;
+    }
+    int w1, w2, w3;
+    if (!(s.flags & 4)) {
+      w1 = s.A1 * (px + k) + s.B1 * py + s.C1;
+      w2 = s.A2 * (px + k) + s.B2 * py + s.C2;
+      w3 = s.A3 * (px + k) + s.B3 * py + s.C3;
+    } else if (!degenerate_covers(s, px + k, py, &w1, &w2, &w3)) {
+      // the sweep row itself wins over the wrapped tail of the row above (written earlier by the same sweep)
+      degenerate_covers(s, px + k + m.cols, py - 1, &w1, &w2, &w3);
+    }
+    const float f1 = (float)w1, f2 = (float)w2, f3 = (float)w3;  // exact: |w| < 2^24
+    const float norm = __fadd_rn(f1, __fadd_rn(f2, f3));
+    const float num = __fadd_rn(__fmul_rn(v1, f1), __fadd_rn(__fmul_rn(v2, f2), __fmul_rn(v3, f3)));
+    out[k] = __fdiv_rn(num, norm);
+  }
+  float* dst = m.img + (size_t)py * m.cols + px;
+  if (px + 4 <= m.cols && (m.cols & 3) == 0 && (fill_nan || all)) {
+    *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (px + k < m.cols && (best[k] >= 0 || fill_nan)) dst[k] = out[k];
   }
 }
 
@@ -549,21 +512,31 @@ int raster_coverage(cudaStream_t st, const MeshDev& m, unsigned long long* d_cou
   return 0;
 }
 
-// ms_dev: device array of n MeshDev. Epoch and big-list counter re-arm themselves on the device, so a
-// projection needs no memset and no host round trip.
-int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_pix, int fill_nan) {
-  if (n == 0 || max_pix == 0) return 0;
-  k_tri_setup<<<dim3(std::max(1, (maxT + 255) / 256), n), 256, 0, st>>>(ms_dev);
-  count_launch();
-  if (maxT > 0) {
-    k_owner_small<<<dim3((maxT + 7) / 8, n), 256, 0, st>>>(ms_dev);
-    k_owner_big<<<dim3(32, n), 256, 0, st>>>(ms_dev);
-    count_launch(2);
+// ms_dev: device array of n MeshDev. rebuild != 0: topology or positions of (some of) the meshes changed
+// since their bins were built; the caller has zeroed [counters | tile_cnt] of every mesh of the batch.
+int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_tiles, int fill_nan,
+                   int rebuild) {
+  if (n == 0 || max_tiles == 0) return 0;
+  if (rebuild && maxT > 0) {
+    k_tri_static<<<dim3((maxT + 31) / 32, n), 256, 0, st>>>(ms_dev);
+    count_launch();
   }
-  k_resolve<<<dim3((max_pix / 4 + 255) / 256 + 1, n), 256, 0, st>>>(ms_dev, fill_nan);
+  k_tiles<<<dim3((max_tiles + TILE_WARPS - 1) / TILE_WARPS, n), 32 * TILE_WARPS, 0, st>>>(ms_dev, fill_nan);
   count_launch();
   FB_CUDA(cudaGetLastError());
   return 0;
+}
+
+int raster_tiles(int rows, int cols) { return ((cols + TILE_W - 1) / TILE_W) * ((rows + TILE_H - 1) / TILE_H); }
+
+// Bin capacity for a mesh of T triangles on a rows x cols image: twice the expected number of triangles
+// whose bounding box touches a 16x8 tile (triangles of equal area tiling the image), at least 16.
+int raster_bin_cap(int T, int rows, int cols) {
+  if (T <= 0) return 16;
+  const double a = (double)rows * cols / T, side = std::sqrt(2.0 * a);
+  const double per_tile = (side + TILE_W) * (side + TILE_H) / a;
+  const int cap = (int)(2.0 * per_tile) + 8;
+  return std::min(std::max((cap + 7) / 8 * 8, 16), 1024);
 }
 
 }  // namespace fb
