@@ -316,6 +316,14 @@ def run_ours(args, rank, world, local_rank):
     from flame_b200 import shard
     W, H, V, iters = synth.CONFIGS[CFG]
     p = _lib.default_pd_params()
+    if args.e2e_only:
+        def barrier0():
+            torch.cuda.synchronize(dev)
+        fr, _ = _frames(N_DISTINCT)
+        e = run_e2e(args, local_rank, fr, (W, H, V, iters), barrier0)
+        print(json.dumps({"e2e_frames_per_s": e["frames"] / e["seconds"], "threads": e["threads"],
+                          "in_flight": e["in_flight"], "breakdown": e["breakdown"]}))
+        return
     # ---- how many frames the device solves concurrently (one thread-block cluster per frame) ----
     probe, _ = _frames(1)
     with _lib.Context(local_rank, 1) as c0:
@@ -555,8 +563,9 @@ def run_e2e(args, local_rank, frames, dims, barrier):
                 if search:  # host feature records in and out (5 000 x 40 B each way), synchronous
                     f = si["feats"].copy()
                     ctx.update_feature_idepths(tp, 1, 0, f, want_diag=False)
-                ctx.process_frame_submit(slot, g["pos"], g["data_term"], g["edges"], g["tris"], H, W, p, iters,
-                                         outs[k][slot].array)
+                ctx.process_frame_submit(slot, g["pos"], g["data_term"], g["edges"], g["tris"], H, W, p,
+                                         int(os.environ.get("E2E_ITERS", iters)),
+                                         None if os.environ.get("E2E_NOMAP") else outs[k][slot].array)
                 busy[slot] = True
                 j += 1
         for slot in range(R):
@@ -617,11 +626,12 @@ def main():
                     help="frames per solver launch inside a step (0 = what the device keeps resident: pd_wave)")
     ap.add_argument("--no-async", action="store_true", help="projection in stream order (no second stream)")
     ap.add_argument("--pipelines", type=int, default=3, help="host threads (one context each) of the e2e leg")
-    ap.add_argument("--ring", type=int, default=8, help="frame slots in flight per e2e host thread")
+    ap.add_argument("--ring", type=int, default=30, help="frame slots per e2e host thread (two 15-frame waves)")
     ap.add_argument("--e2e-batch", type=int, default=480, help="frames per GPU per step of the e2e leg")
     ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 stream, 2 resident")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-search", action="store_true", help="skip the epipolar-search side measurement")
+    ap.add_argument("--e2e-only", action="store_true", help="experiments: only the e2e leg (prints its dict)")
     args = ap.parse_args()
     CFG = args.config
     rank = int(os.environ.get("RANK", "0"))

@@ -53,7 +53,10 @@ struct Slot {
   // asynchronous whole-frame pipeline (flame_b200_process_frame_submit / _wait)
   cudaStream_t stream = nullptr;    // the slot's own stream: frames in different slots overlap
   cudaEvent_t done = nullptr;       // recorded after the frame's last device->host copy
+  cudaEvent_t uploaded = nullptr;   // recorded on the slot's stream after the upload + layout kernels
   bool in_flight = false;
+  bool launched = false;            // the frame's wave has been issued
+  float* out_map = nullptr;         // host destination of the dense map of the frame in flight
   int out_V = 0;                    // vertex count of the frame in flight (x | w1 | w2 staged in h_blob)
   size_t out_off = 0;               // where in h_blob
   int capV = 0, capE = 0;
@@ -103,9 +106,18 @@ struct flame_b200_ctx {
   std::vector<Pending> pending;                      // in issue order (the side stream is in-order)
   std::vector<cudaEvent_t> ev_pool;
   // host scratch for graph prep
-  std::vector<uint32_t> keys, keys2;
-  std::vector<int> idx, idx2, degv, srcdeg, order, koff_tmp, pre_deg, pre_src;
+  std::vector<uint32_t> keys;
+  std::vector<int> degv, srcdeg, order, koff_tmp, pre_deg, pre_src;
   int pd_pref = 0;                   // FLAME_B200_PREF_*: how prep_plan sizes the frame clusters
+  // frame pipeline: frames submitted to consecutive slots are solved as one wave (wave_flush)
+  std::vector<int> wave;
+  flame_b200_pd_params wave_params{};
+  int wave_iters = 0;
+  float wave_scale = 1.0f;
+  cudaStream_t down = nullptr;       // device->host copies of finished waves
+  cudaEvent_t ev_wave = nullptr;
+  int cap_cluster = 0, cap_variant = -1, cap_frames = 1;  // cached pd_resident_capacity of the last plan
+  size_t cap_smem = 0;
   // host-side accounting of the frame pipeline (flame_b200_ctx_stats)
   double t_prep = 0, t_stage = 0, t_enqueue = 0, t_wait = 0;
   uint64_t n_frames = 0, h2d_bytes = 0, d2h_bytes = 0;
@@ -161,46 +173,36 @@ static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const in
   int max_deg = 0;
   for (int v = 0; v < V; ++v) max_deg = std::max(max_deg, c->degv[v]);
 
-  // 1. Morton keys on the bounding box, 11 bits per axis; LSD radix sort, 2 x 11 bits, stable
+  // 1. Z-curve order at cell granularity: a 64 x 64 grid over the bounding box, one stable counting sort by
+  //    the Morton code of the cell (vertices of a cell keep their input order)
   float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
   for (int v = 0; v < V; ++v) {
-    xmin = std::min(xmin, pos[2 * v]);
-    xmax = std::max(xmax, pos[2 * v]);
-    ymin = std::min(ymin, pos[2 * v + 1]);
-    ymax = std::max(ymax, pos[2 * v + 1]);
+    const float x = pos[2 * v], y = pos[2 * v + 1];
+    xmin = x < xmin ? x : xmin;
+    xmax = x > xmax ? x : xmax;
+    ymin = y < ymin ? y : ymin;
+    ymax = y > ymax ? y : ymax;
   }
   const float span = std::max(std::max(xmax - xmin, ymax - ymin), 1e-6f);
-  const float sc = 2047.0f / span;
+  const float sc = 63.999f / span;
+  static uint16_t spread[64];  // bits of a 6-bit coordinate moved to the even positions
+  if (!spread[63])
+    for (int i = 63; i >= 0; --i) spread[i] = (uint16_t)part1by1((uint32_t)i);
   c->keys.resize(V);
-  c->keys2.resize(V);
-  c->idx.resize(V);
-  c->idx2.resize(V);
+  int cnt[4097];
+  std::memset(cnt, 0, sizeof(cnt));
   for (int v = 0; v < V; ++v) {
-    float fx = (pos[2 * v] - xmin) * sc, fy = (pos[2 * v + 1] - ymin) * sc;
-    uint32_t qx = (fx >= 0 && fx <= 2047.0f) ? (uint32_t)fx : 0u;  // NaN-safe
-    uint32_t qy = (fy >= 0 && fy <= 2047.0f) ? (uint32_t)fy : 0u;
-    c->keys[v] = part1by1(qx) | (part1by1(qy) << 1);
-    c->idx[v] = v;
+    const float fx = (pos[2 * v] - xmin) * sc, fy = (pos[2 * v + 1] - ymin) * sc;
+    const int qx = (fx >= 0.0f && fx < 64.0f) ? (int)fx : 0;  // NaN-safe
+    const int qy = (fy >= 0.0f && fy < 64.0f) ? (int)fy : 0;
+    const uint32_t key = (uint32_t)spread[qx] | ((uint32_t)spread[qy] << 1);
+    c->keys[v] = key;
+    cnt[key + 1]++;
   }
-  uint32_t* ka = c->keys.data();
-  uint32_t* kb = c->keys2.data();
-  int* ia = c->idx.data();
-  int* ib = c->idx2.data();
-  for (int pass = 0; pass < 2; ++pass) {
-    int cnt[2049] = {0};
-    const int sh = 11 * pass;
-    for (int v = 0; v < V; ++v) cnt[((ka[v] >> sh) & 2047u) + 1]++;
-    for (int b = 0; b < 2048; ++b) cnt[b + 1] += cnt[b];
-    for (int v = 0; v < V; ++v) {
-      const int d = cnt[(ka[v] >> sh) & 2047u]++;
-      kb[d] = ka[v];
-      ib[d] = ia[v];
-    }
-    std::swap(ka, kb);
-    std::swap(ia, ib);
-  }
-  c->order.assign(ia, ia + V);
-  const int* morton = c->order.data();  // morton[i] = caller vertex at Morton position i
+  for (int b = 0; b < 4096; ++b) cnt[b + 1] += cnt[b];
+  c->order.resize(V);
+  for (int v = 0; v < V; ++v) c->order[cnt[c->keys[v]]++] = v;
+  const int* morton = c->order.data();  // morton[i] = caller vertex at Z-curve position i
 
   // 2. plan: per-chunk incidence / owned-edge counts from prefix sums over the Morton order
   c->pre_deg.resize(V + 1);
@@ -520,6 +522,11 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (auto& sl : c->slots)
     if (sl.stream) cudaStreamSynchronize(sl.stream);
+  if (c->down) {
+    cudaStreamSynchronize(c->down);
+    cudaStreamDestroy(c->down);
+  }
+  if (c->ev_wave) cudaEventDestroy(c->ev_wave);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->ev_vals) cudaEventDestroy(c->ev_vals);
   for (auto& pnd : c->pending) cudaEventDestroy(pnd.done);
@@ -535,6 +542,7 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
     if (s.h_blob) cudaFreeHost(s.h_blob);
     if (s.blob_free) cudaEventDestroy(s.blob_free);
     if (s.done) cudaEventDestroy(s.done);
+    if (s.uploaded) cudaEventDestroy(s.uploaded);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   stereo_destroy(c->stereo);
@@ -546,13 +554,17 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
   delete c;
 }
 
+static int wave_flush(flame_b200_ctx* c);  // frame pipeline, below
+
 int flame_b200_ctx_sync(flame_b200_ctx* c) {
   if (!c) return FLAME_B200_EINVAL;
   if (int rc = use_device(c)) return rc;
+  if (int rc = wave_flush(c)) return rc;
   if (int rc = join_side(c)) return rc;
-  FB_CUDA(cudaStreamSynchronize(c->stream));
   for (auto& sl : c->slots)
     if (sl.stream) FB_CUDA(cudaStreamSynchronize(sl.stream));
+  FB_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->down) FB_CUDA(cudaStreamSynchronize(c->down));
   return 0;
 }
 
@@ -1351,6 +1363,55 @@ struct StreamScope {
 };
 }  // namespace
 
+// Launches the solver, the projection and the downloads of the frames collected in c->wave (consecutive
+// slots, same parameters) as ONE batch on the context's main stream: a single solver launch whose clusters
+// fill the device together, one batched projection, and the device->host copies on the context's download
+// stream so that the next wave's kernels overlap them.
+static int wave_flush(flame_b200_ctx* c) {
+  if (c->wave.empty()) return 0;
+  const double t0 = now_s();
+  const int a = c->wave.front(), n = (int)c->wave.size();
+  c->wave.clear();
+  if (!c->down) FB_CUDA(cudaStreamCreateWithFlags(&c->down, cudaStreamNonBlocking));
+  if (!c->ev_wave) FB_CUDA(cudaEventCreateWithFlags(&c->ev_wave, cudaEventDisableTiming));
+  for (int i = a; i < a + n; ++i) FB_CUDA(cudaStreamWaitEvent(c->stream, c->slots[i].uploaded, 0));
+  const bool saved_async = c->async_proj;
+  c->async_proj = false;  // in stream order: the wave's downloads wait for one event on the main stream
+  int rc = flame_b200_pd_run(c, a, n, &c->wave_params, c->wave_iters, FLAME_B200_PD_AUTO);
+  if (!rc) rc = flame_b200_mesh_project(c, a, n, c->wave_scale);
+  c->async_proj = saved_async;
+  if (rc) return rc;
+  for (int i = a; i < a + n; ++i) {
+    Slot& s = c->slots[i];
+    if (s.out_V > 0)  // x | w1 | w2 (caller order) through the raw staging area, scratch between uploads
+      if ((rc = pd_unpack_xw(c->stream, s.g, s.d_raw()))) return rc;
+  }
+  FB_CUDA(cudaEventRecord(c->ev_wave, c->stream));
+  FB_CUDA(cudaStreamWaitEvent(c->down, c->ev_wave, 0));
+  for (int i = a; i < a + n; ++i) {
+    Slot& s = c->slots[i];
+    if (s.out_map) {
+      FB_CUDA(cudaMemcpyAsync(s.out_map, s.m.img, (size_t)s.m.rows * s.m.cols * sizeof(float),
+                              cudaMemcpyDeviceToHost, c->down));
+      c->d2h_bytes += (uint64_t)s.m.rows * s.m.cols * 4;
+    }
+    if (s.out_V > 0) {
+      FB_CUDA(cudaMemcpyAsync(s.h_blob + s.out_off, s.d_raw(), (size_t)3 * s.out_V * 4, cudaMemcpyDeviceToHost,
+                              c->down));
+      c->d2h_bytes += (uint64_t)3 * s.out_V * 4;
+    }
+    FB_CUDA(cudaEventRecord(s.blob_free, c->down));
+    FB_CUDA(cudaEventRecord(s.done, c->down));
+    s.launched = true;
+  }
+  c->t_enqueue += now_s() - t0;
+  return 0;
+}
+
+static bool same_params(const flame_b200_pd_params& a, const flame_b200_pd_params& b) {
+  return std::memcmp(&a, &b, sizeof(a)) == 0;
+}
+
 int flame_b200_process_frame_submit(flame_b200_ctx* c, int slot, int32_t V, const float* pos,
                                     const float* idepth, const float* weight, int32_t E,
                                     const int32_t* edges, int32_t T, const int32_t* tris, int rows, int cols,
@@ -1363,46 +1424,59 @@ int flame_b200_process_frame_submit(flame_b200_ctx* c, int slot, int32_t V, cons
     set_error("process_frame_submit: the slot still has a frame in flight (call flame_b200_process_frame_wait)");
     return FLAME_B200_ESTATE;
   }
-  if (T < 0 || V < 0) {
+  if (T < 0 || V < 0 || !params || n_iters < 0) {
     set_error("process_frame_submit: bad arguments");
     return FLAME_B200_EINVAL;
   }
   if (!s.stream) FB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
   if (!s.done) FB_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  if (!s.uploaded) FB_CUDA(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
+  // a wave is a run of consecutive slots with identical solver parameters
+  if (!c->wave.empty() && (slot != c->wave.back() + 1 || !same_params(*params, c->wave_params) ||
+                           n_iters != c->wave_iters || scale != c->wave_scale))
+    if (int rc = wave_flush(c)) return rc;
   // work issued on the context's main stream for this slot earlier (uploads, projections) comes first
   if (int rc = join_range(c, slot, slot + 1)) return rc;
   FB_CUDA(cudaEventRecord(s.done, c->stream));
   FB_CUDA(cudaStreamWaitEvent(s.stream, s.done, 0));
   const double t0 = now_s();
-  StreamScope scope(c, s.stream);
-  // one pinned staging blob per slot: [graph image | triangles | x, w1, w2 coming back]
-  s.stage_extra = mesh_stage_bytes(T) + (((size_t)3 * V * 4 + 255) & ~(size_t)255);
-  int rc = flame_b200_graph_init(c, slot, V, pos, idepth, weight, E, edges);
-  s.stage_extra = 0;
-  if (rc) return rc;
-  if ((rc = mesh_bind_slot(c, slot, T, tris, nullptr, nullptr, rows, cols, true))) return rc;
-  const double t1 = now_s();
-  if ((rc = flame_b200_pd_run(c, slot, 1, params, n_iters, FLAME_B200_PD_AUTO))) return rc;
-  if ((rc = flame_b200_mesh_project(c, slot, 1, scale))) return rc;
-  if (out_map) {
-    if ((rc = flame_b200_mesh_download(c, slot, out_map))) return rc;
-    c->d2h_bytes += (uint64_t)rows * cols * 4;
+  {
+    // upload + device-side layout on the slot's own stream: overlaps the waves running on the main stream
+    StreamScope scope(c, s.stream);
+    // one pinned staging blob per slot: [graph image | triangles | x, w1, w2 coming back]
+    s.stage_extra = mesh_stage_bytes(T) + (((size_t)3 * V * 4 + 255) & ~(size_t)255);
+    int rc = flame_b200_graph_init(c, slot, V, pos, idepth, weight, E, edges);
+    s.stage_extra = 0;
+    if (rc) return rc;
+    if ((rc = mesh_bind_slot(c, slot, T, tris, nullptr, nullptr, rows, cols, true))) return rc;
+    FB_CUDA(cudaEventRecord(s.uploaded, s.stream));
   }
-  // x | w1 | w2 (caller order) through the raw staging area, which is scratch between uploads
   s.out_V = V;
   s.out_off = s.stage_used + mesh_stage_bytes(T);
-  if (V > 0) {
-    if ((rc = pd_unpack_xw(c->stream, s.g, s.d_raw()))) return rc;
-    FB_CUDA(cudaMemcpyAsync(s.h_blob + s.out_off, s.d_raw(), (size_t)3 * V * 4, cudaMemcpyDeviceToHost, c->stream));
-    FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
-    c->d2h_bytes += (uint64_t)3 * V * 4;
-  }
-  FB_CUDA(cudaEventRecord(s.done, c->stream));
+  s.out_map = out_map;
   s.in_flight = true;
+  s.launched = false;
   c->n_frames++;
   c->h2d_bytes += (uint64_t)V * 16 + (uint64_t)V * 4 + (uint64_t)E * 8 + (uint64_t)T * 12;
-  c->t_enqueue += now_s() - t1;
-  c->t_stage += t1 - t0;  // includes t_prep (accounted separately inside graph_upload_impl)
+  c->t_stage += now_s() - t0;  // includes t_prep (accounted separately inside graph_upload_impl)
+  // how many frames like this one the device solves concurrently = the wave size
+  int cap = 8;
+  if (s.plan.cluster > 0) {
+    if (s.plan.cluster != c->cap_cluster || s.plan.variant != c->cap_variant || s.plan.smem_bytes > c->cap_smem) {
+      int n = 0;
+      if (int rc = pd_resident_capacity(s.plan, &n)) return rc;
+      c->cap_cluster = s.plan.cluster;
+      c->cap_variant = s.plan.variant;
+      c->cap_smem = s.plan.smem_bytes;
+      c->cap_frames = std::max(n, 1);
+    }
+    cap = c->cap_frames;
+  }
+  c->wave.push_back(slot);
+  c->wave_params = *params;
+  c->wave_iters = n_iters;
+  c->wave_scale = scale;
+  if ((int)c->wave.size() >= std::min(cap, std::max(1, c->n_slots / 2))) return wave_flush(c);
   return 0;
 }
 
@@ -1414,6 +1488,8 @@ int flame_b200_process_frame_wait(flame_b200_ctx* c, int slot, float* out_x, flo
     set_error("process_frame_wait: no frame in flight in this slot");
     return FLAME_B200_ESTATE;
   }
+  if (!s.launched)  // its wave is still collecting frames
+    if (int rc = wave_flush(c)) return rc;
   const double t0 = now_s();
   s.in_flight = false;
   FB_CUDA(cudaEventSynchronize(s.done));
