@@ -113,7 +113,7 @@ SYMBOLS = [
     "flame_b200_mesh_project", "flame_b200_mesh_download", "flame_b200_process_frame",
     "flame_b200_process_frame_submit", "flame_b200_process_frame_wait", "flame_b200_ctx_stats",
     "flame_b200_tri_filter_default_params", "flame_b200_mesh_filter", "flame_b200_mesh_coverage",
-    "flame_b200_mesh_normals",
+    "flame_b200_mesh_normals", "flame_b200_mesh_filter_angles",
     "flame_b200_track_default_params",
     "flame_b200_set_camera", "flame_b200_frame_upload", "flame_b200_frame_upload_raw",
     "flame_b200_frame_download", "flame_b200_update_feature_idepths",
@@ -165,6 +165,7 @@ def lib():
     L.flame_b200_mesh_filter.argtypes = [vp, C.c_int, C.POINTER(TriFilterParams), f32p, C.c_float, u8p, C.c_int]
     L.flame_b200_mesh_coverage.argtypes = [vp, C.c_int, C.POINTER(C.c_int64)]
     L.flame_b200_mesh_normals.argtypes = [vp, C.c_int, f32p, C.c_float, f32p]
+    L.flame_b200_mesh_filter_angles.argtypes = [vp, C.c_int, f32p, C.c_float, f32p]
     L.flame_b200_process_frame.argtypes = [vp, C.c_int, C.c_int32, f32p, f32p, f32p, C.c_int32, i32p, C.c_int32,
                                            i32p, C.c_int, C.c_int, C.POINTER(PDParams), C.c_int, C.c_float,
                                            vp, f32p, f32p, f32p]
@@ -403,6 +404,13 @@ class Context:
         Kinv = np.ascontiguousarray(Kinv, np.float32).ravel()
         out = np.empty(T, np.uint8) if want else None
         check(lib().flame_b200_mesh_filter(self._h, slot, C.byref(params), fptr(Kinv), scale, bptr(out), int(apply)))
+        return out
+
+    def mesh_filter_angles(self, slot, T, Kinv, scale=1.0):
+        """Oblique-filter angle of every triangle as computed on the device (diagnostic): f32[T]."""
+        Kinv = np.ascontiguousarray(Kinv, np.float32).ravel()
+        out = np.empty(T, np.float32)
+        check(lib().flame_b200_mesh_filter_angles(self._h, slot, fptr(Kinv), scale, fptr(out)))
         return out
 
     def mesh_normals(self, slot, V, Kinv, scale=1.0):

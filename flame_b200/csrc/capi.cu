@@ -1240,6 +1240,42 @@ int flame_b200_mesh_filter(flame_b200_ctx* c, int slot, const flame_b200_tri_fil
   return 0;
 }
 
+int flame_b200_mesh_filter_angles(flame_b200_ctx* c, int slot, const float Kinv[9], float scale,
+                                  float* angles_out) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (!Kinv || !angles_out) {
+    set_error("mesh_filter_angles: bad arguments");
+    return FLAME_B200_EINVAL;
+  }
+  if (int rc = use_device(c)) return rc;
+  if (int rc = join_range(c, slot, slot + 1)) return rc;
+  Slot& s = c->slots[slot];
+  if (!s.loaded || !s.m.img || s.m.values != s.d_values || s.m.pos != s.d_pos || s.mesh_V != s.g.V) {
+    set_error("mesh_filter_angles: slot has no graph / mesh bound to the current graph");
+    return FLAME_B200_ESTATE;
+  }
+  const int T = s.m.T;
+  if (T == 0) return 0;
+  if ((size_t)T * 5 > raw_f_total(s.g.V, s.g.E) * 4 || (size_t)T * 4 > s.h_blob_cap) {
+    set_error("mesh_filter_angles: more triangles than the slot's scratch holds");
+    return FLAME_B200_EINVAL;
+  }
+  if (int rc = wait_blob(s)) return rc;
+  if (int rc = raster_values_from_graph(c->stream, c->d_graphs + slot, c->d_meshes + slot, 1, s.g.V, scale))
+    return rc;
+  flame_b200_tri_filter_params p;
+  flame_b200_tri_filter_default_params(&p);
+  // the raw staging area is scratch between uploads: [angles T floats | validity T bytes (discarded)]
+  float* d_ang = s.d_raw();
+  if (int rc = raster_tri_filter(c->stream, s.m, p, Kinv, reinterpret_cast<unsigned char*>(d_ang + T), d_ang))
+    return rc;
+  FB_CUDA(cudaMemcpyAsync(s.h_blob, d_ang, (size_t)T * 4, cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
+  FB_CUDA(cudaStreamSynchronize(c->stream));
+  std::memcpy(angles_out, s.h_blob, (size_t)T * 4);
+  return 0;
+}
+
 int flame_b200_mesh_normals(flame_b200_ctx* c, int slot, const float Kinv[9], float scale, float* normals_out) {
   if (int rc = check_slot(c, slot)) return rc;
   if (!Kinv || !normals_out) {

@@ -125,7 +125,7 @@ int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int 
 int raster_tiles(int rows, int cols);  // screen tiles of an image (size of tile_cnt)
 int raster_bin_cap(int T, int rows, int cols);
 int raster_tri_filter(cudaStream_t st, const MeshDev& m, const flame_b200_tri_filter_params& p,
-                      const float Kinv[9], unsigned char* out);
+                      const float Kinv[9], unsigned char* out, float* angle_out = nullptr);
 int raster_coverage(cudaStream_t st, const MeshDev& m, unsigned long long* d_count);
 int raster_vertex_normals(cudaStream_t st, const MeshDev& m, int V, const float Kinv[9], int* scratch,
                           float* d_normals);

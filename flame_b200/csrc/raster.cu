@@ -293,7 +293,8 @@ __device__ __forceinline__ void normalize3(float v[3]) {  // Eigen 3.2: *this /=
   v[0] = __fdiv_rn(v[0], n); v[1] = __fdiv_rn(v[1], n); v[2] = __fdiv_rn(v[2], n);
 }
 
-__global__ void __launch_bounds__(256) k_tri_filter(MeshDev m, TriFilterArgs a, unsigned char* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_tri_filter(MeshDev m, TriFilterArgs a, unsigned char* __restrict__ out,
+                                                    float* __restrict__ angle_out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= m.T) return;
   const int ia = m.tris[3 * t], ib = m.tris[3 * t + 1], ic = m.tris[3 * t + 2];
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(256) k_tri_filter(MeshDev m, TriFilterArgs a, 
     dot = __fadd_rn(dot, __fmul_rn(ray[1], n[1]));
     dot = __fadd_rn(dot, __fmul_rn(ray[2], n[2]));
     const float angle = fabsf(acosf(dot));  // libdevice acosf: within 2 ulp of libm's (see the test)
+    if (angle_out) angle_out[t] = angle;
     if (angle > a.p.oblique_normal_thresh) ok = false;
     float min_id = (id0 < id1) ? id0 : id1;
     min_id = (min_id < id2) ? min_id : id2;
@@ -349,12 +351,12 @@ __global__ void __launch_bounds__(256) k_tri_filter(MeshDev m, TriFilterArgs a, 
 }
 
 int raster_tri_filter(cudaStream_t st, const MeshDev& m, const flame_b200_tri_filter_params& p,
-                      const float Kinv[9], unsigned char* out) {
+                      const float Kinv[9], unsigned char* out, float* angle_out) {
   if (m.T == 0) return 0;
   TriFilterArgs a;
   a.p = p;
   for (int i = 0; i < 9; ++i) a.Kinv[i] = Kinv[i];
-  k_tri_filter<<<(m.T + 255) / 256, 256, 0, st>>>(m, a, out);
+  k_tri_filter<<<(m.T + 255) / 256, 256, 0, st>>>(m, a, out, angle_out);
   count_launch();
   FB_CUDA(cudaGetLastError());
   return 0;

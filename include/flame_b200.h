@@ -260,6 +260,14 @@ void flame_b200_tri_filter_default_params(flame_b200_tri_filter_params* p);
 int flame_b200_mesh_filter(flame_b200_ctx* ctx, int slot, const flame_b200_tri_filter_params* params,
                            const float Kinv[9], float scale, uint8_t* tri_valid_out, int apply);
 
+/* Diagnostic: the angle [rad] between the inward normal and the viewing ray of every triangle, as the
+ * oblique filter of flame_b200_mesh_filter computes it (flame.cc:2255). Everything up to the acosf argument
+ * is bit-identical to the reference's arithmetic; acosf itself is the GPU's (<= 2 ulp from libm's), which is
+ * why a filter decision can differ for a triangle whose angle lies within ~1e-6 rad of the threshold.
+ * angles_out: T floats. Synchronises. */
+int flame_b200_mesh_filter_angles(flame_b200_ctx* ctx, int slot, const float Kinv[9], float scale,
+                                  float* angles_out);
+
 /* Replaces Flame::getVertexNormals (flame.cc:2554-2640, called at flame.cc:385): per vertex the running,
  * re-normalised average of the outward normals of its triangles in triangle order, with
  * vtx_idepths = x * scale of the slot's graph; triangles with a non-positive corner idepth are skipped.

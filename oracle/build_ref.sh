@@ -26,5 +26,13 @@ if [ -f "$HERE/ref_capi/ref_stereo.cc" ]; then
   g++ $CXXFLAGS -c "$HERE/ref_capi/ref_stereo.cc" -o "$OBJ/ref_stereo.o"
   OBJS="$OBJS $OBJ/inverse_depth_filter.o $OBJ/inverse_depth_meas_model.o $OBJ/ref_stereo.o"
 fi
+if [ -f "$HERE/ref_capi/ref_filters.cc" ]; then
+  # display filters + vertex normals: static members sliced verbatim out of flame.cc (which as a whole
+  # cannot be compiled here) into oracle/_ref/gen/
+  mkdir -p "$OUT/gen"
+  python3 "$HERE/ref_capi/slice_flame.py" "$REF" "$OUT/gen/flame_slices.inc"
+  g++ $CXXFLAGS -I"$OUT/gen" -c "$HERE/ref_capi/ref_filters.cc" -o "$OBJ/ref_filters.o"
+  OBJS="$OBJS $OBJ/ref_filters.o"
+fi
 g++ -shared -o "$OUT/libflame_ref.so" $OBJS -lm -lpthread
 echo "built $OUT/libflame_ref.so"

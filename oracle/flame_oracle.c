@@ -261,7 +261,7 @@ void oracle_interpolate_mesh(int32_t T, const int32_t* tris, int32_t V, const fl
 }
 
 /* ====================================================================================
- * Display filters — flame.cc:389-407, 2207-2356 (PARITY UNPINNED restatement, see header)
+ * Display filters — flame.cc:389-407, 2207-2356 (pinned on the verbatim slices of oracle/ref_capi/ref_filters.cc)
  * ==================================================================================== */
 void oracle_tri_filter_default_params(oracle_tri_filter_params* p) { /* params.h:70-85 */
   p->do_oblique_triangle_filter = 1;

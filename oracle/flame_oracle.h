@@ -78,10 +78,12 @@ void oracle_interpolate_mesh(int32_t T, const int32_t* tris, int32_t V, const fl
                              const uint8_t* tri_valid, float* img, int rows, int cols);
 
 /* ---- display filters (flame.cc:389-407) and the coverage statistic (flame.cc:434-443) ----
- * PARITY UNPINNED: Flame::obliqueTriangleFilter / edgeLengthFilter / idepthTriangleFilter are static
- * members inside flame.cc, which cannot be compiled here (OpenCV/Boost/Sophus); this is a restatement
- * with Eigen 3.2's evaluation order (3x3 * 3x1 as ((a0 b0 + a1 b1) + a2 b2), normalize() = v / sqrt(
- * squaredNorm), no zero check) and libm's acosf. */
+ * Flame::obliqueTriangleFilter / edgeLengthFilter / idepthTriangleFilter are static members inside flame.cc,
+ * which as a whole cannot be compiled here (OpenCV/Boost/Sophus). PINNED on the functions themselves:
+ * oracle/ref_capi/slice_flame.py slices them verbatim out of flame.cc, oracle/ref_capi/ref_filters.cc compiles
+ * the slices against oracle/shim, and tests/test_oracle_kat.py asserts this restatement equals them. What
+ * stays restated is Eigen 3.2's arithmetic inside the shim (3x3 * 3x1 as ((a0 b0 + a1 b1) + a2 b2),
+ * normalize() = v / sqrt(squaredNorm), matrix / scalar as a true division), as for the epipolar geometry. */
 typedef struct { /* params.h:70-85 */
   int32_t do_oblique_triangle_filter;
   float oblique_normal_thresh, oblique_idepth_diff_factor, oblique_idepth_diff_abs;
@@ -96,7 +98,7 @@ void oracle_triangle_filters(const oracle_tri_filter_params* p, const float Kinv
                              const int32_t* tris, const float* pos, const float* idepths,
                              uint8_t* validity, float* angle);
 int64_t oracle_coverage(int rows, int cols, const float* img);
-/* Flame::getVertexNormals (flame.cc:2554-2640), same caveat (PARITY UNPINNED). normals: 3V floats. */
+/* Flame::getVertexNormals (flame.cc:2554-2640), pinned the same way. normals: 3V floats. */
 void oracle_vertex_normals(const float Kinv[9], int32_t V, const float* pos, const float* idepths, int32_t T,
                            const int32_t* tris, float* normals);
 

@@ -234,7 +234,7 @@ def tri_filter_default_params():
 
 
 def triangle_filters(params, Kinv, width, tris, pos, idepths):
-    """flame.cc:389-407 (restatement, parity unpinned): returns (validity u8[T], angle f32[T])."""
+    """flame.cc:389-407, C restatement (pinned on ref_triangle_filters): returns (validity u8[T], angle f32[T])."""
     T = tris.shape[0]
     valid = np.empty(T, np.uint8)
     angle = np.empty(T, np.float32)
@@ -244,8 +244,29 @@ def triangle_filters(params, Kinv, width, tris, pos, idepths):
     return valid, angle
 
 
+def ref_triangle_filters(params, Kinv, width, height, tris, pos, idepths):
+    """The reference's obliqueTriangleFilter / edgeLengthFilter / idepthTriangleFilter, sliced verbatim out of
+    flame.cc and combined as at flame.cc:389-407 (oracle/_ref): validity u8[T]."""
+    T = tris.shape[0]
+    valid = np.empty(T, np.uint8)
+    Kinv = np.ascontiguousarray(Kinv, np.float32).ravel()
+    ref().ref_triangle_filters(C.byref(params), _f(Kinv), C.c_int(width), C.c_int(height), C.c_int32(pos.shape[0]),
+                               C.c_int32(T), _i(tris), _f(pos), _f(idepths), _u8(valid))
+    return valid
+
+
+def ref_vertex_normals(Kinv, pos, idepths, tris):
+    """The reference's Flame::getVertexNormals (flame.cc:2554-2640), sliced verbatim (oracle/_ref)."""
+    V = pos.shape[0]
+    out = np.empty((V, 3), np.float32)
+    Kinv = np.ascontiguousarray(Kinv, np.float32).ravel()
+    ref().ref_vertex_normals(_f(Kinv), C.c_int32(V), _f(pos), _f(idepths), C.c_int32(tris.shape[0]), _i(tris),
+                             _f(out))
+    return out
+
+
 def vertex_normals(Kinv, pos, idepths, tris):
-    """Flame::getVertexNormals (flame.cc:2554-2640), restatement (parity unpinned): [V, 3] float32."""
+    """Flame::getVertexNormals (flame.cc:2554-2640), C restatement (pinned on ref_vertex_normals): [V, 3] float32."""
     V = pos.shape[0]
     out = np.empty((V, 3), np.float32)
     Kinv = np.ascontiguousarray(Kinv, np.float32).ravel()

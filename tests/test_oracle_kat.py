@@ -392,8 +392,48 @@ def test_oracle_clip_line_equals_reference_verbatim(oracle):
             assert np.array_equal(np.float32(o[1]).view(np.uint32), np.float32(r[1]).view(np.uint32))
 
 
+@pytest.mark.parametrize("cfg", ["A", "C"])
+def test_oracle_filters_and_normals_equal_reference_verbatim(oracle, cfg):
+    """obliqueTriangleFilter / edgeLengthFilter / idepthTriangleFilter / getVertexNormals sliced verbatim out
+    of the reference's flame.cc (oracle/ref_capi/slice_flame.py) and compiled against oracle/shim vs the C
+    restatement: identical validity vectors and bit-identical normals, on smooth, noisy and partly
+    non-positive idepths, default and non-default thresholds."""
+    _need_ref(oracle)
+    g = synth.config_graph(cfg)
+    W, H = g["W"], g["H"]
+    K, Kinv = synth.camera(W, H)
+    rng = np.random.default_rng(31)
+    V = g["pos"].shape[0]
+    base = synth.scene_idepth(g["pos"][:, 0], g["pos"][:, 1], W, H).astype(np.float32)
+    cases = [base, (base + rng.normal(0, 0.05, V)).astype(np.float32), g["data_term"].copy()]
+    cases[2][::37] = 0.004
+    cases.append(cases[1].copy())
+    cases[3][::29] = 0.0
+    cases[3][5::31] = -0.1
+    n_removed = 0
+    for k, idepths in enumerate(cases):
+        for variant in range(3):
+            p = oracle.tri_filter_default_params()
+            if variant == 1:
+                p.oblique_normal_thresh, p.oblique_idepth_diff_factor, p.edge_length_thresh = 1.1, 0.2, 0.05
+                p.min_triangle_idepth = 0.3
+            if variant == 2:
+                p.do_oblique_triangle_filter = 0
+            if k == 3 and p.do_oblique_triangle_filter:
+                continue  # max_id == 0 -> FLAME_ASSERT-free but 0/0: the reference would divide by zero here too
+            want = oracle.ref_triangle_filters(p, Kinv, W, H, g["tris"], g["pos"], idepths)
+            got, _ = oracle.triangle_filters(p, Kinv, W, g["tris"], g["pos"], idepths)
+            assert np.array_equal(got, want), (cfg, k, variant, int((got != want).sum()))
+            n_removed += int((want == 0).sum())
+        a = oracle.vertex_normals(Kinv, g["pos"], idepths, g["tris"])
+        b = oracle.ref_vertex_normals(Kinv, g["pos"], idepths, g["tris"])
+        an, bn = np.isnan(a), np.isnan(b)
+        assert np.array_equal(an, bn) and np.array_equal(a[~an].view(np.uint32), b[~bn].view(np.uint32)), (cfg, k)
+    assert n_removed > 0
+
+
 def test_display_filter_restatement_sanity(oracle):
-    """flame.cc:2207-2356 (restatement, parity unpinned): hand-checkable cases."""
+    """flame.cc:2207-2356: hand-checkable cases of the restatement."""
     from flame_b200 import synth
     K, Kinv = synth.camera(640, 480)
     pos = np.array([[100, 100], [140, 100], [100, 140], [400, 100], [100, 300]], np.float32)
@@ -422,7 +462,7 @@ def test_display_filter_restatement_sanity(oracle):
 
 
 def test_vertex_normals_restatement_sanity(oracle):
-    """flame.cc:2554-2640 (restatement, parity unpinned): a fronto-parallel mesh has outward normals
+    """flame.cc:2554-2640, restatement: a fronto-parallel mesh has outward normals
     (0, 0, -1); a plane tilted about the vertical axis tilts them in x only."""
     from flame_b200 import synth
     g = synth.config_graph("A")
