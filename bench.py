@@ -34,11 +34,15 @@ _METRICS = {
     "D": "frames/sec at 1080p (10k vertices, 200 PD iters + dense projection)",
     "C": "frames/sec at 720p (5k vertices, epipolar search + 100 PD iters + dense projection)",
     "B": "frames/sec at VGA (2k vertices, 100 PD iters + dense projection)",
+    "E": "frames/sec at 1080p, one frame per GPU (10k vertices, 200 PD iters + dense projection), results gathered "
+         "to rank 0 over NVLink",
 }
 _WORK = {
     "D": "config D: 1920x1080, V=10000, 200 PD iters + dense projection",
     "C": "config C: 1280x720, V=5000, epipolar search + 100 PD iters + dense projection",
     "B": "config B: 640x480, V=2000, 100 PD iters + dense projection",
+    "E": "config E: batched 1920x1080 frames, one per GPU, V=10000, 200 PD iters + dense projection, dense maps + "
+         "vertex idepths gathered to rank 0 with NCCL",
 }
 N_DISTINCT = 30  # distinct synthetic frames; the slots of a batch cycle through them
 
@@ -82,8 +86,9 @@ def _peaks():
 def _frames(n, first=0):
     """n frame descriptions; at most N_DISTINCT distinct ones (generated once), cycled."""
     from flame_b200 import synth
-    W, H, V, iters = synth.CONFIGS[CFG]
-    distinct = [synth.config_graph(CFG, frame=first + f) for f in range(min(n, N_DISTINCT))]
+    cfg = "D" if CFG == "E" else CFG  # config E = config D's frames, one per GPU
+    W, H, V, iters = synth.CONFIGS[cfg]
+    distinct = [synth.config_graph(cfg, frame=first + f) for f in range(min(n, N_DISTINCT))]
     return [distinct[i % len(distinct)] for i in range(n)], (W, H, V, iters)
 
 
@@ -526,6 +531,99 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_config_e(args, rank, world, local_rank):
+    """BASELINE config E: the batched-frame case. Every GPU holds ONE 1080p / 10k-vertex frame in
+    the latency layout (the frame spread over a 16-CTA cluster); a step = fresh-vertex reset -> 200 x step() ->
+    interpolateMesh on every GPU, then the dense maps and vertex idepths are gathered to rank 0 with NCCL over
+    NVLink. `value` = frames/s of the whole job, next to the per-step latency and the gather's bandwidth."""
+    import torch
+    import torch.distributed as dist
+    from flame_b200 import _lib, shard, synth
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    numa = _pin_to_gpu_node(local_rank)
+    W, H, V, iters = synth.CONFIGS["D"]
+    g = synth.config_graph("D", frame=rank)
+    p = _lib.default_pd_params()
+    ctx = _lib.Context(local_rank, 1)
+    ctx.set_pd_preference(_lib.PREF_LATENCY)
+    ctx.graph_init(0, g["pos"], g["data_term"], g["edges"])
+    ctx.mesh_bind(0, g["tris"], H, W)
+    ctx.sync()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    m, v = ctx.device_tensors(0)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step(ev=None):
+        ctx.graph_reset(0, 1)
+        ctx.pd_run(p, iters, 0, 1, 0)
+        ctx.mesh_project(0, 1, 1.0)
+        if ev is not None:
+            ev[0].record(stream)
+        with torch.cuda.stream(stream):
+            out = shard.gather_frames(m, v, dst=0)
+        if ev is not None:
+            ev[1].record(stream)
+        return out
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.kernel_launches()
+    e0.record(stream)
+    for k in range(args.steps):
+        maps, vals = step(evs[k])
+    e1.record(stream)
+    barrier()
+    launches = _lib.kernel_launches() - launches0
+    ms_total = shard.max_over_ranks(e0.elapsed_time(e1), dev)
+    gather_ms = shard.max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in evs])), dev)
+    clocks = sampler.stop()
+    checksum = None
+    if rank == 0:
+        checksum = float(sum(torch.nan_to_num(x).double().sum().item() for x in maps))
+    if rank == 0:
+        E = g["edges"].shape[0]
+        peak, peak_src = _peaks()
+        gathered = (world - 1) * (4.0 * W * H + 4.0 * V)  # bytes arriving at rank 0 per step
+        solve_ms = ms_total / args.steps - gather_ms
+        line = {
+            "metric": _metric(), "value": world * args.steps / (ms_total * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": _config(),
+            "details": {"E": E, "frames_per_step_per_gpu": 1, "layout": "latency (16-CTA cluster per frame)",
+                        "latency_ms_per_batch": ms_total / args.steps, "gather_ms": gather_ms,
+                        "gather_GBps_into_rank0": gathered / (gather_ms * 1e-3) / 1e9 if world > 1 else None,
+                        "gathered_bytes_per_step": gathered, "checksum": checksum, "host": numa,
+                        "parallelism": "one frame per GPU; NCCL gather of the results to rank 0"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_pd_resident", "achieved": 76.0 * (V + E) * iters / (solve_ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": 76.0 * (V + E) * iters / (solve_ms * 1e-3) / 1e9 / peak,
+                         "peak_source": peak_src, "traffic": None,
+                         "note": "single frame per GPU: effective bandwidth of solve + projection (step minus gather)"},
+            "e2e": {"value": world * args.steps / (ms_total * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0,
+                    "note": "config E keeps inputs and outputs on the GPUs (consumer = rank 0's GPU over NVLink)"},
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_e2e(args, local_rank, frames, dims, barrier):
     """Per frame: graph + triangles up (H2D) -> PD -> projection -> dense map + x, w1, w2 down (D2H), through
     flame_b200_process_frame_submit / _wait. `pipelines` host threads, each driving ONE context with a ring of
@@ -619,7 +717,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="D", choices=["B", "C", "D"])
+    ap.add_argument("--config", default="D", choices=["B", "C", "D", "E"])
     ap.add_argument("--batch", type=int, default=0,
                     help="frames per GPU per step (0 = 40 waves of what the device keeps resident)")
     ap.add_argument("--wave", type=int, default=0,
@@ -639,6 +737,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if CFG == "E":
+        run_config_e(args, rank, world, local_rank)
         return
     run_ours(args, rank, world, local_rank)
 

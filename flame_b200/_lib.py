@@ -111,6 +111,7 @@ SYMBOLS = [
     "flame_b200_graph_project", "flame_b200_graph_resync", "flame_b200_pd_run", "flame_b200_pd_wave",
     "flame_b200_pd_cost", "flame_b200_interpolate_mesh", "flame_b200_mesh_bind",
     "flame_b200_mesh_project", "flame_b200_mesh_download", "flame_b200_process_frame",
+    "flame_b200_slot_device_ptrs",
     "flame_b200_process_frame_submit", "flame_b200_process_frame_wait", "flame_b200_ctx_stats",
     "flame_b200_tri_filter_default_params", "flame_b200_mesh_filter", "flame_b200_mesh_coverage",
     "flame_b200_mesh_normals", "flame_b200_mesh_filter_angles",
@@ -160,6 +161,8 @@ def lib():
     L.flame_b200_mesh_bind.argtypes = [vp, C.c_int, C.c_int32, i32p, u8p, u8p, C.c_int, C.c_int]
     L.flame_b200_mesh_project.argtypes = [vp, C.c_int, C.c_int, C.c_float]
     L.flame_b200_mesh_download.argtypes = [vp, C.c_int, vp]
+    L.flame_b200_slot_device_ptrs.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32),
+                                              C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.flame_b200_tri_filter_default_params.argtypes = [C.POINTER(TriFilterParams)]
     L.flame_b200_tri_filter_default_params.restype = None
     L.flame_b200_mesh_filter.argtypes = [vp, C.c_int, C.POINTER(TriFilterParams), f32p, C.c_float, u8p, C.c_int]
@@ -405,6 +408,25 @@ class Context:
         out = np.empty(T, np.uint8) if want else None
         check(lib().flame_b200_mesh_filter(self._h, slot, C.byref(params), fptr(Kinv), scale, bptr(out), int(apply)))
         return out
+
+    def device_tensors(self, slot):
+        """(dense map [rows, cols], vertex idepths [V]) of the slot as torch CUDA tensors that ALIAS the library's
+        device memory (no copy): for NCCL collectives on the results (flame_b200.shard.gather_frames)."""
+        import torch
+        img, val = C.c_void_p(), C.c_void_p()
+        rows, cols, V = C.c_int32(), C.c_int32(), C.c_int32()
+        check(lib().flame_b200_slot_device_ptrs(self._h, slot, C.byref(img), C.byref(val), C.byref(rows),
+                                                C.byref(cols), C.byref(V)))
+
+        class _View:
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False),
+                                                 "version": 3, "strides": None}
+
+        dev = torch.device("cuda", self.device)
+        m = torch.as_tensor(_View(img.value, (rows.value, cols.value)), device=dev)
+        v = torch.as_tensor(_View(val.value, (max(V.value, 1),)), device=dev)[:V.value]
+        return m, v
 
     def mesh_filter_angles(self, slot, T, Kinv, scale=1.0):
         """Oblique-filter angle of every triangle as computed on the device (diagnostic): f32[T]."""

@@ -1192,6 +1192,22 @@ int flame_b200_mesh_download(flame_b200_ctx* c, int slot, float* out_host) {
   return 0;
 }
 
+int flame_b200_slot_device_ptrs(flame_b200_ctx* c, int slot, void** dense_map, void** values, int32_t* rows,
+                                int32_t* cols, int32_t* V) {
+  if (int rc = check_slot(c, slot)) return rc;
+  Slot& s = c->slots[slot];
+  if (!s.loaded || !s.m.img || s.m.values != s.d_values) {
+    set_error("slot_device_ptrs: slot has no graph / bound mesh");
+    return FLAME_B200_ESTATE;
+  }
+  if (dense_map) *dense_map = s.m.img;
+  if (values) *values = s.d_values;
+  if (rows) *rows = s.m.rows;
+  if (cols) *cols = s.m.cols;
+  if (V) *V = s.g.V;
+  return 0;
+}
+
 void flame_b200_tri_filter_default_params(flame_b200_tri_filter_params* p) {
   if (!p) return;
   p->do_oblique_triangle_filter = 1;  // params.h:70-85

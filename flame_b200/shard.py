@@ -47,3 +47,30 @@ def aggregate_throughput(frames_this_rank, elapsed_s_this_rank, device=None):
     total = sum_over_ranks(frames_this_rank, device)
     tmax = max_over_ranks(elapsed_s_this_rank, device)
     return total / tmax
+
+
+def gather_frames(dense_map, values, dst=0):
+    """The batched-frame case (BASELINE config E): every rank holds one frame's dense inverse-depth
+    map and vertex idepths; rank `dst` receives all of them - NCCL gather over NVLink when the tensors are on
+    the GPUs, gloo on CPU tensors. Returns (maps, values) lists of world_size tensors on `dst`, (None, None)
+    elsewhere; single-process: the inputs themselves. The vertex counts may differ per rank: values travel
+    padded to the largest count, preceded by an all_gather of the counts."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [dense_map], [values]
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = torch.tensor([values.numel()], dtype=torch.int64, device=values.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    vmax = max(max(counts), 1)
+    padded = torch.zeros(vmax, dtype=values.dtype, device=values.device)
+    padded[:values.numel()] = values
+    maps = [torch.empty_like(dense_map) for _ in range(world)] if rank == dst else None
+    vals = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(dense_map.contiguous(), maps, dst=dst)
+    dist.gather(padded, vals, dst=dst)
+    if rank != dst:
+        return None, None
+    return maps, [v[:c] for v, c in zip(vals, counts)]

@@ -235,6 +235,15 @@ int flame_b200_mesh_project(flame_b200_ctx* ctx, int slot0, int n_slots, float s
  * complete after flame_b200_ctx_sync(). */
 int flame_b200_mesh_download(flame_b200_ctx* ctx, int slot, float* out_host);
 
+/* Device pointers of a slot's outputs, for consumers that stay on the GPU - the batched-frame case of
+ * one frame per GPU, the dense maps and vertex idepths gathered to one consumer with NCCL over
+ * NVLink (flame_b200/shard.py gather_frames, bench.py --config E) without a trip through host memory.
+ * dense_map: rows x cols f32 of the last flame_b200_mesh_project; values: V f32 = x * scale of that call, in
+ * the caller's vertex order (vtx_idepths_, flame.cc:376). Valid until the slot's next mesh_bind / upload;
+ * reads must be ordered after the producing work (flame_b200_ctx_stream / flame_b200_ctx_join). */
+int flame_b200_slot_device_ptrs(flame_b200_ctx* ctx, int slot, void** dense_map, void** values, int32_t* rows,
+                                int32_t* cols, int32_t* V);
+
 /* ---- display filters and coverage ----------------------------------------
  * Flame::update filters triangles "for display" (flame.cc:389-407) and getFilteredInverseDepthMap
  * (flame.h:217-228) projects the mesh again honouring them. */

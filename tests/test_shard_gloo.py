@@ -47,6 +47,44 @@ def test_two_rank_sharding_and_aggregation():
     assert all(shard.frame_owner(f, 2, 4) == 0 for f in f0) and all(shard.frame_owner(f, 2, 4) == 1 for f in f1)
 
 
+def _gather_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m = torch.full((3, 4), float(rank + 1))
+    m[0, 0] = float("nan")
+    v = torch.arange(5 + 2 * rank, dtype=torch.float32) + 100 * rank  # different vertex counts per rank
+    maps, vals = shard.gather_frames(m, v, dst=0)
+    if rank == 0:
+        q.put((rank, [x.tolist() for x in maps], [x.tolist() for x in vals]))
+    else:
+        q.put((rank, maps, vals))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_of_frames():
+    """Config E's exchange step on CPU (gloo): rank 0 receives every rank's dense map and (ragged) vertex
+    idepths; the other ranks receive nothing."""
+    import math
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, maps, vals), (_, m1, v1) = res
+    assert m1 is None and v1 is None
+    assert len(maps) == 2 and math.isnan(maps[0][0][0]) and maps[0][1] == [1.0] * 4 and maps[1][2] == [2.0] * 4
+    assert vals[0] == [0.0, 1.0, 2.0, 3.0, 4.0] and vals[1] == [100.0 + i for i in range(7)]
+
+
 def test_single_process_is_identity():
     assert shard.max_over_ranks(1.5) == 1.5 and shard.sum_over_ranks(3) == 3.0
     assert shard.frames_for_rank(0, 1, 3) == [0, 1, 2]
