@@ -554,6 +554,9 @@ def run_config_e(args, rank, world, local_rank):
     ctx.sync()
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     m, v = ctx.device_tensors(0)
+    # exchange step: "peer" = the projection kernel stores its tiles directly into rank 0's gather buffer (CUDA IPC
+    # peer memory over NVLink) and a 4-byte all-reduce signals completion; "nccl" = ncclGather of the finished maps
+    pg = shard.PeerGather(ctx, 0, H, W, V, local_rank) if args.exchange == "peer" else None
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -564,11 +567,17 @@ def run_config_e(args, rank, world, local_rank):
     def step(ev=None):
         ctx.graph_reset(0, 1)
         ctx.pd_run(p, iters, 0, 1, 0)
+        if ev is not None and pg is not None:
+            ev[0].record(stream)  # peer mode: the exchange IS the projection
         ctx.mesh_project(0, 1, 1.0)
-        if ev is not None:
+        if ev is not None and pg is None:
             ev[0].record(stream)
         with torch.cuda.stream(stream):
-            out = shard.gather_frames(m, v, dst=0)
+            if pg is not None:
+                pg.arrive()
+                out = pg.results()
+            else:
+                out = shard.gather_frames(m, v, dst=0)
         if ev is not None:
             ev[1].record(stream)
         return out
@@ -604,6 +613,9 @@ def run_config_e(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": _config(),
             "details": {"E": E, "frames_per_step_per_gpu": 1, "layout": "latency (16-CTA cluster per frame)",
+                        "exchange": "projection stores into rank 0's buffer through peer memory (NVLink) + 4-byte "
+                                    "all-reduce; gather_ms = projection + signal" if pg is not None else
+                                    "ncclGather of the dense maps and vertex idepths; gather_ms = the collective",
                         "latency_ms_per_batch": ms_total / args.steps, "gather_ms": gather_ms,
                         "gather_GBps_into_rank0": gathered / (gather_ms * 1e-3) / 1e9 if world > 1 else None,
                         "gathered_bytes_per_step": gathered, "checksum": checksum, "host": numa,
@@ -618,6 +630,8 @@ def run_config_e(args, rank, world, local_rank):
                     "note": "config E keeps inputs and outputs on the GPUs (consumer = rank 0's GPU over NVLink)"},
         }
         print(json.dumps(line))
+    if pg is not None:
+        pg.close()
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -729,6 +743,8 @@ def main():
     ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 stream, 2 resident")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-search", action="store_true", help="skip the epipolar-search side measurement")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="config E: how the results reach rank 0 (peer stores from the projection kernel / ncclGather)")
     ap.add_argument("--e2e-only", action="store_true", help="experiments: only the e2e leg (prints its dict)")
     args = ap.parse_args()
     CFG = args.config

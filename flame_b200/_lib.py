@@ -111,7 +111,8 @@ SYMBOLS = [
     "flame_b200_graph_project", "flame_b200_graph_resync", "flame_b200_pd_run", "flame_b200_pd_wave",
     "flame_b200_pd_cost", "flame_b200_interpolate_mesh", "flame_b200_mesh_bind",
     "flame_b200_mesh_project", "flame_b200_mesh_download", "flame_b200_process_frame",
-    "flame_b200_slot_device_ptrs",
+    "flame_b200_slot_device_ptrs", "flame_b200_mesh_redirect", "flame_b200_device_alloc",
+    "flame_b200_device_free", "flame_b200_ipc_export", "flame_b200_ipc_open", "flame_b200_ipc_close",
     "flame_b200_process_frame_submit", "flame_b200_process_frame_wait", "flame_b200_ctx_stats",
     "flame_b200_tri_filter_default_params", "flame_b200_mesh_filter", "flame_b200_mesh_coverage",
     "flame_b200_mesh_normals", "flame_b200_mesh_filter_angles",
@@ -161,6 +162,12 @@ def lib():
     L.flame_b200_mesh_bind.argtypes = [vp, C.c_int, C.c_int32, i32p, u8p, u8p, C.c_int, C.c_int]
     L.flame_b200_mesh_project.argtypes = [vp, C.c_int, C.c_int, C.c_float]
     L.flame_b200_mesh_download.argtypes = [vp, C.c_int, vp]
+    L.flame_b200_mesh_redirect.argtypes = [vp, C.c_int, vp, vp]
+    L.flame_b200_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp)]
+    L.flame_b200_device_free.argtypes = [vp]
+    L.flame_b200_ipc_export.argtypes = [vp, C.c_char_p]
+    L.flame_b200_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
+    L.flame_b200_ipc_close.argtypes = [vp]
     L.flame_b200_slot_device_ptrs.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32),
                                               C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.flame_b200_tri_filter_default_params.argtypes = [C.POINTER(TriFilterParams)]
@@ -232,6 +239,48 @@ def default_track_params():
 
 def kernel_launches():
     return int(lib().flame_b200_kernel_launches())
+
+
+class DeviceBuffer:
+    """Raw device allocation that can be shared with the other per-GPU processes of the box (CUDA IPC)."""
+
+    def __init__(self, device, nbytes):
+        self.device, self.nbytes, self._opened = device, nbytes, False
+        self._p = C.c_void_p()
+        check(lib().flame_b200_device_alloc(device, nbytes, C.byref(self._p)))
+
+    @property
+    def ptr(self):
+        return self._p.value
+
+    def export(self):
+        h = C.create_string_buffer(64)
+        check(lib().flame_b200_ipc_export(self._p, h))
+        return h.raw
+
+    @classmethod
+    def open(cls, device, handle, nbytes):
+        self = cls.__new__(cls)
+        self.device, self.nbytes, self._opened = device, nbytes, True
+        self._p = C.c_void_p()
+        check(lib().flame_b200_ipc_open(device, handle, C.byref(self._p)))
+        return self
+
+    def tensor(self, shape, offset_bytes=0):
+        """float32 torch view (no copy) of part of the buffer."""
+        import torch
+
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (self.ptr + offset_bytes, False),
+                                      "version": 3, "strides": None}
+        return torch.as_tensor(v, device=torch.device("cuda", self.device))
+
+    def close(self):
+        if self._p:
+            (lib().flame_b200_ipc_close if self._opened else lib().flame_b200_device_free)(self._p)
+            self._p = C.c_void_p()
 
 
 class PinnedArray:
@@ -408,6 +457,11 @@ class Context:
         out = np.empty(T, np.uint8) if want else None
         check(lib().flame_b200_mesh_filter(self._h, slot, C.byref(params), fptr(Kinv), scale, bptr(out), int(apply)))
         return out
+
+    def mesh_redirect(self, slot, map_ptr, values_ptr=None):
+        """Project straight into (possibly peer) device memory; None restores the slot's own buffers."""
+        check(lib().flame_b200_mesh_redirect(self._h, slot, C.c_void_p(map_ptr) if map_ptr else None,
+                                             C.c_void_p(values_ptr) if values_ptr else None))
 
     def device_tensors(self, slot):
         """(dense map [rows, cols], vertex idepths [V]) of the slot as torch CUDA tensors that ALIAS the library's

@@ -70,6 +70,8 @@ struct Slot {
   MeshDev m{};
   int capT = 0;
   size_t cap_pix = 0;
+  float* own_img = nullptr;         // the slot's own dense map while m.img is redirected (flame_b200_mesh_redirect)
+  float* values_dst = nullptr;      // where mesh_project additionally copies the vertex values (peer memory)
   int cap_tiles = 0;                // screen tiles the bin tables are sized for
   size_t cap_bins = 0;              // ints in m.bins
   bool bins_dirty = true;           // topology / positions changed since the tile bins were built
@@ -532,6 +534,7 @@ void flame_b200_ctx_destroy(flame_b200_ctx* c) {
   for (auto& pnd : c->pending) cudaEventDestroy(pnd.done);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   for (auto& s : c->slots) {
+    if (s.own_img) s.m.img = s.own_img;  // never free a redirected (foreign) destination
     for (void* p : {(void*)s.g.vprim, (void*)s.g.vbar, (void*)s.g.vbar2, (void*)s.g.vprev,
                     (void*)s.g.vwt, (void*)s.g.inc_q, (void*)s.g.inc_s, (void*)s.d_blob,
                     (void*)s.d_pos, (void*)s.d_values,
@@ -1033,6 +1036,11 @@ static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* 
     if (int rc = regrow(&s.m.wide, (size_t)n * sizeof(int))) return rc;
     s.capT = n;
   }
+  if (s.own_img) {  // a new bind ends a redirection of the dense map
+    s.m.img = s.own_img;
+    s.own_img = nullptr;
+  }
+  s.values_dst = nullptr;
   const size_t npix = (size_t)rows * cols;
   if (npix > s.cap_pix) {
     s.cap_pix = 0;
@@ -1150,6 +1158,11 @@ int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float sca
   if (int rc = raster_values_from_graph(c->stream, c->d_graphs + slot0, c->d_meshes + slot0, n_slots,
                                         maxV, scale))
     return rc;
+  for (int i = slot0; i < slot0 + n_slots; ++i) {
+    Slot& s = c->slots[i];
+    if (s.values_dst && s.g.V > 0)  // peer copy of vtx_idepths (UVA: the destination may live on another GPU)
+      FB_CUDA(cudaMemcpyAsync(s.values_dst, s.d_values, (size_t)s.g.V * sizeof(float), cudaMemcpyDefault, c->stream));
+  }
   cudaStream_t rs = c->stream;
   if (c->async_proj) {
     FB_CUDA(cudaEventRecord(c->ev_vals, c->stream));
@@ -1190,6 +1203,58 @@ int flame_b200_mesh_download(flame_b200_ctx* c, int slot, float* out_host) {
   FB_CUDA(cudaMemcpyAsync(out_host, s.m.img, (size_t)s.m.rows * s.m.cols * sizeof(float),
                           cudaMemcpyDeviceToHost, c->stream));
   return 0;
+}
+
+// ---- peer memory for the batched-frame case -------------------------------------------------------
+int flame_b200_device_alloc(int device, size_t bytes, void** out) {
+  if (!out) return FLAME_B200_EINVAL;
+  FB_CUDA(cudaSetDevice(device));
+  FB_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+  return 0;
+}
+
+int flame_b200_device_free(void* p) {
+  if (p) FB_CUDA(cudaFree(p));
+  return 0;
+}
+
+int flame_b200_ipc_export(void* dev_ptr, uint8_t handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!dev_ptr || !handle) return FLAME_B200_EINVAL;
+  cudaIpcMemHandle_t h;
+  FB_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+  std::memcpy(handle, &h, 64);
+  return 0;
+}
+
+int flame_b200_ipc_open(int device, const uint8_t handle[64], void** out) {
+  if (!handle || !out) return FLAME_B200_EINVAL;
+  FB_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  FB_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int flame_b200_ipc_close(void* p) {
+  if (p) FB_CUDA(cudaIpcCloseMemHandle(p));
+  return 0;
+}
+
+int flame_b200_mesh_redirect(flame_b200_ctx* c, int slot, void* dense_map_dst, void* values_dst) {
+  if (int rc = check_slot(c, slot)) return rc;
+  if (int rc = use_device(c)) return rc;
+  if (int rc = join_range(c, slot, slot + 1)) return rc;
+  Slot& s = c->slots[slot];
+  if (!s.loaded || !s.m.img || s.m.values != s.d_values) {
+    set_error("mesh_redirect: slot has no graph / bound mesh");
+    return FLAME_B200_ESTATE;
+  }
+  if (!s.own_img) s.own_img = s.m.img;
+  s.m.img = dense_map_dst ? static_cast<float*>(dense_map_dst) : s.own_img;
+  s.values_dst = static_cast<float*>(values_dst);
+  if (!dense_map_dst) s.own_img = nullptr;
+  return publish_mesh(c, slot);
 }
 
 int flame_b200_slot_device_ptrs(flame_b200_ctx* c, int slot, void** dense_map, void** values, int32_t* rows,

@@ -74,3 +74,54 @@ def gather_frames(dense_map, values, dst=0):
     if rank != dst:
         return None, None
     return maps, [v[:c] for v, c in zip(vals, counts)]
+
+
+class PeerGather:
+    """Config E without a data-path collective: rank `dst` owns one device buffer [world][rows*cols] (+ [world][V])
+    and shares it with the other per-GPU processes of the box through CUDA IPC; every rank redirects its slot's
+    projection into its own row (flame_b200_mesh_redirect), so the dense maps land in the consumer's memory
+    through peer stores over NVLink while the projection kernel runs. `arrive()` is the completion signal: a
+    4-byte NCCL all-reduce issued on the producing streams."""
+
+    def __init__(self, ctx, slot, rows, cols, V, device, dst=0):
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.rank = self.dist.get_rank() if self.dist else 0
+        self.dst, self.rows, self.cols, self.V = dst, rows, cols, V
+        self.map_bytes, self.val_bytes = rows * cols * 4, ((V * 4 + 255) // 256) * 256
+        total = self.world * (self.map_bytes + self.val_bytes)
+        handle = [None]
+        if self.rank == dst:
+            self.buf = _lib.DeviceBuffer(device, total)
+            handle = [self.buf.export()]
+        if self.dist:
+            self.dist.broadcast_object_list(handle, src=dst)
+        if self.rank != dst:
+            self.buf = _lib.DeviceBuffer.open(device, handle[0], total)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", device))
+        ctx.mesh_redirect(slot, self.buf.ptr + self.rank * self.map_bytes,
+                          self.buf.ptr + self.world * self.map_bytes + self.rank * self.val_bytes)
+        self.ctx, self.slot = ctx, slot
+
+    def arrive(self):
+        """Stream-ordered on the caller's current torch stream: completes on `dst` after every rank's projection."""
+        if self.dist:
+            self.dist.all_reduce(self.flag)
+
+    def results(self):
+        """On `dst`: ([world] dense maps, [world] vertex idepths) as views of the gather buffer."""
+        if self.rank != self.dst:
+            return None, None
+        maps = [self.buf.tensor((self.rows, self.cols), r * self.map_bytes) for r in range(self.world)]
+        vals = [self.buf.tensor((self.V,), self.world * self.map_bytes + r * self.val_bytes) for r in range(self.world)]
+        return maps, vals
+
+    def close(self):
+        self.ctx.mesh_redirect(self.slot, None, None)
+        self.ctx.sync()
+        if self.dist:
+            self.dist.barrier()
+        self.buf.close()

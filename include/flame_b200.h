@@ -244,6 +244,23 @@ int flame_b200_mesh_download(flame_b200_ctx* ctx, int slot, float* out_host);
 int flame_b200_slot_device_ptrs(flame_b200_ctx* ctx, int slot, void** dense_map, void** values, int32_t* rows,
                                 int32_t* cols, int32_t* V);
 
+/* The projection fused with the exchange step of the batched-frame case: after
+ * flame_b200_mesh_redirect(ctx, slot, map_dst, values_dst) every flame_b200_mesh_project of the slot stores
+ * the dense map DIRECTLY into map_dst (rows x cols f32) and copies the vertex idepths to values_dst (V f32) -
+ * device memory that may belong to ANOTHER GPU of the box (peer stores over NVLink: the consumer's gather
+ * buffer is filled tile by tile while the projection runs; no separate collective moves the 8.3 MB map).
+ * NULL restores the slot's own buffer; a new mesh_bind ends the redirection. While redirected, the slot's own
+ * map (mesh_download, mesh_coverage) is not updated.
+ * flame_b200_ipc_export / _open share a device allocation between the per-GPU processes of one box (CUDA
+ * IPC; peer access is enabled on open); flame_b200_device_alloc gives memory that can be exported. The
+ * consumer orders its reads after the producers' streams (e.g. a tiny NCCL all-reduce on those streams). */
+int flame_b200_mesh_redirect(flame_b200_ctx* ctx, int slot, void* dense_map_dst, void* values_dst);
+int flame_b200_device_alloc(int device, size_t bytes, void** out);
+int flame_b200_device_free(void* p);
+int flame_b200_ipc_export(void* dev_ptr, uint8_t handle[64]);
+int flame_b200_ipc_open(int device, const uint8_t handle[64], void** out);
+int flame_b200_ipc_close(void* p);
+
 /* ---- display filters and coverage ----------------------------------------
  * Flame::update filters triangles "for display" (flame.cc:389-407) and getFilteredInverseDepthMap
  * (flame.h:217-228) projects the mesh again honouring them. */

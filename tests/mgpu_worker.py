@@ -33,10 +33,26 @@ def main():
             maps, vals = shard.gather_frames(m, v, dst=0)
         ctx.sync()
         torch.cuda.synchronize(dev)
+        # second exchange path: the projection stores straight into rank 0's buffer (peer memory, CUDA IPC)
+        V_all = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(V_all, torch.tensor([g["pos"].shape[0]], dtype=torch.int64, device=dev))
+        Vmax = max(int(x.item()) for x in V_all)
+        pg = shard.PeerGather(ctx, 0, H, W, Vmax, local)
+        ctx.mesh_project(0, 1, 1.0)
+        with torch.cuda.stream(stream):
+            pg.arrive()
+        ctx.sync()
+        torch.cuda.synchronize(dev)
+        pmaps, pvals = pg.results()
         ok = True
         if rank == 0:
             from oracle import pyoracle
             for r in range(world):
+                vr = int(V_all[r].item())
+                if not (torch.equal(pmaps[r].view(torch.int32), maps[r].view(torch.int32)) and
+                        torch.equal(pvals[r][:vr].view(torch.int32), vals[r].view(torch.int32))):
+                    print("rank %d: peer-memory exchange DIFFERS from the NCCL gather" % r)
+                    ok = False
                 gr = synth.config_graph(cfg, frame=r)
                 alpha, beta = pyoracle.edge_weights(gr["edges"], gr["pos"])
                 s = synth.init_state(gr, alpha, beta)
@@ -50,6 +66,7 @@ def main():
                 print("rank %d: x %s, dense map %s" % (r, "ok" if same_x else "DIFFERS", "ok" if same_img else "DIFFERS"))
                 ok = ok and same_x and same_img
         dist.barrier()
+        pg.close()
     dist.destroy_process_group()
     if rank == 0:
         print("MGPU_OK" if ok else "MGPU_FAIL")
