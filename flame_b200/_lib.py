@@ -35,6 +35,18 @@ class Stats(C.Structure):
                 ("enqueue_seconds", C.c_double), ("wait_seconds", C.c_double)]
 
 
+class ProjectRules(C.Structure):
+    """flame_b200_project_rules: the flame::Params fields Flame::projectGraph reads."""
+    _fields_ = [("rescale_factor_max", C.c_float), ("win_size", C.c_int32), ("do_letterbox", C.c_int32),
+                ("do_grad_check_after_projection", C.c_int32), ("min_grad_mag", C.c_float)]
+
+
+class DetectParams(C.Structure):
+    """flame_b200_detect_params: the flame::Params fields the grid detector reads."""
+    _fields_ = [("rescale_factor_max", C.c_float), ("win_size", C.c_int32), ("do_letterbox", C.c_int32),
+                ("min_grad_mag", C.c_float), ("detection_win_size", C.c_int32)]
+
+
 class GraphIn(C.Structure):
     _fields_ = [("V", C.c_int32), ("E", C.c_int32), ("pos", f32p), ("edges", i32p),
                 ("data_term", f32p), ("data_weight", f32p),
@@ -108,7 +120,8 @@ SYMBOLS = [
     "flame_b200_host_alloc", "flame_b200_host_free",
     "flame_b200_pd_default_params", "flame_b200_graph_upload", "flame_b200_graph_init",
     "flame_b200_graph_set_data", "flame_b200_graph_reset", "flame_b200_graph_download",
-    "flame_b200_graph_project", "flame_b200_graph_resync", "flame_b200_pd_run", "flame_b200_pd_wave",
+    "flame_b200_graph_project", "flame_b200_graph_project_marked", "flame_b200_detect_features",
+    "flame_b200_graph_resync", "flame_b200_pd_run", "flame_b200_pd_wave",
     "flame_b200_pd_cost", "flame_b200_interpolate_mesh", "flame_b200_mesh_bind",
     "flame_b200_mesh_project", "flame_b200_mesh_download", "flame_b200_process_frame",
     "flame_b200_slot_device_ptrs", "flame_b200_mesh_redirect", "flame_b200_device_alloc",
@@ -154,6 +167,10 @@ def lib():
     L.flame_b200_graph_download.argtypes = [vp, C.c_int, C.POINTER(GraphOut)]
     L.flame_b200_graph_project.argtypes = [vp, C.c_int, f32p, f32p, C.c_float, f32p, f32p]
     L.flame_b200_graph_resync.argtypes = [vp, C.c_int, C.POINTER(GraphSync)]
+    L.flame_b200_graph_project_marked.argtypes = [vp, C.c_int, f32p, f32p, C.c_float, C.POINTER(ProjectRules), C.c_int,
+                                                  f32p, f32p, u8p]
+    L.flame_b200_detect_features.argtypes = [vp, C.POINTER(DetectParams), C.c_int, C.c_int, f32p, C.c_int32, f32p,
+                                             C.c_int32, C.POINTER(C.c_int32)]
     L.flame_b200_pd_run.argtypes = [vp, C.c_int, C.c_int, C.POINTER(PDParams), C.c_int, C.c_int]
     L.flame_b200_pd_wave.argtypes = [vp, C.c_int, C.POINTER(C.c_int32)]
     L.flame_b200_pd_cost.argtypes = [vp, C.c_int, C.POINTER(PDParams), C.c_int, f32p, f32p]
@@ -338,6 +355,23 @@ class Context:
 
     def set_async_projection(self, on=True):
         check(lib().flame_b200_ctx_set_async_projection(self._h, int(on)))
+
+    def graph_project_marked(self, slot, V, q, t, scale, rules, fnew=-1):
+        """graph_project + the removal rules of Flame::projectGraph: (pos [V,2], idepth [V], remove u8[V])."""
+        pos, idepth, rem = np.empty((V, 2), np.float32), np.empty(V, np.float32), np.empty(V, np.uint8)
+        q, t = np.ascontiguousarray(q, np.float32), np.ascontiguousarray(t, np.float32)
+        check(lib().flame_b200_graph_project_marked(self._h, slot, fptr(q), fptr(t), scale, C.byref(rules), fnew,
+                                                    fptr(pos), fptr(idepth), bptr(rem)))
+        return pos, idepth, rem
+
+    def detect_features(self, params, fref, fprev, curr_xy, max_features=20000):
+        """Grid detector of Flame::detectFeatures on frame slot fref: ((n, 2) float32, n)."""
+        curr = np.ascontiguousarray(curr_xy, np.float32).reshape(-1, 2)
+        out = np.empty((max_features, 2), np.float32)
+        n = C.c_int32()
+        check(lib().flame_b200_detect_features(self._h, C.byref(params), fref, fprev, fptr(curr) if len(curr) else None,
+                                               curr.shape[0], fptr(out), max_features, C.byref(n)))
+        return out[:min(n.value, max_features)].copy(), n.value
 
     def set_pd_preference(self, pref):
         """PREF_THROUGHPUT (smallest cluster per frame) or PREF_LATENCY; applies to later uploads."""

@@ -34,7 +34,10 @@ int stereo_features_download(void* state, cudaStream_t st, flame_b200_feature* f
                              flame_b200_track_diag* diag, int32_t* n_updates, int commit);
 void stereo_destroy(void* state);
 int stereo_graph_project(void* state, cudaStream_t st, const GraphDev& g, float* d_pos,
-                         const float q[4], const float t[3], float scale, float* d_out);
+                         const float q[4], const float t[3], float scale, float* d_out,
+                         const flame_b200_project_rules* rules, int fnew, unsigned char* d_marks);
+int stereo_detect(void* state, cudaStream_t st, const flame_b200_detect_params* p, int fref, int fprev,
+                  const float* curr_xy, int n_curr, float* out_xy, int max_out, int32_t* n_out);
 
 // ------------------------------------------------------------------------------------------
 struct Slot {
@@ -779,8 +782,9 @@ int flame_b200_graph_init(flame_b200_ctx* c, int slot, int32_t V, const float* p
   return graph_upload_impl(c, slot, &g, 1);
 }
 
-int flame_b200_graph_project(flame_b200_ctx* c, int slot, const float q_wxyz[4], const float t[3],
-                             float graph_scale, float* pos_out, float* idepth_out) {
+static int graph_project_impl(flame_b200_ctx* c, int slot, const float q_wxyz[4], const float t[3],
+                              float graph_scale, const flame_b200_project_rules* rules, int fnew, float* pos_out,
+                              float* idepth_out, uint8_t* remove_out) {
   if (int rc = check_slot(c, slot)) return rc;
   if (!q_wxyz || !t || !(graph_scale > 0.0f)) {
     set_error("graph_project: bad arguments");
@@ -795,19 +799,46 @@ int flame_b200_graph_project(flame_b200_ctx* c, int slot, const float q_wxyz[4],
   }
   const int V = s.g.V;
   if (int rc = wait_blob(s)) return rc;
-  // the raw staging area (>= 13V floats) is scratch between uploads: [u_new 2V | idepth_new V]
-  if (int rc = stereo_graph_project(c->stereo, c->stream, s.g, s.d_pos, q_wxyz, t, graph_scale,
-                                    s.d_raw())) return rc;
+  // the raw staging area (>= 13V floats) is scratch between uploads: [u_new 2V | idepth_new V | marks V bytes]
+  unsigned char* d_marks = reinterpret_cast<unsigned char*>(s.d_raw() + 3 * (size_t)V);
+  if (int rc = stereo_graph_project(c->stereo, c->stream, s.g, s.d_pos, q_wxyz, t, graph_scale, s.d_raw(), rules,
+                                    fnew, d_marks)) return rc;
   s.stale = true;
   s.bins_dirty = true;
   if (V == 0) return 0;
-  FB_CUDA(cudaMemcpyAsync(s.h_blob, s.d_blob, (size_t)3 * V * 4, cudaMemcpyDeviceToHost, c->stream));
+  const size_t bytes = (size_t)3 * V * 4 + (rules ? (size_t)V : 0);
+  FB_CUDA(cudaMemcpyAsync(s.h_blob, s.d_blob, bytes, cudaMemcpyDeviceToHost, c->stream));
   FB_CUDA(cudaEventRecord(s.blob_free, c->stream));
   FB_CUDA(cudaStreamSynchronize(c->stream));
   const float* hf = reinterpret_cast<const float*>(s.h_blob);
   if (pos_out) std::memcpy(pos_out, hf, (size_t)2 * V * 4);
   if (idepth_out) std::memcpy(idepth_out, hf + 2 * (size_t)V, (size_t)V * 4);
+  if (remove_out && rules) std::memcpy(remove_out, s.h_blob + (size_t)3 * V * 4, (size_t)V);
   return 0;
+}
+
+int flame_b200_graph_project(flame_b200_ctx* c, int slot, const float q_wxyz[4], const float t[3],
+                             float graph_scale, float* pos_out, float* idepth_out) {
+  return graph_project_impl(c, slot, q_wxyz, t, graph_scale, nullptr, -1, pos_out, idepth_out, nullptr);
+}
+
+int flame_b200_graph_project_marked(flame_b200_ctx* c, int slot, const float q_wxyz[4], const float t[3],
+                                    float graph_scale, const flame_b200_project_rules* rules, int fnew,
+                                    float* pos_out, float* idepth_out, uint8_t* remove_out) {
+  if (!rules) {
+    set_error("graph_project_marked: rules missing");
+    return FLAME_B200_EINVAL;
+  }
+  return graph_project_impl(c, slot, q_wxyz, t, graph_scale, rules, fnew, pos_out, idepth_out, remove_out);
+}
+
+int flame_b200_detect_features(flame_b200_ctx* c, const flame_b200_detect_params* params, int fref, int fprev,
+                               const float* curr_xy, int32_t n_curr, float* features_xy, int32_t max_features,
+                               int32_t* n_features) {
+  if (!c || !params || (n_curr > 0 && !curr_xy) || !n_features) return FLAME_B200_EINVAL;
+  if (int rc = use_device(c)) return rc;
+  return stereo_detect(c->stereo, c->stream, params, fref, fprev, curr_xy, n_curr, features_xy, max_features,
+                       n_features);
 }
 
 int flame_b200_graph_resync(flame_b200_ctx* c, int slot, const flame_b200_graph_sync* y) {

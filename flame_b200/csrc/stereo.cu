@@ -29,6 +29,7 @@
 // 5-px-padded gradient images.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
@@ -92,6 +93,9 @@ struct StereoState {
   flame_b200_track_diag* h_diag = nullptr;
   int* h_count = nullptr;
   cudaEvent_t feats_free = nullptr;
+  unsigned char* d_detect = nullptr;  // feature detection scratch + pinned mirror
+  unsigned char* h_detect = nullptr;
+  size_t detect_cap = 0;
 };
 
 struct StereoArgs {
@@ -1355,6 +1359,14 @@ int stereo_update(void* state, cudaStream_t st, const flame_b200_track_params* p
 struct ProjectArgs {
   float K[9], Kinv[9], q[4], t[3];
   float scale;
+  // removal rules of Flame::projectGraph (flame.cc:1872-1917); marks == nullptr: projection only
+  unsigned char* marks;       // [V] caller order: 1 = the reference would put the vertex into vtx_to_remove
+  float rx, ry, rw, rh;       // cv::Rect_<float> valid_region
+  int grad_check;             // params.do_grad_check_after_projection
+  float grad_thresh2;         // params.min_grad_mag^2
+  const float* gx;            // padded gradients of the new frame (nullable unless grad_check)
+  const float* gy;
+  int pitch, pad;
 };
 
 __global__ void __launch_bounds__(128) k_graph_project(GraphDev g, float* __restrict__ pos,
@@ -1374,25 +1386,269 @@ __global__ void __launch_bounds__(128) k_graph_project(GraphDev g, float* __rest
   out[2 * o] = cx;
   out[2 * o + 1] = cy;
   out[2 * (size_t)g.V + o] = idn;
+  if (a.marks) {
+    // cv::Rect_<float>::contains(Point2f): x <= pt.x < x + width, y <= pt.y < y + height (:1901)
+    const bool inside = a.rx <= cx && cx < a.rx + a.rw && a.ry <= cy && cy < a.ry + a.rh;
+    bool remove = !inside || (idn < 0.0f);
+    if (!remove && a.grad_check) {
+      // bilinearInterp<float, float> on the UNPADDED gradient images (:1908-1911): same weights, the taps
+      // shifted by the padding of the device copies
+      const int xf = (int)cx, yf = (int)cy;
+      const float dx = cx - xf, dy = cy - yf;
+      const float w11 = dx * dy, w01 = dx - w11, w10 = dy - w11, w00 = 1.0f - dx - dy + w11;
+      const size_t at = (size_t)(yf + a.pad) * a.pitch + (xf + a.pad);
+      const float gx = w00 * a.gx[at] + w01 * a.gx[at + 1] + w10 * a.gx[at + a.pitch] + w11 * a.gx[at + 1 + a.pitch];
+      const float gy = w00 * a.gy[at] + w01 * a.gy[at + 1] + w10 * a.gy[at + a.pitch] + w11 * a.gy[at + 1 + a.pitch];
+      if (gx * gx + gy * gy < a.grad_thresh2) remove = true;
+    }
+    a.marks[o] = remove ? 1 : 0;
+  }
 }
 
+// rules == nullptr: projection only. d_marks: V bytes of device scratch.
 int stereo_graph_project(void* state, cudaStream_t st, const GraphDev& g, float* d_pos,
-                         const float q[4], const float t[3], float scale, float* d_out) {
+                         const float q[4], const float t[3], float scale, float* d_out,
+                         const flame_b200_project_rules* rules, int fnew, unsigned char* d_marks) {
   StereoState* s = static_cast<StereoState*>(state);
   if (!s || s->width <= 0) {
     set_error("graph_project: camera not set (flame_b200_set_camera)");
     return FLAME_B200_ESTATE;
   }
-  if (g.V == 0) return 0;
   ProjectArgs a;
+  std::memset(&a, 0, sizeof(a));
   std::memcpy(a.K, s->K, sizeof(a.K));
   std::memcpy(a.Kinv, s->Kinv, sizeof(a.Kinv));
   std::memcpy(a.q, q, sizeof(a.q));
   std::memcpy(a.t, t, sizeof(a.t));
   a.scale = scale;
+  if (rules) {
+    if (rules->do_grad_check_after_projection &&
+        (fnew < 0 || fnew >= FB_MAX_FRAMES || !s->h_frames[fnew].valid)) {
+      set_error("graph_project: the gradient check needs the new frame's slot (flame_b200_frame_upload)");
+      return FLAME_B200_EINVAL;
+    }
+    const int row_offset = rules->do_letterbox ? s->height / 3 : 0;
+    const int border = (int)(rules->rescale_factor_max * rules->win_size / 2 + 1);  // :1881
+    a.marks = d_marks;
+    a.rx = (float)border;
+    a.ry = (float)(border + row_offset);
+    a.rw = (float)(s->width - 2 * border);
+    a.rh = (float)(s->height - 2 * border - 2 * row_offset);
+    a.grad_check = rules->do_grad_check_after_projection;
+    a.grad_thresh2 = rules->min_grad_mag * rules->min_grad_mag;
+    if (a.grad_check) {
+      a.gx = s->d_gx[fnew];
+      a.gy = s->d_gy[fnew];
+    }
+    a.pitch = s->pitch;
+    a.pad = s->pad;
+  }
+  if (g.V == 0) return 0;
   k_graph_project<<<(g.V + 127) / 128, 128, 0, st>>>(g, d_pos, a, d_out);
   count_launch();
   FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Flame::detectFeatures (flame.cc:1192-1277): on a grid of win x win cells, the pixel with the largest
+// squared image gradient along the epipolar direction (prev <- ref geometry), among the pixels whose
+// gradient magnitude and epipolar gradient both exceed min_grad_mag; cells that already hold a feature
+// are masked. One CTA per cell; ties go to the LAST pixel in row-major scan order (the reference's `>=`).
+// ------------------------------------------------------------------------------------------
+struct DetectArgs {
+  float K[9], Kinv[9];
+  float pose_ref[7], pose_prev[7];
+  const float* gx;  // padded gradients of the reference frame
+  const float* gy;
+  int width, height, pitch, pad;
+  int border, row_offset, win, wclvl, hclvl;
+  float thresh2;
+  unsigned long long* best;   // [hclvl * wclvl] (epigrad^2 bits << 32) | scan index, 0 = none
+  unsigned char* mask;        // [hclvl * wclvl] 255 = free, 0 = already holds a feature
+  const float* curr;          // [2 n_curr] current features
+  int n_curr;
+  float* out;                 // [2 max_out] detections (x, y)
+  int max_out;
+  int* n_out;
+};
+
+__global__ void k_detect_mask(DetectArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n_curr) return;
+  // uint32_t x_clvl = curr_feats[ii].x / win_size (:1201-1202): float division, truncated
+  const unsigned xc = (unsigned)(a.curr[2 * i] / (float)a.win), yc = (unsigned)(a.curr[2 * i + 1] / (float)a.win);
+  if (xc < (unsigned)a.wclvl && yc < (unsigned)a.hclvl) a.mask[yc * a.wclvl + xc] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_detect_cells(DetectArgs a) {
+  __shared__ float s_t[3];  // t_cmp_to_ref of the prev <- ref geometry: all referenceEpiline needs besides K
+  __shared__ unsigned long long s_best[8];
+  const int cj = blockIdx.x, ci = blockIdx.y;
+  if (threadIdx.x == 0) {
+    float T[7];
+    se3_inv_mul(a.pose_prev, a.pose_ref, T);  // T_ref_to_prev = fprev.pose^-1 * fref.pose (:1207)
+    EpiGeo e;
+    e.init(a.K, a.Kinv);
+    e.load(T, T + 4);
+    s_t[0] = e.t_cmp_to_ref[0];
+    s_t[1] = e.t_cmp_to_ref[1];
+    s_t[2] = e.t_cmp_to_ref[2];
+  }
+  __syncthreads();
+  EpiGeo e;
+  e.init(a.K, a.Kinv);
+  e.t_cmp_to_ref[0] = s_t[0];
+  e.t_cmp_to_ref[1] = s_t[1];
+  e.t_cmp_to_ref[2] = s_t[2];
+  unsigned long long best = 0ull;
+  const int i_lo = max(ci * a.win, a.border + a.row_offset), i_hi = min((ci + 1) * a.win, a.height - a.border - a.row_offset);
+  const int j_lo = max(cj * a.win, a.border), j_hi = min((cj + 1) * a.win, a.width - a.border);
+  const int w = j_hi - j_lo, n = (i_hi > i_lo && w > 0) ? (i_hi - i_lo) * w : 0;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const int ii = i_lo + k / w, jj = j_lo + k % w;
+    // the cell of a pixel is static_cast<float>(ii) / win_size truncated (:1243-1244) = ii / win for these sizes
+    const size_t at = (size_t)(ii + a.pad) * a.pitch + (jj + a.pad);
+    const float gx = a.gx[at], gy = a.gy[at];
+    if (gx * gx + gy * gy < a.thresh2) continue;
+    float ex, ey;
+    e.reference_epiline((float)ii, (float)jj, &ex, &ey);  // sic: cv::Point2f(ii, jj), row first (:1231)
+    const float epigrad = gx * ex + gy * ey;
+    const float epigrad2 = epigrad * epigrad;
+    if (epigrad2 < a.thresh2 || epigrad2 != epigrad2) continue;  // NaN (pixel at the epipole) never wins `>=`
+    const unsigned long long key = ((unsigned long long)__float_as_uint(epigrad2) << 32) | (unsigned)(ii * a.width + jj);
+    best = key > best ? key : best;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long v = __shfl_xor_sync(0xffffffffu, best, o);
+    best = v > best ? v : best;
+  }
+  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) best = s_best[k] > best ? s_best[k] : best;
+    a.best[ci * a.wclvl + cj] = best;
+  }
+}
+
+// one CTA: detections in row-major cell order (:1262-1270)
+__global__ void __launch_bounds__(1024) k_detect_compact(DetectArgs a) {
+  __shared__ int s_warp[32];
+  __shared__ int s_run, s_tot;
+  const int n = a.hclvl * a.wclvl;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_run = 0;
+  __syncthreads();
+  for (int b = 0; b < n; b += 1024) {
+    const int i = b + threadIdx.x;
+    unsigned long long key = 0ull;
+    bool sel = false;
+    if (i < n) {
+      key = a.best[i];
+      // cmask > 0 && best_gradsc > 0 (:1266)
+      sel = a.mask[i] > 0 && __uint_as_float((unsigned)(key >> 32)) > 0.0f;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, sel);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+      const int v = s_warp[lane];
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      s_warp[lane] = inc - v;  // exclusive offset of every warp
+      if (lane == 31) s_tot = inc;
+    }
+    __syncthreads();
+    const int pos = s_run + s_warp[warp] + __popc(m & ((1u << lane) - 1u));
+    if (sel && pos < a.max_out) {
+      const unsigned idx = (unsigned)(key & 0xffffffffu);
+      a.out[2 * pos] = (float)(idx % (unsigned)a.width);      // cv::Point2f(jj, ii)
+      a.out[2 * pos + 1] = (float)(idx / (unsigned)a.width);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_run += s_tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *a.n_out = s_run;
+}
+
+int stereo_detect(void* state, cudaStream_t st, const flame_b200_detect_params* p, int fref, int fprev,
+                  const float* curr_xy, int n_curr, float* out_xy, int max_out, int32_t* n_out) {
+  StereoState* s = static_cast<StereoState*>(state);
+  if (!s || s->width <= 0) {
+    set_error("detect_features: camera / frames not set");
+    return FLAME_B200_ESTATE;
+  }
+  if (fref < 0 || fref >= FB_MAX_FRAMES || fprev < 0 || fprev >= FB_MAX_FRAMES || !s->h_frames[fref].valid ||
+      !s->h_frames[fprev].valid || p->detection_win_size < 1 || max_out < 0 || n_curr < 0) {
+    set_error("detect_features: bad arguments / frame slot not uploaded");
+    return FLAME_B200_EINVAL;
+  }
+  DetectArgs a;
+  std::memset(&a, 0, sizeof(a));
+  std::memcpy(a.K, s->K, sizeof(a.K));
+  std::memcpy(a.Kinv, s->Kinv, sizeof(a.Kinv));
+  std::memcpy(a.pose_ref, s->h_frames[fref].pose, sizeof(a.pose_ref));
+  std::memcpy(a.pose_prev, s->h_frames[fprev].pose, sizeof(a.pose_prev));
+  a.gx = s->d_gx[fref];
+  a.gy = s->d_gy[fref];
+  a.width = s->width;
+  a.height = s->height;
+  a.pitch = s->pitch;
+  a.pad = s->pad;
+  a.row_offset = p->do_letterbox ? s->height / 3 : 0;
+  a.border = (int)(p->rescale_factor_max * p->win_size / 2 + 1);  // :848
+  a.win = p->detection_win_size;
+  a.hclvl = (s->height + a.win - 1) / a.win;  // fast_ceil(height / win)
+  a.wclvl = (s->width + a.win - 1) / a.win;
+  a.thresh2 = p->min_grad_mag * p->min_grad_mag;
+  const size_t cells = (size_t)a.hclvl * a.wclvl;
+  // device scratch: [best cells u64 | n_out int (+pad) | out 2*max_out f32 | curr 2*n_curr f32 | mask cells u8]
+  const size_t need = cells * 8 + 16 + (size_t)max_out * 8 + (size_t)n_curr * 8 + cells;
+  if (need > s->detect_cap) {
+    s->detect_cap = 0;
+    if (s->d_detect) FB_CUDA(cudaFree(s->d_detect));
+    s->d_detect = nullptr;
+    if (s->h_detect) FB_CUDA(cudaFreeHost(s->h_detect));
+    s->h_detect = nullptr;
+    FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->d_detect), need));
+    FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s->h_detect), need));
+    s->detect_cap = need;
+  }
+  unsigned char* d = s->d_detect;
+  a.best = reinterpret_cast<unsigned long long*>(d);
+  a.n_out = reinterpret_cast<int*>(d + cells * 8);
+  a.out = reinterpret_cast<float*>(d + cells * 8 + 16);
+  float* d_curr = a.out + 2 * (size_t)max_out;
+  a.curr = d_curr;
+  a.n_curr = n_curr;
+  a.mask = reinterpret_cast<unsigned char*>(d_curr + 2 * (size_t)n_curr);
+  a.max_out = max_out;
+  FB_CUDA(cudaStreamSynchronize(st));  // the pinned mirror is reused call to call
+  if (n_curr > 0) {
+    std::memcpy(s->h_detect, curr_xy, (size_t)n_curr * 8);
+    FB_CUDA(cudaMemcpyAsync(d_curr, s->h_detect, (size_t)n_curr * 8, cudaMemcpyHostToDevice, st));
+  }
+  FB_CUDA(cudaMemsetAsync(a.mask, 255, cells, st));
+  if (n_curr > 0) {
+    k_detect_mask<<<(n_curr + 255) / 256, 256, 0, st>>>(a);
+    count_launch();
+  }
+  k_detect_cells<<<dim3(a.wclvl, a.hclvl), 256, 0, st>>>(a);
+  k_detect_compact<<<1, 1024, 0, st>>>(a);
+  count_launch(2);
+  FB_CUDA(cudaGetLastError());
+  unsigned char* h = s->h_detect;
+  FB_CUDA(cudaMemcpyAsync(h, a.n_out, 16 + (size_t)max_out * 8, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  const int n = *reinterpret_cast<int*>(h);
+  if (n_out) *n_out = n;
+  if (out_xy && n > 0) std::memcpy(out_xy, h + 16, (size_t)std::min(n, max_out) * 8);
   return 0;
 }
 
@@ -1405,6 +1661,8 @@ void stereo_destroy(void* state) {
     if (s->d_gy[i]) cudaFree(s->d_gy[i]);
   }
   if (s->d_frames) cudaFree(s->d_frames);
+  if (s->d_detect) cudaFree(s->d_detect);
+  if (s->h_detect) cudaFreeHost(s->h_detect);
   if (s->d_raw) cudaFree(s->d_raw);
   if (s->h_stage) cudaFreeHost(s->h_stage);
   if (s->stage_free) cudaEventDestroy(s->stage_free);

@@ -166,6 +166,23 @@ int flame_b200_graph_download(flame_b200_ctx* ctx, int slot, const flame_b200_gr
 int flame_b200_graph_project(flame_b200_ctx* ctx, int slot, const float q_wxyz[4], const float t[3],
                              float graph_scale, float* pos_out, float* idepth_out);
 
+/* The same with the REMOVAL RULES of Flame::projectGraph evaluated on the device (flame.cc:1872-1917):
+ * remove_out[v] = 1 when the reference would put vertex v into vtx_to_remove - projected outside
+ * valid_region (a cv::Rect_<float>: no rounding here, unlike trackFeature's cv::Rect), behind the camera
+ * (idepth_new < 0), or, with do_grad_check_after_projection, onto a pixel of the NEW frame (frame slot
+ * `fnew`, flame_b200_frame_upload) whose bilinearly interpolated gradient magnitude is below min_grad_mag.
+ * The caller still erases those vertices from its feature maps and re-triangulates. Synchronises. */
+typedef struct { /* the fields of flame::Params Flame::projectGraph reads */
+  float rescale_factor_max;               /* params.h:59  (border = rescale_factor_max * win_size / 2 + 1) */
+  int32_t win_size;                       /* fparams.win_size */
+  int32_t do_letterbox;                   /* params.h:49 */
+  int32_t do_grad_check_after_projection; /* params.h:42 */
+  float min_grad_mag;                     /* params.h:39 */
+} flame_b200_project_rules;
+int flame_b200_graph_project_marked(flame_b200_ctx* ctx, int slot, const float q_wxyz[4], const float t[3],
+                                    float graph_scale, const flame_b200_project_rules* rules, int fnew,
+                                    float* pos_out, float* idepth_out, uint8_t* remove_out);
+
 typedef struct {
   int32_t V, E;
   const float* pos;          /* 2V  new positions (feat.xy, flame.cc:2005 / :2041)                   */
@@ -439,6 +456,23 @@ int flame_b200_update_feature_idepths(flame_b200_ctx* ctx, const flame_b200_trac
                                       int fnew, int curr_pf, flame_b200_feature* feats,
                                       int32_t n_feats, flame_b200_track_diag* diag,
                                       int32_t* n_updates);
+
+/* SURVEY §8(f) rank 3 - replaces the grid detector of Flame::detectFeatures (flame.cc:1192-1277): on a grid
+ * of detection_win_size^2 cells, the pixel of the reference frame (frame slot fref) with the largest squared
+ * gradient along the epipolar direction of the (previous frame fprev <- reference) geometry, among pixels
+ * whose gradient magnitude and epipolar gradient both exceed min_grad_mag, in cells that hold none of the
+ * n_curr current features. features_xy receives up to max_features (x, y) pairs in row-major cell order
+ * (the order of the reference's push_back), *n_features their total number. Synchronises. */
+typedef struct {
+  float rescale_factor_max;   /* params.h:59 */
+  int32_t win_size;           /* fparams.win_size */
+  int32_t do_letterbox;       /* params.h:49 */
+  float min_grad_mag;         /* params.h:39 */
+  int32_t detection_win_size; /* params.h:48 */
+} flame_b200_detect_params;
+int flame_b200_detect_features(flame_b200_ctx* ctx, const flame_b200_detect_params* params, int fref, int fprev,
+                               const float* curr_xy, int32_t n_curr, float* features_xy, int32_t max_features,
+                               int32_t* n_features);
 
 /* The same with the feature set RESIDENT on the device (features stay in HBM from frame to frame, as the
  * graph does with flame_b200_graph_resync):

@@ -30,9 +30,13 @@ if [ -f "$HERE/ref_capi/ref_filters.cc" ]; then
   # display filters + vertex normals: static members sliced verbatim out of flame.cc (which as a whole
   # cannot be compiled here) into oracle/_ref/gen/
   mkdir -p "$OUT/gen"
-  python3 "$HERE/ref_capi/slice_flame.py" "$REF" "$OUT/gen/flame_slices.inc"
-  g++ $CXXFLAGS -I"$OUT/gen" -c "$HERE/ref_capi/ref_filters.cc" -o "$OBJ/ref_filters.o"
-  OBJS="$OBJS $OBJ/ref_filters.o"
+  python3 "$HERE/ref_capi/slice_flame.py" "$REF" "$OUT/gen"
+  for f in ref_filters ref_project ref_detect; do
+    if [ -f "$HERE/ref_capi/$f.cc" ]; then
+      g++ $CXXFLAGS -I"$OUT/gen" -c "$HERE/ref_capi/$f.cc" -o "$OBJ/$f.o"
+      OBJS="$OBJS $OBJ/$f.o"
+    fi
+  done
 fi
 g++ -shared -o "$OUT/libflame_ref.so" $OBJS -lm -lpthread
 echo "built $OUT/libflame_ref.so"

@@ -1316,3 +1316,103 @@ int oracle_update_feature_idepths(const oracle_track_params* P, const float K[9]
   }
   return num_total_updates;
 }
+
+
+/* ====================================================================================
+ * Flame::projectGraph — flame.cc:1862-1937 (vertex loop and removal marks)
+ * ==================================================================================== */
+void oracle_project_graph(const float K[9], const float Kinv[9], const float q_wxyz[4], const float t[3],
+                          int width, int height, const oracle_project_rules* rules, float graph_scale, int32_t V,
+                          float* pos, float* x, const float* gradx, const float* grady, float* idepth_out,
+                          uint8_t* remove) {
+  oracle_epigeo g;
+  oracle_epigeo_init(&g, K, Kinv);
+  oracle_epigeo_load(&g, q_wxyz, t);
+  int row_offset = 0;
+  if (rules->do_letterbox) row_offset = height / 3;                                  /* :1875-1878 */
+  const int border = (int)(rules->rescale_factor_max * rules->win_size / 2 + 1);     /* :1881 */
+  /* cv::Rect_<float> valid_region(border, border + row_offset, width - 2*border, height - 2*border - 2*row_offset) */
+  const float rx = (float)border, ry = (float)(border + row_offset);
+  const float rw = (float)(width - 2 * border), rh = (float)(height - 2 * border - 2 * row_offset);
+  for (int32_t v = 0; v < V; ++v) {
+    float ux, uy, idepth_new;
+    oracle_epigeo_project_idepth(&g, pos[2 * v], pos[2 * v + 1], x[v] * graph_scale, &ux, &uy, &idepth_new);
+    pos[2 * v] = ux;
+    pos[2 * v + 1] = uy;
+    x[v] = idepth_new / graph_scale;
+    if (idepth_out) idepth_out[v] = idepth_new;
+    const int inside = rx <= ux && ux < rx + rw && ry <= uy && uy < ry + rh;
+    int rem = !inside || (idepth_new < 0.0f);                                        /* :1901 */
+    if (!rem && rules->do_grad_check_after_projection) {                             /* :1907-1916 */
+      const float gx = oracle_bilinear_f32(height, width, width * 4, gradx, ux, uy);
+      const float gy = oracle_bilinear_f32(height, width, width * 4, grady, ux, uy);
+      if (gx * gx + gy * gy < rules->min_grad_mag * rules->min_grad_mag) rem = 1;
+    }
+    remove[v] = (uint8_t)rem;
+  }
+}
+
+/* ====================================================================================
+ * Flame::detectFeatures, single-pass grid detector — flame.cc:1192-1277
+ * ==================================================================================== */
+int32_t oracle_detect_features(const float K[9], const float Kinv[9], const float pose_ref[7],
+                               const float pose_prev[7], int width, int height, const oracle_detect_params* p,
+                               const float* gradx, const float* grady, const float* curr_xy, int32_t n_curr,
+                               float* out_xy, int32_t max_out) {
+  int row_offset = 0;
+  if (p->do_letterbox) row_offset = height / 3;                                      /* :840-844 */
+  const int border = (int)(p->rescale_factor_max * p->win_size / 2 + 1);             /* :848 */
+  const int win_size = p->detection_win_size;
+  float fh = (float)height / win_size, fw = (float)width / win_size;                 /* fast_ceil, :1195-1196 */
+  int hclvl = (int)fh, wclvl = (int)fw;
+  if (hclvl < fh) ++hclvl;
+  if (wclvl < fw) ++wclvl;
+  const size_t cells = (size_t)hclvl * wclvl;
+  uint8_t* cmask = (uint8_t*)malloc(cells ? cells : 1);
+  memset(cmask, 255, cells);
+  for (int32_t i = 0; i < n_curr; ++i) {                                             /* :1199-1204 */
+    const uint32_t x_clvl = (uint32_t)(curr_xy[2 * i] / win_size);
+    const uint32_t y_clvl = (uint32_t)(curr_xy[2 * i + 1] / win_size);
+    if (x_clvl < (uint32_t)wclvl && y_clvl < (uint32_t)hclvl) cmask[(size_t)y_clvl * wclvl + x_clvl] = 0;
+  }
+  float T[7];
+  oracle_se3_inv_mul(pose_prev, pose_ref, T);                                        /* :1207 */
+  oracle_epigeo g;
+  oracle_epigeo_init(&g, K, Kinv);
+  oracle_epigeo_load(&g, T, T + 4);
+  float* best = (float*)calloc(cells ? cells : 1, sizeof(float));
+  float* best_px = (float*)calloc(2 * (cells ? cells : 1), sizeof(float));
+  const float grad_thresh2 = p->min_grad_mag * p->min_grad_mag;
+  for (uint32_t ii = (uint32_t)(border + row_offset); ii < (uint32_t)(height - border - row_offset); ++ii) {
+    for (uint32_t jj = (uint32_t)border; jj < (uint32_t)(width - border); ++jj) {
+      const float gx = gradx[(size_t)ii * width + jj], gy = grady[(size_t)ii * width + jj];
+      const float gmag2 = gx * gx + gy * gy;
+      if (gmag2 < grad_thresh2) continue;
+      float ex, ey;
+      oracle_epigeo_reference_epiline(&g, (float)ii, (float)jj, &ex, &ey);           /* sic: Point2f(ii, jj), :1231 */
+      const float epigrad = gx * ex + gy * ey;
+      const float epigrad2 = epigrad * epigrad;
+      if (epigrad2 < grad_thresh2) continue;
+      const int ii_clvl = (int)((float)ii / win_size), jj_clvl = (int)((float)jj / win_size);
+      const size_t idx = (size_t)ii_clvl * wclvl + jj_clvl;
+      if (epigrad2 >= best[idx]) {
+        best[idx] = epigrad2;
+        best_px[2 * idx] = (float)jj;
+        best_px[2 * idx + 1] = (float)ii;
+      }
+    }
+  }
+  int32_t n = 0;
+  for (size_t idx = 0; idx < cells; ++idx)                                           /* :1262-1270 */
+    if (cmask[idx] > 0 && best[idx] > 0) {
+      if (n < max_out) {
+        out_xy[2 * n] = best_px[2 * idx];
+        out_xy[2 * n + 1] = best_px[2 * idx + 1];
+      }
+      ++n;
+    }
+  free(cmask);
+  free(best);
+  free(best_px);
+  return n;
+}

@@ -260,6 +260,36 @@ int oracle_update_feature_idepths(const oracle_track_params* p, const float K[9]
                                   const oracle_frame* frames, int n_frames, int fnew, int curr_pf,
                                   oracle_feature* feats, int n_feats, oracle_track_diag* diag);
 
+/* ---- Flame::projectGraph (flame.cc:1862-1937): per-vertex projection + removal marks ----
+ * pos (2V) and x (V) are updated in place as the reference does (vtx.pos = u_new, vtx.x = idepth_new /
+ * graph_scale); idepth_out[V] (nullable) = idepth_new; remove[V] = 1 where the vertex lands in vtx_to_remove.
+ * gradx / grady: the new frame's UNPADDED level-0 gradients (rows x cols), only read with the gradient check.
+ * Pinned on the function itself sliced out of flame.cc (oracle/ref_capi/ref_project.cc). */
+typedef struct {
+  float rescale_factor_max;
+  int32_t win_size, do_letterbox, do_grad_check_after_projection;
+  float min_grad_mag;
+} oracle_project_rules;
+void oracle_project_graph(const float K[9], const float Kinv[9], const float q_wxyz[4], const float t[3],
+                          int width, int height, const oracle_project_rules* rules, float graph_scale, int32_t V,
+                          float* pos, float* x, const float* gradx, const float* grady, float* idepth_out,
+                          uint8_t* remove);
+
+/* ---- Flame::detectFeatures, the single-pass grid detector (flame.cc:1192-1277) ----
+ * gradx / grady: the reference frame's UNPADDED gradients; pose_ref / pose_prev: camera-to-world (qw qx qy qz
+ * tx ty tz). out_xy: up to max_out (x, y) pairs in row-major cell order; returns the number of detections.
+ * Pinned on the function itself sliced out of flame.cc (oracle/ref_capi/ref_detect.cc). */
+typedef struct {
+  float rescale_factor_max;
+  int32_t win_size, do_letterbox;
+  float min_grad_mag;
+  int32_t detection_win_size;
+} oracle_detect_params;
+int32_t oracle_detect_features(const float K[9], const float Kinv[9], const float pose_ref[7],
+                               const float pose_prev[7], int width, int height, const oracle_detect_params* p,
+                               const float* gradx, const float* grady, const float* curr_xy, int32_t n_curr,
+                               float* out_xy, int32_t max_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -275,6 +275,80 @@ def vertex_normals(Kinv, pos, idepths, tris):
     return out
 
 
+class ProjectRules(C.Structure):
+    _fields_ = [("rescale_factor_max", C.c_float), ("win_size", C.c_int32), ("do_letterbox", C.c_int32),
+                ("do_grad_check_after_projection", C.c_int32), ("min_grad_mag", C.c_float)]
+
+
+class DetectParams(C.Structure):
+    _fields_ = [("rescale_factor_max", C.c_float), ("win_size", C.c_int32), ("do_letterbox", C.c_int32),
+                ("min_grad_mag", C.c_float), ("detection_win_size", C.c_int32)]
+
+
+def project_rules(grad_check=False, letterbox=False, min_grad_mag=5.0):
+    return ProjectRules(1.4, 5, int(letterbox), int(grad_check), min_grad_mag)   # params.h defaults
+
+
+def detect_params(win=16, letterbox=False, min_grad_mag=5.0):
+    return DetectParams(1.4, 5, int(letterbox), min_grad_mag, win)
+
+
+def _project_graph(fn, K, Kinv, q, t, W, H, rules, scale, pos, x, gradx, grady, with_idepth):
+    V = pos.shape[0]
+    pos2, x2 = np.ascontiguousarray(pos, np.float32).copy(), np.ascontiguousarray(x, np.float32).copy()
+    remove = np.zeros(V, np.uint8)
+    K = np.ascontiguousarray(K, np.float32).ravel()
+    Kinv = np.ascontiguousarray(Kinv, np.float32).ravel()
+    q, t = np.ascontiguousarray(q, np.float32), np.ascontiguousarray(t, np.float32)
+    gx = np.ascontiguousarray(gradx, np.float32) if gradx is not None else np.zeros((H, W), np.float32)
+    gy = np.ascontiguousarray(grady, np.float32) if grady is not None else np.zeros((H, W), np.float32)
+    args = [_f(K), _f(Kinv), _f(q), _f(t), C.c_int(W), C.c_int(H), C.byref(rules), C.c_float(scale), C.c_int32(V),
+            _f(pos2), _f(x2), _f(gx), _f(gy)]
+    idepth = np.zeros(V, np.float32)
+    if with_idepth:
+        args.append(_f(idepth))
+    args.append(_u8(remove))
+    fn(*args)
+    return pos2, x2, idepth, remove
+
+
+def project_graph(K, Kinv, q, t, W, H, rules, scale, pos, x, gradx=None, grady=None):
+    """Flame::projectGraph's vertex loop + removal marks, C restatement: (pos', x', idepth_new, remove)."""
+    return _project_graph(lib().oracle_project_graph, K, Kinv, q, t, W, H, rules, scale, pos, x, gradx, grady, True)
+
+
+def ref_project_graph(K, Kinv, q, t, W, H, rules, scale, pos, x, gradx=None, grady=None):
+    """The reference's Flame::projectGraph sliced verbatim (oracle/_ref); pos'/x' only for surviving vertices."""
+    p, xx, _, rem = _project_graph(ref().ref_project_graph, K, Kinv, q, t, W, H, rules, scale, pos, x, gradx, grady,
+                                   False)
+    return p, xx, rem
+
+
+def _detect(fn, K, Kinv, pose_ref, pose_prev, W, H, params, gradx, grady, curr_xy, max_out):
+    K = np.ascontiguousarray(K, np.float32).ravel()
+    Kinv = np.ascontiguousarray(Kinv, np.float32).ravel()
+    curr = np.ascontiguousarray(curr_xy, np.float32).reshape(-1, 2)
+    out = np.zeros((max_out, 2), np.float32)
+    fn.restype = C.c_int32
+    n = fn(_f(K), _f(Kinv), _f(np.ascontiguousarray(pose_ref, np.float32)),
+           _f(np.ascontiguousarray(pose_prev, np.float32)), C.c_int(W), C.c_int(H), C.byref(params),
+           _f(np.ascontiguousarray(gradx, np.float32)), _f(np.ascontiguousarray(grady, np.float32)),
+           _f(curr), C.c_int32(curr.shape[0]), _f(out), C.c_int32(max_out))
+    return out[:min(n, max_out)].copy(), n
+
+
+def detect_features(K, Kinv, pose_ref, pose_prev, W, H, params, gradx, grady, curr_xy, max_out=20000):
+    """Flame::detectFeatures' grid detector (flame.cc:1192-1277), C restatement: ((n, 2) features, n)."""
+    return _detect(lib().oracle_detect_features, K, Kinv, pose_ref, pose_prev, W, H, params, gradx, grady, curr_xy,
+                   max_out)
+
+
+def ref_detect_features(K, Kinv, pose_ref, pose_prev, W, H, params, gradx, grady, curr_xy, max_out=20000):
+    """The reference's Flame::detectFeatures sliced verbatim (oracle/_ref)."""
+    return _detect(ref().ref_detect_features, K, Kinv, pose_ref, pose_prev, W, H, params, gradx, grady, curr_xy,
+                   max_out)
+
+
 def coverage(img):
     lib().oracle_coverage.restype = C.c_int64
     img = np.ascontiguousarray(img, np.float32)

@@ -31,7 +31,7 @@ class Flame {  // the static members of flame::Flame (flame.h:405-475) that the 
                                std::vector<Vector3f>* normals, utils::StatsTracker* stats);
 };
 
-#include "flame_slices.inc"
+#include "flame_slices_filters.inc"
 
 }  // namespace flame
 

@@ -204,6 +204,7 @@ struct Mat_ : public Mat {
   Mat_() : Mat() { type_ = DataType<T>::type; }
   Mat_(int r, int c) : Mat(r, c, DataType<T>::type) {}
   Mat_(int r, int c, T* ext) : Mat(r, c, DataType<T>::type, ext) {}
+  Mat_(int r, int c, const T& v) : Mat(r, c, DataType<T>::type) { *this = v; }  // filled (cv::Mat_(rows, cols, value))
   Mat_(const Mat& m) : Mat(m) {}
   void create(int r, int c) { Mat::create(r, c, DataType<T>::type); }
   void create(Size sz) { Mat::create(sz.height, sz.width, DataType<T>::type); }
@@ -221,6 +222,18 @@ typedef Mat_<uint8_t> Mat1b;
 typedef Mat_<float> Mat1f;
 typedef Mat_<double> Mat1d;
 typedef Mat_<Vec3b> Mat3b;
+
+// cv::KeyPoint (core/types.hpp): what Flame::detectFeatures collects before KeyPoint::convert
+struct KeyPoint {
+  Point2f pt;
+  float size;
+  KeyPoint() : pt(), size(0) {}
+  KeyPoint(Point2f p, float s) : pt(p), size(s) {}
+  static void convert(const std::vector<KeyPoint>& kps, std::vector<Point2f>& pts) {
+    pts.resize(kps.size());
+    for (size_t i = 0; i < kps.size(); ++i) pts[i] = kps[i].pt;
+  }
+};
 
 // Stub (only the legacy scan-line rasterisers, which Flame never calls, use it). Declared so
 // rasterization.cc compiles; NOT a faithful cv::LineIterator.

@@ -181,3 +181,35 @@ def test_graph_resync_grow_shrink_and_errors(gpu_ctx, oracle):
                          np.full(small["edges"].shape[0], -1, np.int32))
     gpu_ctx.pd_run(p, 12, slot0=4)
     _assert_state(gpu_ctx.graph_download(4, 300, small["edges"].shape[0]), old)
+
+
+@pytest.mark.parametrize("grad_check,letterbox", [(False, False), (True, False), (True, True)])
+def test_graph_project_marked_matches_project_graph(gpu_ctx, oracle, grad_check, letterbox):
+    """flame_b200_graph_project_marked vs the oracle's Flame::projectGraph (pinned on the verbatim slice):
+    projected positions / idepths bit-exact and the same removal marks - outside valid_region (float rectangle),
+    behind the camera, and the gradient check on the new frame's (device-resident, padded) gradients."""
+    W, H, V, _ = synth.CONFIGS["A"]
+    K, Kinv, frames = synth.make_stereo_pair(W, H, t_world=(0.10, 0.02, 0.05), yaw_deg=1.5)
+    g = synth.config_graph("A")
+    pad = synth.PAD
+    gx = np.ascontiguousarray(frames[1]["gradx_pad"][pad:-pad, pad:-pad])
+    gy = np.ascontiguousarray(frames[1]["grady_pad"][pad:-pad, pad:-pad])
+    s = _warm_state(oracle, g, 10)
+    s["x"][::31] = 0.0
+    s["x"][5::47] = 1.9
+    q = synth.quat_from_yaw(2.0).astype(np.float32)
+    gpu_ctx.set_camera(W, H, K, Kinv)
+    for i, fr in enumerate(frames):
+        gpu_ctx.frame_upload(i, fr["img_pad"], fr["gradx_pad"], fr["grady_pad"], pad, fr["pose"])
+    n_removed = 0
+    for scale, t in ((1.0, np.array([0.3, -0.05, 0.1], np.float32)), (0.7, np.array([0.05, 0.0, -0.9], np.float32))):
+        rules_o = oracle.project_rules(grad_check, letterbox, 6.0)
+        rules_g = _lib.ProjectRules(1.4, 5, int(letterbox), int(grad_check), 6.0)
+        gpu_ctx.graph_upload(0, s)
+        pos_g, id_g, rem_g = gpu_ctx.graph_project_marked(0, V, q, t, scale, rules_g, fnew=1)
+        pos_w, x_w, id_w, rem_w = oracle.project_graph(K, Kinv, q, t, W, H, rules_o, scale, s["pos"], s["x"], gx, gy)
+        assert _bits_equal(pos_g, pos_w) and _bits_equal(id_g, id_w)
+        assert np.array_equal(rem_g, rem_w)
+        n_removed += int(rem_w.sum())
+        assert _bits_equal(gpu_ctx.graph_download(0, V, g["edges"].shape[0])["x"], x_w)
+    assert 0 < n_removed < 2 * V

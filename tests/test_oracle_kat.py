@@ -528,3 +528,61 @@ def test_oracle_pd_equals_reference_on_random_graphs(oracle):
         for k in oracle.GRAPH_STATE:
             assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), (case, k)
         assert oracle.pd_costs(a, p) == oracle.ref_pd_costs(b, p), case
+
+
+def _sync_scene(cfg="A", t_world=(0.10, 0.02, 0.05), yaw=1.5):
+    W, H, V, _ = synth.CONFIGS[cfg]
+    K, Kinv, frames = synth.make_stereo_pair(W, H, t_world=t_world, yaw_deg=yaw)
+    g = synth.config_graph(cfg)
+    pad = synth.PAD
+    gx = np.ascontiguousarray(frames[1]["gradx_pad"][pad:-pad, pad:-pad])
+    gy = np.ascontiguousarray(frames[1]["grady_pad"][pad:-pad, pad:-pad])
+    return W, H, K, Kinv, frames, g, gx, gy
+
+
+@pytest.mark.parametrize("grad_check,letterbox", [(False, False), (True, False), (True, True)])
+def test_oracle_project_graph_equals_reference_verbatim(oracle, grad_check, letterbox):
+    """Flame::projectGraph sliced verbatim out of flame.cc (Boost graph of V vertices, utils::Frame gradients)
+    vs the restatement: same removal set, bit-identical projected state of the surviving vertices."""
+    _need_ref(oracle)
+    W, H, K, Kinv, frames, g, gx, gy = _sync_scene()
+    rng = np.random.default_rng(3)
+    x = synth.scene_idepth(g["pos"][:, 0], g["pos"][:, 1], W, H).astype(np.float32)
+    x[::31] = 0.0          # idepth 0 -> max-depth projection (a negative idepth trips the reference's FLAME_ASSERT)
+    x[5::47] = 1.9         # close points: behind the camera after the backward motion below
+    q = synth.quat_from_yaw(2.0).astype(np.float32)
+    for scale, t in ((1.0, np.array([0.3, -0.05, 0.1], np.float32)),     # pushes vertices out of the valid region
+                     (0.7, np.array([0.05, 0.0, -0.9], np.float32))):    # and some behind the camera (idepth_new < 0)
+        rules = oracle.project_rules(grad_check, letterbox, 6.0)
+        pos1, x1, id1, rem1 = oracle.project_graph(K, Kinv, q, t, W, H, rules, scale, g["pos"], x, gx, gy)
+        pos2, x2, rem2 = oracle.ref_project_graph(K, Kinv, q, t, W, H, rules, scale, g["pos"], x, gx, gy)
+        assert np.array_equal(rem1, rem2)
+        keep = rem1 == 0
+        assert 0 < keep.sum() < len(keep)
+        assert np.array_equal(pos1[keep].view(np.uint32), pos2[keep].view(np.uint32))
+        assert np.array_equal(x1[keep].view(np.uint32), x2[keep].view(np.uint32))
+        if scale != 1.0:
+            assert (id1 < 0).any()
+        if grad_check:  # the gradient rule removes vertices the geometric rules keep
+            _, _, _, rem0 = oracle.project_graph(K, Kinv, q, t, W, H, oracle.project_rules(False, letterbox), scale,
+                                                 g["pos"], x, gx, gy)
+            assert rem1.sum() > rem0.sum()
+
+
+@pytest.mark.parametrize("win,letterbox", [(16, False), (8, False), (16, True), (20, False)])
+def test_oracle_detect_features_equals_reference_verbatim(oracle, win, letterbox):
+    """Flame::detectFeatures sliced verbatim vs the restatement: the same detections in the same order."""
+    _need_ref(oracle)
+    W, H, K, Kinv, frames, g, _, _ = _sync_scene()
+    pad = synth.PAD
+    gx = np.ascontiguousarray(frames[0]["gradx_pad"][pad:-pad, pad:-pad])
+    gy = np.ascontiguousarray(frames[0]["grady_pad"][pad:-pad, pad:-pad])
+    curr = g["pos"][:150]
+    p = oracle.detect_params(win, letterbox, 5.0)
+    a, na = oracle.detect_features(K, Kinv, frames[0]["pose"], frames[1]["pose"], W, H, p, gx, gy, curr)
+    b, nb = oracle.ref_detect_features(K, Kinv, frames[0]["pose"], frames[1]["pose"], W, H, p, gx, gy, curr)
+    assert na == nb and na > 50
+    assert np.array_equal(a, b)
+    # masked cells hold no detection
+    cells = set((int(x / win), int(y / win)) for x, y in curr)
+    assert not any((int(x / win), int(y / win)) in cells for x, y in a)

@@ -168,3 +168,30 @@ def test_frame_prep_on_device(gpu_ctx, oracle):
         ip, gx, gy = small.frame_download(20, 23, 37, 3)
         wp, wx, wy = oracle.frame_prep(img, 3)
         assert np.array_equal(ip, wp) and np.array_equal(gx, wx) and np.array_equal(gy, wy)
+
+
+@pytest.mark.parametrize("cfg,win,letterbox", [("A", 16, False), ("A", 8, True), ("C", 16, False), ("A", 20, False)])
+def test_detect_features_matches_oracle(gpu_ctx, oracle, cfg, win, letterbox):
+    """flame_b200_detect_features vs the oracle's grid detector (pinned on Flame::detectFeatures sliced verbatim):
+    identical detections in identical (row-major cell) order, masked cells honoured, truncation reported."""
+    W, H, V, _ = synth.CONFIGS[cfg]
+    K, Kinv, frames = synth.make_stereo_pair(W, H)
+    pad = synth.PAD
+    gx = np.ascontiguousarray(frames[0]["gradx_pad"][pad:-pad, pad:-pad])
+    gy = np.ascontiguousarray(frames[0]["grady_pad"][pad:-pad, pad:-pad])
+    curr = synth.config_graph(cfg)["pos"][:200]
+    gpu_ctx.set_camera(W, H, K, Kinv)
+    for i, fr in enumerate(frames):
+        gpu_ctx.frame_upload(i, fr["img_pad"], fr["gradx_pad"], fr["grady_pad"], pad, fr["pose"])
+    gp = _lib.DetectParams(1.4, 5, int(letterbox), 5.0, win)
+    want, n_want = oracle.detect_features(K, Kinv, frames[0]["pose"], frames[1]["pose"], W, H,
+                                          oracle.detect_params(win, letterbox, 5.0), gx, gy, curr)
+    got, n_got = gpu_ctx.detect_features(gp, 0, 1, curr)
+    assert n_got == n_want and n_want > 100
+    assert np.array_equal(got, want)
+    few, n_few = gpu_ctx.detect_features(gp, 0, 1, curr, max_features=7)   # truncated output, full count
+    assert n_few == n_want and np.array_equal(few, want[:7])
+    none, n_none = gpu_ctx.detect_features(gp, 0, 1, np.zeros((0, 2), np.float32))  # nothing masked
+    w2, n2 = oracle.detect_features(K, Kinv, frames[0]["pose"], frames[1]["pose"], W, H,
+                                    oracle.detect_params(win, letterbox, 5.0), gx, gy, np.zeros((0, 2), np.float32))
+    assert n_none == n2 >= n_want and np.array_equal(none, w2)
