@@ -465,6 +465,12 @@ def run_ours(args, rank, world, local_rank):
     ctx.close()
     e2e = run_e2e(args, local_rank, frames, (W, H, V, iters), barrier)
     e2e_value = shard.aggregate_throughput(e2e["frames"], e2e["seconds"], dev)
+    e2e_tri = None
+    if not args.no_tri:
+        # the same pipeline with the Delaunay triangulation of every frame done by the host threads
+        # (flame_b200_delaunay) - the reference pays Triangle per frame too (utils/delaunay.cc:31-77)
+        e2e_tri = run_e2e(args, local_rank, frames, (W, H, V, iters), barrier, triangulate=True)
+        e2e_tri["value"] = shard.aggregate_throughput(e2e_tri["frames"], e2e_tri["seconds"], dev)
 
     if rank == 0:
         E = int(np.mean([g["edges"].shape[0] for g in frames[:N_DISTINCT]]))
@@ -521,6 +527,12 @@ def run_ours(args, rank, world, local_rank):
                     "host_threads": e2e["threads"], "frames_in_flight": e2e["in_flight"],
                     "host_breakdown": e2e["breakdown"]},
         }
+        if e2e_tri is not None:
+            line["e2e_incl_triangulation"] = {
+                "value": e2e_tri["value"], "unit": "frames/s", "host_threads": e2e_tri["threads"],
+                "delaunay_ms_per_frame": 1e-3 * e2e_tri["breakdown"]["per_frame_us"]["delaunay"],
+                "note": "every frame's Delaunay triangulation (10k vertices) computed by the submitting host thread "
+                        "with flame_b200_delaunay while earlier frames run on the GPU; host-core bound"}
         if search is not None:
             line["search"] = search
         if world == 1 and not args.no_cpu:
@@ -638,7 +650,7 @@ def run_config_e(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def run_e2e(args, local_rank, frames, dims, barrier):
+def run_e2e(args, local_rank, frames, dims, barrier, triangulate=False):
     """Per frame: graph + triangles up (H2D) -> PD -> projection -> dense map + x, w1, w2 down (D2H), through
     flame_b200_process_frame_submit / _wait. `pipelines` host threads, each driving ONE context with a ring of
     `ring` slots: while the device works on the frames in flight, the thread prepares and submits the next."""
@@ -646,12 +658,15 @@ def run_e2e(args, local_rank, frames, dims, barrier):
     from flame_b200 import _lib
     W, H, V, iters = dims
     P, R = args.pipelines, args.ring
+    if triangulate:  # the host also triangulates every frame (flame_b200_delaunay): many threads, short rings
+        P, R = args.tri_threads, 6
     p = _lib.default_pd_params()
     ctxs = [_lib.Context(local_rank, R) for _ in range(P)]
     outs = [[_lib.PinnedArray((H, W)) for _ in range(R)] for _ in range(P)]
     vout = [tuple(np.empty(V, np.float32) for _ in range(3)) for _ in range(P)]
-    per_step = args.e2e_batch
+    per_step = args.e2e_batch if not triangulate else max(P * 8, 96)
     search = CFG == "C"
+    tri_s = [0.0] * P
     if search:
         from flame_b200 import synth
         si = _search_inputs()
@@ -672,10 +687,15 @@ def run_e2e(args, local_rank, frames, dims, barrier):
                     ctx.process_frame_wait(slot, x, w1, w2)
                     acc += float(x[0]) + float(outs[k][slot].array[H // 2, W // 2])
                 g = frames[i % len(frames)]
+                tris_i, edges_i = g["tris"], g["edges"]
+                if triangulate:  # Delaunay of this frame's vertices on this host thread, while earlier frames run
+                    t_tri = time.perf_counter()
+                    tris_i, edges_i = _lib.delaunay(g["pos"])
+                    tri_s[k] += time.perf_counter() - t_tri
                 if search:  # host feature records in and out (5 000 x 40 B each way), synchronous
                     f = si["feats"].copy()
                     ctx.update_feature_idepths(tp, 1, 0, f, want_diag=False)
-                ctx.process_frame_submit(slot, g["pos"], g["data_term"], g["edges"], g["tris"], H, W, p,
+                ctx.process_frame_submit(slot, g["pos"], g["data_term"], edges_i, tris_i, H, W, p,
                                          int(os.environ.get("E2E_ITERS", iters)),
                                          None if os.environ.get("E2E_NOMAP") else outs[k][slot].array)
                 busy[slot] = True
@@ -720,6 +740,8 @@ def run_e2e(args, local_rank, frames, dims, barrier):
     for row in outs:
         for o in row:
             o.free()
+    if triangulate:
+        breakdown["per_frame_us"]["delaunay"] = 1e6 * sum(tri_s) / max(1, per_step * (args.steps + 1))
     return {"seconds": dt, "frames": per_step * args.steps, "h2d": h2d, "d2h": d2h,
             "per_step": per_step, "threads": P, "in_flight": P * R, "breakdown": breakdown}
 
@@ -743,6 +765,9 @@ def main():
     ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 stream, 2 resident")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-search", action="store_true", help="skip the epipolar-search side measurement")
+    ap.add_argument("--no-tri", action="store_true", help="skip the e2e leg that includes the host triangulation")
+    ap.add_argument("--tri-threads", type=int, default=0,
+                    help="host threads of the e2e leg that triangulates (0 = usable cpus / ranks on the box - 2, <= 12)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="config E: how the results reach rank 0 (peer stores from the projection kernel / ncclGather)")
     ap.add_argument("--e2e-only", action="store_true", help="experiments: only the e2e leg (prints its dict)")
@@ -750,6 +775,8 @@ def main():
     CFG = args.config
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.tri_threads <= 0:
+        args.tri_threads = max(2, min(12, _usable_cpus() // max(1, world) - 2))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)

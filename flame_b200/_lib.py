@@ -124,7 +124,7 @@ SYMBOLS = [
     "flame_b200_graph_resync", "flame_b200_pd_run", "flame_b200_pd_wave",
     "flame_b200_pd_cost", "flame_b200_interpolate_mesh", "flame_b200_mesh_bind",
     "flame_b200_mesh_project", "flame_b200_mesh_download", "flame_b200_process_frame",
-    "flame_b200_slot_device_ptrs", "flame_b200_mesh_redirect", "flame_b200_device_alloc",
+    "flame_b200_delaunay", "flame_b200_slot_device_ptrs", "flame_b200_mesh_redirect", "flame_b200_device_alloc",
     "flame_b200_device_free", "flame_b200_ipc_export", "flame_b200_ipc_open", "flame_b200_ipc_close",
     "flame_b200_process_frame_submit", "flame_b200_process_frame_wait", "flame_b200_ctx_stats",
     "flame_b200_tri_filter_default_params", "flame_b200_mesh_filter", "flame_b200_mesh_coverage",
@@ -179,6 +179,8 @@ def lib():
     L.flame_b200_mesh_bind.argtypes = [vp, C.c_int, C.c_int32, i32p, u8p, u8p, C.c_int, C.c_int]
     L.flame_b200_mesh_project.argtypes = [vp, C.c_int, C.c_int, C.c_float]
     L.flame_b200_mesh_download.argtypes = [vp, C.c_int, vp]
+    L.flame_b200_delaunay.argtypes = [C.c_int32, f32p, C.c_int32, C.POINTER(C.c_int32), i32p, C.c_int32,
+                                      C.POINTER(C.c_int32), i32p]
     L.flame_b200_mesh_redirect.argtypes = [vp, C.c_int, vp, vp]
     L.flame_b200_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp)]
     L.flame_b200_device_free.argtypes = [vp]
@@ -240,6 +242,18 @@ def bptr(a):
         return None
     assert a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"], "need contiguous uint8"
     return a.ctypes.data_as(u8p)
+
+
+def delaunay(pos):
+    """flame_b200_delaunay: (tris [T,3] int32, edges [E,2] int32) of the points pos [V,2] (host-only, releases the GIL)."""
+    pos = np.ascontiguousarray(pos, np.float32)
+    V = pos.shape[0]
+    tris = np.empty((max(2 * V, 1), 3), np.int32)
+    edges = np.empty((max(3 * V, 1), 2), np.int32)
+    nt, ne = C.c_int32(), C.c_int32()
+    check(lib().flame_b200_delaunay(V, fptr(pos), tris.shape[0], C.byref(nt), iptr(tris), edges.shape[0],
+                                    C.byref(ne), iptr(edges)))
+    return tris[:nt.value].copy(), edges[:ne.value].copy()
 
 
 def default_pd_params():

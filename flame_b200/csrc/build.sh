@@ -12,6 +12,8 @@ for f in pd raster stereo capi; do
   $NVCC $FLAGS -c "$HERE/$f.cu" -o "$OUT/obj/$f.o" &
   pids+=($!)
 done
+$NVCC $FLAGS -c "$HERE/delaunay.cc" -o "$OUT/obj/delaunay.o" &  # host-only (frame pipeline's triangulator)
+pids+=($!)
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libflame_b200.so" "$OUT/obj/pd.o" "$OUT/obj/raster.o" "$OUT/obj/stereo.o" "$OUT/obj/capi.o" -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libflame_b200.so" "$OUT/obj/pd.o" "$OUT/obj/raster.o" "$OUT/obj/stereo.o" "$OUT/obj/capi.o" "$OUT/obj/delaunay.o" -lcudart
 echo "built $OUT/libflame_b200.so"

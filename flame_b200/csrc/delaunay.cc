@@ -1,0 +1,243 @@
+// Host-side Delaunay triangulation for the frame pipeline.
+//
+// The reference triangulates the feature set of every frame with Shewchuk's Triangle
+// (src/flame/utils/delaunay.cc:31-77, "zneQB"); at 10 000 vertices that is ~10 ms of host time, two orders of
+// magnitude above the GPU's share of a frame. Triangle itself is the caller's (it is not part of this
+// library, and callers that need index-identical output keep using it: triangles / edges are plain inputs of
+// every entry point). This file gives the pipeline its own triangulator, so that a host thread can
+// triangulate frame k+1 while the device works on frame k:
+//
+//   * divide and conquer (Guibas & Stolfi 1985) on a quad-edge structure, O(V log V), no super-triangle;
+//   * EXACT predicates: positions are rounded to 1/256 px (int32 fixed point, |coordinate| < 8192 px), the
+//     orientation test is evaluated in int64 and the in-circle test in __int128, so collinear and cocircular
+//     inputs - features sit on the pixel grid - need no tolerances and cannot loop;
+//   * output in Triangle's conventions: triangles with positive signed area in image coordinates (what the
+//     reference calls clockwise, y pointing down), every undirected edge once.
+//
+// What this redefines: the INDEX ARRAYS are a Delaunay triangulation of the same points, not Triangle's
+// arrays (different but equally valid diagonals in cocircular quadruples, different edge order). Everything
+// downstream is bit-exact given the arrays. tests/test_delaunay.py checks the empty-circumcircle property,
+// the Euler counts and the winding against the reference's Triangle.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+namespace fb {
+namespace {
+
+typedef int32_t Edge;  // 4 * quad + rotation
+
+struct Mesh {
+  std::vector<Edge> onext;   // per directed (primal or dual) edge
+  std::vector<int32_t> org;  // per directed edge (meaningful for rotation 0 and 2)
+  std::vector<uint8_t> dead; // per quad
+  const int32_t* px;
+  const int32_t* py;
+
+  static Edge rot(Edge e) { return (e & ~3) | ((e + 1) & 3); }
+  static Edge sym(Edge e) { return (e & ~3) | ((e + 2) & 3); }
+  static Edge invrot(Edge e) { return (e & ~3) | ((e + 3) & 3); }
+  Edge on(Edge e) const { return onext[e]; }
+  Edge oprev(Edge e) const { return rot(onext[rot(e)]); }
+  Edge lnext(Edge e) const { return rot(onext[invrot(e)]); }
+  Edge rprev(Edge e) const { return onext[sym(e)]; }
+  int32_t dest(Edge e) const { return org[sym(e)]; }
+
+  Edge make_edge(int32_t a, int32_t b) {
+    const Edge q = (Edge)onext.size();
+    onext.push_back(q);
+    onext.push_back(q + 3);
+    onext.push_back(q + 2);
+    onext.push_back(q + 1);
+    org.push_back(a);
+    org.push_back(-1);
+    org.push_back(b);
+    org.push_back(-1);
+    dead.push_back(0);
+    return q;
+  }
+  void splice(Edge a, Edge b) {
+    const Edge alpha = rot(onext[a]), beta = rot(onext[b]);
+    std::swap(onext[a], onext[b]);
+    std::swap(onext[alpha], onext[beta]);
+  }
+  Edge connect(Edge a, Edge b) {
+    const Edge e = make_edge(dest(a), org[b]);
+    splice(e, lnext(a));
+    splice(sym(e), b);
+    return e;
+  }
+  void remove(Edge e) {
+    splice(e, oprev(e));
+    splice(sym(e), oprev(sym(e)));
+    dead[e >> 2] = 1;
+  }
+
+  // > 0: a, b, c counter-clockwise (positive signed area in the coordinates as given)
+  int64_t ccw(int32_t a, int32_t b, int32_t c) const {
+    return (int64_t)(px[b] - px[a]) * (py[c] - py[a]) - (int64_t)(py[b] - py[a]) * (px[c] - px[a]);
+  }
+  // d strictly inside the circle through a, b, c (a, b, c counter-clockwise)
+  bool incircle(int32_t a, int32_t b, int32_t c, int32_t d) const {
+    const int64_t ax = px[a] - px[d], ay = py[a] - py[d];
+    const int64_t bx = px[b] - px[d], by = py[b] - py[d];
+    const int64_t cx = px[c] - px[d], cy = py[c] - py[d];
+    const __int128 a2 = (__int128)(ax * ax + ay * ay), b2 = (__int128)(bx * bx + by * by),
+                   c2 = (__int128)(cx * cx + cy * cy);
+    const __int128 det = a2 * (__int128)(bx * cy - by * cx) - b2 * (__int128)(ax * cy - ay * cx) +
+                         c2 * (__int128)(ax * by - ay * bx);
+    return det > 0;
+  }
+  bool right_of(int32_t p, Edge e) const { return ccw(p, dest(e), org[e]) > 0; }
+  bool left_of(int32_t p, Edge e) const { return ccw(p, org[e], dest(e)) > 0; }
+
+  // s[lo, hi): vertex ids sorted by (x, y), all distinct. Returns the ccw convex-hull edge out of the
+  // leftmost vertex and the cw hull edge out of the rightmost one.
+  void build(const int32_t* s, int lo, int hi, Edge* le, Edge* re) {
+    const int n = hi - lo;
+    if (n == 2) {
+      const Edge a = make_edge(s[lo], s[lo + 1]);
+      *le = a;
+      *re = sym(a);
+      return;
+    }
+    if (n == 3) {
+      const Edge a = make_edge(s[lo], s[lo + 1]), b = make_edge(s[lo + 1], s[lo + 2]);
+      splice(sym(a), b);
+      const int64_t o = ccw(s[lo], s[lo + 1], s[lo + 2]);
+      if (o > 0) {
+        connect(b, a);
+        *le = a;
+        *re = sym(b);
+      } else if (o < 0) {
+        const Edge c = connect(b, a);
+        *le = sym(c);
+        *re = c;
+      } else {  // collinear
+        *le = a;
+        *re = sym(b);
+      }
+      return;
+    }
+    const int mid = lo + n / 2;
+    Edge ldo, ldi, rdi, rdo;
+    build(s, lo, mid, &ldo, &ldi);
+    build(s, mid, hi, &rdi, &rdo);
+    for (;;) {  // lower common tangent of the two hulls
+      if (left_of(org[rdi], ldi)) ldi = lnext(ldi);
+      else if (right_of(org[ldi], rdi)) rdi = rprev(rdi);
+      else break;
+    }
+    Edge basel = connect(sym(rdi), ldi);
+    if (org[ldi] == org[ldo]) ldo = sym(basel);
+    if (org[rdi] == org[rdo]) rdo = basel;
+    for (;;) {  // merge: the rising bubble
+      Edge lcand = on(sym(basel));
+      if (right_of(dest(lcand), basel))
+        while (incircle(dest(basel), org[basel], dest(lcand), dest(on(lcand)))) {
+          const Edge t = on(lcand);
+          remove(lcand);
+          lcand = t;
+        }
+      Edge rcand = oprev(basel);
+      if (right_of(dest(rcand), basel))
+        while (incircle(dest(basel), org[basel], dest(rcand), dest(oprev(rcand)))) {
+          const Edge t = oprev(rcand);
+          remove(rcand);
+          rcand = t;
+        }
+      const bool lv = right_of(dest(lcand), basel), rv = right_of(dest(rcand), basel);
+      if (!lv && !rv) break;
+      if (!lv || (rv && incircle(dest(lcand), org[lcand], org[rcand], dest(rcand))))
+        basel = connect(rcand, sym(basel));
+      else
+        basel = connect(sym(basel), sym(lcand));
+    }
+    *le = ldo;
+    *re = rdo;
+  }
+};
+
+}  // namespace
+}  // namespace fb
+
+extern "C" int flame_b200_delaunay(int32_t V, const float* pos, int32_t tri_capacity, int32_t* n_tris,
+                                   int32_t* tris, int32_t edge_capacity, int32_t* n_edges, int32_t* edges) {
+  using namespace fb;
+  if (V < 0 || (V > 0 && !pos) || !n_tris || !n_edges || tri_capacity < 0 || edge_capacity < 0) {
+    set_error("delaunay: bad arguments");
+    return FLAME_B200_EINVAL;
+  }
+  *n_tris = 0;
+  *n_edges = 0;
+  std::vector<int32_t> px(V), py(V), order(V);
+  for (int32_t v = 0; v < V; ++v) {
+    const float x = pos[2 * v], y = pos[2 * v + 1];
+    if (!(std::fabs(x) < 8192.0f) || !(std::fabs(y) < 8192.0f)) {
+      set_error("delaunay: coordinate outside (-8192, 8192) px or not finite");
+      return FLAME_B200_EINVAL;
+    }
+    px[v] = (int32_t)std::lrintf(x * 256.0f);
+    py[v] = (int32_t)std::lrintf(y * 256.0f);
+    order[v] = v;
+  }
+  std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+    return px[a] != px[b] ? px[a] < px[b] : (py[a] != py[b] ? py[a] < py[b] : a < b);
+  });
+  // coincident points (after rounding): the first one represents them, the others stay unconnected (as
+  // Triangle leaves duplicate vertices out)
+  int n = 0;
+  for (int32_t i = 0; i < V; ++i)
+    if (n == 0 || px[order[i]] != px[order[n - 1]] || py[order[i]] != py[order[n - 1]]) order[n++] = order[i];
+  if (n < 2) return 0;
+  Mesh m;
+  m.px = px.data();
+  m.py = py.data();
+  m.onext.reserve((size_t)12 * n + 16);
+  m.org.reserve((size_t)12 * n + 16);
+  m.dead.reserve((size_t)3 * n + 4);
+  Edge le, re;
+  m.build(order.data(), 0, n, &le, &re);
+  const int32_t quads = (int32_t)m.dead.size();
+  int32_t ne = 0, nt = 0;
+  for (int32_t q = 0; q < quads; ++q) {
+    if (m.dead[q]) continue;
+    const Edge e = 4 * q;
+    if (ne < edge_capacity && edges) {
+      edges[2 * ne] = m.org[e];
+      edges[2 * ne + 1] = m.dest(e);
+    }
+    ++ne;
+  }
+  // faces: the cycle to the left of a directed edge; interior faces are positively oriented triangles. Each is
+  // reported from its lowest-numbered directed edge.
+  for (int32_t q = 0; q < quads; ++q) {
+    if (m.dead[q]) continue;
+    for (int half = 0; half < 2; ++half) {
+      const Edge e0 = 4 * q + 2 * half;
+      const Edge e1 = m.lnext(e0), e2 = m.lnext(e1);
+      if (m.lnext(e2) != e0 || e1 < e0 || e2 < e0) continue;
+      const int32_t a = m.org[e0], b = m.org[e1], c = m.org[e2];
+      if (m.ccw(a, b, c) <= 0) continue;  // the outer face (or a degenerate cycle)
+      if (nt < tri_capacity && tris) {
+        tris[3 * nt] = a;
+        tris[3 * nt + 1] = b;
+        tris[3 * nt + 2] = c;
+      }
+      ++nt;
+    }
+  }
+  *n_edges = ne;
+  *n_tris = nt;
+  if ((tris && nt > tri_capacity) || (edges && ne > edge_capacity)) {
+    set_error("delaunay: output capacity too small (needs " + std::to_string(nt) + " triangles, " +
+              std::to_string(ne) + " edges)");
+    return FLAME_B200_ENOMEM;
+  }
+  return 0;
+}

@@ -361,6 +361,22 @@ typedef struct {
 } flame_b200_stats;
 int flame_b200_ctx_stats(flame_b200_ctx* ctx, flame_b200_stats* out, int reset);
 
+/* ---- triangulation for the frame pipeline ------------------------------------------
+ * Replaces utils::Delaunay::triangulate (utils/delaunay.cc:31-77 over external/triangle) where the caller does
+ * not need Triangle's exact index arrays: a host-side (pure CPU, thread-safe, no context) divide-and-conquer
+ * Delaunay triangulation with exact integer predicates on positions rounded to 1/256 px. A host thread runs it
+ * for frame k+1 while the device works on frame k (bench.py e2e "incl_triangulation").
+ * Output in Triangle's conventions: tris = 3 vertex indices per triangle, positively oriented in image
+ * coordinates (Triangle's order); edges = every undirected edge once (source, target). The arrays are A
+ * Delaunay triangulation of the points, NOT Triangle's arrays: cocircular quadruples may be split along the
+ * other diagonal and the edge order differs - callers that need index-identical output keep Triangle and pass
+ * its arrays, which every entry point of this library accepts unchanged.
+ * pos: 2V floats, |coordinate| < 8192. Coincident points (after rounding) are represented by the first of
+ * them; the others get no triangle. tris / edges may be NULL to query the counts. Returns FLAME_B200_ENOMEM
+ * (with the counts set) when a capacity is too small: 2V triangles and 3V edges always suffice. */
+int flame_b200_delaunay(int32_t V, const float* pos, int32_t tri_capacity, int32_t* n_tris, int32_t* tris,
+                        int32_t edge_capacity, int32_t* n_edges, int32_t* edges);
+
 /* ---- epipolar search + measurement + fusion: Flame::updateFeatureIDepths / trackFeature
  *      (flame.cc:1280-1752) over stereo::inverse_depth_filter::{predict,getSearchRegion,search,
  *      update} (stereo/inverse_depth_filter.h:73-107), stereo::line_stereo::match

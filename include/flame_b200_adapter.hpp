@@ -147,6 +147,40 @@ class DeviceGraph {
     }
   }
 
+  // The same including the REMOVAL RULES of Flame::projectGraph (flame.cc:1901-1917) evaluated on the device:
+  // returns, in boost::vertices order of the last upload()/resync(), whether the reference would remove the
+  // vertex (outside valid_region, behind the camera, or - do_grad_check_after_projection - on a gradient-free
+  // pixel of the new frame in frame slot `fnew_slot`). The caller then does what :1920-1928 does for the marked
+  // vertices (clear_vertex / remove_vertex / erase from the feature maps). `RefParams` = flame::Params.
+  template <class RefParams>
+  std::vector<uint8_t> projectMarked(const RefParams& params, const float q_wxyz[4], const float t[3],
+                                     float graph_scale, int fnew_slot, Graph* g) {
+    flame_b200_project_rules r;
+    r.rescale_factor_max = params.rescale_factor_max;
+    r.win_size = params.fparams.win_size;
+    r.do_letterbox = params.do_letterbox ? 1 : 0;
+    r.do_grad_check_after_projection = params.do_grad_check_after_projection ? 1 : 0;
+    r.min_grad_mag = params.min_grad_mag;
+    std::vector<float> pos(static_cast<size_t>(2) * V_ + 2), idepth(static_cast<size_t>(V_) + 1);
+    std::vector<uint8_t> remove(static_cast<size_t>(V_) + 1, 0);
+    check(flame_b200_graph_project_marked(s_->get(), slot_, q_wxyz, t, graph_scale, &r, fnew_slot, pos.data(),
+                                          idepth.data(), remove.data()),
+          "flame_b200_graph_project_marked");
+    for (int32_t v = 0; v < V_; ++v) {
+      auto& d = (*g)[vh_[v]];
+      d.pos.x = pos[2 * v];
+      d.pos.y = pos[2 * v + 1];
+      d.x = idepth[v] / graph_scale;
+    }
+    remove.resize(static_cast<size_t>(V_));
+    return remove;
+  }
+
+  // The vertex handle at position v of the flat order (to act on projectMarked's result).
+  typename std::decay<decltype(*vertices(*static_cast<const Graph*>(nullptr)).first)>::type vertex(int32_t v) const {
+    return vh_[v];
+  }
+
   // After Flame::syncGraph edited the Boost graph (vertices removed / added, edges re-triangulated,
   // flame.cc:1984-2162): rebuild the device graph from it and carry the solver state of the surviving
   // vertices and edges over ON THE DEVICE (no download / upload of x, w, q). `is_new(vertex)` must say
