@@ -330,8 +330,10 @@ def run_ours(args, rank, world, local_rank):
                           "in_flight": e["in_flight"], "breakdown": e["breakdown"]}))
         return
     # ---- how many frames the device solves concurrently (one thread-block cluster per frame) ----
+    pref = _lib.PREF_LATENCY if args.layout == "wide" else _lib.PREF_THROUGHPUT
     probe, _ = _frames(1)
     with _lib.Context(local_rank, 1) as c0:
+        c0.set_pd_preference(pref)
         c0.graph_init(0, probe[0]["pos"], probe[0]["data_term"], probe[0]["edges"])
         wave = c0.pd_wave(0) if args.mode != 1 else 0
     if args.wave > 0:
@@ -343,6 +345,7 @@ def run_ours(args, rank, world, local_rank):
     ids = shard.frames_for_rank(rank, world, B)  # frames shard by rank: no data-path collective
     frames, _ = _frames(B, first=ids[0] % 1000)
     ctx = _lib.Context(local_rank, B)
+    ctx.set_pd_preference(pref)
     for i, g in enumerate(frames):
         ctx.graph_init(i, g["pos"], g["data_term"], g["edges"])
         ctx.mesh_bind(i, g["tris"], H, W)
@@ -499,7 +502,7 @@ def run_ours(args, rank, world, local_rank):
             "details": {"E": E, "frames_per_step_per_gpu": B, "frames_per_solver_launch": wave,
                         "distinct_synthetic_frames": min(B, N_DISTINCT),
                         "async_projection": not args.no_async,
-                        "pd_mode": ["auto", "stream", "resident"][args.mode],
+                        "pd_mode": ["auto", "stream", "resident"][args.mode], "cluster_layout": args.layout,
                         "issue": "a step walks its frames in waves of %d (one solver launch per wave = the frame "
                                  "clusters the device keeps resident); the projection of a wave %s" % (
                                      wave, "runs in stream order" if args.no_async else
@@ -759,6 +762,10 @@ def main():
     ap.add_argument("--wave", type=int, default=0,
                     help="frames per solver launch inside a step (0 = what the device keeps resident: pd_wave)")
     ap.add_argument("--no-async", action="store_true", help="projection in stream order (no second stream)")
+    ap.add_argument("--layout", default="compact", choices=["wide", "compact"],
+                    help="device-resident leg: the cluster size that keeps most SMs busy (9 CTAs per frame, 15 frames "
+                         "per wave on 135 SMs; the low-priority projection stream fills the rest and the gaps) or "
+                         "frame clusters of 16 CTAs (7 frames per wave, lower latency per frame)")
     ap.add_argument("--pipelines", type=int, default=3, help="host threads (one context each) of the e2e leg")
     ap.add_argument("--ring", type=int, default=30, help="frame slots per e2e host thread (two 15-frame waves)")
     ap.add_argument("--e2e-batch", type=int, default=480, help="frames per GPU per step of the e2e leg")

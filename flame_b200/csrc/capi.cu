@@ -105,6 +105,7 @@ struct flame_b200_ctx {
   // asynchronous dense projection (flame_b200_ctx_set_async_projection): the projection kernels run on
   // `side` so that the next frames' solver launches on `stream` overlap them
   bool async_proj = false;
+  int prio_lo = 0;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_vals = nullptr;
   struct Pending { int lo, hi; cudaEvent_t done; };  // projections of slots [lo, hi) issued on `side`
@@ -114,6 +115,7 @@ struct flame_b200_ctx {
   std::vector<uint32_t> keys;
   std::vector<int> degv, srcdeg, order, koff_tmp, pre_deg, pre_src;
   int pd_pref = 0;                   // FLAME_B200_PREF_*: how prep_plan sizes the frame clusters
+  int busy_sms[17] = {0};            // [C] = C x clusters of C CTAs the device keeps resident (full shared memory)
   // frame pipeline: frames submitted to consecutive slots are solved as one wave (wave_flush)
   std::vector<int> wave;
   flame_b200_pd_params wave_params{};
@@ -220,6 +222,7 @@ static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const in
   int forced = 0;
   if (const char* sv = getenv("FLAME_B200_CLUSTER")) forced = atoi(sv);
   ResidentPlan plan{};
+  int best_busy = -1;
   if (V > 0 && V < (1 << 20) && max_deg <= FB_RESIDENT_MAX_DEG) {
     // throughput (default): the smallest cluster that holds the graph - any size, not only powers of two -
     // so that as many frames as possible are resident at once; latency: the smallest cluster of the
@@ -240,6 +243,12 @@ static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const in
         const int variant = pd_resident_variant(Vc, maxEdges, &thr);
         if (variant < 0) continue;
         if (pass == 0 && variant != 0) continue;
+        // throughput: the cluster size that keeps the most SMs busy (clusters resident on the device x CTAs per
+        // cluster - a cluster may not straddle GPCs, so this is not monotonic: 15 x 9 = 135 SMs beats 15 x 8
+        // and 12 x 10); ties and the latency pass: the first (smallest) that fits
+        const int busy = (pass == 1 && !forced) ? c->busy_sms[C] : 0;
+        if (busy < best_busy || (plan.cluster && busy == best_busy)) continue;
+        best_busy = busy;
         plan.cluster = C;
         plan.variant = variant;
         plan.Vc = Vc;
@@ -248,7 +257,7 @@ static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const in
         plan.max_deg = max_deg;
         plan.smem_bytes = smem;
         plan.threads = thr;
-        break;
+        if (pass == 0 || forced) break;
       }
   }
   const int Vc = plan.cluster ? plan.Vc : std::min(std::max(V, 1), 1024);
@@ -508,7 +517,13 @@ int flame_b200_ctx_create(int device, int n_slots, flame_b200_ctx** out) {
   c->device = device;
   c->n_slots = n_slots;
   c->slots.resize(n_slots);
-  FB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  // the main stream carries the solver, whose clusters need whole SMs of one GPC free at the same time: it
+  // gets the highest priority so that pending cluster launches are served before the many small CTAs of the
+  // projection (second stream, lowest priority), which then fill the SMs the clusters leave idle
+  int prio_lo = 0, prio_hi = 0;
+  FB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  c->prio_lo = prio_lo;
+  FB_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
   FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_graphs), sizeof(GraphDev) * n_slots));
   FB_CUDA(cudaMemset(c->d_graphs, 0, sizeof(GraphDev) * n_slots));
   FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_meshes), sizeof(MeshDev) * n_slots));
@@ -516,6 +531,15 @@ int flame_b200_ctx_create(int device, int n_slots, flame_b200_ctx** out) {
   FB_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_cost), 2 * sizeof(double)));
   FB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_cost), 2 * sizeof(double)));
   if (int rc = pd_resident_init()) return rc;
+  for (int C = 1; C <= 16; ++C) {
+    ResidentPlan pl{};
+    pl.cluster = C;
+    pl.variant = 1;  // the 768-thread build; one CTA per SM for every build at these shared-memory sizes
+    pl.smem_bytes = 200 * 1024;
+    int n = 0;
+    if (int rc = pd_resident_capacity(pl, &n)) return rc;
+    c->busy_sms[C] = n * C;
+  }
   *out = c.release();
   return 0;
 }
@@ -579,7 +603,7 @@ int flame_b200_ctx_set_async_projection(flame_b200_ctx* c, int on) {
   if (int rc = use_device(c)) return rc;
   if (int rc = join_side(c)) return rc;
   if (on && !c->side) {
-    FB_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    FB_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, c->prio_lo));
     FB_CUDA(cudaEventCreateWithFlags(&c->ev_vals, cudaEventDisableTiming));
   }
   c->async_proj = on != 0;

@@ -617,14 +617,20 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
       s_bar[i] = g.vbar[v0 + i];
     }
   }
-  // Owned edges = source-role incidence slots of this chunk, listed vertex by vertex (threads of a warp
-  // read the same / adjacent source records): per-vertex out-degree -> exclusive scan by warp 0 -> fill.
+  // Owned edges = source-role incidence slots of this chunk. CUT edges (target in another CTA: their x_bar read
+  // is a DSMEM round trip) come first, so that they spread over the first ceil(ncut / MAXT) rounds of ALL
+  // threads instead of piling up in the warps that own the boundary vertices; within both groups the edges
+  // are listed vertex by vertex (threads of a warp read the same / adjacent source records).
+  // Per-vertex counts -> exclusive scan of (local << 16 | cut) by warp 0 -> fill.
 #pragma unroll
   for (int v = 0; v < VPT; ++v) {
     const int i = tid + v * MAXT;
     if (i < nv) {
       int cnt = 0;
-      for (int k = 0; k < deg[v]; ++k) cnt += ((g.inc_nbr[base + s_koff[k] + i] & 1) == 0);
+      for (int k = 0; k < deg[v]; ++k) {
+        const int ent = g.inc_nbr[base + s_koff[k] + i];
+        if ((ent & 1) == 0) cnt += ((ent >> 1) / Vc != c) ? 1 : (1 << 16);
+      }
       s_scan[i] = cnt;
     }
   }
@@ -646,15 +652,21 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
     if (tid == 0) *s_cnt = run;
   }
   __syncthreads();
-  const int ne = *s_cnt;  // <= MAXT * SPT (planner)
+  const int ncut = *s_cnt & 0xFFFF;
+  const int ne = ncut + (*s_cnt >> 16);  // <= MAXT * SPT (planner)
 #pragma unroll
   for (int v = 0; v < VPT; ++v) {
     const int i = tid + v * MAXT;
     if (i < nv) {
-      int at = s_scan[i];
+      int at_cut = s_scan[i] & 0xFFFF, at_loc = ncut + (s_scan[i] >> 16);
       for (int k = 0; k < deg[v]; ++k) {
         const int slot = s_koff[k] + i;
-        if ((g.inc_nbr[base + slot] & 1) == 0) s_list[at++] = ((unsigned int)i << 16) | (unsigned int)slot;
+        const int ent = g.inc_nbr[base + slot];
+        if ((ent & 1) == 0) {
+          const unsigned int rec = ((unsigned int)i << 16) | (unsigned int)slot;
+          if ((ent >> 1) / Vc != c) s_list[at_cut++] = rec;
+          else s_list[at_loc++] = rec;
+        }
       }
     }
   }
