@@ -583,7 +583,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   float4* s_p4 = s_bar + a.Vc;                      // per incidence slot: (sx, t1, t2, u1)
   float4* s_s = s_p4 + resident_p4_records(a.maxInc, a.maxEdges, a.Vc);  // per owned edge: (alpha, beta, dx, dy)
   float* s_p1 = reinterpret_cast<float*>(s_s + a.maxEdges);             // per incidence slot: u2
-  int* s_koff = reinterpret_cast<int*>(s_p1 + a.maxInc);                // a.max_deg + 1
+  int* s_koff = reinterpret_cast<int*>(s_p1 + ((a.maxInc + 1) & ~1));     // a.max_deg + 1 (8-byte aligned: read in pairs)
   int* s_cnt = s_koff + a.max_deg + 1;                                  // 1
   unsigned int* s_list = reinterpret_cast<unsigned int*>(s_p4);  // load phase only: owned edges (vertex << 16 | slot)
   int* s_scan = reinterpret_cast<int*>(s_list + a.maxEdges);     // load phase only: first owned edge of every vertex
@@ -746,8 +746,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   };
 
   // ---- phase B: ordered accumulation + prox + extragradient ----
+  // Shared-memory byte addresses of the vertex's first-incidence records: incidence k is koff[k] records on.
+  uint32_t vp4[VPT], vp1[VPT];
+#pragma unroll
+  for (int v = 0; v < VPT; ++v) {
+    vp4[v] = p4_addr + (uint32_t)(tid + v * MAXT) * 16u;
+    vp1[v] = smem_u32(s_p1) + (uint32_t)(tid + v * MAXT) * 4u;
+  }
+  const uint32_t koff_addr = smem_u32(s_koff);
   auto phase_b = [&](const bool last) {
-    const int* kr = s_koff;
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
       const int i = tid + v * MAXT;
@@ -755,28 +762,38 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
         const float x_old = x[v], w1_old = w1[v], w2_old = w2[v];
         float xx = x_old, ww1 = w1_old, ww2 = w2_old;
         const int d = deg[v];
-        // software pipeline: the contribution record of incidence k+1 is in flight while k is added
-        float4 p4n = make_float4(0.f, 0.f, 0.f, 0.f);
-        float p1n = 0.f;
-        if (d > 0) {
-          p4n = s_p4[kr[0] + i];
-          p1n = s_p1[kr[0] + i];
+        // plain loop, two incidences per trip: the 24-32 resident warps hide the shared-memory latency, and
+        // a hand-rolled software pipeline costs more issue slots (register copies) than it saves
+        int k = 0;
+        for (; k + 1 < d; k += 2) {
+          uint32_t ko0, ko1;
+          asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(ko0), "=r"(ko1) : "r"(koff_addr + (uint32_t)k * 4u));
+          const float4 a4 = ld_shared_f4(vp4[v] + ko0 * 16u);
+          float a1, b1;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a1) : "r"(vp1[v] + ko0 * 4u));
+          const float4 b4 = ld_shared_f4(vp4[v] + ko1 * 16u);
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(b1) : "r"(vp1[v] + ko1 * 4u));
+          xx = add(xx, a4.x);
+          ww1 = add(ww1, a4.y);
+          ww2 = add(ww2, a4.z);
+          ww1 = add(ww1, a4.w);
+          ww2 = add(ww2, a1);
+          xx = add(xx, b4.x);
+          ww1 = add(ww1, b4.y);
+          ww2 = add(ww2, b4.z);
+          ww1 = add(ww1, b4.w);
+          ww2 = add(ww2, b1);
         }
-        int ko = (d > 1) ? kr[1] : 0;
-        for (int k = 0; k < d; ++k) {
-          const float4 p4 = p4n;
-          const float p1 = p1n;
-          if (k + 1 < d) {
-            const int slot = ko + i;
-            p4n = s_p4[slot];
-            p1n = s_p1[slot];
-            ko = kr[k + 2];  // k + 2 <= max_deg: inside the row
-          }
-          xx = add(xx, p4.x);
-          ww1 = add(ww1, p4.y);
-          ww2 = add(ww2, p4.z);
-          ww1 = add(ww1, p4.w);
-          ww2 = add(ww2, p1);
+        if (k < d) {
+          const uint32_t ko0 = (uint32_t)s_koff[k];
+          const float4 a4 = ld_shared_f4(vp4[v] + ko0 * 16u);
+          float a1;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a1) : "r"(vp1[v] + ko0 * 4u));
+          xx = add(xx, a4.x);
+          ww1 = add(ww1, a4.y);
+          ww2 = add(ww2, a4.z);
+          ww1 = add(ww1, a4.w);
+          ww2 = add(ww2, a1);
         }
         const VertexOut o = vertex_finish(xx, ww1, ww2, data[v], wt[v], x_old, w1_old, w2_old, p);
         x[v] = o.prim.x; w1[v] = ww1; w2[v] = ww2;
@@ -821,7 +838,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
 
 size_t pd_resident_smem(int Vc, int maxInc, int maxEdges, int max_deg) {
   return (size_t)Vc * 16 + (size_t)resident_p4_records(maxInc, maxEdges, Vc) * 16 + (size_t)maxEdges * 16 +
-         (size_t)maxInc * 4 + (size_t)(max_deg + 2) * 4 + 128;
+         (size_t)((maxInc + 1) & ~1) * 4 + (size_t)(max_deg + 2) * 4 + 128;
 }
 
 // The register budgets the kernel is built for: (threads, owned edges per thread, vertices per thread).

@@ -1243,11 +1243,18 @@ int stereo_features_upload(void* state, cudaStream_t st, const flame_b200_featur
     set_error("features_upload: camera / frames not set");
     return FLAME_B200_ESTATE;
   }
-  for (int i = 0; i < n_feats; ++i)
+  for (int i = 0; i < n_feats; ++i) {
     if (feats[i].frame_id >= FB_MAX_FRAMES || !s->h_frames[feats[i].frame_id].valid) {
       set_error("update_feature_idepths: feature parented to a frame slot that was not uploaded");
       return FLAME_B200_EINVAL;
     }
+    // the kernel addresses the images with these: a non-finite coordinate must not reach it
+    if (!std::isfinite(feats[i].x) || !std::isfinite(feats[i].y) || !std::isfinite(feats[i].idepth_mu) ||
+        !std::isfinite(feats[i].idepth_var)) {
+      set_error("update_feature_idepths: feature with a non-finite position / idepth");
+      return FLAME_B200_EINVAL;
+    }
+  }
   if (int rc = feats_reserve(s, n_feats)) return rc;
   FB_CUDA(cudaEventSynchronize(s->feats_free));
   s->n_feats = n_feats;

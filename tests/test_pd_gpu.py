@@ -274,3 +274,26 @@ def test_pd_layout_with_multi_edges_and_self_loops(gpu_ctx, oracle):
         gpu_ctx.pd_run(_lib.default_pd_params(), 15, slot0=3, mode=mode)
         got = gpu_ctx.graph_download(3, V, edges.shape[0])
         _assert_bit_equal(got, want, STATE)
+
+
+def test_pd_vertex_degree_beyond_the_resident_limit(gpu_ctx, oracle):
+    """A hub vertex with more than 64 incident edges (FB_RESIDENT_MAX_DEG): AUTO takes the streaming kernel,
+    RESIDENT refuses, results stay bit-exact."""
+    rng = np.random.default_rng(12)
+    V = 300
+    pos = rng.uniform(4, 600, (V, 2)).astype(np.float32)
+    hub = np.stack([np.zeros(90, np.int32), np.arange(1, 91, dtype=np.int32)], 1)
+    hub[::2] = hub[::2, ::-1]  # the hub is source of some, target of others
+    ring = np.stack([np.arange(1, V - 1, dtype=np.int32), np.arange(2, V, dtype=np.int32)], 1)
+    edges = np.ascontiguousarray(np.concatenate([hub, ring]).astype(np.int32))
+    g = {"pos": pos, "edges": edges, "data_term": rng.uniform(0.1, 2.0, V).astype(np.float32),
+         "data_weight": np.ones(V, np.float32)}
+    alpha, beta = oracle.edge_weights(edges, pos)
+    want = synth.init_state(g, alpha, beta)
+    oracle.pd_run(want, oracle.pd_default_params(), 20)
+    gpu_ctx.graph_init(4, pos, g["data_term"], edges)
+    with pytest.raises(_lib.FlameB200Error):
+        gpu_ctx.pd_run(_lib.default_pd_params(), 1, slot0=4, mode=_lib.PD_RESIDENT)
+    gpu_ctx.graph_init(4, pos, g["data_term"], edges)
+    gpu_ctx.pd_run(_lib.default_pd_params(), 20, slot0=4, mode=_lib.PD_AUTO)
+    _assert_bit_equal(gpu_ctx.graph_download(4, V, edges.shape[0]), want, STATE)

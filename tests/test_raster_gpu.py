@@ -207,3 +207,74 @@ def test_random_triangle_soups(oracle):
             got = ctx.interpolate_mesh(0, c["tris"], c["pos"], c["vals"], H, W, c["vv"], c["tv"],
                                        None if base is None else base.copy())
             _assert_same_image(got, want)
+
+
+def test_limits_are_guarded(gpu_ctx):
+    """The limits the kernels are built around fail loudly at the boundary instead of silently misbehaving:
+    image sides above 2896 px (the reference's fp32 edge functions stop being exact), frame slots beyond 64,
+    search parameters that allow more SSD positions than a warp holds, non-finite feature records."""
+    g = synth.config_graph("A")
+    gpu_ctx.graph_init(0, g["pos"], g["data_term"], g["edges"])
+    gpu_ctx.mesh_bind(0, g["tris"], 2896, 2896)          # the largest image still exact
+    with pytest.raises(_lib.FlameB200Error):
+        gpu_ctx.mesh_bind(0, g["tris"], 480, 2897)
+    with pytest.raises(_lib.FlameB200Error):
+        gpu_ctx.mesh_bind(0, g["tris"], 2897, 640)
+    gpu_ctx.mesh_bind(0, g["tris"], g["H"], g["W"])
+    W, H, _, _ = synth.CONFIGS["A"]
+    K, Kinv, frames = synth.make_stereo_pair(W, H)
+    gpu_ctx.set_camera(W, H, K, Kinv)
+    fr = frames[0]
+    gpu_ctx.frame_upload(63, fr["img_pad"], fr["gradx_pad"], fr["grady_pad"], synth.PAD, fr["pose"])  # last slot
+    with pytest.raises(_lib.FlameB200Error):
+        gpu_ctx.frame_upload(64, fr["img_pad"], fr["gradx_pad"], fr["grady_pad"], synth.PAD, fr["pose"])
+    gpu_ctx.frame_upload(0, fr["img_pad"], fr["gradx_pad"], fr["grady_pad"], synth.PAD, fr["pose"])
+    gpu_ctx.frame_upload(1, frames[1]["img_pad"], frames[1]["gradx_pad"], frames[1]["grady_pad"], synth.PAD,
+                         frames[1]["pose"])
+    feats = synth.make_features(g["pos"], W, H)
+    tp = _lib.default_track_params()
+    tp.fparams.epilength_max = 124.0      # 124 / 1 + 4 = 128 positions: still fits
+    gpu_ctx.update_feature_idepths(tp, 1, 0, feats.copy())
+    tp.fparams.epilength_max = 125.0
+    with pytest.raises(_lib.FlameB200Error):
+        gpu_ctx.update_feature_idepths(tp, 1, 0, feats.copy())
+    tp = _lib.default_track_params()
+    bad = feats.copy()
+    bad["x"][3] = np.nan
+    with pytest.raises(_lib.FlameB200Error):
+        gpu_ctx.update_feature_idepths(tp, 1, 0, bad)
+
+
+def test_projection_redirected_into_another_buffer(gpu_ctx, oracle):
+    """flame_b200_mesh_redirect: the projection stores the map (and copies the vertex idepths) straight into a
+    caller-supplied device buffer - here on the same GPU; tests/test_multi_gpu.py does it across GPUs."""
+    import torch
+    g = synth.config_graph("B")
+    H, W, V = g["H"], g["W"], g["pos"].shape[0]
+    gpu_ctx.graph_init(1, g["pos"], g["data_term"], g["edges"])
+    gpu_ctx.mesh_bind(1, g["tris"], H, W)
+    gpu_ctx.pd_run(_lib.default_pd_params(), 20, slot0=1)
+    x = gpu_ctx.graph_download(1, V, g["edges"].shape[0], fields=("x",))["x"]
+    want = oracle.interpolate_mesh(g["tris"], g["pos"], (x * np.float32(0.5)).astype(np.float32), H, W)
+    buf = _lib.DeviceBuffer(0, H * W * 4 + V * 4)
+    try:
+        buf.tensor((H * W + V,)).fill_(-7.0)
+        torch.cuda.synchronize()
+        gpu_ctx.mesh_redirect(1, buf.ptr, buf.ptr + H * W * 4)
+        gpu_ctx.mesh_project(1, 1, 0.5)
+        gpu_ctx.sync()
+        got = buf.tensor((H, W)).cpu().numpy()
+        vals = buf.tensor((V,), H * W * 4).cpu().numpy()
+        gn, wn = np.isnan(got), np.isnan(want)
+        assert np.array_equal(gn, wn) and np.array_equal(got[~gn].view(np.uint32), want[~wn].view(np.uint32))
+        assert np.array_equal(vals.view(np.uint32), (x * np.float32(0.5)).astype(np.float32).view(np.uint32))
+        gpu_ctx.mesh_redirect(1, None, None)   # back to the slot's own buffer
+        gpu_ctx.mesh_project(1, 1, 0.5)
+        out = np.empty((H, W), np.float32)
+        gpu_ctx.mesh_download(1, out)
+        gpu_ctx.sync()
+        assert np.array_equal(np.isnan(out), wn) and np.array_equal(out[~wn].view(np.uint32), want[~wn].view(np.uint32))
+    finally:
+        gpu_ctx.mesh_redirect(1, None, None)
+        gpu_ctx.sync()
+        buf.close()
