@@ -113,7 +113,8 @@ struct flame_b200_ctx {
   std::vector<cudaEvent_t> ev_pool;
   // host scratch for graph prep
   std::vector<uint32_t> keys;
-  std::vector<int> degv, srcdeg, order, koff_tmp, pre_deg, pre_src;
+  std::vector<int> degv, srcdeg, order, koff_tmp, pre_deg, pre_src, sort_tmp;
+  int own_cnt[FB_RESIDENT_MAX_DEG + 2];
   int pd_pref = 0;                   // FLAME_B200_PREF_*: how prep_plan sizes the frame clusters
   int busy_sms[17] = {0};            // [C] = C x clusters of C CTAs the device keeps resident (full shared memory)
   // frame pipeline: frames submitted to consecutive slots are solved as one wave (wave_flush)
@@ -303,8 +304,31 @@ static void prep_fill(flame_b200_ctx* c, int V, int E, const int32_t* edges, con
     }
     chunk_base[ch + 1] = chunk_base[ch] + ko[max_deg];
     for (int d = 0; d <= max_deg; ++d) cnt[d] = start[d];  // write cursors
+    if (!pr.plan.cluster) {
+      for (int i = a; i < b; ++i) {
+        const int o = morton[i];
+        vperm[a + cnt[c->degv[o]]++] = o;
+      }
+      continue;
+    }
+    // resident solver: secondary key = number of owned (source-role) edges, descending, so that the vertices
+    // that have an r-th owned edge form a few contiguous runs (pd.cu deals the edges rank-major). Two stable
+    // counting sorts: by owned count first, by degree second.
+    c->sort_tmp.resize(b - a);
+    int* own_cnt = c->own_cnt;
+    std::fill(own_cnt, own_cnt + FB_RESIDENT_MAX_DEG + 2, 0);
+    for (int i = a; i < b; ++i) own_cnt[c->srcdeg[morton[i]]]++;
+    for (int d = max_deg, run2 = 0; d >= 0; --d) {
+      const int n = own_cnt[d];
+      own_cnt[d] = run2;
+      run2 += n;
+    }
     for (int i = a; i < b; ++i) {
       const int o = morton[i];
+      c->sort_tmp[own_cnt[c->srcdeg[o]]++] = o;
+    }
+    for (int i = 0; i < b - a; ++i) {
+      const int o = c->sort_tmp[i];
       vperm[a + cnt[c->degv[o]]++] = o;
     }
   }

@@ -562,11 +562,21 @@ __device__ __forceinline__ void cluster_arrive() {
 __device__ __forceinline__ void cluster_wait() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// Contribution records double as load-phase scratch (owned-edge list + per-vertex scan): the region
-// holds max(maxInc records, that scratch).
-__host__ __device__ inline int resident_p4_records(int maxInc, int maxEdges, int Vc) {
-  const int scratch = (maxEdges + Vc + 3) / 4;
-  return maxInc > scratch ? maxInc : scratch;
+// Shared-memory slots of the contribution records. In global memory incidence k of the chunk's i-th vertex
+// is slot koff[k] + i; in shared memory the k-blocks start at multiples of FB_KPAD records (kpad[k] + i), so
+// that the 16-byte bank group of a vertex's records is its index mod 8 for EVERY k: a quarter-warp working on
+// eight consecutive vertices never conflicts, whichever incidences it touches.
+#define FB_KPAD 8
+__host__ __device__ inline int kpad_round(int n) { return (n + FB_KPAD - 1) & ~(FB_KPAD - 1); }
+__host__ __device__ inline int resident_inc_records(int maxInc, int max_deg) {
+  return ((maxInc + FB_KPAD * (max_deg + 1)) + 1) & ~1;
+}
+// The records double as load-phase scratch (two owned-edge lists, the per-vertex scan, two small rank
+// tables): the region holds max(records, that scratch).
+__host__ __device__ inline int resident_p4_records(int maxInc, int maxEdges, int Vc, int max_deg) {
+  const int scratch = (2 * maxEdges + Vc + 1 + 2 * (max_deg + 2) + 3) / 4;
+  const int rec = resident_inc_records(maxInc, max_deg);
+  return rec > scratch ? rec : scratch;
 }
 
 template <int MAXT, int SPT, int VPT, int PD_MLP>
@@ -581,18 +591,22 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   float4* s_bar = reinterpret_cast<float4*>(smem);  // x_bar, w1_bar, w2_bar of the chunk's vertices
   float4* s_p4 = s_bar + a.Vc;                      // per incidence slot: (sx, t1, t2, u1)
-  float4* s_s = s_p4 + resident_p4_records(a.maxInc, a.maxEdges, a.Vc);  // per owned edge: (alpha, beta, dx, dy)
-  float* s_p1 = reinterpret_cast<float*>(s_s + a.maxEdges);             // per incidence slot: u2
-  int* s_koff = reinterpret_cast<int*>(s_p1 + ((a.maxInc + 1) & ~1));     // a.max_deg + 1 (8-byte aligned: read in pairs)
-  int* s_cnt = s_koff + a.max_deg + 1;                                  // 1
-  unsigned int* s_list = reinterpret_cast<unsigned int*>(s_p4);  // load phase only: owned edges (vertex << 16 | slot)
-  int* s_scan = reinterpret_cast<int*>(s_list + a.maxEdges);     // load phase only: first owned edge of every vertex
+  float4* s_s = s_p4 + resident_p4_records(a.maxInc, a.maxEdges, a.Vc, a.max_deg);  // per owned edge: (alpha, beta, dx, dy)
+  float* s_p1 = reinterpret_cast<float*>(s_s + a.maxEdges);                          // per incidence slot: u2
+  int* s_kpad = reinterpret_cast<int*>(s_p1 + resident_inc_records(a.maxInc, a.max_deg));  // a.max_deg + 1 (+1 pad: read in pairs)
+  int* s_koff = s_kpad + ((a.max_deg + 2) & ~1);                                     // a.max_deg + 1
+  int* s_cnt = s_koff + a.max_deg + 1;                                               // 1
+  // load phase only (aliases of the records):
+  unsigned int* s_list = reinterpret_cast<unsigned int*>(s_p4);  // owned edges vertex by vertex (vertex << 16 | k)
+  int* s_scan = reinterpret_cast<int*>(s_list + a.maxEdges);     // first owned edge of every vertex (a.Vc + 1)
+  unsigned int* s_rank = reinterpret_cast<unsigned int*>(s_scan + a.Vc + 1);  // the same edges, rank-major
+  int* s_hist = reinterpret_cast<int*>(s_rank + a.maxEdges);     // #vertices per owned-edge count (max_deg + 2)
+  int* s_roff = s_hist + a.max_deg + 2;                          // first list position of every rank (max_deg + 2)
 
   const bool have = c < g.n_chunks;
   const int v0 = c * Vc;
   const int nv = have ? min(Vc, g.V - v0) : 0;
   const int base = have ? g.chunk_base[c] : 0;
-  const int ni = have ? g.chunk_base[c + 1] - base : 0;
   const uint32_t bar_addr = smem_u32(s_bar);
   const uint32_t p4_addr = smem_u32(s_p4);
   const float neg0 = __int_as_float(0x80000000);
@@ -600,7 +614,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   // ---- load ----
   if (have)
     for (int k = tid; k <= g.max_deg; k += MAXT) s_koff[k] = koff_row(g, c)[k];
+  for (int k = tid; k < g.max_deg + 2; k += MAXT) s_hist[k] = 0;
   __syncthreads();
+  if (tid == 0) {
+    int tot = 0;
+    for (int k = 0; k <= g.max_deg; ++k) {
+      s_kpad[k] = tot;
+      if (k < g.max_deg) tot += have ? kpad_round(s_koff[k + 1] - s_koff[k]) : 0;
+    }
+  }
   // vertex registers: thread t owns vertices t, t + MAXT, ... of the chunk (nv <= MAXT * VPT)
   float x[VPT], w1[VPT], w2[VPT], data[VPT], wt[VPT];
   int deg[VPT];
@@ -617,21 +639,21 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
       s_bar[i] = g.vbar[v0 + i];
     }
   }
-  // Owned edges = source-role incidence slots of this chunk. CUT edges (target in another CTA: their x_bar read
-  // is a DSMEM round trip) come first, so that they spread over the first ceil(ncut / MAXT) rounds of ALL
-  // threads instead of piling up in the warps that own the boundary vertices; within both groups the edges
-  // are listed vertex by vertex (threads of a warp read the same / adjacent source records).
-  // Per-vertex counts -> exclusive scan of (local << 16 | cut) by warp 0 -> fill.
+  // Owned edges = source-role incidences of this chunk's vertices. They are dealt to the threads RANK-MAJOR:
+  // first every vertex's first owned edge (in vertex order), then every vertex's second one, ... The host
+  // orders a chunk by (degree, owned count) descending, so the vertices that have an r-th owned edge are a
+  // few contiguous runs and a quarter-warp's eight edges have (almost always) eight consecutive sources:
+  // their x_bar reads and their source-record stores fall into eight different 16-byte bank groups (FB_KPAD).
+  // Cut edges are wherever their source vertex falls - spread over the chunk by the same sort.
+  //   per-vertex counts + histogram -> exclusive scan (warp 0) -> vertex-major list -> rank-major list
 #pragma unroll
   for (int v = 0; v < VPT; ++v) {
     const int i = tid + v * MAXT;
     if (i < nv) {
       int cnt = 0;
-      for (int k = 0; k < deg[v]; ++k) {
-        const int ent = g.inc_nbr[base + s_koff[k] + i];
-        if ((ent & 1) == 0) cnt += ((ent >> 1) / Vc != c) ? 1 : (1 << 16);
-      }
+      for (int k = 0; k < deg[v]; ++k) cnt += (g.inc_nbr[base + s_koff[k] + i] & 1) ^ 1;
       s_scan[i] = cnt;
+      atomicAdd(&s_hist[cnt], 1);
     }
   }
   __syncthreads();
@@ -649,30 +671,50 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
       if (i < nv) s_scan[i] = run + inc - d0;
       run += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (tid == 0) *s_cnt = run;
-  }
-  __syncthreads();
-  const int ncut = *s_cnt & 0xFFFF;
-  const int ne = ncut + (*s_cnt >> 16);  // <= MAXT * SPT (planner)
-#pragma unroll
-  for (int v = 0; v < VPT; ++v) {
-    const int i = tid + v * MAXT;
-    if (i < nv) {
-      int at_cut = s_scan[i] & 0xFFFF, at_loc = ncut + (s_scan[i] >> 16);
-      for (int k = 0; k < deg[v]; ++k) {
-        const int slot = s_koff[k] + i;
-        const int ent = g.inc_nbr[base + slot];
-        if ((ent & 1) == 0) {
-          const unsigned int rec = ((unsigned int)i << 16) | (unsigned int)slot;
-          if ((ent >> 1) / Vc != c) s_list[at_cut++] = rec;
-          else s_list[at_loc++] = rec;
-        }
+    if (tid == 0) {
+      s_scan[nv] = run;
+      *s_cnt = run;
+      // s_roff[r] = #owned edges of rank < r = sum over r' < r of #vertices with more than r' owned edges
+      int more = 0;
+      for (int r = g.max_deg; r >= 0; --r) {  // s_hist[r] := #vertices with > r owned edges
+        const int h = s_hist[r];
+        s_hist[r] = more;
+        more += h;
+      }
+      int at = 0;
+      for (int r = 0; r <= g.max_deg; ++r) {
+        s_roff[r] = at;
+        at += s_hist[r];
       }
     }
   }
   __syncthreads();
+  const int ne = *s_cnt;  // <= MAXT * SPT (planner)
+#pragma unroll
+  for (int v = 0; v < VPT; ++v) {
+    const int i = tid + v * MAXT;
+    if (i < nv) {
+      int at = s_scan[i];
+      for (int k = 0; k < deg[v]; ++k)
+        if ((g.inc_nbr[base + s_koff[k] + i] & 1) == 0) s_list[at++] = ((unsigned int)i << 16) | (unsigned int)k;
+    }
+  }
+  __syncthreads();
+  for (int r = tid >> 5; r <= g.max_deg && s_hist[r] > 0; r += MAXT >> 5) {  // one warp per rank
+    int run = s_roff[r];
+    const unsigned int lt = (1u << (tid & 31)) - 1u;
+    for (int b = 0; b < nv; b += 32) {
+      const int i = b + (tid & 31);
+      const int first = (i < nv) ? s_scan[i] : 0;
+      const bool act = (i < nv) && (s_scan[i + 1] - first > r);
+      const unsigned int m = __ballot_sync(0xffffffffu, act);
+      if (act) s_rank[run + __popc(m & lt)] = s_list[first + r];
+      run += __popc(m);
+    }
+  }
+  __syncthreads();
   float q1[SPT], q2[SPT], q3[SPT];
-  uint32_t src[SPT];      // (local index of the source vertex << 16) | local incidence slot of the source
+  uint32_t src[SPT];      // (local index of the source vertex << 16) | shared-memory record slot of the source
   uint32_t dst_bar[SPT];  // address of the target's x_bar record: shared::cta, or shared::cluster | 1 if remote
   uint32_t dst_p4[SPT];   // address of the target endpoint's p4 record (same address space as dst_bar)
 #pragma unroll
@@ -683,8 +725,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
     dst_bar[u] = bar_addr;
     dst_p4[u] = p4_addr;
     if (j < ne) {
-      src[u] = s_list[j];
-      const int slot = (int)(src[u] & 0xFFFFu);
+      const unsigned int rec = s_rank[j];
+      const int i = (int)(rec >> 16), k = (int)(rec & 0xFFFFu);
+      const int slot = s_koff[k] + i;  // global slot (relative to the chunk's base)
+      src[u] = (rec & 0xFFFF0000u) | (unsigned int)(s_kpad[k] + i);
       const float4 q = g.inc_q[base + slot];
       q1[u] = q.x; q2[u] = q.y; q3[u] = q.z;
       s_s[j] = g.inc_s[base + slot];
@@ -693,15 +737,31 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
       // bit 0 of dst_bar = "target lives in another CTA": only those go through the DSMEM path
       // (ld/st.shared::cluster is several times slower than ld/st.shared even for the own CTA)
       const bool remote = (oc != c);
-      const uint32_t tb = bar_addr + (uint32_t)(nbr - oc * Vc) * 16u;
-      const int tslot = g.edge_slot[2 * g.inc_edge[base + slot] + 1];
-      const uint32_t tp = p4_addr + (uint32_t)(tslot - g.chunk_base[oc]) * 16u;
+      const int ti = nbr - oc * Vc;
+      const uint32_t tb = bar_addr + (uint32_t)ti * 16u;
+      // the target's record: its global slot is koff_oc[k2] + ti -> shared-memory slot kpad_oc[k2] + ti
+      const int tl = g.edge_slot[2 * g.inc_edge[base + slot] + 1] - g.chunk_base[oc] - ti;  // = koff_oc[k2]
+      int tpad = 0;
+      if (!remote) {
+        int k2 = 0;
+        while (s_koff[k2] != tl) ++k2;
+        tpad = s_kpad[k2];
+      } else {
+        const int* row = koff_row(g, oc);
+        int prev = 0;
+        for (int k2 = 0; prev != tl; ++k2) {
+          const int nxt = row[k2 + 1];
+          tpad += kpad_round(nxt - prev);
+          prev = nxt;
+        }
+      }
+      const uint32_t tp = p4_addr + (uint32_t)(tpad + ti) * 16u;
       dst_bar[u] = remote ? (mapa(tb, (uint32_t)oc) | 1u) : tb;
       dst_p4[u] = remote ? mapa(tp, (uint32_t)oc) : tp;
     }
   }
-  __syncthreads();  // s_list / s_scan (aliases of s_p4) are dead from here on
-  for (int slot = tid; slot < ni; slot += MAXT)
+  __syncthreads();  // the load-phase lists (aliases of s_p4) are dead from here on
+  for (int slot = tid; slot < s_kpad[g.max_deg]; slot += MAXT)
     s_p1[slot] = neg0;  // target slots keep -0.0f forever; source slots are rewritten every iteration
   cluster.sync();
 
@@ -753,7 +813,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
     vp4[v] = p4_addr + (uint32_t)(tid + v * MAXT) * 16u;
     vp1[v] = smem_u32(s_p1) + (uint32_t)(tid + v * MAXT) * 4u;
   }
-  const uint32_t koff_addr = smem_u32(s_koff);
+  const uint32_t koff_addr = smem_u32(s_kpad);
   auto phase_b = [&](const bool last) {
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
@@ -785,7 +845,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
           ww2 = add(ww2, b1);
         }
         if (k < d) {
-          const uint32_t ko0 = (uint32_t)s_koff[k];
+          const uint32_t ko0 = (uint32_t)s_kpad[k];
           const float4 a4 = ld_shared_f4(vp4[v] + ko0 * 16u);
           float a1;
           asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a1) : "r"(vp1[v] + ko0 * 4u));
@@ -828,7 +888,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   for (int u = 0; u < SPT; ++u) {
     const int j = tid + u * MAXT;
     if (j < ne) {
-      const int sslot = base + (int)(src[u] & 0xFFFFu);
+      const int ps = (int)(src[u] & 0xFFFFu) - (int)(src[u] >> 16);  // = kpad[k] of the source incidence
+      int k = 0;
+      while (s_kpad[k] != ps) ++k;
+      const int sslot = base + s_koff[k] + (int)(src[u] >> 16);
       const int tslot = g.edge_slot[2 * g.inc_edge[sslot] + 1];
       g.inc_q[sslot] = make_float4(q1[u], q2[u], q3[u], __int_as_float(g.inc_nbr[sslot]));
       g.inc_q[tslot] = make_float4(q1[u], q2[u], q3[u], __int_as_float(g.inc_nbr[tslot]));
@@ -837,8 +900,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
 }
 
 size_t pd_resident_smem(int Vc, int maxInc, int maxEdges, int max_deg) {
-  return (size_t)Vc * 16 + (size_t)resident_p4_records(maxInc, maxEdges, Vc) * 16 + (size_t)maxEdges * 16 +
-         (size_t)((maxInc + 1) & ~1) * 4 + (size_t)(max_deg + 2) * 4 + 128;
+  return (size_t)Vc * 16 + (size_t)resident_p4_records(maxInc, maxEdges, Vc, max_deg) * 16 + (size_t)maxEdges * 16 +
+         (size_t)resident_inc_records(maxInc, max_deg) * 4 + (size_t)(2 * (max_deg + 2) + 2) * 4 + 128;
 }
 
 // The register budgets the kernel is built for: (threads, owned edges per thread, vertices per thread).
