@@ -279,6 +279,16 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def _prefer_node(node):
+    """set_mempolicy(MPOL_PREFERRED, {node}) for this process (x86-64 syscall 238); returns what happened."""
+    import ctypes
+    libc = ctypes.CDLL(None, use_errno=True)
+    mask = (ctypes.c_ulong * 2)(0, 0)
+    mask[node // 64] = 1 << (node % 64)
+    rc = libc.syscall(238, 1, mask, 129)
+    return "preferred node %d" % node if rc == 0 else "refused (errno %d)" % ctypes.get_errno()
+
+
 def _pin_to_gpu_node(index):
     """Run this rank on the CPUs of its GPU's NUMA node (nvml's ideal CPU affinity of the device): host
     threads and the pinned buffers they allocate (first touch) then sit next to the GPU's PCIe root.
@@ -288,6 +298,18 @@ def _pin_to_gpu_node(index):
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        # the GPU's own NUMA node (sysfs): the page-locked result ring is allocated there even when the
+        # job's CPU mask does not reach that socket (set_mempolicy(MPOL_PREFERRED); a no-op where the
+        # container's memory nodes exclude it)
+        try:
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            with open("/sys/bus/pci/devices/%s/numa_node" % bus[-12:].lower()) as f:
+                info["gpu_numa_node"] = int(f.read())
+            if info["gpu_numa_node"] >= 0 and os.environ.get("FLAME_B200_MEMPOLICY", "gpu") == "gpu":
+                info["mempolicy"] = _prefer_node(info["gpu_numa_node"])
+        except Exception:
+            pass
         n = os.cpu_count()
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
         allowed = os.sched_getaffinity(0)
@@ -324,10 +346,12 @@ def run_ours(args, rank, world, local_rank):
     if args.e2e_only:
         def barrier0():
             torch.cuda.synchronize(dev)
+            if dist is not None:
+                dist.barrier()
         fr, _ = _frames(N_DISTINCT)
         e = run_e2e(args, local_rank, fr, (W, H, V, iters), barrier0)
-        print(json.dumps({"e2e_frames_per_s": e["frames"] / e["seconds"], "threads": e["threads"],
-                          "in_flight": e["in_flight"], "breakdown": e["breakdown"]}))
+        print(json.dumps({"rank": rank, "e2e_frames_per_s": e["frames"] / e["seconds"], "threads": e["threads"],
+                          "in_flight": e["in_flight"], "breakdown": e["breakdown"], "host": numa}))
         return
     # ---- how many frames the device solves concurrently (one thread-block cluster per frame) ----
     pref = _lib.PREF_LATENCY if args.layout == "wide" else _lib.PREF_THROUGHPUT

@@ -567,6 +567,7 @@ __device__ __forceinline__ void cluster_wait() {
 // that the 16-byte bank group of a vertex's records is its index mod 8 for EVERY k: a quarter-warp working on
 // eight consecutive vertices never conflicts, whichever incidences it touches.
 #define FB_KPAD 8
+#define FB_DEAL_INTS (72 + 64 + 64 + 72 + 72)  // dealing tables: supply, demand, list offsets, hole / overflow bases
 __host__ __device__ inline int kpad_round(int n) { return (n + FB_KPAD - 1) & ~(FB_KPAD - 1); }
 __host__ __device__ inline int resident_inc_records(int maxInc, int max_deg) {
   return ((maxInc + FB_KPAD * (max_deg + 1)) + 1) & ~1;
@@ -574,7 +575,7 @@ __host__ __device__ inline int resident_inc_records(int maxInc, int max_deg) {
 // The records double as load-phase scratch (two owned-edge lists, the per-vertex scan, two small rank
 // tables): the region holds max(records, that scratch).
 __host__ __device__ inline int resident_p4_records(int maxInc, int maxEdges, int Vc, int max_deg) {
-  const int scratch = (2 * maxEdges + Vc + 1 + 2 * (max_deg + 2) + 3) / 4;
+  const int scratch = (2 * maxEdges + Vc + 1 + 2 * (max_deg + 2) + maxEdges + (maxEdges + 1) / 2 + FB_DEAL_INTS + 3) / 4;
   const int rec = resident_inc_records(maxInc, max_deg);
   return rec > scratch ? rec : scratch;
 }
@@ -602,6 +603,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   unsigned int* s_rank = reinterpret_cast<unsigned int*>(s_scan + a.Vc + 1);  // the same edges, rank-major
   int* s_hist = reinterpret_cast<int*>(s_rank + a.maxEdges);     // #vertices per owned-edge count (max_deg + 2)
   int* s_roff = s_hist + a.max_deg + 2;                          // first list position of every rank (max_deg + 2)
+  int* s_tmp = s_roff + a.max_deg + 2;                           // per list position: (target group, supply index, demand index)
+  int* s_sup = s_tmp + a.maxEdges;                               // [8][9] edges per (source group, target group | remote)
+  int* s_dem = s_sup + 72;                                       // [8][8] positions per (source group, wanted target group)
+  int* s_off = s_dem + 64;                                       // [8][8] start of every position list
+  int* s_hb = s_off + 64;                                        // [8][9] first hole index of every position list
+  int* s_ob = s_hb + 72;                                         // [8][9] first overflow index of every edge queue
+  unsigned short* s_pos = reinterpret_cast<unsigned short*>(s_ob + 72);  // position lists (a.maxEdges)
 
   const bool have = c < g.n_chunks;
   const int v0 = c * Vc;
@@ -615,6 +623,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   if (have)
     for (int k = tid; k <= g.max_deg; k += MAXT) s_koff[k] = koff_row(g, c)[k];
   for (int k = tid; k < g.max_deg + 2; k += MAXT) s_hist[k] = 0;
+  for (int k = tid; k < 72 + 64; k += MAXT) s_sup[k] = 0;  // s_sup and s_dem are adjacent
   __syncthreads();
   if (tid == 0) {
     int tot = 0;
@@ -713,6 +722,70 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
     }
   }
   __syncthreads();
+  // Balanced dealing. A warp's 16-byte shared-memory access costs max(4, most addresses in one 16-byte bank
+  // group) wavefronts. Sources: position p of the rank-major list keeps the source GROUP (vertex index mod 8)
+  // it has - consecutive vertices, so every warp-sized block holds each group 4 times. Targets: position p
+  // WANTS target group (lane + 2 * (lane / 8) + block parity) mod 8 - each group 4 times per block, and over
+  // two blocks every source group asks for all eight target groups. Edges of a source group are matched to the
+  // positions of that group that want their target group (any order); what does not match - surplus edges and
+  // the cut edges, whose targets are in another SM - fills the positions left over. Only the assignment of
+  // edges to threads changes, neither the arithmetic nor the accumulation order (that is by record slot).
+  for (int pp = tid; pp < ne; pp += MAXT) {
+    const unsigned int rec = s_rank[pp];
+    const int i = (int)(rec >> 16), k = (int)(rec & 0xFFFFu);
+    const int nbr = g.inc_nbr[base + s_koff[k] + i] >> 1;
+    const int ag = i & 7;
+    const int tg = (nbr / Vc == c) ? ((nbr - c * Vc) & 7) : 8;
+    const int lane = pp & 31;
+    const int want = (lane + 2 * (lane >> 3) + ((pp >> 5) & 1)) & 7;
+    const int m = atomicAdd(&s_sup[ag * 9 + tg], 1);
+    const int q = atomicAdd(&s_dem[ag * 8 + want], 1);
+    s_tmp[pp] = (tg << 28) | (m << 14) | q;
+  }
+  __syncthreads();
+  if (tid < 8) {
+    int hb = 0, ob = 0;
+    for (int d = 0; d < 8; ++d) {
+      const int dem = s_dem[tid * 8 + d], sup = s_sup[tid * 9 + d];
+      s_hb[tid * 9 + d] = hb;
+      s_ob[tid * 9 + d] = ob;
+      hb += max(0, dem - sup);
+      ob += max(0, sup - dem);
+    }
+    s_hb[tid * 9 + 8] = hb;
+    s_ob[tid * 9 + 8] = ob;
+  } else if (tid == 32) {
+    int at = 0;
+    for (int kk = 0; kk < 64; ++kk) {
+      s_off[kk] = at;
+      at += s_dem[kk];
+    }
+  }
+  __syncthreads();
+  for (int pp = tid; pp < ne; pp += MAXT) {
+    const int ag = (int)(s_rank[pp] >> 16) & 7;
+    const int lane = pp & 31;
+    const int want = (lane + 2 * (lane >> 3) + ((pp >> 5) & 1)) & 7;
+    s_pos[s_off[ag * 8 + want] + (s_tmp[pp] & 0x3FFF)] = (unsigned short)pp;
+  }
+  __syncthreads();
+  for (int pp = tid; pp < ne; pp += MAXT) {
+    const unsigned int rec = s_rank[pp];
+    const int ag = (int)(rec >> 16) & 7;
+    const int tg = (int)((unsigned int)s_tmp[pp] >> 28), m = (s_tmp[pp] >> 14) & 0x3FFF;
+    const int dem = tg < 8 ? s_dem[ag * 8 + tg] : 0;
+    int at;
+    if (m < dem) {
+      at = s_off[ag * 8 + tg] + m;
+    } else {
+      const int o = s_ob[ag * 9 + tg] + (m - dem);  // index among this source group's unmatched edges
+      int d = 0;
+      while (d < 7 && s_hb[ag * 9 + d + 1] <= o) ++d;  // the list whose holes contain hole number o
+      at = s_off[ag * 8 + d] + s_sup[ag * 9 + d] + (o - s_hb[ag * 9 + d]);
+    }
+    s_list[s_pos[at]] = rec;
+  }
+  __syncthreads();
   float q1[SPT], q2[SPT], q3[SPT];
   uint32_t src[SPT];      // (local index of the source vertex << 16) | shared-memory record slot of the source
   uint32_t dst_bar[SPT];  // address of the target's x_bar record: shared::cta, or shared::cluster | 1 if remote
@@ -725,7 +798,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
     dst_bar[u] = bar_addr;
     dst_p4[u] = p4_addr;
     if (j < ne) {
-      const unsigned int rec = s_rank[j];
+      const unsigned int rec = s_list[j];
       const int i = (int)(rec >> 16), k = (int)(rec & 0xFFFFu);
       const int slot = s_koff[k] + i;  // global slot (relative to the chunk's base)
       src[u] = (rec & 0xFFFF0000u) | (unsigned int)(s_kpad[k] + i);
