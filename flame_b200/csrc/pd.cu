@@ -580,6 +580,24 @@ __host__ __device__ inline int resident_p4_records(int maxInc, int maxEdges, int
   return rec > scratch ? rec : scratch;
 }
 
+#ifdef FB_PROFILE_LOAD
+__device__ unsigned long long fb_dbg[32];
+#define FB_STAMP(n)                                                                  \
+  do {                                                                               \
+    __syncthreads();                                                                 \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                       \
+      unsigned long long t_;                                                         \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                         \
+      fb_dbg[n] = t_;                                                                \
+    }                                                                                \
+  } while (0)
+extern "C" int flame_b200_debug_stamps(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, fb_dbg, sizeof(fb_dbg));
+}
+#else
+#define FB_STAMP(n)
+#endif
+
 template <int MAXT, int SPT, int VPT, int PD_MLP>
 __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -619,6 +637,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   const uint32_t p4_addr = smem_u32(s_p4);
   const float neg0 = __int_as_float(0x80000000);
 
+  FB_STAMP(0);
   // ---- load ----
   if (have)
     for (int k = tid; k <= g.max_deg; k += MAXT) s_koff[k] = koff_row(g, c)[k];
@@ -648,6 +667,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
       s_bar[i] = g.vbar[v0 + i];
     }
   }
+  FB_STAMP(1);
   // Owned edges = source-role incidences of this chunk's vertices. They are dealt to the threads RANK-MAJOR:
   // first every vertex's first owned edge (in vertex order), then every vertex's second one, ... The host
   // orders a chunk by (degree, owned count) descending, so the vertices that have an r-th owned edge are a
@@ -699,6 +719,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   }
   __syncthreads();
   const int ne = *s_cnt;  // <= MAXT * SPT (planner)
+  FB_STAMP(2);
 #pragma unroll
   for (int v = 0; v < VPT; ++v) {
     const int i = tid + v * MAXT;
@@ -709,6 +730,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
     }
   }
   __syncthreads();
+  FB_STAMP(3);
   for (int r = tid >> 5; r <= g.max_deg && s_hist[r] > 0; r += MAXT >> 5) {  // one warp per rank
     int run = s_roff[r];
     const unsigned int lt = (1u << (tid & 31)) - 1u;
@@ -722,6 +744,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
     }
   }
   __syncthreads();
+  FB_STAMP(4);
   // Balanced dealing. A warp's 16-byte shared-memory access costs max(4, most addresses in one 16-byte bank
   // group) wavefronts. Sources: position p of the rank-major list keeps the source GROUP (vertex index mod 8)
   // it has - consecutive vertices, so every warp-sized block holds each group 4 times. Targets: position p
@@ -786,10 +809,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
     s_list[s_pos[at]] = rec;
   }
   __syncthreads();
+  FB_STAMP(5);
   float q1[SPT], q2[SPT], q3[SPT];
   uint32_t src[SPT];      // (local index of the source vertex << 16) | shared-memory record slot of the source
   uint32_t dst_bar[SPT];  // address of the target's x_bar record: shared::cta, or shared::cluster | 1 if remote
   uint32_t dst_p4[SPT];   // address of the target endpoint's p4 record (same address space as dst_bar)
+  // staged so that the dependent global loads of all SPT edges overlap: (q, s, edge id) -> target slot -> rest
+  int e_id[SPT];
 #pragma unroll
   for (int u = 0; u < SPT; ++u) {
     const int j = tid + u * MAXT;
@@ -797,6 +823,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
     src[u] = 0;
     dst_bar[u] = bar_addr;
     dst_p4[u] = p4_addr;
+    e_id[u] = 0;
     if (j < ne) {
       const unsigned int rec = s_list[j];
       const int i = (int)(rec >> 16), k = (int)(rec & 0xFFFFu);
@@ -804,8 +831,19 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
       src[u] = (rec & 0xFFFF0000u) | (unsigned int)(s_kpad[k] + i);
       const float4 q = g.inc_q[base + slot];
       q1[u] = q.x; q2[u] = q.y; q3[u] = q.z;
+      dst_bar[u] = (uint32_t)(__float_as_int(q.w) >> 1);  // the target vertex, until the last stage
+      e_id[u] = g.inc_edge[base + slot];
       s_s[j] = g.inc_s[base + slot];
-      const int nbr = __float_as_int(q.w) >> 1;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < SPT; ++u)
+    if (tid + u * MAXT < ne) e_id[u] = g.edge_slot[2 * e_id[u] + 1];  // global slot of the target's incidence
+#pragma unroll
+  for (int u = 0; u < SPT; ++u) {
+    const int j = tid + u * MAXT;
+    if (j < ne) {
+      const int nbr = (int)dst_bar[u];
       const int oc = nbr / Vc;  // the target vertex lives in chunk oc, and so do its slots
       // bit 0 of dst_bar = "target lives in another CTA": only those go through the DSMEM path
       // (ld/st.shared::cluster is several times slower than ld/st.shared even for the own CTA)
@@ -813,7 +851,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
       const int ti = nbr - oc * Vc;
       const uint32_t tb = bar_addr + (uint32_t)ti * 16u;
       // the target's record: its global slot is koff_oc[k2] + ti -> shared-memory slot kpad_oc[k2] + ti
-      const int tl = g.edge_slot[2 * g.inc_edge[base + slot] + 1] - g.chunk_base[oc] - ti;  // = koff_oc[k2]
+      const int tl = e_id[u] - g.chunk_base[oc] - ti;  // = koff_oc[k2]
       int tpad = 0;
       if (!remote) {
         int k2 = 0;
@@ -833,11 +871,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
       dst_p4[u] = remote ? mapa(tp, (uint32_t)oc) : tp;
     }
   }
+  FB_STAMP(6);
   __syncthreads();  // the load-phase lists (aliases of s_p4) are dead from here on
   for (int slot = tid; slot < s_kpad[g.max_deg]; slot += MAXT)
     s_p1[slot] = neg0;  // target slots keep -0.0f forever; source slots are rewritten every iteration
   cluster.sync();
 
+  FB_STAMP(7);
   const flame_b200_pd_params p = a.p;
 
   // ---- phase A: one dual update per edge, contributions pushed to both endpoints ----
@@ -948,6 +988,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
     cluster_wait();
   }
 
+  FB_STAMP(8);
   // ---- write back (both private copies of every edge's q) ----
 #pragma unroll
   for (int v = 0; v < VPT; ++v) {
@@ -957,19 +998,34 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
       g.vprim[v0 + i] = make_float4(x[v], w1[v], w2[v], data[v]);
     }
   }
+  // (staged like the load: edge ids -> target slots -> stores; the neighbour word of inc_q stays as it is)
+  int wb_s[SPT], wb_t[SPT];
 #pragma unroll
   for (int u = 0; u < SPT; ++u) {
-    const int j = tid + u * MAXT;
-    if (j < ne) {
+    wb_s[u] = wb_t[u] = 0;
+    if (tid + u * MAXT < ne) {
       const int ps = (int)(src[u] & 0xFFFFu) - (int)(src[u] >> 16);  // = kpad[k] of the source incidence
       int k = 0;
       while (s_kpad[k] != ps) ++k;
-      const int sslot = base + s_koff[k] + (int)(src[u] >> 16);
-      const int tslot = g.edge_slot[2 * g.inc_edge[sslot] + 1];
-      g.inc_q[sslot] = make_float4(q1[u], q2[u], q3[u], __int_as_float(g.inc_nbr[sslot]));
-      g.inc_q[tslot] = make_float4(q1[u], q2[u], q3[u], __int_as_float(g.inc_nbr[tslot]));
+      wb_s[u] = base + s_koff[k] + (int)(src[u] >> 16);
+      wb_t[u] = g.inc_edge[wb_s[u]];
     }
   }
+#pragma unroll
+  for (int u = 0; u < SPT; ++u)
+    if (tid + u * MAXT < ne) wb_t[u] = g.edge_slot[2 * wb_t[u] + 1];
+#pragma unroll
+  for (int u = 0; u < SPT; ++u) {
+    if (tid + u * MAXT < ne) {
+      float* qs = reinterpret_cast<float*>(g.inc_q + wb_s[u]);
+      float* qt = reinterpret_cast<float*>(g.inc_q + wb_t[u]);
+      *reinterpret_cast<float2*>(qs) = make_float2(q1[u], q2[u]);
+      qs[2] = q3[u];
+      *reinterpret_cast<float2*>(qt) = make_float2(q1[u], q2[u]);
+      qt[2] = q3[u];
+    }
+  }
+  FB_STAMP(9);
 }
 
 size_t pd_resident_smem(int Vc, int maxInc, int maxEdges, int max_deg) {
