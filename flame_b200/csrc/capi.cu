@@ -1096,6 +1096,10 @@ static int mesh_bind_impl(flame_b200_ctx* c, Slot& s, int32_t T, const int32_t* 
     set_error("mesh: bad arguments");
     return FLAME_B200_EINVAL;
   }
+  if (T >= (1 << 26)) {  // raster.cu packs (triangle id << 5 | chunk position) into one int
+    set_error("mesh: more than 2^26 - 1 triangles");
+    return FLAME_B200_EINVAL;
+  }
   for (int i = 0; i < 3 * T; ++i)
     if (tris[i] < 0 || tris[i] >= V) {
       set_error("mesh: triangle vertex index out of range");

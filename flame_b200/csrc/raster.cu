@@ -103,7 +103,17 @@ __global__ void __launch_bounds__(256) k_tri_static(const MeshDev* __restrict__ 
     if (!wide) {
       const int ntx = tiles_x(m);
       for (int i = sub; i < n; i += 8) {
-        const int tile = (ty0 + i / nx) * ntx + tx0 + i % nx;
+        const int tyi = ty0 + i / nx, txi = tx0 + i % nx;
+        if (!degenerate) {
+          // exact reject: an edge function that is negative at its most favourable corner of the tile is
+          // negative on the whole tile (integers, no rounding) - about a third of the bounding-box tiles
+          const int xl = txi * TILE_W, xh = xl + TILE_W - 1, yl = tyi * TILE_H, yh = yl + TILE_H - 1;
+          const int m1 = s.A1 * (s.A1 >= 0 ? xh : xl) + s.B1 * (s.B1 >= 0 ? yh : yl) + s.C1;
+          const int m2 = s.A2 * (s.A2 >= 0 ? xh : xl) + s.B2 * (s.B2 >= 0 ? yh : yl) + s.C2;
+          const int m3 = s.A3 * (s.A3 >= 0 ? xh : xl) + s.B3 * (s.B3 >= 0 ? yh : yl) + s.C3;
+          if ((m1 | m2 | m3) < 0) continue;
+        }
+        const int tile = tyi * ntx + txi;
         const int at = atomicAdd(&m.tile_cnt[tile], 1);
         if (at < m.bin_cap) m.bins[(size_t)tile * m.bin_cap + at] = t;
         else wide = true;  // bin full: the wide list keeps the triangle reachable from every tile
@@ -118,9 +128,12 @@ __global__ void __launch_bounds__(256) k_tri_static(const MeshDev* __restrict__ 
   if (sub == 0) m.stat[t] = s;
 }
 
-struct StagedTri {  // shared-memory copy of one triangle of the current chunk
-  int A1, B1, C1, A2, B2, C2, A3, B3, C3;
-  int xmin, xend, ymin, ymax, flags, id;
+struct __align__(16) StagedTri {  // shared-memory copy of one triangle of the current chunk (five 16-byte words)
+  int A1, B1, C1, key;  // key = (triangle id << 5) | position in the chunk: the per-pixel maximum names the
+  int A2, B2, C2, flags;  //     winner AND where its copy is staged
+  int A3, B3, C3, xmin;
+  int xend, ymin, ymax, pad;
+  float v1, v2, v3, pad2;  // values at p1, p2, p3
 };
 
 // coverage of sweep position (x, y) by a DEGENERATE triangle: the edge test alone is true on the whole
@@ -144,7 +157,7 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, 10) k_tiles(const MeshDev* __
   const int px = tx * TILE_W + (lane & 3) * 4, py = ty * TILE_H + (lane >> 2);
   __shared__ StagedTri s_all[TILE_WARPS][32];
   StagedTri* s_tri = s_all[warp];
-  int best[4] = {-1, -1, -1, -1};  // per pixel: highest covering triangle so far
+  int best[4] = {-1, -1, -1, -1};  // per pixel: key of the highest covering triangle so far
   const int nbin = m.T > 0 ? min(m.tile_cnt[tile], m.bin_cap) : 0;
   const int nwide = m.T > 0 ? m.counters[0] : 0;
   const int* bin = m.bins + (size_t)tile * m.bin_cap;
@@ -174,7 +187,12 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, 10) k_tiles(const MeshDev* __
       StagedTri& d = s_tri[__popc(mask & ((1u << lane) - 1u))];
       d.A1 = s.A1; d.B1 = s.B1; d.C1 = s.C1; d.A2 = s.A2; d.B2 = s.B2; d.C2 = s.C2;
       d.A3 = s.A3; d.B3 = s.B3; d.C3 = s.C3;
-      d.xmin = s.xmin; d.xend = s.xend; d.ymin = s.ymin; d.ymax = s.ymax; d.flags = s.flags; d.id = t;
+      d.xmin = s.xmin; d.xend = s.xend; d.ymin = s.ymin; d.ymax = s.ymax; d.flags = s.flags;
+      d.key = (t << 5) | __popc(mask & ((1u << lane) - 1u));
+      // values at p1, p2, p3 = reversed triangle order (image_utils.cc:385-391)
+      d.v1 = m.values[m.tris[3 * t + 2]];
+      d.v2 = m.values[m.tris[3 * t + 1]];
+      d.v3 = m.values[m.tris[3 * t]];
     }
     __syncwarp();
     const int n = __popc(mask);
@@ -187,7 +205,7 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, 10) k_tiles(const MeshDev* __
         int w3 = q.A3 * px + q.B3 * py + q.C3;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          best[k] = max(best[k], (w1 | w2 | w3) >= 0 ? q.id : -1);
+          best[k] = max(best[k], (w1 | w2 | w3) >= 0 ? q.key : -1);
           w1 += q.A1; w2 += q.A2; w3 += q.A3;
         }
       } else {
@@ -196,34 +214,41 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, 10) k_tiles(const MeshDev* __
           int w1, w2, w3;
           bool hit = degenerate_covers(q, px + k, py, &w1, &w2, &w3);
           if (!hit && (q.flags & 2)) hit = degenerate_covers(q, px + k + m.cols, py - 1, &w1, &w2, &w3);
-          if (hit) best[k] = max(best[k], q.id);
+          if (hit) best[k] = max(best[k], q.key);
         }
       }
     }
   }
   if (py >= m.rows || px >= m.cols) return;
-  // shade every pixel once with its winner (neighbouring pixels mostly share it: the record stays in L1)
+  // shade every pixel once with its winner. One chunk (the rule): the winner's coefficients and values are
+  // still staged in shared memory, the low key bits say where; several chunks: fetched again by id.
+  const bool staged = nbin + nwide <= 32;
   const float qnan = __uint_as_float(0x7fc00000u);  // quiet_NaN, flame.cc:412
   float out[4];
   bool all = true;
   int last = -1;
-  TriStatic s;
-  float v1 = 0.f, v2 = 0.f, v3 = 0.f;
+  StagedTri s;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     out[k] = qnan;
-    const int t = best[k];
-    if (t < 0) {
+    if (best[k] < 0) {
       all = false;
       continue;
     }
-    if (t != last) {
-      s = m.stat[t];
-      // values at p1, p2, p3 = reversed triangle order (image_utils.cc:385-391)
-      v1 = m.values[m.tris[3 * t + 2]];
-      v2 = m.values[m.tris[3 * t + 1]];
-      v3 = m.values[m.tris[3 * t]];
-      last = t;
+    if (best[k] != last) {
+      last = best[k];
+      if (staged) {
+        s = s_tri[last & 31];
+      } else {
+        const int t = last >> 5;
+        const TriStatic g = m.stat[t];
+        s.A1 = g.A1; s.B1 = g.B1; s.C1 = g.C1; s.A2 = g.A2; s.B2 = g.B2; s.C2 = g.C2;
+        s.A3 = g.A3; s.B3 = g.B3; s.C3 = g.C3;
+        s.xmin = g.xmin; s.xend = g.xend; s.ymin = g.ymin; s.ymax = g.ymax; s.flags = g.flags;
+        s.v1 = m.values[m.tris[3 * t + 2]];
+        s.v2 = m.values[m.tris[3 * t + 1]];
+        s.v3 = m.values[m.tris[3 * t]];
+      }
     }
     int w1, w2, w3;
     if (!(s.flags & 4)) {
@@ -236,7 +261,7 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, 10) k_tiles(const MeshDev* __
     }
     const float f1 = (float)w1, f2 = (float)w2, f3 = (float)w3;  // exact: |w| < 2^24
     const float norm = __fadd_rn(f1, __fadd_rn(f2, f3));
-    const float num = __fadd_rn(__fmul_rn(v1, f1), __fadd_rn(__fmul_rn(v2, f2), __fmul_rn(v3, f3)));
+    const float num = __fadd_rn(__fmul_rn(s.v1, f1), __fadd_rn(__fmul_rn(s.v2, f2), __fmul_rn(s.v3, f3)));
     out[k] = __fdiv_rn(num, norm);
   }
   float* dst = m.img + (size_t)py * m.cols + px;
