@@ -499,6 +499,8 @@ def run_ours(args, rank, world, local_rank):
         e2e_tri = run_e2e(args, local_rank, frames, (W, H, V, iters), barrier, triangulate=True)
         e2e_tri["value"] = shard.aggregate_throughput(e2e_tri["frames"], e2e_tri["seconds"], dev)
 
+    ceiling = _d2h_ceiling(torch, dev, dist, barrier, 4 * W * H)
+
     if rank == 0:
         E = int(np.mean([g["edges"].shape[0] for g in frames[:N_DISTINCT]]))
         peak, peak_src = _peaks()
@@ -552,7 +554,11 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": e2e["h2d"],
                     "d2h_bytes_per_step": e2e["d2h"], "frames_per_step": e2e["per_step"],
                     "host_threads": e2e["threads"], "frames_in_flight": e2e["in_flight"],
-                    "host_breakdown": e2e["breakdown"]},
+                    "host_breakdown": e2e["breakdown"],
+                    "pcie_d2h_ceiling": dict(ceiling, frames_per_s=ceiling["GBps_total"] * 1e9 / (e2e["d2h"] / e2e["per_step"]),
+                                             note="all ranks copying dense maps device->pinned host back to back, nothing "
+                                                  "else running: what the box's PCIe fabric gives the e2e leg (every "
+                                                  "frame returns 4*W*H + 12*V bytes)")},
         }
         if e2e_tri is not None:
             line["e2e_incl_triangulation"] = {
@@ -675,6 +681,41 @@ def run_config_e(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _d2h_ceiling(torch, dev, dist, barrier, nbytes, seconds=0.6):
+    """Raw device->host rate of this box with every rank copying at once (GB/s: total, slowest and fastest rank)."""
+    src = torch.empty(4, nbytes, dtype=torch.uint8, device=dev)
+    ring = torch.empty(16, nbytes, dtype=torch.uint8).pin_memory()
+    st = torch.cuda.Stream(dev)
+
+    def burst(sec):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 0
+        with torch.cuda.stream(st):
+            a.record(st)
+            t0 = time.perf_counter()
+            while time.perf_counter() - t0 < sec:
+                for _ in range(8):
+                    ring[n % 16].copy_(src[n % 4], non_blocking=True)
+                    n += 1
+                st.synchronize()
+            b.record(st)
+        st.synchronize()
+        return n * nbytes / (a.elapsed_time(b) * 1e-3) / 1e9
+
+    burst(0.1)
+    barrier()
+    mine = burst(seconds)
+    barrier()
+    if dist is None:
+        return {"GBps_total": mine, "GBps_slowest_rank": mine, "GBps_fastest_rank": mine}
+    t = torch.tensor([mine, -mine, mine], dtype=torch.float64, device=dev)
+    tot = t.clone()
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    mx = t.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    return {"GBps_total": float(tot[0]), "GBps_slowest_rank": -float(mx[1]), "GBps_fastest_rank": float(mx[2])}
 
 
 def run_e2e(args, local_rank, frames, dims, barrier, triangulate=False):
