@@ -1217,7 +1217,7 @@ int flame_b200_mesh_bind(flame_b200_ctx* c, int slot, int32_t T, const int32_t* 
 int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float scale) {
   if (int rc = check_slot(c, slot0, n_slots)) return rc;
   if (int rc = use_device(c)) return rc;
-  int maxV = 0, maxT = 0, max_tiles = 0;
+  int maxV = 0, maxT = 0, max_rows = 0, max_cols = 0;
   bool rebuild = false;
   for (int i = slot0; i < slot0 + n_slots; ++i) {
     Slot& s = c->slots[i];
@@ -1231,7 +1231,8 @@ int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float sca
     }
     maxV = std::max(maxV, s.g.V);
     maxT = std::max(maxT, s.m.T);
-    max_tiles = std::max(max_tiles, raster_tiles(s.m.rows, s.m.cols));
+    max_rows = std::max(max_rows, s.m.rows);
+    max_cols = std::max(max_cols, s.m.cols);
     rebuild |= s.bins_dirty;
   }
   // values_from_graph overwrites what a pending projection of the same slots still reads
@@ -1258,7 +1259,7 @@ int flame_b200_mesh_project(flame_b200_ctx* c, int slot0, int n_slots, float sca
       FB_CUDA(cudaMemsetAsync(s.m.counters, 0, ((size_t)raster_tiles(s.m.rows, s.m.cols) + 8) * sizeof(int), rs));
       s.bins_dirty = false;
     }
-  if (int rc = raster_project(rs, c->d_meshes + slot0, n_slots, maxT, max_tiles, 1, rebuild)) return rc;
+  if (int rc = raster_project(rs, c->d_meshes + slot0, n_slots, maxT, max_rows, max_cols, 1, rebuild)) return rc;
   if (c->async_proj) {
     cudaEvent_t done = nullptr;
     if (!c->ev_pool.empty()) {
@@ -1532,7 +1533,7 @@ int flame_b200_interpolate_mesh(flame_b200_ctx* c, int slot, int32_t T, const in
   if (!fill_nan)
     FB_CUDA(cudaMemcpyAsync(s.m.img, out_host, npix * 4, cudaMemcpyHostToDevice, c->stream));
   FB_CUDA(cudaMemsetAsync(s.m.counters, 0, ((size_t)raster_tiles(rows, cols) + 8) * sizeof(int), c->stream));
-  if (int rc = raster_project(c->stream, c->d_meshes + slot, 1, s.m.T, raster_tiles(rows, cols), fill_nan, 1)) return rc;
+  if (int rc = raster_project(c->stream, c->d_meshes + slot, 1, s.m.T, rows, cols, fill_nan, 1)) return rc;
   s.bins_dirty = true;  // bound to caller-supplied positions: never reused
   FB_CUDA(cudaMemcpyAsync(out_host, s.m.img, npix * 4, cudaMemcpyDeviceToHost, c->stream));
   FB_CUDA(cudaStreamSynchronize(c->stream));

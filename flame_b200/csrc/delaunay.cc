@@ -82,16 +82,24 @@ struct Mesh {
   int64_t ccw(int32_t a, int32_t b, int32_t c) const {
     return (int64_t)(px[b] - px[a]) * (py[c] - py[a]) - (int64_t)(py[b] - py[a]) * (px[c] - px[a]);
   }
-  // d strictly inside the circle through a, b, c (a, b, c counter-clockwise)
+  // d strictly inside the circle through a, b, c (a, b, c counter-clockwise). |differences| < 2^23, so the
+  // squared lengths and the 2x2 minors fit int64 (< 2^47) and each product is ONE 64x64 -> 128-bit multiply.
   bool incircle(int32_t a, int32_t b, int32_t c, int32_t d) const {
-    const int64_t ax = px[a] - px[d], ay = py[a] - py[d];
-    const int64_t bx = px[b] - px[d], by = py[b] - py[d];
-    const int64_t cx = px[c] - px[d], cy = py[c] - py[d];
-    const __int128 a2 = (__int128)(ax * ax + ay * ay), b2 = (__int128)(bx * bx + by * by),
-                   c2 = (__int128)(cx * cx + cy * cy);
-    const __int128 det = a2 * (__int128)(bx * cy - by * cx) - b2 * (__int128)(ax * cy - ay * cx) +
-                         c2 * (__int128)(ax * by - ay * bx);
-    return det > 0;
+    const int64_t dx = px[d], dy = py[d];
+    const int64_t ax = px[a] - dx, ay = py[a] - dy;
+    const int64_t bx = px[b] - dx, by = py[b] - dy;
+    const int64_t cx = px[c] - dx, cy = py[c] - dy;
+    const int64_t a2 = ax * ax + ay * ay, b2 = bx * bx + by * by, c2 = cx * cx + cy * cy;
+    const int64_t mbc = bx * cy - by * cx, mac = ax * cy - ay * cx, mab = ax * by - ay * bx;
+    // double filter: the three products are < 2^94 and exact terms; the double evaluation is off by less than
+    // 2^-50 of the sum of their magnitudes - decide by sign unless the result is inside that band
+    const double ta = (double)a2 * (double)mbc, tb = (double)b2 * (double)mac, tc = (double)c2 * (double)mab;
+    const double det = ta - tb + tc;
+    const double band = (std::fabs(ta) + std::fabs(tb) + std::fabs(tc)) * 1e-14;
+    if (det > band) return true;
+    if (det < -band) return false;
+    const __int128 exact = (__int128)a2 * mbc - (__int128)b2 * mac + (__int128)c2 * mab;
+    return exact > 0;
   }
   bool right_of(int32_t p, Edge e) const { return ccw(p, dest(e), org[e]) > 0; }
   bool left_of(int32_t p, Edge e) const { return ccw(p, org[e], dest(e)) > 0; }
@@ -186,9 +194,21 @@ extern "C" int flame_b200_delaunay(int32_t V, const float* pos, int32_t tri_capa
     py[v] = (int32_t)std::lrintf(y * 256.0f);
     order[v] = v;
   }
-  std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-    return px[a] != px[b] ? px[a] < px[b] : (py[a] != py[b] ? py[a] < py[b] : a < b);
-  });
+  {  // sort by (x, y, id): one packed 64-bit key per vertex (x, y biased to unsigned 22 bits, id 20 bits) when
+     // the ids fit, else the comparison sort
+    if (V < (1 << 20)) {
+      std::vector<uint64_t> keys(V);
+      for (int32_t v = 0; v < V; ++v)
+        keys[v] = ((uint64_t)(uint32_t)(px[v] + (1 << 21)) << 42) | ((uint64_t)(uint32_t)(py[v] + (1 << 21)) << 20) |
+                  (uint64_t)v;
+      std::sort(keys.begin(), keys.end());
+      for (int32_t v = 0; v < V; ++v) order[v] = (int32_t)(keys[v] & ((1u << 20) - 1));
+    } else {
+      std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        return px[a] != px[b] ? px[a] < px[b] : (py[a] != py[b] ? py[a] < py[b] : a < b);
+      });
+    }
+  }
   // coincident points (after rounding): the first one represents them, the others stay unconnected (as
   // Triangle leaves duplicate vertices out)
   int n = 0;

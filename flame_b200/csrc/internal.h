@@ -51,13 +51,14 @@ struct GraphDev {
   int* edge_slot;   // [2E] (caller edge, role) -> incidence slot                (device-built)
 };
 
-struct __align__(16) TriStatic {  // per triangle, written by k_tri_static; 64 bytes; depends on topology + positions
+struct __align__(16) TriStatic {  // per triangle, written by k_tri_static; 80 bytes; depends on topology + positions
   int A1, B1, C1, A2;             // integer edge functions w1 = e23, w2 = e31, w3 = e12
   int B2, C2, A3, B3;
   int C3, xmin, xend, ymin;       // sweep columns [xmin, xend) (4-px groups), rows [ymin, ymax]
   int ymax, fx1;                  // last column the triangle may write (before clipping to the image)
   int flags;                      // 1 writes nothing, 2 sweep wraps past the right border, 4 degenerate, 8 wide list
-  int pad;
+  int i1;                         // caller vertex ids of p1, p2, p3 (= triangle's vertices in reverse order): the
+  int i2, i3, pad0, pad1;         //     shading values are read without going through tris[]
 };
 
 struct MeshDev {
@@ -120,7 +121,7 @@ inline size_t raw_f_offset(int field, int V, int E) {
 inline size_t raw_f_total(int V, int E) { return (size_t)13 * V + (size_t)5 * E; }
 
 // ---- dense projection (raster.cu) ----
-int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_tiles, int fill_nan,
+int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_rows, int max_cols, int fill_nan,
                    int rebuild);
 int raster_tiles(int rows, int cols);  // screen tiles of an image (size of tile_cnt)
 int raster_bin_cap(int T, int rows, int cols);

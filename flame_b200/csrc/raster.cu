@@ -91,10 +91,12 @@ __global__ void __launch_bounds__(256) k_tri_static(const MeshDev* __restrict__ 
   s.fx1 = degenerate ? s.xend - 1 : xmax;
   const bool wraps = degenerate && (s.xend > m.cols);  // overshoot columns land on the head of the next row
   s.flags = (degenerate ? 4 : 0) | (wraps ? 2 : 0);
-  s.pad = 0;
+  s.i1 = ic; s.i2 = ib; s.i3 = ia;
+  s.pad0 = s.pad1 = 0;
   int fx0, fx1, fy0, fy1;
   footprint(s, m, &fx0, &fx1, &fy0, &fy1);
-  if (fy0 > fy1 || (!wraps && fx0 > fx1)) {
+  // triangles the caller marked invalid (tri_valid / vtx_valid, fixed at mesh_bind like the bins) are not binned
+  if ((m.tri_ok && !m.tri_ok[t]) || fy0 > fy1 || (!wraps && fx0 > fx1)) {
     s.flags |= 1;  // writes nothing
   } else {
     const int tx0 = fx0 / TILE_W, tx1 = fx1 / TILE_W, ty0 = fy0 / TILE_H, ty1 = fy1 / TILE_H;
@@ -148,12 +150,12 @@ __device__ __forceinline__ bool degenerate_covers(const Tri& s, int x, int y, in
 }
 
 __global__ void __launch_bounds__(32 * TILE_WARPS, 10) k_tiles(const MeshDev* __restrict__ ms, int fill_nan) {
-  const MeshDev m = ms[blockIdx.y];
+  const MeshDev m = ms[blockIdx.z];
   const int ntx = tiles_x(m), nty = tiles_y(m);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x * TILE_WARPS + warp;
-  if (tile >= ntx * nty) return;  // warps are independent: no block-wide barrier below
-  const int ty = tile / ntx, tx = tile - ty * ntx;
+  const int tx = blockIdx.x * TILE_WARPS + warp, ty = blockIdx.y;  // a CTA = TILE_WARPS neighbouring tiles of a row
+  if (tx >= ntx || ty >= nty) return;  // warps are independent: no block-wide barrier below
+  const int tile = ty * ntx + tx;
   const int px = tx * TILE_W + (lane & 3) * 4, py = ty * TILE_H + (lane >> 2);
   __shared__ StagedTri s_all[TILE_WARPS][32];
   StagedTri* s_tri = s_all[warp];
@@ -169,10 +171,10 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, 10) k_tiles(const MeshDev* __
     TriStatic s;
     if (use) {
       t = e < nbin ? bin[e] : m.wide[e - nbin];
-      use = !((m.tri_ok && !m.tri_ok[t]) || (m.tri_filt && !m.tri_filt[t]));
+      s = m.stat[t];
+      use = !(m.tri_filt && !m.tri_filt[t]);  // (invalid triangles were never binned)
     }
     if (use) {
-      s = m.stat[t];
       if (e >= nbin) {  // wide list: does its footprint touch this tile at all?
         int fx0, fx1, fy0, fy1;
         footprint(s, m, &fx0, &fx1, &fy0, &fy1);
@@ -190,9 +192,9 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, 10) k_tiles(const MeshDev* __
       d.xmin = s.xmin; d.xend = s.xend; d.ymin = s.ymin; d.ymax = s.ymax; d.flags = s.flags;
       d.key = (t << 5) | __popc(mask & ((1u << lane) - 1u));
       // values at p1, p2, p3 = reversed triangle order (image_utils.cc:385-391)
-      d.v1 = m.values[m.tris[3 * t + 2]];
-      d.v2 = m.values[m.tris[3 * t + 1]];
-      d.v3 = m.values[m.tris[3 * t]];
+      d.v1 = m.values[s.i1];
+      d.v2 = m.values[s.i2];
+      d.v3 = m.values[s.i3];
     }
     __syncwarp();
     const int n = __popc(mask);
@@ -245,9 +247,9 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, 10) k_tiles(const MeshDev* __
         s.A1 = g.A1; s.B1 = g.B1; s.C1 = g.C1; s.A2 = g.A2; s.B2 = g.B2; s.C2 = g.C2;
         s.A3 = g.A3; s.B3 = g.B3; s.C3 = g.C3;
         s.xmin = g.xmin; s.xend = g.xend; s.ymin = g.ymin; s.ymax = g.ymax; s.flags = g.flags;
-        s.v1 = m.values[m.tris[3 * t + 2]];
-        s.v2 = m.values[m.tris[3 * t + 1]];
-        s.v3 = m.values[m.tris[3 * t]];
+        s.v1 = m.values[g.i1];
+        s.v2 = m.values[g.i2];
+        s.v3 = m.values[g.i3];
       }
     }
     int w1, w2, w3;
@@ -541,14 +543,15 @@ int raster_coverage(cudaStream_t st, const MeshDev& m, unsigned long long* d_cou
 
 // ms_dev: device array of n MeshDev. rebuild != 0: topology or positions of (some of) the meshes changed
 // since their bins were built; the caller has zeroed [counters | tile_cnt] of every mesh of the batch.
-int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_tiles, int fill_nan,
+int raster_project(cudaStream_t st, const MeshDev* ms_dev, int n, int maxT, int max_rows, int max_cols, int fill_nan,
                    int rebuild) {
-  if (n == 0 || max_tiles == 0) return 0;
+  if (n == 0 || max_rows <= 0 || max_cols <= 0) return 0;
+  const int gx = ((max_cols + TILE_W - 1) / TILE_W + TILE_WARPS - 1) / TILE_WARPS, gy = (max_rows + TILE_H - 1) / TILE_H;
   if (rebuild && maxT > 0) {
     k_tri_static<<<dim3((maxT + 31) / 32, n), 256, 0, st>>>(ms_dev);
     count_launch();
   }
-  k_tiles<<<dim3((max_tiles + TILE_WARPS - 1) / TILE_WARPS, n), 32 * TILE_WARPS, 0, st>>>(ms_dev, fill_nan);
+  k_tiles<<<dim3(gx, gy, n), 32 * TILE_WARPS, 0, st>>>(ms_dev, fill_nan);
   count_launch();
   FB_CUDA(cudaGetLastError());
   return 0;

@@ -297,3 +297,38 @@ def test_pd_vertex_degree_beyond_the_resident_limit(gpu_ctx, oracle):
     gpu_ctx.graph_init(4, pos, g["data_term"], edges)
     gpu_ctx.pd_run(_lib.default_pd_params(), 20, slot0=4, mode=_lib.PD_AUTO)
     _assert_bit_equal(gpu_ctx.graph_download(4, V, edges.shape[0]), want, STATE)
+
+
+@pytest.mark.parametrize("V,cluster", [(260, None), (2600, None), (6000, "13")])
+def test_pd_hub_vertices_inside_the_resident_limit(gpu_ctx, oracle, V, cluster, monkeypatch):
+    """Hubs of degree 40-60 (all-source, all-target and mixed) on top of a sparse random graph, solved by the
+    resident kernel: many owned-edge ranks with one vertex each, record blocks of very different sizes, source
+    groups whose supply of target groups is lopsided - the rank-major list and the balanced dealing must not
+    change a bit. (cluster = a forced cluster size: chunks that cut through the hubs' neighbourhoods.)"""
+    if cluster:
+        monkeypatch.setenv("FLAME_B200_CLUSTER", cluster)
+    rng = np.random.default_rng(V)
+    pos = rng.uniform(4, 900, (V, 2)).astype(np.float32)
+    hubs = []
+    for h, (deg, flip) in enumerate([(60, "none"), (55, "all"), (48, "half"), (40, "none")]):
+        nb = rng.choice(np.arange(8, V), deg, replace=False).astype(np.int32)
+        e = np.stack([np.full(deg, h, np.int32), nb], 1)
+        if flip == "all":
+            e = e[:, ::-1]
+        elif flip == "half":
+            e[::2] = e[::2, ::-1]
+        hubs.append(e)
+    sparse = rng.integers(8, V, (2 * V, 2)).astype(np.int32)
+    sparse = sparse[sparse[:, 0] != sparse[:, 1]]
+    edges = np.concatenate(hubs + [sparse])
+    edges = np.ascontiguousarray(edges[rng.permutation(edges.shape[0])])
+    deg = np.bincount(edges.ravel(), minlength=V)
+    assert 40 <= deg.max() <= 64
+    g = {"pos": pos, "edges": edges, "data_term": rng.uniform(0.1, 2.0, V).astype(np.float32),
+         "data_weight": np.ones(V, np.float32)}
+    alpha, beta = oracle.edge_weights(edges, pos)
+    want = synth.init_state(g, alpha, beta)
+    oracle.pd_run(want, oracle.pd_default_params(), 12)
+    gpu_ctx.graph_init(5, pos, g["data_term"], edges)
+    gpu_ctx.pd_run(_lib.default_pd_params(), 12, slot0=5, mode=_lib.PD_RESIDENT)
+    _assert_bit_equal(gpu_ctx.graph_download(5, V, edges.shape[0]), want, STATE)
