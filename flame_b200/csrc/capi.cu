@@ -558,7 +558,8 @@ int flame_b200_ctx_create(int device, int n_slots, flame_b200_ctx** out) {
   for (int C = 1; C <= 16; ++C) {
     ResidentPlan pl{};
     pl.cluster = C;
-    pl.variant = 1;  // the 768-thread build; one CTA per SM for every build at these shared-memory sizes
+    pl.variant = 1;  // one CTA per SM for every build at these shared-memory sizes
+    pl.threads = 640;
     pl.smem_bytes = 200 * 1024;
     int n = 0;
     if (int rc = pd_resident_capacity(pl, &n)) return rc;

@@ -512,10 +512,11 @@ int pd_run_stream(cudaStream_t st, const GraphDev* gs_dev, int n, int max_chunks
 //   barrier.cluster
 // Nobody reads x_bar between the two barriers, so ONE x_bar buffer suffices.
 //
-// The template parameters are the register budgets the kernel is built for: MAXT threads, SPT owned
-// edges and VPT vertices per thread. <1024,4,2> holds a 10 000-vertex Delaunay graph in a cluster of
-// NINE CTAs (two such clusters fit every GPC with >= 18 SMs: 15 frames in flight on 135 of the 148 SMs);
-// <640,4,1> is the low-latency variant for 16-CTA clusters (one frame spread over 16 SMs).
+// The template parameters are the register budgets the kernel is built for: at most MAXT threads, SPT owned
+// edges and VPT vertices per thread; the block size is chosen at launch (pd_resident_variant). <640,6,2> holds
+// a 10 000-vertex Delaunay graph in a cluster of NINE CTAs with 576 threads each (two such clusters fit every
+// GPC with >= 18 SMs: 15 frames in flight on 135 of the 148 SMs); <640,4,1> is the low-latency variant for
+// 16-CTA clusters (one frame spread over 16 SMs); <1024,4,2> takes chunks up to 2 048 vertices.
 // ------------------------------------------------------------------------------------------
 struct ResidentArgs {
   const GraphDev* gs;
@@ -605,6 +606,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   const int c = cluster.block_rank();
   const GraphDev g = a.gs[blockIdx.x / C];
   const int tid = threadIdx.x;
+  const int NT = blockDim.x;  // <= MAXT: the planner launches as many threads as balance the chunk (pd_resident_variant)
   const int Vc = g.Vc;  // this graph's chunk width (a.Vc >= Vc is the carve width)
 
   extern __shared__ __align__(128) unsigned char smem[];
@@ -640,9 +642,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   FB_STAMP(0);
   // ---- load ----
   if (have)
-    for (int k = tid; k <= g.max_deg; k += MAXT) s_koff[k] = koff_row(g, c)[k];
-  for (int k = tid; k < g.max_deg + 2; k += MAXT) s_hist[k] = 0;
-  for (int k = tid; k < 72 + 64; k += MAXT) s_sup[k] = 0;  // s_sup and s_dem are adjacent
+    for (int k = tid; k <= g.max_deg; k += NT) s_koff[k] = koff_row(g, c)[k];
+  for (int k = tid; k < g.max_deg + 2; k += NT) s_hist[k] = 0;
+  for (int k = tid; k < 72 + 64; k += NT) s_sup[k] = 0;  // s_sup and s_dem are adjacent
   __syncthreads();
   if (tid == 0) {
     int tot = 0;
@@ -651,12 +653,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
       if (k < g.max_deg) tot += have ? kpad_round(s_koff[k + 1] - s_koff[k]) : 0;
     }
   }
-  // vertex registers: thread t owns vertices t, t + MAXT, ... of the chunk (nv <= MAXT * VPT)
+  // vertex registers: thread t owns vertices t, t + NT, ... of the chunk (nv <= NT * VPT)
   float x[VPT], w1[VPT], w2[VPT], data[VPT], wt[VPT];
   int deg[VPT];
 #pragma unroll
   for (int v = 0; v < VPT; ++v) {
-    const int i = tid + v * MAXT;
+    const int i = tid + v * NT;
     x[v] = w1[v] = w2[v] = data[v] = wt[v] = 0.f;
     deg[v] = 0;
     if (i < nv) {
@@ -677,7 +679,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   //   per-vertex counts + histogram -> exclusive scan (warp 0) -> vertex-major list -> rank-major list
 #pragma unroll
   for (int v = 0; v < VPT; ++v) {
-    const int i = tid + v * MAXT;
+    const int i = tid + v * NT;
     if (i < nv) {
       int cnt = 0;
       for (int k = 0; k < deg[v]; ++k) cnt += (g.inc_nbr[base + s_koff[k] + i] & 1) ^ 1;
@@ -718,11 +720,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
     }
   }
   __syncthreads();
-  const int ne = *s_cnt;  // <= MAXT * SPT (planner)
+  const int ne = *s_cnt;  // <= NT * SPT (planner)
   FB_STAMP(2);
 #pragma unroll
   for (int v = 0; v < VPT; ++v) {
-    const int i = tid + v * MAXT;
+    const int i = tid + v * NT;
     if (i < nv) {
       int at = s_scan[i];
       for (int k = 0; k < deg[v]; ++k)
@@ -731,7 +733,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   }
   __syncthreads();
   FB_STAMP(3);
-  for (int r = tid >> 5; r <= g.max_deg && s_hist[r] > 0; r += MAXT >> 5) {  // one warp per rank
+  for (int r = tid >> 5; r <= g.max_deg && s_hist[r] > 0; r += NT >> 5) {  // one warp per rank
     int run = s_roff[r];
     const unsigned int lt = (1u << (tid & 31)) - 1u;
     for (int b = 0; b < nv; b += 32) {
@@ -753,7 +755,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   // positions of that group that want their target group (any order); what does not match - surplus edges and
   // the cut edges, whose targets are in another SM - fills the positions left over. Only the assignment of
   // edges to threads changes, neither the arithmetic nor the accumulation order (that is by record slot).
-  for (int pp = tid; pp < ne; pp += MAXT) {
+  for (int pp = tid; pp < ne; pp += NT) {
     const unsigned int rec = s_rank[pp];
     const int i = (int)(rec >> 16), k = (int)(rec & 0xFFFFu);
     const int nbr = g.inc_nbr[base + s_koff[k] + i] >> 1;
@@ -785,14 +787,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
     }
   }
   __syncthreads();
-  for (int pp = tid; pp < ne; pp += MAXT) {
+  for (int pp = tid; pp < ne; pp += NT) {
     const int ag = (int)(s_rank[pp] >> 16) & 7;
     const int lane = pp & 31;
     const int want = (lane + 2 * (lane >> 3) + ((pp >> 5) & 1)) & 7;
     s_pos[s_off[ag * 8 + want] + (s_tmp[pp] & 0x3FFF)] = (unsigned short)pp;
   }
   __syncthreads();
-  for (int pp = tid; pp < ne; pp += MAXT) {
+  for (int pp = tid; pp < ne; pp += NT) {
     const unsigned int rec = s_rank[pp];
     const int ag = (int)(rec >> 16) & 7;
     const int tg = (int)((unsigned int)s_tmp[pp] >> 28), m = (s_tmp[pp] >> 14) & 0x3FFF;
@@ -818,7 +820,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   int e_id[SPT];
 #pragma unroll
   for (int u = 0; u < SPT; ++u) {
-    const int j = tid + u * MAXT;
+    const int j = tid + u * NT;
     q1[u] = q2[u] = q3[u] = 0.f;
     src[u] = 0;
     dst_bar[u] = bar_addr;
@@ -838,10 +840,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   }
 #pragma unroll
   for (int u = 0; u < SPT; ++u)
-    if (tid + u * MAXT < ne) e_id[u] = g.edge_slot[2 * e_id[u] + 1];  // global slot of the target's incidence
+    if (tid + u * NT < ne) e_id[u] = g.edge_slot[2 * e_id[u] + 1];  // global slot of the target's incidence
 #pragma unroll
   for (int u = 0; u < SPT; ++u) {
-    const int j = tid + u * MAXT;
+    const int j = tid + u * NT;
     if (j < ne) {
       const int nbr = (int)dst_bar[u];
       const int oc = nbr / Vc;  // the target vertex lives in chunk oc, and so do its slots
@@ -873,7 +875,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   }
   FB_STAMP(6);
   __syncthreads();  // the load-phase lists (aliases of s_p4) are dead from here on
-  for (int slot = tid; slot < s_kpad[g.max_deg]; slot += MAXT)
+  for (int slot = tid; slot < s_kpad[g.max_deg]; slot += NT)
     s_p1[slot] = neg0;  // target slots keep -0.0f forever; source slots are rewritten every iteration
   cluster.sync();
 
@@ -890,8 +892,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
 #pragma unroll
       for (int v = 0; v < PD_MLP; ++v) {
         const int u = u0 + v;
-        if (u < SPT && tid + u * MAXT < ne) {
-          s[v] = s_s[tid + u * MAXT];
+        if (u < SPT && tid + u * NT < ne) {
+          s[v] = s_s[tid + u * NT];
           bi[v] = s_bar[src[u] >> 16];
           bj[v] = (dst_bar[u] & 1u) ? ld_cluster_f4(dst_bar[u] & ~1u) : ld_shared_f4(dst_bar[u]);
         }
@@ -899,7 +901,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
 #pragma unroll
       for (int v = 0; v < PD_MLP; ++v) {
         const int u = u0 + v;
-        if (u < SPT && tid + u * MAXT < ne) {
+        if (u < SPT && tid + u * NT < ne) {
           const float4 qu = dual_update(make_float4(q1[u], q2[u], q3[u], 0.f), s[v], bi[v], bj[v], p.step_q);
           q1[u] = qu.x; q2[u] = qu.y; q3[u] = qu.z;
           // primalStep contributions (cc:125-141), rounded as the reference: a = (q1*step_x)*alpha ...
@@ -923,14 +925,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   uint32_t vp4[VPT], vp1[VPT];
 #pragma unroll
   for (int v = 0; v < VPT; ++v) {
-    vp4[v] = p4_addr + (uint32_t)(tid + v * MAXT) * 16u;
-    vp1[v] = smem_u32(s_p1) + (uint32_t)(tid + v * MAXT) * 4u;
+    vp4[v] = p4_addr + (uint32_t)(tid + v * NT) * 16u;
+    vp1[v] = smem_u32(s_p1) + (uint32_t)(tid + v * NT) * 4u;
   }
   const uint32_t koff_addr = smem_u32(s_kpad);
   auto phase_b = [&](const bool last) {
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
-      const int i = tid + v * MAXT;
+      const int i = tid + v * NT;
       if (i < nv) {
         const float x_old = x[v], w1_old = w1[v], w2_old = w2[v];
         float xx = x_old, ww1 = w1_old, ww2 = w2_old;
@@ -992,7 +994,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   // ---- write back (both private copies of every edge's q) ----
 #pragma unroll
   for (int v = 0; v < VPT; ++v) {
-    const int i = tid + v * MAXT;
+    const int i = tid + v * NT;
     if (i < nv) {
       g.vbar[v0 + i] = s_bar[i];
       g.vprim[v0 + i] = make_float4(x[v], w1[v], w2[v], data[v]);
@@ -1003,7 +1005,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
 #pragma unroll
   for (int u = 0; u < SPT; ++u) {
     wb_s[u] = wb_t[u] = 0;
-    if (tid + u * MAXT < ne) {
+    if (tid + u * NT < ne) {
       const int ps = (int)(src[u] & 0xFFFFu) - (int)(src[u] >> 16);  // = kpad[k] of the source incidence
       int k = 0;
       while (s_kpad[k] != ps) ++k;
@@ -1013,10 +1015,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_pd_resident(ResidentArgs a) {
   }
 #pragma unroll
   for (int u = 0; u < SPT; ++u)
-    if (tid + u * MAXT < ne) wb_t[u] = g.edge_slot[2 * wb_t[u] + 1];
+    if (tid + u * NT < ne) wb_t[u] = g.edge_slot[2 * wb_t[u] + 1];
 #pragma unroll
   for (int u = 0; u < SPT; ++u) {
-    if (tid + u * MAXT < ne) {
+    if (tid + u * NT < ne) {
       float* qs = reinterpret_cast<float*>(g.inc_q + wb_s[u]);
       float* qt = reinterpret_cast<float*>(g.inc_q + wb_t[u]);
       *reinterpret_cast<float2*>(qs) = make_float2(q1[u], q2[u]);
@@ -1033,19 +1035,27 @@ size_t pd_resident_smem(int Vc, int maxInc, int maxEdges, int max_deg) {
          (size_t)resident_inc_records(maxInc, max_deg) * 4 + (size_t)(2 * (max_deg + 2) + 2) * 4 + 128;
 }
 
-// The register budgets the kernel is built for: (threads, owned edges per thread, vertices per thread).
+// The register budgets the kernel is built for: (most threads, owned edges per thread, vertices per thread).
 struct ResidentVariant { int threads, spt, vpt; };
-static const ResidentVariant kVariants[FB_RESIDENT_VARIANTS] = {{640, 4, 1}, {768, 5, 2}, {1024, 4, 2}};
+static const ResidentVariant kVariants[FB_RESIDENT_VARIANTS] = {{640, 4, 1}, {640, 6, 2}, {1024, 4, 2}};
 
-// Smallest variant that holds chunks of Vc vertices / maxEdges owned edges; -1 = none.
+// Smallest variant that holds chunks of Vc vertices / maxEdges owned edges; -1 = none. *threads = the block
+// size to launch: the fewest warps that give every thread vpt vertices and spt edges - a thread count that
+// leaves the last vertex round or the last edge round half empty makes the full warps wait at the cluster
+// barrier for nothing (config D, 1 112-vertex chunks: 576 threads x (2 vertices, 6 edges) 0.80 ms per wave,
+// 768 x (2, 5) 0.86 ms, 384 x (3, 9) 0.84 ms).
 int pd_resident_variant(int Vc, int maxEdges, int* threads) {
-  int forced = -1;
+  int forced = -1, forced_threads = 0;
   if (const char* sv = getenv("FLAME_B200_VARIANT")) forced = atoi(sv);
+  if (const char* sv = getenv("FLAME_B200_THREADS")) forced_threads = atoi(sv);
   for (int i = 0; i < FB_RESIDENT_VARIANTS; ++i) {
     if (forced >= 0 && i != forced) continue;
     const ResidentVariant& r = kVariants[i];
     if (Vc <= r.threads * r.vpt && maxEdges <= r.threads * r.spt) {
-      if (threads) *threads = r.threads;
+      int t = std::max((Vc + r.vpt - 1) / r.vpt, (maxEdges + r.spt - 1) / r.spt);
+      t = std::max(64, (t + 31) / 32 * 32);
+      if (forced_threads >= t && forced_threads <= r.threads && forced_threads % 32 == 0) t = forced_threads;
+      if (threads) *threads = std::min(t, r.threads);
       return i;
     }
   }
@@ -1056,7 +1066,7 @@ typedef void (*ResidentKernel)(ResidentArgs);
 static ResidentKernel resident_kernel(int variant) {
   switch (variant) {
     case 0: return k_pd_resident<640, 4, 1, 2>;
-    case 1: return k_pd_resident<768, 5, 2, 1>;
+    case 1: return k_pd_resident<640, 6, 2, 1>;
     default: return k_pd_resident<1024, 4, 2, 1>;
   }
 }
@@ -1081,7 +1091,7 @@ static void resident_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, 
                             cudaStream_t st) {
   *cfg = cudaLaunchConfig_t{};
   cfg->gridDim = dim3(n * plan.cluster);
-  cfg->blockDim = dim3(kVariants[plan.variant].threads);
+  cfg->blockDim = dim3(plan.threads);
   cfg->dynamicSmemBytes = plan.smem_bytes;
   cfg->stream = st;
   attr[0].id = cudaLaunchAttributeClusterDimension;
