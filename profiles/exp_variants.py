@@ -1,6 +1,9 @@
 """Experiment (not part of the bench contract): the resident PD solver per cluster size / kernel build.
 
-  python profiles/exp_variants.py [C:variant:relaxed2 ...]     # run under gpurun
+  python profiles/exp_variants.py [C:variant:0 ...]     # run under gpurun; C = cluster size, variant = build index
+                                                        # (0 <640,4,1>, 1 <640,6,2>, 2 <1024,4,2>); the third field is
+                                                        # unused (it selected a relaxed second barrier in an earlier build);
+                                                        # FLAME_B200_THREADS=<n> additionally forces the block size
 
 For every configuration: frames resident at once (pd_wave), time of a 200-iteration solve of 1 frame and
 of one full wave, frames/s of back-to-back waves, and a bit-comparison of the result with the first
@@ -25,13 +28,12 @@ def main():
     NF = 60
     frames = [synth.config_graph(cfgname, frame=i % 6) for i in range(6)]
     p = _lib.default_pd_params()
-    combos = sys.argv[1:] or ["16:0:0", "9:2:0", "9:3:0", "9:2:1", "10:2:0", "9:4:0", "9:5:0", "9:6:0"]
+    combos = sys.argv[1:] or ["9:1:0", "16:0:0", "9:2:0", "10:1:0"]
     ref = None
     for combo in combos:
         C_, var, rel = combo.split(":")
         os.environ["FLAME_B200_CLUSTER"] = C_
         os.environ["FLAME_B200_VARIANT"] = var
-        os.environ["FLAME_B200_RELAXED2"] = rel
         ctx = _lib.Context(0, NF)
         try:
             for i in range(NF):
