@@ -7,7 +7,8 @@
 // every entry point). This file gives the pipeline its own triangulator, so that a host thread can
 // triangulate frame k+1 while the device works on frame k:
 //
-//   * divide and conquer (Guibas & Stolfi 1985) on a quad-edge structure, O(V log V), no super-triangle;
+//   * divide and conquer (Guibas & Stolfi 1985) on a quad-edge structure with alternating cuts (Dwyer 1987),
+//     O(V log V), no super-triangle;
 //   * EXACT predicates: positions are rounded to 1/256 px (int32 fixed point, |coordinate| < 8192 px), the
 //     orientation test is evaluated in int64 and the in-circle test in __int128, so collinear and cocircular
 //     inputs - features sit on the pixel grid - need no tolerances and cannot loop;
@@ -32,42 +33,41 @@ namespace {
 
 typedef int32_t Edge;  // 4 * quad + rotation
 
+struct Quad {        // one undirected edge: its four directed / dual edges side by side (one cache line per two)
+  Edge next[4];      // onext of rotation 0..3
+  int32_t org[4];    // origin vertex (meaningful for rotation 0 and 2)
+};
+
 struct Mesh {
-  std::vector<Edge> onext;   // per directed (primal or dual) edge
-  std::vector<int32_t> org;  // per directed edge (meaningful for rotation 0 and 2)
-  std::vector<uint8_t> dead; // per quad
+  std::vector<Quad> quads;
+  std::vector<uint8_t> dead;  // per quad
   const int32_t* px;
   const int32_t* py;
 
   static Edge rot(Edge e) { return (e & ~3) | ((e + 1) & 3); }
   static Edge sym(Edge e) { return (e & ~3) | ((e + 2) & 3); }
   static Edge invrot(Edge e) { return (e & ~3) | ((e + 3) & 3); }
-  Edge on(Edge e) const { return onext[e]; }
-  Edge oprev(Edge e) const { return rot(onext[rot(e)]); }
-  Edge lnext(Edge e) const { return rot(onext[invrot(e)]); }
-  Edge rprev(Edge e) const { return onext[sym(e)]; }
-  int32_t dest(Edge e) const { return org[sym(e)]; }
+  Edge& onext(Edge e) { return quads[e >> 2].next[e & 3]; }
+  Edge on(Edge e) const { return quads[e >> 2].next[e & 3]; }
+  int32_t org(Edge e) const { return quads[e >> 2].org[e & 3]; }
+  Edge oprev(Edge e) const { return rot(on(rot(e))); }
+  Edge lnext(Edge e) const { return rot(on(invrot(e))); }
+  Edge rprev(Edge e) const { return on(sym(e)); }
+  int32_t dest(Edge e) const { return org(sym(e)); }
 
   Edge make_edge(int32_t a, int32_t b) {
-    const Edge q = (Edge)onext.size();
-    onext.push_back(q);
-    onext.push_back(q + 3);
-    onext.push_back(q + 2);
-    onext.push_back(q + 1);
-    org.push_back(a);
-    org.push_back(-1);
-    org.push_back(b);
-    org.push_back(-1);
+    const Edge q = (Edge)(quads.size() << 2);
+    quads.push_back(Quad{{q, q + 3, q + 2, q + 1}, {a, -1, b, -1}});
     dead.push_back(0);
     return q;
   }
   void splice(Edge a, Edge b) {
-    const Edge alpha = rot(onext[a]), beta = rot(onext[b]);
-    std::swap(onext[a], onext[b]);
-    std::swap(onext[alpha], onext[beta]);
+    const Edge alpha = rot(on(a)), beta = rot(on(b));
+    std::swap(onext(a), onext(b));
+    std::swap(onext(alpha), onext(beta));
   }
   Edge connect(Edge a, Edge b) {
-    const Edge e = make_edge(dest(a), org[b]);
+    const Edge e = make_edge(dest(a), org(b));
     splice(e, lnext(a));
     splice(sym(e), b);
     return e;
@@ -101,13 +101,55 @@ struct Mesh {
     const __int128 exact = (__int128)a2 * mbc - (__int128)b2 * mac + (__int128)c2 * mab;
     return exact > 0;
   }
-  bool right_of(int32_t p, Edge e) const { return ccw(p, dest(e), org[e]) > 0; }
-  bool left_of(int32_t p, Edge e) const { return ccw(p, org[e], dest(e)) > 0; }
+  bool right_of(int32_t p, Edge e) const { return ccw(p, dest(e), org(e)) > 0; }
+  bool left_of(int32_t p, Edge e) const { return ccw(p, org(e), dest(e)) > 0; }
 
-  // s[lo, hi): vertex ids sorted by (x, y), all distinct. Returns the ccw convex-hull edge out of the
-  // leftmost vertex and the cw hull edge out of the rightmost one.
-  void build(const int32_t* s, int lo, int hi, Edge* le, Edge* re) {
+  // Total order along the cut axis. Axis 0: (x, y) ascending. Axis 1 is axis 0 seen in a frame turned by a quarter
+  // (x', y') = (y, -x): y ascending, then x descending. A rotation keeps every orientation / in-circle predicate,
+  // so the merge below works unchanged on bottom / top halves.
+  bool before(int32_t a, int32_t b, int axis) const {
+    if (axis == 0) return px[a] != px[b] ? px[a] < px[b] : py[a] < py[b];
+    return py[a] != py[b] ? py[a] < py[b] : px[a] > px[b];
+  }
+  // e: any ccw hull edge (outer face on its right). Returns the ccw hull edge out of the hull's FIRST vertex in
+  // the axis order (the order is a linear functional: one local minimum on a convex hull).
+  Edge first_ccw(Edge e, int axis) const {
+    for (;;) {
+      if (before(dest(e), org(e), axis)) {
+        e = rprev(e);  // next hull vertex, counter-clockwise
+        continue;
+      }
+      const Edge p = sym(oprev(e));  // the ccw hull edge out of the previous hull vertex
+      if (before(org(p), org(e), axis)) {
+        e = p;
+        continue;
+      }
+      return e;
+    }
+  }
+  // e: any cw hull edge (outer face on its left). Returns the cw hull edge out of the hull's LAST vertex.
+  Edge last_cw(Edge e, int axis) const {
+    for (;;) {
+      if (before(org(e), dest(e), axis)) {
+        e = lnext(e);  // next hull vertex, clockwise
+        continue;
+      }
+      const Edge p = sym(on(e));  // the cw hull edge out of the previous hull vertex
+      if (before(org(e), org(p), axis)) {
+        e = p;
+        continue;
+      }
+      return e;
+    }
+  }
+
+  // s[lo, hi): distinct vertex ids (reordered in place). Cuts alternate between the axes (Dwyer 1987: the merged
+  // hulls stay compact, far fewer edges are created only to be deleted again than with vertical strips). Returns
+  // the ccw convex-hull edge out of the first vertex in the order of `axis` and the cw hull edge out of the last.
+  void build(int32_t* s, int lo, int hi, int axis, Edge* le, Edge* re) {
     const int n = hi - lo;
+    const auto cmp = [this, axis](int32_t a, int32_t b) { return before(a, b, axis); };
+    if (n <= 3) std::sort(s + lo, s + hi, cmp);
     if (n == 2) {
       const Edge a = make_edge(s[lo], s[lo + 1]);
       *le = a;
@@ -133,35 +175,41 @@ struct Mesh {
       return;
     }
     const int mid = lo + n / 2;
+    std::nth_element(s + lo, s + mid, s + hi, cmp);
     Edge ldo, ldi, rdi, rdo;
-    build(s, lo, mid, &ldo, &ldi);
-    build(s, mid, hi, &rdi, &rdo);
+    build(s, lo, mid, 1 - axis, &ldo, &ldi);
+    build(s, mid, hi, 1 - axis, &rdi, &rdo);
+    // the halves were built across the other axis: move their handles to this axis' extreme vertices
+    ldo = first_ccw(ldo, axis);
+    ldi = last_cw(ldi, axis);
+    rdi = first_ccw(rdi, axis);
+    rdo = last_cw(rdo, axis);
     for (;;) {  // lower common tangent of the two hulls
-      if (left_of(org[rdi], ldi)) ldi = lnext(ldi);
-      else if (right_of(org[ldi], rdi)) rdi = rprev(rdi);
+      if (left_of(org(rdi), ldi)) ldi = lnext(ldi);
+      else if (right_of(org(ldi), rdi)) rdi = rprev(rdi);
       else break;
     }
     Edge basel = connect(sym(rdi), ldi);
-    if (org[ldi] == org[ldo]) ldo = sym(basel);
-    if (org[rdi] == org[rdo]) rdo = basel;
+    if (org(ldi) == org(ldo)) ldo = sym(basel);
+    if (org(rdi) == org(rdo)) rdo = basel;
     for (;;) {  // merge: the rising bubble
       Edge lcand = on(sym(basel));
       if (right_of(dest(lcand), basel))
-        while (incircle(dest(basel), org[basel], dest(lcand), dest(on(lcand)))) {
+        while (incircle(dest(basel), org(basel), dest(lcand), dest(on(lcand)))) {
           const Edge t = on(lcand);
           remove(lcand);
           lcand = t;
         }
       Edge rcand = oprev(basel);
       if (right_of(dest(rcand), basel))
-        while (incircle(dest(basel), org[basel], dest(rcand), dest(oprev(rcand)))) {
+        while (incircle(dest(basel), org(basel), dest(rcand), dest(oprev(rcand)))) {
           const Edge t = oprev(rcand);
           remove(rcand);
           rcand = t;
         }
       const bool lv = right_of(dest(lcand), basel), rv = right_of(dest(rcand), basel);
       if (!lv && !rv) break;
-      if (!lv || (rv && incircle(dest(lcand), org[lcand], org[rcand], dest(rcand))))
+      if (!lv || (rv && incircle(dest(lcand), org(lcand), org(rcand), dest(rcand))))
         basel = connect(rcand, sym(basel));
       else
         basel = connect(sym(basel), sym(lcand));
@@ -218,18 +266,17 @@ extern "C" int flame_b200_delaunay(int32_t V, const float* pos, int32_t tri_capa
   Mesh m;
   m.px = px.data();
   m.py = py.data();
-  m.onext.reserve((size_t)12 * n + 16);
-  m.org.reserve((size_t)12 * n + 16);
-  m.dead.reserve((size_t)3 * n + 4);
+  m.quads.reserve((size_t)8 * n + 16);  // edges ever created (kept + deleted); ~6.8 n for uniform points
+  m.dead.reserve((size_t)8 * n + 16);
   Edge le, re;
-  m.build(order.data(), 0, n, &le, &re);
+  m.build(order.data(), 0, n, 0, &le, &re);
   const int32_t quads = (int32_t)m.dead.size();
   int32_t ne = 0, nt = 0;
   for (int32_t q = 0; q < quads; ++q) {
     if (m.dead[q]) continue;
     const Edge e = 4 * q;
     if (ne < edge_capacity && edges) {
-      edges[2 * ne] = m.org[e];
+      edges[2 * ne] = m.org(e);
       edges[2 * ne + 1] = m.dest(e);
     }
     ++ne;
@@ -242,7 +289,7 @@ extern "C" int flame_b200_delaunay(int32_t V, const float* pos, int32_t tri_capa
       const Edge e0 = 4 * q + 2 * half;
       const Edge e1 = m.lnext(e0), e2 = m.lnext(e1);
       if (m.lnext(e2) != e0 || e1 < e0 || e2 < e0) continue;
-      const int32_t a = m.org[e0], b = m.org[e1], c = m.org[e2];
+      const int32_t a = m.org(e0), b = m.org(e1), c = m.org(e2);
       if (m.ccw(a, b, c) <= 0) continue;  // the outer face (or a degenerate cycle)
       if (nt < tri_capacity && tris) {
         tris[3 * nt] = a;

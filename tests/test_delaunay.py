@@ -101,3 +101,52 @@ def test_delaunay_random_clouds_including_clusters():
         q = _q(pts)
         uniq = len(set(map(tuple, q.tolist())))
         assert len(edges) <= 3 * uniq - 3 and (n < 3 or len(tris) >= 1)
+
+
+def test_delaunay_alternating_cuts_on_lines_circles_and_every_small_size():
+    """The divide step alternates between x and y cuts and moves the hull handles of the halves to the other
+    axis' extreme vertices: exercise hulls that are segments, axis-parallel lines, cocircular rings and every
+    small size (base cases of 2 and 3 points under both axes)."""
+    from scipy.spatial import ConvexHull
+    rng = np.random.default_rng(11)
+    k = np.arange(13, dtype=np.float32)
+    shapes = {
+        "vertical line": np.stack([np.full(13, 40.0, np.float32), 5 + 7 * k], 1),
+        "horizontal line": np.stack([5 + 7 * k, np.full(13, 40.0, np.float32)], 1),
+        "two vertical lines": np.concatenate([np.stack([np.full(13, 40.0, np.float32), 5 + 7 * k], 1),
+                                              np.stack([np.full(13, 90.0, np.float32), 5 + 7 * k], 1)]),
+        "two horizontal lines": np.concatenate([np.stack([5 + 7 * k, np.full(13, 40.0, np.float32)], 1),
+                                                np.stack([5 + 7 * k, np.full(13, 90.0, np.float32)], 1)]),
+        "L": np.concatenate([np.stack([np.full(9, 10.0, np.float32), 10 + 5 * k[:9]], 1),
+                             np.stack([15 + 5 * k[:9], np.full(9, 10.0, np.float32)], 1)]),
+        # 3-4-5 multiples: exactly cocircular lattice points around (100, 100), radius 25 and 50
+        "ring": np.array([[100 + s * a, 100 + t * b] for r in (1, 2) for a, b in ((15, 20), (20, 15), (7, 24), (24, 7), (0, 25), (25, 0))
+                          for s in (r, -r) for t in (r, -r)], np.float32),
+    }
+    for name, pts in shapes.items():
+        pts = np.unique(pts, axis=0)
+        pts = pts[rng.permutation(len(pts))]
+        tris, edges = _lib.delaunay(pts)
+        area2, eset, sides = _check(pts, tris, edges)
+        q = _q(pts).astype(np.float64)
+        if "line" in name and "two" not in name:
+            assert len(tris) == 0 and len(edges) == len(pts) - 1, name
+        else:
+            assert area2 == int(round(2 * ConvexHull(q).volume)), name
+            assert eset == set(sides), name
+    for n in range(2, 41):
+        for rep in range(6):
+            pts = rng.uniform(0, 300, (n, 2)).astype(np.float32)
+            if rep % 2:
+                pts = np.rint(pts / 16) * 16 + 3      # coarse lattice: many collinear / cocircular subsets
+                pts = np.unique(pts, axis=0).astype(np.float32)
+                if len(pts) < 2:
+                    continue
+            tris, edges = _lib.delaunay(pts)
+            area2, eset, sides = _check(pts, tris, edges)
+            q = _q(pts).astype(np.float64)
+            if len(pts) >= 3 and np.linalg.matrix_rank(q[1:] - q[0]) == 2:
+                assert area2 == int(round(2 * ConvexHull(q).volume)), (n, rep)
+                assert eset == set(sides), (n, rep)
+            else:
+                assert len(tris) == 0 and len(edges) == len(pts) - 1, (n, rep)
