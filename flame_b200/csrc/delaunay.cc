@@ -231,7 +231,14 @@ extern "C" int flame_b200_delaunay(int32_t V, const float* pos, int32_t tri_capa
   }
   *n_tris = 0;
   *n_edges = 0;
-  std::vector<int32_t> px(V), py(V), order(V);
+  // per-thread scratch, kept across calls: a frame pipeline triangulates every frame on several host threads, and
+  // allocating / page-faulting ~3 MB per call serialises them on the process' memory map
+  static thread_local std::vector<int32_t> px, py, order;
+  static thread_local std::vector<uint64_t> keys;
+  static thread_local Mesh m;
+  px.resize(V);
+  py.resize(V);
+  order.resize(V);
   for (int32_t v = 0; v < V; ++v) {
     const float x = pos[2 * v], y = pos[2 * v + 1];
     if (!(std::fabs(x) < 8192.0f) || !(std::fabs(y) < 8192.0f)) {
@@ -245,7 +252,7 @@ extern "C" int flame_b200_delaunay(int32_t V, const float* pos, int32_t tri_capa
   {  // sort by (x, y, id): one packed 64-bit key per vertex (x, y biased to unsigned 22 bits, id 20 bits) when
      // the ids fit, else the comparison sort
     if (V < (1 << 20)) {
-      std::vector<uint64_t> keys(V);
+      keys.resize(V);
       for (int32_t v = 0; v < V; ++v)
         keys[v] = ((uint64_t)(uint32_t)(px[v] + (1 << 21)) << 42) | ((uint64_t)(uint32_t)(py[v] + (1 << 21)) << 20) |
                   (uint64_t)v;
@@ -263,7 +270,8 @@ extern "C" int flame_b200_delaunay(int32_t V, const float* pos, int32_t tri_capa
   for (int32_t i = 0; i < V; ++i)
     if (n == 0 || px[order[i]] != px[order[n - 1]] || py[order[i]] != py[order[n - 1]]) order[n++] = order[i];
   if (n < 2) return 0;
-  Mesh m;
+  m.quads.clear();
+  m.dead.clear();
   m.px = px.data();
   m.py = py.data();
   m.quads.reserve((size_t)8 * n + 16);  // edges ever created (kept + deleted); ~6.8 n for uniform points
