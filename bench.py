@@ -564,8 +564,9 @@ def run_ours(args, rank, world, local_rank):
             line["e2e_incl_triangulation"] = {
                 "value": e2e_tri["value"], "unit": "frames/s", "host_threads": e2e_tri["threads"],
                 "delaunay_ms_per_frame": 1e-3 * e2e_tri["breakdown"]["per_frame_us"]["delaunay"],
-                "note": "every frame's Delaunay triangulation (10k vertices) computed by the submitting host thread "
-                        "with flame_b200_delaunay while earlier frames run on the GPU; host-core bound"}
+                "note": "every frame's Delaunay triangulation (10k vertices) computed inside "
+                        "flame_b200_process_frame_submit (no topology passed: flame_b200_delaunay on the submitting host "
+                        "thread) while earlier frames run on the GPU; host-core bound"}
         if search is not None:
             line["search"] = search
         if world == 1 and not args.no_cpu:
@@ -734,7 +735,6 @@ def run_e2e(args, local_rank, frames, dims, barrier, triangulate=False):
     vout = [tuple(np.empty(V, np.float32) for _ in range(3)) for _ in range(P)]
     per_step = args.e2e_batch if not triangulate else max(P * 8, 96)
     search = CFG == "C"
-    tri_s = [0.0] * P
     if search:
         from flame_b200 import synth
         si = _search_inputs()
@@ -756,10 +756,8 @@ def run_e2e(args, local_rank, frames, dims, barrier, triangulate=False):
                     acc += float(x[0]) + float(outs[k][slot].array[H // 2, W // 2])
                 g = frames[i % len(frames)]
                 tris_i, edges_i = g["tris"], g["edges"]
-                if triangulate:  # Delaunay of this frame's vertices on this host thread, while earlier frames run
-                    t_tri = time.perf_counter()
-                    tris_i, edges_i = _lib.delaunay(g["pos"])
-                    tri_s[k] += time.perf_counter() - t_tri
+                if triangulate:  # no topology passed: process_frame_submit triangulates this frame's vertices itself,
+                    tris_i = edges_i = None  # on this host thread, while the frames submitted before run on the GPU
                 if search:  # host feature records in and out (5 000 x 40 B each way), synchronous
                     f = si["feats"].copy()
                     ctx.update_feature_idepths(tp, 1, 0, f, want_diag=False)
@@ -809,7 +807,7 @@ def run_e2e(args, local_rank, frames, dims, barrier, triangulate=False):
         for o in row:
             o.free()
     if triangulate:
-        breakdown["per_frame_us"]["delaunay"] = 1e6 * sum(tri_s) / max(1, per_step * (args.steps + 1))
+        breakdown["per_frame_us"]["delaunay"] = 1e6 * tot("triangulation_seconds") / nfr
     return {"seconds": dt, "frames": per_step * args.steps, "h2d": h2d, "d2h": d2h,
             "per_step": per_step, "threads": P, "in_flight": P * R, "breakdown": breakdown}
 

@@ -32,7 +32,8 @@ class Stats(C.Structure):
     """flame_b200_stats: host-side accounting of the frame pipeline."""
     _fields_ = [("frames", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("prep_seconds", C.c_double), ("stage_seconds", C.c_double),
-                ("enqueue_seconds", C.c_double), ("wait_seconds", C.c_double)]
+                ("enqueue_seconds", C.c_double), ("wait_seconds", C.c_double),
+                ("triangulation_seconds", C.c_double)]
 
 
 class ProjectRules(C.Structure):
@@ -126,7 +127,8 @@ SYMBOLS = [
     "flame_b200_mesh_project", "flame_b200_mesh_download", "flame_b200_process_frame",
     "flame_b200_delaunay", "flame_b200_slot_device_ptrs", "flame_b200_mesh_redirect", "flame_b200_device_alloc",
     "flame_b200_device_free", "flame_b200_ipc_export", "flame_b200_ipc_open", "flame_b200_ipc_close",
-    "flame_b200_process_frame_submit", "flame_b200_process_frame_wait", "flame_b200_ctx_stats",
+    "flame_b200_process_frame_submit", "flame_b200_process_frame_wait", "flame_b200_process_frame_topology",
+    "flame_b200_ctx_stats",
     "flame_b200_tri_filter_default_params", "flame_b200_mesh_filter", "flame_b200_mesh_coverage",
     "flame_b200_mesh_normals", "flame_b200_mesh_filter_angles",
     "flame_b200_track_default_params",
@@ -202,6 +204,8 @@ def lib():
                                                   C.c_int32, i32p, C.c_int, C.c_int, C.POINTER(PDParams), C.c_int,
                                                   C.c_float, vp]
     L.flame_b200_process_frame_wait.argtypes = [vp, C.c_int, f32p, f32p, f32p]
+    L.flame_b200_process_frame_topology.argtypes = [vp, C.c_int, C.c_int32, C.POINTER(C.c_int32), i32p, C.c_int32,
+                                                    C.POINTER(C.c_int32), i32p]
     L.flame_b200_ctx_stats.argtypes = [vp, C.POINTER(Stats), C.c_int]
     L.flame_b200_track_default_params.argtypes = [C.POINTER(TrackParams)]
     L.flame_b200_track_default_params.restype = None
@@ -561,11 +565,23 @@ class Context:
     def process_frame_submit(self, slot, pos, idepth, edges, tris, rows, cols, params, n_iters, out_map,
                              weight=None, scale=1.0):
         """Enqueue a whole frame on the slot's own stream; inputs are consumed on return, out_map (pinned)
-        is written asynchronously and is valid after process_frame_wait(slot)."""
+        is written asynchronously and is valid after process_frame_wait(slot). edges = tris = None: the call
+        triangulates the vertices itself (process_frame_topology returns the arrays)."""
         check(lib().flame_b200_process_frame_submit(
-            self._h, slot, pos.shape[0], fptr(pos), fptr(idepth), fptr(weight), edges.shape[0], iptr(edges),
-            tris.shape[0], iptr(tris), rows, cols, C.byref(params), n_iters, scale,
+            self._h, slot, pos.shape[0], fptr(pos), fptr(idepth), fptr(weight),
+            edges.shape[0] if edges is not None else 0, iptr(edges),
+            tris.shape[0] if tris is not None else 0, iptr(tris), rows, cols, C.byref(params), n_iters, scale,
             out_map.ctypes.data_as(C.c_void_p) if out_map is not None else None))
+
+    def process_frame_topology(self, slot):
+        """(tris [T,3], edges [E,2]) the slot's last self-triangulating process_frame_submit used."""
+        nt, ne = C.c_int32(), C.c_int32()
+        check(lib().flame_b200_process_frame_topology(self._h, slot, 0, C.byref(nt), None, 0, C.byref(ne), None))
+        tris = np.empty((nt.value, 3), np.int32)
+        edges = np.empty((ne.value, 2), np.int32)
+        check(lib().flame_b200_process_frame_topology(self._h, slot, nt.value, C.byref(nt), iptr(tris), ne.value,
+                                                      C.byref(ne), iptr(edges)))
+        return tris, edges
 
     def process_frame_wait(self, slot, out_x=None, out_w1=None, out_w2=None):
         check(lib().flame_b200_process_frame_wait(self._h, slot, fptr(out_x), fptr(out_w1), fptr(out_w2)))

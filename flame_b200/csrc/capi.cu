@@ -53,6 +53,8 @@ struct Slot {
   cudaEvent_t blob_free = nullptr;  // recorded after the last async op that reads/writes h_blob
   size_t stage_extra = 0;           // bytes the next graph upload reserves behind its own staging image
   size_t stage_used = 0;            // end of the last graph upload's staging image inside h_blob
+  std::vector<int32_t> h_tris, h_edges;  // topology computed by process_frame_submit itself (flame_b200_delaunay)
+  int32_t h_nt = -1, h_ne = -1;
   // asynchronous whole-frame pipeline (flame_b200_process_frame_submit / _wait)
   cudaStream_t stream = nullptr;    // the slot's own stream: frames in different slots overlap
   cudaEvent_t done = nullptr;       // recorded after the frame's last device->host copy
@@ -127,7 +129,7 @@ struct flame_b200_ctx {
   int cap_cluster = 0, cap_variant = -1, cap_frames = 1;  // cached pd_resident_capacity of the last plan
   size_t cap_smem = 0;
   // host-side accounting of the frame pipeline (flame_b200_ctx_stats)
-  double t_prep = 0, t_stage = 0, t_enqueue = 0, t_wait = 0;
+  double t_prep = 0, t_stage = 0, t_enqueue = 0, t_wait = 0, t_tri = 0;
   uint64_t n_frames = 0, h2d_bytes = 0, d2h_bytes = 0;
 };
 
@@ -1630,6 +1632,26 @@ int flame_b200_process_frame_submit(flame_b200_ctx* c, int slot, int32_t V, cons
     set_error("process_frame_submit: bad arguments");
     return FLAME_B200_EINVAL;
   }
+  if (!edges && !tris && V > 0) {
+    // no topology given: triangulate the vertices here, on the calling thread (utils/delaunay.cc:31-77's place in
+    // Flame::update) - the device keeps working on the frames submitted before. The arrays stay with the slot
+    // (flame_b200_process_frame_topology).
+    const double tt = now_s();
+    s.h_tris.resize((size_t)6 * V + 3);
+    s.h_edges.resize((size_t)6 * V + 2);
+    int32_t nt = 0, ne = 0;
+    if (int rc = flame_b200_delaunay(V, pos, 2 * V + 1, &nt, s.h_tris.data(), 3 * V + 1, &ne, s.h_edges.data()))
+      return rc;
+    s.h_nt = nt;
+    s.h_ne = ne;
+    T = nt;
+    E = ne;
+    tris = s.h_tris.data();
+    edges = s.h_edges.data();
+    c->t_tri += now_s() - tt;
+  } else {
+    s.h_nt = s.h_ne = -1;
+  }
   if (!s.stream) FB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
   if (!s.done) FB_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
   if (!s.uploaded) FB_CUDA(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
@@ -1717,6 +1739,29 @@ int flame_b200_process_frame(flame_b200_ctx* c, int slot, int32_t V, const float
   return flame_b200_process_frame_wait(c, slot, out_x, out_w1, out_w2);
 }
 
+int flame_b200_process_frame_topology(flame_b200_ctx* c, int slot, int32_t tri_capacity, int32_t* n_tris,
+                                      int32_t* tris, int32_t edge_capacity, int32_t* n_edges, int32_t* edges) {
+  if (int rc = check_slot(c, slot)) return rc;
+  const Slot& s = c->slots[slot];
+  if (!n_tris || !n_edges || tri_capacity < 0 || edge_capacity < 0) {
+    set_error("process_frame_topology: bad arguments");
+    return FLAME_B200_EINVAL;
+  }
+  if (s.h_nt < 0) {
+    set_error("process_frame_topology: the slot's last frame was submitted with the caller's own triangulation");
+    return FLAME_B200_ESTATE;
+  }
+  *n_tris = s.h_nt;
+  *n_edges = s.h_ne;
+  if ((tris && s.h_nt > tri_capacity) || (edges && s.h_ne > edge_capacity)) {
+    set_error("process_frame_topology: output capacity too small");
+    return FLAME_B200_ENOMEM;
+  }
+  if (tris) std::memcpy(tris, s.h_tris.data(), (size_t)3 * s.h_nt * sizeof(int32_t));
+  if (edges) std::memcpy(edges, s.h_edges.data(), (size_t)2 * s.h_ne * sizeof(int32_t));
+  return 0;
+}
+
 int flame_b200_ctx_stats(flame_b200_ctx* c, flame_b200_stats* out, int reset) {
   if (!c || !out) return FLAME_B200_EINVAL;
   out->frames = c->n_frames;
@@ -1726,9 +1771,10 @@ int flame_b200_ctx_stats(flame_b200_ctx* c, flame_b200_stats* out, int reset) {
   out->stage_seconds = c->t_stage;
   out->enqueue_seconds = c->t_enqueue;
   out->wait_seconds = c->t_wait;
+  out->triangulation_seconds = c->t_tri;
   if (reset) {
     c->n_frames = c->h2d_bytes = c->d2h_bytes = 0;
-    c->t_prep = c->t_stage = c->t_enqueue = c->t_wait = 0;
+    c->t_prep = c->t_stage = c->t_enqueue = c->t_wait = c->t_tri = 0;
   }
   return 0;
 }

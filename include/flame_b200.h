@@ -348,6 +348,13 @@ int flame_b200_process_frame_submit(flame_b200_ctx* ctx, int slot, int32_t V, co
                                     const flame_b200_pd_params* params, int n_iters, float scale,
                                     float* out_map);
 int flame_b200_process_frame_wait(flame_b200_ctx* ctx, int slot, float* out_x, float* out_w1, float* out_w2);
+/* edges == NULL and tris == NULL in flame_b200_process_frame_submit: the call triangulates the vertices itself
+ * (flame_b200_delaunay below, on the calling thread, while the device works on the frames submitted before) -
+ * the place utils::Delaunay::triangulate has in Flame::update (flame.cc:312-330). E and T are ignored. The
+ * arrays it used stay with the slot until its next submit; this returns them (counts always; tris / edges may
+ * be NULL; FLAME_B200_ENOMEM if a capacity is too small, 2V + 1 triangles and 3V + 1 edges always suffice). */
+int flame_b200_process_frame_topology(flame_b200_ctx* ctx, int slot, int32_t tri_capacity, int32_t* n_tris,
+                                      int32_t* tris, int32_t edge_capacity, int32_t* n_edges, int32_t* edges);
 
 /* Host-side accounting of the frame pipeline since context creation / the last reset: where the calling
  * thread's time went (vertex ordering + launch plan, staging copies, enqueueing, waiting) and the bytes
@@ -358,6 +365,7 @@ typedef struct {
   double stage_seconds;   /* process_frame_submit up to the solver launch: prep + staging memcpys + upload calls */
   double enqueue_seconds; /* solver / projection / download launches                               */
   double wait_seconds;    /* blocked in process_frame_wait                                         */
+  double triangulation_seconds; /* flame_b200_delaunay inside process_frame_submit (edges == tris == NULL) */
 } flame_b200_stats;
 int flame_b200_ctx_stats(flame_b200_ctx* ctx, flame_b200_stats* out, int reset);
 

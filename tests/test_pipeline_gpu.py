@@ -100,3 +100,38 @@ def test_pipeline_errors_and_mixed_use(oracle):
         ctx.sync()
         out.free()
         out2.free()
+
+
+def test_pipeline_triangulates_when_no_topology_is_passed(oracle):
+    """edges = tris = None: process_frame_submit triangulates the vertices itself (flame_b200_delaunay); the
+    result equals the oracle run on the arrays process_frame_topology hands back, and those arrays are what
+    flame_b200_delaunay returns for the same points."""
+    iters = 12
+    H, W = 480, 640
+    p = _lib.default_pd_params()
+    graphs = [synth.make_graph(W, H, 250 + 70 * i, seed=900 + i, noise_seed=950 + i, triangulator="scipy")
+              for i in range(3)]
+    with _lib.Context(0, 4) as ctx:
+        outs = [_lib.PinnedArray((H, W)) for _ in range(3)]
+        for i, g in enumerate(graphs):
+            ctx.process_frame_submit(i, g["pos"], g["data_term"], None, None, H, W, p, iters, outs[i].array)
+        for i, g in enumerate(graphs):
+            V = g["pos"].shape[0]
+            x, w1, w2 = (np.empty(V, np.float32) for _ in range(3))
+            ctx.process_frame_wait(i, x, w1, w2)
+            tris, edges = ctx.process_frame_topology(i)
+            t2, e2 = _lib.delaunay(g["pos"])
+            assert np.array_equal(tris, t2) and np.array_equal(edges, e2)
+            g2 = dict(g, tris=tris, edges=edges)
+            s, img = _want(oracle, g2, iters)
+            assert np.array_equal(x.view(np.uint32), s["x"].view(np.uint32))
+            assert np.array_equal(w1.view(np.uint32), s["w1"].view(np.uint32))
+            assert _same_img(outs[i].array, img)
+        # a slot whose frame came with the caller's arrays has no topology to hand back
+        g = graphs[0]
+        ctx.process_frame_submit(3, g["pos"], g["data_term"], g["edges"], g["tris"], H, W, p, iters, None)
+        ctx.process_frame_wait(3)
+        with pytest.raises(_lib.FlameB200Error):
+            ctx.process_frame_topology(3)
+        for o in outs:
+            o.free()
