@@ -193,45 +193,84 @@ __global__ void k_layout_finish(GraphDev g, const float* __restrict__ raw, int a
   const int base = g.chunk_base[ch] + i;
   const int* __restrict__ koff = koff_row(g, ch);
   const int d = g.deg[v];
-  // insertion sort of the claimed keys (typical degree 6), in place: element k lives at base + koff[k]
-  for (int k = 1; k < d; ++k) {
-    const int key = g.inc_edge[base + koff[k]];
-    int j = k - 1;
-    while (j >= 0) {
-      const int kj = g.inc_edge[base + koff[j]];
-      if (kj <= key) break;
-      g.inc_edge[base + koff[j + 1]] = kj;
-      --j;
+  // sort the claimed keys (typical degree 6); element k lives at base + koff[k]. Up to 24 keys are fetched with
+  // independent loads and insertion-sorted in a thread-local array (one global round trip instead of one per
+  // comparison); hubs sort in place in global memory.
+  constexpr int LOCAL_KEYS = 24;
+  if (d <= LOCAL_KEYS) {
+    int keys[LOCAL_KEYS];
+#pragma unroll
+    for (int k = 0; k < LOCAL_KEYS; ++k) keys[k] = k < d ? g.inc_edge[base + koff[k]] : 0x7fffffff;
+    for (int k = 1; k < d; ++k) {
+      const int key = keys[k];
+      int j = k - 1;
+      while (j >= 0 && keys[j] > key) {
+        keys[j + 1] = keys[j];
+        --j;
+      }
+      keys[j + 1] = key;
     }
-    g.inc_edge[base + koff[j + 1]] = key;
+    for (int k = 0; k < d; ++k) g.inc_edge[base + koff[k]] = keys[k];
+  } else {
+    for (int k = 1; k < d; ++k) {
+      const int key = g.inc_edge[base + koff[k]];
+      int j = k - 1;
+      while (j >= 0) {
+        const int kj = g.inc_edge[base + koff[j]];
+        if (kj <= key) break;
+        g.inc_edge[base + koff[j + 1]] = kj;
+        --j;
+      }
+      g.inc_edge[base + koff[j + 1]] = key;
+    }
   }
   const float* eb = raw + 13 * (size_t)V;
-  for (int k = 0; k < d; ++k) {
-    const int slot = base + koff[k];
-    const int key = g.inc_edge[slot];
-    const int o = key >> 1, role = key & 1;
-    const int os = g.edges[2 * o], od = g.edges[2 * o + 1];
-    const float dx = sub(raw[2 * os], raw[2 * od]);          // pos_i.x - pos_j.x (cc:100)
-    const float dy = sub(raw[2 * os + 1], raw[2 * od + 1]);
-    float alpha;
-    if (alpha_on_device) {
-      // flame.cc:2089-2092, 2102: alpha = 1 / sqrt(dx*dx + dy*dy)
-      const float len = __fsqrt_rn(add(mul(dx, dx), mul(dy, dy)));
-      alpha = __fdiv_rn(1.0f, len);
-    } else {
-      alpha = eb[0 * E + o];
+  // eight incidences at a time, staged (keys -> endpoints -> positions / neighbour index -> records) so that the
+  // dependent global loads of a stage are all in flight together
+  for (int k0 = 0; k0 < d; k0 += 8) {
+    int slot[8], o[8], os[8], od[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      slot[u] = base + koff[min(k0 + u, d - 1)];
+      o[u] = g.inc_edge[slot[u]];
     }
-    const int ent = (g.vinv[role ? os : od] << 1) | role;  // (neighbour internal index << 1) | is_target
-    if (fresh) {
-      g.inc_s[slot] = make_float4(alpha, 1.0f, dx, dy);
-      g.inc_q[slot] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(ent));
-    } else {
-      g.inc_s[slot] = make_float4(alpha, eb[1 * E + o], dx, dy);
-      g.inc_q[slot] = make_float4(eb[2 * E + o], eb[3 * E + o], eb[4 * E + o], __int_as_float(ent));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      os[u] = g.edges[2 * (o[u] >> 1)];
+      od[u] = g.edges[2 * (o[u] >> 1) + 1];
     }
-    g.inc_nbr[slot] = ent;
-    g.inc_edge[slot] = o;
-    g.edge_slot[2 * o + role] = slot;  // inverse map: (edge, role) -> incidence slot
+    float dx[8], dy[8];
+    int ent[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      dx[u] = sub(raw[2 * os[u]], raw[2 * od[u]]);          // pos_i.x - pos_j.x (cc:100)
+      dy[u] = sub(raw[2 * os[u] + 1], raw[2 * od[u] + 1]);
+      const int role = o[u] & 1;
+      ent[u] = (g.vinv[role ? os[u] : od[u]] << 1) | role;  // (neighbour internal index << 1) | is_target
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (k0 + u >= d) break;
+      const int e = o[u] >> 1, role = o[u] & 1;
+      float alpha;
+      if (alpha_on_device) {
+        // flame.cc:2089-2092, 2102: alpha = 1 / sqrt(dx*dx + dy*dy)
+        const float len = __fsqrt_rn(add(mul(dx[u], dx[u]), mul(dy[u], dy[u])));
+        alpha = __fdiv_rn(1.0f, len);
+      } else {
+        alpha = eb[0 * E + e];
+      }
+      if (fresh) {
+        g.inc_s[slot[u]] = make_float4(alpha, 1.0f, dx[u], dy[u]);
+        g.inc_q[slot[u]] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(ent[u]));
+      } else {
+        g.inc_s[slot[u]] = make_float4(alpha, eb[1 * E + e], dx[u], dy[u]);
+        g.inc_q[slot[u]] = make_float4(eb[2 * E + e], eb[3 * E + e], eb[4 * E + e], __int_as_float(ent[u]));
+      }
+      g.inc_nbr[slot[u]] = ent[u];
+      g.inc_edge[slot[u]] = e;
+      g.edge_slot[2 * e + role] = slot[u];  // inverse map: (edge, role) -> incidence slot
+    }
   }
 }
 
