@@ -7,7 +7,7 @@ import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["FLAME_B200_CLUSTER"] = sys.argv[1] if len(sys.argv) > 1 else "9"
-import numpy as np, torch
+import torch  # noqa: F401 (loads the CUDA runtime the library links against)
 from flame_b200 import _lib, synth
 ctx = _lib.Context(0, 15)
 for i in range(15):

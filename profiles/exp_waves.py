@@ -5,7 +5,6 @@ the dense projection hides behind the PD solver when two contexts (streams) alte
 """
 import os
 import sys
-import time
 
 import numpy as np
 
