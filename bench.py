@@ -829,7 +829,11 @@ def main():
                     help="device-resident leg: the cluster size that keeps most SMs busy (9 CTAs per frame, 15 frames "
                          "per wave on 135 SMs; the low-priority projection stream fills the rest and the gaps) or "
                          "frame clusters of 16 CTAs (7 frames per wave, lower latency per frame)")
-    ap.add_argument("--pipelines", type=int, default=3, help="host threads (one context each) of the e2e leg")
+    ap.add_argument("--pipelines", type=int, default=0,
+                    help="host threads (one context each) of the e2e leg (0 = 3; 4 at three or more ranks if every rank "
+                         "has at least 6 usable CPUs: the per-frame host work - vertex order, launch plan, staging - slows "
+                         "down with the box's DMA load, and at 4 ranks three threads per rank were measured host-bound, "
+                         "profiles/r2_bench_n4_final.json; at one rank a fourth thread only adds contention)")
     ap.add_argument("--ring", type=int, default=30, help="frame slots per e2e host thread (two 15-frame waves)")
     ap.add_argument("--e2e-batch", type=int, default=480, help="frames per GPU per step of the e2e leg")
     ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 stream, 2 resident")
@@ -845,6 +849,8 @@ def main():
     CFG = args.config
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.pipelines <= 0:
+        args.pipelines = 4 if (world >= 3 and _usable_cpus() // world >= 6) else 3
     if args.tri_threads <= 0:
         args.tri_threads = max(2, min(12, _usable_cpus() // max(1, world) - 2))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
