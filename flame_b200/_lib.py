@@ -36,6 +36,13 @@ class Stats(C.Structure):
                 ("triangulation_seconds", C.c_double)]
 
 
+class GraphLayout(C.Structure):
+    """flame_b200_graph_layout: what flame_b200_graph_plan reports."""
+    _fields_ = [("chunk_width", C.c_int32), ("n_chunks", C.c_int32), ("max_degree", C.c_int32),
+                ("cluster", C.c_int32), ("variant", C.c_int32), ("threads", C.c_int32),
+                ("max_incidences", C.c_int32), ("max_owned_edges", C.c_int32), ("shared_bytes", C.c_int64)]
+
+
 class ProjectRules(C.Structure):
     """flame_b200_project_rules: the flame::Params fields Flame::projectGraph reads."""
     _fields_ = [("rescale_factor_max", C.c_float), ("win_size", C.c_int32), ("do_letterbox", C.c_int32),
@@ -128,7 +135,7 @@ SYMBOLS = [
     "flame_b200_delaunay", "flame_b200_slot_device_ptrs", "flame_b200_mesh_redirect", "flame_b200_device_alloc",
     "flame_b200_device_free", "flame_b200_ipc_export", "flame_b200_ipc_open", "flame_b200_ipc_close",
     "flame_b200_process_frame_submit", "flame_b200_process_frame_wait", "flame_b200_process_frame_topology",
-    "flame_b200_ctx_stats",
+    "flame_b200_ctx_stats", "flame_b200_graph_plan",
     "flame_b200_tri_filter_default_params", "flame_b200_mesh_filter", "flame_b200_mesh_coverage",
     "flame_b200_mesh_normals", "flame_b200_mesh_filter_angles",
     "flame_b200_track_default_params",
@@ -207,6 +214,8 @@ def lib():
     L.flame_b200_process_frame_topology.argtypes = [vp, C.c_int, C.c_int32, C.POINTER(C.c_int32), i32p, C.c_int32,
                                                     C.POINTER(C.c_int32), i32p]
     L.flame_b200_ctx_stats.argtypes = [vp, C.POINTER(Stats), C.c_int]
+    L.flame_b200_graph_plan.argtypes = [C.c_int32, f32p, C.c_int32, i32p, C.c_int, i32p, C.POINTER(GraphLayout),
+                                        i32p, C.c_int32, i32p, i32p]
     L.flame_b200_track_default_params.argtypes = [C.POINTER(TrackParams)]
     L.flame_b200_track_default_params.restype = None
     L.flame_b200_set_camera.argtypes = [vp, C.c_int, C.c_int, f32p, f32p]
@@ -258,6 +267,27 @@ def delaunay(pos):
     check(lib().flame_b200_delaunay(V, fptr(pos), tris.shape[0], C.byref(nt), iptr(tris), edges.shape[0],
                                     C.byref(ne), iptr(edges)))
     return tris[:nt.value].copy(), edges[:ne.value].copy()
+
+
+# SMs kept busy by clusters of C CTAs on a B200 (GPCs of 20/20/20/20/18/18/18/14 SMs, one CTA per SM)
+B200_BUSY_SMS = np.array([0] + [C_ * sum(n // C_ for n in (20, 20, 20, 20, 18, 18, 18, 14)) for C_ in range(1, 17)],
+                         np.int32)
+
+
+def graph_plan(pos, edges, preference=0, busy_sms=B200_BUSY_SMS):
+    """flame_b200_graph_plan (host only): (layout dict, vperm, koff [n_chunks, max_degree + 1], chunk_base)."""
+    pos = np.ascontiguousarray(pos, np.float32)
+    edges = np.ascontiguousarray(edges, np.int32)
+    lay = GraphLayout()
+    bs = None if busy_sms is None else np.ascontiguousarray(busy_sms, np.int32)
+    check(lib().flame_b200_graph_plan(pos.shape[0], fptr(pos), edges.shape[0], iptr(edges), preference, iptr(bs),
+                                      C.byref(lay), None, 0, None, None))
+    vperm = np.empty(pos.shape[0], np.int32)
+    koff = np.empty((lay.n_chunks, lay.max_degree + 1), np.int32)
+    chunk_base = np.empty(lay.n_chunks + 1, np.int32)
+    check(lib().flame_b200_graph_plan(pos.shape[0], fptr(pos), edges.shape[0], iptr(edges), preference, iptr(bs),
+                                      C.byref(lay), iptr(vperm), koff.size, iptr(koff), iptr(chunk_base)))
+    return {k: getattr(lay, k) for k, _ in GraphLayout._fields_}, vperm, koff, chunk_base
 
 
 def default_pd_params():

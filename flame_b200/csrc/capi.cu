@@ -115,7 +115,8 @@ struct flame_b200_ctx {
   std::vector<cudaEvent_t> ev_pool;
   // host scratch for graph prep
   std::vector<uint32_t> keys;
-  std::vector<int> degv, srcdeg, order, koff_tmp, pre_deg, pre_src, sort_tmp;
+  std::vector<int> order, koff_tmp, pre_deg, pre_src, sort_tmp;
+  std::vector<uint64_t> degw, degm;  // per vertex (degree | owned edges << 32): caller order, Z-curve order
   int own_cnt[FB_RESIDENT_MAX_DEG + 2];
   int pd_pref = 0;                   // FLAME_B200_PREF_*: how prep_plan sizes the frame clusters
   int busy_sms[17] = {0};            // [C] = C x clusters of C CTAs the device keeps resident (full shared memory)
@@ -168,20 +169,20 @@ static size_t blob_bytes(int V, int E, int n_chunks, int max_deg) {
 //  2. cluster size C / chunk width Vc from the shared-memory footprint (0 -> streaming chunks).
 static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const int32_t* edges,
                      PrepOut* out) {
-  c->degv.assign(V, 0);
-  c->srcdeg.assign(V, 0);
+  // per vertex: degree in the low half, owned (source-role) edges in the high half of one 64-bit word
+  c->degw.assign(V, 0);
+  uint64_t* const dg = c->degw.data();
   for (int e = 0; e < E; ++e) {
     const int s = edges[2 * e], d = edges[2 * e + 1];
     if ((unsigned)s >= (unsigned)V || (unsigned)d >= (unsigned)V) {
       set_error("graph_upload: edge endpoint out of range");
       return FLAME_B200_EINVAL;
     }
-    c->degv[s]++;
-    c->degv[d]++;
-    c->srcdeg[s]++;
+    dg[s] += 0x100000001ull;
+    dg[d] += 1;
   }
   int max_deg = 0;
-  for (int v = 0; v < V; ++v) max_deg = std::max(max_deg, c->degv[v]);
+  for (int v = 0; v < V; ++v) max_deg = std::max(max_deg, (int)(uint32_t)dg[v]);
 
   // 1. Z-curve order at cell granularity: a 64 x 64 grid over the bounding box, one stable counting sort by
   //    the Morton code of the cell (vertices of a cell keep their input order)
@@ -214,13 +215,23 @@ static int prep_plan(flame_b200_ctx* c, int V, int E, const float* pos, const in
   for (int v = 0; v < V; ++v) c->order[cnt[c->keys[v]]++] = v;
   const int* morton = c->order.data();  // morton[i] = caller vertex at Z-curve position i
 
-  // 2. plan: per-chunk incidence / owned-edge counts from prefix sums over the Morton order
+  // 2. plan: per-chunk incidence / owned-edge counts from prefix sums over the Morton order. The packed counts
+  //    are gathered into Z-curve order once (c->degm, reused by prep_fill): everything after is sequential.
+  c->degm.resize(V);
   c->pre_deg.resize(V + 1);
   c->pre_src.resize(V + 1);
   c->pre_deg[0] = c->pre_src[0] = 0;
-  for (int i = 0; i < V; ++i) {
-    c->pre_deg[i + 1] = c->pre_deg[i] + c->degv[morton[i]];
-    c->pre_src[i + 1] = c->pre_src[i] + c->srcdeg[morton[i]];
+  {
+    uint64_t* const dm = c->degm.data();
+    int a_deg = 0, a_src = 0;
+    for (int i = 0; i < V; ++i) {
+      const uint64_t w = dg[morton[i]];
+      dm[i] = w;
+      a_deg += (int)(uint32_t)w;
+      a_src += (int)(w >> 32);
+      c->pre_deg[i + 1] = a_deg;
+      c->pre_src[i + 1] = a_src;
+    }
   }
   int forced = 0;
   if (const char* sv = getenv("FLAME_B200_CLUSTER")) forced = atoi(sv);
@@ -287,11 +298,12 @@ static void prep_fill(flame_b200_ctx* c, int V, int E, const int32_t* edges, con
   c->koff_tmp.assign(2 * (size_t)(max_deg + 2), 0);
   int* cnt = c->koff_tmp.data();         // cnt[d]   = #vertices of degree d in the chunk
   int* start = cnt + (max_deg + 2);      // start[d] = #vertices of degree > d (block start of d)
+  const uint64_t* const dm = c->degm.data();  // (degree | owned << 32) at every Z-curve position (prep_plan)
   chunk_base[0] = 0;
   for (int ch = 0; ch < n_chunks; ++ch) {
     const int a = ch * Vc, b = std::min(a + Vc, V);
     std::fill(cnt, cnt + max_deg + 2, 0);
-    for (int i = a; i < b; ++i) cnt[c->degv[morton[i]]]++;
+    for (int i = a; i < b; ++i) cnt[(uint32_t)dm[i]]++;
     int run = 0;
     for (int d = max_deg; d >= 0; --d) {
       start[d] = run;
@@ -307,31 +319,25 @@ static void prep_fill(flame_b200_ctx* c, int V, int E, const int32_t* edges, con
     chunk_base[ch + 1] = chunk_base[ch] + ko[max_deg];
     for (int d = 0; d <= max_deg; ++d) cnt[d] = start[d];  // write cursors
     if (!pr.plan.cluster) {
-      for (int i = a; i < b; ++i) {
-        const int o = morton[i];
-        vperm[a + cnt[c->degv[o]]++] = o;
-      }
+      for (int i = a; i < b; ++i) vperm[a + cnt[(uint32_t)dm[i]]++] = morton[i];
       continue;
     }
     // resident solver: secondary key = number of owned (source-role) edges, descending, so that the vertices
     // that have an r-th owned edge form a few contiguous runs (pd.cu deals the edges rank-major). Two stable
-    // counting sorts: by owned count first, by degree second.
+    // counting sorts: by owned count first (into positions of the chunk), by degree second.
     c->sort_tmp.resize(b - a);
     int* own_cnt = c->own_cnt;
-    std::fill(own_cnt, own_cnt + FB_RESIDENT_MAX_DEG + 2, 0);
-    for (int i = a; i < b; ++i) own_cnt[c->srcdeg[morton[i]]]++;
+    std::fill(own_cnt, own_cnt + max_deg + 2, 0);
+    for (int i = a; i < b; ++i) own_cnt[dm[i] >> 32]++;
     for (int d = max_deg, run2 = 0; d >= 0; --d) {
       const int n = own_cnt[d];
       own_cnt[d] = run2;
       run2 += n;
     }
-    for (int i = a; i < b; ++i) {
-      const int o = morton[i];
-      c->sort_tmp[own_cnt[c->srcdeg[o]]++] = o;
-    }
-    for (int i = 0; i < b - a; ++i) {
-      const int o = c->sort_tmp[i];
-      vperm[a + cnt[c->degv[o]]++] = o;
+    for (int i = a; i < b; ++i) c->sort_tmp[own_cnt[dm[i] >> 32]++] = i;
+    for (int j = 0; j < b - a; ++j) {
+      const int i = c->sort_tmp[j];
+      vperm[a + cnt[(uint32_t)dm[i]]++] = morton[i];
     }
   }
 }
@@ -1046,6 +1052,43 @@ int flame_b200_pd_run(flame_b200_ctx* c, int slot0, int n_slots, const flame_b20
     return pd_run_resident(c->stream, c->d_graphs + slot0, n_slots, plan, *params, n_iters);
   const int threads = (maxVc + 31) / 32 * 32;  // widest chunk; the kernel covers it with 128-thread CTAs
   return pd_run_stream(c->stream, c->d_graphs + slot0, n_slots, max_chunks, threads, *params, n_iters);
+}
+
+// Host-only: the vertex order and launch plan a graph upload would compute (no device, no context).
+int flame_b200_graph_plan(int32_t V, const float* pos, int32_t E, const int32_t* edges, int preference,
+                          const int32_t* busy_sms, flame_b200_graph_layout* out, int32_t* vperm,
+                          int32_t koff_capacity, int32_t* koff, int32_t* chunk_base) {
+  if (V < 0 || E < 0 || !out || (V > 0 && !pos) || (E > 0 && !edges)) {
+    set_error("graph_plan: bad arguments");
+    return FLAME_B200_EINVAL;
+  }
+  std::unique_ptr<flame_b200_ctx> c(new flame_b200_ctx());
+  c->pd_pref = preference;
+  for (int i = 0; i <= 16; ++i) c->busy_sms[i] = busy_sms ? busy_sms[i] : 0;
+  PrepOut prep;
+  if (int rc = prep_plan(c.get(), V, E, pos, edges, &prep)) return rc;
+  out->chunk_width = prep.Vc;
+  out->n_chunks = prep.n_chunks;
+  out->max_degree = prep.max_deg;
+  out->cluster = prep.plan.cluster;
+  out->variant = prep.plan.cluster ? prep.plan.variant : -1;
+  out->threads = prep.plan.threads;
+  out->max_incidences = prep.plan.maxInc;
+  out->max_owned_edges = prep.plan.maxEdges;
+  out->shared_bytes = (int64_t)prep.plan.smem_bytes;
+  if (!vperm && !koff && !chunk_base) return 0;
+  const size_t need = (size_t)prep.n_chunks * (prep.max_deg + 1);
+  if (koff && (size_t)koff_capacity < need) {
+    set_error("graph_plan: koff capacity too small (needs n_chunks * (max_degree + 1))");
+    return FLAME_B200_ENOMEM;
+  }
+  std::vector<int> ints(ints_uploaded(V, E, prep.n_chunks, prep.max_deg));
+  int *h_vperm, *h_koff, *h_chunk_base, *h_edges;
+  prep_fill(c.get(), V, E, edges, prep, ints.data(), &h_vperm, &h_koff, &h_chunk_base, &h_edges);
+  if (vperm && V > 0) std::memcpy(vperm, h_vperm, (size_t)V * sizeof(int));
+  if (koff && need) std::memcpy(koff, h_koff, need * sizeof(int));
+  if (chunk_base) std::memcpy(chunk_base, h_chunk_base, ((size_t)prep.n_chunks + 1) * sizeof(int));
+  return 0;
 }
 
 int flame_b200_pd_wave(flame_b200_ctx* c, int slot, int32_t* frames) {

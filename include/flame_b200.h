@@ -217,6 +217,24 @@ enum {
 int flame_b200_pd_run(flame_b200_ctx* ctx, int slot0, int n_slots,
                       const flame_b200_pd_params* params, int n_iters, int mode);
 
+/* Host-only diagnostic (no device, no context): the vertex order and launch plan that a graph upload computes
+ * for these vertices / edges - the only per-graph host computation of the library (everything else of the
+ * layout is built by kernels). busy_sms: optional table [17], entry C = SMs kept busy by clusters of C CTAs
+ * (what flame_b200_ctx_create measures with cudaOccupancyMaxActiveClusters; NULL = take the first size that
+ * fits). vperm [V]: caller vertex at every internal position (Z-curve chunks, each sorted by degree and owned-edge
+ * count); koff [n_chunks * (max_degree + 1)] and chunk_base [n_chunks + 1]: incidence k of the i-th vertex of
+ * chunk c lives at slot chunk_base[c] + koff[c][k] + i. Any of the three may be NULL. */
+typedef struct {
+  int32_t chunk_width, n_chunks, max_degree;
+  int32_t cluster;          /* CTAs per frame cluster of the resident solver; 0 = the streaming solver */
+  int32_t variant, threads; /* kernel build and block size */
+  int32_t max_incidences, max_owned_edges;
+  int64_t shared_bytes;     /* dynamic shared memory per CTA */
+} flame_b200_graph_layout;
+int flame_b200_graph_plan(int32_t V, const float* pos, int32_t E, const int32_t* edges, int preference,
+                          const int32_t* busy_sms, flame_b200_graph_layout* out, int32_t* vperm,
+                          int32_t koff_capacity, int32_t* koff, int32_t* chunk_base);
+
 /* Number of frames like the one in `slot` that the resident solver runs CONCURRENTLY: one frame is one
  * thread-block cluster, and the GPU holds a limited number of clusters at a time (7 of 16 CTAs on a
  * B200: cudaOccupancyMaxActiveClusters). pd_run over more slots proceeds in waves of this size; batches

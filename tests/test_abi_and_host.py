@@ -137,3 +137,43 @@ def test_sync_topology_bookkeeping():
     assert np.array_equal(s["w1"][:nk], old["w1"][keep]) and (s["w1"][nk:] == 0).all()
     assert np.array_equal(s["x"][nk:], data[nk:]) and np.array_equal(s["x_prev"][nk:], data[nk:])
     assert np.array_equal(s["q2"][carried], old["q2"][edge_from[carried]]) and (s["q2"][~carried] == 0).all()
+
+
+def test_graph_plan_vertex_order_and_launch_plan():
+    """flame_b200_graph_plan (host only): the vertex order is a permutation, cut into Z-curve chunks that are sorted
+    by (degree, owned edges) descending; koff / chunk_base address exactly the incidences that exist; and the
+    launch plan of a config-D graph on a B200's cluster-occupancy table is the one DESIGN.md quotes."""
+    from flame_b200 import _lib, synth
+    rng = np.random.default_rng(8)
+    graphs = [(synth.config_graph(c)["pos"], synth.config_graph(c)["edges"]) for c in ("A", "D")]
+    V = 3000
+    e = rng.integers(0, V, (3 * V, 2)).astype(np.int32)
+    graphs.append((rng.uniform(0, 800, (V, 2)).astype(np.float32), np.ascontiguousarray(e[e[:, 0] != e[:, 1]])))
+    for pos, edges in graphs:
+        for pref in (_lib.PREF_THROUGHPUT, _lib.PREF_LATENCY):
+            lay, vperm, koff, chunk_base = _lib.graph_plan(pos, edges, pref)
+            V, E = pos.shape[0], edges.shape[0]
+            deg = np.bincount(edges.ravel(), minlength=V)
+            own = np.bincount(edges[:, 0], minlength=V)
+            assert sorted(vperm.tolist()) == list(range(V))
+            assert lay["max_degree"] == deg.max() and lay["n_chunks"] == -(-V // lay["chunk_width"])
+            assert chunk_base[0] == 0 and chunk_base[-1] == 2 * E
+            for c in range(lay["n_chunks"]):
+                ids = vperm[c * lay["chunk_width"]:(c + 1) * lay["chunk_width"]]
+                d, o = deg[ids], own[ids]
+                assert np.all(np.diff(d) <= 0)                      # degree descending
+                assert np.all((np.diff(o) <= 0) | (np.diff(d) < 0))  # owned count descending inside a degree class
+                # incidence k exists for the first #(deg > k) vertices of the chunk; the blocks are packed
+                starts = np.array([(d > k).sum() for k in range(lay["max_degree"] + 1)])
+                assert np.array_equal(koff[c], np.concatenate([[0], np.cumsum(starts)[:-1]]))
+                assert chunk_base[c + 1] - chunk_base[c] == d.sum()
+            if lay["cluster"]:
+                assert lay["max_incidences"] == np.diff(chunk_base).max()
+                assert lay["shared_bytes"] <= 227 * 1024
+    lay, _, _, _ = _lib.graph_plan(*graphs[1][:2], _lib.PREF_THROUGHPUT)
+    assert (lay["cluster"], lay["variant"], lay["threads"]) == (9, 1, 576)
+    lay, _, _, _ = _lib.graph_plan(*graphs[1][:2], _lib.PREF_LATENCY)
+    assert (lay["cluster"], lay["variant"], lay["threads"]) == (16, 0, 640)
+    # edges are validated before anything else
+    with pytest.raises(_lib.FlameB200Error):
+        _lib.graph_plan(graphs[0][0], np.array([[0, 10 ** 6]], np.int32))
